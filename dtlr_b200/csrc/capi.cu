@@ -1,0 +1,16 @@
+// dtlr_b200 -- library identification and per-thread error string of the C ABI (include/dtlr_b200.h)
+#include "common.cuh"
+
+namespace dtlr {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace dtlr
+
+extern "C" int dtlr_version(void) { return (0 << 16) | (1 << 8) | 0; }
+extern "C" int dtlr_built_for_sm(void) { return 100; }
+extern "C" const char* dtlr_last_error(void) { return dtlr::g_err; }

@@ -1,0 +1,64 @@
+// dtlr_b200 -- shared host/device helpers for the sm_100a kernels behind include/dtlr_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dtlr_b200.h"
+
+namespace dtlr {
+
+void set_error(const char* fmt, ...);
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline int max_smem_optin() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (n <= 0) n = 227 * 1024;
+    }
+    return n;
+}
+
+#define DTLR_CHECK_ARG(cond, ...)                    \
+    do {                                             \
+        if (!(cond)) {                               \
+            dtlr::set_error(__VA_ARGS__);            \
+            return DTLR_ERR_INVALID;                 \
+        }                                            \
+    } while (0)
+
+#define DTLR_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dtlr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                            __LINE__);                                                         \
+            return DTLR_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define DTLR_CHECK_LAUNCH() DTLR_CHECK_CUDA(cudaGetLastError())
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+}  // namespace dtlr

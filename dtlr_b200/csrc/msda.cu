@@ -1,0 +1,478 @@
+// dtlr_b200 -- multi-scale deformable attention core for sm_100a.
+//
+// Replaces the reference op models/dino/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299 (forward, one thread per
+// output scalar, every lane re-reading loc/weight scalars) and :301-403 (backward) behind the C ABI of
+// include/dtlr_b200.h.  Design:
+//
+//  * D == 32 fast path (the only head width DTLR uses: d_model 256 / 8 heads).  One CTA = one (image, head,
+//    query range).  The head's value slab -- every level, S pixels x 32 channels -- is staged ONCE in shared
+//    memory with 16-byte cp.async (fp32 slab 117 KB, bf16 58 KB at S=912), with one zero pixel of padding on
+//    each side, so that all 64 bilinear taps of every query are shared-memory reads.
+//  * one warp = one query at a time.  Lane (pt = lane&15, row = lane>>4) computes the tap parameters of ONE
+//    (sampling point, y-row) pair: pixel index of the left corner and the two x-corner weights (attention
+//    weight, y weight and validity folded in).  The 32 parameter triples are then handed round by shuffles.
+//  * gather: a group of 2*LPP lanes (LPP = lanes per pixel = 32*sizeof(T)/16) reads the two x-adjacent corners
+//    of one (point,row) as ONE contiguous 2*32*sizeof(T)-byte run with 16-byte loads -> bank-conflict free by
+//    construction; fp32 accumulation; butterfly "transpose" reduction leaves one output channel per lane.
+//  * slabs that do not fit in shared memory (large S) use the same code with the taps read through L1/L2.
+//  * generic path (any D, fp32/fp64): one warp per (b,q,m), lanes over channels.  Used by the fp64 KATs.
+#include "common.cuh"
+
+namespace dtlr {
+
+constexpr int MAX_LEVELS = 8;
+
+struct Levels {
+    int n;
+    int H[MAX_LEVELS], W[MAX_LEVELS], start[MAX_LEVELS];
+};
+
+// ------------------------------------------------------------------------------------------------ fast path
+// Blackwell packed fp32 FMA (FFMA2): d.xy = a.xy * b.xy + d.xy on 64-bit register pairs.
+__device__ __forceinline__ void ffma2(unsigned long long& acc, const unsigned long long a, const unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(const float lo, const float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack2u(const uint32_t lo, const uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(const unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+template <typename T>
+struct Vec16;  // 16 bytes of T -> NP packed fp32 pairs
+template <>
+struct Vec16<float> {
+    static constexpr int NP = 2;
+    __device__ static __forceinline__ void load(const void* p, unsigned long long (&v)[2]) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+    static constexpr int NP = 4;
+    __device__ static __forceinline__ void load(const void* p, unsigned long long (&v)[4]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        v[0] = pack2u(t.x << 16, t.x & 0xffff0000u);
+        v[1] = pack2u(t.y << 16, t.y & 0xffff0000u);
+        v[2] = pack2u(t.z << 16, t.z & 0xffff0000u);
+        v[3] = pack2u(t.w << 16, t.w & 0xffff0000u);
+    }
+};
+
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T, bool STAGE, bool SINGLE, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
+                    T* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
+                    const int P, const int q_per_cta) {
+    constexpr int ROWB = 32 * (int)sizeof(T);   // bytes of one pixel (32 channels)
+    constexpr int LPP = ROWB / 16;              // lanes per pixel (8 fp32 / 4 bf16)
+    constexpr int GL = 2 * LPP;                 // lanes per (point,row) group: two x-adjacent pixels
+    constexpr int G = 32 / GL;                  // groups per warp (2 fp32 / 4 bf16)
+    constexpr int ITER = 16 / G;                // gather iterations per y-row of a 16-point chunk
+    constexpr int NP = Vec16<T>::NP;            // packed channel pairs per lane
+    constexpr int NV = 2 * NP;                  // channels per lane
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(Lq, q0 + q_per_cta);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int LP = lv.n * P;
+
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * M + m) * ROWB;
+    const size_t gstride = (size_t)M * ROWB;    // bytes between consecutive pixels of one head in (B,S,M,D)
+
+    if (STAGE) {
+        // slab[p+1] = pixel p; slab[0] and slab[S+1] are zero padding (taps with zero weight may land there)
+        for (int i = tid; i < S * LPP; i += NWARPS * 32) {
+            const int row = i / LPP, ch = i - row * LPP;
+            cp_async16(smem + (size_t)(row + 1) * ROWB + ch * 16, gbase + (size_t)row * gstride + ch * 16);
+        }
+        cp_async_commit();
+        if (tid < 2 * LPP) {
+            const int row = (tid < LPP) ? 0 : (S + 1);
+            *reinterpret_cast<uint4*>(smem + (size_t)row * ROWB + (tid % LPP) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+    }
+
+    const int sub = lane % GL;        // position inside the 2-pixel run
+    const int g = lane / GL;          // group id
+    const int side = sub / LPP;       // 0 = left corner (x0), 1 = right corner (x0+1)
+    // parameter role of this lane: sampling point (lane & 15) of the current 16-point chunk, x-side (lane >> 4).
+    // It produces, for BOTH y-rows, the byte offset of the row's left pixel and the weight of its own side.
+    const int pt16 = lane & 15, pside = lane >> 4;
+    // the lane this lane fetches its taps from in iteration i is (i*G + g) + 16*side
+    const int src0 = g + 16 * side;
+    const uint32_t lane_off = STAGE ? (uint32_t)(ROWB + sub * 16) : (uint32_t)((sub - side * LPP) * 16);
+
+    for (int q = q0 + warp; q < q1; q += NWARPS) {
+        const size_t pbase = ((size_t)((size_t)b * Lq + q) * M + m) * LP;
+        unsigned long long acc[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) acc[k] = 0ull;
+
+        // SINGLE: L*P <= 16 (DTLR: 4 levels x 4 points) -> one chunk, level constants hoisted out of the query loop
+        for (int c0 = 0; c0 < (SINGLE ? 1 : LP); c0 += 16) {
+            // ---- tap parameters of point c0+pt16 (branch-free: out-of-range points get weight 0 and a safe offset)
+            const int pt = min(c0 + pt16, LP - 1);
+            const bool pt_ok = (c0 + pt16) < LP;
+            const float2 xy = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
+            const float aw = attn[pbase + pt];
+            const int l = pt / P;
+            const int H = lv.H[l], W = lv.W[l];
+            const float y = fmaf(xy.y, (float)H, -0.5f), x = fmaf(xy.x, (float)W, -0.5f);
+            const bool inside = pt_ok && y > -1.f && x > -1.f && y < (float)H && x < (float)W;
+            const float yf = floorf(y), xf = floorf(x);
+            const int y0 = (int)yf, x0 = (int)xf;
+            const float fy = y - yf, fx = x - xf;
+            // weight of this lane's x-side, zero when that corner column is outside the map
+            const bool col_ok = pside ? (x0 + 1 <= W - 1) : (x0 >= 0);
+            const float wx = (inside && col_ok) ? (pside ? fx : 1.f - fx) * aw : 0.f;
+            const bool r0_ok = inside && y0 >= 0, r1_ok = inside && y0 + 1 <= H - 1;
+            const float w_r0 = r0_ok ? wx * (1.f - fy) : 0.f;
+            const float w_r1 = r1_ok ? wx * fy : 0.f;
+            const int pix0 = lv.start[l] + y0 * W + x0;
+            int o_r0, o_r1;   // pixel index (STAGE: scaled to bytes) of the left corner of each row, 0 if the row is unused
+            if (STAGE) {
+                o_r0 = r0_ok ? pix0 * ROWB : 0;
+                o_r1 = r1_ok ? (pix0 + W) * ROWB : 0;
+            } else {
+                o_r0 = r0_ok ? pix0 : 0;
+                o_r1 = r1_ok ? pix0 + W : 0;
+            }
+            // ---- gather: iteration (r,i), group g consumes point i*G+g, y-row r
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    const int src = src0 + i * G;
+                    const int so = __shfl_sync(0xffffffffu, r ? o_r1 : o_r0, src);
+                    const float sw = __shfl_sync(0xffffffffu, r ? w_r1 : w_r0, src);
+                    const unsigned long long w2 = pack2(sw, sw);
+                    unsigned long long v[NP];
+                    if (STAGE) {
+                        Vec16<T>::load(smem + (uint32_t)so + lane_off, v);
+                    } else {
+                        const int p = so + side;
+                        if (p >= 0 && p < S && sw != 0.f) {
+                            Vec16<T>::load(gbase + (size_t)p * gstride + lane_off, v);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < NP; ++k) v[k] = 0ull;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) ffma2(acc[k], v[k], w2);
+                }
+            }
+        }
+
+        // ---- reduce over the lanes that hold the same channels (same sub % LPP): butterfly with halving,
+        //      ends with exactly one channel per lane.
+        float a[NV];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) unpack2(acc[k], a[2 * k], a[2 * k + 1]);
+        int ch = (sub % LPP) * NV;
+        if (NV == 8) {
+            {   // xor 16: keep 4
+                const bool hi = (lane & 16) != 0;
+                float keep[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float send = hi ? a[k] : a[k + 4];
+                    const float mine = hi ? a[k + 4] : a[k];
+                    keep[k] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+                ch += hi ? 4 : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = keep[k];
+            }
+            {   // xor 8: keep 2
+                const bool hi = (lane & 8) != 0;
+                float keep[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = hi ? a[k] : a[k + 2];
+                    const float mine = hi ? a[k + 2] : a[k];
+                    keep[k] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                ch += hi ? 2 : 0;
+                a[0] = keep[0]; a[1] = keep[1];
+            }
+            {   // xor 4: keep 1
+                const bool hi = (lane & 4) != 0;
+                const float send = hi ? a[0] : a[1];
+                const float mine = hi ? a[1] : a[0];
+                a[0] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+                ch += hi ? 1 : 0;
+            }
+        } else {  // NV == 4: lanes sharing (lane & 7): xor 16, xor 8
+            {
+                const bool hi = (lane & 16) != 0;
+                float keep[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = hi ? a[k] : a[k + 2];
+                    const float mine = hi ? a[k + 2] : a[k];
+                    keep[k] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+                ch += hi ? 2 : 0;
+                a[0] = keep[0]; a[1] = keep[1];
+            }
+            {
+                const bool hi = (lane & 8) != 0;
+                const float send = hi ? a[0] : a[1];
+                const float mine = hi ? a[1] : a[0];
+                a[0] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+                ch += hi ? 1 : 0;
+            }
+        }
+        store_out(out + ((size_t)((size_t)b * Lq + q) * M + m) * 32 + ch, a[0]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generic path
+template <typename T>
+__device__ __forceinline__ T ld_as(const T* p) { return *p; }
+
+template <typename T>
+__global__ void msda_fwd_generic_kernel(const T* __restrict__ value, const T* __restrict__ loc,
+                                        const T* __restrict__ attn, T* __restrict__ out, const __grid_constant__ Levels lv, const int B,
+                                        const int S, const int M, const int D, const int Lq, const int P) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total = (long long)B * Lq * M;
+    if (wid >= total) return;
+    const int m = (int)(wid % M);
+    const long long bq = wid / M;
+    const int b = (int)(bq / Lq);
+    const int LP = lv.n * P;
+    const T* vb = value + (size_t)b * S * M * D + (size_t)m * D;
+    for (int c = lane; c < D; c += 32) {
+        T acc = 0;
+        for (int pt = 0; pt < LP; ++pt) {
+            const int l = pt / P;
+            const int H = lv.H[l], W = lv.W[l];
+            const T lx = loc[((size_t)wid * LP + pt) * 2], ly = loc[((size_t)wid * LP + pt) * 2 + 1];
+            const T aw = attn[(size_t)wid * LP + pt];
+            const T y = ly * H - (T)0.5, x = lx * W - (T)0.5;
+            if (!(y > -1 && x > -1 && y < H && x < W)) continue;
+            const int y0 = (int)floor((double)y), x0 = (int)floor((double)x);
+            const T fy = y - y0, fx = x - x0;
+            T val = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+                if (yy < 0 || yy > H - 1 || xx < 0 || xx > W - 1) continue;
+                const T cw = ((k >> 1) ? fy : 1 - fy) * ((k & 1) ? fx : 1 - fx);
+                val += cw * vb[(size_t)(lv.start[l] + yy * W + xx) * M * D + c];
+            }
+            acc += aw * val;
+        }
+        out[(size_t)wid * D + c] = acc;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// backward: one warp per (b,q,m); lanes over channels; grad_value scattered with atomics (as the reference does,
+// ms_deform_im2col_cuda.cuh:125-152), grad_loc / grad_attn reduced with shuffles instead of shared memory + a
+// serial thread-0 sum (reference :377-393).
+template <typename T>
+__global__ void msda_bwd_kernel(const T* __restrict__ value, const T* __restrict__ loc, const T* __restrict__ attn,
+                                const T* __restrict__ gout, T* __restrict__ gvalue, T* __restrict__ gloc,
+                                T* __restrict__ gattn, const __grid_constant__ Levels lv, const int B, const int S, const int M,
+                                const int D, const int Lq, const int P) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total = (long long)B * Lq * M;
+    if (wid >= total) return;
+    const int m = (int)(wid % M);
+    const int b = (int)((wid / M) / Lq);
+    const int LP = lv.n * P;
+    const size_t voff = (size_t)b * S * M * D + (size_t)m * D;
+    const T* go = gout + (size_t)wid * D;
+    for (int pt = 0; pt < LP; ++pt) {
+        const int l = pt / P;
+        const int H = lv.H[l], W = lv.W[l];
+        const size_t ip = (size_t)wid * LP + pt;
+        const T y = loc[ip * 2 + 1] * H - (T)0.5, x = loc[ip * 2] * W - (T)0.5;
+        const T aw = attn[ip];
+        T acc_w = 0, acc_x = 0, acc_y = 0;
+        if (y > -1 && x > -1 && y < H && x < W) {
+            const int y0 = (int)floor((double)y), x0 = (int)floor((double)x);
+            const T fy = y - y0, fx = x - x0, gy = 1 - fy, gx = 1 - fx;
+            for (int c = lane; c < D; c += 32) {
+                const T g = go[c], ga = g * aw;
+                T val = 0, ddy = 0, ddx = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+                    if (yy < 0 || yy > H - 1 || xx < 0 || xx > W - 1) continue;
+                    const T cw = ((k >> 1) ? fy : gy) * ((k & 1) ? fx : gx);
+                    const T dy = ((k >> 1) ? (T)1 : (T)-1) * ((k & 1) ? fx : gx);
+                    const T dx = ((k & 1) ? (T)1 : (T)-1) * ((k >> 1) ? fy : gy);
+                    const size_t idx = voff + (size_t)(lv.start[l] + yy * W + xx) * M * D + c;
+                    const T v = value[idx];
+                    val += cw * v; ddy += dy * v; ddx += dx * v;
+                    atomicAdd(gvalue + idx, cw * ga);
+                }
+                acc_w += g * val;
+                acc_x += (T)W * ddx * ga;
+                acc_y += (T)H * ddy * ga;
+            }
+        }
+        acc_w = warp_sum(acc_w); acc_x = warp_sum(acc_x); acc_y = warp_sum(acc_y);
+        if (lane == 0) { gattn[ip] = acc_w; gloc[ip * 2] = acc_x; gloc[ip * 2 + 1] = acc_y; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int fill_levels(Levels& lv, const int64_t* shapes, const int64_t* lsi, int L, int S) {
+    DTLR_CHECK_ARG(L >= 1 && L <= MAX_LEVELS, "msda: n_levels %d not in [1,%d]", L, MAX_LEVELS);
+    long long tot = 0;
+    lv.n = L;
+    for (int l = 0; l < L; ++l) {
+        lv.H[l] = (int)shapes[2 * l];
+        lv.W[l] = (int)shapes[2 * l + 1];
+        lv.start[l] = (int)lsi[l];
+        DTLR_CHECK_ARG(lv.H[l] > 0 && lv.W[l] > 0, "msda: level %d has empty shape", l);
+        DTLR_CHECK_ARG(lv.start[l] == tot, "msda: level_start_index[%d]=%d, expected %lld", l, lv.start[l], tot);
+        tot += (long long)lv.H[l] * lv.W[l];
+    }
+    DTLR_CHECK_ARG(tot == S, "msda: sum(H*W)=%lld != S=%d", tot, S);
+    return DTLR_OK;
+}
+
+template <typename T, int NW>
+static int launch_fwd_d32_nw(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
+                             int S, int M, int Lq, int P, bool stage, size_t slab, int occ, cudaStream_t st) {
+    const long long slots = (long long)sm_count() * occ;
+    // split the query range so that the grid is several waves deep but every CTA keeps >= 64 queries
+    int qsplit = (int)((4 * slots + (long long)B * M - 1) / ((long long)B * M));
+    const int max_split = (Lq + 63) / 64;
+    if (qsplit > max_split) qsplit = max_split;
+    if (qsplit < 1) qsplit = 1;
+    const int q_per_cta = (Lq + qsplit - 1) / qsplit;
+    qsplit = (Lq + q_per_cta - 1) / q_per_cta;
+    dim3 grid(qsplit, M, B), block(NW * 32);
+    const bool single = lv.n * P <= 16;
+    if (stage) {
+        auto k = single ? msda_fwd_d32_kernel<T, true, true, NW> : msda_fwd_d32_kernel<T, true, false, NW>;
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
+        k<<<grid, block, slab, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
+                                     q_per_cta);
+    } else {
+        auto k = single ? msda_fwd_d32_kernel<T, false, true, NW> : msda_fwd_d32_kernel<T, false, false, NW>;
+        k<<<grid, block, 0, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
+                                  q_per_cta);
+    }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+template <typename T>
+static int launch_fwd_d32(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
+                          int S, int M, int Lq, int P, cudaStream_t st) {
+    const size_t slab = (size_t)(S + 2) * 32 * sizeof(T);
+    const bool stage = slab <= (size_t)max_smem_optin();
+    // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA)
+    int occ_smem = stage ? (int)min((size_t)8, (size_t)(228 * 1024) / (slab + 1024)) : 8;
+    if (occ_smem < 1) occ_smem = 1;
+    // 64 registers/thread -> at most 32 warps per SM: one 32-warp CTA when only one slab fits, else 16-warp CTAs
+    if (occ_smem == 1)
+        return launch_fwd_d32_nw<T, 32>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, 1, st);
+    return launch_fwd_d32_nw<T, 16>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, min(occ_smem, 2), st);
+}
+
+}  // namespace dtlr
+
+using namespace dtlr;
+
+extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                                 const void* attn, void* out, int B, int S, int M, int D, int L, int Lq, int P,
+                                 int dtype, void* stream) {
+    DTLR_CHECK_ARG(B >= 0 && Lq >= 0 && S > 0 && M > 0 && D > 0 && P > 0, "msda_forward: bad sizes");
+    DTLR_CHECK_ARG(shapes && lsi, "msda_forward: null shapes");
+    Levels lv;
+    int rc = fill_levels(lv, shapes, lsi, L, S);
+    if (rc) return rc;
+    if (B == 0 || Lq == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(value && loc && attn && out, "msda_forward: null pointer");
+    DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward: B or M exceeds 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = (((uintptr_t)value | (uintptr_t)loc) & 15) == 0;
+    if (D == 32 && aligned && (dtype == DTLR_F32 || dtype == DTLR_BF16)) {
+        return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, loc, attn, out, lv, B, S, M, Lq, P, st)
+                                 : launch_fwd_d32<__nv_bfloat16>(value, loc, attn, out, lv, B, S, M, Lq, P, st);
+    }
+    const long long warps = (long long)B * Lq * M;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    DTLR_CHECK_ARG(blocks < (1ll << 31), "msda_forward: problem too large for the generic kernel");
+    if (dtype == DTLR_F32) {
+        msda_fwd_generic_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
+            (const float*)value, (const float*)loc, (const float*)attn, (float*)out, lv, B, S, M, D, Lq, P);
+    } else if (dtype == DTLR_F64) {
+        msda_fwd_generic_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(
+            (const double*)value, (const double*)loc, (const double*)attn, (double*)out, lv, B, S, M, D, Lq, P);
+    } else {
+        set_error("msda_forward: dtype %d with D=%d has no kernel (bf16 requires D=32, 16-byte aligned)", dtype, D);
+        return DTLR_ERR_UNSUPPORTED;
+    }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                                  const void* attn, const void* grad_out, void* grad_value, void* grad_loc,
+                                  void* grad_attn, int B, int S, int M, int D, int L, int Lq, int P, int dtype,
+                                  void* stream) {
+    DTLR_CHECK_ARG(B >= 0 && Lq >= 0 && S > 0 && M > 0 && D > 0 && P > 0, "msda_backward: bad sizes");
+    DTLR_CHECK_ARG(shapes && lsi, "msda_backward: null shapes");
+    Levels lv;
+    int rc = fill_levels(lv, shapes, lsi, L, S);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == DTLR_F64 ? 8 : 4;
+    DTLR_CHECK_ARG(dtype == DTLR_F32 || dtype == DTLR_F64, "msda_backward: dtype must be f32 or f64");
+    if (B == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(grad_value, "msda_backward: null grad_value");
+    DTLR_CHECK_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)B * S * M * D * esz, st));
+    if (Lq == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(value && loc && attn && grad_out && grad_loc && grad_attn, "msda_backward: null pointer");
+    const long long warps = (long long)B * Lq * M;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    DTLR_CHECK_ARG(blocks < (1ll << 31), "msda_backward: problem too large");
+    if (dtype == DTLR_F32) {
+        msda_bwd_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
+            (const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out, (float*)grad_value,
+            (float*)grad_loc, (float*)grad_attn, lv, B, S, M, D, Lq, P);
+    } else {
+        msda_bwd_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(
+            (const double*)value, (const double*)loc, (const double*)attn, (const double*)grad_out,
+            (double*)grad_value, (double*)grad_loc, (double*)grad_attn, lv, B, S, M, D, Lq, P);
+    }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}

@@ -1,0 +1,181 @@
+"""GPU: the sm_100a MSDA kernels through the C ABI against (a) the committed reference known-answer vectors
+(reference ops/test.py fixture) and (b) the C oracle on seeded inputs, including out-of-range points, empty query
+sets, a slab too large for shared memory and the full BASELINE config-2 size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda as omsda
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "msda_kat.npz"))
+
+
+def _levels(shapes):
+    shp = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = torch.cat((shp.new_zeros((1,)), shp.prod(1).cumsum(0)[:-1]))
+    return shp, lsi
+
+
+def _rand_case(B, shapes, M, D, Lq, P, seed, dtype=torch.float32, oob=True):
+    g = torch.Generator().manual_seed(seed)
+    shp, lsi = _levels(shapes)
+    S = int(shp.prod(1).sum())
+    L = len(shapes)
+    value = torch.randn(B, S, M, D, generator=g).to(dtype)
+    loc = torch.rand(B, Lq, M, L, P, 2, generator=g)
+    if oob:
+        loc = loc * 1.3 - 0.15
+    w = torch.softmax(torch.randn(B, Lq, M, L * P, generator=g), -1).view(B, Lq, M, L, P)
+    return value, shp, lsi, loc.to(dtype), w.to(dtype)
+
+
+@pytest.mark.parametrize("D", [2, 30, 32, 64, 71])
+def test_forward_double_reference_kat(kat, D):
+    from dtlr_b200 import msda
+    t = lambda k: torch.from_numpy(kat["D%d_%s" % (D, k)]).cuda()
+    shp, lsi = torch.from_numpy(kat["shapes"]).cuda(), torch.from_numpy(kat["lsi"]).cuda()
+    out = msda.ms_deform_attn_forward(t("value"), shp, lsi, t("loc"), t("w"), 2)
+    assert torch.allclose(out.cpu(), torch.from_numpy(kat["D%d_out" % D]))          # reference test.py:40
+
+
+@pytest.mark.parametrize("D", [2, 32])
+def test_forward_float_reference_kat(kat, D):
+    from dtlr_b200 import msda
+    t = lambda k: torch.from_numpy(kat["D%d_%s" % (D, k)]).float().cuda()
+    shp, lsi = torch.from_numpy(kat["shapes"]).cuda(), torch.from_numpy(kat["lsi"]).cuda()
+    out = msda.ms_deform_attn_forward(t("value"), shp, lsi, t("loc"), t("w"), 2)
+    ref = torch.from_numpy(kat["D%d_out" % D])
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-2, atol=1e-3)               # reference test.py:56
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-5, atol=1e-8)               # and much tighter
+
+
+@pytest.mark.parametrize("D", [2, 30, 32, 64, 71])
+def test_backward_double_reference_kat(kat, D):
+    from dtlr_b200 import msda
+    t = lambda k: torch.from_numpy(kat["D%d_%s" % (D, k)]).cuda()
+    shp, lsi = torch.from_numpy(kat["shapes"]).cuda(), torch.from_numpy(kat["lsi"]).cuda()
+    gv, gl, ga = msda.ms_deform_attn_backward(t("value"), shp, lsi, t("loc"), t("w"), t("gout"), 2)
+    assert torch.allclose(gv.cpu(), torch.from_numpy(kat["D%d_gvalue" % D]), rtol=1e-9, atol=1e-13)
+    assert torch.allclose(gl.cpu(), torch.from_numpy(kat["D%d_gloc" % D]), rtol=1e-9, atol=1e-13)
+    assert torch.allclose(ga.cpu(), torch.from_numpy(kat["D%d_gw" % D]), rtol=1e-9, atol=1e-13)
+
+
+def test_autograd_function_gradcheck():
+    """reference test.py:63-78 (gradcheck in fp64 through MSDeformAttnFunction)."""
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(1, [(6, 4), (3, 2)], 2, 32, 2, 2, 5, torch.float64, oob=False)
+    value = (value * 0.01).cuda().requires_grad_()
+    loc = loc.cuda().requires_grad_()
+    w = w.cuda().requires_grad_()
+    assert torch.autograd.gradcheck(msda.MSDeformAttnFunction.apply, (value, shp.cuda(), lsi.cuda(), loc, w, 2))
+
+
+A_SHAPES = [(5, 128), (3, 64), (2, 32), (1, 16)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Lq", [1, 37, 900])
+def test_fast_path_vs_oracle(dtype, Lq):
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(2, A_SHAPES, 8, 32, Lq, 4, 100 + Lq)
+    vq = value.to(dtype)
+    ref = omsda.msda_forward(vq.float(), shp, lsi, loc, w)           # oracle on the same (rounded) values
+    out = msda.ms_deform_attn_forward(vq.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64).float().cpu()
+    if dtype == torch.float32:
+        assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
+    else:   # bf16 output rounding only (fp32 accumulation inside)
+        assert torch.allclose(out, ref, rtol=1e-2, atol=1e-2)
+
+
+def test_fast_path_committed_vector(kat):
+    from dtlr_b200 import msda
+    g = torch.Generator().manual_seed(11)
+    value = torch.randn(2, 912, 8, 32, generator=g)
+    loc = torch.rand(2, 37, 8, 4, 4, 2, generator=g) * 1.3 - 0.15
+    w = torch.softmax(torch.randn(2, 37, 8, 16, generator=g), -1).view(2, 37, 8, 4, 4)
+    shp, lsi = torch.from_numpy(kat["A_shapes"]), torch.from_numpy(kat["A_lsi"])
+    out = msda.ms_deform_attn_forward(value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64).cpu()
+    assert torch.allclose(out, torch.from_numpy(kat["A_out"]), rtol=1e-4, atol=1e-5)
+
+
+def test_points_on_borders_and_far_outside():
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(1, A_SHAPES, 8, 32, 64, 4, 7)
+    # exact borders, half-pixel positions, far outside, negative
+    special = torch.tensor([0.0, 1.0, -1e-7, 1.0 + 1e-7, 0.5 / 128, 1 - 0.5 / 128, -5.0, 7.0, 1.5 / 5, 0.999999])
+    idx = torch.randint(0, len(special), loc.shape, generator=torch.Generator().manual_seed(1))
+    loc = special[idx]
+    ref = omsda.msda_forward(value, shp, lsi, loc, w)
+    out = msda.ms_deform_attn_forward(value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64).cpu()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_empty_query_set_and_batch():
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(2, A_SHAPES, 8, 32, 4, 4, 3)
+    out = msda.ms_deform_attn_forward(value.cuda(), shp.cuda(), lsi.cuda(), loc[:, :0].contiguous().cuda(),
+                                      w[:, :0].contiguous().cuda(), 64)
+    assert out.shape == (2, 0, 256)
+
+
+def test_large_map_gathers_from_global():
+    """real IAM resolution (~94x1333 -> S=2676+): the fp32 slab (342 KB) does not fit shared memory."""
+    from dtlr_b200 import msda
+    shapes = [(12, 167), (6, 84), (3, 42), (2, 21)]
+    for dtype in (torch.float32, torch.bfloat16):
+        value, shp, lsi, loc, w = _rand_case(1, shapes, 8, 32, 200, 4, 9)
+        vq = value.to(dtype)
+        ref = omsda.msda_forward(vq.float(), shp, lsi, loc, w)
+        out = msda.ms_deform_attn_forward(vq.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64).float().cpu()
+        tol = 1e-4 if dtype == torch.float32 else 1e-2
+        assert torch.allclose(out, ref, rtol=tol, atol=tol * 0.1 if dtype == torch.float32 else 1e-2)
+
+
+def test_generic_path_other_head_width():
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(2, [(6, 4), (3, 2)], 2, 30, 5, 2, 13)
+    ref = omsda.msda_forward(value, shp, lsi, loc, w)
+    out = msda.ms_deform_attn_forward(value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64).cpu()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_backward_fp32_vs_oracle_config_size():
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(2, A_SHAPES, 8, 32, 50, 4, 21)
+    go = torch.randn(2, 50, 256, generator=torch.Generator().manual_seed(2))
+    rv, rl, ra = omsda.msda_backward(value.double(), shp, lsi, loc.double(), w.double(), go.double())
+    gv, gl, ga = msda.ms_deform_attn_backward(value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), go.cuda(), 64)
+    assert torch.allclose(gv.cpu().double(), rv, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(gl.cpu().double(), rl, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(ga.cpu().double(), ra, rtol=1e-3, atol=1e-4)
+
+
+def test_full_size_linearity_config2():
+    """BASELINE config 2 size (B=64, S=912, Lq=912): size-independent property -- the op is linear in value and in the
+    attention weights: f(a*v1 + v2, w) == a*f(v1,w) + f(v2,w)."""
+    from dtlr_b200 import msda
+    value, shp, lsi, loc, w = _rand_case(64, A_SHAPES, 8, 32, 912, 4, 33)
+    v1 = value.cuda()
+    v2 = torch.randn_like(v1)
+    shp, lsi, loc, w = shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda()
+    f = lambda v: msda.ms_deform_attn_forward(v, shp, lsi, loc, w, 64)
+    lhs = f(2.5 * v1 + v2)
+    rhs = 2.5 * f(v1) + f(v2)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-4)
+    # and a slice of it against the oracle
+    ref = omsda.msda_forward(value[:1], shp.cpu(), lsi.cpu(), loc[:1].cpu(), w[:1].cpu())
+    assert torch.allclose(f(v1)[:1].cpu(), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_rejects_cpu_tensors():
+    from dtlr_b200 import msda, _lib
+    value, shp, lsi, loc, w = _rand_case(1, [(6, 4), (3, 2)], 2, 32, 2, 2, 1)
+    with pytest.raises(_lib.DtlrError):
+        msda.ms_deform_attn_forward(value, shp, lsi, loc, w, 64)
