@@ -1,0 +1,411 @@
+"""DINO model boundary: `build_dino(args) -> (model, criterion, postprocessors)`,
+`DINO.forward(samples, targets=None) -> dict`, `SetCriterion.loss_CTC`, `PostProcess` -- same names, argument meaning,
+output dict keys and state-dict layout as reference models/dino/dino.py:49-1194, so engine.py / evaluation.py /
+finetuning.py of the reference drive this model unchanged.
+
+Two execution paths share the parameters held here:
+  * inference (model.eval() under torch.no_grad()): dtlr_b200.engine.InferenceEngine -- fused hand-written sm_100a
+    kernels through the C ABI, fp32 "parity" or bf16 "throughput" mode (model.compute_dtype);
+  * training / autograd: the module path below (torch autograd + the C-ABI deformable-attention forward/backward).
+Neither path runs on the CPU.
+"""
+import copy
+import math
+from typing import List
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .backbone import build_backbone
+from .misc import NestedTensor, inverse_sigmoid, nested_tensor_from_tensor_list
+from .registry import MODULE_BUILD_FUNCS
+from .transformer import MLP, build_deformable_transformer
+
+
+# ----------------------------------------------------------------------------------------------- DN queries
+def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, label_enc):
+    """reference models/dino/dn_components.py:20-142.  Device-agnostic restatement (the reference calls .cuda()).
+    In DTLR's CTC fine-tuning (use_dn=False -> dn_number 0 -> one group, zero GT boxes) the result is deterministic:
+    the noise terms multiply zero-size boxes and the label-noise draw is never applied (quirk Q3)."""
+    if not training:
+        return None, None, None, None
+    targets, dn_number, label_noise_ratio, box_noise_scale = dn_args
+    dn_number = dn_number * 2
+    device = label_enc.weight.device
+    known_num = [int(t["labels"].numel()) for t in targets]
+    batch_size = len(known_num)
+    if max(known_num) == 0:
+        dn_number = 1
+    elif dn_number >= 100:
+        dn_number = dn_number // (max(known_num) * 2)
+    elif dn_number < 1:
+        dn_number = 1
+    if dn_number == 0:
+        dn_number = 1
+    labels = torch.cat([t["labels"] for t in targets]).to(device)
+    boxes = torch.cat([t["boxes"] for t in targets]).to(device)
+    batch_idx = torch.cat([torch.full((n,), i, dtype=torch.long) for i, n in enumerate(known_num)]).to(device)
+    known_labels = labels.repeat(2 * dn_number, 1).view(-1)
+    known_bid = batch_idx.repeat(2 * dn_number, 1).view(-1)
+    known_bboxs = boxes.repeat(2 * dn_number, 1)
+    known_bbox_expand = known_bboxs.clone()
+    single_pad = max(known_num)
+    pad_size = int(single_pad * 2 * dn_number)
+    nb = boxes.shape[0]
+    positive_idx = (torch.arange(nb, device=device)[None] + (torch.arange(dn_number, device=device) * nb * 2)[:, None]).flatten()
+    negative_idx = positive_idx + nb
+    if box_noise_scale > 0 and nb > 0:
+        xyxy = torch.cat([known_bboxs[:, :2] - known_bboxs[:, 2:] / 2, known_bboxs[:, :2] + known_bboxs[:, 2:] / 2], 1)
+        diff = torch.cat([known_bboxs[:, 2:] / 2, known_bboxs[:, 2:] / 2], 1)
+        rand_sign = torch.randint_like(known_bboxs, low=0, high=2, dtype=torch.float32) * 2.0 - 1.0
+        rand_part = torch.rand_like(known_bboxs)
+        rand_part[negative_idx] += 1.0
+        rand_part *= rand_sign
+        xyxy = (xyxy + rand_part * diff * box_noise_scale).clamp(min=0.0, max=1.0)
+        known_bbox_expand = torch.cat([(xyxy[:, :2] + xyxy[:, 2:]) / 2, xyxy[:, 2:] - xyxy[:, :2]], 1)
+    input_label_embed = label_enc(known_labels.long())
+    input_bbox_embed = inverse_sigmoid(known_bbox_expand)
+    input_query_label = torch.zeros(batch_size, pad_size, hidden_dim, device=device)
+    input_query_bbox = torch.zeros(batch_size, pad_size, 4, device=device)
+    if nb > 0:
+        within = torch.cat([torch.arange(n, device=device) for n in known_num])
+        map_known = torch.cat([within + single_pad * i for i in range(2 * dn_number)]).long()
+        input_query_label[(known_bid, map_known)] = input_label_embed
+        input_query_bbox[(known_bid, map_known)] = input_bbox_embed
+    tgt_size = pad_size + num_queries
+    attn_mask = torch.zeros(tgt_size, tgt_size, dtype=torch.bool, device=device)
+    attn_mask[pad_size:, :pad_size] = True
+    g = single_pad * 2
+    for i in range(dn_number):
+        attn_mask[g * i:g * (i + 1), g * (i + 1):pad_size] = True
+        attn_mask[g * i:g * (i + 1), :g * i] = True
+    return input_query_label, input_query_bbox, attn_mask, {"pad_size": pad_size, "num_dn_group": dn_number}
+
+
+def dn_post_process(outputs_class, outputs_coord, dn_meta, aux_loss, _set_aux_loss):
+    """reference dn_components.py:145-159"""
+    if dn_meta and dn_meta["pad_size"] > 0:
+        p = dn_meta["pad_size"]
+        known_class, known_coord = outputs_class[:, :, :p, :], outputs_coord[:, :, :p, :]
+        outputs_class, outputs_coord = outputs_class[:, :, p:, :], outputs_coord[:, :, p:, :]
+        out = {"pred_logits": known_class[-1], "pred_boxes": known_coord[-1]}
+        if aux_loss:
+            out["aux_outputs"] = _set_aux_loss(known_class, known_coord)
+        dn_meta["output_known_lbs_bboxes"] = out
+    return outputs_class, outputs_coord
+
+
+# ----------------------------------------------------------------------------------------------- model
+class DINO(nn.Module):
+    """reference models/dino/dino.py:49-425"""
+
+    def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, iter_update=False, query_dim=2,
+                 random_refpoints_xy=False, fix_refpoints_hw=-1, num_feature_levels=1, nheads=8, two_stage_type="no",
+                 two_stage_add_query_num=0, dec_pred_class_embed_share=True, dec_pred_bbox_embed_share=True,
+                 two_stage_class_embed_share=True, two_stage_bbox_embed_share=True, decoder_sa_type="sa",
+                 num_patterns=0, dn_number=100, dn_box_noise_scale=0.4, dn_label_noise_ratio=0.5, dn_labelbook_size=100):
+        super().__init__()
+        self.num_queries = num_queries
+        self.transformer = transformer
+        self.num_classes = num_classes
+        self.hidden_dim = hidden_dim = transformer.d_model
+        self.num_feature_levels = num_feature_levels
+        self.nheads = nheads
+        self.label_enc = nn.Embedding(dn_labelbook_size + 1, hidden_dim)
+        self.query_dim = query_dim
+        assert query_dim == 4
+        self.random_refpoints_xy = random_refpoints_xy
+        self.fix_refpoints_hw = fix_refpoints_hw
+        self.num_patterns = num_patterns
+        self.dn_number = dn_number
+        self.dn_box_noise_scale = dn_box_noise_scale
+        self.dn_label_noise_ratio = dn_label_noise_ratio
+        self.dn_labelbook_size = dn_labelbook_size
+
+        assert num_feature_levels > 1, "DTLR configs use 4 feature levels"
+        num_backbone_outs = len(backbone.num_channels)
+        proj = []
+        for i in range(num_backbone_outs):
+            proj.append(nn.Sequential(nn.Conv2d(backbone.num_channels[i], hidden_dim, kernel_size=1),
+                                      nn.GroupNorm(32, hidden_dim)))
+        in_channels = backbone.num_channels[-1]
+        for _ in range(num_feature_levels - num_backbone_outs):
+            proj.append(nn.Sequential(nn.Conv2d(in_channels, hidden_dim, kernel_size=3, stride=2, padding=1),
+                                      nn.GroupNorm(32, hidden_dim)))
+            in_channels = hidden_dim
+        self.input_proj = nn.ModuleList(proj)
+        self.backbone = backbone
+        self.aux_loss = aux_loss
+        self.iter_update = iter_update
+        assert iter_update, "Why not iter_update?"
+
+        self.dec_pred_class_embed_share = dec_pred_class_embed_share
+        self.dec_pred_bbox_embed_share = dec_pred_bbox_embed_share
+        _class_embed = nn.Linear(hidden_dim, num_classes)
+        _bbox_embed = MLP(hidden_dim, hidden_dim, 4, 3)
+        prior_prob = 0.01
+        _class_embed.bias.data = torch.ones(self.num_classes) * (-math.log((1 - prior_prob) / prior_prob))
+        nn.init.constant_(_bbox_embed.layers[-1].weight.data, 0)
+        nn.init.constant_(_bbox_embed.layers[-1].bias.data, 0)
+        n_dec = transformer.num_decoder_layers
+        self.bbox_embed = nn.ModuleList([_bbox_embed if dec_pred_bbox_embed_share else copy.deepcopy(_bbox_embed)
+                                         for _ in range(n_dec)])
+        self.class_embed = nn.ModuleList([_class_embed if dec_pred_class_embed_share else copy.deepcopy(_class_embed)
+                                          for _ in range(n_dec)])
+        self.transformer.decoder.bbox_embed = self.bbox_embed
+        self.transformer.decoder.class_embed = self.class_embed
+
+        self.two_stage_type = two_stage_type
+        self.two_stage_add_query_num = two_stage_add_query_num
+        assert two_stage_type in ["no", "standard"]
+        if two_stage_type != "no":
+            if two_stage_bbox_embed_share:
+                assert dec_pred_class_embed_share and dec_pred_bbox_embed_share
+                self.transformer.enc_out_bbox_embed = _bbox_embed
+            else:
+                self.transformer.enc_out_bbox_embed = copy.deepcopy(_bbox_embed)
+            if two_stage_class_embed_share:
+                assert dec_pred_class_embed_share and dec_pred_bbox_embed_share
+                self.transformer.enc_out_class_embed = _class_embed
+            else:
+                self.transformer.enc_out_class_embed = copy.deepcopy(_class_embed)
+            self.refpoint_embed = None
+        self.decoder_sa_type = decoder_sa_type
+        assert decoder_sa_type == "sa"
+        self.label_embedding = None
+        for proj in self.input_proj:
+            nn.init.xavier_uniform_(proj[0].weight, gain=1)
+            nn.init.constant_(proj[0].bias, 0)
+
+        # ---- dtlr_b200 execution controls (not part of the reference surface)
+        self.compute_dtype = torch.float32      # torch.float32 = parity mode, torch.bfloat16 = throughput mode
+        self.use_engine = True                  # eval + no_grad -> fused inference engine
+        self.engine_outputs = "all"             # "all": every reference dict key; "final": last-layer logits/boxes only
+        self._engine = None
+
+    # -------------------------------------------------------------------------------------------
+    def _make_inputs(self, samples):
+        if isinstance(samples, (list, torch.Tensor)):
+            samples = nested_tensor_from_tensor_list(samples)
+        if not samples.tensors.is_cuda:
+            raise RuntimeError("dtlr_b200.DINO runs on CUDA tensors only; there is no CPU fallback "
+                               "(the CPU oracle lives in oracle/ and is test infrastructure)")
+        return samples
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import InferenceEngine
+            self._engine = InferenceEngine(self)
+        return self._engine
+
+    def forward(self, samples: NestedTensor, targets: List = None):
+        samples = self._make_inputs(samples)
+        if self.use_engine and not self.training and not torch.is_grad_enabled() and targets is None:
+            return self.engine().forward(samples)
+        return self.forward_modules(samples, targets)
+
+    def forward_modules(self, samples: NestedTensor, targets: List = None):
+        """the reference-shaped module path (reference dino.py:270-415)"""
+        features, poss = self.backbone(samples)
+        srcs, masks = [], []
+        for l, feat in enumerate(features):
+            src, mask = feat.decompose()
+            srcs.append(self.input_proj[l](src))
+            masks.append(mask)
+        if self.num_feature_levels > len(srcs):
+            _len_srcs = len(srcs)
+            for l in range(_len_srcs, self.num_feature_levels):
+                src = self.input_proj[l](features[-1].tensors) if l == _len_srcs else self.input_proj[l](srcs[-1])
+                mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+                pos_l = self.backbone[1](NestedTensor(src, mask)).to(src.dtype)
+                srcs.append(src)
+                masks.append(mask)
+                poss.append(pos_l)
+
+        if self.dn_number > 0 or targets is not None:
+            input_query_label, input_query_bbox, attn_mask, dn_meta = prepare_for_cdn(
+                dn_args=(targets, self.dn_number, self.dn_label_noise_ratio, self.dn_box_noise_scale),
+                training=self.training, num_queries=self.num_queries, num_classes=self.num_classes,
+                hidden_dim=self.hidden_dim, label_enc=self.label_enc)
+        else:
+            input_query_bbox = input_query_label = attn_mask = dn_meta = None
+
+        hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(
+            srcs, masks, input_query_bbox, poss, input_query_label, attn_mask)
+        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0
+
+        outputs_coord_list = torch.stack([
+            (bbox_embed(layer_hs) + inverse_sigmoid(layer_ref)).sigmoid()
+            for layer_ref, bbox_embed, layer_hs in zip(reference[:-1], self.bbox_embed, hs)])
+        outputs_class = torch.stack([cls(layer_hs) for cls, layer_hs in zip(self.class_embed, hs)])
+        if self.dn_number > 0 and dn_meta is not None:
+            outputs_class, outputs_coord_list = dn_post_process(outputs_class, outputs_coord_list, dn_meta,
+                                                                self.aux_loss, self._set_aux_loss)
+        out = {"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord_list[-1]}
+        if self.aux_loss:
+            out["aux_outputs"] = self._set_aux_loss(outputs_class, outputs_coord_list)
+        if hs_enc is not None:
+            interm_class = self.transformer.enc_out_class_embed(hs_enc[-1])
+            out["interm_outputs"] = {"pred_logits": interm_class, "pred_boxes": ref_enc[-1]}
+            out["interm_outputs_for_matching_pre"] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
+        out["dn_meta"] = dn_meta
+        return out
+
+    @torch.jit.unused
+    def _set_aux_loss(self, outputs_class, outputs_coord):
+        return [{"pred_logits": a, "pred_boxes": b} for a, b in zip(outputs_class[:-1], outputs_coord[:-1])]
+
+
+# ----------------------------------------------------------------------------------------------- criterion / decode
+def ctc_view(pred_logits, pred_boxes, eps=0.003):
+    """the "CTC view" of the detections, reference dino.py:472-502: sort queries by cx, sigmoid, synthesise the blank
+    probability.  Returns new_pred_logits (B,Q,C+1).  (torch ops; the fused CUDA decode lives in the engine.)"""
+    __, idx = torch.sort(pred_boxes[:, :, 0])
+    p = torch.gather(pred_logits, 1, idx.unsqueeze(-1).expand(-1, -1, pred_logits.shape[-1])).sigmoid()
+    s = p.sum(-1)
+    low = s < 1 - eps
+    new = torch.empty(p.shape[0], p.shape[1], p.shape[2] + 1, dtype=p.dtype, device=p.device)
+    new[..., 1:] = torch.where(low[..., None], p, (1 - eps) * p / s[..., None])
+    new[..., 0] = torch.where(low, 1 - s, torch.full_like(s, eps))
+    return new
+
+
+class SetCriterion(nn.Module):
+    """reference dino.py:428-983, CTC part.  The Hungarian detection loss (forward_standard) is SURVEY.md §8(f) 'next'."""
+
+    def __init__(self, num_classes, matcher, weight_dict, focal_alpha, losses, CTC=False):
+        super().__init__()
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.weight_dict = weight_dict
+        self.losses = losses
+        self.focal_alpha = focal_alpha
+        self.CTC = CTC
+
+    def loss_CTC(self, outputs, targets, indices, num_boxes, log=True, return_preds=False):
+        """reference dino.py:457-551"""
+        pred_logits = outputs["pred_logits"].float()
+        device = pred_logits.device
+        new_pred_logits = ctc_view(pred_logits, outputs["pred_boxes"].float(), eps=0.003)
+        B, Q, C1 = new_pred_logits.shape
+        padded = torch.empty(B, 2 * Q, C1, dtype=new_pred_logits.dtype, device=device)
+        padded[:, ::2, :] = new_pred_logits
+        padded[:, 1::2, :] = 1e-5
+        padded[:, 1::2, 0] = 1
+        length_pred = torch.full((B,), 2 * Q, dtype=torch.int64)
+        with torch.no_grad():
+            lens = [len(t["labels"]) for t in targets]
+            length_input = torch.tensor(lens, dtype=torch.int64)
+            targets_tensor = torch.zeros(B, max(lens) if lens else 0)
+            for i, t in enumerate(targets):
+                targets_tensor[i, : lens[i]] = (t["labels"] + 1).to(targets_tensor)
+        loss = F.ctc_loss(torch.log(padded.permute(1, 0, 2)), targets_tensor, length_pred, length_input, blank=0,
+                          reduction="mean", zero_infinity=True)
+        losses = {"loss_CTC": loss}
+        if return_preds:
+            return losses, new_pred_logits, None
+        return losses
+
+    def forward(self, outputs, targets, return_indices=False):
+        raise NotImplementedError("the Hungarian detection loss (reference dino.py:780-964) is outside round-1 scope "
+                                  "(SURVEY.md §8f); DTLR fine-tuning and evaluation call loss_CTC directly")
+
+
+def convert_output_to_pred(new_pred_logits):
+    """reference engine.py:512-530 (duplicate=False): argmax over C+1, drop blanks, shift by one."""
+    am = new_pred_logits.argmax(-1)
+    return [(row[row != 0] - 1).tolist() for row in am.cpu()]
+
+
+def _box_cxcywh_to_xyxy(x):
+    cx, cy, w, h = x.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+
+
+def _nms(boxes, scores, iou_threshold):
+    """class-agnostic NMS (reference uses torchvision.ops.nms, dino.py:1030-1034); small N (num_select) -> plain torch."""
+    order = scores.argsort(descending=True)
+    b = boxes[order]
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(b[:, None, :2], b[None, :, :2])
+    rb = torch.min(b[:, None, 2:], b[None, :, 2:])
+    inter = (rb - lt).clamp(min=0).prod(-1)
+    iou = inter / (area[:, None] + area[None, :] - inter)
+    over = (iou > iou_threshold).triu(1).cpu()
+    keep = torch.ones(b.shape[0], dtype=torch.bool)
+    for i in range(b.shape[0]):
+        if keep[i]:
+            keep &= ~over[i]
+    return order[keep.to(order.device)]
+
+
+class PostProcess(nn.Module):
+    """reference dino.py:985-1046"""
+
+    def __init__(self, num_select=100, nms_iou_threshold=-1) -> None:
+        super().__init__()
+        self.num_select = num_select
+        self.nms_iou_threshold = nms_iou_threshold
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, not_to_xyxy=False, test=False):
+        out_logits, out_bbox = outputs["pred_logits"].float(), outputs["pred_boxes"].float()
+        assert len(out_logits) == len(target_sizes)
+        assert target_sizes.shape[1] == 2
+        prob = out_logits.sigmoid()
+        scores, topk_indexes = torch.topk(prob.view(out_logits.shape[0], -1), self.num_select, dim=1)
+        topk_boxes = topk_indexes // out_logits.shape[2]
+        labels = topk_indexes % out_logits.shape[2]
+        boxes = out_bbox if not_to_xyxy else _box_cxcywh_to_xyxy(out_bbox)
+        if test:
+            assert not not_to_xyxy
+            boxes[:, :, 2:] = boxes[:, :, 2:] - boxes[:, :, :2]
+        boxes = torch.gather(boxes, 1, topk_boxes.unsqueeze(-1).repeat(1, 1, 4))
+        img_h, img_w = target_sizes.unbind(1)
+        boxes = boxes * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
+        if self.nms_iou_threshold > 0:
+            keep = [_nms(b, s, self.nms_iou_threshold) for b, s in zip(boxes, scores)]
+            return [{"scores": s[i], "labels": l[i], "boxes": b[i]} for s, l, b, i in zip(scores, labels, boxes, keep)]
+        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, boxes)]
+
+
+@MODULE_BUILD_FUNCS.registe_with_name(module_name="dino")
+def build_dino(args):
+    """reference dino.py:1049-1194"""
+    num_classes = args.num_classes
+    backbone = build_backbone(args)
+    transformer = build_deformable_transformer(args)
+    dn_labelbook_size = getattr(args, "dn_labelbook_size", num_classes)
+    if getattr(args, "masks", False):
+        raise NotImplementedError("segmentation heads are unused by DTLR (masks=False in every config)")
+    model = DINO(
+        backbone, transformer, num_classes=num_classes, num_queries=args.num_queries, aux_loss=True, iter_update=True,
+        query_dim=4, random_refpoints_xy=args.random_refpoints_xy, fix_refpoints_hw=args.fix_refpoints_hw,
+        num_feature_levels=args.num_feature_levels, nheads=args.nheads,
+        dec_pred_class_embed_share=getattr(args, "dec_pred_class_embed_share", True),
+        dec_pred_bbox_embed_share=getattr(args, "dec_pred_bbox_embed_share", True),
+        two_stage_type=args.two_stage_type, two_stage_bbox_embed_share=args.two_stage_bbox_embed_share,
+        two_stage_class_embed_share=args.two_stage_class_embed_share, decoder_sa_type=args.decoder_sa_type,
+        num_patterns=args.num_patterns, dn_number=args.dn_number if args.use_dn else 0,
+        dn_box_noise_scale=args.dn_box_noise_scale, dn_label_noise_ratio=args.dn_label_noise_ratio,
+        dn_labelbook_size=dn_labelbook_size)
+
+    weight_dict = {"loss_ce": args.cls_loss_coef, "loss_bbox": args.bbox_loss_coef, "loss_giou": args.giou_loss_coef}
+    clean_wo_dn = copy.deepcopy(weight_dict)
+    if args.use_dn:
+        weight_dict.update({"loss_ce_dn": args.cls_loss_coef, "loss_bbox_dn": args.bbox_loss_coef,
+                            "loss_giou_dn": args.giou_loss_coef})
+    clean = copy.deepcopy(weight_dict)
+    if args.aux_loss:
+        for i in range(args.dec_layers - 1):
+            weight_dict.update({k + "_%d" % i: v for k, v in clean.items()})
+    if args.two_stage_type != "no":
+        no_box = getattr(args, "no_interm_box_loss", False)
+        coeff = {"loss_ce": 1.0, "loss_bbox": 0.0 if no_box else 1.0, "loss_giou": 0.0 if no_box else 1.0}
+        ic = getattr(args, "interm_loss_coef", 1.0)
+        weight_dict.update({k + "_interm": v * ic * coeff[k] for k, v in clean_wo_dn.items()})
+    criterion = SetCriterion(num_classes, matcher=None, weight_dict=weight_dict, focal_alpha=args.focal_alpha,
+                             losses=["labels", "boxes", "cardinality"])
+    postprocessors = {"bbox": PostProcess(num_select=args.num_select, nms_iou_threshold=args.nms_iou_threshold)}
+    return model, criterion, postprocessors
