@@ -1,0 +1,427 @@
+// dtlr_b200 -- dense contractions of the DINO hot path for sm_100a.
+//
+//   C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])
+//
+// which is every nn.Linear of the reference transformer (models/dino/deformable_transformer.py:787-790,852-855,
+// ops/modules/ms_deform_attn.py:55-58, utils.py:110-122), nn.MultiheadAttention's in/out projections, and -- with the
+// activations in NHWC -- every 1x1 convolution of the ResNet-50 trunk and of input_proj.
+//
+//  * bf16 operands (throughput mode): tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), operands staged by TMA
+//    into 128B-swizzled shared memory, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//    thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> bias/ReLU/residual -> global).  One 128 x BN
+//    output tile per CTA, STAGES-deep mbarrier ring; two CTAs are co-resident per SM so one tile's epilogue overlaps
+//    the other's main loop.
+//  * fp32 operands (parity mode): a plain SIMT kernel with exact fp32 FMA accumulation -- tensor cores have no fp32
+//    input type and TF32 (10-bit mantissa) cannot hold the 1e-3 end-to-end tolerance / top-k ranking of the reference.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dtlr {
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SW128=2 [61,64))
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+struct GemmEpi {
+    const float* bias;       // [N] fp32 or null
+    const void* residual;    // [M, ldr] same dtype as C, or null
+    void* C;                 // [M, ldc]
+    int ldr, ldc;
+    int M, N, K;
+    int relu;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;   // 64 bf16 = 128 B = one swizzle atom row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col0, const uint32_t (&acc)[32], bool vec_ok) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    const int ncol = min(32, e.N - col0);
+    if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < ncol) v[j] += __ldg(e.bias + col0 + j);
+    }
+    if (e.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    OutT* crow = reinterpret_cast<OutT*>(e.C) + (size_t)row * e.ldc + col0;
+    const OutT* rrow = e.residual ? reinterpret_cast<const OutT*>(e.residual) + (size_t)row * e.ldr + col0 : nullptr;
+    if (vec_ok && ncol == 32) {
+        if constexpr (sizeof(OutT) == 2) {
+            if (rrow) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 t = *reinterpret_cast<const uint4*>(rrow + j);
+                    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[j + 2 * k] += __uint_as_float(w[k] << 16);
+                        v[j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(crow + j) = o;
+            }
+        } else {
+            if (rrow) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(rrow + j);
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < ncol) {
+                float x = v[j];
+                if (rrow) x += (float)rrow[j];
+                crow[j] = (OutT)x;
+            }
+        }
+    }
+}
+
+template <int BN, int STAGES, typename OutT>
+__global__ void __launch_bounds__(192)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmEpi e) {
+    using S = GemmSmem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle pattern shared between TMA and the UMMA descriptors
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+    const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);                       // slot free (first lap passes immediately)
+                mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                unsigned char* sa = smem + s * S::STAGE_BYTES;
+                tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+                tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+        // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);                                // TMA bytes have landed
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+                const uint64_t da = make_sw128_kmajor_desc(sa);
+                const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);                             // frees the smem slot when these MMAs retire
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);       // accumulator complete -> epilogue
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int qd = warp & 3;
+        const int row = m0 + qd * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const bool vec_ok = ((e.ldc * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.C & 15) == 0) &&
+                            (!e.residual || (((e.ldr * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.residual & 15) == 0)));
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            if (n0 + c >= e.N) break;
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
+            if (row < e.M) epi_store_row<OutT>(e, row, n0 + c, acc, vec_ok);
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fp32 SIMT GEMM (parity mode)
+// 64x64 tile, 16-deep K slab, 256 threads, 4x4 register micro-tile; exact fp32 FMA accumulation in K order.
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, const GemmEpi e) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;     // loader: row 0..63, k offset 0,4,8,12
+    for (int k0 = 0; k0 < e.K; k0 += 16) {
+        {
+            const int gm = m0 + lr, gn = n0 + lr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gk = k0 + lk + j;
+                As[lk + j][lr] = (gm < e.M && gk < e.K) ? A[(size_t)gm * lda + gk] : 0.f;
+                Ws[lk + j][lr] = (gn < e.N && gk < e.K) ? W[(size_t)gn * ldw + gk] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = reinterpret_cast<float*>(e.C);
+    const float* R = reinterpret_cast<const float*>(e.residual);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= e.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= e.N) continue;
+            float v = acc[i][j];
+            if (e.bias) v += e.bias[gn];
+            if (e.relu) v = fmaxf(v, 0.f);
+            if (R) v += R[(size_t)gm * e.ldr + gn];
+            C[(size_t)gm * e.ldc + gn] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: rows x cols (cols contiguous), row pitch ld elements, box = box_rows x 64 cols, 128B swizzle
+static int make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return DTLR_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for %dx%d ld=%d", (int)r, rows, cols, ld);
+        return DTLR_ERR_CUDA;
+    }
+    return DTLR_OK;
+}
+
+template <int BN, int STAGES, typename OutT>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st) {
+    using S = GemmSmem<BN, STAGES>;
+    auto k = gemm_bf16_tcgen05_kernel<BN, STAGES, OutT>;
+    DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    dim3 grid((e.M + GEMM_BM - 1) / GEMM_BM, (e.N + BN - 1) / BN);
+    k<<<grid, 192, S::TOTAL, st>>>(ta, tb, e);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+}  // namespace dtlr
+
+using namespace dtlr;
+
+extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
+                         int ldr, void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu,
+                         void* stream) {
+    DTLR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
+    DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu};
+    if (in_dtype == DTLR_F32) {
+        DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
+        dim3 grid((M + 63) / 64, (N + 63) / 64);
+        sgemm_kernel<<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)W, ldw, e);
+        DTLR_CHECK_LAUNCH();
+        return DTLR_OK;
+    }
+    DTLR_CHECK_ARG(in_dtype == DTLR_BF16, "gemm: operands must be f32 or bf16");
+    DTLR_CHECK_ARG(out_dtype == DTLR_BF16 || out_dtype == DTLR_F32, "gemm: output must be bf16 or f32");
+    DTLR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0,
+                   "gemm: bf16 operands need 16-byte aligned rows (lda=%d ldw=%d)", lda, ldw);
+    CUtensorMap ta, tb;
+    int rc;
+    if (N > 64) {
+        if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
+        if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 128))) return rc;
+        return out_dtype == DTLR_BF16 ? launch_tc<128, 3, __nv_bfloat16>(ta, tb, e, st) : launch_tc<128, 3, float>(ta, tb, e, st);
+    }
+    if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 64))) return rc;
+    return out_dtype == DTLR_BF16 ? launch_tc<64, 4, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 4, float>(ta, tb, e, st);
+}

@@ -66,6 +66,22 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
                        void* grad_attn, int B, int S, int M, int D, int L, int Lq, int P, int dtype,
                        void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense contraction with fused epilogue:  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N])
+ *
+ * Replaces every torch.nn.Linear / F.linear call on the path (cuBLAS in the reference):
+ *   models/dino/ops/modules/ms_deform_attn.py:55-58,94,98,99,125; models/dino/deformable_transformer.py:787-790,
+ *   804-808,852-855,876-880,326,341; models/dino/utils.py:110-122 (MLP); nn.MultiheadAttention in/out projections
+ *   (deformable_transformer.py:847); and, on NHWC activations, the 1x1 convolutions of backbone.py / dino.py:118-125.
+ *
+ * A dev [M,lda], W dev [N,ldw] (both K contiguous), bias dev fp32 [N] or NULL, residual dev [M,ldr] (dtype of C) or
+ * NULL, C dev [M,ldc].  in_dtype DTLR_BF16: tcgen05 tensor-core path (fp32 accumulate), out_dtype BF16 or F32,
+ * rows 16-byte aligned (lda,ldw multiples of 8).  in_dtype DTLR_F32: exact-fp32 SIMT path (parity mode), out F32.
+ */
+int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
+              void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,67 @@
+"""GPU: the tcgen05 bf16 GEMM and the fp32 SIMT GEMM (dtlr_gemm) against torch fp32/fp64 matmul of the same operands
+(floating-point kernel -> plain torch reference, tolerance stated per case)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (M, N, K) -- SURVEY.md appendix C shapes (per image x small batch) + ragged tails
+    (912 * 2, 256, 256), (900 * 2, 2048, 256), (912 * 2, 256, 2048), (900, 384, 256), (900, 768, 256),
+    (900, 256, 512), (912, 166, 256), (900, 4, 256), (130, 64, 64), (1, 256, 256), (257, 200, 72), (640, 256, 512),
+]
+
+
+def _mk(M, N, K, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, K, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn(N, device="cuda", generator=g)
+    return a, w, bias
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_bf16_tcgen05(M, N, K, out_dtype):
+    from dtlr_b200 import ops
+    if K % 8:
+        pytest.skip("bf16 rows must be 16-byte aligned")
+    a, w, bias = _mk(M, N, K, torch.bfloat16, M + N + K)
+    ref = a.double() @ w.double().T + bias.double()
+    out = ops.gemm(a, w, bias, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 1e-4      # bf16 output rounding vs fp32 accumulate only
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err
+    # relu + residual epilogue
+    res = torch.randn(M, N, device="cuda").to(out_dtype)
+    out2 = ops.gemm(a, w, bias, residual=res, relu=True, out_dtype=out_dtype)
+    ref2 = torch.relu(ref) + res.double()
+    err2 = (out2.double() - ref2).abs().max().item() / ref2.abs().max().item()
+    assert err2 < tol, err2
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_fp32_simt(M, N, K):
+    from dtlr_b200 import ops
+    a, w, bias = _mk(M, N, K, torch.float32, M * 3 + N + K)
+    ref = a.double() @ w.double().T + bias.double()
+    out = ops.gemm(a, w, bias)
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+    res = torch.randn(M, N, device="cuda")
+    out2 = ops.gemm(a, w, None, residual=res, relu=True)
+    ref2 = torch.relu(a.double() @ w.double().T) + res.double()
+    assert (out2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 1e-5
+
+
+def test_strided_operands_and_output():
+    """activations are often column slices of a wider buffer (fused QKV etc.)"""
+    from dtlr_b200 import ops
+    big = torch.randn(300, 1024, device="cuda").bfloat16()
+    a = big[:, 256:512]
+    w = (torch.randn(128, 256, device="cuda") / 16).bfloat16()
+    outbuf = torch.zeros(300, 512, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, None, out=outbuf[:, 128:256])
+    ref = a.float() @ w.float().T
+    assert (outbuf[:, 128:256].float() - ref).abs().max() / ref.abs().max() < 2e-2
+    assert outbuf[:, :128].abs().sum() == 0 and outbuf[:, 256:].abs().sum() == 0
