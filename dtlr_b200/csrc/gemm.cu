@@ -108,7 +108,7 @@ struct GemmEpi {
     void* C;                 // [M, ldc]
     int ldr, ldc;
     int M, N, K;
-    int relu;
+    int relu;                // 0 none, 1 ReLU before the residual add, 2 ReLU after it (ResNet bottleneck)
 };
 
 constexpr int GEMM_BM = 128;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col
         for (int j = 0; j < 32; ++j)
             if (j < ncol) v[j] += __ldg(e.bias + col0 + j);
     }
-    if (e.relu) {
+    if (e.relu == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
@@ -152,6 +152,10 @@ __device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col
                         v[j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
                     }
                 }
+            }
+            if (e.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -172,6 +176,10 @@ __device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col
                     v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                 }
             }
+            if (e.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -182,6 +190,7 @@ __device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col
             if (j < ncol) {
                 float x = v[j];
                 if (rrow) x += (float)rrow[j];
+                if (e.relu == 2) x = fmaxf(x, 0.f);
                 crow[j] = (OutT)x;
             }
         }
@@ -334,8 +343,9 @@ sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, 
             if (gn >= e.N) continue;
             float v = acc[i][j];
             if (e.bias) v += e.bias[gn];
-            if (e.relu) v = fmaxf(v, 0.f);
+            if (e.relu == 1) v = fmaxf(v, 0.f);
             if (R) v += R[(size_t)gm * e.ldr + gn];
+            if (e.relu == 2) v = fmaxf(v, 0.f);
             C[(size_t)gm * e.ldc + gn] = v;
         }
     }

@@ -1,0 +1,600 @@
+// dtlr_b200 -- the non-GEMM kernels of the DINO forward (all HBM-bound elementwise / small-reduction work):
+// im2col (NHWC), max-pool, GroupNorm, sine position embedding, residual LayerNorm, deformable-attention prologue
+// (softmax + sampling locations), proposal generation, sine query embedding, iterative box refinement, row max.
+// Each kernel states the reference lines it restates.  T is the activation type (float = parity, bf16 = throughput);
+// statistics and transcendental math are always fp32.
+#include "common.cuh"
+
+namespace dtlr {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 8 consecutive channels <-> 8 floats
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 o;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- im2col
+// NHWC (or NCHW fp32 for the network input) -> patch matrix [B*Ho*Wo, ldo], K ordered (kh, kw, cin), zero padding.
+// Makes every k>1 / strided convolution of the ResNet-50 trunk (torchvision resnet50 as wrapped by reference
+// models/dino/backbone.py:109-128) and of input_proj[3] (dino.py:126-135) a dtlr_gemm call.
+template <typename TI, typename TO, bool NCHW_IN>
+__global__ void im2col_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C, int KH, int KW,
+                              int stride, int pad, int Ho, int Wo, int ldo) {
+    const int K = KH * KW * C;
+    const long long total = (long long)B * Ho * Wo * ldo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ldo);
+        const long long r = i / ldo;
+        float v = 0.f;
+        if (k < K) {
+            const int c = k % C, kw = (k / C) % KW, kh = k / (C * KW);
+            const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+            const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+                const size_t idx = NCHW_IN ? (((size_t)b * C + c) * H + hi) * W + wi : (((size_t)b * H + hi) * W + wi) * C + c;
+                v = ldf<TI>(x + idx);
+            }
+        }
+        stf<TO>(out + i, v);
+    }
+}
+
+// 8-channel vectorised variant for NHWC inputs with C % 8 == 0 (every conv except the stem)
+template <typename T>
+__global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int KH, int KW,
+                                   int stride, int pad, int Ho, int Wo) {
+    const int C8 = C / 8;
+    const int K8 = KH * KW * C8;
+    const long long total = (long long)B * Ho * Wo * K8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K8);
+        const long long r = i / K8;
+        const int c8 = k % C8, kw = (k / C8) % KW, kh = k / (C8 * KW);
+        const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+        const int hi = ho * stride - pad + kh, wi = wo * stride - pad + kw;
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) ld8<T>(x + ((((size_t)b * H + hi) * W + wi) * C + c8 * 8), v);
+        st8<T>(out + (size_t)i * 8, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- max-pool 3x3 s2 p1 (NHWC)
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
+    const int C8 = C / 8;
+    const long long total = (long long)B * Ho * Wo * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const long long r = i / C8;
+        const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+        for (int dh = 0; dh < 3; ++dh)
+            for (int dw = 0; dw < 3; ++dw) {
+                const int hi = ho * 2 - 1 + dh, wi = wo * 2 - 1 + dw;
+                if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+                float v[8];
+                ld8<T>(x + ((((size_t)b * H + hi) * W + wi) * C + c8 * 8), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+            }
+        st8<T>(out + (size_t)i * 8, m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm(32, C) on NHWC
+// reference models/dino/dino.py:121-124 (nn.GroupNorm(32, hidden_dim), eps 1e-5) applied to one feature level; the
+// result is written straight into the level's slice of the flattened token buffer (deformable_transformer.py:278-288).
+// grid (groups, B); x [B, HW, C] (fp32 from the projection GEMM), out rows b*out_stride_b + hw.
+template <typename TO>
+__global__ void groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 TO* __restrict__ out, int HW, int C, int G, long long out_stride_b, float eps) {
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int cpg = C / G;
+    const float* xb = x + (size_t)b * HW * C + g * cpg;
+    const int n = HW * cpg;
+    float s = 0.f, ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = xb[(size_t)(i / cpg) * C + (i % cpg)];
+        s += v;
+    }
+    __shared__ float red[32];
+    __shared__ float stat[2];
+    s = warp_sum_f(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum_f(t);
+        if (threadIdx.x == 0) stat[0] = t / n;
+    }
+    __syncthreads();
+    const float mean = stat[0];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = xb[(size_t)(i / cpg) * C + (i % cpg)] - mean;
+        ss += d * d;
+    }
+    ss = warp_sum_f(ss);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum_f(t);
+        if (threadIdx.x == 0) stat[1] = rsqrtf(t / n + eps);
+    }
+    __syncthreads();
+    const float rstd = stat[1];
+    TO* ob = out + (size_t)b * out_stride_b * C + g * cpg;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i % cpg;
+        const size_t off = (size_t)(i / cpg) * C + c;
+        stf<TO>(ob + off, (xb[off] - mean) * rstd * gamma[g * cpg + c] + beta[g * cpg + c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- sine position embedding
+// reference models/dino/position_encoding.py:79-108 (+ level_embed, deformable_transformer.py:281-282).
+// mask [B,H,W] uint8 (1 = padding); out rows b*out_stride_b + (y*W+x), C = 2*npf channels: [pos_y | pos_x].
+template <typename TO>
+__global__ void pos_sine_kernel(const unsigned char* __restrict__ mask, const float* __restrict__ level_embed,
+                                TO* __restrict__ out, int B, int H, int W, int npf, float temp_h, float temp_w,
+                                long long out_stride_b) {
+    const int C = 2 * npf;
+    const long long total = (long long)B * H * W;
+    const long long tok = blockIdx.x;
+    if (tok >= total) return;
+    const int x = (int)(tok % W), y = (int)((tok / W) % H), b = (int)(tok / ((long long)W * H));
+    const unsigned char* mb = mask + (size_t)b * H * W;
+    __shared__ float emb[2];
+    if (threadIdx.x == 0) {
+        float cy = 0.f, ty = 0.f, cx = 0.f, tx = 0.f;
+        for (int i = 0; i < H; ++i) { const float nm = mb[i * W + x] ? 0.f : 1.f; ty += nm; if (i <= y) cy += nm; }
+        for (int j = 0; j < W; ++j) { const float nm = mb[y * W + j] ? 0.f : 1.f; tx += nm; if (j <= x) cx += nm; }
+        const float two_pi = 6.283185307179586f;
+        emb[0] = cy / (ty + 1e-6f) * two_pi;
+        emb[1] = cx / (tx + 1e-6f) * two_pi;
+    }
+    __syncthreads();
+    TO* o = out + ((size_t)b * out_stride_b + (size_t)y * W + x) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bool is_x = c >= npf;
+        const int i = is_x ? c - npf : c;
+        const float t = is_x ? temp_w : temp_h;
+        const float dim_t = powf(t, 2.f * (float)(i / 2) / (float)npf);
+        const float a = (is_x ? emb[1] : emb[0]) / dim_t;
+        const float v = (i & 1) ? cosf(a) : sinf(a);
+        stf<TO>(o + c, v + (level_embed ? level_embed[c] : 0.f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- (residual +) LayerNorm, C = 256
+// reference nn.LayerNorm(256) eps 1e-5 after every attention / FFN block (deformable_transformer.py:813-814,806-807,
+// 906-907,956-957,878-879), enc_output_norm (:326) and decoder.norm (:758).  One warp per row, 8 channels per lane.
+// y = LN(x (+ res)); optional second output y2 = y + add2 (the "+pos" query of the next block).
+template <typename T>
+__global__ void add_layernorm256_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, T* __restrict__ y, const T* __restrict__ add2,
+                                        T* __restrict__ y2, int rows, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t off = (size_t)row * 256 + lane * 8;
+    float v[8];
+    ld8<T>(x + off, v);
+    if (res) {
+        float r[8];
+        ld8<T>(res + off, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    const float mean = warp_sum_f(s) * (1.f / 256.f);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; ss += d * d; }
+    const float rstd = rsqrtf(warp_sum_f(ss) * (1.f / 256.f) + eps);
+    float g[8], bt[8], o[8];
+    ld8<float>(gamma + lane * 8, g);
+    ld8<float>(beta + lane * 8, bt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (v[k] - mean) * rstd * g[k] + bt[k];
+    st8<T>(y + off, o);
+    if (y2) {
+        float a[8];
+        ld8<T>(add2 + off, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += o[k];
+        st8<T>(y2 + off, a);
+    }
+}
+
+// out = a + b (8-wide), optionally zeroing rows where rowmask != 0 (value.masked_fill, ms_deform_attn.py:95-96)
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float x[8], y[8];
+        ld8<T>(a + i * 8, x);
+        ld8<T>(b + i * 8, y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] += y[k];
+        st8<T>(out + i * 8, x);
+    }
+}
+template <typename T>
+__global__ void zero_masked_rows_kernel(T* __restrict__ x, const unsigned char* __restrict__ rowmask, long long rows, int C8) {
+    const long long total = rows * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (rowmask[i / C8]) {
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            st8<T>(x + i * 8, z);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- MSDA prologue
+// reference ops/modules/ms_deform_attn.py:98-108: softmax over the L*P attention logits of each head and
+//   2-coord refs (encoder): loc = ref_l + off / (W_l, H_l)
+//   4-coord refs (decoder): loc = ref_l[:2] + off / P * ref_l[2:] * 0.5
+// with ref_l = ref * valid_ratio_l (deformable_transformer.py:491, 686-687).
+// proj [rows, ld] fp32: columns [0, M*L*P*2) offsets (m,l,p,xy), then M*L*P logits.  One thread per (row, head).
+struct PrepLevels { int n; int H[8], W[8]; };
+__global__ void msda_prep_kernel(const float* __restrict__ proj, int ld, const float* __restrict__ ref, int RD,
+                                 const float* __restrict__ valid_ratios, float* __restrict__ loc, float* __restrict__ attn,
+                                 const __grid_constant__ PrepLevels lv, int B, int Lq, int M, int P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Lq * M;
+    if (i >= total) return;
+    const int m = (int)(i % M);
+    const long long row = i / M;
+    const int b = (int)(row / Lq);
+    const int L = lv.n, LP = L * P;
+    const float* pr = proj + (size_t)row * ld;
+    const float* off = pr + (size_t)m * LP * 2;
+    const float* lg = pr + (size_t)M * LP * 2 + (size_t)m * LP;
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float den = 0.f;
+    for (int k = 0; k < LP; ++k) den += expf(lg[k] - mx);
+    const float inv = 1.f / den;
+    const float* rf = ref + (size_t)row * RD;
+    float* lo = loc + (size_t)i * LP * 2;
+    float* at = attn + (size_t)i * LP;
+    for (int l = 0; l < L; ++l) {
+        const float vx = valid_ratios[((size_t)b * L + l) * 2], vy = valid_ratios[((size_t)b * L + l) * 2 + 1];
+        const float rx = rf[0] * vx, ry = rf[1] * vy;
+        for (int p = 0; p < P; ++p) {
+            const int k = l * P + p;
+            const float ox = off[2 * k], oy = off[2 * k + 1];
+            float x, y;
+            if (RD == 2) {
+                x = rx + ox / (float)lv.W[l];
+                y = ry + oy / (float)lv.H[l];
+            } else {
+                x = rx + ox / (float)P * (rf[2] * vx) * 0.5f;
+                y = ry + oy / (float)P * (rf[3] * vy) * 0.5f;
+            }
+            lo[2 * k] = x;
+            lo[2 * k + 1] = y;
+            at[k] = expf(lg[k] - mx) * inv;
+        }
+    }
+}
+
+// encoder reference points before the per-level valid-ratio product (deformable_transformer.py:479-490):
+// ref[b, tok] = ((x+0.5)/(vr_w*W_l), (y+0.5)/(vr_h*H_l)) for the token's own level l.
+__global__ void enc_ref_kernel(const float* __restrict__ valid_ratios, float* __restrict__ ref, const __grid_constant__ PrepLevels lv,
+                               int B, int S) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * S) return;
+    const int b = (int)(i / S);
+    int t = (int)(i % S), l = 0;
+    while (l < lv.n - 1 && t >= lv.H[l] * lv.W[l]) { t -= lv.H[l] * lv.W[l]; ++l; }
+    const int y = t / lv.W[l], x = t % lv.W[l];
+    const float vx = valid_ratios[((size_t)b * lv.n + l) * 2], vy = valid_ratios[((size_t)b * lv.n + l) * 2 + 1];
+    ref[i * 2] = ((float)x + 0.5f) / (vx * (float)lv.W[l]);
+    ref[i * 2 + 1] = ((float)y + 0.5f) / (vy * (float)lv.H[l]);
+}
+
+// ---------------------------------------------------------------------------------------------- two-stage proposals
+// reference models/dino/utils.py:15-64: anchor (cx,cy,w,h) per token, validity, logit; zeroes invalid/padded memory rows.
+// valid_hw [B, L, 2] = (valid_H, valid_W) counts from the level masks.
+template <typename T>
+__global__ void proposals_kernel(const T* __restrict__ memory, const unsigned char* __restrict__ pad, const int* __restrict__ valid_hw,
+                                 T* __restrict__ out_memory, float* __restrict__ proposals, const __grid_constant__ PrepLevels lv,
+                                 int B, int S, int C, float default_hw) {
+    const long long tok = blockIdx.x;
+    if (tok >= (long long)B * S) return;
+    const int b = (int)(tok / S);
+    int t = (int)(tok % S), l = 0;
+    while (l < lv.n - 1 && t >= lv.H[l] * lv.W[l]) { t -= lv.H[l] * lv.W[l]; ++l; }
+    const int y = t / lv.W[l], x = t % lv.W[l];
+    const float vh = (float)valid_hw[((size_t)b * lv.n + l) * 2], vw = (float)valid_hw[((size_t)b * lv.n + l) * 2 + 1];
+    float p[4];
+    p[0] = ((float)x + 0.5f) / vw;
+    p[1] = ((float)y + 0.5f) / vh;
+    p[2] = p[3] = default_hw * exp2f((float)l);
+    bool valid = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid = valid && (p[k] > 0.01f) && (p[k] < 0.99f);
+    const bool keep = valid && !pad[tok];
+    if (threadIdx.x < 4) proposals[tok * 4 + threadIdx.x] = keep ? logf(p[threadIdx.x] / (1.f - p[threadIdx.x])) : INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        out_memory[tok * C + c] = keep ? memory[tok * C + c] : (T)0.f;
+}
+
+// row-wise max over the first N columns (two-stage class score, deformable_transformer.py:345)
+__global__ void rowmax_kernel(const float* __restrict__ x, int ld, int N, float* __restrict__ out, long long rows) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float m = -INFINITY;
+    for (int c = threadIdx.x & 31; c < N; c += 32) m = fmaxf(m, x[(size_t)row * ld + c]);
+    m = warp_max_f(m);
+    if ((threadIdx.x & 31) == 0) out[row] = m;
+}
+
+// ---------------------------------------------------------------------------------------------- decoder helpers
+// reference models/dino/utils.py:141-167 on ref*valid_ratio[level 0] (deformable_transformer.py:686-691):
+// (x,y,w,h) -> 512-dim sine embedding in order (y, x, w, h), T = 10000, scale 2*pi.  One block per query.
+template <typename TO>
+__global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, TO* __restrict__ out,
+                                  int B, int Q, int L) {
+    const long long row = blockIdx.x;
+    const int b = (int)(row / Q);
+    const float vx = valid_ratios[(size_t)b * L * 2], vy = valid_ratios[(size_t)b * L * 2 + 1];
+    const float* r = ref + row * 4;
+    const float comp[4] = {r[1] * vy, r[0] * vx, r[2] * vx, r[3] * vy};   // y, x, w, h
+    const float two_pi = 6.283185307179586f;
+    for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+        const int part = c >> 7, i = c & 127;
+        const float dim_t = powf(10000.f, 2.f * (float)(i / 2) / 128.f);
+        const float a = comp[part] * two_pi / dim_t;
+        stf<TO>(out + row * 512 + c, (i & 1) ? cosf(a) : sinf(a));
+    }
+}
+
+// new_ref = sigmoid(delta + inverse_sigmoid(ref)), eps 1e-3 (deformable_transformer.py:734-738, dino.py:343-345,
+// util/misc.py:575-579).  ref_is_logit: the reference is already in logit space (two-stage init: refpoint.sigmoid()).
+__global__ void box_refine_kernel(const float* __restrict__ delta, int ldd, const float* __restrict__ ref, float* __restrict__ out,
+                                  long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long row = i / 4;
+    const int c = (int)(i % 4);
+    float x = fminf(fmaxf(ref[i], 0.f), 1.f);
+    const float x1 = fmaxf(x, 1e-3f), x2 = fmaxf(1.f - x, 1e-3f);
+    const float z = delta[row * ldd + c] + logf(x1 / x2);
+    out[i] = 1.f / (1.f + expf(-z));
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.f / (1.f + expf(-x[i]));
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        stf<TO>(out + i, ldf<TI>(x + i));
+}
+
+static inline int grid_for(long long n, int threads) {
+    long long g = (n + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dtlr
+
+using namespace dtlr;
+
+#define DISPATCH_T(dtype, ...)                                          \
+    if ((dtype) == DTLR_F32) { using T = float; __VA_ARGS__ }           \
+    else if ((dtype) == DTLR_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+    else { set_error("unsupported dtype %d", (int)(dtype)); return DTLR_ERR_INVALID; }
+
+extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+                           int Ho, int Wo, int ldo, int in_dtype, int out_dtype, int nchw_input, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DTLR_CHECK_ARG(ldo >= KH * KW * C, "im2col: ldo too small");
+    const long long total = (long long)B * Ho * Wo * ldo;
+    if (total == 0) return DTLR_OK;
+    if (!nchw_input && in_dtype == out_dtype && C % 8 == 0 && ldo == KH * KW * C) {
+        const long long t8 = total / 8;
+        DISPATCH_T(in_dtype, im2col_vec8_kernel<T><<<grid_for(t8, 256), 256, 0, st>>>((const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo);)
+    } else if (nchw_input && in_dtype == DTLR_F32) {
+        DISPATCH_T(out_dtype, im2col_kernel<float, T, true><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
+    } else if (!nchw_input && in_dtype == out_dtype) {
+        DISPATCH_T(in_dtype, im2col_kernel<T, T, false><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
+    } else {
+        set_error("im2col: unsupported dtype/layout combination");
+        return DTLR_ERR_UNSUPPORTED;
+    }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_maxpool3x3s2(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, int dtype, void* stream) {
+    DTLR_CHECK_ARG(C % 8 == 0, "maxpool: C must be a multiple of 8");
+    const long long total = (long long)B * Ho * Wo * (C / 8);
+    if (total == 0) return DTLR_OK;
+    DISPATCH_T(dtype, maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, B, H, W, C, Ho, Wo);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_groupnorm(const float* x, const float* gamma, const float* beta, void* out, int B, int HW, int C, int G,
+                              long long out_stride_b, float eps, int out_dtype, void* stream) {
+    DTLR_CHECK_ARG(C % G == 0, "groupnorm: C %% G != 0");
+    if (B == 0 || HW == 0) return DTLR_OK;
+    dim3 grid(G, B);
+    DISPATCH_T(out_dtype, groupnorm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (T*)out, HW, C, G, out_stride_b, eps);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_pos_sine(const unsigned char* mask, const float* level_embed, void* out, int B, int H, int W, int npf,
+                             float temp_h, float temp_w, long long out_stride_b, int out_dtype, void* stream) {
+    const long long total = (long long)B * H * W;
+    if (total == 0) return DTLR_OK;
+    DISPATCH_T(out_dtype, pos_sine_kernel<T><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>(mask, level_embed, (T*)out, B, H, W, npf, temp_h, temp_w, out_stride_b);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* y, const void* add2,
+                                  void* y2, long long rows, int C, float eps, int dtype, void* stream) {
+    DTLR_CHECK_ARG(C == 256, "add_layernorm: only C=256 (d_model of every DTLR config) is implemented, got %d", C);
+    if (rows == 0) return DTLR_OK;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    DISPATCH_T(dtype, add_layernorm256_kernel<T><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
+    DTLR_CHECK_ARG(n % 8 == 0, "add: n must be a multiple of 8");
+    if (n == 0) return DTLR_OK;
+    DISPATCH_T(dtype, add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n / 8);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_zero_masked_rows(void* x, const unsigned char* rowmask, long long rows, int C, int dtype, void* stream) {
+    DTLR_CHECK_ARG(C % 8 == 0, "zero_masked_rows: C %% 8 != 0");
+    if (rows == 0) return DTLR_OK;
+    DISPATCH_T(dtype, zero_masked_rows_kernel<T><<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((T*)x, rowmask, rows, C / 8);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+static int fill_prep_levels(PrepLevels& lv, const int64_t* shapes, int L) {
+    DTLR_CHECK_ARG(L >= 1 && L <= 8, "n_levels %d not in [1,8]", L);
+    lv.n = L;
+    for (int l = 0; l < L; ++l) { lv.H[l] = (int)shapes[2 * l]; lv.W[l] = (int)shapes[2 * l + 1]; }
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_msda_prep(const float* proj, int ld, const float* ref, int ref_dim, const float* valid_ratios,
+                              const int64_t* shapes, int L, float* loc, float* attn, int B, int Lq, int M, int P, void* stream) {
+    DTLR_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "msda_prep: reference points must have 2 or 4 coordinates");
+    PrepLevels lv;
+    int rc = fill_prep_levels(lv, shapes, L);
+    if (rc) return rc;
+    const long long total = (long long)B * Lq * M;
+    if (total == 0) return DTLR_OK;
+    msda_prep_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(proj, ld, ref, ref_dim, valid_ratios, loc, attn, lv, B, Lq, M, P);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_enc_ref_points(const float* valid_ratios, const int64_t* shapes, int L, float* ref, int B, int S, void* stream) {
+    PrepLevels lv;
+    int rc = fill_prep_levels(lv, shapes, L);
+    if (rc) return rc;
+    const long long total = (long long)B * S;
+    if (total == 0) return DTLR_OK;
+    enc_ref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(valid_ratios, ref, lv, B, S);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_encoder_proposals(const void* memory, const unsigned char* pad, const int* valid_hw, const int64_t* shapes, int L,
+                                      void* out_memory, float* proposals, int B, int S, int C, float default_hw, int dtype, void* stream) {
+    PrepLevels lv;
+    int rc = fill_prep_levels(lv, shapes, L);
+    if (rc) return rc;
+    const long long total = (long long)B * S;
+    if (total == 0) return DTLR_OK;
+    DISPATCH_T(dtype, proposals_kernel<T><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>((const T*)memory, pad, valid_hw, (T*)out_memory, proposals, lv, B, S, C, default_hw);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long rows, void* stream) {
+    if (rows == 0) return DTLR_OK;
+    rowmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, ld, N, out, rows);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream) {
+    const long long rows = (long long)B * Q;
+    if (rows == 0) return DTLR_OK;
+    DISPATCH_T(out_dtype, sine_embed_kernel<T><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(ref, valid_ratios, (T*)out, B, Q, L);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_box_refine(const float* delta, int ldd, const float* ref, float* out, long long rows, void* stream) {
+    const long long n4 = rows * 4;
+    if (n4 == 0) return DTLR_OK;
+    box_refine_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(delta, ldd, ref, out, n4);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_sigmoid(const float* x, float* out, long long n, void* stream) {
+    if (n == 0) return DTLR_OK;
+    sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype, void* stream) {
+    if (n == 0) return DTLR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == DTLR_F32 && out_dtype == DTLR_BF16)
+        cast_kernel<float, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, n);
+    else if (in_dtype == DTLR_BF16 && out_dtype == DTLR_F32)
+        cast_kernel<__nv_bfloat16, float><<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (float*)out, n);
+    else if (in_dtype == out_dtype && in_dtype == DTLR_F32)
+        cast_kernel<float, float><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (float*)out, n);
+    else if (in_dtype == out_dtype && in_dtype == DTLR_BF16)
+        cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
+    else { set_error("cast: unsupported dtypes"); return DTLR_ERR_INVALID; }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}

@@ -1,0 +1,308 @@
+"""Fused inference path of the DINO forward: every compute step is a libdtlr_b200 kernel (C ABI, include/dtlr_b200.h).
+
+Layout in HBM (DESIGN.md §data layout): activations are token-major / NHWC matrices [rows, channels] in the compute
+dtype T (bf16 throughput mode, fp32 parity mode); convolutions are (im2col +) GEMM with FrozenBatchNorm folded into
+weight and bias; the multi-level feature maps are written by the GroupNorm kernel directly into the flattened
+(B, S, 256) token tensor; sampling locations / attention weights / boxes / scores stay fp32.
+
+The engine reads the parameters of the nn.Module tree in dtlr_b200/dino.py (same state-dict as the reference) and
+re-packs them once per (dtype, parameter version).  PyTorch is used for allocation, the current stream, a handful of
+index bookkeeping ops on tiny tensors (masks, top-k, gathers) and nothing else.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import msda as msda_mod
+from . import ops
+
+
+def _fold_conv_bn(conv, bn, dtype, pad_k_to=8):
+    """FrozenBatchNorm (reference backbone.py:62-72) folded into the conv: w' = w*scale, b' = bias - mean*scale;
+    weight reordered to [Cout, kh, kw, Cin] (im2col K order)."""
+    w = conv.weight.detach().float()
+    scale, bias = bn.scale_bias()
+    w = (w * scale.float().view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    K = w.shape[1]
+    if K % pad_k_to:
+        w = F.pad(w, (0, pad_k_to - K % pad_k_to))
+    return w.to(dtype).contiguous(), bias.detach().float().contiguous()
+
+
+def _lin(linear, dtype):
+    return linear.weight.detach().to(dtype).contiguous(), linear.bias.detach().float().contiguous()
+
+
+class InferenceEngine:
+    def __init__(self, model):
+        self.model = model
+        self._packed = None
+        self._key = None
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _pack_key(self, dtype, device):
+        ver = 0
+        for p in self.model.parameters():
+            ver += p._version
+        for b in self.model.buffers():
+            ver += b._version
+        return (dtype, str(device), ver)
+
+    def packed(self, dtype, device):
+        key = self._pack_key(dtype, device)
+        if self._packed is not None and self._key == key:
+            return self._packed
+        m = self.model
+        tr = m.transformer
+        body = m.backbone[0].body
+        P = {}
+        P["stem"] = _fold_conv_bn(body.conv1, body.bn1, dtype)
+        blocks = []
+        for li in range(1, 5):
+            for blk in getattr(body, "layer%d" % li):
+                d = {"c1": _fold_conv_bn(blk.conv1, blk.bn1, dtype), "c2": _fold_conv_bn(blk.conv2, blk.bn2, dtype),
+                     "c3": _fold_conv_bn(blk.conv3, blk.bn3, dtype), "stride": blk.stride, "ds": None, "layer": li}
+                if blk.downsample is not None:
+                    d["ds"] = _fold_conv_bn(blk.downsample[0], blk.downsample[1], dtype)
+                blocks.append(d)
+        P["blocks"] = blocks
+        P["return_layers"] = list(body.return_layers)
+        proj = []
+        for seq in m.input_proj:
+            conv, gn = seq[0], seq[1]
+            w = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1)
+            proj.append({"w": w.to(dtype).contiguous(), "b": conv.bias.detach().float().contiguous(),
+                         "gw": gn.weight.detach().float().contiguous(), "gb": gn.bias.detach().float().contiguous(),
+                         "k": conv.kernel_size[0], "stride": conv.stride[0], "pad": conv.padding[0], "groups": gn.num_groups})
+        P["proj"] = proj
+        P["level_embed"] = tr.level_embed.detach().float().contiguous()
+
+        def pack_msda(a):
+            w_oa = torch.cat([a.sampling_offsets.weight, a.attention_weights.weight], 0).detach().to(dtype).contiguous()
+            b_oa = torch.cat([a.sampling_offsets.bias, a.attention_weights.bias], 0).detach().float().contiguous()
+            return {"val": _lin(a.value_proj, dtype), "oa": (w_oa, b_oa), "out": _lin(a.output_proj, dtype),
+                    "M": a.n_heads, "L": a.n_levels, "P": a.n_points}
+
+        def ln(n):
+            return n.weight.detach().float().contiguous(), n.bias.detach().float().contiguous()
+
+        P["enc"] = [{"attn": pack_msda(l.self_attn), "ln1": ln(l.norm1), "l1": _lin(l.linear1, dtype),
+                     "l2": _lin(l.linear2, dtype), "ln2": ln(l.norm2)} for l in tr.encoder.layers]
+        P["enc_output"] = _lin(tr.enc_output, dtype)
+        P["enc_output_norm"] = ln(tr.enc_output_norm)
+        P["enc_cls"] = _lin(tr.enc_out_class_embed, dtype)
+        P["enc_bbox"] = [_lin(l, dtype) for l in tr.enc_out_bbox_embed.layers]
+        dec = []
+        C = tr.d_model
+        for l in tr.decoder.layers:
+            sa = l.self_attn
+            wi, bi = sa.in_proj_weight.detach(), sa.in_proj_bias.detach()
+            dec.append({"ca": pack_msda(l.cross_attn), "ln1": ln(l.norm1),
+                        "qk": (wi[:2 * C].to(dtype).contiguous(), bi[:2 * C].float().contiguous()),
+                        "v": (wi[2 * C:].to(dtype).contiguous(), bi[2 * C:].float().contiguous()),
+                        "o": _lin(sa.out_proj, dtype), "heads": sa.num_heads, "ln2": ln(l.norm2),
+                        "l1": _lin(l.linear1, dtype), "l2": _lin(l.linear2, dtype), "ln3": ln(l.norm3)})
+        P["dec"] = dec
+        P["dec_norm"] = ln(tr.decoder.norm)
+        P["rph"] = [_lin(l, dtype) for l in tr.decoder.ref_point_head.layers]
+        P["bbox"] = [[_lin(l, dtype) for l in be.layers] for be in m.bbox_embed]
+        P["cls"] = [_lin(ce, dtype) for ce in m.class_embed]
+        P["tgt_embed"] = tr.tgt_embed.weight.detach().to(dtype).contiguous()
+        self._packed, self._key = P, key
+        return P
+
+    # ------------------------------------------------------------------------------------------------ pieces
+    @staticmethod
+    def _mlp3(x, layers, out_f32_last=True):
+        h = ops.gemm(x, *layers[0], relu=1)
+        h = ops.gemm(h, *layers[1], relu=1)
+        return ops.gemm(h, *layers[2], out_dtype=torch.float32 if out_f32_last else None)
+
+    def _backbone(self, P, x, B, H, W, T):
+        col, Ho, Wo = ops.im2col(x, B, H, W, 3, 7, 7, 2, 3, T, nchw_input=True, ldo=P["stem"][0].shape[1])
+        y = ops.gemm(col, *P["stem"], relu=1)
+        y, Hc, Wc = ops.maxpool3x3s2(y, B, Ho, Wo, 64)
+        feats = []
+        cin = 64
+        nblk = len(P["blocks"])
+        for i, blk in enumerate(P["blocks"]):
+            s = blk["stride"]
+            a = ops.gemm(y, *blk["c1"], relu=1)
+            planes = blk["c1"][0].shape[0]
+            col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
+            bmid = ops.gemm(col, *blk["c2"], relu=1)
+            if blk["ds"] is not None:
+                sub = y if s == 1 else ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0]
+                idt = ops.gemm(sub, *blk["ds"])
+            else:
+                idt = y
+            y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2)
+            Hc, Wc, cin = Hn, Wn, planes * 4
+            last_of_layer = (i == nblk - 1) or (P["blocks"][i + 1]["layer"] != blk["layer"])
+            if last_of_layer and blk["layer"] in P["return_layers"]:
+                feats.append((y, Hc, Wc, cin))
+        return feats
+
+    def _msda(self, a, query, ref, ref_dim, value_src_or_value, pad_u8, vr, shapes_host, lsi_host, nlev, B, Lq, S, T,
+              precomputed_value=False):
+        M, Pn = a["M"], a["P"]
+        if precomputed_value:
+            val = value_src_or_value
+        else:
+            val = ops.gemm(value_src_or_value, *a["val"])
+            ops.zero_masked_rows_(val, pad_u8)
+        oa = ops.gemm(query, *a["oa"], out_dtype=torch.float32)
+        loc, attn = ops.msda_prep(oa, ref, vr, shapes_host, nlev, B, Lq, M, Pn)
+        core = msda_mod.msda_forward_raw(val.view(B, S, M, val.shape[1] // M), shapes_host, lsi_host, nlev, loc, attn)
+        return core.view(B * Lq, -1)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, samples, stages=None):
+        m = self.model
+        tr = m.transformer
+        T = m.compute_dtype
+        x = samples.tensors
+        mask = samples.mask
+        L.require_cuda(x, mask)
+        dev = x.device
+        x = x.float().contiguous()
+        B, _, H, W = x.shape
+        P = self.packed(T, dev)
+        d = tr.d_model
+        st = stages
+
+        with torch.cuda.device(dev):
+            feats = self._backbone(P, x, B, H, W, T)
+            if st is not None:
+                st["feats"] = [(f.view(B, h, w, c).permute(0, 3, 1, 2), h, w) for f, h, w, c in feats]
+
+            # ---- level geometry
+            nlev = len(P["proj"])
+            level_hw = [(h, w) for _, h, w, _ in feats]
+            extra_in = feats[-1]
+            for l in range(len(feats), nlev):
+                pj = P["proj"][l]
+                h_in, w_in = level_hw[-1] if l > len(feats) else (extra_in[1], extra_in[2])
+                level_hw.append(((h_in + 2 * pj["pad"] - pj["k"]) // pj["stride"] + 1, (w_in + 2 * pj["pad"] - pj["k"]) // pj["stride"] + 1))
+            S = sum(h * w for h, w in level_hw)
+            starts = [0]
+            for h, w in level_hw[:-1]:
+                starts.append(starts[-1] + h * w)
+            shapes_host = L.i64_host([v for hw in level_hw for v in hw])
+            lsi_host = L.i64_host(starts)
+
+            # ---- masks, valid ratios (tiny index bookkeeping; reference backbone.py:103, dino.py:304-307,
+            #      deformable_transformer.py:239-246)
+            masks = [F.interpolate(mask[None].float(), size=hw).to(torch.bool)[0] for hw in level_hw]
+            pad = torch.cat([mk.flatten(1) for mk in masks], 1).contiguous()
+            pad_u8 = pad.view(torch.uint8).reshape(-1)
+            vh = torch.stack([(~mk[:, :, 0]).sum(1) for mk in masks], 1)
+            vw = torch.stack([(~mk[:, 0, :]).sum(1) for mk in masks], 1)
+            hs_t = torch.tensor([hw[0] for hw in level_hw], device=dev, dtype=torch.float32)
+            ws_t = torch.tensor([hw[1] for hw in level_hw], device=dev, dtype=torch.float32)
+            vr = torch.stack([vw.float() / ws_t, vh.float() / hs_t], -1).contiguous()            # (B,L,2) = (w,h)
+            valid_hw = torch.stack([vh, vw], -1).to(torch.int32).contiguous()
+
+            # ---- input_proj + GroupNorm -> src ; sine PE + level embed -> pos
+            src = torch.empty((B * S, d), dtype=T, device=dev)
+            pos = torch.empty((B * S, d), dtype=T, device=dev)
+            prev = None
+            for l in range(nlev):
+                pj = P["proj"][l]
+                h, w = level_hw[l]
+                if l < len(feats):
+                    f, fh, fw, fc = feats[l]
+                    a_in = f
+                else:
+                    f, fh, fw, fc = (extra_in if l == len(feats) else prev)
+                    a_in = ops.im2col(f, B, fh, fw, fc, pj["k"], pj["k"], pj["stride"], pj["pad"], T)[0]
+                y = ops.gemm(a_in, pj["w"], pj["b"], out_dtype=torch.float32)
+                ops.groupnorm_into(y, pj["gw"], pj["gb"], src, B, h * w, d, pj["groups"], starts[l], S)
+                if l >= len(feats):
+                    prev = (src.view(B, S, d)[:, starts[l]:starts[l] + h * w].reshape(B * h * w, d), h, w, d)
+                pe = m.backbone[1]
+                ops.pos_sine_into(masks[l].contiguous().view(torch.uint8), P["level_embed"][l].contiguous(), pos, B, h, w,
+                                  pe.num_pos_feats, float(pe.temperatureH), float(pe.temperatureW), starts[l], S)
+            if st is not None:
+                st["src_flatten"], st["pos"] = src.view(B, S, d), pos.view(B, S, d)
+
+            # ---- encoder
+            ref_enc = ops.enc_ref_points(vr, shapes_host, nlev, B, S)
+            q = ops.add(src, pos)
+            for i, lyr in enumerate(P["enc"]):
+                core = self._msda(lyr["attn"], q, ref_enc, 2, src, pad_u8, vr, shapes_host, lsi_host, nlev, B, S, S, T)
+                if st is not None and i == 0:
+                    st["enc0_core"] = core.view(B, S, d)
+                x1 = ops.gemm(core, *lyr["attn"]["out"], residual=src)
+                s1 = ops.add_layernorm(x1, None, *lyr["ln1"])
+                hdn = ops.gemm(s1, *lyr["l1"], relu=1)
+                x2 = ops.gemm(hdn, *lyr["l2"], residual=s1)
+                if i + 1 < len(P["enc"]):
+                    src, q = ops.add_layernorm(x2, None, *lyr["ln2"], add2=pos)
+                else:
+                    src = ops.add_layernorm(x2, None, *lyr["ln2"])
+            memory = src
+            if st is not None:
+                st["memory"] = memory.view(B, S, d)
+
+            # ---- two-stage query selection (deformable_transformer.py:320-363)
+            Q = tr.num_queries
+            om, prop = ops.encoder_proposals(memory, pad_u8, valid_hw, shapes_host, nlev, B, S, d, tr.two_stage_default_hw)
+            omn = ops.add_layernorm(ops.gemm(om, *P["enc_output"]), None, *P["enc_output_norm"])
+            cls_unsel = ops.gemm(omn, *P["enc_cls"], out_dtype=torch.float32)
+            scores = ops.rowmax(cls_unsel, cls_unsel.shape[1]).view(B, S)
+            coord_unsel = (self._mlp3(omn, P["enc_bbox"]) + prop).view(B, S, 4)
+            topk = torch.topk(scores, Q, dim=1)[1]
+            if tr.debug_force_topk is not None:
+                topk = tr.debug_force_topk.to(dev)
+            if st is not None:
+                st["topk_scores"], st["topk_idx"] = scores, topk
+            refpoint = torch.gather(coord_unsel, 1, topk.unsqueeze(-1).expand(-1, -1, 4)).contiguous()
+            init_box_proposal = torch.gather(prop.view(B, S, 4), 1, topk.unsqueeze(-1).expand(-1, -1, 4)).sigmoid()
+            tgt_undetach = torch.gather(omn.view(B, S, d), 1, topk.unsqueeze(-1).expand(-1, -1, d)).contiguous()
+
+            # ---- decoder (deformable_transformer.py:652-766)
+            ref = ops.sigmoid(refpoint.view(B * Q, 4))
+            refs = [ref]
+            tgt = P["tgt_embed"][None].expand(B, -1, -1).reshape(B * Q, d).contiguous()
+            hs = []
+            for i, lyr in enumerate(P["dec"]):
+                sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
+                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1), *P["rph"][1])
+                qk_in = ops.add(tgt, qp)
+                qk = ops.gemm(qk_in, *lyr["qk"])
+                v = ops.gemm(tgt, *lyr["v"])
+                att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
+                x1 = ops.gemm(att, *lyr["o"], residual=tgt)
+                tgt, qca = ops.add_layernorm(x1, None, *lyr["ln2"], add2=qp)
+                core = self._msda(lyr["ca"], qca, ref, 4, memory, pad_u8, vr, shapes_host, lsi_host, nlev, B, Q, S, T)
+                if st is not None and i == 0:
+                    st["dec0_core"] = core.view(B, Q, d)
+                x2 = ops.gemm(core, *lyr["ca"]["out"], residual=tgt)
+                tgt = ops.add_layernorm(x2, None, *lyr["ln1"])
+                hdn = ops.gemm(tgt, *lyr["l1"], relu=1)
+                x3 = ops.gemm(hdn, *lyr["l2"], residual=tgt)
+                tgt = ops.add_layernorm(x3, None, *lyr["ln3"])
+                ref = ops.box_refine(self._mlp3(tgt, P["bbox"][i]), ref)
+                refs.append(ref)
+                hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"]))
+            if st is not None:
+                st["hs"] = [h_.view(B, Q, d) for h_ in hs]
+                st["refs"] = [r.view(B, Q, 4) for r in refs]
+
+            # ---- heads (dino.py:339-354)
+            n_dec = len(hs)
+            want = range(n_dec) if m.engine_outputs == "all" else [n_dec - 1]
+            coords, classes = {}, {}
+            for i in want:
+                coords[i] = ops.box_refine(self._mlp3(hs[i], P["bbox"][i]), refs[i]).view(B, Q, 4)
+                classes[i] = ops.gemm(hs[i], *P["cls"][i], out_dtype=torch.float32).view(B, Q, -1)
+            out = {"pred_logits": classes[n_dec - 1], "pred_boxes": coords[n_dec - 1]}
+            if m.aux_loss:
+                out["aux_outputs"] = [{"pred_logits": classes[i], "pred_boxes": coords[i]} for i in want if i != n_dec - 1]
+            interm_class = ops.gemm(tgt_undetach.view(B * Q, d), *P["enc_cls"], out_dtype=torch.float32).view(B, Q, -1)
+            out["interm_outputs"] = {"pred_logits": interm_class, "pred_boxes": refpoint.sigmoid()}
+            out["interm_outputs_for_matching_pre"] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
+            out["dn_meta"] = None
+            return out

@@ -6,7 +6,7 @@ from . import _lib as L
 
 
 def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
-    """C = act(a @ w.T + bias) (+ residual).  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
+    """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
     bias fp32 (N) or None, residual (M,N) of the output dtype or None."""
     L.require_cuda(a, w, bias, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
@@ -27,6 +27,142 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
-                               M, N, K, L.dtype_code(a), L.dtype_code(out), 1 if relu else 0, L.stream_ptr(a.device))
+                               M, N, K, L.dtype_code(a), L.dtype_code(out), int(relu), L.stream_ptr(a.device))
     L.check(rc, "dtlr_gemm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _call(name, *args):
+    L.check(getattr(L.lib(), name)(*args), name)
+
+
+def _p(t):
+    return L.ptr(t) if t is not None else None
+
+
+def _st(t):
+    return L.stream_ptr(t.device)
+
+
+def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=None):
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    K = KH * KW * C
+    ldo = ldo or K
+    out = torch.empty((B * Ho * Wo, ldo), dtype=out_dtype, device=x.device)
+    _call("dtlr_im2col", _p(x), _p(out), B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo, L.dtype_code(x),
+          L.dtype_code(out), 1 if nchw_input else 0, _st(x))
+    return out, Ho, Wo
+
+
+def maxpool3x3s2(x, B, H, W, C):
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = torch.empty((B * Ho * Wo, C), dtype=x.dtype, device=x.device)
+    _call("dtlr_maxpool3x3s2", _p(x), _p(out), B, H, W, C, Ho, Wo, L.dtype_code(x), _st(x))
+    return out, Ho, Wo
+
+
+def groupnorm_into(x_f32, gamma, beta, out, B, HW, C, G, row_offset, rows_per_batch, eps=1e-5):
+    """x_f32 [B*HW, C] fp32 -> out[b, row_offset + hw, :] of the (B, rows_per_batch, C) token buffer."""
+    import ctypes
+    dst = out.view(-1, C)[row_offset:]
+    _call("dtlr_groupnorm", _p(x_f32), _p(gamma), _p(beta), _p(dst), B, HW, C, G, ctypes.c_longlong(rows_per_batch),
+          ctypes.c_float(eps), L.dtype_code(out), _st(out))
+
+
+def pos_sine_into(mask_u8, level_embed, out, B, H, W, npf, temp_h, temp_w, row_offset, rows_per_batch):
+    import ctypes
+    C = 2 * npf
+    dst = out.view(-1, C)[row_offset:]
+    _call("dtlr_pos_sine", _p(mask_u8), _p(level_embed), _p(dst), B, H, W, npf, ctypes.c_float(temp_h),
+          ctypes.c_float(temp_w), ctypes.c_longlong(rows_per_batch), L.dtype_code(out), _st(out))
+
+
+def add_layernorm(x, res, gamma, beta, add2=None, eps=1e-5):
+    import ctypes
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    y2 = torch.empty_like(x) if add2 is not None else None
+    _call("dtlr_add_layernorm", _p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(add2), _p(y2), ctypes.c_longlong(rows), C,
+          ctypes.c_float(eps), L.dtype_code(x), _st(x))
+    return (y, y2) if add2 is not None else y
+
+
+def add(a, b):
+    import ctypes
+    out = torch.empty_like(a)
+    _call("dtlr_add", _p(a), _p(b), _p(out), ctypes.c_longlong(a.numel()), L.dtype_code(a), _st(a))
+    return out
+
+
+def zero_masked_rows_(x, rowmask_u8):
+    import ctypes
+    _call("dtlr_zero_masked_rows", _p(x), _p(rowmask_u8), ctypes.c_longlong(x.shape[0]), x.shape[1], L.dtype_code(x), _st(x))
+    return x
+
+
+def msda_prep(proj_f32, ref, valid_ratios, shapes_host, n_levels, B, Lq, M, P):
+    loc = torch.empty((B, Lq, M, n_levels, P, 2), dtype=torch.float32, device=proj_f32.device)
+    attn = torch.empty((B, Lq, M, n_levels, P), dtype=torch.float32, device=proj_f32.device)
+    _call("dtlr_msda_prep", _p(proj_f32), proj_f32.stride(0), _p(ref), ref.shape[-1], _p(valid_ratios), shapes_host, n_levels,
+          _p(loc), _p(attn), B, Lq, M, P, _st(proj_f32))
+    return loc, attn
+
+
+def enc_ref_points(valid_ratios, shapes_host, n_levels, B, S):
+    ref = torch.empty((B * S, 2), dtype=torch.float32, device=valid_ratios.device)
+    _call("dtlr_enc_ref_points", _p(valid_ratios), shapes_host, n_levels, _p(ref), B, S, _st(valid_ratios))
+    return ref
+
+
+def encoder_proposals(memory, pad_u8, valid_hw_i32, shapes_host, n_levels, B, S, C, default_hw):
+    import ctypes
+    out_mem = torch.empty_like(memory)
+    prop = torch.empty((B * S, 4), dtype=torch.float32, device=memory.device)
+    _call("dtlr_encoder_proposals", _p(memory), _p(pad_u8), _p(valid_hw_i32), shapes_host, n_levels, _p(out_mem), _p(prop),
+          B, S, C, ctypes.c_float(default_hw), L.dtype_code(memory), _st(memory))
+    return out_mem, prop
+
+
+def rowmax(x_f32, N):
+    import ctypes
+    out = torch.empty((x_f32.shape[0],), dtype=torch.float32, device=x_f32.device)
+    _call("dtlr_rowmax", _p(x_f32), x_f32.stride(0), N, _p(out), ctypes.c_longlong(x_f32.shape[0]), _st(x_f32))
+    return out
+
+
+def sine_embed(ref, valid_ratios, B, Q, n_levels, out_dtype):
+    out = torch.empty((B * Q, 512), dtype=out_dtype, device=ref.device)
+    _call("dtlr_sine_embed", _p(ref), _p(valid_ratios), _p(out), B, Q, n_levels, L.dtype_code(out), _st(ref))
+    return out
+
+
+def box_refine(delta_f32, ref):
+    import ctypes
+    out = torch.empty_like(ref)
+    _call("dtlr_box_refine", _p(delta_f32), delta_f32.stride(0), _p(ref), _p(out), ctypes.c_longlong(ref.shape[0]), _st(ref))
+    return out
+
+
+def sigmoid(x):
+    import ctypes
+    out = torch.empty_like(x)
+    _call("dtlr_sigmoid", _p(x), _p(out), ctypes.c_longlong(x.numel()), _st(x))
+    return out
+
+
+def cast(x, dtype):
+    import ctypes
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _call("dtlr_cast", _p(x), _p(out), ctypes.c_longlong(x.numel()), L.dtype_code(x), L.dtype_code(out), _st(x))
+    return out
+
+
+def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
+    out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
+    _call("dtlr_mha_self_attention", _p(qk), qk.stride(0), k_off, _p(v), v.stride(0), _p(attn_mask_u8), _p(out), out.stride(0),
+          B, Q, heads, head_dim, L.dtype_code(v), _st(v))
     return out

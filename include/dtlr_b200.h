@@ -81,6 +81,63 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
  */
 int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
               void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);
+/* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Convolution front end (NHWC activations).  A k x k / strided convolution of the ResNet-50 trunk (torchvision
+ * resnet50 as wrapped by models/dino/backbone.py:109-128) or of input_proj[3] (models/dino/dino.py:126-135) is
+ * dtlr_im2col + dtlr_gemm with the FrozenBatchNorm (backbone.py:62-72) folded into the weights and bias.
+ * x: NHWC [B,H,W,C] of in_dtype, or (nchw_input=1) the fp32 NCHW network input; out [B*Ho*Wo, ldo] of out_dtype,
+ * K ordered (kh, kw, cin), columns >= KH*KW*C zero-filled.
+ */
+int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho,
+                int Wo, int ldo, int in_dtype, int out_dtype, int nchw_input, void* stream);
+/* 3x3 / stride 2 / pad 1 max-pool of the ResNet stem, NHWC, C % 8 == 0 */
+int dtlr_maxpool3x3s2(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, int dtype, void* stream);
+/* nn.GroupNorm(G, C), eps (models/dino/dino.py:121-124) over one feature level: x fp32 [B,HW,C] -> out rows
+ * (b*out_stride_b + hw) of a [.., C] buffer of out_dtype, i.e. directly into the flattened multi-level token tensor
+ * (models/dino/deformable_transformer.py:278-288). */
+int dtlr_groupnorm(const float* x, const float* gamma, const float* beta, void* out, int B, int HW, int C, int G,
+                   long long out_stride_b, float eps, int out_dtype, void* stream);
+/* PositionEmbeddingSineHW (models/dino/position_encoding.py:79-108, normalize=True) + level_embed[C] (may be NULL;
+ * deformable_transformer.py:281-282).  mask [B,H,W] uint8, 1 = padding; out as dtlr_groupnorm; C = 2*npf. */
+int dtlr_pos_sine(const unsigned char* mask, const float* level_embed, void* out, int B, int H, int W, int npf,
+                  float temp_h, float temp_w, long long out_stride_b, int out_dtype, void* stream);
+/* y = LayerNorm_256(x (+ res)), eps; optional y2 = y + add2 (the "+pos" query of the next block).
+ * models/dino/deformable_transformer.py:813-814,806-807,906-907,956-957,878-879,326,758.  res/add2/y2 may be NULL. */
+int dtlr_add_layernorm(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                       const void* add2, void* y2, long long rows, int C, float eps, int dtype, void* stream);
+int dtlr_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream);
+/* value.masked_fill(padding_mask[..., None], 0) (models/dino/ops/modules/ms_deform_attn.py:95-96) */
+int dtlr_zero_masked_rows(void* x, const unsigned char* rowmask, long long rows, int C, int dtype, void* stream);
+/* softmax over the L*P attention logits of each head + sampling locations (ms_deform_attn.py:98-108) with the
+ * per-level valid-ratio scaling of the reference points folded in (deformable_transformer.py:491, 686-687).
+ * proj fp32 [B*Lq, ld]: M*L*P*2 offsets then M*L*P logits; ref fp32 [B*Lq, ref_dim] (2: encoder, 4: decoder boxes);
+ * valid_ratios fp32 [B,L,2]; shapes host (L,2); loc [B,Lq,M,L,P,2], attn [B,Lq,M,L,P] fp32 out. */
+int dtlr_msda_prep(const float* proj, int ld, const float* ref, int ref_dim, const float* valid_ratios,
+                   const int64_t* shapes, int L, float* loc, float* attn, int B, int Lq, int M, int P, void* stream);
+/* TransformerEncoder.get_reference_points (deformable_transformer.py:479-490) before the valid-ratio product */
+int dtlr_enc_ref_points(const float* valid_ratios, const int64_t* shapes, int L, float* ref, int B, int S, void* stream);
+/* gen_encoder_output_proposals (models/dino/utils.py:15-64): proposals fp32 [B,S,4] (logit space, +inf when invalid),
+ * out_memory = memory with invalid / padded rows zeroed.  valid_hw int32 [B,L,2] = (valid_H, valid_W). */
+int dtlr_encoder_proposals(const void* memory, const unsigned char* pad, const int* valid_hw, const int64_t* shapes,
+                           int L, void* out_memory, float* proposals, int B, int S, int C, float default_hw, int dtype,
+                           void* stream);
+/* max over the first N columns of each row (two-stage class score, deformable_transformer.py:345) */
+int dtlr_rowmax(const float* x, int ld, int N, float* out, long long rows, void* stream);
+/* gen_sineembed_for_position (models/dino/utils.py:141-167) of ref*valid_ratio[:,0] (deformable_transformer.py:686-691):
+ * ref fp32 [B*Q,4] -> out [B*Q,512] in order (y,x,w,h) */
+int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream);
+/* out = sigmoid(delta[:, :4] + inverse_sigmoid(ref, eps=1e-3)) (deformable_transformer.py:734-738, dino.py:343-345) */
+int dtlr_box_refine(const float* delta, int ldd, const float* ref, float* out, long long rows, void* stream);
+int dtlr_sigmoid(const float* x, float* out, long long n, void* stream);
+int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype, void* stream);
+/* nn.MultiheadAttention(d_model, heads) core of the decoder self-attention (deformable_transformer.py:847, 903-905):
+ * softmax(q k^T / sqrt(head_dim) [masked]) v per (batch, head), scores never materialised.
+ * q rows: qk[b*Q+i, h*32 ...], k rows: qk[b*Q+j, k_off + h*32 ...], v rows: v[b*Q+j, h*32 ...];
+ * attn_mask uint8 [Q,Q], 1 = blocked, or NULL; out [B*Q, ld_o]. */
+int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const unsigned char* attn_mask,
+                            void* out, int ld_o, int B, int Q, int heads, int head_dim, int dtype, void* stream);
 
 #ifdef __cplusplus
 }
