@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json headline metric: text-line images/sec, DINO forward, batch 64 of 3x40x1024 per GPU
+(config/Latin_CTC.py: ResNet-50 + 6+6 deformable enc/dec, 900 queries, 166 classes), bf16, synthetic data.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run, one rank/GPU)
+  python bench.py --impl reference ...                     (the reference path's CPU restatement on the host cores)
+
+One "step" = one full forward (all reference outputs: 6 decoder layers of logits/boxes + interm outputs) of one batch.
+Prints ONE JSON line (rank 0).  See DESIGN.md §measurement for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 64
+IMG_H, IMG_W = 40, 1024
+WORKLOAD = "IAM English config/Latin_CTC.py: ResNet-50 + 6+6 deformable enc/dec, 900 queries, 166 classes, 64x3x40x1024 per GPU, forward"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_ours(device, dtype):
+    from dtlr_b200 import config, dino, synth
+    model, criterion, post = dino.build_dino(config.latin_ctc_args())
+    synth.load_synth_weights(model, seed=0)
+    model = model.to(device).eval()
+    model.compute_dtype = dtype
+    model.engine_outputs = "all"
+    return model
+
+
+def cpu_baseline_run(batch, iters, warmup=1):
+    """the oracle (CPU restatement of the reference path: torch CPU ops + C MSDA core) on the host cores."""
+    import json as _json
+    from dtlr_b200 import synth
+    from oracle import dino_ref
+    shapes = _json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    sd = synth.synth_state_dict(shapes, seed=0)
+    cfg = dino_ref.default_cfg(num_queries=900)
+    x = synth.synth_images(batch, IMG_H, IMG_W, seed=0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(warmup):
+        dino_ref.dino_forward(sd, cfg, x)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        dino_ref.dino_forward(sd, cfg, x)
+    dt = time.perf_counter() - t0
+    return batch * iters / dt, dt / iters
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = 8
+    ips, sec = cpu_baseline_run(batch, max(1, args.steps), max(1, min(args.warmup, 1)))
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "text-line images/sec (DINO forward)", "value": round(ips, 3), "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "bounded sample: %d images per step on the host CPU" % batch},
+            "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps of %d images (3x40x1024), oracle/dino_ref.py + oracle/msda_ref.c, fp32" % (args.steps, batch)},
+            "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    from dtlr_b200 import _lib, dino, synth
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model = build_ours(device, dtype)
+    B = BATCH_PER_GPU
+    host_imgs = synth.synth_images(B, IMG_H, IMG_W, seed=100 + rank).pin_memory()
+    dev_imgs = host_imgs.to(device, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------- device-resident throughput (`value`) with the dominant kernel family timed by CUDA events
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(dev_imgs)
+    gemm_events, cur = [], {}
+
+    def timer(name, flops, dev, begin):
+        if begin:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cur["e0"], cur["fl"] = e0, flops
+        else:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            gemm_events.append((cur["e0"], e1, cur["fl"]))
+
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    _lib.LAUNCHES = 0
+    _lib.TIMER = timer
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    with torch.no_grad():
+        for _ in range(args.steps):
+            out = model(dev_imgs)
+    e1.record()
+    barrier()
+    _lib.TIMER = None
+    launches = _lib.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    n_gemm = len(gemm_events)
+
+    # ---------------- end to end through the public API with HOST buffers (`e2e`)
+    from dtlr_b200.misc import nested_tensor_from_tensor_list
+
+    def e2e_step():
+        x = host_imgs.to(device, non_blocking=True)
+        o = model(x)
+        new = dino.ctc_view(o["pred_logits"], o["pred_boxes"])
+        ids = new.argmax(-1).to(torch.int32)
+        return ids.cpu()
+
+    with torch.no_grad():
+        for _ in range(2):
+            ids = e2e_step()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            ids = e2e_step()
+        t1.record()
+        barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions)" if dtype == torch.bfloat16 else "sgemm_kernel (fp32 parity mode)",
+                "bound": "tensor", "achieved": round(ach_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(ach_tf / peak_tf, 4), "traffic": None, "peak_kind": pk_kind + " sustained cuBLAS bf16",
+                "launches_timed": n_gemm, "share_of_step": round(gemm_ms / ms_total, 3),
+                "algorithmic_flops_per_step": gemm_flops / args.steps}
+    cpu = None
+    if not args.no_cpu_baseline:
+        ips, sec = cpu_baseline_run(8, 3, 1)
+        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "3 forwards of 8 images (3x40x1024) after 1 warm-up, oracle/dino_ref.py + oracle/msda_ref.c, fp32"}
+    line = {"metric": "text-line images/sec (DINO forward)", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (independent shards, no collective)" % world,
+                       "weights": "random (dtlr_b200.synth, seed 0)", "outputs": "all reference dict keys (6 decoder layers + interm)",
+                       "l2": "no explicit flush: one step streams >1 GB of activations (126 MB L2)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": host_imgs.numel() * 4 ,
+                    "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "api": "DINO.forward(pinned host images) + ctc_view argmax -> host int32 ids"},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

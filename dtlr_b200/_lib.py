@@ -29,9 +29,17 @@ def lib():
     return _lib
 
 
+# number of libdtlr_b200 kernel launches issued through the C ABI (bench.py reports it as "gpu_launches")
+LAUNCHES = 0
+# optional profiler hook: callable(name) -> context manager, set by bench.py to time one kernel family with CUDA events
+TIMER = None
+
+
 def check(rc, what):
+    global LAUNCHES
     if rc != 0:
         raise DtlrError("%s failed (status %d): %s" % (what, rc, lib().dtlr_last_error().decode()))
+    LAUNCHES += 1
 
 
 def dtype_code(t):

