@@ -101,6 +101,27 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+template <typename OutT> __device__ __forceinline__ void unpack_chunk(const uint4& d, float* f);
+template <> __device__ __forceinline__ void unpack_chunk<float>(const uint4& d, float* f) {
+    f[0] = __uint_as_float(d.x); f[1] = __uint_as_float(d.y); f[2] = __uint_as_float(d.z); f[3] = __uint_as_float(d.w);
+}
+template <> __device__ __forceinline__ void unpack_chunk<__nv_bfloat16>(const uint4& d, float* f) {
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename OutT> __device__ __forceinline__ uint4 pack_chunk(const float* f);
+template <> __device__ __forceinline__ uint4 pack_chunk<float>(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+template <> __device__ __forceinline__ uint4 pack_chunk<__nv_bfloat16>(const float* f) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
 // ---------------------------------------------------------------------------------------------- tcgen05 GEMM
 struct GemmEpi {
     const float* bias;       // [N] fp32 or null
@@ -109,109 +130,49 @@ struct GemmEpi {
     int ldr, ldc;
     int M, N, K;
     int relu;                // 0 none, 1 ReLU before the residual add, 2 ReLU after it (ResNet bottleneck)
+    int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = 128 B = one swizzle atom row
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES, typename OutT>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int ROW_BYTES = BN * (int)sizeof(OutT);          // staging row pitch (16-byte chunks XOR-swizzled)
+    static constexpr int STAGING_BYTES = GEMM_BM * ROW_BYTES;
+    static constexpr int BIAS_BYTES = 4 * BN * 4;                     // one fp32 bias row per epilogue warp
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <typename OutT>
-__device__ __forceinline__ void epi_store_row(const GemmEpi& e, int row, int col0, const uint32_t (&acc)[32], bool vec_ok) {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    const int ncol = min(32, e.N - col0);
-    if (e.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < ncol) v[j] += __ldg(e.bias + col0 + j);
-    }
-    if (e.relu == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    OutT* crow = reinterpret_cast<OutT*>(e.C) + (size_t)row * e.ldc + col0;
-    const OutT* rrow = e.residual ? reinterpret_cast<const OutT*>(e.residual) + (size_t)row * e.ldr + col0 : nullptr;
-    if (vec_ok && ncol == 32) {
-        if constexpr (sizeof(OutT) == 2) {
-            if (rrow) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint4 t = *reinterpret_cast<const uint4*>(rrow + j);
-                    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        v[j + 2 * k] += __uint_as_float(w[k] << 16);
-                        v[j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
-                    }
-                }
-            }
-            if (e.relu == 2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(crow + j) = o;
-            }
-        } else {
-            if (rrow) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(rrow + j);
-                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-            }
-            if (e.relu == 2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < ncol) {
-                float x = v[j];
-                if (rrow) x += (float)rrow[j];
-                if (e.relu == 2) x = fmaxf(x, 0.f);
-                crow[j] = (OutT)x;
-            }
-        }
-    }
-}
-
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue.
+// Two TMEM accumulators: the MMA warp fills one while the epilogue drains the other.  Epilogue: TMEM -> registers
+// (bias, ReLU) -> XOR-swizzled shared staging -> fully coalesced 16-byte global stores (+ coalesced residual reads).
 template <int BN, int STAGES, typename OutT>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmEpi e) {
-    using S = GemmSmem<BN, STAGES>;
+    using S = GemmSmem<BN, STAGES, OutT>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared between TMA and the UMMA descriptors
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    unsigned char* staging = smem + STAGES * S::STAGE_BYTES;
+    float* bias_s = reinterpret_cast<float*>(staging + S::STAGING_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * BN;
+    const int num_m = (e.M + GEMM_BM - 1) / GEMM_BM, num_n = (e.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
     const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
@@ -221,10 +182,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);          // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_ptr);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_ptr);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -233,14 +197,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);                       // slot free (first lap passes immediately)
-                mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-                unsigned char* sa = smem + s * S::STAGE_BYTES;
-                tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
-                tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);                   // slot free (first lap passes immediately)
+                    mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                    unsigned char* sa = smem + s * S::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+                    tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -248,46 +216,143 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
         // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);                                // TMA bytes have landed
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[as], aph ^ 1);                    // epilogue has drained this accumulator
             tcgen05_fence_after();
-            if (elect_one()) {
-                const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint64_t da = make_sw128_kmajor_desc(sa);
-                const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);                            // TMA bytes have landed
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint64_t da = make_sw128_kmajor_desc(sa);
+                    const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        if (e.dbg & 2) break;
+                        // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);                         // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&empty_bar[s]);                             // frees the smem slot when these MMAs retire
-                if (kb == num_kb - 1) umma_commit(tmem_full_bar);       // accumulator complete -> epilogue
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) and the matching 32 rows of the staging tile =====
         const int qd = warp & 3;
-        const int row = m0 + qd * 32 + lane;
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
+        constexpr int CHUNKS = S::ROW_BYTES / 16;                       // 16-byte chunks per staging row
+        constexpr int EPC = 16 / (int)sizeof(OutT);                     // elements per chunk
+        unsigned char* my_rows = staging + (size_t)(qd * 32) * S::ROW_BYTES;
         const bool vec_ok = ((e.ldc * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.C & 15) == 0) &&
                             (!e.residual || (((e.ldr * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.residual & 15) == 0)));
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            // bias row of this tile -> warp-private shared memory while the MMAs of the tile are still running
+            float* my_bias = bias_s + qd * BN;
+            if (e.bias) {
+                for (int j = lane; j < BN; j += 32) my_bias[j] = (n0 + j < e.N) ? __ldg(e.bias + n0 + j) : 0.f;
+                __syncwarp();
+            }
+            mbar_wait(&tmem_full_bar[as], aph);
+            tcgen05_fence_after();
+            // ---- step 1: TMEM -> registers -> bias / ReLU -> swizzled staging (thread = row qd*32 + lane)
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            if (n0 + c >= e.N) break;
-            uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
-            if (row < e.M) epi_store_row<OutT>(e, row, n0 + c, acc, vec_ok);
+            for (int c = 0; c < BN; c += 32) {
+                if (e.dbg & 4) break;
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                if (e.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c + j);
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                }
+                if (e.relu == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                unsigned char* srow = my_rows + (size_t)lane * S::ROW_BYTES;
+                if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 o;
+                        o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                        o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                        const int chunk = (c + j) / 8;
+                        *reinterpret_cast<uint4*>(srow + ((chunk ^ (lane & 7)) * 16)) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int chunk = (c + j) / 4;
+                        *reinterpret_cast<float4*>(srow + ((chunk ^ (lane & 7)) * 16)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            // ---- step 2: staging -> global, coalesced (each warp stores its own 32 rows), + residual, + late ReLU
+            const int ncols = (e.dbg & 1) ? 0 : min(BN, e.N - n0);
+            if (vec_ok && (ncols % EPC) == 0) {
+                const int nchunks = ncols / EPC;
+                for (int idx = lane; idx < 32 * CHUNKS; idx += 32) {
+                    const int r = idx / CHUNKS, ch = idx % CHUNKS;
+                    const int grow = m0 + qd * 32 + r;
+                    if (ch >= nchunks || grow >= e.M) continue;
+                    uint4 d = *reinterpret_cast<const uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16));
+                    OutT* cp = reinterpret_cast<OutT*>(e.C) + (size_t)grow * e.ldc + n0 + ch * EPC;
+                    if (e.residual || e.relu == 2) {
+                        float f[EPC];
+                        unpack_chunk<OutT>(d, f);
+                        if (e.residual) {
+                            const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const OutT*>(e.residual) + (size_t)grow * e.ldr + n0 + ch * EPC);
+                            float g[EPC];
+                            unpack_chunk<OutT>(rr, g);
+#pragma unroll
+                            for (int k = 0; k < EPC; ++k) f[k] += g[k];
+                        }
+                        if (e.relu == 2) {
+#pragma unroll
+                            for (int k = 0; k < EPC; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        d = pack_chunk<OutT>(f);
+                    }
+                    *reinterpret_cast<uint4*>(cp) = d;
+                }
+            } else {
+                for (int idx = lane; idx < 32 * BN; idx += 32) {
+                    const int r = idx / BN, col = idx % BN;
+                    const int grow = m0 + qd * 32 + r;
+                    if (col >= ncols || grow >= e.M) continue;
+                    const int ch = col / EPC;
+                    const OutT x = *reinterpret_cast<const OutT*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16) + (col % EPC) * sizeof(OutT));
+                    float f = (float)x;
+                    if (e.residual) f += (float)reinterpret_cast<const OutT*>(e.residual)[(size_t)grow * e.ldr + n0 + col];
+                    if (e.relu == 2) f = fmaxf(f, 0.f);
+                    reinterpret_cast<OutT*>(e.C)[(size_t)grow * e.ldc + n0 + col] = (OutT)f;
+                }
+            }
+            __syncwarp();          // staging rows are rewritten by the next tile
         }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
 }
 
@@ -391,10 +456,15 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols
 
 template <int BN, int STAGES, typename OutT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st) {
-    using S = GemmSmem<BN, STAGES>;
+    using S = GemmSmem<BN, STAGES, OutT>;
     auto k = gemm_bf16_tcgen05_kernel<BN, STAGES, OutT>;
-    DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    dim3 grid((e.M + GEMM_BM - 1) / GEMM_BM, (e.N + BN - 1) / BN);
+    static bool configured = false;     // per template instantiation
+    if (!configured) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    const int tiles = ((e.M + GEMM_BM - 1) / GEMM_BM) * ((e.N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
     k<<<grid, 192, S::TOTAL, st>>>(ta, tb, e);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -404,6 +474,9 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
 
 using namespace dtlr;
 
+static int g_debug_flags = 0;
+extern "C" int dtlr_debug_flags(int flags) { const int old = g_debug_flags; g_debug_flags = flags; return old; }
+
 extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                          int ldr, void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu,
                          void* stream) {
@@ -412,7 +485,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
     DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
-    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu};
+    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, g_debug_flags};
     if (in_dtype == DTLR_F32) {
         DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
         dim3 grid((M + 63) / 64, (N + 63) / 64);
@@ -429,9 +502,9 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     if (N > 64) {
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
         if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 128))) return rc;
-        return out_dtype == DTLR_BF16 ? launch_tc<128, 3, __nv_bfloat16>(ta, tb, e, st) : launch_tc<128, 3, float>(ta, tb, e, st);
+        return out_dtype == DTLR_BF16 ? launch_tc<128, 4, __nv_bfloat16>(ta, tb, e, st) : launch_tc<128, 4, float>(ta, tb, e, st);
     }
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 64))) return rc;
-    return out_dtype == DTLR_BF16 ? launch_tc<64, 4, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 4, float>(ta, tb, e, st);
+    return out_dtype == DTLR_BF16 ? launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 6, float>(ta, tb, e, st);
 }

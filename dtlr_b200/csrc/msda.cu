@@ -71,11 +71,22 @@ struct Vec16<__nv_bfloat16> {
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-template <typename T, bool STAGE, bool SINGLE, int NWARPS>
+// FUSED: the kernel also does the MSDeformAttn prologue (reference ops/modules/ms_deform_attn.py:98-108): `loc` points at
+// the fp32 projection rows [B*Lq, fz.ld] (M*L*P*2 offsets, then M*L*P attention logits); the softmax over the L*P
+// logits of the head is a 16-lane shuffle reduction and the sampling location is ref*valid_ratio + offset-term, so the
+// (B,Lq,M,L,P,2) location and (B,Lq,M,L,P) weight tensors never exist in HBM.  Requires SINGLE (L*P <= 16).
+struct FusedArgs {
+    const float* ref;            // [B*Lq, RD] reference points (RD = 2: encoder centres, 4: decoder boxes)
+    const float* valid_ratios;   // [B, L, 2] (w, h)
+    int ld;                      // row pitch of the projection matrix
+    int RD;
+};
+
+template <typename T, bool STAGE, bool SINGLE, bool FUSED, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                     T* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
-                    const int P, const int q_per_cta) {
+                    const int P, const int q_per_cta, const FusedArgs fz) {
     constexpr int ROWB = 32 * (int)sizeof(T);   // bytes of one pixel (32 channels)
     constexpr int LPP = ROWB / 16;              // lanes per pixel (8 fp32 / 4 bf16)
     constexpr int GL = 2 * LPP;                 // lanes per (point,row) group: two x-adjacent pixels
@@ -130,10 +141,37 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
             // ---- tap parameters of point c0+pt16 (branch-free: out-of-range points get weight 0 and a safe offset)
             const int pt = min(c0 + pt16, LP - 1);
             const bool pt_ok = (c0 + pt16) < LP;
-            const float2 xy = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
-            const float aw = attn[pbase + pt];
             const int l = pt / P;
             const int H = lv.H[l], W = lv.W[l];
+            float2 xy;
+            float aw;
+            if (FUSED) {
+                const size_t row = (size_t)b * Lq + q;
+                const float* pr = loc + row * fz.ld;
+                const float2 off = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
+                const float lg = pt_ok ? pr[(size_t)M * LP * 2 + (size_t)m * LP + pt] : -INFINITY;
+                float mx = lg;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float ex = expf(lg - mx);
+                float den = ex;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+                aw = ex * (1.f / den);
+                const float* rf = fz.ref + row * fz.RD;
+                const float vx = fz.valid_ratios[((size_t)b * lv.n + l) * 2], vy = fz.valid_ratios[((size_t)b * lv.n + l) * 2 + 1];
+                const float rx = rf[0] * vx, ry = rf[1] * vy;
+                if (fz.RD == 2) {
+                    xy.x = rx + off.x / (float)W;
+                    xy.y = ry + off.y / (float)H;
+                } else {
+                    xy.x = rx + off.x / (float)P * (rf[2] * vx) * 0.5f;
+                    xy.y = ry + off.y / (float)P * (rf[3] * vy) * 0.5f;
+                }
+            } else {
+                xy = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
+                aw = attn[pbase + pt];
+            }
             const float y = fmaf(xy.y, (float)H, -0.5f), x = fmaf(xy.x, (float)W, -0.5f);
             const bool inside = pt_ok && y > -1.f && x > -1.f && y < (float)H && x < (float)W;
             const float yf = floorf(y), xf = floorf(x);
@@ -365,7 +403,10 @@ static int fill_levels(Levels& lv, const int64_t* shapes, const int64_t* lsi, in
 
 template <typename T, int NW>
 static int launch_fwd_d32_nw(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
-                             int S, int M, int Lq, int P, bool stage, size_t slab, int occ, cudaStream_t st) {
+                             int S, int M, int Lq, int P, bool stage, size_t slab, int occ, const FusedArgs* fzp,
+                             cudaStream_t st) {
+    const bool fused = fzp != nullptr;
+    const FusedArgs fz = fused ? *fzp : FusedArgs{nullptr, nullptr, 0, 0};
     const long long slots = (long long)sm_count() * occ;
     // split the query range so that the grid is several waves deep but every CTA keeps >= 64 queries
     int qsplit = (int)((4 * slots + (long long)B * M - 1) / ((long long)B * M));
@@ -376,15 +417,21 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
     qsplit = (Lq + q_per_cta - 1) / q_per_cta;
     dim3 grid(qsplit, M, B), block(NW * 32);
     const bool single = lv.n * P <= 16;
+    if (fused && !single) {
+        set_error("msda fused prologue needs n_levels*n_points <= 16");
+        return DTLR_ERR_UNSUPPORTED;
+    }
     if (stage) {
-        auto k = single ? msda_fwd_d32_kernel<T, true, true, NW> : msda_fwd_d32_kernel<T, true, false, NW>;
+        auto k = fused ? msda_fwd_d32_kernel<T, true, true, true, NW>
+                       : (single ? msda_fwd_d32_kernel<T, true, true, false, NW> : msda_fwd_d32_kernel<T, true, false, false, NW>);
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
         k<<<grid, block, slab, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
-                                     q_per_cta);
+                                     q_per_cta, fz);
     } else {
-        auto k = single ? msda_fwd_d32_kernel<T, false, true, NW> : msda_fwd_d32_kernel<T, false, false, NW>;
+        auto k = fused ? msda_fwd_d32_kernel<T, false, true, true, NW>
+                       : (single ? msda_fwd_d32_kernel<T, false, true, false, NW> : msda_fwd_d32_kernel<T, false, false, false, NW>);
         k<<<grid, block, 0, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
-                                  q_per_cta);
+                                  q_per_cta, fz);
     }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -392,7 +439,7 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
 
 template <typename T>
 static int launch_fwd_d32(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
-                          int S, int M, int Lq, int P, cudaStream_t st) {
+                          int S, int M, int Lq, int P, cudaStream_t st, const FusedArgs* fzp = nullptr) {
     const size_t slab = (size_t)(S + 2) * 32 * sizeof(T);
     const bool stage = slab <= (size_t)max_smem_optin();
     // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA)
@@ -400,8 +447,8 @@ static int launch_fwd_d32(const void* value, const void* loc, const void* attn, 
     if (occ_smem < 1) occ_smem = 1;
     // 64 registers/thread -> at most 32 warps per SM: one 32-warp CTA when only one slab fits, else 16-warp CTAs
     if (occ_smem == 1)
-        return launch_fwd_d32_nw<T, 32>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, 1, st);
-    return launch_fwd_d32_nw<T, 16>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, min(occ_smem, 2), st);
+        return launch_fwd_d32_nw<T, 32>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, 1, fzp, st);
+    return launch_fwd_d32_nw<T, 16>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, min(occ_smem, 2), fzp, st);
 }
 
 }  // namespace dtlr
@@ -441,6 +488,27 @@ extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const
     }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
+}
+
+extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const float* proj,
+                                       int ld_proj, const float* ref, int ref_dim, const float* valid_ratios, void* out,
+                                       int B, int S, int M, int D, int L, int Lq, int P, int dtype, void* stream) {
+    DTLR_CHECK_ARG(B >= 0 && Lq >= 0 && S > 0 && M > 0 && P > 0, "msda_forward_fused: bad sizes");
+    DTLR_CHECK_ARG(D == 32 && (dtype == DTLR_F32 || dtype == DTLR_BF16), "msda_forward_fused: needs D=32, f32 or bf16 values");
+    DTLR_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "msda_forward_fused: reference points must have 2 or 4 coordinates");
+    DTLR_CHECK_ARG(shapes && lsi, "msda_forward_fused: null shapes");
+    DTLR_CHECK_ARG(ld_proj >= M * L * P * 3 && (ld_proj % 2) == 0, "msda_forward_fused: projection row pitch %d too small/odd", ld_proj);
+    Levels lv;
+    int rc = fill_levels(lv, shapes, lsi, L, S);
+    if (rc) return rc;
+    if (B == 0 || Lq == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(value && proj && ref && valid_ratios && out, "msda_forward_fused: null pointer");
+    DTLR_CHECK_ARG((((uintptr_t)value | (uintptr_t)proj) & 15) == 0, "msda_forward_fused: value/proj must be 16-byte aligned");
+    DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward_fused: B or M exceeds 65535");
+    const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim};
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz)
+                             : launch_fwd_d32<__nv_bfloat16>(value, proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz);
 }
 
 extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,

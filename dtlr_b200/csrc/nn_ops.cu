@@ -380,17 +380,28 @@ __global__ void rowmax_kernel(const float* __restrict__ x, int ld, int N, float*
 template <typename TO>
 __global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, TO* __restrict__ out,
                                   int B, int Q, int L) {
-    const long long row = blockIdx.x;
+    // 64 threads per query row handle one (sin, cos) pair of each of the 4 components: dim_t[2k] == dim_t[2k+1]
+    __shared__ float dim_t[64];
+    if (threadIdx.x < 64) dim_t[threadIdx.x] = powf(10000.f, 2.f * (float)threadIdx.x / 128.f);
+    __syncthreads();
+    const int rows_per_block = blockDim.x / 64;
+    const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / 64;
+    if (row >= (long long)B * Q) return;
+    const int k = threadIdx.x & 63;
     const int b = (int)(row / Q);
     const float vx = valid_ratios[(size_t)b * L * 2], vy = valid_ratios[(size_t)b * L * 2 + 1];
-    const float* r = ref + row * 4;
-    const float comp[4] = {r[1] * vy, r[0] * vx, r[2] * vx, r[3] * vy};   // y, x, w, h
+    const float4 r = *reinterpret_cast<const float4*>(ref + row * 4);
+    const float comp[4] = {r.y * vy, r.x * vx, r.z * vx, r.w * vy};   // y, x, w, h
     const float two_pi = 6.283185307179586f;
-    for (int c = threadIdx.x; c < 512; c += blockDim.x) {
-        const int part = c >> 7, i = c & 127;
-        const float dim_t = powf(10000.f, 2.f * (float)(i / 2) / 128.f);
-        const float a = comp[part] * two_pi / dim_t;
-        stf<TO>(out + row * 512 + c, (i & 1) ? cosf(a) : sinf(a));
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+        // same operation order as the reference: (v * 2pi) / dim_t
+        const float a = comp[part] * two_pi / dim_t[k];
+        float sn, cs;
+        sincosf(a, &sn, &cs);
+        TO* o = out + row * 512 + part * 128 + 2 * k;
+        stf<TO>(o, sn);
+        stf<TO>(o + 1, cs);
     }
 }
 
@@ -563,7 +574,7 @@ extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long 
 extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream) {
     const long long rows = (long long)B * Q;
     if (rows == 0) return DTLR_OK;
-    DISPATCH_T(out_dtype, sine_embed_kernel<T><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(ref, valid_ratios, (T*)out, B, Q, L);)
+    DISPATCH_T(out_dtype, sine_embed_kernel<T><<<(unsigned)((rows + 3) / 4), 256, 0, (cudaStream_t)stream>>>(ref, valid_ratios, (T*)out, B, Q, L);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

@@ -182,6 +182,7 @@ class DINO(nn.Module):
         self.compute_dtype = torch.float32      # torch.float32 = parity mode, torch.bfloat16 = throughput mode
         self.use_engine = True                  # eval + no_grad -> fused inference engine
         self.engine_outputs = "all"             # "all": every reference dict key; "final": last-layer logits/boxes only
+        self.use_cuda_graph = False             # replay one captured CUDA graph per input shape (static output buffers)
         self._engine = None
 
     # -------------------------------------------------------------------------------------------

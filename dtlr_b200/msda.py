@@ -59,6 +59,23 @@ def msda_forward_raw(value, shapes_host, lsi_host, n_levels, loc, attn, out=None
     return out
 
 
+def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_ratios, Lq, P, out=None):
+    """MSDA core with the prologue fused (include/dtlr_b200.h: dtlr_msda_forward_fused).  value (B,S,M,32);
+    proj fp32 (B*Lq, ld) = offsets | logits; ref fp32 (B*Lq, 2|4); valid_ratios fp32 (B,L,2)."""
+    L.require_cuda(value, proj, ref, valid_ratios)
+    B, S, M, D = value.shape
+    assert proj.dtype == torch.float32 and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
+    assert value.is_contiguous() and ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
+    if out is None:
+        out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.ptr(ref),
+                                             ref.shape[-1], L.ptr(valid_ratios), L.ptr(out), B, S, M, D, n_levels, Lq, P,
+                                             L.dtype_code(value), L.stream_ptr(value.device))
+    L.check(rc, "dtlr_msda_forward_fused")
+    return out
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
     """Drop-in for MultiScaleDeformableAttention.ms_deform_attn_forward (reference src/ms_deform_attn.h:21-40).
     im2col_step is accepted and ignored (no batch chunking on B200)."""

@@ -55,6 +55,15 @@ int dtlr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
                       const void* attn, void* out, int B, int S, int M, int D, int L, int Lq, int P,
                       int dtype, void* stream);
 
+/* The same core with the MSDeformAttn prologue fused in (models/dino/ops/modules/ms_deform_attn.py:98-108 + :116-123):
+ * proj fp32 [B*Lq, ld_proj] = sampling_offsets (M*L*P*2) then attention logits (M*L*P) of each query; the softmax over
+ * the L*P logits and loc = ref*valid_ratio + offset/(W,H) (ref_dim 2) or + offset/P*wh*0.5 (ref_dim 4) happen in the
+ * kernel, so sampling_locations / attention_weights never exist in HBM.  Needs D = 32 and L*P <= 16.
+ * ref fp32 [B*Lq, ref_dim], valid_ratios fp32 [B, L, 2] = (w, h) (deformable_transformer.py:239-246, 491, 686-687). */
+int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const float* proj, int ld_proj,
+                            const float* ref, int ref_dim, const float* valid_ratios, void* out, int B, int S, int M,
+                            int D, int L, int Lq, int P, int dtype, void* stream);
+
 /* Replaces  MultiScaleDeformableAttention.ms_deform_attn_backward
  *           models/dino/ops/src/vision.cpp:15, src/cuda/ms_deform_attn_cuda.cu:83-153,
  *           src/cuda/ms_deform_im2col_cuda.cuh:87-159, 301-403
@@ -81,6 +90,8 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
  */
 int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
               void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);
+/* tuning aid only: sets kernel debug flags (0 = normal operation), returns the previous value */
+int dtlr_debug_flags(int flags);
 /* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */
 
 /* ---------------------------------------------------------------------------------------------------------

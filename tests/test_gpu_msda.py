@@ -179,3 +179,38 @@ def test_rejects_cpu_tensors():
     value, shp, lsi, loc, w = _rand_case(1, [(6, 4), (3, 2)], 2, 32, 2, 2, 1)
     with pytest.raises(_lib.DtlrError):
         msda.ms_deform_attn_forward(value, shp, lsi, loc, w, 64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_fused_prologue_matches_prep_plus_core(dtype, ref_dim):
+    """dtlr_msda_forward_fused == dtlr_msda_prep + dtlr_msda_forward (softmax + sampling locations folded in),
+    and both follow reference ms_deform_attn.py:98-108 (checked against plain torch here)."""
+    from dtlr_b200 import msda, ops, _lib
+    B, Lq, M, L, P = 3, 77, 8, 4, 4
+    g = torch.Generator().manual_seed(5 + ref_dim)
+    shp, lsi = _levels(A_SHAPES)
+    S = 912
+    value = torch.randn(B, S, M, 32, generator=g).to(dtype).cuda()
+    proj = torch.randn(B * Lq, 384, generator=g).cuda()
+    proj[:, :256] *= 2.0
+    ref = torch.rand(B * Lq, ref_dim, generator=g).cuda()
+    if ref_dim == 4:
+        ref[:, 2:] *= 0.3
+    vr = (0.5 + 0.5 * torch.rand(B, L, 2, generator=g)).cuda()
+    sh, ls, n = msda._host_levels(shp.cuda(), lsi.cuda())
+    fused = msda.msda_forward_fused(value, sh, ls, n, proj, ref, vr, Lq, P).float()
+    loc, attn = ops.msda_prep(proj, ref, vr, sh, n, B, Lq, M, P)
+    two = msda.msda_forward_raw(value, sh, ls, n, loc, attn).float()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert torch.allclose(fused, two, rtol=tol, atol=tol)
+    # plain torch statement of the prologue
+    off = proj[:, :256].view(B, Lq, M, L, P, 2)
+    aw = torch.softmax(proj[:, 256:].view(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
+    r = ref.view(B, Lq, 1, ref_dim) * torch.cat([vr, vr], -1)[:, None, :, :ref_dim]
+    if ref_dim == 2:
+        norm = torch.stack([shp[:, 1], shp[:, 0]], -1).float().cuda()
+        loc_t = r[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc_t = r[:, :, None, :, None, :2] + off / P * r[:, :, None, :, None, 2:] * 0.5
+    assert torch.allclose(loc, loc_t, rtol=1e-5, atol=1e-6) and torch.allclose(attn, aw, rtol=1e-5, atol=1e-7)

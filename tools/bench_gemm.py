@@ -35,6 +35,9 @@ def run(M, N, K, iters=20):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3:
+        run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), iters=3)
+        sys.exit(0)
     for (M, N, K) in [(58368, 256, 256), (58368, 384, 256), (58368, 2048, 256), (58368, 256, 2048), (57600, 768, 256),
                       (57600, 256, 512), (40960, 512, 128), (40960, 128, 512)]:
         run(M, N, K)
