@@ -151,11 +151,12 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue
+// (two warps per TMEM lane quarter, each draining half of the tile's columns).
 // Two TMEM accumulators: the MMA warp fills one while the epilogue drains the other.  Epilogue: TMEM -> registers
 // (bias, ReLU) -> XOR-swizzled shared staging -> fully coalesced 16-byte global stores (+ coalesced residual reads).
 template <int BN, int STAGES, typename OutT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmEpi e) {
     using S = GemmSmem<BN, STAGES, OutT>;
@@ -184,7 +185,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 4);          // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[a], 8);          // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -244,8 +245,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) and the matching 32 rows of the staging tile =====
+        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) = 32 tile rows, and column half (w-2)/4 of them =====
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int HW_COLS = BN / 2;
         constexpr int CHUNKS = S::ROW_BYTES / 16;                       // 16-byte chunks per staging row
         constexpr int EPC = 16 / (int)sizeof(OutT);                     // elements per chunk
         unsigned char* my_rows = staging + (size_t)(qd * 32) * S::ROW_BYTES;
@@ -256,16 +259,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             // bias row of this tile -> warp-private shared memory while the MMAs of the tile are still running
-            float* my_bias = bias_s + qd * BN;
+            float* my_bias = bias_s + (warp - 2) * HW_COLS - half * HW_COLS;   // indexed by tile column
             if (e.bias) {
-                for (int j = lane; j < BN; j += 32) my_bias[j] = (n0 + j < e.N) ? __ldg(e.bias + n0 + j) : 0.f;
+                for (int j = half * HW_COLS + lane; j < (half + 1) * HW_COLS; j += 32) my_bias[j] = (n0 + j < e.N) ? __ldg(e.bias + n0 + j) : 0.f;
                 __syncwarp();
             }
             mbar_wait(&tmem_full_bar[as], aph);
             tcgen05_fence_after();
             // ---- step 1: TMEM -> registers -> bias / ReLU -> swizzled staging (thread = row qd*32 + lane)
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = half * HW_COLS; c < (half + 1) * HW_COLS; c += 32) {
                 if (e.dbg & 4) break;
                 uint32_t acc[32];
                 tmem_ld32(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
@@ -309,8 +312,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int ncols = (e.dbg & 1) ? 0 : min(BN, e.N - n0);
             if (vec_ok && (ncols % EPC) == 0) {
                 const int nchunks = ncols / EPC;
-                for (int idx = lane; idx < 32 * CHUNKS; idx += 32) {
-                    const int r = idx / CHUNKS, ch = idx % CHUNKS;
+                constexpr int CW = CHUNKS / 2;                           // chunks per row owned by this warp
+                for (int idx = lane; idx < 32 * CW; idx += 32) {
+                    const int r = idx / CW, ch = half * CW + idx % CW;
                     const int grow = m0 + qd * 32 + r;
                     if (ch >= nchunks || grow >= e.M) continue;
                     uint4 d = *reinterpret_cast<const uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16));
@@ -334,8 +338,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     *reinterpret_cast<uint4*>(cp) = d;
                 }
             } else {
-                for (int idx = lane; idx < 32 * BN; idx += 32) {
-                    const int r = idx / BN, col = idx % BN;
+                for (int idx = lane; idx < 32 * HW_COLS; idx += 32) {
+                    const int r = idx / HW_COLS, col = half * HW_COLS + idx % HW_COLS;
                     const int grow = m0 + qd * 32 + r;
                     if (col >= ncols || grow >= e.M) continue;
                     const int ch = col / EPC;
@@ -465,7 +469,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     const int tiles = ((e.M + GEMM_BM - 1) / GEMM_BM) * ((e.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    k<<<grid, 192, S::TOTAL, st>>>(ta, tb, e);
+    k<<<grid, 320, S::TOTAL, st>>>(ta, tb, e);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

@@ -246,8 +246,13 @@ class InferenceEngine:
             pad_u8 = pad.view(torch.uint8).reshape(-1)
             vh = torch.stack([(~mk[:, :, 0]).sum(1) for mk in masks], 1)
             vw = torch.stack([(~mk[:, 0, :]).sum(1) for mk in masks], 1)
-            hs_t = torch.tensor([hw[0] for hw in level_hw], device=dev, dtype=torch.float32)
-            ws_t = torch.tensor([hw[1] for hw in level_hw], device=dev, dtype=torch.float32)
+            ck = (tuple(level_hw), str(dev))
+            if not hasattr(self, "_consts"):
+                self._consts = {}
+            if ck not in self._consts:      # created once (eager warm-up), so graph capture sees no host->device copy
+                self._consts[ck] = (torch.tensor([hw[0] for hw in level_hw], device=dev, dtype=torch.float32),
+                                    torch.tensor([hw[1] for hw in level_hw], device=dev, dtype=torch.float32))
+            hs_t, ws_t = self._consts[ck]
             vr = torch.stack([vw.float() / ws_t, vh.float() / hs_t], -1).contiguous()            # (B,L,2) = (w,h)
             valid_hw = torch.stack([vh, vw], -1).to(torch.int32).contiguous()
 
