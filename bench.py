@@ -139,12 +139,10 @@ def main():
         run_reference(args, rank)
         return
 
-    import torch.distributed as dist
+    from dtlr_b200 import dist_util
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    dist_util.init("nccl", device)
 
     from dtlr_b200 import _lib, dino, synth
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -155,16 +153,10 @@ def main():
     torch.cuda.synchronize()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        dist_util.barrier(device)
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
+        return dist_util.max_over_ranks(ms, device)
 
     # ---------------- device-resident throughput (`value`) with the dominant kernel family timed by CUDA events
     with torch.no_grad():
@@ -199,7 +191,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1e3)
+    value = dist_util.whole_job_throughput(B, world, args.steps, ms_total)
 
     # ---------------- roofline of the dominant kernel family: the same steps once more, launched eagerly (no CUDA graph) with
     # a CUDA-event pair around every dtlr_gemm launch on its stream; durations are per launch, FLOPs are algorithmic 2*M*N*K
@@ -247,8 +239,7 @@ def main():
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist_util.shutdown()
         return
 
     pk, pk_kind = peaks()
@@ -278,8 +269,7 @@ def main():
                     "api": "DINO.forward(pinned host images) + ctc_view argmax -> host int32 ids"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    dist_util.shutdown()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,56 @@
+"""CPU: the N>1 plumbing with world_size 2 over gloo (127.0.0.1), and the rank behaviour of bench.py --impl reference."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    from dtlr_b200 import dist_util, synth
+    r, w = dist_util.init("gloo")
+    dist_util.barrier()
+    slow = dist_util.max_over_ranks(10.0 + 5.0 * rank)              # rank 1 is the slow one
+    lo, hi = dist_util.shard_range(13, r, w)
+    x = synth.synth_images(2, 8, 16, seed=100 + r)                    # each rank draws its own shard of synthetic lines
+    q.put((r, w, slow, lo, hi, float(x.sum())))
+    dist_util.barrier()
+    dist_util.shutdown()
+
+
+def test_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29533, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [2, 2]
+    assert all(abs(r[2] - 15.0) < 1e-9 for r in res)                  # max over ranks, seen by both
+    assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 7, 7, 13)
+    assert res[0][5] != res[1][5]                                     # different shards
+    from dtlr_b200 import dist_util
+    assert dist_util.whole_job_throughput(64, 2, 10, 1000.0) == 1280.0
+
+
+def test_reference_arm_runs_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env["RANK"] = "0"; env["LOCAL_RANK"] = "0"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
