@@ -85,7 +85,7 @@ mha_simt_kernel(const T* __restrict__ qk, int ld_qk, int k_off, const T* __restr
 // the head (Q x 32 bf16 each) are staged once in shared memory (80-byte row pitch: conflict-free ldmatrix), each warp
 // owns 16 queries at a time and sweeps the keys 64 at a time: S = Q K^T and O += P V on mma.sync m16n8k16 (bf16 in,
 // fp32 accumulate), online softmax in registers with exp2f.  Scores never leave the register file.
-constexpr int FA_WARPS = 8;
+constexpr int FA_WARPS = 16;
 constexpr int FA_PITCH = 40;   // bf16 elements per smem row (32 + 8 padding)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
@@ -254,8 +254,8 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
              (size_t)((Q + 63) / 64 * 64) * FA_PITCH * 2 * 2 <= (size_t)max_smem_optin()) {
         const int KP = (Q + 63) / 64 * 64;
         const size_t smem = (size_t)KP * FA_PITCH * 2 * 2;
-        // two CTAs per (image, head) once a half still fills the 8 warps (16 queries each) a few times over
-        const int splits = Q >= 512 ? 2 : 1;
+        // one round of 16-query tiles per CTA: ceil(Q / 256) CTAs per (image, head), each staging K and V once
+        const int splits = (Q + FA_WARPS * 16 - 1) / (FA_WARPS * 16);
         int q_per_cta = ((Q + splits - 1) / splits + 15) / 16 * 16;
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_flash_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);

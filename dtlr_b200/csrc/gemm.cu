@@ -313,7 +313,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (vec_ok && (ncols % EPC) == 0) {
                 const int nchunks = ncols / EPC;
                 constexpr int CW = CHUNKS / 2;                           // chunks per row owned by this warp
-                for (int idx = lane; idx < 32 * CW; idx += 32) {
+                constexpr int NIT = CW;                                  // 32 rows * CW chunks / 32 lanes
+                // all residual loads of this warp's 32 x (BN/2) block are issued before anything consumes them
+                constexpr int GRP = NIT < 8 ? NIT : 8;                   // residual prefetch depth (register budget)
+#pragma unroll 1
+                for (int g0 = 0; g0 < NIT; g0 += GRP) {
+                uint4 rres[GRP];
+                if (e.residual) {
+#pragma unroll
+                    for (int it = 0; it < GRP; ++it) {
+                        const int idx = (g0 + it) * 32 + lane;
+                        const int r = idx / CW, ch = half * CW + idx % CW;
+                        const int grow = m0 + qd * 32 + r;
+                        rres[it] = make_uint4(0, 0, 0, 0);
+                        if (ch < nchunks && grow < e.M)
+                            rres[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const OutT*>(e.residual) + (size_t)grow * e.ldr + n0 + ch * EPC));
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < GRP; ++it) {
+                    const int idx = (g0 + it) * 32 + lane;
                     const int r = idx / CW, ch = half * CW + idx % CW;
                     const int grow = m0 + qd * 32 + r;
                     if (ch >= nchunks || grow >= e.M) continue;
@@ -323,9 +342,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         float f[EPC];
                         unpack_chunk<OutT>(d, f);
                         if (e.residual) {
-                            const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const OutT*>(e.residual) + (size_t)grow * e.ldr + n0 + ch * EPC);
                             float g[EPC];
-                            unpack_chunk<OutT>(rr, g);
+                            unpack_chunk<OutT>(rres[it], g);
 #pragma unroll
                             for (int k = 0; k < EPC; ++k) f[k] += g[k];
                         }
@@ -336,6 +354,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         d = pack_chunk<OutT>(f);
                     }
                     *reinterpret_cast<uint4*>(cp) = d;
+                }
                 }
             } else {
                 for (int idx = lane; idx < 32 * HW_COLS; idx += 32) {

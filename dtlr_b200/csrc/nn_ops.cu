@@ -430,6 +430,70 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long
         stf<TO>(out + i, ldf<TI>(x + i));
 }
 
+// ---------------------------------------------------------------------------------------------- ResNet stem, direct
+// conv1 7x7 / stride 2 / pad 3, 3 -> 64 channels, + folded FrozenBatchNorm + ReLU (torchvision resnet50 stem as wrapped by
+// reference models/dino/backbone.py:109-128), straight from the fp32 NCHW network input to NHWC activations.  K = 147 is
+// too thin for the tensor-core path to pay for a 200 MB im2col round trip, so this one convolution runs on FFMA:
+// CTA = 2 x 64 output pixels x 64 channels, input patch (parity-split columns -> conflict-free stride-2 taps) and the
+// 147 x 64 weight matrix in shared memory, thread = one pixel x 32 output channels.
+constexpr int STEM_TH = 2, STEM_TW = 64, STEM_PR = STEM_TH * 2 + 5, STEM_PC = STEM_TW * 2 + 5;   // patch 9 x 133
+constexpr int STEM_PCH = (STEM_PC + 1) / 2;                                                      // columns per parity plane (67)
+template <typename TO>
+__global__ void __launch_bounds__(256)
+stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out,
+                    int H, int W, int Ho, int Wo) {
+    extern __shared__ float stem_smem[];
+    float* ws = stem_smem;                                   // [147][64]
+    float* patch = stem_smem + 147 * 64;                     // [3][STEM_PR][2 parities][STEM_PCH + 1]
+    constexpr int PPL = STEM_PCH + 1;
+    const int b = blockIdx.z, oh0 = blockIdx.y * STEM_TH, ow0 = blockIdx.x * STEM_TW;
+    for (int i = threadIdx.x; i < 147 * 64; i += 256) ws[i] = w[i];
+    const int ih0 = oh0 * 2 - 3, iw0 = ow0 * 2 - 3;
+    for (int i = threadIdx.x; i < 3 * STEM_PR * STEM_PC; i += 256) {
+        const int c = i / (STEM_PR * STEM_PC), rem = i % (STEM_PR * STEM_PC);
+        const int r = rem / STEM_PC, col = rem % STEM_PC;
+        const int ih = ih0 + r, iw = iw0 + col;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)b * 3 + c) * H + ih) * W + iw];
+        patch[((c * STEM_PR + r) * 2 + (col & 1)) * PPL + (col >> 1)] = v;
+    }
+    __syncthreads();
+    const int pix = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int pr = pix / STEM_TW, pc = pix % STEM_TW;
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = patch[((c * STEM_PR + pr * 2 + kh) * 2 + (kw & 1)) * PPL + pc + (kw >> 1)];
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((kh * 7 + kw) * 3 + c) * 64 + half * 32);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 w4 = wp[k];
+                    acc[4 * k] = fmaf(v, w4.x, acc[4 * k]);
+                    acc[4 * k + 1] = fmaf(v, w4.y, acc[4 * k + 1]);
+                    acc[4 * k + 2] = fmaf(v, w4.z, acc[4 * k + 2]);
+                    acc[4 * k + 3] = fmaf(v, w4.w, acc[4 * k + 3]);
+                }
+            }
+        }
+    }
+    const int oh = oh0 + pr, ow = ow0 + pc;
+    if (oh < Ho && ow < Wo) {
+        TO* o = out + (((size_t)b * Ho + oh) * Wo + ow) * 64 + half * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v8[j] = fmaxf(acc[k + j] + bias[half * 32 + k + j], 0.f);
+            st8<TO>(o + k, v8);
+        }
+    }
+}
+
 static inline int grid_for(long long n, int threads) {
     long long g = (n + threads - 1) / threads;
     const long long cap = (long long)sm_count() * 32;
@@ -462,6 +526,25 @@ extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C,
         set_error("im2col: unsupported dtype/layout combination");
         return DTLR_ERR_UNSUPPORTED;
     }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_stem_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Ho, int Wo,
+                              int out_dtype, void* stream) {
+    DTLR_CHECK_ARG(Ho == (H + 6 - 7) / 2 + 1 && Wo == (W + 6 - 7) / 2 + 1, "stem_conv: output size does not match 7x7/s2/p3");
+    if (B == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(B <= 65535, "stem_conv: batch too large");
+    const size_t smem = (size_t)(147 * 64 + 3 * STEM_PR * 2 * (STEM_PCH + 1)) * sizeof(float);
+    dim3 grid((Wo + STEM_TW - 1) / STEM_TW, (Ho + STEM_TH - 1) / STEM_TH, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == DTLR_F32) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv7x7_kernel<float><<<grid, 256, smem, st>>>(x, w, bias, (float*)out, H, W, Ho, Wo);
+    } else if (out_dtype == DTLR_BF16) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv7x7_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo);
+    } else { set_error("stem_conv: unsupported dtype"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

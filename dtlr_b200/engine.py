@@ -56,7 +56,9 @@ class InferenceEngine:
         tr = m.transformer
         body = m.backbone[0].body
         P = {}
-        P["stem"] = _fold_conv_bn(body.conv1, body.bn1, dtype)
+        sc, sb = body.bn1.scale_bias()
+        P["stem_direct"] = ((body.conv1.weight.detach().float() * sc.float().view(-1, 1, 1, 1)).permute(2, 3, 1, 0).contiguous(),
+                            sb.detach().float().contiguous())          # [kh][kw][cin][cout] fp32, bias
         blocks = []
         for li in range(1, 5):
             for blk in getattr(body, "layer%d" % li):
@@ -119,8 +121,7 @@ class InferenceEngine:
         return ops.gemm(h, *layers[2], out_dtype=torch.float32 if out_f32_last else None)
 
     def _backbone(self, P, x, B, H, W, T):
-        col, Ho, Wo = ops.im2col(x, B, H, W, 3, 7, 7, 2, 3, T, nchw_input=True, ldo=P["stem"][0].shape[1])
-        y = ops.gemm(col, *P["stem"], relu=1)
+        y, Ho, Wo = ops.stem_conv(x, *P["stem_direct"], B, H, W, T)
         y, Hc, Wc = ops.maxpool3x3s2(y, B, Ho, Wo, 64)
         feats = []
         cin = 64

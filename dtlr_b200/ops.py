@@ -60,6 +60,13 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
     return out, Ho, Wo
 
 
+def stem_conv(x, w_khkwcico, bias, B, H, W, out_dtype):
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty((B * Ho * Wo, 64), dtype=out_dtype, device=x.device)
+    _call("dtlr_stem_conv", _p(x), _p(w_khkwcico), _p(bias), _p(out), B, H, W, Ho, Wo, L.dtype_code(out), _st(x))
+    return out, Ho, Wo
+
+
 def maxpool3x3s2(x, B, H, W, C):
     Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
     out = torch.empty((B * Ho * Wo, C), dtype=x.dtype, device=x.device)

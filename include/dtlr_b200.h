@@ -103,6 +103,11 @@ int dtlr_debug_flags(int flags);
  */
 int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho,
                 int Wo, int ldo, int in_dtype, int out_dtype, int nchw_input, void* stream);
+/* ResNet stem: conv1 7x7/s2/p3 (3->64) + folded FrozenBatchNorm + ReLU, direct (no im2col): x fp32 NCHW [B,3,H,W],
+ * w fp32 [7][7][3][64] (BN scale folded), bias fp32 [64] -> out NHWC [B*Ho*Wo, 64] of out_dtype.
+ * (torchvision resnet50.conv1/bn1/relu as wrapped by models/dino/backbone.py:109-128, FrozenBatchNorm2d :62-72) */
+int dtlr_stem_conv(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Ho, int Wo,
+                   int out_dtype, void* stream);
 /* 3x3 / stride 2 / pad 1 max-pool of the ResNet stem, NHWC, C % 8 == 0 */
 int dtlr_maxpool3x3s2(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, int dtype, void* stream);
 /* nn.GroupNorm(G, C), eps (models/dino/dino.py:121-124) over one feature level: x fp32 [B,HW,C] -> out rows
