@@ -221,9 +221,7 @@ def main():
     def e2e_step():
         x = host_imgs.to(device, non_blocking=True)
         o = model(x)
-        new = dino.ctc_view(o["pred_logits"], o["pred_boxes"])
-        ids = new.argmax(-1).to(torch.int32)
-        return ids.cpu()
+        return dino.decode_frames(o).cpu()
 
     with torch.no_grad():
         for _ in range(2):
@@ -266,7 +264,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": host_imgs.numel() * 4 ,
                     "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "api": "DINO.forward(pinned host images) + ctc_view argmax -> host int32 ids"},
+                    "api": "DINO.forward(pinned host images) + dino.decode_frames (fused CTC-view argmax) -> host int32 frame ids"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     dist_util.shutdown()

@@ -85,7 +85,8 @@ mha_simt_kernel(const T* __restrict__ qk, int ld_qk, int k_off, const T* __restr
 // the head (Q x 32 bf16 each) are staged once in shared memory (80-byte row pitch: conflict-free ldmatrix), each warp
 // owns 16 queries at a time and sweeps the keys 64 at a time: S = Q K^T and O += P V on mma.sync m16n8k16 (bf16 in,
 // fp32 accumulate), online softmax in registers with exp2f.  Scores never leave the register file.
-constexpr int FA_WARPS = 16;
+constexpr int FA_WARPS = 8;
+constexpr int FA_MT = 2;        // 16-query m-tiles per warp
 constexpr int FA_PITCH = 40;   // bf16 elements per smem row (32 + 8 padding)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
@@ -108,6 +109,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// MT = 16-query m-tiles per warp: every K / V fragment fetched from shared memory feeds MT MMAs (MT = 2 halves the
+// ldmatrix traffic per FLOP, which is what bounds the MT = 1 version).
+template <int MT>
 __global__ void __launch_bounds__(FA_WARPS * 32)
 mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off, const __nv_bfloat16* __restrict__ v, int ld_v,
                       __nv_bfloat16* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
@@ -142,95 +146,120 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
     const int k_row = lane & 7, k_chunk = lane >> 3;
     const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_chunk = lane >> 4;
 
-    for (int q0 = q_begin + warp * 16; q0 < q_end; q0 += FA_WARPS * 16) {
+    for (int q0 = q_begin + warp * (16 * MT); q0 < q_end; q0 += FA_WARPS * 16 * MT) {
         // ---- Q fragments (A operand, 2 k-steps over dh = 32), straight from global memory
-        uint32_t qa[2][4];
-        const int r_lo = min(q0 + g, Q - 1), r_hi = min(q0 + g + 8, Q - 1);
-        const __nv_bfloat16* qlo = qk + (row0 + r_lo) * ld_qk + h * 32;
-        const __nv_bfloat16* qhi = qk + (row0 + r_hi) * ld_qk + h * 32;
+        uint32_t qa[MT][2][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            qa[ks][0] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 2 * t);
-            qa[ks][1] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 2 * t);
-            qa[ks][2] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 8 + 2 * t);
-            qa[ks][3] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 8 + 2 * t);
+        for (int mt = 0; mt < MT; ++mt) {
+            const int r_lo = min(q0 + mt * 16 + g, Q - 1), r_hi = min(q0 + mt * 16 + g + 8, Q - 1);
+            const __nv_bfloat16* qlo = qk + (row0 + r_lo) * ld_qk + h * 32;
+            const __nv_bfloat16* qhi = qk + (row0 + r_hi) * ld_qk + h * 32;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                qa[mt][ks][0] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 2 * t);
+                qa[mt][ks][1] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 2 * t);
+                qa[mt][ks][2] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 8 + 2 * t);
+                qa[mt][ks][3] = *reinterpret_cast<const uint32_t*>(qhi + ks * 16 + 8 + 2 * t);
+            }
         }
-        float o[4][4];
+        float o[MT][4][4];
+        float m_lo[MT], m_hi[MT], l_lo[MT], l_hi[MT];
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
+        for (int mt = 0; mt < MT; ++mt) {
+            m_lo[mt] = m_hi[mt] = -INFINITY;
+            l_lo[mt] = l_hi[mt] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[n][k] = 0.f;
-        float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[mt][n][k] = 0.f;
+        }
 
         for (int kb = 0; kb < KP; kb += 64) {
-            // ---- S = Q K^T for 64 keys: 8 n-blocks of 8 keys
-            float sc[8][4];
+            // ---- S = Q K^T for 64 keys: 8 n-blocks of 8 keys, each K fragment reused by the MT m-tiles
+            float sc[MT][8][4];
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 uint32_t kf[4];
                 ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + k_row) * FA_PITCH + k_chunk * 8);
-                sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
-                mma_bf16_16816(sc[n], qa[0], kf[0], kf[1]);
-                mma_bf16_16816(sc[n], qa[1], kf[2], kf[3]);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
+                    mma_bf16_16816(sc[mt][n], qa[mt][0], kf[0], kf[1]);
+                    mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
+                }
             }
             if (kb + 64 > Q) {    // key padding -> -inf
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                     const int key = kb + n * 8 + 2 * t;
-                    if (key >= Q) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
-                    if (key + 1 >= Q) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (key >= Q) { sc[mt][n][0] = -INFINITY; sc[mt][n][2] = -INFINITY; }
+                        if (key + 1 >= Q) { sc[mt][n][1] = -INFINITY; sc[mt][n][3] = -INFINITY; }
+                    }
                 }
             }
-            // ---- online softmax (rows g and g+8 of the tile); a quad of lanes shares a row
-            float mx_lo = m_lo, mx_hi = m_hi;
+            // ---- online softmax (rows g and g+8 of each m-tile); a quad of lanes shares a row
+            uint32_t pa[MT][4][4];    // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                mx_lo = fmaxf(mx_lo, fmaxf(sc[n][0], sc[n][1]));
-                mx_hi = fmaxf(mx_hi, fmaxf(sc[n][2], sc[n][3]));
+            for (int mt = 0; mt < MT; ++mt) {
+                float mx_lo = m_lo[mt], mx_hi = m_hi[mt];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    mx_lo = fmaxf(mx_lo, fmaxf(sc[mt][n][0], sc[mt][n][1]));
+                    mx_hi = fmaxf(mx_hi, fmaxf(sc[mt][n][2], sc[mt][n][3]));
+                }
+                mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+                mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+                mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+                mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+                const float c_lo = exp2f((m_lo[mt] - mx_lo) * scale_log2), c_hi = exp2f((m_hi[mt] - mx_hi) * scale_log2);
+                m_lo[mt] = mx_lo; m_hi[mt] = mx_hi;
+                l_lo[mt] *= c_lo; l_hi[mt] *= c_hi;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) { o[mt][n][0] *= c_lo; o[mt][n][1] *= c_lo; o[mt][n][2] *= c_hi; o[mt][n][3] *= c_hi; }
+                const float ml = mx_lo * scale_log2, mh = mx_hi * scale_log2;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float p0 = exp2f(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = exp2f(fmaf(sc[mt][n][1], scale_log2, -ml));
+                    const float p2 = exp2f(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = exp2f(fmaf(sc[mt][n][3], scale_log2, -mh));
+                    l_lo[mt] += p0 + p1;
+                    l_hi[mt] += p2 + p3;
+                    pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
+                    pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
+                }
             }
-            mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-            mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-            mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-            mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-            const float c_lo = exp2f((m_lo - mx_lo) * scale_log2), c_hi = exp2f((m_hi - mx_hi) * scale_log2);
-            m_lo = mx_lo; m_hi = mx_hi;
-            l_lo *= c_lo; l_hi *= c_hi;
-#pragma unroll
-            for (int n = 0; n < 4; ++n) { o[n][0] *= c_lo; o[n][1] *= c_lo; o[n][2] *= c_hi; o[n][3] *= c_hi; }
-            const float ml = m_lo * scale_log2, mh = m_hi * scale_log2;
-            uint32_t pa[4][4];    // P as A fragments: 4 k-steps of 16 keys
-#pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                const float p0 = exp2f(fmaf(sc[n][0], scale_log2, -ml)), p1 = exp2f(fmaf(sc[n][1], scale_log2, -ml));
-                const float p2 = exp2f(fmaf(sc[n][2], scale_log2, -mh)), p3 = exp2f(fmaf(sc[n][3], scale_log2, -mh));
-                l_lo += p0 + p1;
-                l_hi += p2 + p3;
-                pa[n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
-                pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
-            }
-            // ---- O += P V
+            // ---- O += P V, each V fragment reused by the MT m-tiles
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
                 for (int nn = 0; nn < 2; ++nn) {
                     uint32_t vf[4];
                     ldmatrix_x4_trans(vf, Vs + (size_t)(kb + kk * 16 + v_row) * FA_PITCH + (nn * 2 + v_chunk) * 8);
-                    mma_bf16_16816(o[nn * 2], pa[kk], vf[0], vf[1]);
-                    mma_bf16_16816(o[nn * 2 + 1], pa[kk], vf[2], vf[3]);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_bf16_16816(o[mt][nn * 2], pa[mt][kk], vf[0], vf[1]);
+                        mma_bf16_16816(o[mt][nn * 2 + 1], pa[mt][kk], vf[2], vf[3]);
+                    }
                 }
             }
         }
-        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-        const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            if (q0 + g < q_end)
-                *reinterpret_cast<uint32_t*>(out + (row0 + q0 + g) * ld_o + h * 32 + n * 8 + 2 * t) = pack_bf16(o[n][0] * i_lo, o[n][1] * i_lo);
-            if (q0 + g + 8 < q_end)
-                *reinterpret_cast<uint32_t*>(out + (row0 + q0 + g + 8) * ld_o + h * 32 + n * 8 + 2 * t) = pack_bf16(o[n][2] * i_hi, o[n][3] * i_hi);
+        for (int mt = 0; mt < MT; ++mt) {
+            float ll = l_lo[mt], lh = l_hi[mt];
+            ll += __shfl_xor_sync(0xffffffffu, ll, 1);
+            ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+            lh += __shfl_xor_sync(0xffffffffu, lh, 1);
+            lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+            const float i_lo = 1.f / ll, i_hi = 1.f / lh;
+            const int qr = q0 + mt * 16 + g;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                if (qr < q_end)
+                    *reinterpret_cast<uint32_t*>(out + (row0 + qr) * ld_o + h * 32 + n * 8 + 2 * t) = pack_bf16(o[mt][n][0] * i_lo, o[mt][n][1] * i_lo);
+                if (qr + 8 < q_end)
+                    *reinterpret_cast<uint32_t*>(out + (row0 + qr + 8) * ld_o + h * 32 + n * 8 + 2 * t) = pack_bf16(o[mt][n][2] * i_hi, o[mt][n][3] * i_hi);
+            }
         }
     }
 }
@@ -254,12 +283,13 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
              (size_t)((Q + 63) / 64 * 64) * FA_PITCH * 2 * 2 <= (size_t)max_smem_optin()) {
         const int KP = (Q + 63) / 64 * 64;
         const size_t smem = (size_t)KP * FA_PITCH * 2 * 2;
-        // one round of 16-query tiles per CTA: ceil(Q / 256) CTAs per (image, head), each staging K and V once
-        const int splits = (Q + FA_WARPS * 16 - 1) / (FA_WARPS * 16);
-        int q_per_cta = ((Q + splits - 1) / splits + 15) / 16 * 16;
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_flash_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // one round of (16*MT)-query tiles per CTA: ceil(Q / 256) CTAs per (image, head), each staging K and V once
+        const int per_round = FA_WARPS * 16 * FA_MT;
+        const int splits = (Q + per_round - 1) / per_round;
+        int q_per_cta = ((Q + splits - 1) / splits + 16 * FA_MT - 1) / (16 * FA_MT) * (16 * FA_MT);
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_flash_bf16_kernel<FA_MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
-        mha_flash_bf16_kernel<<<fgrid, FA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v,
+        mha_flash_bf16_kernel<FA_MT><<<fgrid, FA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v,
                                                                   (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f);
     } else if (dtype == DTLR_BF16)
         mha_simt_kernel<__nv_bfloat16><<<grid, ATT_QT, 0, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v, attn_mask, (__nv_bfloat16*)out, ld_o, Q, scale);

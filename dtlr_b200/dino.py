@@ -313,6 +313,13 @@ class SetCriterion(nn.Module):
                                   "(SURVEY.md §8f); DTLR fine-tuning and evaluation call loss_CTC directly")
 
 
+def decode_frames(outputs, eps=0.003):
+    """fused CUDA decode of a model output dict: int32 (B,Q) frame labels in reading order (0 = blank, c+1 = class c);
+    equals ctc_view(...).argmax(-1) without materialising (B,Q,C+1) (reference dino.py:472-502 + engine.py:523-529)."""
+    from . import ops
+    return ops.ctc_decode(outputs["pred_logits"], outputs["pred_boxes"], eps)
+
+
 def convert_output_to_pred(new_pred_logits):
     """reference engine.py:512-530 (duplicate=False): argmax over C+1, drop blanks, shift by one."""
     am = new_pred_logits.argmax(-1)

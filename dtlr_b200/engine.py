@@ -151,7 +151,8 @@ class InferenceEngine:
             val = value_src_or_value
         else:
             val = ops.gemm(value_src_or_value, *a["val"])
-            ops.zero_masked_rows_(val, pad_u8)
+            if pad_u8 is not None:
+                ops.zero_masked_rows_(val, pad_u8)
         oa = ops.gemm(query, *a["oa"], out_dtype=torch.float32)
         val4 = val.view(B, S, M, val.shape[1] // M)
         if nlev * Pn <= 16 and val4.shape[-1] == 32:
@@ -176,7 +177,8 @@ class InferenceEngine:
         from .misc import NestedTensor
         m = self.model
         x, mask = samples.tensors, samples.mask
-        key = (tuple(x.shape), str(x.device), m.compute_dtype, m.engine_outputs, self._pack_key(m.compute_dtype, x.device))
+        key = (tuple(x.shape), str(x.device), m.compute_dtype, m.engine_outputs, bool(getattr(samples, "nopad", False)),
+               self._pack_key(m.compute_dtype, x.device))
         ent = self._graphs.get(key) if hasattr(self, "_graphs") else None
         if ent is None:
             if not hasattr(self, "_graphs"):
@@ -187,12 +189,12 @@ class InferenceEngine:
             side.wait_stream(torch.cuda.current_stream(x.device))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self._forward_eager(NestedTensor(sx, sm), None)
+                    self._forward_eager(NestedTensor(sx, sm, getattr(samples, "nopad", False)), None)
             torch.cuda.current_stream(x.device).wait_stream(side)
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._forward_eager(NestedTensor(sx, sm), None)
+                out = self._forward_eager(NestedTensor(sx, sm, getattr(samples, "nopad", False)), None)
             ent = (graph, sx, sm, out)
             if len(self._graphs) > 8:
                 self._graphs.clear()
@@ -245,6 +247,7 @@ class InferenceEngine:
             masks = [F.interpolate(mask[None].float(), size=hw).to(torch.bool)[0] for hw in level_hw]
             pad = torch.cat([mk.flatten(1) for mk in masks], 1).contiguous()
             pad_u8 = pad.view(torch.uint8).reshape(-1)
+            pad_rows = None if getattr(samples, "nopad", False) else pad_u8     # value.masked_fill is a no-op without padding
             vh = torch.stack([(~mk[:, :, 0]).sum(1) for mk in masks], 1)
             vw = torch.stack([(~mk[:, 0, :]).sum(1) for mk in masks], 1)
             ck = (tuple(level_hw), str(dev))
@@ -284,7 +287,7 @@ class InferenceEngine:
             ref_enc = ops.enc_ref_points(vr, shapes_host, nlev, B, S)
             q = ops.add(src, pos)
             for i, lyr in enumerate(P["enc"]):
-                core = self._msda(lyr["attn"], q, ref_enc, 2, src, pad_u8, vr, shapes_host, lsi_host, nlev, B, S, S, T)
+                core = self._msda(lyr["attn"], q, ref_enc, 2, src, pad_rows, vr, shapes_host, lsi_host, nlev, B, S, S, T)
                 if st is not None and i == 0:
                     st["enc0_core"] = core.view(B, S, d)
                 x1 = ops.gemm(core, *lyr["attn"]["out"], residual=src)
@@ -329,7 +332,7 @@ class InferenceEngine:
                 att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
                 x1 = ops.gemm(att, *lyr["o"], residual=tgt)
                 tgt, qca = ops.add_layernorm(x1, None, *lyr["ln2"], add2=qp)
-                core = self._msda(lyr["ca"], qca, ref, 4, memory, pad_u8, vr, shapes_host, lsi_host, nlev, B, Q, S, T)
+                core = self._msda(lyr["ca"], qca, ref, 4, memory, pad_rows, vr, shapes_host, lsi_host, nlev, B, Q, S, T)
                 if st is not None and i == 0:
                     st["dec0_core"] = core.view(B, Q, d)
                 x2 = ops.gemm(core, *lyr["ca"]["out"], residual=tgt)

@@ -8,13 +8,14 @@ from torch import Tensor
 class NestedTensor(object):
     """mirror of reference util/misc.py:301-372 (tensors + padding mask, True on padding)."""
 
-    def __init__(self, tensors, mask: Optional[Tensor]):
+    def __init__(self, tensors, mask: Optional[Tensor], nopad: bool = False):
         self.tensors = tensors
         self.mask = mask
+        self.nopad = nopad      # dtlr_b200 hint: the mask is known (on the host) to be all-False -> padding passes are skipped
 
     def to(self, device):
         m = self.mask.to(device) if self.mask is not None else None
-        return NestedTensor(self.tensors.to(device), m)
+        return NestedTensor(self.tensors.to(device), m, self.nopad)
 
     def decompose(self):
         return self.tensors, self.mask
@@ -32,7 +33,7 @@ def nested_tensor_from_tensor_list(tensor_list: List[Tensor]):
     (a (B,C,H,W) tensor iterates as a list of equally sized images -> all-False mask)."""
     if torch.is_tensor(tensor_list) and tensor_list.dim() == 4:
         b, c, h, w = tensor_list.shape
-        return NestedTensor(tensor_list, torch.zeros((b, h, w), dtype=torch.bool, device=tensor_list.device))
+        return NestedTensor(tensor_list, torch.zeros((b, h, w), dtype=torch.bool, device=tensor_list.device), nopad=True)
     if tensor_list[0].ndim != 3:
         raise ValueError("not supported")
     c = tensor_list[0].shape[0]
@@ -44,7 +45,8 @@ def nested_tensor_from_tensor_list(tensor_list: List[Tensor]):
     for img, pad_img, m in zip(tensor_list, tensor, mask):
         pad_img[: img.shape[0], : img.shape[1], : img.shape[2]].copy_(img)
         m[: img.shape[1], : img.shape[2]] = False
-    return NestedTensor(tensor, mask)
+    same = all(int(t.shape[1]) == h and int(t.shape[2]) == w for t in tensor_list)
+    return NestedTensor(tensor, mask, nopad=same)
 
 
 def inverse_sigmoid(x, eps=1e-3):

@@ -177,3 +177,22 @@ def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
     _call("dtlr_mha_self_attention", _p(qk), qk.stride(0), k_off, _p(v), v.stride(0), _p(attn_mask_u8), _p(out), out.stride(0),
           B, Q, heads, head_dim, L.dtype_code(v), _st(v))
     return out
+
+
+def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
+    """fused CTC-view decode: pred_logits fp32 (B,Q,C), pred_boxes fp32 (B,Q,4) -> frames int32 (B,Q) in reading order
+    (0 = blank, c+1 = class c) [, new_pred_logits fp32 (B,Q,C+1)]."""
+    import ctypes
+    L.require_cuda(pred_logits, pred_boxes)
+    B, Q, C = pred_logits.shape
+    logits = pred_logits.float().contiguous()
+    boxes = pred_boxes.float().contiguous()
+    dev = logits.device
+    frames = torch.empty((B, Q), dtype=torch.int32, device=dev)
+    label = torch.empty((B, Q), dtype=torch.int32, device=dev)
+    perm = torch.empty((B, Q), dtype=torch.int32, device=dev) if want_new_pred else None
+    rsum = torch.empty((B, Q), dtype=torch.float32, device=dev) if want_new_pred else None
+    newp = torch.empty((B, Q, C + 1), dtype=torch.float32, device=dev) if want_new_pred else None
+    _call("dtlr_ctc_decode", _p(logits), C, _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum), B, Q, C,
+          ctypes.c_float(eps), _st(logits))
+    return (frames, newp) if want_new_pred else frames

@@ -154,6 +154,13 @@ int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype
  * attn_mask uint8 [Q,Q], 1 = blocked, or NULL; out [B*Q, ld_o]. */
 int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const unsigned char* attn_mask,
                             void* out, int ld_o, int B, int Q, int heads, int head_dim, int dtype, void* stream);
+/* The "CTC view" decode tail, fused (models/dino/dino.py:472-502 transform + engine.py:512-530 argmax; evaluation.py:116-158
+ * uses eps = 0.03/C): frames[b,pos] = argmax over [blank, classes] of the pos-th query in cx order (0 = blank, c+1 = class c).
+ * logits fp32 [B*Q, ld], boxes fp32 [B*Q,4] (cx first).  perm (int32 [B,Q], may be NULL) receives the sort permutation,
+ * new_pred (fp32 [B,Q,C+1], may be NULL; needs perm + scratch_sum) the full new_pred_logits tensor.  scratch_label int32 [B*Q],
+ * scratch_sum fp32 [B*Q] (may be NULL when new_pred is NULL). */
+int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
+                    int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,34 @@
+"""GPU: the fused CTC-view decode (dtlr_ctc_decode) against the committed reference decode (argmax frames of
+reference loss_CTC's new_pred_logits, fixture dino_A_b2) and against the torch statement on random inputs, including the
+evaluation.py eps variant, the renormalised branch and a wide head."""
+import numpy as np
+import pytest
+import torch
+
+from dtlr_b200 import dino, ops
+from gpu_common import fixture, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_matches_reference_frames_fixture():
+    fx = fixture("dino_A_b2")
+    logits, boxes = torch.from_numpy(fx["pred_logits"]).cuda(), torch.from_numpy(fx["pred_boxes"]).cuda()
+    frames, new = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)
+    assert (frames.cpu().numpy() == fx["ctc_argmax"]).all()
+    assert rel(new[:, ::4].cpu(), fx["ctc_new_pred_s"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,Q,C,eps,shift", [(3, 900, 166, 0.003, -6.0), (2, 986, 166, 0.03 / 166, -4.0), (2, 300, 7356, 0.003, -9.0), (1, 17, 5, 0.003, 0.0)])
+def test_matches_torch_statement(B, Q, C, eps, shift):
+    g = torch.Generator(device="cuda").manual_seed(Q + C)
+    logits = torch.randn(B, Q, C, device="cuda", generator=g) * 2.0 + shift
+    boxes = torch.rand(B, Q, 4, device="cuda", generator=g)
+    frames, new = ops.ctc_decode(logits, boxes, eps, want_new_pred=True)
+    ref_new = dino.ctc_view(logits, boxes, eps)
+    assert torch.allclose(new, ref_new, rtol=1e-5, atol=1e-7)
+    top2 = ref_new.topk(2, dim=-1)[0]
+    decided = (top2[..., 0] - top2[..., 1]) > 1e-6
+    assert (frames.long() == ref_new.argmax(-1))[decided].all()
+    s = logits.sigmoid().sum(-1)
+    assert (s < 1 - eps).any() or C <= 5

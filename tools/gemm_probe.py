@@ -18,6 +18,6 @@ def t(M, N, K, flags, iters=20):
     _lib.lib().dtlr_debug_flags(0)
     return e0.elapsed_time(e1) * 1000 / iters
 
-for (M, N, K) in [(58368, 256, 256), (58368, 256, 2048), (58368, 2048, 256)]:
+for (M, N, K) in [(58368, 256, 256), (58368, 256, 2048), (58368, 2048, 256), (163840, 256, 64), (57600, 512, 256)]:
     print(M, N, K, {name: round(t(M, N, K, f), 1) for name, f in
-                    [("full", 0), ("no_store", 1), ("no_mma", 2), ("no_mma_no_store", 3), ("no_epilogue", 5), ("loads_only", 7)]})
+                    [("full_bn256", 0), ("full_bn128", 8), ("no_store", 1), ("no_mma", 2), ("no_epilogue", 5), ("loads_only", 7)]})
