@@ -85,8 +85,8 @@ mha_simt_kernel(const T* __restrict__ qk, int ld_qk, int k_off, const T* __restr
 // the head (Q x 32 bf16 each) are staged once in shared memory (80-byte row pitch: conflict-free ldmatrix), each warp
 // owns 16 queries at a time and sweeps the keys 64 at a time: S = Q K^T and O += P V on mma.sync m16n8k16 (bf16 in,
 // fp32 accumulate), online softmax in registers with exp2f.  Scores never leave the register file.
-constexpr int FA_WARPS = 8;
-constexpr int FA_MT = 2;        // 16-query m-tiles per warp
+constexpr int FA_WARPS = 16;
+constexpr int FA_MT = 1;        // 16-query m-tiles per warp (MT = 2 with 8 warps measured slower: 305 vs 287 us/layer)
 constexpr int FA_PITCH = 40;   // bf16 elements per smem row (32 + 8 padding)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {

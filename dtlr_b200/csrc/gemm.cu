@@ -522,7 +522,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
                    "gemm: bf16 operands need 16-byte aligned rows (lda=%d ldw=%d)", lda, ldw);
     CUtensorMap ta, tb;
     int rc;
-    if (out_dtype == DTLR_BF16 && (N % 256) == 0 && !(g_debug_flags & 8)) {
+    if (out_dtype == DTLR_BF16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
         // N = 256 layers become one tile per row block
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;

@@ -83,7 +83,7 @@ struct FusedArgs {
 };
 
 template <typename T, bool STAGE, bool SINGLE, bool FUSED, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, NWARPS == 16 ? 2 : 1)   // <= 64 registers: 32 resident warps per SM
 msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                     T* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
                     const int P, const int q_per_cta, const FusedArgs fz) {
@@ -130,8 +130,34 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
     const int src0 = g + 16 * side;
     const uint32_t lane_off = STAGE ? (uint32_t)(ROWB + sub * 16) : (uint32_t)((sub - side * LPP) * 16);
 
+    // SINGLE: the raw per-query inputs of this lane (FUSED: offset pair, logit, reference box; else location pair and
+    // weight) are fetched one query ahead, so their global-memory latency hides behind the previous query's gather.
+    float2 pf_a = make_float2(0.f, 0.f);
+    float pf_b = 0.f;
+    float4 pf_ref = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto prefetch = [&](int q) {
+        const int pt = min(pt16, LP - 1);
+        if (FUSED) {
+            const size_t row = (size_t)b * Lq + q;
+            const float* pr = loc + row * fz.ld;
+            pf_a = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
+            pf_b = pr[(size_t)M * LP * 2 + (size_t)m * LP + pt];
+            if (fz.RD == 4) pf_ref = *reinterpret_cast<const float4*>(fz.ref + row * 4);
+            else { const float2 r2 = *reinterpret_cast<const float2*>(fz.ref + row * 2); pf_ref = make_float4(r2.x, r2.y, 0.f, 0.f); }
+        } else {
+            const size_t pb = ((size_t)((size_t)b * Lq + q) * M + m) * LP;
+            pf_a = *reinterpret_cast<const float2*>(loc + (pb + pt) * 2);
+            pf_b = attn[pb + pt];
+        }
+    };
+    if (SINGLE && q0 + warp < q1) prefetch(q0 + warp);
+
     for (int q = q0 + warp; q < q1; q += NWARPS) {
         const size_t pbase = ((size_t)((size_t)b * Lq + q) * M + m) * LP;
+        const float2 cur_a = pf_a;
+        const float cur_b = pf_b;
+        const float4 cur_ref = pf_ref;
+        if (SINGLE && q + NWARPS < q1) prefetch(q + NWARPS);
         unsigned long long acc[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) acc[k] = 0ull;
@@ -146,10 +172,8 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
             float2 xy;
             float aw;
             if (FUSED) {
-                const size_t row = (size_t)b * Lq + q;
-                const float* pr = loc + row * fz.ld;
-                const float2 off = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
-                const float lg = pt_ok ? pr[(size_t)M * LP * 2 + (size_t)m * LP + pt] : -INFINITY;
+                const float2 off = cur_a;                       // FUSED implies SINGLE: prefetched
+                const float lg = pt_ok ? cur_b : -INFINITY;
                 float mx = lg;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -158,7 +182,7 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
                 aw = ex * (1.f / den);
-                const float* rf = fz.ref + row * fz.RD;
+                const float rf[4] = {cur_ref.x, cur_ref.y, cur_ref.z, cur_ref.w};
                 const float vx = fz.valid_ratios[((size_t)b * lv.n + l) * 2], vy = fz.valid_ratios[((size_t)b * lv.n + l) * 2 + 1];
                 const float rx = rf[0] * vx, ry = rf[1] * vy;
                 if (fz.RD == 2) {
@@ -168,6 +192,9 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
                     xy.x = rx + off.x / (float)P * (rf[2] * vx) * 0.5f;
                     xy.y = ry + off.y / (float)P * (rf[3] * vy) * 0.5f;
                 }
+            } else if (SINGLE) {
+                xy = cur_a;
+                aw = cur_b;
             } else {
                 xy = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
                 aw = attn[pbase + pt];
