@@ -135,3 +135,29 @@ def test_bf16_throughput_mode_agreement():
     print("bf16: logits %.3e boxes %.3e memory %.3e per-query decision agreement %.4f CER-vs-fp32-decode %.4f" % (
         e_log, e_box, rel(st["memory"][:, ::8, ::4].float(), fx["memory_s"]), agree, cer))
     assert e_log < 5e-2 and e_box < 5e-2 and agree >= 0.90
+
+
+def test_hwdb_wide_head_engine_matches_module_path():
+    """BASELINE config 3 (config/HWDB_full.py, 7356 classes): no reference fixture exists for it (52 M parameters, no
+    checkpoint), so the fused engine is checked against the module path, which is itself pinned to the reference vectors
+    at C=166; the only new ingredient is the C-wide class head (N = 7356 GEMMs, 7357-row label table)."""
+    from dtlr_b200 import config
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, _, _ = dino.build_dino(config.hwdb_args(num_queries=300))
+    synth.load_synth_weights(model, 0)
+    model = model.cuda().eval()
+    x = synth.synth_images(2, 40, 1024, seed=7).cuda()
+    model.use_engine = False
+    st = {}
+    model.transformer.debug_stages = st
+    with torch.no_grad():
+        ref = model(x)
+    model.transformer.debug_stages = None
+    out, _ = run_engine(model, x, force=st["topk_idx"])
+    assert out["pred_logits"].shape == (2, 300, 7356)
+    assert rel(out["pred_logits"], ref["pred_logits"]) < TOL and rel(out["pred_boxes"], ref["pred_boxes"]) < TOL
+    frames = dino.decode_frames(out)
+    assert (frames.long().cpu() == dino.ctc_view(ref["pred_logits"], ref["pred_boxes"]).argmax(-1).cpu()).float().mean() > 0.99
+    out16, _ = run_engine(model, x, force=st["topk_idx"], dtype=torch.bfloat16)
+    assert rel(out16["pred_logits"], ref["pred_logits"]) < 5e-2
