@@ -56,6 +56,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -123,6 +128,15 @@ template <> __device__ __forceinline__ uint4 pack_chunk<__nv_bfloat16>(const flo
 }
 
 // ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+// Implicit-GEMM geometry of a stride-1 k x k convolution on NHWC activations: the A operand of k-block kb is the
+// (kh,kw) tap / 64-channel slice of the input, fetched by TMA straight from the [B,H,W,C] tensor (4-D map, zero fill
+// outside the image = the conv padding); a 128-pixel M tile is nseg runs of seg_w consecutive output pixels of one row.
+struct ConvGeo {
+    int enabled;
+    int Ho, Wo, KW, pad, cblocks;     // cblocks = C / 64
+    int seg_w, nseg;                  // seg_w * nseg == 128, Wo % seg_w == 0
+};
+
 struct GemmEpi {
     const float* bias;       // [N] fp32 or null
     const void* residual;    // [M, ldr] same dtype as C, or null
@@ -130,6 +144,7 @@ struct GemmEpi {
     int ldr, ldc;
     int M, N, K;
     int relu;                // 0 none, 1 ReLU before the residual add, 2 ReLU after it (ResNet bottleneck)
+    ConvGeo conv;            // conv.enabled: implicit-GEMM convolution (A fetched through the 4-D map)
     int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
 };
 
@@ -205,9 +220,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);                   // slot free (first lap passes immediately)
-                    mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
                     unsigned char* sa = smem + s * S::STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+                    if (e.conv.enabled) {
+                        const ConvGeo& cg = e.conv;
+                        const int kpos = kb / cg.cblocks, c0 = (kb - kpos * cg.cblocks) * GEMM_BK;
+                        const int kh = kpos / cg.KW, kw = kpos - kh * cg.KW;
+                        int nvalid = 0;
+                        for (int j = 0; j < cg.nseg; ++j) nvalid += (m0 + j * cg.seg_w < e.M) ? 1 : 0;
+                        mbar_expect_tx(&full_bar[s], (uint32_t)(nvalid * cg.seg_w * GEMM_BK * 2 + S::B_BYTES));
+                        for (int j = 0; j < nvalid; ++j) {
+                            const int p = m0 + j * cg.seg_w;
+                            const int hw = cg.Ho * cg.Wo;
+                            const int bimg = p / hw, rem = p - bimg * hw;
+                            const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
+                            tma_load_4d(sa + (size_t)j * cg.seg_w * (GEMM_BK * 2), &tmA, &full_bar[s], c0, wo + kw - cg.pad, ho + kh - cg.pad, bimg);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+                    }
                     tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0);
                 }
             }
@@ -477,6 +508,27 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols
     return DTLR_OK;
 }
 
+// 4-D bf16 tensor map over NHWC activations: dims (C, W, H, B), box (64 channels, seg_w pixels, 1, 1), 128B swizzle
+static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int W, int C, int seg_w) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return DTLR_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)GEMM_BK, (cuuint32_t)seg_w, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (NHWC 4-D) failed (%d) for B=%d H=%d W=%d C=%d", (int)r, B, H, W, C);
+        return DTLR_ERR_CUDA;
+    }
+    return DTLR_OK;
+}
+
 template <int BN, int STAGES, typename OutT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st) {
     using S = GemmSmem<BN, STAGES, OutT>;
@@ -508,7 +560,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
     DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
-    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, g_debug_flags};
+    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
     if (in_dtype == DTLR_F32) {
         DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
         dim3 grid((M + 63) / 64, (N + 63) / 64);
@@ -537,4 +589,35 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 64))) return rc;
     return out_dtype == DTLR_BF16 ? launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 6, float>(ta, tb, e, st);
+}
+
+// Convolution (stride 1, "same" padding) on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel above: no im2col
+// matrix ever exists; the k x k taps are TMA loads with shifted coordinates and hardware zero fill.
+extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int H,
+                                int W, int C, int Cout, int KH, int KW, int pad, int relu, int out_dtype, void* stream) {
+    DTLR_CHECK_ARG(x && w && out, "conv2d_nhwc: null pointer");
+    DTLR_CHECK_ARG(KH == 2 * pad + 1 && KW == 2 * pad + 1, "conv2d_nhwc: only stride-1 'same' convolutions (k = 2*pad+1)");
+    DTLR_CHECK_ARG(C % 64 == 0, "conv2d_nhwc: C must be a multiple of 64 (got %d)", C);
+    int seg_w = W >= 128 ? 128 : W;
+    DTLR_CHECK_ARG(seg_w >= 8 && (128 % seg_w) == 0 && (W % seg_w) == 0,
+                   "conv2d_nhwc: output width %d cannot be tiled into 128-pixel row segments (use im2col + gemm)", W);
+    DTLR_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv2d_nhwc: operands must be 16-byte aligned");
+    DTLR_CHECK_ARG(out_dtype == DTLR_BF16, "conv2d_nhwc: bf16 output only");
+    const int M = B * H * W, K = KH * KW * C;
+    if (M == 0) return DTLR_OK;
+    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w}, g_debug_flags};
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_nhwc(&ta, x, B, H, W, C, seg_w))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((Cout % 256) == 0) {
+        if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 256))) return rc;
+        return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, st);
+    }
+    if (Cout > 64) {
+        if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 128))) return rc;
+        return launch_tc<128, 4, __nv_bfloat16>(ta, tb, e, st);
+    }
+    if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 64))) return rc;
+    return launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st);
 }

@@ -130,8 +130,11 @@ class InferenceEngine:
             s = blk["stride"]
             a = ops.gemm(y, *blk["c1"], relu=1)
             planes = blk["c1"][0].shape[0]
-            col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
-            bmid = ops.gemm(col, *blk["c2"], relu=1)
+            if ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
+                bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1), Hc, Wc
+            else:
+                col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
+                bmid = ops.gemm(col, *blk["c2"], relu=1)
             if blk["ds"] is not None:
                 sub = y if s == 1 else ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0]
                 idt = ops.gemm(sub, *blk["ds"])

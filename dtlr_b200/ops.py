@@ -60,6 +60,20 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
     return out, Ho, Wo
 
 
+def conv2d_nhwc_supported(x, H, W, C, k, stride):
+    seg = 128 if W >= 128 else W
+    return (x.dtype == torch.bfloat16 and stride == 1 and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and W % seg == 0)
+
+
+def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None):
+    """stride-1 'same' conv as implicit GEMM: x bf16 [B*H*W, C] NHWC, w bf16 [Cout, k*k*C] -> bf16 [B*H*W, Cout]"""
+    Cout = w.shape[0]
+    out = torch.empty((B * H * W, Cout), dtype=torch.bfloat16, device=x.device)
+    _call("dtlr_conv2d_nhwc", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(relu),
+          L.dtype_code(out), _st(x))
+    return out
+
+
 def stem_conv(x, w_khkwcico, bias, B, H, W, out_dtype):
     Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     out = torch.empty((B * Ho * Wo, 64), dtype=out_dtype, device=x.device)

@@ -103,6 +103,13 @@ int dtlr_debug_flags(int flags);
  */
 int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho,
                 int Wo, int ldo, int in_dtype, int out_dtype, int nchw_input, void* stream);
+/* Stride-1 "same" k x k convolution on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel: the taps are TMA
+ * loads from x [B,H,W,C] with shifted coordinates and hardware zero fill (no im2col matrix).  w bf16 [Cout, KH*KW*C]
+ * (K ordered kh, kw, cin; FrozenBatchNorm folded), bias fp32 [Cout] or NULL, residual/out bf16 [B*H*W, Cout].
+ * Needs C % 64 == 0 and W a power of two <= 128 or a multiple of 128; other shapes use dtlr_im2col + dtlr_gemm.
+ * (the 3x3 conv2 of every torchvision Bottleneck, models/dino/backbone.py:109-128) */
+int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int H, int W,
+                     int C, int Cout, int KH, int KW, int pad, int relu, int out_dtype, void* stream);
 /* ResNet stem: conv1 7x7/s2/p3 (3->64) + folded FrozenBatchNorm + ReLU, direct (no im2col): x fp32 NCHW [B,3,H,W],
  * w fp32 [7][7][3][64] (BN scale folded), bias fp32 [64] -> out NHWC [B*Ho*Wo, 64] of out_dtype.
  * (torchvision resnet50.conv1/bn1/relu as wrapped by models/dino/backbone.py:109-128, FrozenBatchNorm2d :62-72) */
