@@ -94,7 +94,9 @@ def cpu_baseline_run(batch, iters, warmup=1):
     sd = synth.synth_state_dict(shapes, seed=0)
     cfg = dino_ref.default_cfg(num_queries=900)
     x = synth.synth_images(batch, IMG_H, IMG_W, seed=0)
-    torch.set_num_threads(os.cpu_count() or 1)
+    # all the host threads the restatement can use: its small per-layer ops stop scaling past ~16-32 threads (measured on the
+    # 128-core B200 host: 8 threads 5.7 img/s, 16: 6.3, 32: 6.2, 64: 3.7, 128: 0.38), so the baseline runs at its best setting
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     for _ in range(warmup):
         dino_ref.dino_forward(sd, cfg, x)
     t0 = time.perf_counter()

@@ -8,6 +8,13 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False          # the torch reference convs must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
 @pytest.mark.parametrize("B,H,W,C,Cout", [(2, 10, 256, 64, 64), (3, 5, 128, 128, 128), (3, 3, 64, 256, 256), (5, 2, 32, 512, 512), (2, 1, 16, 64, 128)])
 def test_implicit_gemm_conv3x3(B, H, W, C, Cout):
     from dtlr_b200 import ops
