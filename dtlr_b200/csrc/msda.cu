@@ -78,8 +78,9 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __fl
 struct FusedArgs {
     const float* ref;            // [B*Lq, RD] reference points (RD = 2: encoder centres, 4: decoder boxes)
     const float* valid_ratios;   // [B, L, 2] (w, h)
-    int ld;                      // row pitch of the projection matrix
+    int ld;                      // row pitch of the projection matrix (elements)
     int RD;
+    int proj_bf16;               // projection rows are bf16 (throughput mode) instead of fp32
 };
 
 template <typename T, bool STAGE, bool SINGLE, bool FUSED, int NWARPS>
@@ -139,9 +140,16 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
         const int pt = min(pt16, LP - 1);
         if (FUSED) {
             const size_t row = (size_t)b * Lq + q;
-            const float* pr = loc + row * fz.ld;
-            pf_a = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
-            pf_b = pr[(size_t)M * LP * 2 + (size_t)m * LP + pt];
+            if (fz.proj_bf16) {
+                const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(loc) + row * fz.ld;
+                const uint32_t o2 = *reinterpret_cast<const uint32_t*>(pr + ((size_t)m * LP + pt) * 2);
+                pf_a = make_float2(__uint_as_float(o2 << 16), __uint_as_float(o2 & 0xffff0000u));
+                pf_b = __bfloat162float(pr[(size_t)M * LP * 2 + (size_t)m * LP + pt]);
+            } else {
+                const float* pr = loc + row * fz.ld;
+                pf_a = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
+                pf_b = pr[(size_t)M * LP * 2 + (size_t)m * LP + pt];
+            }
             if (fz.RD == 4) pf_ref = *reinterpret_cast<const float4*>(fz.ref + row * 4);
             else { const float2 r2 = *reinterpret_cast<const float2*>(fz.ref + row * 2); pf_ref = make_float4(r2.x, r2.y, 0.f, 0.f); }
         } else {
@@ -433,7 +441,7 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
                              int S, int M, int Lq, int P, bool stage, size_t slab, int occ, const FusedArgs* fzp,
                              cudaStream_t st) {
     const bool fused = fzp != nullptr;
-    const FusedArgs fz = fused ? *fzp : FusedArgs{nullptr, nullptr, 0, 0};
+    const FusedArgs fz = fused ? *fzp : FusedArgs{nullptr, nullptr, 0, 0, 0};
     const long long slots = (long long)sm_count() * occ;
     // split the query range so that the grid is several waves deep but every CTA keeps >= 64 queries
     int qsplit = (int)((4 * slots + (long long)B * M - 1) / ((long long)B * M));
@@ -517,9 +525,10 @@ extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const
     return DTLR_OK;
 }
 
-extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const float* proj,
-                                       int ld_proj, const float* ref, int ref_dim, const float* valid_ratios, void* out,
-                                       int B, int S, int M, int D, int L, int Lq, int P, int dtype, void* stream) {
+extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const void* proj,
+                                       int ld_proj, int proj_dtype, const float* ref, int ref_dim, const float* valid_ratios,
+                                       void* out, int B, int S, int M, int D, int L, int Lq, int P, int dtype, void* stream) {
+    DTLR_CHECK_ARG(proj_dtype == DTLR_F32 || proj_dtype == DTLR_BF16, "msda_forward_fused: projection must be f32 or bf16");
     DTLR_CHECK_ARG(B >= 0 && Lq >= 0 && S > 0 && M > 0 && P > 0, "msda_forward_fused: bad sizes");
     DTLR_CHECK_ARG(D == 32 && (dtype == DTLR_F32 || dtype == DTLR_BF16), "msda_forward_fused: needs D=32, f32 or bf16 values");
     DTLR_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "msda_forward_fused: reference points must have 2 or 4 coordinates");
@@ -532,10 +541,10 @@ extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes,
     DTLR_CHECK_ARG(value && proj && ref && valid_ratios && out, "msda_forward_fused: null pointer");
     DTLR_CHECK_ARG((((uintptr_t)value | (uintptr_t)proj) & 15) == 0, "msda_forward_fused: value/proj must be 16-byte aligned");
     DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward_fused: B or M exceeds 65535");
-    const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim};
+    const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim, proj_dtype == DTLR_BF16 ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
-    return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz)
-                             : launch_fwd_d32<__nv_bfloat16>(value, proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz);
+    return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz)
+                             : launch_fwd_d32<__nv_bfloat16>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz);
 }
 
 extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,

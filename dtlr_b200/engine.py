@@ -156,9 +156,11 @@ class InferenceEngine:
             val = ops.gemm(value_src_or_value, *a["val"])
             if pad_u8 is not None:
                 ops.zero_masked_rows_(val, pad_u8)
-        oa = ops.gemm(query, *a["oa"], out_dtype=torch.float32)
         val4 = val.view(B, S, M, val.shape[1] // M)
-        if nlev * Pn <= 16 and val4.shape[-1] == 32:
+        fusable = nlev * Pn <= 16 and val4.shape[-1] == 32
+        # offsets / logits stay in the compute dtype when the fused kernel consumes them (bf16 mode: half the traffic)
+        oa = ops.gemm(query, *a["oa"], out_dtype=T if fusable else torch.float32)
+        if fusable:
             core = msda_mod.msda_forward_fused(val4, shapes_host, lsi_host, nlev, oa, ref, vr, Lq, Pn)
         else:
             loc, attn = ops.msda_prep(oa, ref, vr, shapes_host, nlev, B, Lq, M, Pn)

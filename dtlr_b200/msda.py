@@ -64,12 +64,12 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     proj fp32 (B*Lq, ld) = offsets | logits; ref fp32 (B*Lq, 2|4); valid_ratios fp32 (B,L,2)."""
     L.require_cuda(value, proj, ref, valid_ratios)
     B, S, M, D = value.shape
-    assert proj.dtype == torch.float32 and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
+    assert proj.dtype in (torch.float32, torch.bfloat16) and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
     assert value.is_contiguous() and ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
     if out is None:
         out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
-        rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.ptr(ref),
+        rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.dtype_code(proj), L.ptr(ref),
                                              ref.shape[-1], L.ptr(valid_ratios), L.ptr(out), B, S, M, D, n_levels, Lq, P,
                                              L.dtype_code(value), L.stream_ptr(value.device))
     L.check(rc, "dtlr_msda_forward_fused")

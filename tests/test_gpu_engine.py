@@ -161,3 +161,20 @@ def test_hwdb_wide_head_engine_matches_module_path():
     assert (frames.long().cpu() == dino.ctc_view(ref["pred_logits"], ref["pred_boxes"]).argmax(-1).cpu()).float().mean() > 0.99
     out16, _ = run_engine(model, x, force=st["topk_idx"], dtype=torch.bfloat16)
     assert rel(out16["pred_logits"], ref["pred_logits"]) < 5e-2
+
+
+def test_host_pipeline_matches_direct_calls():
+    """dtlr_b200.pipeline.HostPipeline (overlapped H2D / forward+decode / D2H) returns, in order, exactly what direct calls do,
+    also with CUDA-graph replay (static output buffers) underneath."""
+    from dtlr_b200.pipeline import HostPipeline
+    model, _, _ = build_model(300)
+    model.eval()
+    model.compute_dtype = torch.bfloat16
+    batches = [synth.synth_images(2, 40, 704, seed=40 + i).pin_memory() for i in range(5)]
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        direct = [dino.decode_frames(model(b.cuda())).cpu() for b in batches]
+        for graph in (False, True):
+            model.use_cuda_graph = graph
+            got = [f.clone() for f in HostPipeline(model).run(iter(batches))]
+            assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, direct))

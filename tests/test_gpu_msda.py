@@ -204,6 +204,12 @@ def test_fused_prologue_matches_prep_plus_core(dtype, ref_dim):
     two = msda.msda_forward_raw(value, sh, ls, n, loc, attn).float()
     tol = 1e-4 if dtype == torch.float32 else 2e-2
     assert torch.allclose(fused, two, rtol=tol, atol=tol)
+    if dtype == torch.bfloat16:      # throughput mode feeds the projection rows in bf16 as well
+        pb = proj.bfloat16()
+        fused_b = msda.msda_forward_fused(value, sh, ls, n, pb, ref, vr, Lq, P).float()
+        loc_b, attn_b = ops.msda_prep(pb.float(), ref, vr, sh, n, B, Lq, M, P)
+        two_b = msda.msda_forward_raw(value, sh, ls, n, loc_b, attn_b).float()
+        assert torch.allclose(fused_b, two_b, rtol=tol, atol=tol)
     # plain torch statement of the prologue
     off = proj[:, :256].view(B, Lq, M, L, P, 2)
     aw = torch.softmax(proj[:, 256:].view(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
