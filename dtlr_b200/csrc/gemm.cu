@@ -137,6 +137,17 @@ struct ConvGeo {
     int seg_w, nseg;                  // seg_w * nseg == 128, Wo % seg_w == 0
 };
 
+// optional LayerNorm fused into the epilogue of a full-row (N == 256 == BN) bf16 GEMM:
+//   y = LN(gemm + bias + residual) * gamma + beta ;  y2 = y + add2 (optional second output)
+struct LnArgs {
+    const float* gamma;      // null = no LayerNorm
+    const float* beta;
+    const void* add2;        // [M, ld2] bf16 or null
+    void* out2;              // [M, ld2] bf16
+    int ld2;
+    float eps;
+};
+
 struct GemmEpi {
     const float* bias;       // [N] fp32 or null
     const void* residual;    // [M, ldr] same dtype as C, or null
@@ -144,6 +155,7 @@ struct GemmEpi {
     int ldr, ldc;
     int M, N, K;
     int relu;                // 0 none, 1 ReLU before the residual add, 2 ReLU after it (ResNet bottleneck)
+    LnArgs ln;
     ConvGeo conv;            // conv.enabled: implicit-GEMM convolution (A fetched through the 4-D map)
     int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
 };
@@ -163,7 +175,8 @@ struct GemmSmem {
     static constexpr int ROW_BYTES = BN * (int)sizeof(OutT);          // staging row pitch (16-byte chunks XOR-swizzled)
     static constexpr int STAGING_BYTES = GEMM_BM * ROW_BYTES;
     static constexpr int BIAS_BYTES = 4 * BN * 4;                     // one fp32 bias row per epilogue warp
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int LN_BYTES = (BN == 256 && sizeof(OutT) == 2) ? (2 * GEMM_BM * 4 * 4 + 2 * BN * 4) : 0;   // row stats x2 + gamma/beta
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + LN_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue
@@ -180,7 +193,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* staging = smem + STAGES * S::STAGE_BYTES;
     float* bias_s = reinterpret_cast<float*>(staging + S::STAGING_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);
+    float* ln_stat_s = reinterpret_cast<float*>(staging + S::STAGING_BYTES + S::BIAS_BYTES);     // [2][128][4]
+    float* ln_gb_s = ln_stat_s + 2 * GEMM_BM * 4;                                                // gamma[BN], beta[BN]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STAGING_BYTES + S::BIAS_BYTES + S::LN_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -285,6 +300,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         unsigned char* my_rows = staging + (size_t)(qd * 32) * S::ROW_BYTES;
         const bool vec_ok = ((e.ldc * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.C & 15) == 0) &&
                             (!e.residual || (((e.ldr * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.residual & 15) == 0)));
+        bool do_ln = false;
+        if constexpr (S::LN_BYTES > 0) {
+            do_ln = e.ln.gamma != nullptr;
+            if (do_ln) {
+                for (int j = threadIdx.x - 64; j < BN; j += 256) { ln_gb_s[j] = e.ln.gamma[j]; ln_gb_s[BN + j] = e.ln.beta[j]; }
+                asm volatile("bar.sync 5, 256;" ::: "memory");          // the 8 epilogue warps only
+            }
+        }
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
@@ -341,6 +364,84 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
             // ---- step 2: staging -> global, coalesced (each warp stores its own 32 rows), + residual, + late ReLU
             const int ncols = (e.dbg & 1) ? 0 : min(BN, e.N - n0);
+            if constexpr (S::LN_BYTES > 0) {
+                if (do_ln) {
+                    // ---- fused residual + LayerNorm over the full 256-wide row (this warp holds 128 columns of 32 rows;
+                    //      the partner warp (same lane quarter, other half) holds the rest; stats meet in shared memory)
+                    constexpr int CW = CHUNKS / 2, NIT = CW, GRP = 8;      // 16 chunks per row half, 2 rows per iteration
+                    float* stat = ln_stat_s + (tcount & 1) * (GEMM_BM * 4);
+                    const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+#pragma unroll 1
+                    for (int g0 = 0; g0 < NIT; g0 += GRP) {
+                        uint4 rres[GRP];
+#pragma unroll
+                        for (int it = 0; it < GRP; ++it) {
+                            const int idx = (g0 + it) * 32 + lane;
+                            const int r = idx / CW, ch = half * CW + idx % CW;
+                            const int grow = m0 + qd * 32 + r;
+                            rres[it] = make_uint4(0, 0, 0, 0);
+                            if (resp && grow < e.M) rres[it] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + ch * 8));
+                        }
+#pragma unroll
+                        for (int it = 0; it < GRP; ++it) {
+                            const int idx = (g0 + it) * 32 + lane;
+                            const int r = idx / CW, ch = half * CW + idx % CW;
+                            uint4* sp = reinterpret_cast<uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16));
+                            float f[8], gres[8];
+                            unpack_chunk<__nv_bfloat16>(*sp, f);
+                            unpack_chunk<__nv_bfloat16>(rres[it], gres);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] += gres[k];
+                            const uint4 rounded = pack_chunk<__nv_bfloat16>(f);       // LN input is the bf16-rounded sum, as un-fused
+                            *sp = rounded;
+                            unpack_chunk<__nv_bfloat16>(rounded, f);
+                            float sm = 0.f, sq = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { sm += f[k]; sq = fmaf(f[k], f[k], sq); }
+#pragma unroll
+                            for (int o = 8; o > 0; o >>= 1) {
+                                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                            }
+                            if ((lane & 15) == 0) {
+                                stat[(qd * 32 + r) * 4 + half * 2] = sm;
+                                stat[(qd * 32 + r) * 4 + half * 2 + 1] = sq;
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");     // partner warps (w, w+4) of this lane quarter
+                    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.C);
+                    const __nv_bfloat16* add2 = reinterpret_cast<const __nv_bfloat16*>(e.ln.add2);
+                    __nv_bfloat16* out2 = reinterpret_cast<__nv_bfloat16*>(e.ln.out2);
+#pragma unroll 2
+                    for (int it = 0; it < NIT; ++it) {
+                        const int idx = it * 32 + lane;
+                        const int r = idx / CW, ch = half * CW + idx % CW;
+                        const int grow = m0 + qd * 32 + r;
+                        if (grow >= e.M || ncols == 0) continue;
+                        const float* st4 = stat + (qd * 32 + r) * 4;
+                        const float mean = (st4[0] + st4[2]) * (1.f / 256.f);
+                        const float var = fmaxf((st4[1] + st4[3]) * (1.f / 256.f) - mean * mean, 0.f);
+                        const float rstd = rsqrtf(var + e.ln.eps);
+                        float f[8];
+                        unpack_chunk<__nv_bfloat16>(*reinterpret_cast<const uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16)), f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean) * rstd * ln_gb_s[ch * 8 + k] + ln_gb_s[BN + ch * 8 + k];
+                        const uint4 y = pack_chunk<__nv_bfloat16>(f);
+                        *reinterpret_cast<uint4*>(outp + (size_t)grow * e.ldc + ch * 8) = y;
+                        if (out2) {
+                            float a2[8];
+                            unpack_chunk<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(add2 + (size_t)grow * e.ln.ld2 + ch * 8)), a2);
+                            unpack_chunk<__nv_bfloat16>(y, f);             // second output adds to the ROUNDED y, as un-fused
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a2[k] += f[k];
+                            *reinterpret_cast<uint4*>(out2 + (size_t)grow * e.ln.ld2 + ch * 8) = pack_chunk<__nv_bfloat16>(a2);
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             if (vec_ok && (ncols % EPC) == 0) {
                 const int nchunks = ncols / EPC;
                 constexpr int CW = CHUNKS / 2;                           // chunks per row owned by this warp
@@ -560,7 +661,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
     DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
-    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
+    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
     if (in_dtype == DTLR_F32) {
         DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
         dim3 grid((M + 63) / 64, (N + 63) / 64);
@@ -591,6 +692,28 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     return out_dtype == DTLR_BF16 ? launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 6, float>(ta, tb, e, st);
 }
 
+// y = LayerNorm_256(A.W^T + bias (+ residual)) * gamma + beta, optional y2 = y + add2 -- the Linear -> (+residual) -> LayerNorm
+// tail of every attention / FFN block (reference deformable_transformer.py:813-814,806-807,906-907,956-957,878-879,326) in ONE
+// tcgen05 kernel: the 128 x 256 tile holds whole rows, so the normalisation happens in the epilogue.
+extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
+                            const float* gamma, const float* beta, float eps, void* Y, int ldy, const void* add2, void* Y2, int ld2,
+                            int M, int K, void* stream) {
+    const int N = 256;
+    DTLR_CHECK_ARG(M >= 0 && K > 0, "gemm_ln: bad sizes");
+    if (M == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(A && W && Y && gamma && beta, "gemm_ln: null pointer");
+    DTLR_CHECK_ARG(lda >= K && ldw >= K && ldy >= N && (!residual || ldr >= N) && (!Y2 || (add2 && ld2 >= N)), "gemm_ln: bad leading dimension");
+    DTLR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (ldy % 8) == 0 && (!residual || (ldr % 8) == 0) && (!Y2 || (ld2 % 8) == 0) &&
+                   ((((uintptr_t)A | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)residual | (uintptr_t)add2 | (uintptr_t)Y2)) & 15) == 0,
+                   "gemm_ln: operands need 16-byte aligned rows");
+    GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 256))) return rc;
+    return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, (cudaStream_t)stream);
+}
+
 // Convolution (stride 1, "same" padding) on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel above: no im2col
 // matrix ever exists; the k x k taps are TMA loads with shifted coordinates and hardware zero fill.
 extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int H,
@@ -605,7 +728,7 @@ extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias,
     DTLR_CHECK_ARG(out_dtype == DTLR_BF16, "conv2d_nhwc: bf16 output only");
     const int M = B * H * W, K = KH * KW * C;
     if (M == 0) return DTLR_OK;
-    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w}, g_debug_flags};
+    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w}, g_debug_flags};
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap_nhwc(&ta, x, B, H, W, C, seg_w))) return rc;

@@ -295,14 +295,12 @@ class InferenceEngine:
                 core = self._msda(lyr["attn"], q, ref_enc, 2, src, pad_rows, vr, shapes_host, lsi_host, nlev, B, S, S, T)
                 if st is not None and i == 0:
                     st["enc0_core"] = core.view(B, S, d)
-                x1 = ops.gemm(core, *lyr["attn"]["out"], residual=src)
-                s1 = ops.add_layernorm(x1, None, *lyr["ln1"])
+                s1 = ops.linear_ln(core, *lyr["attn"]["out"], src, *lyr["ln1"])
                 hdn = ops.gemm(s1, *lyr["l1"], relu=1)
-                x2 = ops.gemm(hdn, *lyr["l2"], residual=s1)
                 if i + 1 < len(P["enc"]):
-                    src, q = ops.add_layernorm(x2, None, *lyr["ln2"], add2=pos)
+                    src, q = ops.linear_ln(hdn, *lyr["l2"], s1, *lyr["ln2"], add2=pos)
                 else:
-                    src = ops.add_layernorm(x2, None, *lyr["ln2"])
+                    src = ops.linear_ln(hdn, *lyr["l2"], s1, *lyr["ln2"])
             memory = src
             if st is not None:
                 st["memory"] = memory.view(B, S, d)
@@ -310,7 +308,7 @@ class InferenceEngine:
             # ---- two-stage query selection (deformable_transformer.py:320-363)
             Q = tr.num_queries
             om, prop = ops.encoder_proposals(memory, pad_u8, valid_hw, shapes_host, nlev, B, S, d, tr.two_stage_default_hw)
-            omn = ops.add_layernorm(ops.gemm(om, *P["enc_output"]), None, *P["enc_output_norm"])
+            omn = ops.linear_ln(om, *P["enc_output"], None, *P["enc_output_norm"])
             cls_unsel = ops.gemm(omn, *P["enc_cls"], out_dtype=torch.float32)
             scores = ops.rowmax(cls_unsel, cls_unsel.shape[1]).view(B, S)
             coord_unsel = (self._mlp3(omn, P["enc_bbox"]) + prop).view(B, S, 4)
@@ -335,16 +333,13 @@ class InferenceEngine:
                 qk = ops.gemm(qk_in, *lyr["qk"])
                 v = ops.gemm(tgt, *lyr["v"])
                 att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
-                x1 = ops.gemm(att, *lyr["o"], residual=tgt)
-                tgt, qca = ops.add_layernorm(x1, None, *lyr["ln2"], add2=qp)
+                tgt, qca = ops.linear_ln(att, *lyr["o"], tgt, *lyr["ln2"], add2=qp)
                 core = self._msda(lyr["ca"], qca, ref, 4, memory, pad_rows, vr, shapes_host, lsi_host, nlev, B, Q, S, T)
                 if st is not None and i == 0:
                     st["dec0_core"] = core.view(B, Q, d)
-                x2 = ops.gemm(core, *lyr["ca"]["out"], residual=tgt)
-                tgt = ops.add_layernorm(x2, None, *lyr["ln1"])
+                tgt = ops.linear_ln(core, *lyr["ca"]["out"], tgt, *lyr["ln1"])
                 hdn = ops.gemm(tgt, *lyr["l1"], relu=1)
-                x3 = ops.gemm(hdn, *lyr["l2"], residual=tgt)
-                tgt = ops.add_layernorm(x3, None, *lyr["ln3"])
+                tgt = ops.linear_ln(hdn, *lyr["l2"], tgt, *lyr["ln3"])
                 ref = ops.box_refine(self._mlp3(tgt, P["bbox"][i]), ref)
                 refs.append(ref)
                 hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"]))

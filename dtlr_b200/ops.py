@@ -210,3 +210,24 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
     _call("dtlr_ctc_decode", _p(logits), C, _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum), B, Q, C,
           ctypes.c_float(eps), _st(logits))
     return (frames, newp) if want_new_pred else frames
+
+
+def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5):
+    """bf16 only, N = 256: y = LN(a @ w.T + bias (+ residual)); optional y2 = y + add2.  One tcgen05 kernel."""
+    import ctypes
+    M, K = a.shape
+    assert w.shape[0] == 256 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    y = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device)
+    y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if add2 is not None else None
+    _call("dtlr_gemm_ln", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
+          _p(gamma), _p(beta), ctypes.c_float(eps), _p(y), y.stride(0), _p(add2), _p(y2), add2.stride(0) if add2 is not None else 0,
+          M, K, _st(a))
+    return (y, y2) if add2 is not None else y
+
+
+def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
+    """Linear (+residual) + LayerNorm [+ second output]: fused tcgen05 kernel in bf16 mode, GEMM + LN kernels otherwise."""
+    if a.dtype == torch.bfloat16 and w.shape[0] == 256:
+        return gemm_ln(a, w, bias, residual, gamma, beta, add2)
+    x = gemm(a, w, bias, residual=residual)
+    return add_layernorm(x, None, gamma, beta, add2=add2)

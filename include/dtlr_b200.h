@@ -90,6 +90,12 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
  */
 int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
               void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);
+/* Linear -> (+residual) -> LayerNorm(256) [-> second output y + add2] in one tcgen05 kernel (bf16 operands, N = 256 = d_model):
+ * Y = LN(A.W^T + bias + residual) * gamma + beta;  Y2 = Y + add2 when Y2 != NULL.  Replaces the nn.Linear + dropout(0) + residual +
+ * nn.LayerNorm tail of every block: models/dino/deformable_transformer.py:813-814, 806-807, 906-907, 956-957, 878-879, 326. */
+int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
+                 const float* gamma, const float* beta, float eps, void* Y, int ldy, const void* add2, void* Y2, int ld2,
+                 int M, int K, void* stream);
 /* tuning aid only: sets kernel debug flags (0 = normal operation), returns the previous value */
 int dtlr_debug_flags(int flags);
 /* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */

@@ -65,3 +65,34 @@ def test_strided_operands_and_output():
     ref = a.float() @ w.float().T
     assert (outbuf[:, 128:256].float() - ref).abs().max() / ref.abs().max() < 2e-2
     assert outbuf[:, :128].abs().sum() == 0 and outbuf[:, 256:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("M,K", [(2700, 256), (912 * 3, 2048), (130, 256), (58368, 256)])
+@pytest.mark.parametrize("with_res,with_add2", [(True, True), (True, False), (False, False)])
+def test_gemm_with_fused_layernorm(M, K, with_res, with_add2):
+    """dtlr_gemm_ln: Linear -> (+residual) -> LayerNorm(256) [-> y + add2] in one tcgen05 kernel vs torch fp32 on the same
+    bf16 operands (the LN input is the bf16-rounded sum, exactly like the un-fused GEMM + LN kernels)."""
+    import torch.nn.functional as F
+    from dtlr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(256, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(256, device="cuda", generator=g)
+    res = torch.randn(M, 256, device="cuda", generator=g).bfloat16() if with_res else None
+    add2 = torch.randn(M, 256, device="cuda", generator=g).bfloat16() if with_add2 else None
+    gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(256, device="cuda", generator=g)
+    got = ops.gemm_ln(a, w, bias, res, gamma, beta, add2)
+    y = got[0] if with_add2 else got
+    x = (a.float() @ w.float().T + bias).bfloat16().float()
+    if with_res:
+        x = (x + res.float()).bfloat16().float()
+    ref = F.layer_norm(x, (256,), gamma, beta, 1e-5)
+    assert (y.float() - ref).abs().max().item() < 5e-2
+    assert (y.float() - ref).abs().mean().item() < 4e-3
+    if with_add2:
+        ref2 = ref.bfloat16().float() + add2.float()
+        assert (got[1].float() - ref2).abs().max().item() < 8e-2
+    # and the composed un-fused path gives the same thing
+    un = ops.add_layernorm(ops.gemm(a, w, bias, residual=res), None, gamma, beta)
+    assert (y.float() - un.float()).abs().max().item() < 5e-2
