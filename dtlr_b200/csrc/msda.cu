@@ -87,7 +87,7 @@ template <typename T, bool STAGE, bool SINGLE, bool FUSED, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 16 ? 2 : 1)   // <= 64 registers: 32 resident warps per SM
 msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                     T* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
-                    const int P, const int q_per_cta, const FusedArgs fz) {
+                    const int P, const int q_per_cta, const FusedArgs fz, const int vld /* value elements per pixel row */) {
     constexpr int ROWB = 32 * (int)sizeof(T);   // bytes of one pixel (32 channels)
     constexpr int LPP = ROWB / 16;              // lanes per pixel (8 fp32 / 4 bf16)
     constexpr int GL = 2 * LPP;                 // lanes per (point,row) group: two x-adjacent pixels
@@ -103,8 +103,8 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int LP = lv.n * P;
 
-    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * M + m) * ROWB;
-    const size_t gstride = (size_t)M * ROWB;    // bytes between consecutive pixels of one head in (B,S,M,D)
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * vld + (size_t)m * 32) * sizeof(T);
+    const size_t gstride = (size_t)vld * sizeof(T);    // bytes between consecutive pixels of one head (vld = M*32 when contiguous)
 
     if (STAGE) {
         // slab[p+1] = pixel p; slab[0] and slab[S+1] are zero padding (taps with zero weight may land there)
@@ -439,7 +439,7 @@ static int fill_levels(Levels& lv, const int64_t* shapes, const int64_t* lsi, in
 template <typename T, int NW>
 static int launch_fwd_d32_nw(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
                              int S, int M, int Lq, int P, bool stage, size_t slab, int occ, const FusedArgs* fzp,
-                             cudaStream_t st) {
+                             cudaStream_t st, int vld) {
     const bool fused = fzp != nullptr;
     const FusedArgs fz = fused ? *fzp : FusedArgs{nullptr, nullptr, 0, 0, 0};
     const long long slots = (long long)sm_count() * occ;
@@ -461,12 +461,12 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
                        : (single ? msda_fwd_d32_kernel<T, true, true, false, NW> : msda_fwd_d32_kernel<T, true, false, false, NW>);
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
         k<<<grid, block, slab, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
-                                     q_per_cta, fz);
+                                     q_per_cta, fz, vld);
     } else {
         auto k = fused ? msda_fwd_d32_kernel<T, false, true, true, NW>
                        : (single ? msda_fwd_d32_kernel<T, false, true, false, NW> : msda_fwd_d32_kernel<T, false, false, false, NW>);
         k<<<grid, block, 0, st>>>((const T*)value, (const float*)loc, (const float*)attn, (T*)out, lv, S, M, Lq, P,
-                                  q_per_cta, fz);
+                                  q_per_cta, fz, vld);
     }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -474,7 +474,8 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
 
 template <typename T>
 static int launch_fwd_d32(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
-                          int S, int M, int Lq, int P, cudaStream_t st, const FusedArgs* fzp = nullptr) {
+                          int S, int M, int Lq, int P, cudaStream_t st, const FusedArgs* fzp = nullptr, int vld = 0) {
+    if (vld == 0) vld = M * 32;
     const size_t slab = (size_t)(S + 2) * 32 * sizeof(T);
     const bool stage = slab <= (size_t)max_smem_optin();
     // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA)
@@ -482,8 +483,8 @@ static int launch_fwd_d32(const void* value, const void* loc, const void* attn, 
     if (occ_smem < 1) occ_smem = 1;
     // 64 registers/thread -> at most 32 warps per SM: one 32-warp CTA when only one slab fits, else 16-warp CTAs
     if (occ_smem == 1)
-        return launch_fwd_d32_nw<T, 32>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, 1, fzp, st);
-    return launch_fwd_d32_nw<T, 16>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, min(occ_smem, 2), fzp, st);
+        return launch_fwd_d32_nw<T, 32>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, 1, fzp, st, vld);
+    return launch_fwd_d32_nw<T, 16>(value, loc, attn, out, lv, B, S, M, Lq, P, stage, slab, min(occ_smem, 2), fzp, st, vld);
 }
 
 }  // namespace dtlr
@@ -525,7 +526,7 @@ extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const
     return DTLR_OK;
 }
 
-extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const void* proj,
+extern "C" int dtlr_msda_forward_fused(const void* value, int value_ld, const int64_t* shapes, const int64_t* lsi, const void* proj,
                                        int ld_proj, int proj_dtype, const float* ref, int ref_dim, const float* valid_ratios,
                                        void* out, int B, int S, int M, int D, int L, int Lq, int P, int dtype, void* stream) {
     DTLR_CHECK_ARG(proj_dtype == DTLR_F32 || proj_dtype == DTLR_BF16, "msda_forward_fused: projection must be f32 or bf16");
@@ -541,10 +542,11 @@ extern "C" int dtlr_msda_forward_fused(const void* value, const int64_t* shapes,
     DTLR_CHECK_ARG(value && proj && ref && valid_ratios && out, "msda_forward_fused: null pointer");
     DTLR_CHECK_ARG((((uintptr_t)value | (uintptr_t)proj) & 15) == 0, "msda_forward_fused: value/proj must be 16-byte aligned");
     DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward_fused: B or M exceeds 65535");
+    DTLR_CHECK_ARG(value_ld >= M * 32 && (value_ld % 8) == 0, "msda_forward_fused: value row pitch %d too small / unaligned", value_ld);
     const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim, proj_dtype == DTLR_BF16 ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
-    return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz)
-                             : launch_fwd_d32<__nv_bfloat16>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz);
+    return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz, value_ld)
+                             : launch_fwd_d32<__nv_bfloat16>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz, value_ld);
 }
 
 extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,

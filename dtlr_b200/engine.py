@@ -105,6 +105,8 @@ class InferenceEngine:
                         "o": _lin(sa.out_proj, dtype), "heads": sa.num_heads, "ln2": ln(l.norm2),
                         "l1": _lin(l.linear1, dtype), "l2": _lin(l.linear2, dtype), "ln3": ln(l.norm3)})
         P["dec"] = dec
+        P["dec_val_all"] = (torch.cat([l.cross_attn.value_proj.weight.detach() for l in tr.decoder.layers], 0).to(dtype).contiguous(),
+                            torch.cat([l.cross_attn.value_proj.bias.detach() for l in tr.decoder.layers], 0).float().contiguous())
         P["dec_norm"] = ln(tr.decoder.norm)
         P["rph"] = [_lin(l, dtype) for l in tr.decoder.ref_point_head.layers]
         P["bbox"] = [[_lin(l, dtype) for l in be.layers] for be in m.bbox_embed]
@@ -156,7 +158,7 @@ class InferenceEngine:
             val = ops.gemm(value_src_or_value, *a["val"])
             if pad_u8 is not None:
                 ops.zero_masked_rows_(val, pad_u8)
-        val4 = val.view(B, S, M, val.shape[1] // M)
+        val4 = val.unflatten(0, (B, S)).unflatten(2, (M, val.shape[1] // M))      # a view also for column blocks (pitch kept)
         fusable = nlev * Pn <= 16 and val4.shape[-1] == 32
         # offsets / logits stay in the compute dtype when the fused kernel consumes them (bf16 mode: half the traffic)
         oa = ops.gemm(query, *a["oa"], out_dtype=T if fusable else torch.float32)
@@ -164,7 +166,7 @@ class InferenceEngine:
             core = msda_mod.msda_forward_fused(val4, shapes_host, lsi_host, nlev, oa, ref, vr, Lq, Pn)
         else:
             loc, attn = ops.msda_prep(oa, ref, vr, shapes_host, nlev, B, Lq, M, Pn)
-            core = msda_mod.msda_forward_raw(val4, shapes_host, lsi_host, nlev, loc, attn)
+            core = msda_mod.msda_forward_raw(val4.contiguous(), shapes_host, lsi_host, nlev, loc, attn)
         return core.view(B * Lq, -1)
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -324,8 +326,18 @@ class InferenceEngine:
             # ---- decoder (deformable_transformer.py:652-766)
             ref = ops.sigmoid(refpoint.view(B * Q, 4))
             refs = [ref]
+            # cross-attention values of all decoder layers in one GEMM: memory is read once, N = n_layers * 256
+            val_all = ops.gemm(memory, *P["dec_val_all"])
+            if pad_rows is not None:
+                ops.zero_masked_rows_(val_all, pad_rows)
             tgt = P["tgt_embed"][None].expand(B, -1, -1).reshape(B * Q, d).contiguous()
             hs = []
+            # the shared prediction heads (dec_pred_{bbox,class}_embed_share, reference dino.py:170-191) of all decoder layers are
+            # evaluated as ONE batched MLP / GEMM over the stacked layer outputs
+            shared_heads = (m.engine_outputs == "all" and all(be is m.bbox_embed[0] for be in m.bbox_embed)
+                            and all(ce is m.class_embed[0] for ce in m.class_embed))
+            n_layers = len(P["dec"])
+            hs_all = torch.empty((n_layers * B * Q, d), dtype=T, device=dev) if shared_heads else None
             for i, lyr in enumerate(P["dec"]):
                 sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
                 qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1), *P["rph"][1])
@@ -334,7 +346,8 @@ class InferenceEngine:
                 v = ops.gemm(tgt, *lyr["v"])
                 att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
                 tgt, qca = ops.linear_ln(att, *lyr["o"], tgt, *lyr["ln2"], add2=qp)
-                core = self._msda(lyr["ca"], qca, ref, 4, memory, pad_rows, vr, shapes_host, lsi_host, nlev, B, Q, S, T)
+                core = self._msda(lyr["ca"], qca, ref, 4, val_all[:, i * d:(i + 1) * d], None, vr, shapes_host, lsi_host, nlev, B, Q, S, T,
+                                  precomputed_value=True)
                 if st is not None and i == 0:
                     st["dec0_core"] = core.view(B, Q, d)
                 tgt = ops.linear_ln(core, *lyr["ca"]["out"], tgt, *lyr["ln1"])
@@ -342,7 +355,10 @@ class InferenceEngine:
                 tgt = ops.linear_ln(hdn, *lyr["l2"], tgt, *lyr["ln3"])
                 ref = ops.box_refine(self._mlp3(tgt, P["bbox"][i]), ref)
                 refs.append(ref)
-                hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"]))
+                if hs_all is not None:       # decoder.norm output of layer i lands in row block i of one (n_dec*B*Q, d) matrix
+                    hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"], out=hs_all[i * B * Q:(i + 1) * B * Q]))
+                else:
+                    hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"]))
             if st is not None:
                 st["hs"] = [h_.view(B, Q, d) for h_ in hs]
                 st["refs"] = [r.view(B, Q, 4) for r in refs]
@@ -351,9 +367,16 @@ class InferenceEngine:
             n_dec = len(hs)
             want = range(n_dec) if m.engine_outputs == "all" else [n_dec - 1]
             coords, classes = {}, {}
-            for i in want:
-                coords[i] = ops.box_refine(self._mlp3(hs[i], P["bbox"][i]), refs[i]).view(B, Q, 4)
-                classes[i] = ops.gemm(hs[i], *P["cls"][i], out_dtype=torch.float32).view(B, Q, -1)
+            if hs_all is not None:
+                ref_all = torch.cat(refs[:n_dec], 0)
+                box_all = ops.box_refine(self._mlp3(hs_all, P["bbox"][0]), ref_all).view(n_dec, B, Q, 4)
+                cls_all = ops.gemm(hs_all, *P["cls"][0], out_dtype=torch.float32).view(n_dec, B, Q, -1)
+                for i in want:
+                    coords[i], classes[i] = box_all[i], cls_all[i]
+            else:
+                for i in want:
+                    coords[i] = ops.box_refine(self._mlp3(hs[i], P["bbox"][i]), refs[i]).view(B, Q, 4)
+                    classes[i] = ops.gemm(hs[i], *P["cls"][i], out_dtype=torch.float32).view(B, Q, -1)
             out = {"pred_logits": classes[n_dec - 1], "pred_boxes": coords[n_dec - 1]}
             if m.aux_loss:
                 out["aux_outputs"] = [{"pred_logits": classes[i], "pred_boxes": coords[i]} for i in want if i != n_dec - 1]

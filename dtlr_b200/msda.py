@@ -64,12 +64,14 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     proj fp32 (B*Lq, ld) = offsets | logits; ref fp32 (B*Lq, 2|4); valid_ratios fp32 (B,L,2)."""
     L.require_cuda(value, proj, ref, valid_ratios)
     B, S, M, D = value.shape
+    # value may be a column block of a wider matrix (several layers' value projections from one GEMM): pixel pitch = stride(1)
+    assert value.stride(3) == 1 and value.stride(2) == D and value.stride(0) == S * value.stride(1), "unsupported value layout"
     assert proj.dtype in (torch.float32, torch.bfloat16) and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
-    assert value.is_contiguous() and ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
+    assert ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
     if out is None:
         out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
-        rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.dtype_code(proj), L.ptr(ref),
+        rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), value.stride(1), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.dtype_code(proj), L.ptr(ref),
                                              ref.shape[-1], L.ptr(valid_ratios), L.ptr(out), B, S, M, D, n_levels, Lq, P,
                                              L.dtype_code(value), L.stream_ptr(value.device))
     L.check(rc, "dtlr_msda_forward_fused")

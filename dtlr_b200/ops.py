@@ -37,6 +37,10 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+import os as _os
+LN_FUSE_MIN_K = int(_os.environ.get("DTLR_LN_FUSE_MIN_K", "1024"))
+
+
 def _call(name, *args):
     L.check(getattr(L.lib(), name)(*args), name)
 
@@ -104,10 +108,11 @@ def pos_sine_into(mask_u8, level_embed, out, B, H, W, npf, temp_h, temp_w, row_o
           ctypes.c_float(temp_w), ctypes.c_longlong(rows_per_batch), L.dtype_code(out), _st(out))
 
 
-def add_layernorm(x, res, gamma, beta, add2=None, eps=1e-5):
+def add_layernorm(x, res, gamma, beta, add2=None, eps=1e-5, out=None):
     import ctypes
     rows, C = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_contiguous() and y.shape == x.shape
     y2 = torch.empty_like(x) if add2 is not None else None
     _call("dtlr_add_layernorm", _p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(add2), _p(y2), ctypes.c_longlong(rows), C,
           ctypes.c_float(eps), L.dtype_code(x), _st(x))
@@ -227,7 +232,9 @@ def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5):
 
 def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
     """Linear (+residual) + LayerNorm [+ second output]: fused tcgen05 kernel in bf16 mode, GEMM + LN kernels otherwise."""
-    if a.dtype == torch.bfloat16 and w.shape[0] == 256:
+    # fused only when the main loop is long enough to hide the two-pass LN epilogue (measured on B200: K = 256 layers are
+    # epilogue-bound and run faster as GEMM + add_layernorm256; K = 2048 (FFN linear2) gains)
+    if a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] >= LN_FUSE_MIN_K:
         return gemm_ln(a, w, bias, residual, gamma, beta, add2)
     x = gemm(a, w, bias, residual=residual)
     return add_layernorm(x, None, gamma, beta, add2=add2)

@@ -60,7 +60,7 @@ int dtlr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
  * the L*P logits and loc = ref*valid_ratio + offset/(W,H) (ref_dim 2) or + offset/P*wh*0.5 (ref_dim 4) happen in the
  * kernel, so sampling_locations / attention_weights never exist in HBM.  Needs D = 32 and L*P <= 16.
  * ref fp32 [B*Lq, ref_dim], valid_ratios fp32 [B, L, 2] = (w, h) (deformable_transformer.py:239-246, 491, 686-687). */
-int dtlr_msda_forward_fused(const void* value, const int64_t* shapes, const int64_t* lsi, const void* proj, int ld_proj,
+int dtlr_msda_forward_fused(const void* value, int value_ld /* elements per pixel row, >= M*32 */, const int64_t* shapes, const int64_t* lsi, const void* proj, int ld_proj,
                             int proj_dtype /* DTLR_F32 or DTLR_BF16 */, const float* ref, int ref_dim, const float* valid_ratios, void* out, int B, int S, int M,
                             int D, int L, int Lq, int P, int dtype, void* stream);
 

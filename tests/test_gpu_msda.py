@@ -210,6 +210,11 @@ def test_fused_prologue_matches_prep_plus_core(dtype, ref_dim):
         loc_b, attn_b = ops.msda_prep(pb.float(), ref, vr, sh, n, B, Lq, M, P)
         two_b = msda.msda_forward_raw(value, sh, ls, n, loc_b, attn_b).float()
         assert torch.allclose(fused_b, two_b, rtol=tol, atol=tol)
+    # value given as a column block of a wider matrix (row pitch 3*256), as the engine's batched value projection does
+    wide = torch.randn(B * S, 3 * M * 32, device="cuda").to(dtype)
+    wide[:, 256:512] = value.view(B * S, 256)
+    blk = wide[:, 256:512].unflatten(0, (B, S)).unflatten(2, (M, 32))
+    assert torch.equal(msda.msda_forward_fused(blk, sh, ls, n, proj, ref, vr, Lq, P).float(), fused)
     # plain torch statement of the prologue
     off = proj[:, :256].view(B, Lq, M, L, P, 2)
     aw = torch.softmax(proj[:, 256:].view(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
