@@ -178,3 +178,51 @@ def test_host_pipeline_matches_direct_calls():
             model.use_cuda_graph = graph
             got = [f.clone() for f in HostPipeline(model).run(iter(batches))]
             assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, direct))
+
+
+def test_real_resolution_line_vs_oracle():
+    """evaluation-time geometry (reference datasets/IAM.py:225-229 resizes lines to ~94x1333 -> S = 2676 tokens, odd feature
+    widths 167/84/42/21): exercises the large-map MSDA paths (fp32 slab does not fit shared memory -> L1/L2 gather), the
+    im2col fallback for non-power-of-two widths and ragged level sizes, against the CPU oracle on the same weights."""
+    from oracle import dino_ref
+    model, _, _ = build_model(900)
+    x = synth.synth_images(1, 94, 1333, seed=11)
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    st = {}
+    ref = dino_ref.dino_forward(sd, dino_ref.default_cfg(num_queries=900), x, stages=st)
+    assert st["src_flatten"].shape[1] == 2676
+    out, est = run_engine(model, x.cuda(), force=st["topk_idx"])
+    assert rel(est["memory"], st["memory"]) < TOL and rel(est["topk_scores"], st["topk_scores"]) < TOL
+    assert rel(out["pred_logits"], ref["pred_logits"]) < TOL and rel(out["pred_boxes"], ref["pred_boxes"]) < TOL
+    out16, _ = run_engine(model, x.cuda(), force=st["topk_idx"], dtype=torch.bfloat16)
+    assert rel(out16["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out16["pred_boxes"], ref["pred_boxes"]) < 5e-2
+
+
+def test_ddp_wrapped_finetune_step_single_rank_nccl():
+    """the model is a plain nn.Module: DistributedDataParallel over NCCL (reference finetuning.py:211-215) wraps it and a CTC
+    fine-tuning step (forward with targets -> loss_CTC -> backward -> clip -> AdamW) runs; world size 1 here (the 1-GPU test
+    box), the gradient all-reduce path is the same code."""
+    import os
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    model, crit, _ = build_model(300)
+    model.train()
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        ddp = DDP(model, device_ids=[0], find_unused_parameters=True)
+        opt = torch.optim.AdamW([p for p in ddp.parameters() if p.requires_grad], lr=1e-5)
+        tg = [{k: v.cuda() for k, v in t.items()} for t in synth.synth_targets(2, 166, seed=3)]
+        before = model.class_embed[0].weight.detach().clone()
+        out = ddp(synth.synth_images(2, 40, 1024, seed=3).cuda(), tg)
+        loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ddp.parameters(), 0.01)            # clip_max_norm of config/Latin_CTC.py:18
+        opt.step()
+        assert torch.isfinite(loss) and not torch.equal(before, model.class_embed[0].weight.detach())
+    finally:
+        if created:
+            dist.destroy_process_group()
