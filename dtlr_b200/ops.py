@@ -191,8 +191,20 @@ def cast(x, dtype):
     return out
 
 
+ATTN_IMPL = _os.environ.get("DTLR_ATTN", "tc")       # "tc": tcgen05 kernel where it applies; "hmma": mma.sync flash kernel
+
+
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
     out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
+    if ATTN_IMPL == "tc" and v.dtype == torch.bfloat16 and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:
+        vt = torch.empty((B * heads * 32, 1024), dtype=torch.bfloat16, device=v.device)
+        rc = L.lib().dtlr_mha_tcgen05(_p(qk), qk.stride(0), k_off, _p(v), v.stride(0), _p(vt), _p(out), out.stride(0), B, Q, heads,
+                                      head_dim, _st(v))
+        if rc == 0:
+            L.LAUNCHES += 2
+            return out
+        if rc != 3:
+            L.check(rc, "dtlr_mha_tcgen05")
     _call("dtlr_mha_self_attention", _p(qk), qk.stride(0), k_off, _p(v), v.stride(0), _p(attn_mask_u8), _p(out), out.stride(0),
           B, Q, heads, head_dim, L.dtype_code(v), _st(v))
     return out

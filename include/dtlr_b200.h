@@ -167,6 +167,11 @@ int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype
  * attn_mask uint8 [Q,Q], 1 = blocked, or NULL; out [B*Q, ld_o]. */
 int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const unsigned char* attn_mask,
                             void* out, int ld_o, int B, int Q, int heads, int head_dim, int dtype, void* stream);
+/* The same attention on the tcgen05 tensor cores (bf16, no mask, head_dim 32, Q <= 1024): K / V^T resident in shared memory via
+ * TMA, S = QK^T and O += PV as tcgen05.mma with TMEM accumulators, two-pass softmax between them.  vt_scratch: device buffer of
+ * B*heads*32*1024 bf16 (V^T, written by a pre-pass).  Returns DTLR_ERR_UNSUPPORTED for shapes it does not cover. */
+int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, void* vt_scratch, void* out, int ld_o, int B,
+                     int Q, int heads, int head_dim, void* stream);
 /* The "CTC view" decode tail, fused (models/dino/dino.py:472-502 transform + engine.py:512-530 argmax; evaluation.py:116-158
  * uses eps = 0.03/C): frames[b,pos] = argmax over [blank, classes] of the pos-th query in cx order (0 = blank, c+1 = class c).
  * logits fp32 [B*Q, ld], boxes fp32 [B*Q,4] (cx first).  perm (int32 [B,Q], may be NULL) receives the sort permutation,
