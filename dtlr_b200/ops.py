@@ -191,7 +191,9 @@ def cast(x, dtype):
     return out
 
 
-ATTN_IMPL = _os.environ.get("DTLR_ATTN", "tc")       # "tc": tcgen05 kernel where it applies; "hmma": mma.sync flash kernel
+# "hmma": mma.sync flash kernel (default: 287 us/layer at B=64); "tc": the tcgen05/TMEM kernel (correct, 519 us/layer in its
+# first version -- both are bound by the softmax ALU work, ~8.5 instructions per query-key pair, not by the tensor pipe)
+ATTN_IMPL = _os.environ.get("DTLR_ATTN", "hmma")
 
 
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):

@@ -21,6 +21,22 @@ def ref_attention(qk, v, B, Q, heads, mask=None):
     return (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(B * Q, d)
 
 
+@pytest.mark.parametrize("Q", [900, 986, 100, 17, 1024])
+def test_self_attention_tcgen05_kernel(Q, monkeypatch):
+    """the tcgen05 / TMEM / TMA attention kernel (opt-in, DTLR_ATTN=tc) against torch fp32 on the same bf16 operands"""
+    from dtlr_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_IMPL", "tc")
+    B, heads, d = 3, 8, 256
+    g = torch.Generator(device="cuda").manual_seed(Q + 1)
+    qk = (torch.randn(B * Q, 2 * d, device="cuda", generator=g) * 1.5).bfloat16()
+    v = torch.randn(B * Q, d, device="cuda", generator=g).bfloat16()
+    before = ops.L.LAUNCHES
+    out = ops.mha_self_attention(qk, d, v, None, B, Q, heads, d // heads)
+    assert ops.L.LAUNCHES - before == 2          # transpose pre-pass + tcgen05 kernel, not the fallback
+    ref = ref_attention(qk, v, B, Q, heads)
+    assert (out.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("Q", [900, 986, 100, 17])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_self_attention(Q, dtype):
