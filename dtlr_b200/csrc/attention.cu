@@ -213,7 +213,7 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                 mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
                 mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
                 mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-                const float c_lo = exp2f((m_lo[mt] - mx_lo) * scale_log2), c_hi = exp2f((m_hi[mt] - mx_hi) * scale_log2);
+                const float c_lo = ex2_approx((m_lo[mt] - mx_lo) * scale_log2), c_hi = ex2_approx((m_hi[mt] - mx_hi) * scale_log2);
                 m_lo[mt] = mx_lo; m_hi[mt] = mx_hi;
                 l_lo[mt] *= c_lo; l_hi[mt] *= c_hi;
 #pragma unroll
@@ -221,8 +221,8 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                 const float ml = mx_lo * scale_log2, mh = mx_hi * scale_log2;
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                    const float p0 = exp2f(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = exp2f(fmaf(sc[mt][n][1], scale_log2, -ml));
-                    const float p2 = exp2f(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = exp2f(fmaf(sc[mt][n][3], scale_log2, -mh));
+                    const float p0 = ex2_approx(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = ex2_approx(fmaf(sc[mt][n][1], scale_log2, -ml));
+                    const float p2 = ex2_approx(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = ex2_approx(fmaf(sc[mt][n][3], scale_log2, -mh));
                     l_lo[mt] += p0 + p1;
                     l_hi[mt] += p2 + p3;
                     pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);

@@ -208,7 +208,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     float p[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        p[j] = (key0 + j < Q) ? exp2f(fmaf(__uint_as_float(acc[j]), scale_log2, -mxs)) : 0.f;
+                        p[j] = (key0 + j < Q) ? ex2_approx(fmaf(__uint_as_float(acc[j]), scale_log2, -mxs)) : 0.f;
                         sum += p[j];
                     }
 #pragma unroll

@@ -61,4 +61,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+// 2^x on the SFU without exp2f's denormal-range pre/post scaling (2 FMUL + 1 FSETP per call): in the softmax the result
+// either is <= 1 with an argument <= 0 or is flushed to zero, so the plain approximation is exactly what is wanted.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 }  // namespace dtlr
