@@ -10,8 +10,8 @@
 //            scale) is written as bf16 straight into the 128B-swizzled K-major layout an A operand needs, and
 //            O += P_c V_c^T runs as tcgen05.mma 128x32x16 into a third TMEM region;
 //   epilogue O / rowsum -> bf16 -> global.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-9 softmax (two warps per TMEM lane quarter,
-// each owning 64 of the 128 key columns of a chunk).  All hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-17 softmax (four warps per TMEM lane quarter,
+// each owning 32 of the 128 key columns of a chunk).  All hand-offs are mbarriers; tcgen05.commit signals MMA completion.
 #include "tc_common.cuh"
 
 namespace dtlr {
@@ -24,7 +24,7 @@ constexpr int AT_SMEM_K = AT_KPAD * 64;            // 64 KB
 constexpr int AT_SMEM_V = 16 * 4096;               // 16 k-blocks of 32 rows x 128 B
 constexpr int AT_SMEM_Q = AT_QT * 64;              // 8 KB
 constexpr int AT_SMEM_P = 2 * 16384;               // one P chunk: 2 k-blocks of 128 rows x 128 B
-constexpr int AT_XCH_FLOATS = 2 * 2 * 128 * 2;     // {max, sum} x tile parity x 128 rows x 2 column halves
+constexpr int AT_XCH_FLOATS = 2 * 2 * 128 * 4;     // {max, sum} x tile parity x 128 rows x 4 column quarters
 constexpr int AT_SMEM_TOTAL = AT_SMEM_K + AT_SMEM_V + AT_SMEM_Q + 2 * AT_SMEM_P + AT_XCH_FLOATS * 4 + 1024 + 512;
 
 // V^T pre-pass: vt[(b*H + h)*32 + d][key] = v[b*Q + key][h*32 + d], zero for key >= Q
@@ -41,7 +41,7 @@ __global__ void vt_transpose_kernel(const __nv_bfloat16* __restrict__ v, int ld_
         vt[((size_t)(b * H + h) * 32 + d) * AT_KPAD + k0 + tx] = tile[tx][d];
 }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ld_o, int Q, int H, int k_off,
                    float scale_log2) {
@@ -75,10 +75,10 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(q_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-            mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 16);
+            mbar_init(&p_full[i], 16); mbar_init(&p_empty[i], 1);
         }
-        mbar_init(o_full, 1); mbar_init(o_empty, 8);
+        mbar_init(o_full, 1); mbar_init(o_empty, 16);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -162,7 +162,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else {
         // ===== softmax warps =====
         const int qd = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;                               // which 32 of the 128 key columns of a chunk (0..3)
         const int row = qd * 32 + lane;                                 // row of the 128-query tile == TMEM lane
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
         uint32_t si = 0, pi = 0;
@@ -174,23 +174,28 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const uint32_t sb = si & 1;
                 mbar_wait(&s_full[sb], (si >> 1) & 1);
                 tcgen05_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                const bool full_chunk = (c + 1) * AT_KC <= Q;       // only the boundary chunk pays for per-key masking
+                {
                     uint32_t acc[32];
-                    tmem_ld32(tmem_S + sb * AT_KC + lane_sel + half * 64 + cc * 32, acc);
-                    const int key0 = c * AT_KC + half * 64 + cc * 32;
+                    tmem_ld32(tmem_S + sb * AT_KC + lane_sel + part * 32, acc);
+                    if (full_chunk) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (key0 + j < Q) mx = fmaxf(mx, __uint_as_float(acc[j]));
+                        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])));
+                    } else {
+                        const int key0 = c * AT_KC + part * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (key0 + j < Q) mx = fmaxf(mx, __uint_as_float(acc[j]));
+                    }
                 }
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[sb]);
             }
-            float* xm = xch + (t & 1) * 256;
-            xm[row * 2 + half] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-            mx = fmaxf(xm[row * 2], xm[row * 2 + 1]);
+            float* xm = xch + (t & 1) * 512;
+            xm[row * 4 + part] = mx;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");            // the 4 warps of this lane quarter
+            mx = fmaxf(fmaxf(xm[row * 4], xm[row * 4 + 1]), fmaxf(xm[row * 4 + 2], xm[row * 4 + 3]));
             const float mxs = mx * scale_log2;
             // ---- pass 2: P = exp2(S*scale - max*scale) -> bf16 -> swizzled A-operand tile; row sums
             float sum = 0.f;
@@ -199,17 +204,24 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(&s_full[sb], (si >> 1) & 1);
                 mbar_wait(&p_empty[pb], ((pi >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
-                unsigned char* prow = sP + pb * AT_SMEM_P + half * 16384 + row * 128;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
+                unsigned char* prow = sP + pb * AT_SMEM_P + (part >> 1) * 16384 + row * 128;
+                {
                     uint32_t acc[32];
-                    tmem_ld32(tmem_S + sb * AT_KC + lane_sel + half * 64 + cc * 32, acc);
-                    const int key0 = c * AT_KC + half * 64 + cc * 32;
+                    tmem_ld32(tmem_S + sb * AT_KC + lane_sel + part * 32, acc);
+                    const int key0 = c * AT_KC + part * 32;
                     float p[32];
+                    if ((c + 1) * AT_KC <= Q) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        p[j] = (key0 + j < Q) ? ex2_approx(fmaf(__uint_as_float(acc[j]), scale_log2, -mxs)) : 0.f;
-                        sum += p[j];
+                        for (int j = 0; j < 32; ++j) {
+                            p[j] = ex2_approx(fmaf(__uint_as_float(acc[j]), scale_log2, -mxs));
+                            sum += p[j];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            p[j] = (key0 + j < Q) ? ex2_approx(fmaf(__uint_as_float(acc[j]), scale_log2, -mxs)) : 0.f;
+                            sum += p[j];
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
@@ -218,7 +230,7 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         __nv_bfloat162 a2 = __floats2bfloat162_rn(p[j + 4], p[j + 5]), a3 = __floats2bfloat162_rn(p[j + 6], p[j + 7]);
                         o.x = *reinterpret_cast<uint32_t*>(&a0); o.y = *reinterpret_cast<uint32_t*>(&a1);
                         o.z = *reinterpret_cast<uint32_t*>(&a2); o.w = *reinterpret_cast<uint32_t*>(&a3);
-                        const int chunk = cc * 4 + j / 8;                      // 16-byte chunk inside the 128-byte row
+                        const int chunk = (part & 1) * 4 + j / 8;                // 16-byte chunk inside the 128-byte row
                         *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) * 16)) = o;
                     }
                 }
@@ -227,32 +239,27 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&s_empty[sb]); mbar_arrive(&p_full[pb]); }
             }
-            float* xs = xch + 512 + (t & 1) * 256;
-            xs[row * 2 + half] = sum;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-            const float inv = 1.f / (xs[row * 2] + xs[row * 2 + 1]);
-            // ---- epilogue: O (128 x 32 fp32 in TMEM) / row sum -> bf16; this warp writes 16 of the 32 head channels
+            float* xs = xch + 1024 + (t & 1) * 512;
+            xs[row * 4 + part] = sum;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory");
+            const float inv = 1.f / ((xs[row * 4] + xs[row * 4 + 1]) + (xs[row * 4 + 2] + xs[row * 4 + 3]));
+            // ---- epilogue: O (128 x 32 fp32 in TMEM) / row sum -> bf16; this warp writes 8 of the 32 head channels
             mbar_wait(o_full, t & 1);
             tcgen05_fence_after();
-            uint32_t oacc[16];
-            tmem_ld16(tmem_O + lane_sel + half * 16, oacc);
+            uint32_t oacc[8];
+            tmem_ld8(tmem_O + lane_sel + part * 8, oacc);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
             if (q < Q) {
-                __nv_bfloat16* op = out + (size_t)(row_base + q) * ld_o + h * 32 + half * 16;
-                uint4 o0, o1;
-                __nv_bfloat162 t0;
-                uint32_t w[8];
+                __nv_bfloat16* op = out + (size_t)(row_base + q) * ld_o + h * 32 + part * 8;
+                uint32_t w[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    t0 = __floats2bfloat162_rn(__uint_as_float(oacc[2 * j]) * inv, __uint_as_float(oacc[2 * j + 1]) * inv);
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(oacc[2 * j]) * inv, __uint_as_float(oacc[2 * j + 1]) * inv);
                     w[j] = *reinterpret_cast<uint32_t*>(&t0);
                 }
-                o0 = make_uint4(w[0], w[1], w[2], w[3]);
-                o1 = make_uint4(w[4], w[5], w[6], w[7]);
-                *reinterpret_cast<uint4*>(op) = o0;
-                *reinterpret_cast<uint4*>(op + 8) = o1;
+                *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
     }
@@ -294,7 +301,7 @@ extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void
     const int n_qtiles = (Q + AT_QT - 1) / AT_QT;
     dim3 grid((n_qtiles + AT_TILES - 1) / AT_TILES, heads, B);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
-    mha_tcgen05_kernel<<<grid, 320, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2);
+    mha_tcgen05_kernel<<<grid, 576, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
