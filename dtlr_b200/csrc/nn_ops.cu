@@ -179,31 +179,38 @@ template <typename TO>
 __global__ void pos_sine_kernel(const unsigned char* __restrict__ mask, const float* __restrict__ level_embed,
                                 TO* __restrict__ out, int B, int H, int W, int npf, float temp_h, float temp_w,
                                 long long out_stride_b) {
+    // one 128-thread block per token.  Warp 0 counts the unmasked pixels of the token's column (cumsum over H), warp 1 those
+    // of its row (cumsum over W); then every thread produces one (sin, cos) pair per axis: dim_t[2k] == dim_t[2k+1].
     const int C = 2 * npf;
-    const long long total = (long long)B * H * W;
     const long long tok = blockIdx.x;
-    if (tok >= total) return;
     const int x = (int)(tok % W), y = (int)((tok / W) % H), b = (int)(tok / ((long long)W * H));
     const unsigned char* mb = mask + (size_t)b * H * W;
     __shared__ float emb[2];
-    if (threadIdx.x == 0) {
-        float cy = 0.f, ty = 0.f, cx = 0.f, tx = 0.f;
-        for (int i = 0; i < H; ++i) { const float nm = mb[i * W + x] ? 0.f : 1.f; ty += nm; if (i <= y) cy += nm; }
-        for (int j = 0; j < W; ++j) { const float nm = mb[y * W + j] ? 0.f : 1.f; tx += nm; if (j <= x) cx += nm; }
-        const float two_pi = 6.283185307179586f;
-        emb[0] = cy / (ty + 1e-6f) * two_pi;
-        emb[1] = cx / (tx + 1e-6f) * two_pi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        float cum = 0.f, tot = 0.f;
+        if (warp == 0) {
+            for (int i = lane; i < H; i += 32) { const float nm = mb[i * W + x] ? 0.f : 1.f; tot += nm; if (i <= y) cum += nm; }
+        } else {
+            for (int j = lane; j < W; j += 32) { const float nm = mb[y * W + j] ? 0.f : 1.f; tot += nm; if (j <= x) cum += nm; }
+        }
+        cum = warp_sum_f(cum);
+        tot = warp_sum_f(tot);
+        if (lane == 0) emb[warp] = cum / (tot + 1e-6f) * 6.283185307179586f;
     }
     __syncthreads();
     TO* o = out + ((size_t)b * out_stride_b + (size_t)y * W + x) * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const bool is_x = c >= npf;
-        const int i = is_x ? c - npf : c;
-        const float t = is_x ? temp_w : temp_h;
-        const float dim_t = powf(t, 2.f * (float)(i / 2) / (float)npf);
+    const int half_pairs = npf / 2;                              // (sin, cos) pairs per axis
+    for (int k = threadIdx.x; k < 2 * half_pairs; k += blockDim.x) {
+        const bool is_x = k >= half_pairs;
+        const int i = is_x ? k - half_pairs : k;
+        const float dim_t = powf(is_x ? temp_w : temp_h, 2.f * (float)i / (float)npf);
         const float a = (is_x ? emb[1] : emb[0]) / dim_t;
-        const float v = (i & 1) ? cosf(a) : sinf(a);
-        stf<TO>(o + c, v + (level_embed ? level_embed[c] : 0.f));
+        float sn, cs;
+        sincosf(a, &sn, &cs);
+        const int c = (is_x ? npf : 0) + 2 * i;
+        stf<TO>(o + c, sn + (level_embed ? level_embed[c] : 0.f));
+        stf<TO>(o + c + 1, cs + (level_embed ? level_embed[c + 1] : 0.f));
     }
 }
 
@@ -435,8 +442,9 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long
 // reference models/dino/backbone.py:109-128), straight from the fp32 NCHW network input to NHWC activations.  K = 147 is
 // too thin for the tensor-core path to pay for a 200 MB im2col round trip, so this one convolution runs on FFMA:
 // CTA = 2 x 64 output pixels x 64 channels, input patch (parity-split columns -> conflict-free stride-2 taps) and the
-// 147 x 64 weight matrix in shared memory, thread = one pixel x 32 output channels.
-constexpr int STEM_TH = 2, STEM_TW = 64, STEM_PR = STEM_TH * 2 + 5, STEM_PC = STEM_TW * 2 + 5;   // patch 9 x 133
+// 147 x 64 weight matrix in shared memory, thread = two pixels (rows r, r+2) x 32 output channels, so every weight
+// vector fetched from shared memory feeds two FMAs (the one-pixel version was shared-memory bound at 37 % FMA use).
+constexpr int STEM_TH = 4, STEM_TW = 64, STEM_PR = STEM_TH * 2 + 5, STEM_PC = STEM_TW * 2 + 5;   // patch 13 x 133
 constexpr int STEM_PCH = (STEM_PC + 1) / 2;                                                      // columns per parity plane (67)
 template <typename TO>
 __global__ void __launch_bounds__(256)
@@ -459,37 +467,43 @@ stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     }
     __syncthreads();
     const int pix = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int pr = pix / STEM_TW, pc = pix % STEM_TW;
-    float acc[32];
+    const int pr = pix / STEM_TW, pc = pix % STEM_TW;          // pr in {0,1}; this thread also owns row pr + 2
+    float acc0[32], acc1[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 32; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
     for (int kh = 0; kh < 7; ++kh) {
 #pragma unroll
         for (int kw = 0; kw < 7; ++kw) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float v = patch[((c * STEM_PR + pr * 2 + kh) * 2 + (kw & 1)) * PPL + pc + (kw >> 1)];
+                const int col = pc + (kw >> 1);
+                const float v0 = patch[((c * STEM_PR + pr * 2 + kh) * 2 + (kw & 1)) * PPL + col];
+                const float v1 = patch[((c * STEM_PR + (pr + 2) * 2 + kh) * 2 + (kw & 1)) * PPL + col];
                 const float4* wp = reinterpret_cast<const float4*>(ws + ((kh * 7 + kw) * 3 + c) * 64 + half * 32);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float4 w4 = wp[k];
-                    acc[4 * k] = fmaf(v, w4.x, acc[4 * k]);
-                    acc[4 * k + 1] = fmaf(v, w4.y, acc[4 * k + 1]);
-                    acc[4 * k + 2] = fmaf(v, w4.z, acc[4 * k + 2]);
-                    acc[4 * k + 3] = fmaf(v, w4.w, acc[4 * k + 3]);
+                    acc0[4 * k] = fmaf(v0, w4.x, acc0[4 * k]);         acc1[4 * k] = fmaf(v1, w4.x, acc1[4 * k]);
+                    acc0[4 * k + 1] = fmaf(v0, w4.y, acc0[4 * k + 1]); acc1[4 * k + 1] = fmaf(v1, w4.y, acc1[4 * k + 1]);
+                    acc0[4 * k + 2] = fmaf(v0, w4.z, acc0[4 * k + 2]); acc1[4 * k + 2] = fmaf(v1, w4.z, acc1[4 * k + 2]);
+                    acc0[4 * k + 3] = fmaf(v0, w4.w, acc0[4 * k + 3]); acc1[4 * k + 3] = fmaf(v1, w4.w, acc1[4 * k + 3]);
                 }
             }
         }
     }
-    const int oh = oh0 + pr, ow = ow0 + pc;
-    if (oh < Ho && ow < Wo) {
-        TO* o = out + (((size_t)b * Ho + oh) * Wo + ow) * 64 + half * 32;
+    const int ow = ow0 + pc;
 #pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-            float v8[8];
+    for (int rr = 0; rr < 2; ++rr) {
+        const int oh = oh0 + pr + rr * 2;
+        if (oh < Ho && ow < Wo) {
+            TO* o = out + (((size_t)b * Ho + oh) * Wo + ow) * 64 + half * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v8[j] = fmaxf(acc[k + j] + bias[half * 32 + k + j], 0.f);
-            st8<TO>(o + k, v8);
+            for (int k = 0; k < 32; k += 8) {
+                float v8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v8[j] = fmaxf((rr ? acc1[k + j] : acc0[k + j]) + bias[half * 32 + k + j], 0.f);
+                st8<TO>(o + k, v8);
+            }
         }
     }
 }
