@@ -160,118 +160,97 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
     };
     if (SINGLE && q0 + warp < q1) prefetch(q0 + warp);
 
-    // tap parameters of this lane's (point, x-side) role from the raw per-query inputs: for BOTH y-rows the offset of the
-    // row's left pixel (STAGE: in bytes) and the weight of this lane's side; out-of-range points/rows get weight 0 and a
-    // safe offset (branch-free).  With FUSED the softmax over the L*P logits is a 16-lane shuffle reduction.
-    struct Taps { int o_r0, o_r1; float w_r0, w_r1; };
-    auto make_taps = [&](const int pt, const bool pt_ok, const float2 ra, const float rb, const float4 rref) -> Taps {
-        const int l = pt / P;
-        const int H = lv.H[l], W = lv.W[l];
-        float2 xy;
-        float aw;
-        if (FUSED) {
-            const float lg = pt_ok ? rb : -INFINITY;
-            float mx = lg;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float ex = expf(lg - mx);
-            float den = ex;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-            aw = ex * (1.f / den);
-            const float vx = fz.valid_ratios[((size_t)b * lv.n + l) * 2], vy = fz.valid_ratios[((size_t)b * lv.n + l) * 2 + 1];
-            const float rx = rref.x * vx, ry = rref.y * vy;
-            if (fz.RD == 2) {
-                xy.x = rx + ra.x / (float)W;
-                xy.y = ry + ra.y / (float)H;
-            } else {
-                xy.x = rx + ra.x / (float)P * (rref.z * vx) * 0.5f;
-                xy.y = ry + ra.y / (float)P * (rref.w * vy) * 0.5f;
-            }
-        } else {
-            xy = ra;
-            aw = rb;
-        }
-        const float y = fmaf(xy.y, (float)H, -0.5f), x = fmaf(xy.x, (float)W, -0.5f);
-        const bool inside = pt_ok && y > -1.f && x > -1.f && y < (float)H && x < (float)W;
-        const float yf = floorf(y), xf = floorf(x);
-        const int y0 = (int)yf, x0 = (int)xf;
-        const float fy = y - yf, fx = x - xf;
-        const bool col_ok = pside ? (x0 + 1 <= W - 1) : (x0 >= 0);       // this lane's corner column inside the map?
-        const float wx = (inside && col_ok) ? (pside ? fx : 1.f - fx) * aw : 0.f;
-        const bool r0_ok = inside && y0 >= 0, r1_ok = inside && y0 + 1 <= H - 1;
-        Taps tp;
-        tp.w_r0 = r0_ok ? wx * (1.f - fy) : 0.f;
-        tp.w_r1 = r1_ok ? wx * fy : 0.f;
-        const int pix0 = lv.start[l] + y0 * W + x0;
-        if (STAGE) {
-            tp.o_r0 = r0_ok ? pix0 * ROWB : 0;
-            tp.o_r1 = r1_ok ? (pix0 + W) * ROWB : 0;
-        } else {
-            tp.o_r0 = r0_ok ? pix0 : 0;
-            tp.o_r1 = r1_ok ? pix0 + W : 0;
-        }
-        return tp;
-    };
-    // gather: iteration (r,i), group g consumes point i*G+g, y-row r
-    auto gather = [&](const Taps& tp, unsigned long long (&acc)[NP]) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-#pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const int src = src0 + i * G;
-                const int so = __shfl_sync(0xffffffffu, r ? tp.o_r1 : tp.o_r0, src);
-                const float sw = __shfl_sync(0xffffffffu, r ? tp.w_r1 : tp.w_r0, src);
-                const unsigned long long w2 = pack2(sw, sw);
-                unsigned long long v[NP];
-                if (STAGE) {
-                    Vec16<T>::load(smem + (uint32_t)so + lane_off, v);
-                } else {
-                    const int p = so + side;
-                    if (p >= 0 && p < S && sw != 0.f) {
-                        Vec16<T>::load(gbase + (size_t)p * gstride + lane_off, v);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) v[k] = 0ull;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NP; ++k) ffma2(acc[k], v[k], w2);
-            }
-        }
-    };
-
-    // SINGLE (L*P <= 16, DTLR: 4 levels x 4 points): software pipeline -- the taps of query q+NWARPS are computed (loads were
-    // issued one iteration earlier) in the same instruction stream as the gather of query q, so neither waits for the other.
-    Taps cur_taps{0, 0, 0.f, 0.f};
-    if (SINGLE && q0 + warp < q1) {
-        cur_taps = make_taps(min(pt16, LP - 1), pt16 < LP, pf_a, pf_b, pf_ref);
-        if (q0 + warp + NWARPS < q1) prefetch(q0 + warp + NWARPS);
-    }
-
     for (int q = q0 + warp; q < q1; q += NWARPS) {
+        const size_t pbase = ((size_t)((size_t)b * Lq + q) * M + m) * LP;
+        const float2 cur_a = pf_a;
+        const float cur_b = pf_b;
+        const float4 cur_ref = pf_ref;
+        if (SINGLE && q + NWARPS < q1) prefetch(q + NWARPS);
         unsigned long long acc[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) acc[k] = 0ull;
-        if (SINGLE) {
-            Taps nxt{0, 0, 0.f, 0.f};
-            if (q + NWARPS < q1) {
-                const float2 na = pf_a;
-                const float nb = pf_b;
-                const float4 nref = pf_ref;
-                if (q + 2 * NWARPS < q1) prefetch(q + 2 * NWARPS);
-                nxt = make_taps(min(pt16, LP - 1), pt16 < LP, na, nb, nref);
+
+        // SINGLE: L*P <= 16 (DTLR: 4 levels x 4 points) -> one chunk, level constants hoisted out of the query loop
+        for (int c0 = 0; c0 < (SINGLE ? 1 : LP); c0 += 16) {
+            // ---- tap parameters of point c0+pt16 (branch-free: out-of-range points get weight 0 and a safe offset)
+            const int pt = min(c0 + pt16, LP - 1);
+            const bool pt_ok = (c0 + pt16) < LP;
+            const int l = pt / P;
+            const int H = lv.H[l], W = lv.W[l];
+            float2 xy;
+            float aw;
+            if (FUSED) {
+                const float2 off = cur_a;                       // FUSED implies SINGLE: prefetched
+                const float lg = pt_ok ? cur_b : -INFINITY;
+                float mx = lg;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float ex = expf(lg - mx);
+                float den = ex;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+                aw = ex * (1.f / den);
+                const float rf[4] = {cur_ref.x, cur_ref.y, cur_ref.z, cur_ref.w};
+                const float vx = fz.valid_ratios[((size_t)b * lv.n + l) * 2], vy = fz.valid_ratios[((size_t)b * lv.n + l) * 2 + 1];
+                const float rx = rf[0] * vx, ry = rf[1] * vy;
+                if (fz.RD == 2) {
+                    xy.x = rx + off.x / (float)W;
+                    xy.y = ry + off.y / (float)H;
+                } else {
+                    xy.x = rx + off.x / (float)P * (rf[2] * vx) * 0.5f;
+                    xy.y = ry + off.y / (float)P * (rf[3] * vy) * 0.5f;
+                }
+            } else if (SINGLE) {
+                xy = cur_a;
+                aw = cur_b;
+            } else {
+                xy = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
+                aw = attn[pbase + pt];
             }
-            gather(cur_taps, acc);
-            cur_taps = nxt;
-        } else {
-            const size_t pbase = ((size_t)((size_t)b * Lq + q) * M + m) * LP;
-            for (int c0 = 0; c0 < LP; c0 += 16) {
-                const int pt = min(c0 + pt16, LP - 1);
-                const float2 ra = *reinterpret_cast<const float2*>(loc + (pbase + pt) * 2);
-                const float rb = attn[pbase + pt];
-                const Taps tp = make_taps(pt, (c0 + pt16) < LP, ra, rb, make_float4(0.f, 0.f, 0.f, 0.f));
-                gather(tp, acc);
+            const float y = fmaf(xy.y, (float)H, -0.5f), x = fmaf(xy.x, (float)W, -0.5f);
+            const bool inside = pt_ok && y > -1.f && x > -1.f && y < (float)H && x < (float)W;
+            const float yf = floorf(y), xf = floorf(x);
+            const int y0 = (int)yf, x0 = (int)xf;
+            const float fy = y - yf, fx = x - xf;
+            // weight of this lane's x-side, zero when that corner column is outside the map
+            const bool col_ok = pside ? (x0 + 1 <= W - 1) : (x0 >= 0);
+            const float wx = (inside && col_ok) ? (pside ? fx : 1.f - fx) * aw : 0.f;
+            const bool r0_ok = inside && y0 >= 0, r1_ok = inside && y0 + 1 <= H - 1;
+            const float w_r0 = r0_ok ? wx * (1.f - fy) : 0.f;
+            const float w_r1 = r1_ok ? wx * fy : 0.f;
+            const int pix0 = lv.start[l] + y0 * W + x0;
+            int o_r0, o_r1;   // pixel index (STAGE: scaled to bytes) of the left corner of each row, 0 if the row is unused
+            if (STAGE) {
+                o_r0 = r0_ok ? pix0 * ROWB : 0;
+                o_r1 = r1_ok ? (pix0 + W) * ROWB : 0;
+            } else {
+                o_r0 = r0_ok ? pix0 : 0;
+                o_r1 = r1_ok ? pix0 + W : 0;
+            }
+            // ---- gather: iteration (r,i), group g consumes point i*G+g, y-row r
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int i = 0; i < ITER; ++i) {
+                    const int src = src0 + i * G;
+                    const int so = __shfl_sync(0xffffffffu, r ? o_r1 : o_r0, src);
+                    const float sw = __shfl_sync(0xffffffffu, r ? w_r1 : w_r0, src);
+                    const unsigned long long w2 = pack2(sw, sw);
+                    unsigned long long v[NP];
+                    if (STAGE) {
+                        Vec16<T>::load(smem + (uint32_t)so + lane_off, v);
+                    } else {
+                        const int p = so + side;
+                        if (p >= 0 && p < S && sw != 0.f) {
+                            Vec16<T>::load(gbase + (size_t)p * gstride + lane_off, v);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < NP; ++k) v[k] = 0ull;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) ffma2(acc[k], v[k], w2);
+                }
             }
         }
 
