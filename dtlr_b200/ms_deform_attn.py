@@ -58,7 +58,9 @@ class MSDeformAttn(nn.Module):
         else:
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
         odt = value.dtype
-        if odt in (torch.float16,):
+        if odt in (torch.float16, torch.bfloat16):
+            # autocast (engine.py:197 `autocast(enabled=args.amp)`): the core runs in fp32 like the reference's fp16 branch
+            # (ops/modules/ms_deform_attn.py:114-120); the backward kernel is fp32/fp64 only
             value = value.float()
         cdt = torch.float64 if value.dtype == torch.float64 else torch.float32
         out = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
