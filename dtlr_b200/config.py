@@ -24,7 +24,7 @@ _LATIN_CTC = dict(
     dn_box_noise_scale=0.4, dn_label_noise_ratio=0.5, embed_init_tgt=True, dn_labelbook_size=167,
     match_unstable_error=True, use_detached_boxes_dec_out=False, focal_alpha=0.25, cls_loss_coef=1.0,
     bbox_loss_coef=5.0, giou_loss_coef=2.0, interm_loss_coef=1.0, no_interm_box_loss=False, CTC_loss_coef=1,
-    set_cost_class=2.0, set_cost_bbox=5.0, set_cost_giou=2.0, frozen_weights=None, device="cuda",
+    set_cost_class=2.0, set_cost_bbox=5.0, set_cost_giou=2.0, matcher_type="HungarianMatcher", frozen_weights=None, device="cuda",
 )
 
 

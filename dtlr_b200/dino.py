@@ -273,7 +273,8 @@ def ctc_view(pred_logits, pred_boxes, eps=0.003):
 
 
 class SetCriterion(nn.Module):
-    """reference dino.py:428-983, CTC part.  The Hungarian detection loss (forward_standard) is SURVEY.md §8(f) 'next'."""
+    """reference dino.py:428-983: `loss_CTC` (fine-tuning / evaluation) and the Hungarian detection loss `forward`
+    (synthetic pre-training).  Mask losses are not implemented (masks=False in every DTLR config)."""
 
     def __init__(self, num_classes, matcher, weight_dict, focal_alpha, losses, CTC=False):
         super().__init__()
@@ -283,6 +284,9 @@ class SetCriterion(nn.Module):
         self.losses = losses
         self.focal_alpha = focal_alpha
         self.CTC = CTC
+        if self.CTC:
+            self.losses_all = list(losses)
+            self.losses_CTC = ["loss_CTC"]
 
     def loss_CTC(self, outputs, targets, indices, num_boxes, log=True, return_preds=False):
         """reference dino.py:457-551"""
@@ -308,9 +312,188 @@ class SetCriterion(nn.Module):
             return losses, new_pred_logits, None
         return losses
 
-    def forward(self, outputs, targets, return_indices=False):
-        raise NotImplementedError("the Hungarian detection loss (reference dino.py:780-964) is outside round-1 scope "
-                                  "(SURVEY.md §8f); DTLR fine-tuning and evaluation call loss_CTC directly")
+    # ---------------------------------------------------------------------------------------------------------------
+    # detection loss of the synthetic pre-training (main_synthetic.py): SURVEY.md §8(f).1, reference dino.py:553-964
+    @staticmethod
+    def _src_permutation_idx(indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        src_idx = torch.cat([src for (src, _) in indices])
+        return batch_idx, src_idx
+
+    def loss_labels(self, outputs, targets, indices, num_boxes, log=True):
+        """sigmoid focal classification loss, reference dino.py:553-600 + utils.py:82-107"""
+        src_logits = outputs["pred_logits"]
+        idx = self._src_permutation_idx(indices)
+        target_classes_o = torch.cat([t["labels"][J] for t, (_, J) in zip(targets, indices)]).to(src_logits.device)
+        target_classes = torch.full(src_logits.shape[:2], self.num_classes, dtype=torch.int64, device=src_logits.device)
+        target_classes[idx] = target_classes_o
+        onehot = torch.zeros([src_logits.shape[0], src_logits.shape[1], src_logits.shape[2] + 1], dtype=src_logits.dtype,
+                             device=src_logits.device)
+        onehot.scatter_(2, target_classes.unsqueeze(-1), 1)
+        onehot = onehot[:, :, :-1]
+        losses = {"loss_ce": sigmoid_focal_loss(src_logits, onehot, num_boxes, alpha=self.focal_alpha, gamma=2) * src_logits.shape[1]}
+        if log:
+            losses["class_error"] = 100 - _accuracy(src_logits[idx], target_classes_o)
+        return losses
+
+    @torch.no_grad()
+    def loss_cardinality(self, outputs, targets, indices, num_boxes):
+        """reference dino.py:602-617"""
+        pred_logits = outputs["pred_logits"]
+        tgt_lengths = torch.as_tensor([len(v["labels"]) for v in targets], device=pred_logits.device)
+        card_pred = (pred_logits.argmax(-1) != pred_logits.shape[-1] - 1).sum(1)
+        return {"cardinality_error": F.l1_loss(card_pred.float(), tgt_lengths.float())}
+
+    def loss_boxes(self, outputs, targets, indices, num_boxes):
+        """L1 + GIoU, reference dino.py:619-650"""
+        from .matcher import box_cxcywh_to_xyxy, generalized_box_iou
+        idx = self._src_permutation_idx(indices)
+        src_boxes = outputs["pred_boxes"][idx]
+        target_boxes = torch.cat([t["boxes"][i] for t, (_, i) in zip(targets, indices)], dim=0).to(src_boxes.device)
+        loss_bbox = F.l1_loss(src_boxes, target_boxes, reduction="none")
+        losses = {"loss_bbox": loss_bbox.sum() / num_boxes}
+        loss_giou = 1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src_boxes), box_cxcywh_to_xyxy(target_boxes)))
+        losses["loss_giou"] = loss_giou.sum() / num_boxes
+        with torch.no_grad():
+            losses["loss_xy"] = loss_bbox[..., :2].sum() / num_boxes
+            losses["loss_hw"] = loss_bbox[..., 2:].sum() / num_boxes
+        return losses
+
+    def get_loss(self, loss, outputs, targets, indices, num_boxes, **kwargs):
+        loss_map = {"labels": self.loss_labels, "cardinality": self.loss_cardinality, "boxes": self.loss_boxes,
+                    "loss_CTC": self.loss_CTC}
+        assert loss in loss_map, f"do you really want to compute {loss} loss?"
+        return loss_map[loss](outputs, targets, indices, num_boxes, **kwargs)
+
+    def forward(self, outputs, targets, return_indices=False, eval=False):
+        """reference dino.py:966-974: CTC fine-tuning uses the CTC loss alone; `eval=True` (or a non-CTC criterion) takes
+        the detection loss."""
+        if self.CTC and not eval:
+            self.losses = self.losses_CTC
+            return self.forward_CTC(outputs, targets, return_indices)
+        if self.CTC:
+            self.losses = self.losses_all
+        return self.forward_standard(outputs, targets, return_indices)
+
+    def forward_CTC(self, outputs, targets, return_indices=False):
+        """reference dino.py:713-770: loss_CTC on the final output, every aux output (`_i`) and the interm output (`_interm`);
+        no matcher."""
+        num_boxes = max(float(sum(len(t["labels"]) for t in targets)), 1.0)
+        losses = {}
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, None, num_boxes))
+        for idx, aux in enumerate(outputs.get("aux_outputs", [])):
+            for loss in self.losses:
+                losses.update({k + f"_{idx}": v for k, v in self.get_loss(loss, aux, targets, None, num_boxes).items()})
+        if "interm_outputs" in outputs:
+            l_dict = self.get_loss(self.losses[-1], outputs["interm_outputs"], targets, None, num_boxes)
+            losses.update({k + "_interm": v for k, v in l_dict.items()})
+        return losses
+
+    def forward_standard(self, outputs, targets, return_indices=False):
+        """reference dino.py:780-964: Hungarian matching per decoder layer + interm output, focal / L1 / GIoU
+        losses, DN losses when dn_meta carries denoising outputs.  The matcher runs on the GPU (dtlr_lsap)."""
+        if self.matcher is None:
+            raise RuntimeError("SetCriterion was built without a matcher")
+        outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        device = next(iter(outputs.values())).device
+        # every matching of the step (final, aux 0..n-1, interm) in one pair of launches when the matcher can batch layers
+        aux_list = outputs.get("aux_outputs", [])
+        layers = [outputs_without_aux] + list(aux_list) + ([outputs["interm_outputs"]] if "interm_outputs" in outputs else [])
+        if hasattr(self.matcher, "match_layers"):
+            pre = self.matcher.match_layers([{"pred_logits": o["pred_logits"], "pred_boxes": o["pred_boxes"]} for o in layers],
+                                            targets)
+            match = lambda k, o: pre[k]
+        else:
+            match = lambda k, o: self.matcher(o, targets)
+        indices = match(0, outputs_without_aux)
+        indices_list, indices0 = [], indices
+        num_boxes = sum(len(t["labels"]) for t in targets)
+        num_boxes = torch.as_tensor([num_boxes], dtype=torch.float, device=device)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(num_boxes)
+            num_boxes = torch.clamp(num_boxes / torch.distributed.get_world_size(), min=1).item()
+        else:
+            num_boxes = torch.clamp(num_boxes, min=1).item()
+        losses = {}
+        dn_meta = outputs.get("dn_meta")
+        zero = lambda: torch.as_tensor(0.0, device=device)
+        dn_keys = ("loss_bbox_dn", "loss_giou_dn", "loss_ce_dn", "loss_xy_dn", "loss_hw_dn", "cardinality_error_dn")
+        has_dn = bool(self.training and dn_meta and "output_known_lbs_bboxes" in dn_meta)
+        if has_dn:
+            known = dn_meta["output_known_lbs_bboxes"]
+            scalar, pad_size = dn_meta["num_dn_group"], dn_meta["pad_size"]
+            assert pad_size % scalar == 0
+            single_pad = pad_size // scalar
+            dn_pos_idx = []
+            for t in targets:
+                n = len(t["labels"])
+                if n > 0:
+                    tt = torch.arange(n, device=device).long().unsqueeze(0).repeat(scalar, 1)
+                    tgt_idx = tt.flatten()
+                    output_idx = ((torch.arange(scalar, device=device) * single_pad).long().unsqueeze(1) + tt).flatten()
+                else:
+                    output_idx = tgt_idx = torch.tensor([], device=device).long()
+                dn_pos_idx.append((output_idx, tgt_idx))
+            l_dict = {}
+            for loss in self.losses:
+                kw = {"log": False} if "labels" in loss else {}
+                l_dict.update(self.get_loss(loss, known, targets, dn_pos_idx, num_boxes * scalar, **kw))
+            losses.update({k + "_dn": v for k, v in l_dict.items()})
+        else:
+            losses.update({k: zero() for k in dn_keys})
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, indices, num_boxes))
+        if "aux_outputs" in outputs:
+            for idx, aux in enumerate(outputs["aux_outputs"]):
+                indices = match(1 + idx, aux)
+                indices_list.append(indices)
+                for loss in self.losses:
+                    kw = {"log": False} if loss == "labels" else {}
+                    l_dict = self.get_loss(loss, aux, targets, indices, num_boxes, **kw)
+                    losses.update({k + f"_{idx}": v for k, v in l_dict.items()})
+                if has_dn:
+                    aux_known = known["aux_outputs"][idx]
+                    l_dict = {}
+                    for loss in self.losses:
+                        kw = {"log": False} if "labels" in loss else {}
+                        l_dict.update(self.get_loss(loss, aux_known, targets, dn_pos_idx, num_boxes * scalar, **kw))
+                    losses.update({k + f"_dn_{idx}": v for k, v in l_dict.items()})
+                else:
+                    losses.update({k + f"_{idx}": zero() for k in dn_keys})
+        if "interm_outputs" in outputs:
+            interm = outputs["interm_outputs"]
+            indices = match(1 + len(aux_list), interm)
+            indices_list.append(indices)
+            for loss in self.losses:
+                kw = {"log": False} if loss == "labels" else {}
+                l_dict = self.get_loss(loss, interm, targets, indices, num_boxes, **kw)
+                losses.update({k + "_interm": v for k, v in l_dict.items()})
+        if return_indices:
+            indices_list.append(indices0)
+            return losses, indices_list
+        return losses
+
+
+def sigmoid_focal_loss(inputs, targets, num_boxes, alpha: float = 0.25, gamma: float = 2):
+    """reference models/dino/utils.py:82-107"""
+    prob = inputs.sigmoid()
+    ce_loss = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    p_t = prob * targets + (1 - prob) * (1 - targets)
+    loss = ce_loss * ((1 - p_t) ** gamma)
+    if alpha >= 0:
+        alpha_t = alpha * targets + (1 - alpha) * (1 - targets)
+        loss = alpha_t * loss
+    return loss.mean(1).sum() / num_boxes
+
+
+def _accuracy(output, target):
+    """top-1 precision in percent, reference util/misc.py:522-537"""
+    if target.numel() == 0:
+        return torch.zeros([], device=output.device)
+    pred = output.topk(1, 1, True, True)[1].t()
+    correct = pred.eq(target.view(1, -1).expand_as(pred))
+    return correct[:1].reshape(-1).float().sum(0) * (100.0 / target.size(0))
 
 
 def decode_frames(outputs, eps=0.003):
@@ -413,7 +596,8 @@ def build_dino(args):
         coeff = {"loss_ce": 1.0, "loss_bbox": 0.0 if no_box else 1.0, "loss_giou": 0.0 if no_box else 1.0}
         ic = getattr(args, "interm_loss_coef", 1.0)
         weight_dict.update({k + "_interm": v * ic * coeff[k] for k, v in clean_wo_dn.items()})
-    criterion = SetCriterion(num_classes, matcher=None, weight_dict=weight_dict, focal_alpha=args.focal_alpha,
+    from .matcher import build_matcher
+    criterion = SetCriterion(num_classes, matcher=build_matcher(args), weight_dict=weight_dict, focal_alpha=args.focal_alpha,
                              losses=["labels", "boxes", "cardinality"])
     postprocessors = {"bbox": PostProcess(num_select=args.num_select, nms_iou_threshold=args.nms_iou_threshold)}
     return model, criterion, postprocessors

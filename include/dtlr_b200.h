@@ -180,6 +180,22 @@ int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void* v, int ld
 int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
                     int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, void* stream);
 
+/* Hungarian matcher of the detection loss (models/dino/matcher.py:57-96), two kernels for all P = layers x B problems of a
+ * training step at once (the reference runs a cdist/GIoU chain over the full (B*Q) x sum(T) matrix, copies it to the CPU and
+ * calls scipy.optimize.linear_sum_assignment per image, once per decoder layer).
+ *
+ * dtlr_match_cost: block-diagonal matching cost, target-major: cost[p][t][q] fp32 [P, Tmax, Q] =
+ *   w_bbox * L1(cxcywh) + w_class * focal_class_cost(alpha, gamma 2) + w_giou * (-GIoU); logits fp32 [P, Q, C], boxes fp32
+ *   [P, Q, 4]; targets concatenated over the B images of one layer: tgt_labels int64 [sum T], tgt_boxes fp32 [sum T, 4],
+ *   t_off / t_cnt device int32 [B]; problem p uses the targets of image p % B.  Rows t >= t_cnt are left untouched.
+ * dtlr_lsap: problem p assigns its t_cnt[p % B] targets (rows of its [Tmax, Q] cost block) to distinct queries with minimal
+ *   total cost; q_of_t int32 [P, Tmax] receives the query of each target (-1 pad).  One CTA per problem, shortest augmenting
+ *   paths in fp64 like scipy (Tmax <= Q). */
+int dtlr_match_cost(const float* logits, const float* boxes, const int64_t* tgt_labels, const float* tgt_boxes, const int* t_off,
+                    const int* t_cnt, int P, int B, int Q, int C, int Tmax, float w_class, float w_bbox, float w_giou,
+                    float alpha, float* cost, void* stream);
+int dtlr_lsap(const float* cost, int P, int B, int Q, const int* t_cnt, int Tmax, int* q_of_t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
