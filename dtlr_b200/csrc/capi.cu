@@ -3,6 +3,7 @@
 
 namespace dtlr {
 static thread_local char g_err[512] = "";
+int g_debug_flags = 0;
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -14,3 +15,4 @@ void set_error(const char* fmt, ...) {
 extern "C" int dtlr_version(void) { return (0 << 16) | (1 << 8) | 0; }
 extern "C" int dtlr_built_for_sm(void) { return 100; }
 extern "C" const char* dtlr_last_error(void) { return dtlr::g_err; }
+extern "C" int dtlr_debug_flags(int flags) { const int old = dtlr::g_debug_flags; dtlr::g_debug_flags = flags; return old; }

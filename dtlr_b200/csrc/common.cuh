@@ -11,6 +11,9 @@
 namespace dtlr {
 
 void set_error(const char* fmt, ...);
+// tuning / A-B switches set through dtlr_debug_flags() (capi.cu): 1,2,4,8 = GEMM probes (gemm.cu), 16 = MSDA on the SIMT
+// kernel instead of the tensor-core gather kernel (msda.cu)
+extern int g_debug_flags;
 
 inline int sm_count() {
     static int n = 0;

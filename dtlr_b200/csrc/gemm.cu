@@ -542,8 +542,6 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
 
 using namespace dtlr;
 
-static int g_debug_flags = 0;
-extern "C" int dtlr_debug_flags(int flags) { const int old = g_debug_flags; g_debug_flags = flags; return old; }
 
 extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                          int ldr, void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu,

@@ -318,6 +318,253 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core gather path
+// bf16 values, D = 32, 4 levels x 4 points (every DTLR config).  The SIMT kernel above is bound by the shared-memory /
+// shuffle crossbar (65 wavefronts per (query, head): 32 for the gather itself, 33 for handing tap parameters round and
+// reducing) and by instruction issue (331 instructions per (query, head), a third of them bf16 -> fp32 unpacking).  Here:
+//
+//  * phase 1, lane = query (32 queries of one warp at a time): the whole prologue -- softmax over the 16 logits, sampling
+//    locations, bilinear corner weights, validity -- is straight-line per-lane code with NO shuffles; each lane leaves a
+//    192-byte tap table in shared memory: 32 u16 slab offsets (point x y-row) and 32 packed bf16 weight pairs.
+//  * phase 2, warp = one query at a time: the 16 points are consumed two at a time by ONE ldmatrix.x4.trans + ONE
+//    mma.sync.m16n8k16 (bf16 x bf16 -> fp32): the four 8x8 matrices are the four 128-byte runs (2 x-adjacent pixels x 32
+//    channels) of {point a, point b} x {row y0, row y1}, each read conflict-free straight from the staged slab as the A
+//    operand (M = point slot x channel-in-chunk, K = y-row x x-corner x 16-byte chunk); the B operand holds the corner
+//    weights on the chunk diagonal (N = point slot x output chunk), so the tensor core does the unpack, the 64-tap
+//    weighted sum and most of the reduction.  Per (query, head): 8 LDSM + 8 HMMA + 3 table loads + 2 shuffles.
+constexpr int MMA_NW = 8;             // warps per CTA (two CTAs per SM: 2 x (slab + 8 tap tables))
+constexpr int MMA_TSTRIDE = 208;      // bytes per query in a tap table: 64 offsets + 128 weights + 16 pad (the pad makes the
+                                      // 16-byte stores of 8 consecutive lanes hit 8 different bank groups)
+constexpr int MMA_TAB_BYTES = 32 * MMA_TSTRIDE;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t prmt(const uint32_t a, const uint32_t b, const uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(const float lo, const float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// MODE 0: sampling locations / attention weights given (fp32 tensors of the operator boundary)
+// MODE 1: fused prologue, fp32 projection rows;  MODE 2: fused prologue, bf16 projection rows
+template <int MODE>
+__global__ void __launch_bounds__(MMA_NW * 32, 2)
+msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restrict__ loc_or_proj, const float* __restrict__ attn,
+                    __nv_bfloat16* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
+                    const int q_per_cta, const FusedArgs fz, const int vld) {
+    constexpr int P = 4, LP = 16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(Lq, q0 + q_per_cta);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- stage the head's value slab: slab pixel p+1 = pixel p, pixels 0 and S+1 are zero padding
+    {
+        const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * vld + (size_t)m * 32) * 2;
+        const size_t gstride = (size_t)vld * 2;
+        for (int i = tid; i < S * 4; i += MMA_NW * 32) {
+            const int row = i >> 2, ch = i & 3;
+            cp_async16(smem + (size_t)(row + 1) * 64 + ch * 16, gbase + (size_t)row * gstride + ch * 16);
+        }
+        cp_async_commit();
+        if (tid < 8) {
+            const int row = (tid < 4) ? 0 : (S + 1);
+            *reinterpret_cast<uint4*>(smem + (size_t)row * 64 + (tid & 3) * 16) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    unsigned char* tab = smem + (size_t)(S + 2) * 64 + (size_t)warp * MMA_TAB_BYTES;
+
+    // phase-2 lane roles
+    const int g = lane >> 2, j = lane & 3;
+    const int mi = lane >> 3;                                        // ldmatrix: row (lane & 7) of matrix mi = 2*yrow + slot
+    const uint32_t slab_lane = (uint32_t)__cvta_generic_to_shared(smem) + (lane & 7) * 16;
+    const uint32_t tab_o = mi * 16;                                   // this lane's 8 offsets (one per ldmatrix)
+    const uint32_t tab_w = 64 + ((g >> 2) * 2 + (j >> 1)) * 32;       // 8 weight pairs of (slot g>>2, x-corner j>>1)
+    // B fragment: element e of b0/b1 is B[k = 2j+e (+8)][n = g]; k -> (x-corner j>>1, chunk 2(j&1)+e), n -> (slot g>>2, chunk g&3)
+    const bool contrib = (j & 1) == ((g >> 1) & 1);
+    const uint32_t sel0 = contrib ? ((g & 1) ? 0x1044u : 0x4410u) : 0x4444u;   // y-row 0 weight (low half of the pair)
+    const uint32_t sel1 = contrib ? ((g & 1) ? 0x3244u : 0x4432u) : 0x4444u;   // y-row 1 weight (high half)
+
+    const int per_warp = (q1 - q0 + MMA_NW - 1) / MMA_NW;
+    const int wq0 = q0 + warp * per_warp;
+    const int wq1 = min(q1, wq0 + per_warp);
+    // every warp passes the block barrier exactly once (after its first prologue, which overlaps the slab copy); a warp whose
+    // query range is empty only waits for its copies
+    int qb = wq0;
+    bool first = true;
+    while (true) {
+        const bool have = qb < wq1;
+        // =============================== phase 1: lane = query qb + lane
+        if (have) {
+            const int q = min(qb + lane, wq1 - 1);
+            const size_t row = (size_t)b * Lq + q;
+            float ox[LP], oy[LP], aw[LP];
+            if (MODE == 0) {
+                const float4* pl = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(loc_or_proj) + (row * M + m) * (LP * 2));
+                const float4* pa = reinterpret_cast<const float4*>(attn + (row * M + m) * LP);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float4 t = __ldg(pl + k); ox[2 * k] = t.x; oy[2 * k] = t.y; ox[2 * k + 1] = t.z; oy[2 * k + 1] = t.w; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float4 t = __ldg(pa + k); aw[4 * k] = t.x; aw[4 * k + 1] = t.y; aw[4 * k + 2] = t.z; aw[4 * k + 3] = t.w; }
+            } else if (MODE == 1) {
+                const float* pr = reinterpret_cast<const float*>(loc_or_proj) + row * fz.ld;
+                const float4* pl = reinterpret_cast<const float4*>(pr + m * (LP * 2));
+                const float4* pa = reinterpret_cast<const float4*>(pr + M * (LP * 2) + m * LP);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float4 t = __ldg(pl + k); ox[2 * k] = t.x; oy[2 * k] = t.y; ox[2 * k + 1] = t.z; oy[2 * k + 1] = t.w; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float4 t = __ldg(pa + k); aw[4 * k] = t.x; aw[4 * k + 1] = t.y; aw[4 * k + 2] = t.z; aw[4 * k + 3] = t.w; }
+            } else {
+                const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(loc_or_proj) + row * fz.ld;
+                const uint4* pl = reinterpret_cast<const uint4*>(pr + m * (LP * 2));
+                const uint4* pa = reinterpret_cast<const uint4*>(pr + M * (LP * 2) + m * LP);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 t = __ldg(pl + k);
+                    const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ox[4 * k + i] = __uint_as_float(w4[i] << 16); oy[4 * k + i] = __uint_as_float(w4[i] & 0xffff0000u); }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint4 t = __ldg(pa + k);
+                    const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { aw[8 * k + 2 * i] = __uint_as_float(w4[i] << 16); aw[8 * k + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u); }
+                }
+            }
+            float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE != 0) {
+                // softmax over the head's 16 logits (reference ops/modules/ms_deform_attn.py:100)
+                float mx = aw[0];
+#pragma unroll
+                for (int p = 1; p < LP; ++p) mx = fmaxf(mx, aw[p]);
+                float den = 0.f;
+#pragma unroll
+                for (int p = 0; p < LP; ++p) { aw[p] = __expf(aw[p] - mx); den += aw[p]; }
+                const float inv = 1.f / den;
+#pragma unroll
+                for (int p = 0; p < LP; ++p) aw[p] *= inv;
+                if (fz.RD == 4) rf = __ldg(reinterpret_cast<const float4*>(fz.ref + row * 4));
+                else { const float2 r2 = __ldg(reinterpret_cast<const float2*>(fz.ref + row * 2)); rf = make_float4(r2.x, r2.y, 0.f, 0.f); }
+            }
+            // pixel-space coordinate of a point of level l: x = ox * ax[l] + cx[l]  (= loc_x * W - 0.5 with the location
+            // arithmetic of reference ops/modules/ms_deform_attn.py:102-108 folded into one FMA; bf16 mode, not bit-exact)
+            float ax[4], ay[4], cx[4], cy[4];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                const float Hf = (float)lv.H[l], Wf = (float)lv.W[l];
+                if (MODE == 0) {
+                    ax[l] = Wf; ay[l] = Hf; cx[l] = -0.5f; cy[l] = -0.5f;
+                } else {
+                    const float vx = fz.valid_ratios[((size_t)b * 4 + l) * 2], vy = fz.valid_ratios[((size_t)b * 4 + l) * 2 + 1];
+                    cx[l] = fmaf(rf.x * vx, Wf, -0.5f);
+                    cy[l] = fmaf(rf.y * vy, Hf, -0.5f);
+                    ax[l] = fz.RD == 2 ? 1.f : 0.125f * (rf.z * vx) * Wf;      // off / W * W  |  off / P * w * 0.5 * W
+                    ay[l] = fz.RD == 2 ? 1.f : 0.125f * (rf.w * vy) * Hf;
+                }
+            }
+            uint32_t opk[LP], wp0[LP], wp1[LP];     // per point: offsets (row0 | row1 << 16), weight pairs of x-corner 0 / 1
+#pragma unroll
+            for (int p = 0; p < LP; ++p) {
+                const int l = p / P;
+                const int H = lv.H[l], W = lv.W[l];
+                const float Hf = (float)H, Wf = (float)W;
+                const float y = fmaf(oy[p], ay[l], cy[l]), x = fmaf(ox[p], ax[l], cx[l]);
+                const bool inside = y > -1.f && x > -1.f && y < Hf && x < Wf;
+                const float yf = floorf(y), xf = floorf(x);
+                const int y0 = (int)yf, x0 = (int)xf;
+                const float fy = y - yf, fx = x - xf;
+                const float wx0 = (inside && x0 >= 0) ? (1.f - fx) * aw[p] : 0.f;          // left corner column inside the map
+                const float wx1 = (inside && x0 + 1 <= W - 1) ? fx * aw[p] : 0.f;         // right corner column inside the map
+                const bool r0_ok = inside && y0 >= 0, r1_ok = inside && y0 + 1 <= H - 1;
+                const float gy0 = r0_ok ? 1.f - fy : 0.f, gy1 = r1_ok ? fy : 0.f;
+                wp0[p] = pack_bf16x2_rn(wx0 * gy0, wx0 * gy1);
+                wp1[p] = pack_bf16x2_rn(wx1 * gy0, wx1 * gy1);
+                const int pix0 = lv.start[l] + y0 * W + x0;                  // left pixel of row y0 (>= -1 when the row is used)
+                const uint32_t o0 = r0_ok ? (uint32_t)(pix0 + 1) * 64u : 0u;
+                const uint32_t o1 = r1_ok ? (uint32_t)(pix0 + W + 1) * 64u : 0u;
+                opk[p] = o0 | (o1 << 16);
+            }
+            unsigned char* t = tab + lane * MMA_TSTRIDE;
+            // offsets of ldmatrix role mi = 2*yrow + slot: half-word `it` = point 2*it + slot, row yrow
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int s = r & 1;
+                const uint32_t sel = (r >> 1) ? 0x7632u : 0x5410u;
+                uint4 v;
+                v.x = prmt(opk[0 + s], opk[2 + s], sel);
+                v.y = prmt(opk[4 + s], opk[6 + s], sel);
+                v.z = prmt(opk[8 + s], opk[10 + s], sel);
+                v.w = prmt(opk[12 + s], opk[14 + s], sel);
+                *reinterpret_cast<uint4*>(t + r * 16) = v;
+            }
+            // weight pairs of role 2*slot + x-corner: word `it` = point 2*it + slot
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                *reinterpret_cast<uint4*>(t + 64 + (2 * s) * 32) = make_uint4(wp0[0 + s], wp0[2 + s], wp0[4 + s], wp0[6 + s]);
+                *reinterpret_cast<uint4*>(t + 64 + (2 * s) * 32 + 16) = make_uint4(wp0[8 + s], wp0[10 + s], wp0[12 + s], wp0[14 + s]);
+                *reinterpret_cast<uint4*>(t + 64 + (2 * s + 1) * 32) = make_uint4(wp1[0 + s], wp1[2 + s], wp1[4 + s], wp1[6 + s]);
+                *reinterpret_cast<uint4*>(t + 64 + (2 * s + 1) * 32 + 16) = make_uint4(wp1[8 + s], wp1[10 + s], wp1[12 + s], wp1[14 + s]);
+            }
+        }
+        if (first) {
+            cp_async_wait_all();
+            __syncthreads();
+            first = false;
+        } else {
+            __syncwarp();
+        }
+        if (!have) break;
+
+        // =============================== phase 2: one query at a time, 8 x (ldmatrix.x4.trans + mma)
+        const int nq = min(32, wq1 - qb);
+        for (int jq = 0; jq < nq; ++jq) {
+            const unsigned char* t = tab + jq * MMA_TSTRIDE;
+            const uint4 o4 = *reinterpret_cast<const uint4*>(t + tab_o);
+            const uint4 wa = *reinterpret_cast<const uint4*>(t + tab_w);
+            const uint4 wb = *reinterpret_cast<const uint4*>(t + tab_w + 16);
+            const uint32_t ov[4] = {o4.x, o4.y, o4.z, o4.w};
+            const uint32_t wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const uint32_t off = (it & 1) ? (ov[it >> 1] >> 16) : (ov[it >> 1] & 0xffffu);
+                uint32_t a[4];
+                ldsm_x4_trans(a, slab_lane + off);
+                const uint32_t b0 = prmt(wv[it], 0u, sel0), b1 = prmt(wv[it], 0u, sel1);
+                if (it & 1) mma_bf16_m16n8k16(c1, a, b0, b1);
+                else mma_bf16_m16n8k16(c0, a, b0, b1);
+            }
+            // D rows 0-7 = slot 0 (useful columns n < 4: lanes j < 2), rows 8-15 = slot 1 (columns n >= 4: lanes j >= 2)
+            float r0 = c0[0] + c1[0], r1 = c0[1] + c1[1];
+            const float r2 = c0[2] + c1[2], r3 = c0[3] + c1[3];
+            r0 += __shfl_down_sync(0xffffffffu, r2, 2);
+            r1 += __shfl_down_sync(0xffffffffu, r3, 2);
+            if (j < 2) {
+                __nv_bfloat16* o = out + ((size_t)((size_t)b * Lq + qb + jq) * M + m) * 32 + g;
+                o[(2 * j) * 8] = __float2bfloat16_rn(r0);
+                o[(2 * j + 1) * 8] = __float2bfloat16_rn(r1);
+            }
+        }
+        __syncwarp();                // the table is rewritten by the next batch
+        qb += 32;
+        if (qb >= wq1) break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ generic path
 template <typename T>
 __device__ __forceinline__ T ld_as(const T* p) { return *p; }
@@ -472,10 +719,45 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
     return DTLR_OK;
 }
 
+// tensor-core gather kernel: bf16 values, 4 levels x 4 points, slab + tap tables resident in shared memory
+static bool mma_path_ok(const Levels& lv, int S, int P, const void* loc, const void* attn, const FusedArgs* fzp, int vld) {
+    if (g_debug_flags & 16) return false;
+    if (lv.n != 4 || P != 4 || S > 1023 || (vld % 8) != 0) return false;
+    if ((size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES > (size_t)max_smem_optin()) return false;
+    if (fzp) {
+        if ((fzp->ld % (fzp->proj_bf16 ? 8 : 4)) != 0) return false;
+        if (((uintptr_t)fzp->ref & (fzp->RD == 4 ? 15 : 7)) != 0) return false;
+    } else if ((((uintptr_t)loc | (uintptr_t)attn) & 15) != 0) {
+        return false;
+    }
+    return true;
+}
+
+static int launch_fwd_mma(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B, int S,
+                          int M, int Lq, const FusedArgs* fzp, cudaStream_t st, int vld) {
+    const size_t smem = (size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES;
+    // one 32-query batch per warp where possible: ceil(Lq / 256) CTAs per (image, head); small problems are split further
+    // (down to 64 queries per CTA) until the grid covers the machine twice
+    int qsplit = (Lq + MMA_NW * 32 - 1) / (MMA_NW * 32);
+    while ((long long)B * M * qsplit < 2ll * sm_count() && Lq / (qsplit + 1) >= 64) ++qsplit;
+    const int q_per_cta = (Lq + qsplit - 1) / qsplit;
+    qsplit = (Lq + q_per_cta - 1) / q_per_cta;
+    const FusedArgs fz = fzp ? *fzp : FusedArgs{nullptr, nullptr, 0, 0, 0};
+    const int mode = !fzp ? 0 : (fzp->proj_bf16 ? 2 : 1);
+    auto k = mode == 0 ? msda_fwd_mma_kernel<0> : (mode == 1 ? msda_fwd_mma_kernel<1> : msda_fwd_mma_kernel<2>);
+    DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(qsplit, M, B), block(MMA_NW * 32);
+    k<<<grid, block, smem, st>>>((const __nv_bfloat16*)value, loc, (const float*)attn, (__nv_bfloat16*)out, lv, S, M, Lq, q_per_cta, fz, vld);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
 template <typename T>
 static int launch_fwd_d32(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B,
                           int S, int M, int Lq, int P, cudaStream_t st, const FusedArgs* fzp = nullptr, int vld = 0) {
     if (vld == 0) vld = M * 32;
+    if (sizeof(T) == 2 && mma_path_ok(lv, S, P, loc, attn, fzp, vld))
+        return launch_fwd_mma(value, loc, attn, out, lv, B, S, M, Lq, fzp, st, vld);
     const size_t slab = (size_t)(S + 2) * 32 * sizeof(T);
     const bool stage = slab <= (size_t)max_smem_optin();
     // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA)

@@ -225,3 +225,32 @@ def test_fused_prologue_matches_prep_plus_core(dtype, ref_dim):
     else:
         loc_t = r[:, :, None, :, None, :2] + off / P * r[:, :, None, :, None, 2:] * 0.5
     assert torch.allclose(loc, loc_t, rtol=1e-5, atol=1e-6) and torch.allclose(attn, aw, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_tensor_core_gather_kernel_matches_simt_kernel_full_size(ref_dim):
+    """bf16 throughput mode at BASELINE config-2 size: msda_fwd_mma_kernel (ldmatrix + mma.sync gather, the default) against
+    msda_fwd_d32_kernel (SIMT, selected with dtlr_debug_flags(16)) on the same inputs, ragged valid ratios included.
+    The two differ only by the bf16 rounding of the 64 corner weights (fp32 accumulation in both)."""
+    from dtlr_b200 import msda, _lib
+    B, Lq, M, L, P, S = 64, 900 if ref_dim == 4 else 912, 8, 4, 4, 912
+    g = torch.Generator(device="cuda").manual_seed(17 + ref_dim)
+    shp, lsi = _levels(A_SHAPES)
+    sh, ls, n = msda._host_levels(shp.cuda(), lsi.cuda())
+    value = torch.randn(B, S, M, 32, device="cuda", generator=g).bfloat16()
+    proj = torch.randn(B * Lq, 384, device="cuda", generator=g)
+    proj[:, :256] *= 3.0                                    # offsets large enough to leave the map at every level
+    proj = proj.bfloat16()
+    ref = torch.rand(B * Lq, ref_dim, device="cuda", generator=g)
+    if ref_dim == 4:
+        ref[:, 2:] *= 0.3
+    vr = 0.5 + 0.5 * torch.rand(B, L, 2, device="cuda", generator=g)
+    new = msda.msda_forward_fused(value, sh, ls, n, proj, ref, vr, Lq, P).float()
+    _lib.lib().dtlr_debug_flags(16)
+    try:
+        old = msda.msda_forward_fused(value, sh, ls, n, proj, ref, vr, Lq, P).float()
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
+    assert torch.isfinite(new).all()
+    assert torch.allclose(new, old, rtol=2e-2, atol=2e-2)
+    assert (new - old).abs().mean().item() < 2e-3
