@@ -419,6 +419,210 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------- weight-stationary tcgen05 GEMM
+// K <= 256 (every Linear of the transformer except linear2 / ref_point_head.0, and the 1x1 convolutions of layer1-2): the
+// tile kernel above re-fetches the weight tile with every output tile and can hold only ONE tile's operands in its ring, so
+// with K = 256 it runs at the L2 -> SM rate (a 128 x 128 tile moves 128 KB for 8.4 MFLOP).  Here a persistent CTA owns one
+// BN-wide slice of W for its whole life (loaded once, up to 128 KB resident in shared memory) and streams only A tiles
+// through the ring (16 KB stages, several tiles deep); with BN = 256 a 256-wide layer reads A exactly once.  CTA c works on
+// slice c % ns and row tiles c / ns, c / ns + cps, ... so that the ns CTAs sharing an A tile fetch it at the same time (one
+// HBM read, the rest L2 hits).  Epilogue: 8 warps, TMEM -> registers -> bias / ReLU -> 32 x 32 XOR-swizzled staging block per
+// warp -> coalesced 16-byte stores (+ coalesced residual reads).
+template <int BN, typename OutT>
+struct WsSmem {
+    static constexpr int KB_MAX = 4;
+    static constexpr int W_KB_BYTES = BN * GEMM_BK * 2;                       // one 64-wide k-block of the slice
+    static constexpr int W_BYTES = KB_MAX * W_KB_BYTES;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                     // 16 KB
+    static constexpr int STG_WARP = 32 * 32 * (int)sizeof(OutT);              // 32 rows x 32 columns per epilogue warp
+    static constexpr int STG_BYTES = 8 * STG_WARP;
+    static constexpr int BIAS_BYTES = BN * 4;
+    static constexpr int FIXED = W_BYTES + STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int STAGES_FIT = (232448 - FIXED) / A_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int TOTAL = FIXED + STAGES * A_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    static_assert(STAGES >= 3, "weight slice leaves too little room for the A ring");
+};
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(320, 1)
+gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi e,
+                       const int ns, const int cps) {
+    using S = WsSmem<BN, OutT>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* wreg = smem;                                          // [KB_MAX][BN rows x 128 B], 128B swizzle
+    unsigned char* aring = smem + S::W_BYTES;                            // [STAGES][128 rows x 128 B]
+    unsigned char* staging = aring + STAGES * S::A_BYTES;
+    float* bias_s = reinterpret_cast<float*>(staging + S::STG_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STG_BYTES + S::BIAS_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* w_bar = empty_bar + STAGES;              // [KB_MAX]
+    uint64_t* tmem_full_bar = w_bar + S::KB_MAX;       // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slice = blockIdx.x % ns, r0 = blockIdx.x / ns;
+    if (r0 >= cps) return;                                               // CTAs beyond ns * cps have no work (whole CTA leaves)
+    const int n0 = slice * BN;
+    const int num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
+    const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int k = 0; k < S::KB_MAX; ++k) mbar_init(&w_bar[k], 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_ptr);
+    for (int j = threadIdx.x; j < BN; j += 320) bias_s[j] = (e.bias && n0 + j < e.N) ? __ldg(e.bias + n0 + j) : 0.f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: the weight slice once, then A tiles
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_expect_tx(&w_bar[kb], S::W_KB_BYTES);
+                tma_load_2d(wreg + kb * S::W_KB_BYTES, &tmB, &w_bar[kb], kb * GEMM_BK, n0);
+            }
+            uint32_t it = 0;
+            for (int mt = r0; mt < num_m; mt += cps) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], S::A_BYTES);
+                    tma_load_2d(aring + s * S::A_BYTES, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+        uint32_t it = 0, tcount = 0;
+        for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                if (tcount == 0) mbar_wait(&w_bar[kb], 0);              // weight k-block resident (first tile only)
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(aring + s * S::A_BYTES));
+                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(wreg + kb * S::W_KB_BYTES));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) = 32 tile rows and column half (w - 2) / 4
+        const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int HW_COLS = BN / 2;
+        constexpr int EPC = 16 / (int)sizeof(OutT);                      // elements per 16-byte chunk
+        constexpr int CH = 32 / EPC;                                     // chunks per 32-column staging row (4 bf16 / 8 fp32)
+        constexpr int RPI = 32 / CH;                                     // rows covered by one warp-wide 16-byte access
+        unsigned char* stg = staging + (warp - 2) * S::STG_WARP;
+        const OutT* resp = reinterpret_cast<const OutT*>(e.residual);
+        OutT* outp = reinterpret_cast<OutT*>(e.C);
+        uint32_t tcount = 0;
+        for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
+            const int m0 = mt * GEMM_BM;
+            const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tmem_full_bar[as], aph);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = half * HW_COLS; c < (half + 1) * HW_COLS; c += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
+                if (c + 32 == (half + 1) * HW_COLS) {                    // last TMEM read of this accumulator by this warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                // residual chunks of this 32 x 32 block: coalesced, issued before the staging round trip
+                uint4 rres[CH];
+                if (resp) {
+#pragma unroll
+                    for (int itx = 0; itx < CH; ++itx) {
+                        const int r = itx * RPI + lane / CH, ch = lane % CH;
+                        const int grow = m0 + qd * 32 + r, col = n0 + c + ch * EPC;
+                        rres[itx] = make_uint4(0, 0, 0, 0);
+                        if (grow < e.M && col < e.N) rres[itx] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + col));
+                    }
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j);
+                    v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+                    v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+                }
+                if (e.relu == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                unsigned char* srow = stg + lane * (32 * (int)sizeof(OutT));
+#pragma unroll
+                for (int k = 0; k < CH; ++k)
+                    *reinterpret_cast<uint4*>(srow + ((k ^ (lane & (CH - 1))) * 16)) = pack_chunk<OutT>(v + k * EPC);
+                __syncwarp();
+#pragma unroll
+                for (int itx = 0; itx < CH; ++itx) {
+                    const int r = itx * RPI + lane / CH, ch = lane % CH;
+                    const int grow = m0 + qd * 32 + r, col = n0 + c + ch * EPC;
+                    uint4 d = *reinterpret_cast<const uint4*>(stg + r * (32 * (int)sizeof(OutT)) + ((ch ^ (r & (CH - 1))) * 16));
+                    if (resp || e.relu == 2) {
+                        float f[EPC];
+                        unpack_chunk<OutT>(d, f);
+                        if (resp) {
+                            float g[EPC];
+                            unpack_chunk<OutT>(rres[itx], g);
+#pragma unroll
+                            for (int k = 0; k < EPC; ++k) f[k] += g[k];
+                        }
+                        if (e.relu == 2) {
+#pragma unroll
+                            for (int k = 0; k < EPC; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        d = pack_chunk<OutT>(f);
+                    }
+                    if (grow < e.M && col < e.N && !(e.dbg & 1)) *reinterpret_cast<uint4*>(outp + (size_t)grow * e.ldc + col) = d;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<S::TMEM_COLS>(tmem_base);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- fp32 SIMT GEMM (parity mode)
 // 64x64 tile, 16-deep K slab, 256 threads, 4x4 register micro-tile; exact fp32 FMA accumulation in K order.
 __global__ void __launch_bounds__(256)
@@ -522,6 +726,52 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int 
     return DTLR_OK;
 }
 
+template <int BN, typename OutT>
+static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st) {
+    using S = WsSmem<BN, OutT>;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta, A, e.M, e.K, lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16(&tb, W, e.N, e.K, ldw, BN))) return rc;
+    auto k = gemm_ws_tcgen05_kernel<BN, OutT>;
+    static bool configured = false;
+    if (!configured) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    const int ns = e.N / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
+    int cps = sm_count() / ns;
+    if (cps > num_m) cps = num_m;
+    k<<<ns * cps, 320, S::TOTAL, st>>>(ta, tb, e, ns, cps);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+// weight-stationary path: K <= 256, N a multiple of the slice width, vectorisable rows, and enough row tiles that every CTA
+// amortises its weight slice over >= 2 of them
+template <typename OutT>
+static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st, int* rc) {
+    if (g_debug_flags & 32) return false;
+    constexpr int EPC = 16 / (int)sizeof(OutT);
+    if (e.K > 256 || (e.N % EPC) != 0 || (e.ldc % EPC) != 0 || ((uintptr_t)e.C & 15) != 0) return false;
+    if (e.residual && ((e.ldr % EPC) != 0 || ((uintptr_t)e.residual & 15) != 0)) return false;
+    const long long num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
+    int bn = 0;
+    if ((e.N % 256) == 0) bn = 256;
+    else if ((e.N % 192) == 0) bn = 192;
+    else if ((e.N % 128) == 0) bn = 128;
+    else if ((e.N % 64) == 0) bn = 64;
+    if (!bn || e.N / bn > sm_count()) return false;
+    if (num_m * (e.N / bn) < 2ll * sm_count()) return false;
+    switch (bn) {
+        case 256: *rc = launch_ws<256, OutT>(A, lda, W, ldw, e, st); break;
+        case 192: *rc = launch_ws<192, OutT>(A, lda, W, ldw, e, st); break;
+        case 128: *rc = launch_ws<128, OutT>(A, lda, W, ldw, e, st); break;
+        default: *rc = launch_ws<64, OutT>(A, lda, W, ldw, e, st); break;
+    }
+    return true;
+}
+
 template <int BN, int STAGES, typename OutT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st) {
     using S = GemmSmem<BN, STAGES, OutT>;
@@ -564,7 +814,8 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0,
                    "gemm: bf16 operands need 16-byte aligned rows (lda=%d ldw=%d)", lda, ldw);
     CUtensorMap ta, tb;
-    int rc;
+    int rc = DTLR_OK;
+    if (out_dtype == DTLR_BF16 ? ws_try<__nv_bfloat16>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
     if (out_dtype == DTLR_BF16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
         // N = 256 layers become one tile per row block

@@ -96,3 +96,34 @@ def test_gemm_with_fused_layernorm(M, K, with_res, with_add2):
     # and the composed un-fused path gives the same thing
     un = ops.add_layernorm(ops.gemm(a, w, bias, residual=res), None, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
+
+
+WS_SHAPES = [  # (M, N, K): large enough that dtlr_gemm picks the weight-stationary kernel (K <= 256, >= 2 row tiles per CTA)
+    (58368, 256, 256), (57600 + 77, 384, 256), (20000, 2048, 256), (57600, 512, 256), (163840, 256, 64), (80000, 64, 256),
+    (50000, 128, 192), (45000, 256, 152), (60000, 1536, 256), (40960, 512, 128),
+]
+
+
+@pytest.mark.parametrize("M,N,K", WS_SHAPES)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_weight_stationary_kernel(M, N, K, out_dtype):
+    """gemm_ws_tcgen05_kernel (resident weight slice, A-only ring) vs fp64 matmul of the same bf16 operands, all epilogues
+    (bias, ReLU before / after the residual add), ragged M and K tails; and bit-identical to the tile kernel
+    (dtlr_debug_flags(32) disables the weight-stationary path): same MMA order, same fp32 epilogue arithmetic."""
+    from dtlr_b200 import ops, _lib
+    a, w, bias = _mk(M, N, K, torch.bfloat16, M + N + K)
+    res = torch.randn(M, N, device="cuda").to(out_dtype)
+    tol = 2e-2 if out_dtype == torch.bfloat16 else 1e-4
+    ref = a.double() @ w.double().T + bias.double()
+    cases = [dict(relu=0, residual=None), dict(relu=1, residual=res), dict(relu=2, residual=res)]
+    outs = [ops.gemm(a, w, bias, out_dtype=out_dtype, **c) for c in cases]
+    _lib.lib().dtlr_debug_flags(32)
+    try:
+        olds = [ops.gemm(a, w, bias, out_dtype=out_dtype, **c) for c in cases]
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
+    refs = [ref, torch.relu(ref) + res.double(), torch.relu(ref + res.double())]
+    for o, old, r in zip(outs, olds, refs):
+        err = (o.double() - r).abs().max().item() / r.abs().max().item()
+        assert err < tol, err
+        assert torch.equal(o, old)
