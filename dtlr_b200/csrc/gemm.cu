@@ -420,24 +420,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------- weight-stationary tcgen05 GEMM
-// K <= 256 (every Linear of the transformer except linear2 / ref_point_head.0, and the 1x1 convolutions of layer1-2): the
-// tile kernel above re-fetches the weight tile with every output tile and can hold only ONE tile's operands in its ring, so
-// with K = 256 it runs at the L2 -> SM rate (a 128 x 128 tile moves 128 KB for 8.4 MFLOP).  Here a persistent CTA owns one
-// BN-wide slice of W for its whole life (loaded once, up to 128 KB resident in shared memory) and streams only A tiles
-// through the ring (16 KB stages, several tiles deep); with BN = 256 a 256-wide layer reads A exactly once.  CTA c works on
-// slice c % ns and row tiles c / ns, c / ns + cps, ... so that the ns CTAs sharing an A tile fetch it at the same time (one
-// HBM read, the rest L2 hits).  Epilogue: 8 warps, TMEM -> registers -> bias / ReLU -> 32 x 32 XOR-swizzled staging block per
-// warp -> coalesced 16-byte stores (+ coalesced residual reads).
-template <int BN, typename OutT>
+// K <= 256 (every Linear of the transformer except linear2 / ref_point_head.0, and the 1x1 convolutions of layer1-3).
+// Measured on the tile kernel above (tools/gemm_probe.py, CUDA-graph timing): with K = 256 the loads need 10 us and the MMAs
+// 3 us of a 18 us launch -- the EPILOGUE (TMEM -> registers -> staging -> LDS -> STG with per-lane address arithmetic) is what
+// bounds it, and the weight tile is re-fetched with every output tile.  Here:
+//  * a persistent CTA owns one BN-wide slice of W for its whole life (loaded once, up to 128 KB resident in shared memory)
+//    and streams only A tiles through the TMA ring (16 KB stages); with BN = 256 a 256-wide layer reads A exactly once.
+//    CTA c works on slice c % ns and row tiles c / ns, c / ns + cps, ... so the ns CTAs that share an A tile fetch it at the
+//    same time (one HBM read, the rest L2 hits).
+//  * the epilogue never touches global memory through the LSU: each of the 8 epilogue warps converts a 32-row x 128-byte block
+//    (thread = row: tcgen05.ld, bias, ReLU, pack), writes it 128B-swizzled into its own 4 KB buffer (conflict-free 16-byte
+//    stores) and one lane hands it to the TMA store engine (cp.async.bulk.tensor, bulk-group completion; rows / columns beyond
+//    M / N are clipped by the hardware).  A residual operand arrives the same way in the other direction: TMA-loaded one
+//    block ahead into the buffer the result will overwrite (two buffers per warp), read back swizzled by the row's thread.
+template <int BN, typename OutT, bool RES>
 struct WsSmem {
     static constexpr int KB_MAX = 4;
     static constexpr int W_KB_BYTES = BN * GEMM_BK * 2;                       // one 64-wide k-block of the slice
     static constexpr int W_BYTES = KB_MAX * W_KB_BYTES;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                     // 16 KB
-    static constexpr int STG_WARP = 32 * 32 * (int)sizeof(OutT);              // 32 rows x 32 columns per epilogue warp
+    static constexpr int BLK_BYTES = 32 * 128;                                // one epilogue block: 32 rows x 128 bytes
+    static constexpr int NBUF = RES ? 2 : 1;
+    static constexpr int STG_WARP = NBUF * BLK_BYTES;
     static constexpr int STG_BYTES = 8 * STG_WARP;
     static constexpr int BIAS_BYTES = BN * 4;
-    static constexpr int FIXED = W_BYTES + STG_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int FIXED = W_BYTES + STG_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
     static constexpr int STAGES_FIT = (232448 - FIXED) / A_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int TOTAL = FIXED + STAGES * A_BYTES;
@@ -445,24 +453,34 @@ struct WsSmem {
     static_assert(STAGES >= 3, "weight slice leaves too little room for the A ring");
 };
 
-template <int BN, typename OutT>
+template <typename OutT, int CB> struct TmemBlock;
+template <> struct TmemBlock<__nv_bfloat16, 64> {
+    static __device__ __forceinline__ void load(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld64(taddr, r); }
+};
+template <> struct TmemBlock<float, 32> {
+    static __device__ __forceinline__ void load(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+};
+
+template <int BN, typename OutT, bool RES>
 __global__ void __launch_bounds__(320, 1)
-gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi e,
+gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmEpi e,
                        const int ns, const int cps) {
-    using S = WsSmem<BN, OutT>;
+    using S = WsSmem<BN, OutT, RES>;
     constexpr int STAGES = S::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* wreg = smem;                                          // [KB_MAX][BN rows x 128 B], 128B swizzle
     unsigned char* aring = smem + S::W_BYTES;                            // [STAGES][128 rows x 128 B]
-    unsigned char* staging = aring + STAGES * S::A_BYTES;
+    unsigned char* staging = aring + STAGES * S::A_BYTES;                // [8 warps][NBUF][32 rows x 128 B], 128B swizzle
     float* bias_s = reinterpret_cast<float*>(staging + S::STG_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + S::STG_BYTES + S::BIAS_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* w_bar = empty_bar + STAGES;              // [KB_MAX]
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* w_bar = empty_bar + 8;                   // [KB_MAX]
     uint64_t* tmem_full_bar = w_bar + S::KB_MAX;       // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* res_bar = tmem_empty_bar + 2;            // [8 warps][2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slice = blockIdx.x % ns, r0 = blockIdx.x / ns;
@@ -474,6 +492,8 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        if (RES) tma_prefetch_desc(&tmR);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -483,6 +503,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(&tmem_full_bar[a], 1);
             mbar_init(&tmem_empty_bar[a], 8);
         }
+        for (int k = 0; k < 16; ++k) mbar_init(&res_bar[k], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<S::TMEM_COLS>(tmem_ptr);
@@ -529,8 +550,10 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const uint64_t da = make_sw128_kmajor_desc(smem_u32(aring + s * S::A_BYTES));
                     const uint64_t db = make_sw128_kmajor_desc(smem_u32(wreg + kb * S::W_KB_BYTES));
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        if (e.dbg & 2) break;
                         umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[s]);
                     if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
                 }
@@ -538,83 +561,100 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) = 32 tile rows and column half (w - 2) / 4
+        // ===== epilogue: warp w owns TMEM lane quarter (w % 4) = 32 tile rows and every second 128-byte column block
         const int qd = warp & 3;
-        const int half = (warp - 2) >> 2;
-        constexpr int HW_COLS = BN / 2;
+        const int hsel = (warp - 2) >> 2;
         constexpr int EPC = 16 / (int)sizeof(OutT);                      // elements per 16-byte chunk
-        constexpr int CH = 32 / EPC;                                     // chunks per 32-column staging row (4 bf16 / 8 fp32)
-        constexpr int RPI = 32 / CH;                                     // rows covered by one warp-wide 16-byte access
-        unsigned char* stg = staging + (warp - 2) * S::STG_WARP;
-        const OutT* resp = reinterpret_cast<const OutT*>(e.residual);
-        OutT* outp = reinterpret_cast<OutT*>(e.C);
-        uint32_t tcount = 0;
+        constexpr int CB = 8 * EPC;                                      // columns per block (64 bf16 / 32 fp32)
+        constexpr int NCB = BN / CB;
+        unsigned char* buf0 = staging + (warp - 2) * S::STG_WARP;
+        uint64_t* rbar = res_bar + (warp - 2) * 2;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        uint32_t tcount = 0, bcount = 0;
+        if (RES && hsel < NCB && r0 < num_m && lane == 0) {              // residual of this warp's first block
+            mbar_expect_tx(&rbar[0], S::BLK_BYTES);
+            tma_load_2d(buf0, &tmR, &rbar[0], n0 + hsel * CB, r0 * GEMM_BM + qd * 32);
+        }
         for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
             const int m0 = mt * GEMM_BM;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-            mbar_wait(&tmem_full_bar[as], aph);
-            tcgen05_fence_after();
+            bool waited = false;
+            if (!(e.dbg & 4)) {
 #pragma unroll 1
-            for (int c = half * HW_COLS; c < (half + 1) * HW_COLS; c += 32) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, acc);
-                if (c + 32 == (half + 1) * HW_COLS) {                    // last TMEM read of this accumulator by this warp
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                }
-                // residual chunks of this 32 x 32 block: coalesced, issued before the staging round trip
-                uint4 rres[CH];
-                if (resp) {
-#pragma unroll
-                    for (int itx = 0; itx < CH; ++itx) {
-                        const int r = itx * RPI + lane / CH, ch = lane % CH;
-                        const int grow = m0 + qd * 32 + r, col = n0 + c + ch * EPC;
-                        rres[itx] = make_uint4(0, 0, 0, 0);
-                        if (grow < e.M && col < e.N) rres[itx] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + col));
+                for (int cb = hsel; cb < NCB; cb += 2, ++bcount) {
+                    unsigned char* buf = buf0 + (RES ? (bcount & 1) * S::BLK_BYTES : 0);
+                    if (RES && lane == 0) {
+                        // the other buffer was last read by the store of block bcount-1 (the newest bulk group): once that read is
+                        // done, fetch the residual of block bcount+1 into it
+                        tma_store_wait_read<0>();
+                        int ncb = cb + 2, nmt = mt;
+                        if (ncb >= NCB) { ncb = hsel; nmt = mt + cps; }
+                        if (nmt < num_m) {
+                            uint64_t* nb = &rbar[(bcount + 1) & 1];
+                            mbar_expect_tx(nb, S::BLK_BYTES);
+                            tma_load_2d(buf0 + ((bcount + 1) & 1) * S::BLK_BYTES, &tmR, nb, n0 + ncb * CB, nmt * GEMM_BM + qd * 32);
+                        }
                     }
-                }
-                float v[32];
+                    if (!waited) {
+                        mbar_wait(&tmem_full_bar[as], aph);
+                        tcgen05_fence_after();
+                        waited = true;
+                    }
+                    uint32_t acc[CB];
+                    TmemBlock<OutT, CB>::load(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * CB), acc);
+                    if (cb + 2 >= NCB) {                                 // last TMEM read of this accumulator by this warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                    float v[CB];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + j);
-                    v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
-                    v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
-                }
-                if (e.relu == 1) {
+                    for (int j = 0; j < CB; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cb * CB + j);
+                        v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+                        v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+                    }
+                    if (e.relu == 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                unsigned char* srow = stg + lane * (32 * (int)sizeof(OutT));
+                        for (int j = 0; j < CB; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    unsigned char* srow = buf + lane * 128;
+                    if (RES) {
+                        mbar_wait(&rbar[bcount & 1], (bcount >> 1) & 1);  // residual block has landed (TMA, swizzled)
 #pragma unroll
-                for (int k = 0; k < CH; ++k)
-                    *reinterpret_cast<uint4*>(srow + ((k ^ (lane & (CH - 1))) * 16)) = pack_chunk<OutT>(v + k * EPC);
-                __syncwarp();
-#pragma unroll
-                for (int itx = 0; itx < CH; ++itx) {
-                    const int r = itx * RPI + lane / CH, ch = lane % CH;
-                    const int grow = m0 + qd * 32 + r, col = n0 + c + ch * EPC;
-                    uint4 d = *reinterpret_cast<const uint4*>(stg + r * (32 * (int)sizeof(OutT)) + ((ch ^ (r & (CH - 1))) * 16));
-                    if (resp || e.relu == 2) {
-                        float f[EPC];
-                        unpack_chunk<OutT>(d, f);
-                        if (resp) {
+                        for (int k = 0; k < 8; ++k) {
                             float g[EPC];
-                            unpack_chunk<OutT>(rres[itx], g);
+                            unpack_chunk<OutT>(*reinterpret_cast<const uint4*>(srow + ((k ^ swz) * 16)), g);
 #pragma unroll
-                            for (int k = 0; k < EPC; ++k) f[k] += g[k];
+                            for (int i = 0; i < EPC; ++i) v[k * EPC + i] += g[i];
                         }
-                        if (e.relu == 2) {
-#pragma unroll
-                            for (int k = 0; k < EPC; ++k) f[k] = fmaxf(f[k], 0.f);
-                        }
-                        d = pack_chunk<OutT>(f);
+                    } else {
+                        if (lane == 0) tma_store_wait_read<0>();         // the previous store has finished reading this buffer
+                        __syncwarp();
                     }
-                    if (grow < e.M && col < e.N && !(e.dbg & 1)) *reinterpret_cast<uint4*>(outp + (size_t)grow * e.ldc + col) = d;
+                    if (e.relu == 2) {
+#pragma unroll
+                        for (int j = 0; j < CB; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        *reinterpret_cast<uint4*>(srow + ((k ^ swz) * 16)) = pack_chunk<OutT>(v + k * EPC);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(e.dbg & 1)) {
+                        tma_store_2d(&tmC, buf, n0 + cb * CB, m0 + qd * 32);
+                        tma_store_commit();
+                    }
                 }
+            }
+            if (!waited) {                                               // no block of this tile belongs to this warp
+                mbar_wait(&tmem_full_bar[as], aph);
+                tcgen05_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
             }
         }
+        if (lane == 0) tma_store_wait<0>();                              // the buffers must outlive the last store
     }
     __syncthreads();
     if (warp == 1) {
@@ -726,14 +766,39 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int 
     return DTLR_OK;
 }
 
-template <int BN, typename OutT>
+// 2-D tensor map of an output / residual matrix for the TMA epilogue: box = 32 rows x 128 bytes, 128B swizzle
+template <typename OutT>
+static int make_tmap_out(CUtensorMap* map, const void* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return DTLR_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(OutT)};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(OutT)), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for the %dx%d output (ld=%d)", (int)r, rows, cols, ld);
+        return DTLR_ERR_CUDA;
+    }
+    return DTLR_OK;
+}
+
+template <int BN, typename OutT, bool RES>
 static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st) {
-    using S = WsSmem<BN, OutT>;
-    CUtensorMap ta, tb;
+    using S = WsSmem<BN, OutT, RES>;
+    CUtensorMap ta, tb, tc, tr;
     int rc;
     if ((rc = make_tmap_bf16(&ta, A, e.M, e.K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, e.N, e.K, ldw, BN))) return rc;
-    auto k = gemm_ws_tcgen05_kernel<BN, OutT>;
+    if ((rc = make_tmap_out<OutT>(&tc, e.C, e.M, e.N, e.ldc))) return rc;
+    tr = tc;
+    if (RES && (rc = make_tmap_out<OutT>(&tr, e.residual, e.M, e.N, e.ldr))) return rc;
+    auto k = gemm_ws_tcgen05_kernel<BN, OutT, RES>;
     static bool configured = false;
     if (!configured) {
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -742,13 +807,13 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
     const int ns = e.N / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int cps = sm_count() / ns;
     if (cps > num_m) cps = num_m;
-    k<<<ns * cps, 320, S::TOTAL, st>>>(ta, tb, e, ns, cps);
+    k<<<ns * cps, 320, S::TOTAL, st>>>(ta, tb, tc, tr, e, ns, cps);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
 
-// weight-stationary path: K <= 256, N a multiple of the slice width, vectorisable rows, and enough row tiles that every CTA
-// amortises its weight slice over >= 2 of them
+// weight-stationary path: K <= 256, N a multiple of the slice width, 16-byte aligned output / residual rows, and enough row
+// tiles that every CTA amortises its weight slice over >= 2 of them
 template <typename OutT>
 static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st, int* rc) {
     if (g_debug_flags & 32) return false;
@@ -757,17 +822,26 @@ static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi
     if (e.residual && ((e.ldr % EPC) != 0 || ((uintptr_t)e.residual & 15) != 0)) return false;
     const long long num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int bn = 0;
-    if ((e.N % 256) == 0) bn = 256;
-    else if ((e.N % 192) == 0) bn = 192;
-    else if ((e.N % 128) == 0) bn = 128;
-    else if ((e.N % 64) == 0) bn = 64;
+    if (e.residual) {                    // two epilogue buffers per warp: the weight slice is at most 128 wide
+        if ((e.N % 128) == 0) bn = 128;
+        else if ((e.N % 64) == 0) bn = 64;
+    } else {
+        if ((e.N % 256) == 0) bn = 256;
+        else if ((e.N % 192) == 0) bn = 192;
+        else if ((e.N % 128) == 0) bn = 128;
+        else if ((e.N % 64) == 0) bn = 64;
+    }
     if (!bn || e.N / bn > sm_count()) return false;
     if (num_m * (e.N / bn) < 2ll * sm_count()) return false;
+    if (e.residual) {
+        *rc = bn == 128 ? launch_ws<128, OutT, true>(A, lda, W, ldw, e, st) : launch_ws<64, OutT, true>(A, lda, W, ldw, e, st);
+        return true;
+    }
     switch (bn) {
-        case 256: *rc = launch_ws<256, OutT>(A, lda, W, ldw, e, st); break;
-        case 192: *rc = launch_ws<192, OutT>(A, lda, W, ldw, e, st); break;
-        case 128: *rc = launch_ws<128, OutT>(A, lda, W, ldw, e, st); break;
-        default: *rc = launch_ws<64, OutT>(A, lda, W, ldw, e, st); break;
+        case 256: *rc = launch_ws<256, OutT, false>(A, lda, W, ldw, e, st); break;
+        case 192: *rc = launch_ws<192, OutT, false>(A, lda, W, ldw, e, st); break;
+        case 128: *rc = launch_ws<128, OutT, false>(A, lda, W, ldw, e, st); break;
+        default: *rc = launch_ws<64, OutT, false>(A, lda, W, ldw, e, st); break;
     }
     return true;
 }

@@ -108,8 +108,8 @@ WS_SHAPES = [  # (M, N, K): large enough that dtlr_gemm picks the weight-station
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
 def test_weight_stationary_kernel(M, N, K, out_dtype):
     """gemm_ws_tcgen05_kernel (resident weight slice, A-only ring) vs fp64 matmul of the same bf16 operands, all epilogues
-    (bias, ReLU before / after the residual add), ragged M and K tails; and bit-identical to the tile kernel
-    (dtlr_debug_flags(32) disables the weight-stationary path): same MMA order, same fp32 epilogue arithmetic."""
+    (bias, ReLU before / after the residual add; TMA-store epilogue, TMA-loaded residual), ragged M and K tails; and
+    identical to the tile kernel (dtlr_debug_flags(32) disables the weight-stationary path): same MMA order."""
     from dtlr_b200 import ops, _lib
     a, w, bias = _mk(M, N, K, torch.bfloat16, M + N + K)
     res = torch.randn(M, N, device="cuda").to(out_dtype)
@@ -123,7 +123,10 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
     finally:
         _lib.lib().dtlr_debug_flags(0)
     refs = [ref, torch.relu(ref) + res.double(), torch.relu(ref + res.double())]
-    for o, old, r in zip(outs, olds, refs):
+    for c, o, old, r in zip(cases, outs, olds, refs):
         err = (o.double() - r).abs().max().item() / r.abs().max().item()
         assert err < tol, err
-        assert torch.equal(o, old)
+        if c["residual"] is None or out_dtype == torch.float32:
+            assert torch.equal(o, old)
+        else:   # the tile kernel rounds to bf16 before the residual add, this one adds in fp32 and rounds once
+            assert (o.float() - old.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()

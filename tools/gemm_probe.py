@@ -1,23 +1,58 @@
-"""Tuning probe: time dtlr_gemm with parts of the kernel disabled (dtlr_debug_flags) to see what bounds a tile."""
+"""Tuning probe: time dtlr_gemm with parts of the kernel disabled (dtlr_debug_flags) to see what bounds a tile, next to
+plain device copies of the same byte counts (what the memory system gives a kernel of this size)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dtlr_b200 import ops, _lib
 
-def t(M, N, K, flags, iters=20):
-    _lib.lib().dtlr_debug_flags(flags)
-    a = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(4)]
-    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
-    bias = torch.randn(N, device="cuda")
-    out = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(4)]
-    for i in range(4): ops.gemm(a[i % 4], w, bias, out=out[i % 4])
+
+def timeit(fn, iters=20):
+    """GPU time per call of `iters` back-to-back launches replayed from a CUDA graph (no host launch gaps)."""
+    for i in range(4):
+        fn(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(2):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters): ops.gemm(a[i % 4], w, bias, out=out[i % 4])
-    e1.record(); torch.cuda.synchronize()
-    _lib.lib().dtlr_debug_flags(0)
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1000 / iters
 
-for (M, N, K) in [(58368, 256, 256), (58368, 256, 2048), (58368, 2048, 256), (163840, 256, 64), (57600, 512, 256)]:
-    print(M, N, K, {name: round(t(M, N, K, f), 1) for name, f in
-                    [("full_bn256", 0), ("full_bn128", 8), ("no_store", 1), ("no_mma", 2), ("no_epilogue", 5), ("loads_only", 7)]})
+
+def t(M, N, K, flags, nbuf=6):
+    _lib.lib().dtlr_debug_flags(flags)
+    a = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    us = timeit(lambda i: ops.gemm(a[i % nbuf], w, bias, out=out[i % nbuf]))
+    _lib.lib().dtlr_debug_flags(0)
+    return us
+
+
+def copy_ref(M, N, K, nbuf=6):
+    """device copy moving the same bytes as the GEMM reads + writes (A in, C out)"""
+    a = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
+    out = [torch.empty(M, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    us = timeit(lambda i: out[i % nbuf].copy_(a[i % nbuf]))
+    return us, 2 * M * K * 2 / us / 1e3
+
+
+for (M, N, K) in [(58368, 256, 256), (58368, 2048, 256), (57600, 512, 256), (163840, 256, 64), (58368, 256, 2048)]:
+    res = {name: round(t(M, N, K, f), 1) for name, f in
+           [("ws", 0), ("ws_no_store", 1), ("ws_no_mma", 2), ("ws_no_epilogue", 4), ("ws_loads_only", 6),
+            ("tile", 32), ("tile_no_store", 33), ("tile_no_mma", 34), ("tile_loads_only", 39)]}
+    cu, gbs = copy_ref(M, N, K)
+    print(M, N, K, res, "copy %dx%d bf16: %.1f us (%.0f GB/s)" % (M, K, cu, gbs), flush=True)
