@@ -1,0 +1,362 @@
+// dtlr_b200 -- the position-wise feed-forward block of a transformer layer as ONE tcgen05 kernel for sm_100a:
+//
+//     Y = LayerNorm( X + W2 . relu(W1 . X + b1) + b2 ) * gamma + beta          X, Y: [M, 256] bf16, hidden = HID
+//
+// which is `forward_ffn` + `norm` of reference models/dino/deformable_transformer.py:804-808,816-817 (encoder layer) and
+// :876-880 (decoder layer); d_model 256, dim_feedforward 2048, ReLU, dropout 0, post-norm.
+//
+// Why fused: as two GEMMs the hidden activation (M x 2048 bf16 = 239 MB at B = 64) is written to HBM and read back; measured
+// (tools/gemm_probe.py) linear1 is bound by that write (64 us, HBM floor 42 us) and linear2 by re-reading it (~95 us), 159 us
+// per layer for 122 GFLOP.  Here the hidden activation never leaves the SM:
+//
+//   per 128-row tile of X (resident in shared memory, 64 KB, also the residual and finally the output staging):
+//     for each chunk j of 128 hidden units (HID / 128 chunks, software-pipelined by one chunk):
+//       G1(j):  Hacc[j&1] (TMEM, 128 x 128 fp32)  = X . W1[j]^T                      16 x tcgen05.mma 128x128x16
+//       E1(j):  8 epilogue warps: TMEM -> +b1 -> ReLU -> bf16 -> shared memory Hs[j&1] in the K-major 128B-swizzled
+//               A-operand layout (conflict-free 16-byte stores, thread = row)
+//       G2(j):  Yacc (TMEM, 128 x 256 fp32)      += Hs[j&1] . W2[:, j]^T              16 x tcgen05.mma 128x128x16
+//     final:   Yacc + b2 + X -> LayerNorm (row statistics: thread = row, the two column halves meet in shared memory)
+//              -> bf16 written over the X tile in place -> TMA store.
+//   W1 / W2 chunks (2 MB per tile in total, L2-resident) stream through a 5-stage TMA ring of 16 KB stages.
+//   TMEM: Yacc 256 columns + 2 x 128 columns of Hacc = 512.
+//
+// Warp roles as in gemm.cu: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue.
+#include "tc_common.cuh"
+
+namespace dtlr {
+
+constexpr int FF_D = 256;          // d_model (one full LayerNorm row per tile)
+constexpr int FF_BM = 128;
+constexpr int FF_HC = 128;         // hidden units per chunk
+constexpr int FF_STAGE = 16384;    // ring stage: 128 rows x 64 k (bf16, 128B swizzle)
+constexpr int FF_NS = 5;           // ring depth
+constexpr int FF_MAX_HID = 2048;
+
+struct FfnArgs {
+    const float* b1;      // [HID]
+    const float* b2;      // [256]
+    const float* gamma;   // [256]
+    const float* beta;    // [256]
+    float eps;
+    int M, HID;
+};
+
+struct FfnSmem {
+    static constexpr int XS = 4 * FF_STAGE;                 // X tile: 4 k-blocks of 128 x 64
+    static constexpr int HS = 2 * 2 * FF_STAGE;             // hidden chunk, A-operand layout, double-buffered (2 k-blocks each)
+    static constexpr int RING = FF_NS * FF_STAGE;
+    static constexpr int B1 = FF_MAX_HID * 4;
+    static constexpr int VEC = 3 * FF_D * 4;                // b2, gamma, beta
+    static constexpr int STAT = FF_BM * 2 * 2 * 4;          // per row, per column half: sum, sum of squares
+    static constexpr int BAR = 512;
+    static constexpr int TOTAL = 1024 + XS + HS + RING + B1 + VEC + STAT + BAR;
+};
+static_assert(FfnSmem::TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
+
+__device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ff_round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__global__ void __launch_bounds__(320, 1)
+ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* xs = smem;
+    unsigned char* hs = xs + FfnSmem::XS;
+    unsigned char* ring = hs + FfnSmem::HS;
+    float* b1_s = reinterpret_cast<float*>(ring + FfnSmem::RING);
+    float* b2_s = b1_s + FF_MAX_HID;
+    float* gamma_s = b2_s + FF_D;
+    float* beta_s = gamma_s + FF_D;
+    float* stat_s = beta_s + FF_D;                           // [128 rows][2 halves][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + FF_BM * 4);
+    uint64_t* x_full = bars;             // [1]
+    uint64_t* x_free = bars + 1;         // [1]  8 arrivals (epilogue warps): the X tile (output staging) may be overwritten
+    uint64_t* w_full = bars + 2;         // [FF_NS]
+    uint64_t* w_empty = w_full + FF_NS;  // [FF_NS]
+    uint64_t* hacc_full = w_empty + FF_NS;   // [2] G1 complete
+    uint64_t* hacc_free = hacc_full + 2;     // [2] 8 arrivals: TMEM hidden accumulator drained
+    uint64_t* hs_full = hacc_free + 2;       // [2] 8 arrivals: hidden chunk written to shared memory
+    uint64_t* hs_free = hs_full + 2;         // [2] G2 complete
+    uint64_t* y_full = hs_free + 2;          // [1]
+    uint64_t* y_free = y_full + 1;           // [1] 8 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(y_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (a.M + FF_BM - 1) / FF_BM;
+    const int NJ = a.HID / FF_HC;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW1);
+        tma_prefetch_desc(&tmW2);
+        tma_prefetch_desc(&tmO);
+        mbar_init(x_full, 1);
+        mbar_init(x_free, 8);
+        for (int s = 0; s < FF_NS; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&hacc_full[b], 1);
+            mbar_init(&hacc_free[b], 8);
+            mbar_init(&hs_full[b], 8);
+            mbar_init(&hs_free[b], 1);
+        }
+        mbar_init(y_full, 1);
+        mbar_init(y_free, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + i);
+    for (int i = threadIdx.x; i < FF_D; i += 320) {
+        b2_s[i] = __ldg(a.b2 + i);
+        gamma_s[i] = __ldg(a.gamma + i);
+        beta_s[i] = __ldg(a.beta + i);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tm_y = tmem_base;                 // columns [0, 256)
+    const uint32_t tm_h = tmem_base + 256;           // 2 x 128 columns
+
+    if (warp == 0) {
+        // ===== TMA producer: X tile, then the weight chunks in exactly the order the MMA warp consumes them
+        if (elect_one()) {
+            uint32_t it = 0, t = 0;
+            for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t) {
+                mbar_wait(x_free, (t & 1) ^ 1);
+                mbar_expect_tx(x_full, FfnSmem::XS);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + kb * FF_STAGE, &tmX, x_full, kb * 64, mt * FF_BM);
+                for (int j = 0; j <= NJ; ++j) {
+                    if (j < NJ) {
+                        for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
+                            const int s = it % FF_NS;
+                            mbar_wait(&w_empty[s], ((it / FF_NS) & 1) ^ 1);
+                            mbar_expect_tx(&w_full[s], FF_STAGE);
+                            tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
+                        }
+                    }
+                    if (j >= 1) {
+                        for (int q = 0; q < 4; ++q, ++it) {                 // W2 output rows (q&1)*128.., hidden columns of chunk j-1
+                            const int s = it % FF_NS;
+                            mbar_wait(&w_empty[s], ((it / FF_NS) & 1) ^ 1);
+                            mbar_expect_tx(&w_full[s], FF_STAGE);
+                            tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: G1(j) one chunk ahead of G2(j-1)
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
+        uint32_t it = 0, g = 0, t = 0;
+        for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
+            mbar_wait(x_full, t & 1);
+            tcgen05_fence_after();
+            for (int j = 0; j <= NJ; ++j) {
+                if (j < NJ) {
+                    const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
+                    mbar_wait(&hacc_free[b], (u & 1) ^ 1);                   // epilogue has drained this hidden accumulator
+                    tcgen05_fence_after();
+                    for (int kb = 0; kb < 4; ++kb, ++it) {
+                        const int s = it % FF_NS;
+                        mbar_wait(&w_full[s], (it / FF_NS) & 1);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + kb * FF_STAGE));
+                            const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                            umma_commit(&w_empty[s]);
+                            if (kb == 3) umma_commit(&hacc_full[b]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (j >= 1) {
+                    const uint32_t gj = g + j - 1, b = gj & 1, u = gj >> 1;
+                    mbar_wait(&hs_full[b], u & 1);                           // hidden chunk j-1 is in shared memory
+                    if (j == 1) mbar_wait(y_free, (t & 1) ^ 1);              // previous tile's output accumulator drained
+                    tcgen05_fence_after();
+                    for (int q = 0; q < 4; ++q, ++it) {
+                        const int s = it % FF_NS;
+                        const int kb2 = q >> 1, half = q & 1;
+                        mbar_wait(&w_full[s], (it / FF_NS) & 1);
+                        tcgen05_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(hs + b * (2 * FF_STAGE) + kb2 * FF_STAGE));
+                            const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tm_y + half * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                          (j > 1) || kb2 > 0 || k > 0);
+                            umma_commit(&w_empty[s]);
+                            if (q == 3) {
+                                umma_commit(&hs_free[b]);
+                                if (j == NJ) umma_commit(y_full);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter qd (32 rows), column half hsel
+        const int qd = warp & 3;
+        const int hsel = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        uint32_t g = 0, t = 0;
+        for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
+            // ---- E1: hidden chunk j: +b1, ReLU, bf16, into the A-operand tile of G2
+            for (int j = 0; j < NJ; ++j) {
+                const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
+                mbar_wait(&hacc_full[b], u & 1);
+                tcgen05_fence_after();
+                uint32_t acc[64];
+                tmem_ld64(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 64), acc);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hacc_free[b]);
+                const float* bp = b1_s + j * FF_HC + hsel * 64;
+                uint32_t pk[32];
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bp + c);
+                    const float v0 = fmaxf(__uint_as_float(acc[c]) + b4.x, 0.f), v1 = fmaxf(__uint_as_float(acc[c + 1]) + b4.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(acc[c + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(acc[c + 3]) + b4.w, 0.f);
+                    pk[c / 2] = ff_pack_bf16x2(v0, v1);
+                    pk[c / 2 + 1] = ff_pack_bf16x2(v2, v3);
+                }
+                mbar_wait(&hs_free[b], (u & 1) ^ 1);                         // G2 of chunk gj-2 has finished reading this buffer
+                unsigned char* dst = hs + b * (2 * FF_STAGE) + hsel * FF_STAGE + row * 128;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    *reinterpret_cast<uint4*>(dst + ((k ^ swz) * 16)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hs_full[b]);
+            }
+            // ---- final: Yacc + b2 + X -> LayerNorm -> bf16 over the X tile -> TMA store
+            mbar_wait(x_full, t & 1);
+            mbar_wait(y_full, t & 1);
+            tcgen05_fence_after();
+            float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+            for (int cb = 0; cb < 2; ++cb) {
+                uint32_t acc[64];
+                tmem_ld64(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64), acc);
+                const unsigned char* xrow = xs + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                const float* bp = b2_s + hsel * 128 + cb * 64;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 r4 = *reinterpret_cast<const uint4*>(xrow + ((k ^ swz) * 16));
+                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x0 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i]) + bp[k * 8 + 2 * i] + __uint_as_float(rw[i] << 16));
+                        const float x1 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i + 1]) + bp[k * 8 + 2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u));
+                        sum += x0 + x1;
+                        sq = fmaf(x0, x0, sq);
+                        sq = fmaf(x1, x1, sq);
+                    }
+                }
+            }
+            stat_s[(row * 2 + hsel) * 2] = sum;
+            stat_s[(row * 2 + hsel) * 2 + 1] = sq;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // the two warps of this lane quarter
+            const float mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
+            const float var = fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + a.eps);
+#pragma unroll 1
+            for (int cb = 0; cb < 2; ++cb) {
+                uint32_t acc[64];
+                tmem_ld64(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64), acc);
+                if (cb == 1) {                                               // last TMEM read of the output accumulator
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(y_free);
+                }
+                unsigned char* xrow = xs + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                const int c0 = hsel * 128 + cb * 64;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint4* p = reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16));
+                    const uint4 r4 = *p;
+                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c0 + k * 8 + 2 * i;
+                        const float x0 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i]) + b2_s[c] + __uint_as_float(rw[i] << 16));
+                        const float x1 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i + 1]) + b2_s[c + 1] + __uint_as_float(rw[i] & 0xffff0000u));
+                        o[i] = ff_pack_bf16x2((x0 - mean) * rstd * gamma_s[c] + beta_s[c], (x1 - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
+                    }
+                    *p = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                for (int cb = 0; cb < 2; ++cb)
+                    tma_store_2d(&tmO, xs + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, mt * FF_BM + qd * 32);
+                tma_store_commit();
+                tma_store_wait_read<0>();                                    // the X tile may now be refilled
+                mbar_arrive(x_free);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static int ffn_tmap(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows) {
+    return make_tmap_2d_bf16(map, base, rows, cols, ld, box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace dtlr
+
+using namespace dtlr;
+
+extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                           const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
+                           void* stream) {
+    DTLR_CHECK_ARG(M >= 0 && hidden > 0, "ffn_ln: bad sizes");
+    if (M == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(X && W1 && b1 && W2 && b2 && gamma && beta && Y, "ffn_ln: null pointer");
+    DTLR_CHECK_ARG((hidden % FF_HC) == 0 && hidden <= FF_MAX_HID, "ffn_ln: hidden width %d must be a multiple of 128 and <= %d", hidden, FF_MAX_HID);
+    DTLR_CHECK_ARG(ldx >= FF_D && ldw1 >= FF_D && ldw2 >= hidden && ldy >= FF_D, "ffn_ln: leading dimension too small");
+    DTLR_CHECK_ARG((ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 && (ldy % 8) == 0 &&
+                   ((((uintptr_t)X | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)Y)) & 15) == 0, "ffn_ln: operands need 16-byte aligned rows");
+    CUtensorMap tx, tw1, tw2, to;
+    int rc;
+    if ((rc = ffn_tmap(&tx, X, M, FF_D, ldx, FF_BM))) return rc;
+    if ((rc = ffn_tmap(&tw1, W1, hidden, FF_D, ldw1, 128))) return rc;
+    if ((rc = ffn_tmap(&tw2, W2, FF_D, hidden, ldw2, 128))) return rc;
+    if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        configured = true;
+    }
+    const int num_m = (M + FF_BM - 1) / FF_BM;
+    const int grid = num_m < sm_count() ? num_m : sm_count();
+    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden};
+    ffn_ln_tcgen05_kernel<<<grid, 320, FfnSmem::TOTAL, (cudaStream_t)stream>>>(tx, tw1, tw2, to, a);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}

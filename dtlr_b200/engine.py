@@ -298,11 +298,9 @@ class InferenceEngine:
                 if st is not None and i == 0:
                     st["enc0_core"] = core.view(B, S, d)
                 s1 = ops.linear_ln(core, *lyr["attn"]["out"], src, *lyr["ln1"])
-                hdn = ops.gemm(s1, *lyr["l1"], relu=1)
+                src = ops.ffn_ln(s1, *lyr["l1"], *lyr["l2"], *lyr["ln2"])
                 if i + 1 < len(P["enc"]):
-                    src, q = ops.linear_ln(hdn, *lyr["l2"], s1, *lyr["ln2"], add2=pos)
-                else:
-                    src = ops.linear_ln(hdn, *lyr["l2"], s1, *lyr["ln2"])
+                    q = ops.add(src, pos)
             memory = src
             if st is not None:
                 st["memory"] = memory.view(B, S, d)
@@ -351,8 +349,7 @@ class InferenceEngine:
                 if st is not None and i == 0:
                     st["dec0_core"] = core.view(B, Q, d)
                 tgt = ops.linear_ln(core, *lyr["ca"]["out"], tgt, *lyr["ln1"])
-                hdn = ops.gemm(tgt, *lyr["l1"], relu=1)
-                tgt = ops.linear_ln(hdn, *lyr["l2"], tgt, *lyr["ln3"])
+                tgt = ops.ffn_ln(tgt, *lyr["l1"], *lyr["l2"], *lyr["ln3"])
                 ref = ops.box_refine(self._mlp3(tgt, P["bbox"][i]), ref)
                 refs.append(ref)
                 if hs_all is not None:       # decoder.norm output of layer i lands in row block i of one (n_dec*B*Q, d) matrix

@@ -252,3 +252,21 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
         return gemm_ln(a, w, bias, residual, gamma, beta, add2)
     x = gemm(a, w, bias, residual=residual)
     return add_layernorm(x, None, gamma, beta, add2=add2)
+
+
+FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "1") != "0"
+
+
+def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5):
+    """y = LN(x + W2 relu(W1 x + b1) + b2): one tcgen05 kernel in bf16 mode when d_model = 256 and the hidden width is a multiple of
+    128 (<= 2048) -- the hidden activation never reaches HBM; otherwise linear1 + fused linear2/LayerNorm."""
+    import ctypes
+    M = x.shape[0]
+    hid = w1.shape[0]
+    if (FFN_FUSED and x.dtype == torch.bfloat16 and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
+            and x.stride(1) == 1 and x.stride(0) % 8 == 0):
+        y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
+        _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
+              ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _st(x))
+        return y
+    return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)

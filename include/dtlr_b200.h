@@ -96,6 +96,12 @@ int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias,
 int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
                  const float* gamma, const float* beta, float eps, void* Y, int ldy, const void* add2, void* Y2, int ld2,
                  int M, int K, void* stream);
+/* The whole position-wise FFN block of a transformer layer in ONE tcgen05 kernel (bf16, d_model 256, hidden <= 2048 and a
+ * multiple of 128):  Y = LN(X + W2 . relu(W1 . X + b1) + b2) * gamma + beta.  The hidden activation lives only in TMEM / shared
+ * memory.  Replaces forward_ffn + norm of models/dino/deformable_transformer.py:804-808,816-817 (encoder) and :876-880 (decoder).
+ * X [M,ldx], W1 [hidden,ldw1] (256 used), W2 [256,ldw2] (hidden used), Y [M,ldy]; b1 [hidden], b2/gamma/beta [256] fp32. */
+int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2, const float* b2,
+                const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden, void* stream);
 /* tuning aid only: sets kernel debug flags (0 = normal operation), returns the previous value */
 int dtlr_debug_flags(int flags);
 /* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */

@@ -130,3 +130,29 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
             assert torch.equal(o, old)
         else:   # the tile kernel rounds to bf16 before the residual add, this one adds in fp32 and rounds once
             assert (o.float() - old.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()
+
+
+@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048)])
+def test_fused_ffn_block(M, hid):
+    """dtlr_ffn_ln: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM / shared memory) vs
+    torch fp32 on the same bf16 operands with the hidden activation rounded to bf16 (as both our paths do), and vs the
+    un-fused kernels (linear1 GEMM + linear2/LayerNorm GEMM)."""
+    import torch.nn.functional as F
+    from dtlr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + hid)
+    x = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(hid, 256, device="cuda", generator=g) / 16).bfloat16()
+    b1 = 0.5 * torch.randn(hid, device="cuda", generator=g)
+    w2 = (torch.randn(256, hid, device="cuda", generator=g) / hid ** 0.5).bfloat16()
+    b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(256, device="cuda", generator=g)
+    y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+    h = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
+    pre = (h @ w2.float().T + b2 + x.float()).bfloat16().float()
+    ref = F.layer_norm(pre, (256,), gamma, beta, 1e-5)
+    assert torch.isfinite(y).all()
+    assert (y.float() - ref).abs().max().item() < 5e-2
+    assert (y.float() - ref).abs().mean().item() < 4e-3
+    un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
+    assert (y.float() - un.float()).abs().max().item() < 5e-2

@@ -56,3 +56,20 @@ for (M, N, K) in [(58368, 256, 256), (58368, 2048, 256), (57600, 512, 256), (163
             ("tile", 32), ("tile_no_store", 33), ("tile_no_mma", 34), ("tile_loads_only", 39)]}
     cu, gbs = copy_ref(M, N, K)
     print(M, N, K, res, "copy %dx%d bf16: %.1f us (%.0f GB/s)" % (M, K, cu, gbs), flush=True)
+
+
+def ffn_probe(M=58368, hid=2048, nbuf=4):
+    x = [torch.randn(M, 256, device="cuda").bfloat16() for _ in range(nbuf)]
+    w1 = (torch.randn(hid, 256, device="cuda") / 16).bfloat16()
+    w2 = (torch.randn(256, hid, device="cuda") / hid ** 0.5).bfloat16()
+    b1, b2 = torch.randn(hid, device="cuda"), torch.randn(256, device="cuda")
+    gm, bt = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    fused = timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10)
+    ops.FFN_FUSED = False
+    unf = timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10)
+    ops.FFN_FUSED = True
+    fl = 4.0 * M * 256 * hid
+    print("ffn M=%d hid=%d: fused %.1f us (%.0f TFLOP/s), linear1 + linear2/LN %.1f us" % (M, hid, fused, fl / fused / 1e6, unf), flush=True)
+
+
+ffn_probe()
