@@ -39,6 +39,7 @@ struct FfnArgs {
     const float* beta;    // [256]
     float eps;
     int M, HID;
+    int dbg;              // probes (dtlr_debug_flags): 256 no E1 work, 512 no G1 MMAs, 1024 no G2 MMAs, 2048 no final epilogue work
 };
 
 struct FfnSmem {
@@ -172,8 +173,10 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + kb * FF_STAGE));
                             const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < 4; ++k) {
+                                if (a.dbg & 512) break;
                                 umma_bf16(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                            }
                             umma_commit(&w_empty[s]);
                             if (kb == 3) umma_commit(&hacc_full[b]);
                         }
@@ -194,9 +197,11 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             const uint64_t da = make_sw128_kmajor_desc(smem_u32(hs + b * (2 * FF_STAGE) + kb2 * FF_STAGE));
                             const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < 4; ++k) {
+                                if (a.dbg & 1024) break;
                                 umma_bf16(tm_y + half * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
                                           (j > 1) || kb2 > 0 || k > 0);
+                            }
                             umma_commit(&w_empty[s]);
                             if (q == 3) {
                                 umma_commit(&hs_free[b]);
@@ -222,6 +227,14 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
                 mbar_wait(&hacc_full[b], u & 1);
                 tcgen05_fence_after();
+                if (a.dbg & 256) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hacc_free[b]);
+                    mbar_wait(&hs_free[b], (u & 1) ^ 1);
+                    if (lane == 0) mbar_arrive(&hs_full[b]);
+                    continue;
+                }
                 uint32_t acc[64];
                 tmem_ld64(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 64), acc);
                 tcgen05_fence_before();
@@ -250,6 +263,12 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             mbar_wait(x_full, t & 1);
             mbar_wait(y_full, t & 1);
             tcgen05_fence_after();
+            if (a.dbg & 2048) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(y_free); mbar_arrive(x_free); }
+                continue;
+            }
             float sum = 0.f, sq = 0.f;
 #pragma unroll 1
             for (int cb = 0; cb < 2; ++cb) {
@@ -355,7 +374,7 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
     const int grid = num_m < sm_count() ? num_m : sm_count();
-    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden};
+    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags};
     ffn_ln_tcgen05_kernel<<<grid, 320, FfnSmem::TOTAL, (cudaStream_t)stream>>>(tx, tw1, tw2, to, a);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

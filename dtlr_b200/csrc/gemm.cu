@@ -433,7 +433,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 //    stores) and one lane hands it to the TMA store engine (cp.async.bulk.tensor, bulk-group completion; rows / columns beyond
 //    M / N are clipped by the hardware).  A residual operand arrives the same way in the other direction: TMA-loaded one
 //    block ahead into the buffer the result will overwrite (two buffers per warp), read back swizzled by the row's thread.
-template <int BN, typename OutT, bool RES>
+template <int BN, typename OutT, bool RES, bool LN = false>
 struct WsSmem {
     static constexpr int KB_MAX = 4;
     static constexpr int W_KB_BYTES = BN * GEMM_BK * 2;                       // one 64-wide k-block of the slice
@@ -443,7 +443,7 @@ struct WsSmem {
     static constexpr int NBUF = RES ? 2 : 1;
     static constexpr int STG_WARP = NBUF * BLK_BYTES;
     static constexpr int STG_BYTES = 8 * STG_WARP;
-    static constexpr int BIAS_BYTES = BN * 4;
+    static constexpr int BIAS_BYTES = BN * 4 + (LN ? 2 * BN * 4 /*gamma, beta*/ + GEMM_BM * 4 * 4 /*row statistics*/ : 0);
     static constexpr int BAR_BYTES = 512;
     static constexpr int FIXED = W_BYTES + STG_BYTES + BIAS_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
     static constexpr int STAGES_FIT = (232448 - FIXED) / A_BYTES;
@@ -461,12 +461,13 @@ template <> struct TmemBlock<float, 32> {
     static __device__ __forceinline__ void load(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 };
 
-template <int BN, typename OutT, bool RES>
+template <int BN, typename OutT, bool RES, bool LN = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmEpi e,
                        const int ns, const int cps) {
-    using S = WsSmem<BN, OutT, RES>;
+    using S = WsSmem<BN, OutT, RES, LN>;
+    static_assert(!LN || (BN == 256 && sizeof(OutT) == 2 && !RES), "LayerNorm epilogue: one 256-wide bf16 slice, residual through the LSU");
     constexpr int STAGES = S::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -571,6 +572,117 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint64_t* rbar = res_bar + (warp - 2) * 2;
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t tcount = 0, bcount = 0;
+        if constexpr (LN) {
+            // ---- Linear -> (+residual) -> LayerNorm(256): this warp holds columns {hsel, hsel+2} x 64 of its 32 rows, the partner
+            //      warp of the lane quarter the other half; the bf16-rounded pre-norm row stays packed in registers between the
+            //      statistics pass and the normalisation pass.  The residual block is fetched coalesced (8 x 16 bytes per lane) and
+            //      turned to thread-per-row order through the warp's swizzled staging block.
+            float* gamma_s = bias_s + BN;
+            float* beta_s = gamma_s + BN;
+            float* stat_s = beta_s + BN;                                 // [128 rows][2 halves][2]
+            for (int j = threadIdx.x - 64; j < BN; j += 256) { gamma_s[j] = e.ln.gamma[j]; beta_s[j] = e.ln.beta[j]; }
+            asm volatile("bar.sync 5, 256;" ::: "memory");               // the 8 epilogue warps only
+            const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+            const int row = qd * 32 + lane;
+            unsigned char* srow = buf0 + lane * 128;
+            for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
+                const int m0 = mt * GEMM_BM;
+                const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+                uint4 rr[2][8];
+                auto load_res = [&](int blk) {
+                    const int cb = hsel + 2 * blk;
+#pragma unroll
+                    for (int itx = 0; itx < 8; ++itx) {
+                        const int r = itx * 4 + (lane >> 3), ch = lane & 7;
+                        const int grow = m0 + qd * 32 + r;
+                        rr[blk][itx] = make_uint4(0, 0, 0, 0);
+                        if (resp && grow < e.M) rr[blk][itx] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + cb * 64 + ch * 8));
+                    }
+                };
+                load_res(0);
+                mbar_wait(&tmem_full_bar[as], aph);
+                tcgen05_fence_after();
+                load_res(1);
+                uint32_t xp[64];                                         // the row's 128 pre-norm values of this warp, packed bf16x2
+                float sum = 0.f, sq = 0.f;
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int cb = hsel + 2 * blk;
+                    if (resp) {
+                        if (lane == 0) tma_store_wait_read<0>();         // the previous tile's store has finished reading the block
+                        __syncwarp();
+#pragma unroll
+                        for (int itx = 0; itx < 8; ++itx) {
+                            const int r = itx * 4 + (lane >> 3), ch = lane & 7;
+                            *reinterpret_cast<uint4*>(buf0 + r * 128 + ((ch ^ (r & 7)) * 16)) = rr[blk][itx];
+                        }
+                        __syncwarp();
+                    }
+                    uint32_t acc[64];
+                    tmem_ld64(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * 64), acc);
+                    if (blk == 1) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint4 r4 = make_uint4(0, 0, 0, 0);
+                        if (resp) r4 = *reinterpret_cast<const uint4*>(srow + ((k ^ swz) * 16));
+                        const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                        const float4 ba = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8);
+                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8 + 4);
+                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x0 = __uint_as_float(acc[k * 8 + 2 * i]) + bv[2 * i] + __uint_as_float(rw[i] << 16);
+                            const float x1 = __uint_as_float(acc[k * 8 + 2 * i + 1]) + bv[2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
+                            const uint32_t pk = pack_bf16x2(x0, x1);
+                            xp[blk * 32 + k * 4 + i] = pk;
+                            const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
+                            sum += y0 + y1;
+                            sq = fmaf(y0, y0, sq);
+                            sq = fmaf(y1, y1, sq);
+                        }
+                    }
+                    if (resp) __syncwarp();                              // the block is rewritten (next residual / output)
+                }
+                float* st = stat_s;
+                st[(row * 2 + hsel) * 2] = sum;
+                st[(row * 2 + hsel) * 2 + 1] = sq;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+                const float mean = (st[row * 4] + st[row * 4 + 2]) * (1.f / 256.f);
+                const float var = fmaxf((st[row * 4 + 1] + st[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + e.ln.eps);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // statistics consumed before the next tile overwrites them
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int cb = hsel + 2 * blk;
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t pk = xp[blk * 32 + k * 4 + i];
+                            const int c = cb * 64 + k * 8 + 2 * i;
+                            const float y0 = (__uint_as_float(pk << 16) - mean) * rstd * gamma_s[c] + beta_s[c];
+                            const float y1 = (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1];
+                            o[i] = pack_bf16x2(y0, y1);
+                        }
+                        *reinterpret_cast<uint4*>(srow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, buf0, n0 + cb * 64, m0 + qd * 32);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (lane == 0) tma_store_wait<0>();
+        } else {
         if (RES && hsel < NCB && r0 < num_m && lane == 0) {              // residual of this warp's first block
             mbar_expect_tx(&rbar[0], S::BLK_BYTES);
             tma_load_2d(buf0, &tmR, &rbar[0], n0 + hsel * CB, r0 * GEMM_BM + qd * 32);
@@ -655,6 +767,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
         if (lane == 0) tma_store_wait<0>();                              // the buffers must outlive the last store
+        }   // !LN
     }
     __syncthreads();
     if (warp == 1) {
@@ -788,9 +901,9 @@ static int make_tmap_out(CUtensorMap* map, const void* base, int rows, int cols,
     return DTLR_OK;
 }
 
-template <int BN, typename OutT, bool RES>
+template <int BN, typename OutT, bool RES, bool LN = false>
 static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st) {
-    using S = WsSmem<BN, OutT, RES>;
+    using S = WsSmem<BN, OutT, RES, LN>;
     CUtensorMap ta, tb, tc, tr;
     int rc;
     if ((rc = make_tmap_bf16(&ta, A, e.M, e.K, lda, GEMM_BM))) return rc;
@@ -798,7 +911,7 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
     if ((rc = make_tmap_out<OutT>(&tc, e.C, e.M, e.N, e.ldc))) return rc;
     tr = tc;
     if (RES && (rc = make_tmap_out<OutT>(&tr, e.residual, e.M, e.N, e.ldr))) return rc;
-    auto k = gemm_ws_tcgen05_kernel<BN, OutT, RES>;
+    auto k = gemm_ws_tcgen05_kernel<BN, OutT, RES, LN>;
     static bool configured = false;
     if (!configured) {
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -922,6 +1035,9 @@ extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, cons
                    ((((uintptr_t)A | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)residual | (uintptr_t)add2 | (uintptr_t)Y2)) & 15) == 0,
                    "gemm_ln: operands need 16-byte aligned rows");
     GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
+    // K <= 256: weight-stationary kernel with the LayerNorm in its TMA-store epilogue (no second output there)
+    if (K <= 256 && !Y2 && (long long)((M + GEMM_BM - 1) / GEMM_BM) >= 2ll * sm_count() && !(g_debug_flags & 32))
+        return launch_ws<256, __nv_bfloat16, false, true>(A, lda, W, ldw, e, (cudaStream_t)stream);
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;

@@ -523,6 +523,55 @@ using namespace dtlr;
     else if ((dtype) == DTLR_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
     else { set_error("unsupported dtype %d", (int)(dtype)); return DTLR_ERR_INVALID; }
 
+// Stem patches for the tensor-core path: fp32 NCHW network input (C = 3) -> bf16 rows [B*Ho*Wo, ldo] in (kh, kw, c) order for a
+// 7x7 / stride 2 / pad 3 convolution.  One CTA = 128 consecutive output pixels of one output row: the 7 x 3 input row segments
+// it touches (261 columns) are staged once in shared memory as bf16 (coalesced reads), then every thread emits 16-byte chunks
+// of 8 consecutive k, consecutive threads = consecutive chunks of a row (fully coalesced 304-byte rows).  HBM-bound by its
+// output (B*Ho*Wo*ldo*2 bytes); the generic per-element kernel below runs 20x slower on this shape.
+constexpr int SIC_SEG = 128;                     // output pixels per CTA
+constexpr int SIC_COLS = 2 * SIC_SEG + 5;        // input columns touched
+constexpr int SIC_ROW = SIC_COLS * 3 + 1;        // bf16 elements per staged input row (column-major pixels, channel fastest)
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const int H, const int W, const int Ho,
+                   const int Wo, const int ldo) {
+    // tile[kh][col * 3 + c]: for a fixed kh the 21 values (kw, c) of output pixel p are the 21 CONSECUTIVE elements from 6 * p
+    __shared__ __nv_bfloat16 tile[7 * SIC_ROW];
+    const int ox0 = blockIdx.x * SIC_SEG, oy = blockIdx.y, b = blockIdx.z;
+    const int ix0 = 2 * ox0 - 3;
+    for (int i = threadIdx.x; i < 21 * SIC_COLS; i += 256) {
+        const int rowi = i / SIC_COLS, col = i - rowi * SIC_COLS;      // rowi = kh * 3 + c (coalesced along col)
+        const int kh = rowi / 3, c = rowi - kh * 3;
+        const int iy = 2 * oy + kh - 3, ix = ix0 + col;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + iy) * W + ix);
+        tile[kh * SIC_ROW + col * 3 + c] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    const int nchunk = ldo / 8;                                        // 16-byte chunks per output row
+    const int npx = min(SIC_SEG, Wo - ox0);
+    const size_t row0 = ((size_t)b * Ho + oy) * Wo + ox0;
+    const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+    for (int idx = threadIdx.x; idx < npx * nchunk; idx += 256) {
+        const int p = idx / nchunk, j = idx - p * nchunk;
+        int k = 8 * j;
+        int kh = k / 21, r = k - kh * 21;                              // walk (kh, r) incrementally over the chunk's 8 elements
+        int a = kh * SIC_ROW + 6 * p + r;
+        uint32_t w4[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            uint32_t h[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                h[q] = (k < 147) ? (uint32_t)t16[a] : 0u;
+                ++k; ++r; ++a;
+                if (r == 21) { r = 0; a += SIC_ROW - 21; }
+            }
+            w4[e2] = h[0] | (h[1] << 16);
+        }
+        *reinterpret_cast<uint4*>(out + (row0 + p) * ldo + 8 * j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+}
+
 extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
                            int Ho, int Wo, int ldo, int in_dtype, int out_dtype, int nchw_input, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -532,6 +581,10 @@ extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C,
     if (!nchw_input && in_dtype == out_dtype && C % 8 == 0 && ldo == KH * KW * C) {
         const long long t8 = total / 8;
         DISPATCH_T(in_dtype, im2col_vec8_kernel<T><<<grid_for(t8, 256), 256, 0, st>>>((const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo);)
+    } else if (nchw_input && in_dtype == DTLR_F32 && out_dtype == DTLR_BF16 && C == 3 && KH == 7 && KW == 7 && stride == 2 && pad == 3 &&
+               (ldo % 8) == 0 && (((uintptr_t)out) & 15) == 0 && B <= 65535 && Ho <= 65535) {
+        dim3 grid((Wo + SIC_SEG - 1) / SIC_SEG, Ho, B);
+        stem_im2col_kernel<<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, H, W, Ho, Wo, ldo);
     } else if (nchw_input && in_dtype == DTLR_F32) {
         DISPATCH_T(out_dtype, im2col_kernel<float, T, true><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
     } else if (!nchw_input && in_dtype == out_dtype) {

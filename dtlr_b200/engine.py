@@ -59,6 +59,8 @@ class InferenceEngine:
         sc, sb = body.bn1.scale_bias()
         P["stem_direct"] = ((body.conv1.weight.detach().float() * sc.float().view(-1, 1, 1, 1)).permute(2, 3, 1, 0).contiguous(),
                             sb.detach().float().contiguous())          # [kh][kw][cin][cout] fp32, bias
+        # bf16 throughput mode: the stem runs on the tensor cores as patches (shared-memory staged im2col) x [64, 152] GEMM
+        P["stem_gemm"] = _fold_conv_bn(body.conv1, body.bn1, dtype) if dtype == torch.bfloat16 else None
         blocks = []
         for li in range(1, 5):
             for blk in getattr(body, "layer%d" % li):
@@ -123,7 +125,11 @@ class InferenceEngine:
         return ops.gemm(h, *layers[2], out_dtype=torch.float32 if out_f32_last else None)
 
     def _backbone(self, P, x, B, H, W, T):
-        y, Ho, Wo = ops.stem_conv(x, *P["stem_direct"], B, H, W, T)
+        if P["stem_gemm"] is not None and ops.STEM_TENSOR_CORE:
+            col, Ho, Wo = ops.im2col(x, B, H, W, 3, 7, 7, 2, 3, T, nchw_input=True, ldo=P["stem_gemm"][0].shape[1])
+            y = ops.gemm(col, *P["stem_gemm"], relu=1)
+        else:
+            y, Ho, Wo = ops.stem_conv(x, *P["stem_direct"], B, H, W, T)
         y, Hc, Wc = ops.maxpool3x3s2(y, B, Ho, Wo, 64)
         feats = []
         cin = 64

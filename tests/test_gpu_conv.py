@@ -82,3 +82,24 @@ def test_groupnorm_into_token_buffer():
     got = buf.view(B, S, C)[:, off:off + HW]
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
     assert buf.view(B, S, C)[:, :off].abs().sum() == 0 and buf.view(B, S, C)[:, off + HW:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 40, 1024), (3, 37, 133), (64, 40, 1024)])
+def test_stem_as_staged_im2col_plus_tensor_core_gemm(B, H, W):
+    """bf16 throughput mode stem: stem_im2col_kernel (fp32 NCHW -> bf16 (kh,kw,c) patches, K padded 147 -> 152) + dtlr_gemm
+    vs torch conv2d on the same bf16-rounded operands, including ragged widths (133) and odd heights."""
+    from dtlr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + H + W)
+    x = torch.randn(B, 3, H, W, device="cuda", generator=g)
+    w = torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 147 ** 0.5
+    bias = torch.randn(64, device="cuda", generator=g)
+    wk = F.pad(w.permute(0, 2, 3, 1).reshape(64, 147), (0, 5)).bfloat16().contiguous()
+    col, Ho, Wo = ops.im2col(x, B, H, W, 3, 7, 7, 2, 3, torch.bfloat16, nchw_input=True, ldo=152)
+    # the patch matrix itself is exact (bf16 rounding of the input only): compare with unfold
+    ref_col = F.unfold(x.bfloat16().float(), 7, padding=3, stride=2).view(B, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 147)
+    assert torch.equal(col[:, :147].float(), ref_col) and col[:, 147:].abs().sum() == 0
+    y = ops.gemm(col, wk, bias, relu=1)
+    ref = F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), bias, stride=2, padding=3))
+    assert (Ho, Wo) == tuple(ref.shape[-2:])
+    err = (y.float().view(B, Ho, Wo, 64).permute(0, 3, 1, 2) - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err

@@ -147,7 +147,11 @@ def test_fused_ffn_block(M, hid):
     b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
     gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
     beta = 0.1 * torch.randn(256, device="cuda", generator=g)
-    y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+    ops.FFN_FUSED = True
+    try:
+        y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+    finally:
+        ops.FFN_FUSED = False
     h = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
     pre = (h @ w2.float().T + b2 + x.float()).bfloat16().float()
     ref = F.layer_norm(pre, (256,), gamma, beta, 1e-5)

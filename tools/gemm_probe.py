@@ -5,30 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dtlr_b200 import ops, _lib
 
 
-def timeit(fn, iters=20):
-    """GPU time per call of `iters` back-to-back launches replayed from a CUDA graph (no host launch gaps)."""
-    for i in range(4):
-        fn(i)
-    torch.cuda.synchronize()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for i in range(2):
-            fn(i)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for i in range(iters):
-            fn(i)
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1000 / iters
+from gemm_probe_util import timeit  # noqa: E402
 
 
 def t(M, N, K, flags, nbuf=6):
@@ -50,7 +27,8 @@ def copy_ref(M, N, K, nbuf=6):
     return us, 2 * M * K * 2 / us / 1e3
 
 
-for (M, N, K) in [(58368, 256, 256), (58368, 2048, 256), (57600, 512, 256), (163840, 256, 64), (58368, 256, 2048)]:
+import sys as _s
+for (M, N, K) in [] if (len(_s.argv) > 1 and _s.argv[1] == 'ffn') else [(58368, 256, 256), (58368, 2048, 256), (57600, 512, 256), (163840, 256, 64), (58368, 256, 2048)]:
     res = {name: round(t(M, N, K, f), 1) for name, f in
            [("ws", 0), ("ws_no_store", 1), ("ws_no_mma", 2), ("ws_no_epilogue", 4), ("ws_loads_only", 6),
             ("tile", 32), ("tile_no_store", 33), ("tile_no_mma", 34), ("tile_loads_only", 39)]}
@@ -64,12 +42,36 @@ def ffn_probe(M=58368, hid=2048, nbuf=4):
     w2 = (torch.randn(256, hid, device="cuda") / hid ** 0.5).bfloat16()
     b1, b2 = torch.randn(hid, device="cuda"), torch.randn(256, device="cuda")
     gm, bt = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    ops.FFN_FUSED = True
     fused = timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10)
+    probes = {}
+    for name, f in [("no_E1", 256), ("no_G1", 512), ("no_G2", 1024), ("no_final", 2048), ("no_mma", 1536), ("no_mma_no_E1", 1792), ("loads_only", 3840)]:
+        _lib.lib().dtlr_debug_flags(f)
+        probes[name] = round(timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10), 1)
+    _lib.lib().dtlr_debug_flags(0)
+    print("ffn probes", probes, flush=True)
     ops.FFN_FUSED = False
     unf = timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10)
-    ops.FFN_FUSED = True
     fl = 4.0 * M * 256 * hid
     print("ffn M=%d hid=%d: fused %.1f us (%.0f TFLOP/s), linear1 + linear2/LN %.1f us" % (M, hid, fused, fl / fused / 1e6, unf), flush=True)
 
 
 ffn_probe()
+
+
+def ln_probe(M=58368, nbuf=6):
+    a = [torch.randn(M, 256, device="cuda").bfloat16() for _ in range(nbuf)]
+    r = [torch.randn(M, 256, device="cuda").bfloat16() for _ in range(nbuf)]
+    w = (torch.randn(256, 256, device="cuda") / 16).bfloat16()
+    b = torch.randn(256, device="cuda")
+    gm, bt = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    ops.LN_FUSE_WS = True
+    fused = timeit(lambda i: ops.linear_ln(a[i % nbuf], w, b, r[i % nbuf], gm, bt))
+    fused_nores = timeit(lambda i: ops.linear_ln(a[i % nbuf], w, b, None, gm, bt))
+    ops.LN_FUSE_WS = False
+    unf = timeit(lambda i: ops.linear_ln(a[i % nbuf], w, b, r[i % nbuf], gm, bt))
+    ops.LN_FUSE_WS = True
+    print("linear(256->256)+res+LN M=%d: fused %.1f us (no residual %.1f), gemm + add_layernorm %.1f us" % (M, fused, fused_nores, unf), flush=True)
+
+
+ln_probe()
