@@ -87,6 +87,147 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + LN_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void ln_load_blk(uint4 (&dst)[8], const __nv_bfloat16* src, const int ld, const int cb, const int m0,
+                                            const int qd, const int lane, const int M) {
+#pragma unroll
+    for (int itx = 0; itx < 8; ++itx) {
+        const int r = itx * 4 + (lane >> 3), ch = lane & 7;
+        const int grow = m0 + qd * 32 + r;
+        dst[itx] = make_uint4(0, 0, 0, 0);
+        if (src && grow < M) dst[itx] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)grow * ld + cb * 64 + ch * 8));
+    }
+}
+// coalesced registers -> swizzled rows of the warp's staging block (after every earlier TMA store has finished reading it)
+__device__ __forceinline__ void ln_stage_blk(const uint4 (&src)[8], unsigned char* buf0, const int lane) {
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int itx = 0; itx < 8; ++itx) {
+        const int r = itx * 4 + (lane >> 3), ch = lane & 7;
+        *reinterpret_cast<uint4*>(buf0 + r * 128 + ((ch ^ (r & 7)) * 16)) = src[itx];
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t ln_norm_pair(const uint32_t pk, const float mean, const float rstd, const float* g, const float* b) {
+    const float y0 = (__uint_as_float(pk << 16) - mean) * rstd * g[0] + b[0];
+    const float y1 = (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * g[1] + b[1];
+    return pack_bf16x2(y0, y1);
+}
+
+// Linear -> (+residual) -> LayerNorm(256) [-> second output y + add2] epilogue of one 128 x 256 accumulator tile, shared by the
+// weight-stationary kernel (K <= 256) and the tile kernel (any K).  8 epilogue warps; warp (qd, hsel) holds the column blocks
+// {hsel, hsel + 2} x 64 of its 32 rows (thread = row), the partner warp of the lane quarter the other half; the bf16-rounded
+// pre-norm row stays packed in registers between the statistics pass and the normalisation pass.  Residual / add2 blocks are
+// fetched coalesced (8 x 16 bytes per lane) and turned to thread-per-row order through the warp's 4 KB 128B-swizzled staging block,
+// which then carries the outputs to the TMA store engine (tmC: y, tmC2: y + add2).
+__device__ __forceinline__ void ln_epilogue_tile(const GemmEpi& e, const CUtensorMap* tmC, const CUtensorMap* tmC2, const int m0,
+                                                 const uint32_t tmem_acc, uint64_t* full_bar, const uint32_t full_phase, uint64_t* empty_bar,
+                                                 unsigned char* buf0, const float* bias_s, const float* gamma_s, const float* beta_s,
+                                                 float* stat_s, const int qd, const int hsel, const int lane) {
+    const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+    const __nv_bfloat16* add2 = reinterpret_cast<const __nv_bfloat16*>(e.ln.add2);
+    const int row = qd * 32 + lane;
+    const uint32_t swz = (uint32_t)(lane & 7);
+    unsigned char* srow = buf0 + lane * 128;
+    uint4 rr[8];                                                      // one coalesced block in flight (residual, then add2)
+    ln_load_blk(rr, resp, e.ldr, hsel, m0, qd, lane, e.M);
+    mbar_wait(full_bar, full_phase);
+    tcgen05_fence_after();
+    uint32_t xp[64];                                                  // the row's 128 pre-norm values of this warp, packed bf16x2
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        const int cb = hsel + 2 * blk;
+        if (resp) {
+            ln_stage_blk(rr, buf0, lane);
+            if (blk == 0) ln_load_blk(rr, resp, e.ldr, hsel + 2, m0, qd, lane, e.M);        // next block's residual in flight behind this block's math
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                              // 32 accumulator columns at a time (register budget)
+            uint32_t acc[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * 64 + hf * 32), acc);
+            if (blk == 1 && hf == 1) {                                // last TMEM read of this accumulator by this warp
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = hf * 4 + kk;
+                uint4 r4 = make_uint4(0, 0, 0, 0);
+                if (resp) r4 = *reinterpret_cast<const uint4*>(srow + ((k ^ swz) * 16));
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                const float4 ba = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8);
+                const float4 bb = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8 + 4);
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bv[2 * i] + __uint_as_float(rw[i] << 16);
+                    const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bv[2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
+                    const uint32_t pk = pack_bf16x2(x0, x1);
+                    xp[blk * 32 + k * 4 + i] = pk;
+                    const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
+                    sum += y0 + y1;
+                    sq = fmaf(y0, y0, sq);
+                    sq = fmaf(y1, y1, sq);
+                }
+            }
+        }
+        if (resp) __syncwarp();                                       // the block is rewritten next
+    }
+    if (add2) ln_load_blk(rr, add2, e.ln.ld2, hsel, m0, qd, lane, e.M);                     // in flight across the statistics exchange
+    stat_s[(row * 2 + hsel) * 2] = sum;
+    stat_s[(row * 2 + hsel) * 2 + 1] = sq;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // the two warps of this lane quarter
+    const float mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
+    const float var = fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + e.ln.eps);
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // statistics consumed before the next tile overwrites them
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        const int cb = hsel + 2 * blk;
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = ln_norm_pair(xp[blk * 32 + k * 4 + i], mean, rstd, gamma_s + cb * 64 + k * 8 + 2 * i, beta_s + cb * 64 + k * 8 + 2 * i);
+            *reinterpret_cast<uint4*>(srow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmC, buf0, cb * 64, m0 + qd * 32);
+            tma_store_commit();
+        }
+        if (add2) {                                                   // second output: the ROUNDED y plus add2, as un-fused
+            ln_stage_blk(rr, buf0, lane);                                            // (waits for the y store to finish reading the block)
+            if (blk == 0) ln_load_blk(rr, add2, e.ln.ld2, hsel + 2, m0, qd, lane, e.M);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint4* p = reinterpret_cast<uint4*>(srow + ((k ^ swz) * 16));
+                const uint4 t4 = *p;
+                const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+                uint32_t z[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t y = ln_norm_pair(xp[blk * 32 + k * 4 + i], mean, rstd, gamma_s + cb * 64 + k * 8 + 2 * i, beta_s + cb * 64 + k * 8 + 2 * i);
+                    z[i] = pack_bf16x2(__uint_as_float(y << 16) + __uint_as_float(tw[i] << 16),
+                                       __uint_as_float(y & 0xffff0000u) + __uint_as_float(tw[i] & 0xffff0000u));
+                }
+                *p = make_uint4(z[0], z[1], z[2], z[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tmC2, buf0, cb * 64, m0 + qd * 32);
+                tma_store_commit();
+            }
+        }
+    }
+}
+
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue
 // (two warps per TMEM lane quarter, each draining half of the tile's columns).
 // Two TMEM accumulators: the MMA warp fills one while the epilogue drains the other.  Epilogue: TMEM -> registers
@@ -94,7 +235,7 @@ struct GemmSmem {
 template <int BN, int STAGES, typename OutT>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmEpi e) {
+                         const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmEpi e) {
     using S = GemmSmem<BN, STAGES, OutT>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared between TMA and the UMMA descriptors
@@ -209,13 +350,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool vec_ok = ((e.ldc * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.C & 15) == 0) &&
                             (!e.residual || (((e.ldr * (int)sizeof(OutT)) % 16 == 0) && (((uintptr_t)e.residual & 15) == 0)));
         bool do_ln = false;
+        if constexpr (S::LN_BYTES > 0) do_ln = e.ln.gamma != nullptr;
         if constexpr (S::LN_BYTES > 0) {
-            do_ln = e.ln.gamma != nullptr;
             if (do_ln) {
-                for (int j = threadIdx.x - 64; j < BN; j += 256) { ln_gb_s[j] = e.ln.gamma[j]; ln_gb_s[BN + j] = e.ln.beta[j]; }
+                // full-row (N == BN == 256) LayerNorm epilogue: thread = row, TMA stores (ln_epilogue_tile)
+                for (int j = threadIdx.x - 64; j < BN; j += 256) {
+                    ln_gb_s[j] = e.ln.gamma[j];
+                    ln_gb_s[BN + j] = e.ln.beta[j];
+                    bias_s[j] = e.bias ? __ldg(e.bias + j) : 0.f;
+                }
                 asm volatile("bar.sync 5, 256;" ::: "memory");          // the 8 epilogue warps only
+                unsigned char* buf0 = staging + (warp - 2) * 4096;
+                uint32_t tc = 0;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tc) {
+                    const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                    ln_epilogue_tile(e, &tmC, &tmC2, (tile % num_m) * GEMM_BM, tmem_base + as * BN, &tmem_full_bar[as], aph,
+                                     &tmem_empty_bar[as], buf0, bias_s, ln_gb_s, ln_gb_s + BN, ln_stat_s, qd, half, lane);
+                }
+                if (lane == 0) tma_store_wait<0>();
             }
         }
+        if (!do_ln) {
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
@@ -272,84 +427,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
             // ---- step 2: staging -> global, coalesced (each warp stores its own 32 rows), + residual, + late ReLU
             const int ncols = (e.dbg & 1) ? 0 : min(BN, e.N - n0);
-            if constexpr (S::LN_BYTES > 0) {
-                if (do_ln) {
-                    // ---- fused residual + LayerNorm over the full 256-wide row (this warp holds 128 columns of 32 rows;
-                    //      the partner warp (same lane quarter, other half) holds the rest; stats meet in shared memory)
-                    constexpr int CW = CHUNKS / 2, NIT = CW, GRP = 8;      // 16 chunks per row half, 2 rows per iteration
-                    float* stat = ln_stat_s + (tcount & 1) * (GEMM_BM * 4);
-                    const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
-#pragma unroll 1
-                    for (int g0 = 0; g0 < NIT; g0 += GRP) {
-                        uint4 rres[GRP];
-#pragma unroll
-                        for (int it = 0; it < GRP; ++it) {
-                            const int idx = (g0 + it) * 32 + lane;
-                            const int r = idx / CW, ch = half * CW + idx % CW;
-                            const int grow = m0 + qd * 32 + r;
-                            rres[it] = make_uint4(0, 0, 0, 0);
-                            if (resp && grow < e.M) rres[it] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + ch * 8));
-                        }
-#pragma unroll
-                        for (int it = 0; it < GRP; ++it) {
-                            const int idx = (g0 + it) * 32 + lane;
-                            const int r = idx / CW, ch = half * CW + idx % CW;
-                            uint4* sp = reinterpret_cast<uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16));
-                            float f[8], gres[8];
-                            unpack_chunk<__nv_bfloat16>(*sp, f);
-                            unpack_chunk<__nv_bfloat16>(rres[it], gres);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) f[k] += gres[k];
-                            const uint4 rounded = pack_chunk<__nv_bfloat16>(f);       // LN input is the bf16-rounded sum, as un-fused
-                            *sp = rounded;
-                            unpack_chunk<__nv_bfloat16>(rounded, f);
-                            float sm = 0.f, sq = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) { sm += f[k]; sq = fmaf(f[k], f[k], sq); }
-#pragma unroll
-                            for (int o = 8; o > 0; o >>= 1) {
-                                sm += __shfl_xor_sync(0xffffffffu, sm, o);
-                                sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                            }
-                            if ((lane & 15) == 0) {
-                                stat[(qd * 32 + r) * 4 + half * 2] = sm;
-                                stat[(qd * 32 + r) * 4 + half * 2 + 1] = sq;
-                            }
-                        }
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");     // partner warps (w, w+4) of this lane quarter
-                    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(e.C);
-                    const __nv_bfloat16* add2 = reinterpret_cast<const __nv_bfloat16*>(e.ln.add2);
-                    __nv_bfloat16* out2 = reinterpret_cast<__nv_bfloat16*>(e.ln.out2);
-#pragma unroll 2
-                    for (int it = 0; it < NIT; ++it) {
-                        const int idx = it * 32 + lane;
-                        const int r = idx / CW, ch = half * CW + idx % CW;
-                        const int grow = m0 + qd * 32 + r;
-                        if (grow >= e.M || ncols == 0) continue;
-                        const float* st4 = stat + (qd * 32 + r) * 4;
-                        const float mean = (st4[0] + st4[2]) * (1.f / 256.f);
-                        const float var = fmaxf((st4[1] + st4[3]) * (1.f / 256.f) - mean * mean, 0.f);
-                        const float rstd = rsqrtf(var + e.ln.eps);
-                        float f[8];
-                        unpack_chunk<__nv_bfloat16>(*reinterpret_cast<const uint4*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16)), f);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean) * rstd * ln_gb_s[ch * 8 + k] + ln_gb_s[BN + ch * 8 + k];
-                        const uint4 y = pack_chunk<__nv_bfloat16>(f);
-                        *reinterpret_cast<uint4*>(outp + (size_t)grow * e.ldc + ch * 8) = y;
-                        if (out2) {
-                            float a2[8];
-                            unpack_chunk<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(add2 + (size_t)grow * e.ln.ld2 + ch * 8)), a2);
-                            unpack_chunk<__nv_bfloat16>(y, f);             // second output adds to the ROUNDED y, as un-fused
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) a2[k] += f[k];
-                            *reinterpret_cast<uint4*>(out2 + (size_t)grow * e.ln.ld2 + ch * 8) = pack_chunk<__nv_bfloat16>(a2);
-                        }
-                    }
-                    __syncwarp();
-                    continue;
-                }
-            }
             if (vec_ok && (ncols % EPC) == 0) {
                 const int nchunks = ncols / EPC;
                 constexpr int CW = CHUNKS / 2;                           // chunks per row owned by this warp
@@ -411,6 +488,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             __syncwarp();          // staging rows are rewritten by the next tile
         }
+        }   // !do_ln
     }
     __syncthreads();
     if (warp == 1) {
@@ -573,113 +651,15 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t swz = (uint32_t)(lane & 7);
         uint32_t tcount = 0, bcount = 0;
         if constexpr (LN) {
-            // ---- Linear -> (+residual) -> LayerNorm(256): this warp holds columns {hsel, hsel+2} x 64 of its 32 rows, the partner
-            //      warp of the lane quarter the other half; the bf16-rounded pre-norm row stays packed in registers between the
-            //      statistics pass and the normalisation pass.  The residual block is fetched coalesced (8 x 16 bytes per lane) and
-            //      turned to thread-per-row order through the warp's swizzled staging block.
             float* gamma_s = bias_s + BN;
             float* beta_s = gamma_s + BN;
             float* stat_s = beta_s + BN;                                 // [128 rows][2 halves][2]
             for (int j = threadIdx.x - 64; j < BN; j += 256) { gamma_s[j] = e.ln.gamma[j]; beta_s[j] = e.ln.beta[j]; }
             asm volatile("bar.sync 5, 256;" ::: "memory");               // the 8 epilogue warps only
-            const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
-            const int row = qd * 32 + lane;
-            unsigned char* srow = buf0 + lane * 128;
             for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
-                const int m0 = mt * GEMM_BM;
                 const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-                uint4 rr[2][8];
-                auto load_res = [&](int blk) {
-                    const int cb = hsel + 2 * blk;
-#pragma unroll
-                    for (int itx = 0; itx < 8; ++itx) {
-                        const int r = itx * 4 + (lane >> 3), ch = lane & 7;
-                        const int grow = m0 + qd * 32 + r;
-                        rr[blk][itx] = make_uint4(0, 0, 0, 0);
-                        if (resp && grow < e.M) rr[blk][itx] = __ldg(reinterpret_cast<const uint4*>(resp + (size_t)grow * e.ldr + cb * 64 + ch * 8));
-                    }
-                };
-                load_res(0);
-                mbar_wait(&tmem_full_bar[as], aph);
-                tcgen05_fence_after();
-                load_res(1);
-                uint32_t xp[64];                                         // the row's 128 pre-norm values of this warp, packed bf16x2
-                float sum = 0.f, sq = 0.f;
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    const int cb = hsel + 2 * blk;
-                    if (resp) {
-                        if (lane == 0) tma_store_wait_read<0>();         // the previous tile's store has finished reading the block
-                        __syncwarp();
-#pragma unroll
-                        for (int itx = 0; itx < 8; ++itx) {
-                            const int r = itx * 4 + (lane >> 3), ch = lane & 7;
-                            *reinterpret_cast<uint4*>(buf0 + r * 128 + ((ch ^ (r & 7)) * 16)) = rr[blk][itx];
-                        }
-                        __syncwarp();
-                    }
-                    uint32_t acc[64];
-                    tmem_ld64(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * 64), acc);
-                    if (blk == 1) {
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        uint4 r4 = make_uint4(0, 0, 0, 0);
-                        if (resp) r4 = *reinterpret_cast<const uint4*>(srow + ((k ^ swz) * 16));
-                        const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-                        const float4 ba = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8);
-                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + cb * 64 + k * 8 + 4);
-                        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float x0 = __uint_as_float(acc[k * 8 + 2 * i]) + bv[2 * i] + __uint_as_float(rw[i] << 16);
-                            const float x1 = __uint_as_float(acc[k * 8 + 2 * i + 1]) + bv[2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
-                            const uint32_t pk = pack_bf16x2(x0, x1);
-                            xp[blk * 32 + k * 4 + i] = pk;
-                            const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
-                            sum += y0 + y1;
-                            sq = fmaf(y0, y0, sq);
-                            sq = fmaf(y1, y1, sq);
-                        }
-                    }
-                    if (resp) __syncwarp();                              // the block is rewritten (next residual / output)
-                }
-                float* st = stat_s;
-                st[(row * 2 + hsel) * 2] = sum;
-                st[(row * 2 + hsel) * 2 + 1] = sq;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-                const float mean = (st[row * 4] + st[row * 4 + 2]) * (1.f / 256.f);
-                const float var = fmaxf((st[row * 4 + 1] + st[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + e.ln.eps);
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // statistics consumed before the next tile overwrites them
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                    const int cb = hsel + 2 * blk;
-                    if (lane == 0) tma_store_wait_read<0>();
-                    __syncwarp();
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        uint32_t o[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t pk = xp[blk * 32 + k * 4 + i];
-                            const int c = cb * 64 + k * 8 + 2 * i;
-                            const float y0 = (__uint_as_float(pk << 16) - mean) * rstd * gamma_s[c] + beta_s[c];
-                            const float y1 = (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1];
-                            o[i] = pack_bf16x2(y0, y1);
-                        }
-                        *reinterpret_cast<uint4*>(srow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, buf0, n0 + cb * 64, m0 + qd * 32);
-                        tma_store_commit();
-                    }
-                }
+                ln_epilogue_tile(e, &tmC, &tmR, mt * GEMM_BM, tmem_base + as * BN, &tmem_full_bar[as], aph, &tmem_empty_bar[as], buf0,
+                                 bias_s, gamma_s, beta_s, stat_s, qd, hsel, lane);
             }
             if (lane == 0) tma_store_wait<0>();
         } else {
@@ -911,6 +891,7 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
     if ((rc = make_tmap_out<OutT>(&tc, e.C, e.M, e.N, e.ldc))) return rc;
     tr = tc;
     if (RES && (rc = make_tmap_out<OutT>(&tr, e.residual, e.M, e.N, e.ldr))) return rc;
+    if (LN && e.ln.out2 && (rc = make_tmap_out<OutT>(&tr, e.ln.out2, e.M, e.N, e.ln.ld2))) return rc;   // LayerNorm variant: tmR carries y + add2
     auto k = gemm_ws_tcgen05_kernel<BN, OutT, RES, LN>;
     static bool configured = false;
     if (!configured) {
@@ -960,7 +941,8 @@ static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi
 }
 
 template <int BN, int STAGES, typename OutT>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& e, cudaStream_t st, const CUtensorMap* tc = nullptr,
+                     const CUtensorMap* tc2 = nullptr) {
     using S = GemmSmem<BN, STAGES, OutT>;
     auto k = gemm_bf16_tcgen05_kernel<BN, STAGES, OutT>;
     static bool configured = false;     // per template instantiation
@@ -970,7 +952,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     const int tiles = ((e.M + GEMM_BM - 1) / GEMM_BM) * ((e.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    k<<<grid, 320, S::TOTAL, st>>>(ta, tb, e);
+    k<<<grid, 320, S::TOTAL, st>>>(ta, tb, tc ? *tc : ta, tc2 ? *tc2 : ta, e);      // output maps only used by the LayerNorm epilogue
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -1035,14 +1017,17 @@ extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, cons
                    ((((uintptr_t)A | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)residual | (uintptr_t)add2 | (uintptr_t)Y2)) & 15) == 0,
                    "gemm_ln: operands need 16-byte aligned rows");
     GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
-    // K <= 256: weight-stationary kernel with the LayerNorm in its TMA-store epilogue (no second output there)
-    if (K <= 256 && !Y2 && (long long)((M + GEMM_BM - 1) / GEMM_BM) >= 2ll * sm_count() && !(g_debug_flags & 32))
+    // K <= 256: weight-stationary kernel; otherwise the tile kernel -- both end in ln_epilogue_tile (TMA stores)
+    if (K <= 256 && (long long)((M + GEMM_BM - 1) / GEMM_BM) >= 2ll * sm_count() && !(g_debug_flags & 32))
         return launch_ws<256, __nv_bfloat16, false, true>(A, lda, W, ldw, e, (cudaStream_t)stream);
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tc, tc2;
     int rc;
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 256))) return rc;
-    return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, (cudaStream_t)stream);
+    if ((rc = make_tmap_out<__nv_bfloat16>(&tc, Y, M, N, ldy))) return rc;
+    tc2 = tc;
+    if (Y2 && (rc = make_tmap_out<__nv_bfloat16>(&tc2, Y2, M, N, ld2))) return rc;
+    return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, (cudaStream_t)stream, &tc, &tc2);
 }
 
 // Convolution (stride 1, "same" padding) on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel above: no im2col

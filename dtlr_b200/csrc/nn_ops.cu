@@ -538,13 +538,23 @@ stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
     __shared__ __nv_bfloat16 tile[7 * SIC_ROW];
     const int ox0 = blockIdx.x * SIC_SEG, oy = blockIdx.y, b = blockIdx.z;
     const int ix0 = 2 * ox0 - 3;
-    for (int i = threadIdx.x; i < 21 * SIC_COLS; i += 256) {
+    constexpr int NLD = (21 * SIC_COLS + 255) / 256;                   // all loads of a thread in flight together
+    float v[NLD];
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+        const int i = threadIdx.x + u * 256;
         const int rowi = i / SIC_COLS, col = i - rowi * SIC_COLS;      // rowi = kh * 3 + c (coalesced along col)
         const int kh = rowi / 3, c = rowi - kh * 3;
         const int iy = 2 * oy + kh - 3, ix = ix0 + col;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + iy) * W + ix);
-        tile[kh * SIC_ROW + col * 3 + c] = __float2bfloat16_rn(v);
+        v[u] = 0.f;
+        if (i < 21 * SIC_COLS && iy >= 0 && iy < H && ix >= 0 && ix < W) v[u] = __ldg(x + ((size_t)(b * 3 + c) * H + iy) * W + ix);
+    }
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+        const int i = threadIdx.x + u * 256;
+        const int rowi = i / SIC_COLS, col = i - rowi * SIC_COLS;
+        const int kh = rowi / 3, c = rowi - kh * 3;
+        if (i < 21 * SIC_COLS) tile[kh * SIC_ROW + col * 3 + c] = __float2bfloat16_rn(v[u]);
     }
     __syncthreads();
     const int nchunk = ldo / 8;                                        // 16-byte chunks per output row

@@ -304,9 +304,10 @@ class InferenceEngine:
                 if st is not None and i == 0:
                     st["enc0_core"] = core.view(B, S, d)
                 s1 = ops.linear_ln(core, *lyr["attn"]["out"], src, *lyr["ln1"])
-                src = ops.ffn_ln(s1, *lyr["l1"], *lyr["l2"], *lyr["ln2"])
                 if i + 1 < len(P["enc"]):
-                    q = ops.add(src, pos)
+                    src, q = ops.ffn_ln(s1, *lyr["l1"], *lyr["l2"], *lyr["ln2"], add2=pos)
+                else:
+                    src = ops.ffn_ln(s1, *lyr["l1"], *lyr["l2"], *lyr["ln2"])
             memory = src
             if st is not None:
                 st["memory"] = memory.view(B, S, d)

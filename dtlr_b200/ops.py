@@ -252,10 +252,12 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
     # epilogue-bound and run faster as GEMM + add_layernorm256; K = 2048 (FFN linear2) gains)
     if a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] >= LN_FUSE_MIN_K:
         return gemm_ln(a, w, bias, residual, gamma, beta, add2)
-    # K <= 256 on many rows: the weight-stationary kernel normalises in its TMA-store epilogue (single output only)
-    if (LN_FUSE_WS and a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] <= 256 and add2 is None
+    # K <= 256 on many rows: the weight-stationary kernel normalises in its TMA-store epilogue.  Measured (B200, M = 58368,
+    # CUDA-graph timing): 23 us without a residual vs 16 + 17 us un-fused; WITH a residual the 128 KB resident weight slice
+    # leaves no room to prefetch residual tiles by TMA and the LSU transposition makes it 34 us vs 33 us -> un-fused then.
+    if (LN_FUSE_WS and a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] <= 256 and residual is None and add2 is None
             and a.shape[0] >= 2 * 148 * 128):
-        return gemm_ln(a, w, bias, residual, gamma, beta, None)
+        return gemm_ln(a, w, bias, None, gamma, beta, None)
     x = gemm(a, w, bias, residual=residual)
     return add_layernorm(x, None, gamma, beta, add2=add2)
 
@@ -265,9 +267,10 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
 FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "0") != "0"
 
 
-def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5):
-    """y = LN(x + W2 relu(W1 x + b1) + b2): one tcgen05 kernel in bf16 mode when d_model = 256 and the hidden width is a multiple of
-    128 (<= 2048) -- the hidden activation never reaches HBM; otherwise linear1 + fused linear2/LayerNorm."""
+def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
+    """y = LN(x + W2 relu(W1 x + b1) + b2) [, y2 = y + add2]: one tcgen05 kernel in bf16 mode when d_model = 256 and the hidden
+    width is a multiple of 128 (<= 2048) -- the hidden activation never reaches HBM (opt-in, see FFN_FUSED); otherwise linear1 +
+    fused linear2/LayerNorm."""
     import ctypes
     M = x.shape[0]
     hid = w1.shape[0]
@@ -276,5 +279,5 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5):
         y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
         _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
               ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _st(x))
-        return y
-    return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
+        return (y, add(y, add2)) if add2 is not None else y
+    return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta, add2=add2)

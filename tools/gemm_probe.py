@@ -75,3 +75,18 @@ def ln_probe(M=58368, nbuf=6):
 
 
 ln_probe()
+
+
+def ln2048_probe(M=58368, nbuf=4):
+    a = [torch.randn(M, 2048, device="cuda").bfloat16() for _ in range(nbuf)]
+    r = [torch.randn(M, 256, device="cuda").bfloat16() for _ in range(nbuf)]
+    w = (torch.randn(256, 2048, device="cuda") / 45).bfloat16()
+    b = torch.randn(256, device="cuda")
+    gm, bt = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    plain = timeit(lambda i: ops.gemm(a[i % nbuf], w, b, residual=r[i % nbuf]), iters=10)
+    ln = timeit(lambda i: ops.gemm_ln(a[i % nbuf], w, b, r[i % nbuf], gm, bt), iters=10)
+    ln2 = timeit(lambda i: ops.gemm_ln(a[i % nbuf], w, b, r[i % nbuf], gm, bt, r[(i + 1) % nbuf]), iters=10)
+    print("linear2 (2048->256) M=%d: gemm+res %.1f us, gemm_ln %.1f us, gemm_ln+add2 %.1f us" % (M, plain, ln, ln2), flush=True)
+
+
+ln2048_probe()
