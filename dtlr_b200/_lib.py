@@ -26,6 +26,8 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.dtlr_last_error.restype = ctypes.c_char_p
         _lib.dtlr_version.restype = ctypes.c_int
+        if os.environ.get("DTLR_DEBUG_FLAGS"):      # tuning / A-B switches of include/dtlr_b200.h (dtlr_debug_flags)
+            _lib.dtlr_debug_flags(int(os.environ["DTLR_DEBUG_FLAGS"]))
     return _lib
 
 

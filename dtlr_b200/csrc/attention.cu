@@ -122,6 +122,8 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
     const int b = blockIdx.z, h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t row0 = (size_t)b * Q;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- stage K and V of this (image, head): 4 x 16-byte chunks per row, zero rows for the key padding
     for (int i = tid; i < KP * 4; i += FA_WARPS * 32) {
@@ -289,8 +291,8 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         int q_per_cta = ((Q + splits - 1) / splits + 16 * FA_MT - 1) / (16 * FA_MT) * (16 * FA_MT);
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_flash_bf16_kernel<FA_MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
-        mha_flash_bf16_kernel<FA_MT><<<fgrid, FA_WARPS * 32, smem, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v,
-                                                                  (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f);
+        DTLR_CHECK_CUDA(launch_pdl(mha_flash_bf16_kernel<FA_MT>, fgrid, dim3(FA_WARPS * 32), smem, st, (const __nv_bfloat16*)qk, ld_qk, k_off,
+                                   (const __nv_bfloat16*)v, ld_v, (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
     } else if (dtype == DTLR_BF16)
         mha_simt_kernel<__nv_bfloat16><<<grid, ATT_QT, 0, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v, attn_mask, (__nv_bfloat16*)out, ld_o, Q, scale);
     else { set_error("mha: unsupported dtype"); return DTLR_ERR_INVALID; }

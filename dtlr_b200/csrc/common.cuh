@@ -64,12 +64,34 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream is still
+// draining; it runs its private prologue (barrier init, TMEM allocation, descriptor prefetch, constant weights) and must execute
+// pdl_wait() before its first access to memory the predecessor may touch.  pdl_launch_dependents() lets the NEXT kernel start
+// early (no effect when that one is launched normally).  dtlr_debug_flags(64) turns the launch attribute off (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 2^x on the SFU without exp2f's denormal-range pre/post scaling (2 FMUL + 1 FSETP per call): in the softmax the result
 // either is <= 1 with an argument <= 0 or is flushed to zero, so the plain approximation is exactly what is wanted.
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_debug_flags & 64) ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace dtlr

@@ -273,6 +273,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();                                        // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -591,6 +593,8 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    if (warp != 0) pdl_wait();                         // (the producer first fetches the constant weight slice)
 
     if (warp == 0) {
         // ===== TMA producer: the weight slice once, then A tiles
@@ -599,6 +603,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 mbar_expect_tx(&w_bar[kb], S::W_KB_BYTES);
                 tma_load_2d(wreg + kb * S::W_KB_BYTES, &tmB, &w_bar[kb], kb * GEMM_BK, n0);
             }
+            pdl_wait();                                // activations of the previous kernel from here on
             uint32_t it = 0;
             for (int mt = r0; mt < num_m; mt += cps) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -901,8 +906,7 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
     const int ns = e.N / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int cps = sm_count() / ns;
     if (cps > num_m) cps = num_m;
-    k<<<ns * cps, 320, S::TOTAL, st>>>(ta, tb, tc, tr, e, ns, cps);
-    DTLR_CHECK_LAUNCH();
+    DTLR_CHECK_CUDA(launch_pdl(k, dim3(ns * cps), dim3(320), S::TOTAL, st, ta, tb, tc, tr, e, ns, cps));
     return DTLR_OK;
 }
 
@@ -952,8 +956,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     }
     const int tiles = ((e.M + GEMM_BM - 1) / GEMM_BM) * ((e.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    k<<<grid, 320, S::TOTAL, st>>>(ta, tb, tc ? *tc : ta, tc2 ? *tc2 : ta, e);      // output maps only used by the LayerNorm epilogue
-    DTLR_CHECK_LAUNCH();
+    DTLR_CHECK_CUDA(launch_pdl(k, dim3(grid), dim3(320), S::TOTAL, st, ta, tb, tc ? *tc : ta, tc2 ? *tc2 : ta, e));   // output maps: LayerNorm epilogue only
     return DTLR_OK;
 }
 

@@ -369,6 +369,8 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(Lq, q0 + q_per_cta);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- stage the head's value slab: slab pixel p+1 = pixel p, pixels 0 and S+1 are zero padding
     {
@@ -747,8 +749,7 @@ static int launch_fwd_mma(const void* value, const void* loc, const void* attn, 
     auto k = mode == 0 ? msda_fwd_mma_kernel<0> : (mode == 1 ? msda_fwd_mma_kernel<1> : msda_fwd_mma_kernel<2>);
     DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(qsplit, M, B), block(MMA_NW * 32);
-    k<<<grid, block, smem, st>>>((const __nv_bfloat16*)value, loc, (const float*)attn, (__nv_bfloat16*)out, lv, S, M, Lq, q_per_cta, fz, vld);
-    DTLR_CHECK_LAUNCH();
+    DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const __nv_bfloat16*)value, loc, (const float*)attn, (__nv_bfloat16*)out, lv, S, M, Lq, q_per_cta, fz, vld));
     return DTLR_OK;
 }
 

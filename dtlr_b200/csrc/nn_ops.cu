@@ -5,6 +5,18 @@
 // statistics and transcendental math are always fp32.
 #include "common.cuh"
 
+
+// every kernel of this file starts with pdl_launch_dependents(); pdl_wait(); and is launched with the programmatic-dependent-launch
+// attribute: its launch latency overlaps the tail of its predecessor in the stream (common.cuh)
+#define DTLR_LAUNCH(kernel, grid, block, smem, st, ...)                                                                   \
+    do {                                                                                                                  \
+        cudaError_t _le = dtlr::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__);             \
+        if (_le != cudaSuccess) {                                                                                         \
+            dtlr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_le), __FILE__, __LINE__);            \
+            return DTLR_ERR_CUDA;                                                                                         \
+        }                                                                                                                 \
+    } while (0)
+
 namespace dtlr {
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
@@ -58,6 +70,8 @@ __device__ __forceinline__ float warp_max_f(float v) {
 template <typename TI, typename TO, bool NCHW_IN>
 __global__ void im2col_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int H, int W, int C, int KH, int KW,
                               int stride, int pad, int Ho, int Wo, int ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int K = KH * KW * C;
     const long long total = (long long)B * Ho * Wo * ldo;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -81,6 +95,8 @@ __global__ void im2col_kernel(const TI* __restrict__ x, TO* __restrict__ out, in
 template <typename T>
 __global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int KH, int KW,
                                    int stride, int pad, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C8 = C / 8;
     const int K8 = KH * KW * C8;
     const long long total = (long long)B * Ho * Wo * K8;
@@ -99,6 +115,8 @@ __global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ out,
 // ---------------------------------------------------------------------------------------------- max-pool 3x3 s2 p1 (NHWC)
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C8 = C / 8;
     const long long total = (long long)B * Ho * Wo * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -128,6 +146,8 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ out
 template <typename TO>
 __global__ void groupnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  TO* __restrict__ out, int HW, int C, int G, long long out_stride_b, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int g = blockIdx.x, b = blockIdx.y;
     const int cpg = C / G;
     const float* xb = x + (size_t)b * HW * C + g * cpg;
@@ -179,6 +199,8 @@ template <typename TO>
 __global__ void pos_sine_kernel(const unsigned char* __restrict__ mask, const float* __restrict__ level_embed,
                                 TO* __restrict__ out, int B, int H, int W, int npf, float temp_h, float temp_w,
                                 long long out_stride_b) {
+    pdl_launch_dependents();
+    pdl_wait();
     // one 128-thread block per token.  Warp 0 counts the unmasked pixels of the token's column (cumsum over H), warp 1 those
     // of its row (cumsum over W); then every thread produces one (sin, cos) pair per axis: dim_t[2k] == dim_t[2k+1].
     const int C = 2 * npf;
@@ -222,6 +244,8 @@ template <typename T>
 __global__ void add_layernorm256_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, T* __restrict__ y, const T* __restrict__ add2,
                                         T* __restrict__ y2, int rows, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -260,6 +284,8 @@ __global__ void add_layernorm256_kernel(const T* __restrict__ x, const T* __rest
 // out = a + b (8-wide), optionally zeroing rows where rowmask != 0 (value.masked_fill, ms_deform_attn.py:95-96)
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float x[8], y[8];
         ld8<T>(a + i * 8, x);
@@ -271,6 +297,8 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
 }
 template <typename T>
 __global__ void zero_masked_rows_kernel(T* __restrict__ x, const unsigned char* __restrict__ rowmask, long long rows, int C8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = rows * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         if (rowmask[i / C8]) {
@@ -290,6 +318,8 @@ struct PrepLevels { int n; int H[8], W[8]; };
 __global__ void msda_prep_kernel(const float* __restrict__ proj, int ld, const float* __restrict__ ref, int RD,
                                  const float* __restrict__ valid_ratios, float* __restrict__ loc, float* __restrict__ attn,
                                  const __grid_constant__ PrepLevels lv, int B, int Lq, int M, int P) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Lq * M;
     if (i >= total) return;
@@ -333,6 +363,8 @@ __global__ void msda_prep_kernel(const float* __restrict__ proj, int ld, const f
 // ref[b, tok] = ((x+0.5)/(vr_w*W_l), (y+0.5)/(vr_h*H_l)) for the token's own level l.
 __global__ void enc_ref_kernel(const float* __restrict__ valid_ratios, float* __restrict__ ref, const __grid_constant__ PrepLevels lv,
                                int B, int S) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * S) return;
     const int b = (int)(i / S);
@@ -351,6 +383,8 @@ template <typename T>
 __global__ void proposals_kernel(const T* __restrict__ memory, const unsigned char* __restrict__ pad, const int* __restrict__ valid_hw,
                                  T* __restrict__ out_memory, float* __restrict__ proposals, const __grid_constant__ PrepLevels lv,
                                  int B, int S, int C, float default_hw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long tok = blockIdx.x;
     if (tok >= (long long)B * S) return;
     const int b = (int)(tok / S);
@@ -373,6 +407,8 @@ __global__ void proposals_kernel(const T* __restrict__ memory, const unsigned ch
 
 // row-wise max over the first N columns (two-stage class score, deformable_transformer.py:345)
 __global__ void rowmax_kernel(const float* __restrict__ x, int ld, int N, float* __restrict__ out, long long rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     float m = -INFINITY;
@@ -387,6 +423,8 @@ __global__ void rowmax_kernel(const float* __restrict__ x, int ld, int N, float*
 template <typename TO>
 __global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, TO* __restrict__ out,
                                   int B, int Q, int L) {
+    pdl_launch_dependents();
+    pdl_wait();
     // 64 threads per query row handle one (sin, cos) pair of each of the 4 components: dim_t[2k] == dim_t[2k+1]
     __shared__ float dim_t[64];
     if (threadIdx.x < 64) dim_t[threadIdx.x] = powf(10000.f, 2.f * (float)threadIdx.x / 128.f);
@@ -416,6 +454,8 @@ __global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __
 // util/misc.py:575-579).  ref_is_logit: the reference is already in logit space (two-stage init: refpoint.sigmoid()).
 __global__ void box_refine_kernel(const float* __restrict__ delta, int ldd, const float* __restrict__ ref, float* __restrict__ out,
                                   long long n4) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const long long row = i / 4;
@@ -427,12 +467,16 @@ __global__ void box_refine_kernel(const float* __restrict__ delta, int ldd, cons
 }
 
 __global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = 1.f / (1.f + expf(-x[i]));
 }
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         stf<TO>(out + i, ldf<TI>(x + i));
 }
@@ -450,6 +494,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256)
 stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, TO* __restrict__ out,
                     int H, int W, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float stem_smem[];
     float* ws = stem_smem;                                   // [147][64]
     float* patch = stem_smem + 147 * 64;                     // [3][STEM_PR][2 parities][STEM_PCH + 1]
@@ -534,6 +580,8 @@ constexpr int SIC_ROW = SIC_COLS * 3 + 1;        // bf16 elements per staged inp
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const int H, const int W, const int Ho,
                    const int Wo, const int ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     // tile[kh][col * 3 + c]: for a fixed kh the 21 values (kw, c) of output pixel p are the 21 CONSECUTIVE elements from 6 * p
     __shared__ __nv_bfloat16 tile[7 * SIC_ROW];
     const int ox0 = blockIdx.x * SIC_SEG, oy = blockIdx.y, b = blockIdx.z;
@@ -590,15 +638,15 @@ extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C,
     if (total == 0) return DTLR_OK;
     if (!nchw_input && in_dtype == out_dtype && C % 8 == 0 && ldo == KH * KW * C) {
         const long long t8 = total / 8;
-        DISPATCH_T(in_dtype, im2col_vec8_kernel<T><<<grid_for(t8, 256), 256, 0, st>>>((const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo);)
+        DISPATCH_T(in_dtype, DTLR_LAUNCH((im2col_vec8_kernel<T>), grid_for(t8, 256), 256, 0, st, (const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo);)
     } else if (nchw_input && in_dtype == DTLR_F32 && out_dtype == DTLR_BF16 && C == 3 && KH == 7 && KW == 7 && stride == 2 && pad == 3 &&
                (ldo % 8) == 0 && (((uintptr_t)out) & 15) == 0 && B <= 65535 && Ho <= 65535) {
         dim3 grid((Wo + SIC_SEG - 1) / SIC_SEG, Ho, B);
-        stem_im2col_kernel<<<grid, 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, H, W, Ho, Wo, ldo);
+        DTLR_LAUNCH((stem_im2col_kernel), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)out, H, W, Ho, Wo, ldo);
     } else if (nchw_input && in_dtype == DTLR_F32) {
-        DISPATCH_T(out_dtype, im2col_kernel<float, T, true><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
+        DISPATCH_T(out_dtype, DTLR_LAUNCH((im2col_kernel<float, T, true>), grid_for(total, 256), 256, 0, st, (const float*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
     } else if (!nchw_input && in_dtype == out_dtype) {
-        DISPATCH_T(in_dtype, im2col_kernel<T, T, false><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
+        DISPATCH_T(in_dtype, DTLR_LAUNCH((im2col_kernel<T, T, false>), grid_for(total, 256), 256, 0, st, (const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
     } else {
         set_error("im2col: unsupported dtype/layout combination");
         return DTLR_ERR_UNSUPPORTED;
@@ -617,10 +665,10 @@ extern "C" int dtlr_stem_conv(const float* x, const float* w, const float* bias,
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == DTLR_F32) {
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv7x7_kernel<float><<<grid, 256, smem, st>>>(x, w, bias, (float*)out, H, W, Ho, Wo);
+        DTLR_LAUNCH((stem_conv7x7_kernel<float>), grid, 256, smem, st, x, w, bias, (float*)out, H, W, Ho, Wo);
     } else if (out_dtype == DTLR_BF16) {
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stem_conv7x7_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo);
+        DTLR_LAUNCH((stem_conv7x7_kernel<__nv_bfloat16>), grid, 256, smem, st, x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo);
     } else { set_error("stem_conv: unsupported dtype"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -630,7 +678,7 @@ extern "C" int dtlr_maxpool3x3s2(const void* x, void* out, int B, int H, int W, 
     DTLR_CHECK_ARG(C % 8 == 0, "maxpool: C must be a multiple of 8");
     const long long total = (long long)B * Ho * Wo * (C / 8);
     if (total == 0) return DTLR_OK;
-    DISPATCH_T(dtype, maxpool3x3s2_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, B, H, W, C, Ho, Wo);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((maxpool3x3s2_kernel<T>), grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const T*)x, (T*)out, B, H, W, C, Ho, Wo);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -640,7 +688,7 @@ extern "C" int dtlr_groupnorm(const float* x, const float* gamma, const float* b
     DTLR_CHECK_ARG(C % G == 0, "groupnorm: C %% G != 0");
     if (B == 0 || HW == 0) return DTLR_OK;
     dim3 grid(G, B);
-    DISPATCH_T(out_dtype, groupnorm_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (T*)out, HW, C, G, out_stride_b, eps);)
+    DISPATCH_T(out_dtype, DTLR_LAUNCH((groupnorm_kernel<T>), grid, 256, 0, (cudaStream_t)stream, x, gamma, beta, (T*)out, HW, C, G, out_stride_b, eps);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -649,7 +697,7 @@ extern "C" int dtlr_pos_sine(const unsigned char* mask, const float* level_embed
                              float temp_h, float temp_w, long long out_stride_b, int out_dtype, void* stream) {
     const long long total = (long long)B * H * W;
     if (total == 0) return DTLR_OK;
-    DISPATCH_T(out_dtype, pos_sine_kernel<T><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>(mask, level_embed, (T*)out, B, H, W, npf, temp_h, temp_w, out_stride_b);)
+    DISPATCH_T(out_dtype, DTLR_LAUNCH((pos_sine_kernel<T>), (unsigned)total, 128, 0, (cudaStream_t)stream, mask, level_embed, (T*)out, B, H, W, npf, temp_h, temp_w, out_stride_b);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -660,7 +708,7 @@ extern "C" int dtlr_add_layernorm(const void* x, const void* res, const float* g
     if (rows == 0) return DTLR_OK;
     const int wpb = 8;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    DISPATCH_T(dtype, add_layernorm256_kernel<T><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((add_layernorm256_kernel<T>), grid, wpb * 32, 0, (cudaStream_t)stream, (const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -668,7 +716,7 @@ extern "C" int dtlr_add_layernorm(const void* x, const void* res, const float* g
 extern "C" int dtlr_add(const void* a, const void* b, void* out, long long n, int dtype, void* stream) {
     DTLR_CHECK_ARG(n % 8 == 0, "add: n must be a multiple of 8");
     if (n == 0) return DTLR_OK;
-    DISPATCH_T(dtype, add_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)out, n / 8);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((add_kernel<T>), grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream, (const T*)a, (const T*)b, (T*)out, n / 8);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -676,7 +724,7 @@ extern "C" int dtlr_add(const void* a, const void* b, void* out, long long n, in
 extern "C" int dtlr_zero_masked_rows(void* x, const unsigned char* rowmask, long long rows, int C, int dtype, void* stream) {
     DTLR_CHECK_ARG(C % 8 == 0, "zero_masked_rows: C %% 8 != 0");
     if (rows == 0) return DTLR_OK;
-    DISPATCH_T(dtype, zero_masked_rows_kernel<T><<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((T*)x, rowmask, rows, C / 8);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((zero_masked_rows_kernel<T>), grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream, (T*)x, rowmask, rows, C / 8);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -696,7 +744,7 @@ extern "C" int dtlr_msda_prep(const float* proj, int ld, const float* ref, int r
     if (rc) return rc;
     const long long total = (long long)B * Lq * M;
     if (total == 0) return DTLR_OK;
-    msda_prep_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(proj, ld, ref, ref_dim, valid_ratios, loc, attn, lv, B, Lq, M, P);
+    DTLR_LAUNCH((msda_prep_kernel), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, proj, ld, ref, ref_dim, valid_ratios, loc, attn, lv, B, Lq, M, P);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -707,7 +755,7 @@ extern "C" int dtlr_enc_ref_points(const float* valid_ratios, const int64_t* sha
     if (rc) return rc;
     const long long total = (long long)B * S;
     if (total == 0) return DTLR_OK;
-    enc_ref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(valid_ratios, ref, lv, B, S);
+    DTLR_LAUNCH((enc_ref_kernel), (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, valid_ratios, ref, lv, B, S);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -719,14 +767,14 @@ extern "C" int dtlr_encoder_proposals(const void* memory, const unsigned char* p
     if (rc) return rc;
     const long long total = (long long)B * S;
     if (total == 0) return DTLR_OK;
-    DISPATCH_T(dtype, proposals_kernel<T><<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>((const T*)memory, pad, valid_hw, (T*)out_memory, proposals, lv, B, S, C, default_hw);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((proposals_kernel<T>), (unsigned)total, 128, 0, (cudaStream_t)stream, (const T*)memory, pad, valid_hw, (T*)out_memory, proposals, lv, B, S, C, default_hw);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
 
 extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long rows, void* stream) {
     if (rows == 0) return DTLR_OK;
-    rowmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, ld, N, out, rows);
+    DTLR_LAUNCH((rowmax_kernel), (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, x, ld, N, out, rows);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -734,7 +782,7 @@ extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long 
 extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream) {
     const long long rows = (long long)B * Q;
     if (rows == 0) return DTLR_OK;
-    DISPATCH_T(out_dtype, sine_embed_kernel<T><<<(unsigned)((rows + 3) / 4), 256, 0, (cudaStream_t)stream>>>(ref, valid_ratios, (T*)out, B, Q, L);)
+    DISPATCH_T(out_dtype, DTLR_LAUNCH((sine_embed_kernel<T>), (unsigned)((rows + 3) / 4), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (T*)out, B, Q, L);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -742,14 +790,14 @@ extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void
 extern "C" int dtlr_box_refine(const float* delta, int ldd, const float* ref, float* out, long long rows, void* stream) {
     const long long n4 = rows * 4;
     if (n4 == 0) return DTLR_OK;
-    box_refine_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(delta, ldd, ref, out, n4);
+    DTLR_LAUNCH((box_refine_kernel), (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, delta, ldd, ref, out, n4);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
 
 extern "C" int dtlr_sigmoid(const float* x, float* out, long long n, void* stream) {
     if (n == 0) return DTLR_OK;
-    sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    DTLR_LAUNCH((sigmoid_kernel), (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, x, out, n);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -758,13 +806,13 @@ extern "C" int dtlr_cast(const void* x, void* out, long long n, int in_dtype, in
     if (n == 0) return DTLR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (in_dtype == DTLR_F32 && out_dtype == DTLR_BF16)
-        cast_kernel<float, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (__nv_bfloat16*)out, n);
+        DTLR_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid_for(n, 256), 256, 0, st, (const float*)x, (__nv_bfloat16*)out, n);
     else if (in_dtype == DTLR_BF16 && out_dtype == DTLR_F32)
-        cast_kernel<__nv_bfloat16, float><<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (float*)out, n);
+        DTLR_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid_for(n, 256), 256, 0, st, (const __nv_bfloat16*)x, (float*)out, n);
     else if (in_dtype == out_dtype && in_dtype == DTLR_F32)
-        cast_kernel<float, float><<<grid_for(n, 256), 256, 0, st>>>((const float*)x, (float*)out, n);
+        DTLR_LAUNCH((cast_kernel<float, float>), grid_for(n, 256), 256, 0, st, (const float*)x, (float*)out, n);
     else if (in_dtype == out_dtype && in_dtype == DTLR_BF16)
-        cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
+        DTLR_LAUNCH((cast_kernel<__nv_bfloat16, __nv_bfloat16>), grid_for(n, 256), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
     else { set_error("cast: unsupported dtypes"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
