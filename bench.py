@@ -35,31 +35,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed regions (B200_PROFILING.md).  The sampler process is started
+    before the warm-up (nvidia-smi needs ~0.5 s to produce its first line) and every line is time-stamped on arrival; only lines
+    that arrived inside a window opened by begin() / closed by end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.windows, self._t0 = gpu_index, None, [], [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self._t0 = time.perf_counter()
+
+    def end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.perf_counter()))
+            self._t0 = None
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if not any(a <= ts <= b + 0.02 for a, b in self.windows):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -71,7 +84,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "device-resident timed region + end-to-end timed region (nvidia-smi -lms 20)"}
 
 
 def build_ours(device, dtype):
@@ -161,36 +175,39 @@ def main():
         return dist_util.max_over_ranks(ms, device)
 
     # ---------------- device-resident throughput (`value`) with the dominant kernel family timed by CUDA events
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(args.warmup):
             model(dev_imgs)
     gemm_events, cur = [], {}
 
-    def timer(name, flops, dev, begin):
+    msda_events = []
+
+    def timer(name, qty, dev, begin):
         if begin:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            cur["e0"], cur["fl"] = e0, flops
+            cur["e0"], cur["fl"] = e0, qty
         else:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            gemm_events.append((cur["e0"], e1, cur["fl"]))
+            (gemm_events if name == "gemm" else msda_events).append((cur["e0"], e1, cur["fl"]))
 
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     _lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     with torch.no_grad():
         for _ in range(args.steps):
             out = model(dev_imgs)
     e1.record()
     barrier()
+    sampler.end()
     launches = _lib.LAUNCHES
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = dist_util.whole_job_throughput(B, world, args.steps, ms_total)
@@ -216,6 +233,8 @@ def main():
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
     gemm_flops = sum(f for _, _, f in gemm_events)
     n_gemm = len(gemm_events)
+    msda_ms = sum(a.elapsed_time(b) for a, b, _ in msda_events)
+    msda_bytes = sum(q for _, _, q in msda_events)
 
     # ---------------- end to end through the public API with HOST buffers (`e2e`)
     from dtlr_b200.misc import nested_tensor_from_tensor_list
@@ -232,11 +251,14 @@ def main():
     with torch.no_grad():
         ids = e2e_run(2)
         barrier()
+        sampler.begin()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         ids = e2e_run(args.steps)
         t1.record()
         barrier()
+        sampler.end()
+    clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
@@ -253,6 +275,15 @@ def main():
                 "launches_timed": n_gemm, "share_of_step": round(gemm_ms / n_prof / ms_step, 3),
                 "eager_profiled_ms_per_step": round(prof_ms / n_prof, 3),
                 "algorithmic_flops_per_step": gemm_flops / n_prof}
+    # the north-star kernel (multi-scale deformable attention core, fused prologue): HBM roofline from its algorithmic bytes;
+    # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_msda_mma_ncu.txt)
+    hbm = pk["hbm_gbs"]
+    msda_gbs = msda_bytes / (msda_ms * 1e-3) / 1e9 if msda_ms > 0 else 0.0
+    roofline_msda = {"kernel": "msda_fwd_mma_kernel (dtlr_msda_forward_fused)", "bound": "hbm", "achieved": round(msda_gbs, 1), "peak": hbm,
+                     "unit": "GB/s", "frac": round(msda_gbs / hbm, 4), "traffic": 86.7e6, "peak_kind": pk_kind + " copy bandwidth",
+                     "launches_timed": len(msda_events), "share_of_step": round(msda_ms / n_prof / ms_step, 3),
+                     "algorithmic_bytes_per_launch": round(msda_bytes / max(1, len(msda_events))),
+                     "binding_resource": "shared-memory gather bandwidth (4 KB of taps per (query, head) at 128 B/clk/SM), see DESIGN.md 3.1"}
     cpu = None
     if not args.no_cpu_baseline:
         ips, sec = cpu_baseline_run(8, 3, 1)
@@ -269,7 +300,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": host_imgs.numel() * 4 ,
                     "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(e2e_ms / args.steps, 3),
                     "api": "dtlr_b200.pipeline.HostPipeline: pinned host images -> DINO.forward -> dino.decode_frames (fused CTC-view argmax) -> pinned host int32 frame ids; H2D / compute / D2H of consecutive steps overlap"},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roofline, "roofline_msda": roofline_msda, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     dist_util.shutdown()
 

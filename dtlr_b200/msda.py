@@ -70,11 +70,16 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     assert ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
     if out is None:
         out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    if L.TIMER is not None:     # bench.py: algorithmic bytes of this call (values + projection rows + reference points + output)
+        L.TIMER("msda", float(B * (S * M * D * value.element_size() + Lq * proj.shape[1] * proj.element_size()
+                                   + Lq * ref.shape[-1] * 4 + Lq * M * D * value.element_size()) + 96), value.device, True)
     with torch.cuda.device(value.device):
         rc = L.lib().dtlr_msda_forward_fused(L.ptr(value), value.stride(1), shapes_host, lsi_host, L.ptr(proj), proj.stride(0), L.dtype_code(proj), L.ptr(ref),
                                              ref.shape[-1], L.ptr(valid_ratios), L.ptr(out), B, S, M, D, n_levels, Lq, P,
                                              L.dtype_code(value), L.stream_ptr(value.device))
     L.check(rc, "dtlr_msda_forward_fused")
+    if L.TIMER is not None:
+        L.TIMER("msda", 0.0, value.device, False)
     return out
 
 
