@@ -903,7 +903,7 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
-    const int ns = e.N / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
+    const int ns = (e.N + BN - 1) / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int cps = sm_count() / ns;
     if (cps > num_m) cps = num_m;
     DTLR_CHECK_CUDA(launch_pdl(k, dim3(ns * cps), dim3(320), S::TOTAL, st, ta, tb, tc, tr, e, ns, cps));
@@ -916,7 +916,11 @@ template <typename OutT>
 static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st, int* rc) {
     if (g_debug_flags & 32) return false;
     constexpr int EPC = 16 / (int)sizeof(OutT);
-    if (e.K > 256 || (e.N % EPC) != 0 || (e.ldc % EPC) != 0 || ((uintptr_t)e.C & 15) != 0) return false;
+    // only the row PITCH has to be 16-byte aligned (TMA store clips the columns beyond N, the weight rows beyond N are zero-filled)
+    if (e.K > 256 || (e.ldc % EPC) != 0 || ((uintptr_t)e.C & 15) != 0) return false;
+    // the TMA store clips at 16-byte granularity: with N % EPC != 0 the last chunk of a row is written whole, so the columns up to
+    // the next 16-byte boundary receive zeros -- only allowed when they are padding by construction (pitch == N rounded up)
+    if ((e.N % EPC) != 0 && (e.ldc != (e.N + EPC - 1) / EPC * EPC || e.residual)) return false;
     if (e.residual && ((e.ldr % EPC) != 0 || ((uintptr_t)e.residual & 15) != 0)) return false;
     const long long num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int bn = 0;
@@ -928,9 +932,11 @@ static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi
         else if ((e.N % 192) == 0) bn = 192;
         else if ((e.N % 128) == 0) bn = 128;
         else if ((e.N % 64) == 0) bn = 64;
+        else if (e.N <= 256 && e.N > 16) bn = (e.N + 63) / 64 * 64;          // one ragged slice (e.g. the 166-class heads)
     }
-    if (!bn || e.N / bn > sm_count()) return false;
-    if (num_m * (e.N / bn) < 2ll * sm_count()) return false;
+    if (!bn) return false;
+    const int ns_ = (e.N + bn - 1) / bn;
+    if (ns_ > sm_count() || num_m * ns_ < 2ll * sm_count()) return false;
     if (e.residual) {
         *rc = bn == 128 ? launch_ws<128, OutT, true>(A, lda, W, ldw, e, st) : launch_ws<64, OutT, true>(A, lda, W, ldw, e, st);
         return true;

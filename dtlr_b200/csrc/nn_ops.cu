@@ -450,6 +450,37 @@ __global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __
     }
 }
 
+// bf16 throughput mode of the same embedding: arguments lie in [0, 2*pi*valid_ratio] (reference points are sigmoids), so the SFU
+// sin/cos are accurate to ~1e-6 absolute -- far below the bf16 output rounding; 1/dim_t from one ex2 per thread, 32 rows per
+// block, (sin, cos) pairs stored as one packed 4-byte word (256-byte coalesced rows per component).
+__global__ void __launch_bounds__(256)
+sine_embed_bf16_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, __nv_bfloat16* __restrict__ out,
+                       const long long rows, const int Q, const int L) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int k = threadIdx.x & 63;
+    // 2*pi / 10000^(2k/128)
+    const float w = 6.283185307179586f * exp2f(-(float)k * (13.287712379549449f / 64.f));
+    const long long row0 = (long long)blockIdx.x * 32 + (threadIdx.x >> 6);
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+        const long long row = row0 + it * 4;
+        if (row >= rows) break;
+        const int b = (int)(row / Q);
+        const float vx = __ldg(valid_ratios + (size_t)b * L * 2), vy = __ldg(valid_ratios + (size_t)b * L * 2 + 1);
+        const float4 r = __ldg(reinterpret_cast<const float4*>(ref + row * 4));
+        const float comp[4] = {r.y * vy, r.x * vx, r.z * vx, r.w * vy};   // y, x, w, h
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + row * 512) + k;
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+            float sn, cs;
+            __sincosf(comp[part] * w, &sn, &cs);
+            __nv_bfloat162 t = __floats2bfloat162_rn(sn, cs);
+            o[part * 64] = *reinterpret_cast<uint32_t*>(&t);
+        }
+    }
+}
+
 // new_ref = sigmoid(delta + inverse_sigmoid(ref)), eps 1e-3 (deformable_transformer.py:734-738, dino.py:343-345,
 // util/misc.py:575-579).  ref_is_logit: the reference is already in logit space (two-stage init: refpoint.sigmoid()).
 __global__ void box_refine_kernel(const float* __restrict__ delta, int ldd, const float* __restrict__ ref, float* __restrict__ out,
@@ -782,6 +813,10 @@ extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long 
 extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream) {
     const long long rows = (long long)B * Q;
     if (rows == 0) return DTLR_OK;
+    if (out_dtype == DTLR_BF16 && !(g_debug_flags & 128)) {
+        DTLR_LAUNCH((sine_embed_bf16_kernel), (unsigned)((rows + 31) / 32), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (__nv_bfloat16*)out, rows, Q, L);
+        return DTLR_OK;
+    }
     DISPATCH_T(out_dtype, DTLR_LAUNCH((sine_embed_kernel<T>), (unsigned)((rows + 3) / 4), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (T*)out, B, Q, L);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

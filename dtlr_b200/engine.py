@@ -119,6 +119,14 @@ class InferenceEngine:
 
     # ------------------------------------------------------------------------------------------------ pieces
     @staticmethod
+    def _head_gemm(x, w, b):
+        """fp32 class logits.  The row pitch is padded to a multiple of 4 floats (166 -> 168) so that the weight-stationary GEMM can
+        write them with TMA stores; the returned (M, N) tensor is a column view of that buffer."""
+        M, N = x.shape[0], w.shape[0]
+        buf = torch.empty((M, (N + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+        return ops.gemm(x, w, b, out_dtype=torch.float32, out=buf[:, :N])
+
+    @staticmethod
     def _mlp3(x, layers, out_f32_last=True):
         h = ops.gemm(x, *layers[0], relu=1)
         h = ops.gemm(h, *layers[1], relu=1)
@@ -316,7 +324,7 @@ class InferenceEngine:
             Q = tr.num_queries
             om, prop = ops.encoder_proposals(memory, pad_u8, valid_hw, shapes_host, nlev, B, S, d, tr.two_stage_default_hw)
             omn = ops.linear_ln(om, *P["enc_output"], None, *P["enc_output_norm"])
-            cls_unsel = ops.gemm(omn, *P["enc_cls"], out_dtype=torch.float32)
+            cls_unsel = self._head_gemm(omn, *P["enc_cls"])
             scores = ops.rowmax(cls_unsel, cls_unsel.shape[1]).view(B, S)
             coord_unsel = (self._mlp3(omn, P["enc_bbox"]) + prop).view(B, S, 4)
             topk = torch.topk(scores, Q, dim=1)[1]
@@ -374,17 +382,17 @@ class InferenceEngine:
             if hs_all is not None:
                 ref_all = torch.cat(refs[:n_dec], 0)
                 box_all = ops.box_refine(self._mlp3(hs_all, P["bbox"][0]), ref_all).view(n_dec, B, Q, 4)
-                cls_all = ops.gemm(hs_all, *P["cls"][0], out_dtype=torch.float32).view(n_dec, B, Q, -1)
+                cls_all = self._head_gemm(hs_all, *P["cls"][0]).unflatten(0, (n_dec, B, Q))
                 for i in want:
                     coords[i], classes[i] = box_all[i], cls_all[i]
             else:
                 for i in want:
                     coords[i] = ops.box_refine(self._mlp3(hs[i], P["bbox"][i]), refs[i]).view(B, Q, 4)
-                    classes[i] = ops.gemm(hs[i], *P["cls"][i], out_dtype=torch.float32).view(B, Q, -1)
+                    classes[i] = self._head_gemm(hs[i], *P["cls"][i]).unflatten(0, (B, Q))
             out = {"pred_logits": classes[n_dec - 1], "pred_boxes": coords[n_dec - 1]}
             if m.aux_loss:
                 out["aux_outputs"] = [{"pred_logits": classes[i], "pred_boxes": coords[i]} for i in want if i != n_dec - 1]
-            interm_class = ops.gemm(tgt_undetach.view(B * Q, d), *P["enc_cls"], out_dtype=torch.float32).view(B, Q, -1)
+            interm_class = self._head_gemm(tgt_undetach.view(B * Q, d), *P["enc_cls"]).unflatten(0, (B, Q))
             out["interm_outputs"] = {"pred_logits": interm_class, "pred_boxes": refpoint.sigmoid()}
             out["interm_outputs_for_matching_pre"] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
             out["dn_meta"] = None

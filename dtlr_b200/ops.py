@@ -220,7 +220,9 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
     import ctypes
     L.require_cuda(pred_logits, pred_boxes)
     B, Q, C = pred_logits.shape
-    logits = pred_logits.float().contiguous()
+    logits = pred_logits.float()
+    if not (logits.stride(2) == 1 and logits.stride(0) == Q * logits.stride(1)):      # rows may be pitched (engine: 166 -> 168)
+        logits = logits.contiguous()
     boxes = pred_boxes.float().contiguous()
     dev = logits.device
     frames = torch.empty((B, Q), dtype=torch.int32, device=dev)
@@ -228,7 +230,7 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
     perm = torch.empty((B, Q), dtype=torch.int32, device=dev) if want_new_pred else None
     rsum = torch.empty((B, Q), dtype=torch.float32, device=dev) if want_new_pred else None
     newp = torch.empty((B, Q, C + 1), dtype=torch.float32, device=dev) if want_new_pred else None
-    _call("dtlr_ctc_decode", _p(logits), C, _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum), B, Q, C,
+    _call("dtlr_ctc_decode", _p(logits), logits.stride(1), _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum), B, Q, C,
           ctypes.c_float(eps), _st(logits))
     return (frames, newp) if want_new_pred else frames
 

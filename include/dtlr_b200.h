@@ -87,6 +87,8 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
  * A dev [M,lda], W dev [N,ldw] (both K contiguous), bias dev fp32 [N] or NULL, residual dev [M,ldr] (dtype of C) or
  * NULL, C dev [M,ldc].  in_dtype DTLR_BF16: tcgen05 tensor-core path (fp32 accumulate), out_dtype BF16 or F32,
  * rows 16-byte aligned (lda,ldw multiples of 8).  in_dtype DTLR_F32: exact-fp32 SIMT path (parity mode), out F32.
+ * When N is no multiple of 16 bytes of output elements and ldc is exactly N rounded up to that multiple (a padded row pitch),
+ * the pad columns of C are scratch: the TMA-store epilogue may write zeros there.
  */
 int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
               void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);

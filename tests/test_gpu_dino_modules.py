@@ -97,3 +97,26 @@ def test_training_mode_forward_backward_Q3():
     g = model.transformer.encoder.layers[0].self_attn.sampling_offsets.weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
     assert model.backbone[0].body.conv1.weight.grad is None          # conv1 + layer1 frozen (reference backbone.py:79-81)
+
+
+def test_sine_embed_bf16_fast_kernel_matches_reference_formula():
+    """gen_sineembed_for_position (reference models/dino/utils.py:141-167) on reference boxes x valid ratios: the bf16 throughput
+    kernel (SFU sin/cos, packed stores) against the exact fp32 kernel and a plain torch statement of the formula."""
+    import math
+    from dtlr_b200 import ops
+    B, Q, L = 3, 900, 4
+    g = torch.Generator(device="cuda").manual_seed(4)
+    ref = torch.rand(B * Q, 4, device="cuda", generator=g)
+    vr = (0.5 + 0.5 * torch.rand(B, L, 2, device="cuda", generator=g)).contiguous()
+    exact = ops.sine_embed(ref, vr, B, Q, L, torch.float32)
+    fast = ops.sine_embed(ref, vr, B, Q, L, torch.bfloat16).float()
+    assert (fast - exact).abs().max().item() <= 2 ** -8 + 1e-6           # bf16 rounding of values in [-1, 1]
+    dim_t = 10000 ** (2 * (torch.arange(128, device="cuda") // 2) / 128.0)
+    scl = torch.cat([vr[:, 0], vr[:, 0]], -1)[:, None, :]                # (B,1,4) = (vx, vy, vx, vy)
+    r = ref.view(B, Q, 4) * scl
+    parts = []
+    for comp in (r[..., 1], r[..., 0], r[..., 2], r[..., 3]):            # y, x, w, h
+        p = comp[..., None] * 2 * math.pi / dim_t
+        parts.append(torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), -1).flatten(-2))
+    formula = torch.cat(parts, -1).view(B * Q, 512)
+    assert (exact - formula).abs().max().item() < 1e-5

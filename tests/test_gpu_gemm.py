@@ -160,3 +160,26 @@ def test_fused_ffn_block(M, hid):
     assert (y.float() - ref).abs().mean().item() < 4e-3
     un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("M,N,K,out_dtype", [(57600 * 2, 166, 256, torch.float32), (58368, 166, 256, torch.float32),
+                                              (60000, 100, 128, torch.bfloat16), (50000, 200, 256, torch.float32)])
+def test_weight_stationary_ragged_slice_pitched_output(M, N, K, out_dtype):
+    """class heads: N = 166 is no multiple of anything -- one ragged weight slice (rows beyond N zero-filled by TMA), output rows
+    pitched to 16 bytes (166 -> 168 floats); the TMA store clips at 16-byte granularity, so the pad columns (padding by
+    construction: pitch == N rounded up) receive zeros, nothing beyond the row is touched."""
+    from dtlr_b200 import ops, _lib
+    a, w, bias = _mk(M, N, K, torch.bfloat16, M + N + K)
+    epc = 4 if out_dtype == torch.float32 else 8
+    buf = torch.full((M, (N + epc - 1) // epc * epc), 7.0, device="cuda", dtype=out_dtype)
+    out = ops.gemm(a, w, bias, out_dtype=out_dtype, out=buf[:, :N])
+    ref = a.double() @ w.double().T + bias.double()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < (1e-4 if out_dtype == torch.float32 else 2e-2), err
+    assert ((buf[:, N:] == 7.0) | (buf[:, N:] == 0.0)).all()
+    _lib.lib().dtlr_debug_flags(32)
+    try:
+        old = ops.gemm(a, w, bias, out_dtype=out_dtype)
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
+    assert torch.equal(out, old)
