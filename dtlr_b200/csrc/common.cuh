@@ -63,6 +63,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the stream is still
 // draining; it runs its private prologue (barrier init, TMEM allocation, descriptor prefetch, constant weights) and must execute

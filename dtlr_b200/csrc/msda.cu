@@ -336,6 +336,7 @@ constexpr int MMA_NW = 8;             // warps per CTA (two CTAs per SM: 2 x (sl
 constexpr int MMA_TSTRIDE = 208;      // bytes per query in a tap table: 64 offsets + 128 weights + 16 pad (the pad makes the
                                       // 16-byte stores of 8 consecutive lanes hit 8 different bank groups)
 constexpr int MMA_TAB_BYTES = 32 * MMA_TSTRIDE;
+constexpr int MMA_RAW_PITCH = 112;    // staged raw projection row of a query (96 B used): lanes 0-7 hit 8 different 16-byte bank groups
 
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const uint32_t saddr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -372,6 +373,27 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
     pdl_launch_dependents();
     pdl_wait();
 
+    unsigned char* tab = smem + (size_t)(S + 2) * 64 + (size_t)warp * MMA_TAB_BYTES;
+    const int per_warp = (q1 - q0 + MMA_NW - 1) / MMA_NW;
+    const int wq0 = q0 + warp * per_warp;
+    const int wq1 = min(q1, wq0 + per_warp);
+    // MODE 2: the raw projection rows of a 32-query batch (64 B of offsets + 32 B of logits per query, 768 B apart in HBM) are
+    // fetched by cp.async with consecutive lanes on consecutive 16-byte chunks (6-11 lines per instruction instead of 32) into the
+    // warp's table region (112-byte pitch: conflict-free 16-byte reads by lane = query); the first batch flies behind the slab copy
+    auto stage_raw = [&](int qb) {
+        const __nv_bfloat16* pbase = reinterpret_cast<const __nv_bfloat16*>(loc_or_proj);
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int c = lane + 32 * u;
+            const int qi = c / 6, part = c - qi * 6;
+            const int q = min(qb + qi, wq1 - 1);
+            const __nv_bfloat16* src = pbase + ((size_t)b * Lq + q) * fz.ld + (part < 4 ? m * (LP * 2) + part * 8 : M * (LP * 2) + m * LP + (part - 4) * 8);
+            cp_async16(tab + qi * MMA_RAW_PITCH + part * 16, src);
+        }
+        cp_async_commit();
+    };
+    if (MODE == 2 && wq0 < wq1) stage_raw(wq0);
+
     // ---- stage the head's value slab: slab pixel p+1 = pixel p, pixels 0 and S+1 are zero padding
     {
         const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * vld + (size_t)m * 32) * 2;
@@ -386,8 +408,6 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
             *reinterpret_cast<uint4*>(smem + (size_t)row * 64 + (tid & 3) * 16) = make_uint4(0, 0, 0, 0);
         }
     }
-    unsigned char* tab = smem + (size_t)(S + 2) * 64 + (size_t)warp * MMA_TAB_BYTES;
-
     // phase-2 lane roles
     const int g = lane >> 2, j = lane & 3;
     const int mi = lane >> 3;                                        // ldmatrix: row (lane & 7) of matrix mi = 2*yrow + slot
@@ -399,9 +419,6 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
     const uint32_t sel0 = contrib ? ((g & 1) ? 0x1044u : 0x4410u) : 0x4444u;   // y-row 0 weight (low half of the pair)
     const uint32_t sel1 = contrib ? ((g & 1) ? 0x3244u : 0x4432u) : 0x4444u;   // y-row 1 weight (high half)
 
-    const int per_warp = (q1 - q0 + MMA_NW - 1) / MMA_NW;
-    const int wq0 = q0 + warp * per_warp;
-    const int wq1 = min(q1, wq0 + per_warp);
     // every warp passes the block barrier exactly once (after its first prologue, which overlaps the slab copy); a warp whose
     // query range is empty only waits for its copies
     int qb = wq0;
@@ -429,19 +446,26 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { const float4 t = __ldg(pa + k); aw[4 * k] = t.x; aw[4 * k + 1] = t.y; aw[4 * k + 2] = t.z; aw[4 * k + 3] = t.w; }
             } else {
-                const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(loc_or_proj) + row * fz.ld;
-                const uint4* pl = reinterpret_cast<const uint4*>(pr + m * (LP * 2));
-                const uint4* pa = reinterpret_cast<const uint4*>(pr + M * (LP * 2) + m * LP);
+                if (!first) stage_raw(qb);                               // (the first batch was requested at kernel start)
+                if (first) cp_async_wait_group<1>(); else cp_async_wait_all();   // group order: raw rows, then the slab
+                __syncwarp();
+                const uint4* pl = reinterpret_cast<const uint4*>(tab + lane * MMA_RAW_PITCH);
+                const uint4* pa = pl + 4;
+                uint4 raw[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) raw[k] = pl[k];
+                (void)pa;
+                __syncwarp();                                            // every lane holds its row: the region becomes the tap table
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint4 t = __ldg(pl + k);
+                    const uint4 t = raw[k];
                     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { ox[4 * k + i] = __uint_as_float(w4[i] << 16); oy[4 * k + i] = __uint_as_float(w4[i] & 0xffff0000u); }
                 }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const uint4 t = __ldg(pa + k);
+                    const uint4 t = raw[4 + k];
                     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { aw[8 * k + 2 * i] = __uint_as_float(w4[i] << 16); aw[8 * k + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u); }
