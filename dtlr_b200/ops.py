@@ -235,13 +235,15 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
     return (frames, newp) if want_new_pred else frames
 
 
-def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5):
+def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5, out=None, out2=None):
     """bf16 only, N = 256: y = LN(a @ w.T + bias (+ residual)); optional y2 = y + add2.  One tcgen05 kernel."""
     import ctypes
     M, K = a.shape
     assert w.shape[0] == 256 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
-    y = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device)
-    y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if add2 is not None else None
+    y = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if out is None else out
+    y2 = None
+    if add2 is not None:
+        y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if out2 is None else out2
     _call("dtlr_gemm_ln", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
           _p(gamma), _p(beta), ctypes.c_float(eps), _p(y), y.stride(0), _p(add2), _p(y2), add2.stride(0) if add2 is not None else 0,
           M, K, _st(a))
@@ -267,6 +269,8 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
 # measured in the full step (B200, B=64): 9.71 ms with the fused FFN kernel vs 9.54 ms with linear1 + linear2/LN (whose hidden
 # activation partly stays in the 126 MB L2) -- the single-CTA fused kernel is shared-memory-bandwidth bound; opt-in
 FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "0") != "0"
+# measured (one box, full step): no chunking 8.82 ms, 37888-row chunks 8.96, 18944: 9.32, 9472: 10.01 -> off by default
+FFN_CHUNK_ROWS = int(_os.environ.get("DTLR_FFN_CHUNK_ROWS", "0"))
 
 
 def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
@@ -282,4 +286,17 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
         _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
               ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _st(x))
         return (y, add(y, add2)) if add2 is not None else y
+    # experiment (opt-in): un-fused in row chunks that keep the hidden activation inside the 126 MB L2 (one reused buffer that
+    # linear2 reads back before it is evicted).  The saved HBM traffic does not pay for the extra launches, the smaller M per
+    # launch and the repeated weight-slice loads
+    if (FFN_CHUNK_ROWS > 0 and x.dtype == torch.bfloat16 and w2.shape[0] == 256 and hid >= LN_FUSE_MIN_K and M > FFN_CHUNK_ROWS):
+        y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
+        y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device) if add2 is not None else None
+        hbuf = torch.empty((FFN_CHUNK_ROWS, hid), dtype=torch.bfloat16, device=x.device)
+        for r0 in range(0, M, FFN_CHUNK_ROWS):
+            r1 = min(M, r0 + FFN_CHUNK_ROWS)
+            h = gemm(x[r0:r1], w1, b1, relu=1, out=hbuf[:r1 - r0])
+            gemm_ln(h, w2, b2, x[r0:r1], gamma, beta, add2[r0:r1] if add2 is not None else None, eps, out=y[r0:r1],
+                    out2=y2[r0:r1] if add2 is not None else None)
+        return (y, y2) if add2 is not None else y
     return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta, add2=add2)
