@@ -270,6 +270,224 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- single-pass version
+// The two-pass kernel above reads every score from TMEM twice and recomputes S.  Here every score is read ONCE:
+//  * FOUR 128-query tiles are in flight per CTA (FlashAttention-4 style ping-pong, taken further because the head dimension is
+//    only 32): 16 softmax warps, four per SM sub-partition;
+//  * a softmax thread owns one query row and takes a whole 64-key chunk into registers (one tcgen05.ld.32x32b.x64), so the row
+//    maximum needs no cross-warp exchange and the S buffer is handed back to the MMA warp right after the load;
+//  * online softmax with the running maximum: when a chunk raises it, the 128 x 32 fp32 output accumulator in TMEM is rescaled by
+//    the row's own thread (tcgen05.ld -> multiply -> tcgen05.st) -- cheap because the head dimension is 32 -- after the previous
+//    P.V has completed and before the next one is issued;
+//  * P is rounded to bf16 on the integer pipe (add 0x8000, high halves by one PRMT per pair; F2FP shares the SFU pipe with ex2)
+//    and goes straight into the 128B-swizzled K-major A-operand tile (one 16 KB buffer per tile).
+// TMEM: per tile 64 columns of S + 32 of O (4 x 96 = 384).  Warps: 0 TMA, 1 MMA issuer, 2-17 softmax (slot = (warp-2)/4).
+// Measured (B = 64, Q = 900, CUDA-graph timing incl. the 20 us V^T pre-pass): 269 us vs 311 us two-pass vs 254 us for the
+// mma.sync flash kernel, which therefore stays the default.  Probes (exponentials and / or TMEM loads replaced by constants)
+// move the time by < 15 %: neither the SFU nor the TMEM read path bounds it, the per-chunk chain of mbarrier hand-offs between
+// the softmax warps and the single MMA-issuing warp does (variants tried: 2 tiles with software-pipelined TMEM loads 419 us,
+// 3 tiles with double-buffered S 294 us).  DESIGN.md 3.3.
+constexpr int A2_KC = 64;                            // keys per chunk
+constexpr int A2_SLOTS = 4;                          // query tiles in flight
+constexpr int A2_SMEM_P = 16384;                     // P chunk of one tile: 128 rows x 128 B
+constexpr int A2_TM = 96;                            // TMEM columns per slot
+constexpr int A2_SMEM_TOTAL = AT_SMEM_K + AT_SMEM_V + A2_SLOTS * AT_SMEM_Q + A2_SLOTS * A2_SMEM_P + 1024 + 512;
+static_assert(A2_SMEM_TOTAL <= 232448, "attention kernel shared memory exceeds 227 KB");
+
+__global__ void __launch_bounds__(576, 1)
+mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+               __nv_bfloat16* __restrict__ out, int ld_o, int Q, int H, int k_off, float scale_log2) {
+    extern __shared__ unsigned char at_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)at_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sK = smem;
+    unsigned char* sV = sK + AT_SMEM_K;
+    unsigned char* sQ = sV + AT_SMEM_V;                      // [slots][128 rows x 64 B]
+    unsigned char* sP = sQ + A2_SLOTS * AT_SMEM_Q;           // [slots][128 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + A2_SLOTS * A2_SMEM_P);
+    uint64_t* kv_full = bars;                   // 1
+    uint64_t* q_full = bars + 1;                // [slots]
+    uint64_t* s_full = q_full + A2_SLOTS;       // commit: S chunk in TMEM
+    uint64_t* s_empty = s_full + A2_SLOTS;      // 4 arrivals: S chunk is in registers
+    uint64_t* p_full = s_empty + A2_SLOTS;      // 4 arrivals: P chunk in shared memory (and O rescaled)
+    uint64_t* p_empty = p_full + A2_SLOTS;      // commit: P.V of the chunk complete
+    uint64_t* o_full = p_empty + A2_SLOTS;      // commit: all P.V of the tile complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + A2_SLOTS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int tile0 = blockIdx.x * A2_SLOTS;
+    const int n_qtiles = (Q + AT_QT - 1) / AT_QT;
+    const int my_tiles = min(A2_SLOTS, n_qtiles - tile0);    // one tile per slot, one round per CTA
+    const int row_base = b * Q;
+    const int n_chunks = (Q + A2_KC - 1) / A2_KC;            // chunks that contain at least one real key
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < A2_SLOTS; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+            mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int sl = 0; sl < my_tiles; ++sl) {
+                mbar_expect_tx(&q_full[sl], AT_SMEM_Q);
+                tma_load_2d(sQ + sl * AT_SMEM_Q, &tmQ, &q_full[sl], h * 32, row_base + (tile0 + sl) * AT_QT);
+            }
+            mbar_expect_tx(kv_full, AT_SMEM_K + AT_SMEM_V);
+            for (int j = 0; j < 4; ++j)
+                tma_load_2d(sK + j * 256 * 64, &tmK, kv_full, k_off + h * 32, row_base + j * 256);
+            for (int j = 0; j < 16; ++j)
+                tma_load_2d(sV + j * 4096, &tmV, kv_full, j * 64, (b * H + h) * 32);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(kv_full, 0);
+        for (int sl = 0; sl < my_tiles; ++sl) mbar_wait(&q_full[sl], 0);
+        tcgen05_fence_after();
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+        for (int c = 0; c <= n_chunks; ++c) {
+            if (c < n_chunks) {
+                for (int sl = 0; sl < my_tiles; ++sl) {      // S_sl(c) = Q_sl K_c^T
+                    mbar_wait(&s_empty[sl], (c & 1) ^ 1);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t dq = make_sw64_kmajor_desc(aQ + sl * AT_SMEM_Q);
+                        const uint64_t dk = make_sw64_kmajor_desc(aK + c * A2_KC * 64);
+                        umma_bf16(tmem_base + sl * A2_TM, dq, dk, IDESC_S, 0);
+                        umma_bf16(tmem_base + sl * A2_TM, dq + 2, dk + 2, IDESC_S, 1);
+                        umma_commit(&s_full[sl]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (c >= 1) {
+                for (int sl = 0; sl < my_tiles; ++sl) {      // O_sl += P_sl(c-1) V_{c-1}
+                    mbar_wait(&p_full[sl], (c - 1) & 1);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t dp = make_sw128_kmajor_desc(aP + sl * A2_SMEM_P);
+                        const uint64_t dv = make_sw128_kmajor_desc(aV + (c - 1) * 4096);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + sl * A2_TM + A2_KC, dp + (uint64_t)(2 * k), dv + (uint64_t)(2 * k), IDESC_O,
+                                      (c == 1 && k == 0) ? 0u : 1u);
+                        umma_commit(&p_empty[sl]);
+                        if (c == n_chunks) umma_commit(&o_full[sl]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== softmax warps: slot sl, TMEM lane quarter qd, thread = query row =====
+        const int sl = (warp - 2) >> 2;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t tS = tmem_base + sl * A2_TM + ((uint32_t)(qd * 32) << 16), tO = tS + A2_KC;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        if (sl < my_tiles) {
+            const int q = (tile0 + sl) * AT_QT + row;
+            float m = -INFINITY, l = 0.f;
+            unsigned char* prow = sP + sl * A2_SMEM_P + row * 128;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&s_full[sl], c & 1);
+                tcgen05_fence_after();
+                uint32_t a[64];
+                tmem_ld64(tS, a);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sl]);                // the S buffer may be overwritten by the next chunk
+                const int key0 = c * A2_KC;
+                if (key0 + A2_KC > Q) {                                   // boundary chunk: keys beyond Q do not exist
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (key0 + j >= Q) a[j] = 0xff800000u;
+                }
+                float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                    c0 = fmaxf(c0, __uint_as_float(a[j])); c1 = fmaxf(c1, __uint_as_float(a[j + 1]));
+                    c2 = fmaxf(c2, __uint_as_float(a[j + 2])); c3 = fmaxf(c3, __uint_as_float(a[j + 3]));
+                }
+                const float m_new = fmaxf(fmaxf(m, fmaxf(c0, c1)), fmaxf(c2, c3));
+                const float alpha = ex2_approx((m - m_new) * scale_log2);     // 0 on the first chunk (m = -inf), 1 when unchanged
+                const float mxs = m_new * scale_log2;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {                             // P overwrites S in place: word j/2 = keys j, j+1
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(a[j]), scale_log2, -mxs)), p1 = ex2_approx(fmaf(__uint_as_float(a[j + 1]), scale_log2, -mxs));
+                    const float p2 = ex2_approx(fmaf(__uint_as_float(a[j + 2]), scale_log2, -mxs)), p3 = ex2_approx(fmaf(__uint_as_float(a[j + 3]), scale_log2, -mxs));
+                    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                    // round to nearest bf16 on the integer pipe (p >= 0, finite): + 0x8000, keep the high halves
+                    a[j / 2] = __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632);
+                    a[j / 2 + 1] = __byte_perm(__float_as_uint(p2) + 0x8000u, __float_as_uint(p3) + 0x8000u, 0x7632);
+                }
+                l = l * alpha + ((s0 + s1) + (s2 + s3));
+                m = m_new;
+                // the previous P.V has completed: P buffer free, O may be rescaled
+                mbar_wait(&p_empty[sl], (c & 1) ^ 1);
+                tcgen05_fence_after();
+                if (c > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+                    uint32_t o[32];
+                    tmem_ld32(tO, o);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                    tmem_st32(tO, o);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    *reinterpret_cast<uint4*>(prow + ((ch ^ swz) * 16)) = make_uint4(a[ch * 4], a[ch * 4 + 1], a[ch * 4 + 2], a[ch * 4 + 3]);
+                tcgen05_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[sl]);
+            }
+            // ---- epilogue: O / l -> bf16 -> global (64 bytes per row)
+            mbar_wait(&o_full[sl], 0);
+            tcgen05_fence_after();
+            uint32_t o[32];
+            tmem_ld32(tO, o);
+            if (q < Q) {
+                const float inv = 1.f / l;
+                uint4* op = reinterpret_cast<uint4*>(out + (size_t)(row_base + q) * ld_o + h * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[j * 8 + 2 * i]) * inv, __uint_as_float(o[j * 8 + 2 * i + 1]) * inv);
+                        w[i] = *reinterpret_cast<uint32_t*>(&t0);
+                    }
+                    op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 }  // namespace dtlr
 
 using namespace dtlr;
@@ -301,6 +519,16 @@ extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void
     const int n_qtiles = (Q + AT_QT - 1) / AT_QT;
     dim3 grid((n_qtiles + AT_TILES - 1) / AT_TILES, heads, B);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    if (!(g_debug_flags & 256)) {                 // single-pass kernel (default of this path); flag 256: the two-pass kernel
+        static bool configured2 = false;
+        if (!configured2) {
+            DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_TOTAL));
+            configured2 = true;
+        }
+        grid.x = (n_qtiles + A2_SLOTS - 1) / A2_SLOTS;
+        DTLR_CHECK_CUDA(launch_pdl(mha_tc2_kernel, grid, dim3(576), A2_SMEM_TOTAL, st, tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2));
+        return DTLR_OK;
+    }
     mha_tcgen05_kernel<<<grid, 576, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

@@ -22,10 +22,13 @@ def ref_attention(qk, v, B, Q, heads, mask=None):
 
 
 @pytest.mark.parametrize("Q", [900, 986, 100, 17, 1024])
-def test_self_attention_tcgen05_kernel(Q, monkeypatch):
-    """the tcgen05 / TMEM / TMA attention kernel (opt-in, DTLR_ATTN=tc) against torch fp32 on the same bf16 operands"""
-    from dtlr_b200 import ops
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_self_attention_tcgen05_kernel(Q, two_pass, monkeypatch):
+    """the tcgen05 / TMEM / TMA attention kernels (opt-in, DTLR_ATTN=tc) against torch fp32 on the same bf16 operands: the
+    single-pass kernel (4 tiles in flight, online softmax with TMEM rescale) and the two-pass kernel (dtlr_debug_flags(256))"""
+    from dtlr_b200 import ops, _lib
     monkeypatch.setattr(ops, "ATTN_IMPL", "tc")
+    _lib.lib().dtlr_debug_flags(256 if two_pass else 0)
     B, heads, d = 3, 8, 256
     g = torch.Generator(device="cuda").manual_seed(Q + 1)
     qk = (torch.randn(B * Q, 2 * d, device="cuda", generator=g) * 1.5).bfloat16()
@@ -33,6 +36,7 @@ def test_self_attention_tcgen05_kernel(Q, monkeypatch):
     before = ops.L.LAUNCHES
     out = ops.mha_self_attention(qk, d, v, None, B, Q, heads, d // heads)
     assert ops.L.LAUNCHES - before == 2          # transpose pre-pass + tcgen05 kernel, not the fallback
+    _lib.lib().dtlr_debug_flags(0)
     ref = ref_attention(qk, v, B, Q, heads)
     assert (out.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
 

@@ -1,14 +1,18 @@
+"""Decoder self-attention at BASELINE config-2 size (B=64, Q=900, 8 heads x 32): the mma.sync flash kernel (default), the
+single-pass tcgen05 kernel (DTLR_ATTN=tc) and the two-pass tcgen05 kernel (dtlr_debug_flags(256)).  CUDA-graph timing."""
 import json, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dtlr_b200 import ops
+from dtlr_b200 import ops, _lib
+from gemm_probe_util import timeit
+
 B, Q, heads, d = 64, 900, 8, 256
-qk = torch.randn(B * Q, 2 * d, device="cuda").bfloat16(); v = torch.randn(B * Q, d, device="cuda").bfloat16()
-for _ in range(3): ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10): ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32)
-e1.record(); torch.cuda.synchronize()
-us = e0.elapsed_time(e1) * 100
+qk = torch.randn(B * Q, 2 * d, device="cuda").bfloat16()
+v = torch.randn(B * Q, d, device="cuda").bfloat16()
 fl = 4.0 * B * heads * Q * Q * 32
-print(json.dumps({"kernel": "mha_flash_bf16", "us": round(us, 1), "TFLOPs": round(fl / us / 1e6, 1)}))
+for name, impl, flags in (("mma.sync flash", "flash", 0), ("tcgen05 single-pass", "tc", 0), ("tcgen05 two-pass", "tc", 256)):
+    ops.ATTN_IMPL = impl
+    _lib.lib().dtlr_debug_flags(flags)
+    us = timeit(lambda i: ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32), iters=10)
+    _lib.lib().dtlr_debug_flags(0)
+    print(json.dumps({"kernel": name, "us": round(us, 1), "TFLOPs": round(fl / us / 1e6, 1)}), flush=True)
