@@ -42,17 +42,21 @@ struct FfnArgs {
     int dbg;              // probes (dtlr_debug_flags): 256 no E1 work, 512 no G1 MMAs, 1024 no G2 MMAs, 2048 no final epilogue work
 };
 
-struct FfnSmem {
+// HTM: the hidden chunk goes back into TMEM (bf16, in place over its own fp32 accumulator) and feeds G2 as a TMEM A operand:
+// no shared-memory round trip for H (-1.5 MB of shared-memory traffic per tile) and 64 KB more for the weight ring
+template <bool HTM>
+struct FfnSmemT {
     static constexpr int XS = 4 * FF_STAGE;                 // X tile: 4 k-blocks of 128 x 64
-    static constexpr int HS = 2 * 2 * FF_STAGE;             // hidden chunk, A-operand layout, double-buffered (2 k-blocks each)
-    static constexpr int RING = FF_NS * FF_STAGE;
+    static constexpr int HS = HTM ? 0 : 2 * 2 * FF_STAGE;   // hidden chunk, A-operand layout, double-buffered (2 k-blocks each)
+    static constexpr int NS = HTM ? 9 : FF_NS;              // ring depth
+    static constexpr int RING = NS * FF_STAGE;
     static constexpr int B1 = FF_MAX_HID * 4;
     static constexpr int VEC = 3 * FF_D * 4;                // b2, gamma, beta
     static constexpr int STAT = FF_BM * 2 * 2 * 4;          // per row, per column half: sum, sum of squares
     static constexpr int BAR = 512;
     static constexpr int TOTAL = 1024 + XS + HS + RING + B1 + VEC + STAT + BAR;
+    static_assert(TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
 };
-static_assert(FfnSmem::TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
 
 __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -60,10 +64,13 @@ __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float ff_round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+template <bool HTM>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
     extern __shared__ unsigned char smem_raw[];
+    using FfnSmem = FfnSmemT<HTM>;
+    constexpr int NS = FfnSmem::NS;
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* xs = smem;
     unsigned char* hs = xs + FfnSmem::XS;
@@ -76,9 +83,9 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + FF_BM * 4);
     uint64_t* x_full = bars;             // [1]
     uint64_t* x_free = bars + 1;         // [1]  8 arrivals (epilogue warps): the X tile (output staging) may be overwritten
-    uint64_t* w_full = bars + 2;         // [FF_NS]
-    uint64_t* w_empty = w_full + FF_NS;  // [FF_NS]
-    uint64_t* hacc_full = w_empty + FF_NS;   // [2] G1 complete
+    uint64_t* w_full = bars + 2;         // [NS]
+    uint64_t* w_empty = w_full + NS;     // [NS]
+    uint64_t* hacc_full = w_empty + NS;  // [2] G1 complete
     uint64_t* hacc_free = hacc_full + 2;     // [2] 8 arrivals: TMEM hidden accumulator drained
     uint64_t* hs_full = hacc_free + 2;       // [2] 8 arrivals: hidden chunk written to shared memory
     uint64_t* hs_free = hs_full + 2;         // [2] G2 complete
@@ -97,7 +104,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tma_prefetch_desc(&tmO);
         mbar_init(x_full, 1);
         mbar_init(x_free, 8);
-        for (int s = 0; s < FF_NS; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
         }
@@ -122,6 +129,8 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tm_y = tmem_base;                 // columns [0, 256)
     const uint32_t tm_h = tmem_base + 256;           // 2 x 128 columns
 
@@ -136,16 +145,16 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 for (int j = 0; j <= NJ; ++j) {
                     if (j < NJ) {
                         for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
-                            const int s = it % FF_NS;
-                            mbar_wait(&w_empty[s], ((it / FF_NS) & 1) ^ 1);
+                            const int s = it % NS;
+                            mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
                             tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
                         }
                     }
                     if (j >= 1) {
                         for (int q = 0; q < 4; ++q, ++it) {                 // W2 output rows (q&1)*128.., hidden columns of chunk j-1
-                            const int s = it % FF_NS;
-                            mbar_wait(&w_empty[s], ((it / FF_NS) & 1) ^ 1);
+                            const int s = it % NS;
+                            mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
                             tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
                         }
@@ -163,11 +172,13 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int j = 0; j <= NJ; ++j) {
                 if (j < NJ) {
                     const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
-                    mbar_wait(&hacc_free[b], (u & 1) ^ 1);                   // epilogue has drained this hidden accumulator
-                    tcgen05_fence_after();
+                    if (!HTM) {                                              // (HTM: ordered behind G2 of chunk gj-2 by issue order)
+                        mbar_wait(&hacc_free[b], (u & 1) ^ 1);               // epilogue has drained this hidden accumulator
+                        tcgen05_fence_after();
+                    }
                     for (int kb = 0; kb < 4; ++kb, ++it) {
-                        const int s = it % FF_NS;
-                        mbar_wait(&w_full[s], (it / FF_NS) & 1);
+                        const int s = it % NS;
+                        mbar_wait(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         if (elect_one()) {
                             const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + kb * FF_STAGE));
@@ -189,9 +200,9 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     if (j == 1) mbar_wait(y_free, (t & 1) ^ 1);              // previous tile's output accumulator drained
                     tcgen05_fence_after();
                     for (int q = 0; q < 4; ++q, ++it) {
-                        const int s = it % FF_NS;
+                        const int s = it % NS;
                         const int kb2 = q >> 1, half = q & 1;
-                        mbar_wait(&w_full[s], (it / FF_NS) & 1);
+                        mbar_wait(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         if (elect_one()) {
                             const uint64_t da = make_sw128_kmajor_desc(smem_u32(hs + b * (2 * FF_STAGE) + kb2 * FF_STAGE));
@@ -199,8 +210,12 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if (a.dbg & 1024) break;
-                                umma_bf16(tm_y + half * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
-                                          (j > 1) || kb2 > 0 || k > 0);
+                                if (HTM)   // A = bf16 hidden chunk in TMEM: 64 hidden units of k-block kb2 = 32 columns, 8 per K = 16 step
+                                    umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
+                                                 (j > 1) || kb2 > 0 || k > 0);
+                                else
+                                    umma_bf16(tm_y + half * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                              (j > 1) || kb2 > 0 || k > 0);
                             }
                             umma_commit(&w_empty[s]);
                             if (q == 3) {
@@ -249,6 +264,16 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     const float v2 = fmaxf(__uint_as_float(acc[c + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(acc[c + 3]) + b4.w, 0.f);
                     pk[c / 2] = ff_pack_bf16x2(v0, v1);
                     pk[c / 2 + 1] = ff_pack_bf16x2(v2, v3);
+                }
+                if (HTM) {
+                    // in place: this warp's 64 hidden units -> 32 packed columns at hsel*32 of the accumulator it came from; the
+                    // partner warp of the lane quarter (other 64 columns) must have finished ITS load of those columns first
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+                    tmem_st32(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 32), pk);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&hs_full[b]);
+                    continue;
                 }
                 mbar_wait(&hs_free[b], (u & 1) ^ 1);                         // G2 of chunk gj-2 has finished reading this buffer
                 unsigned char* dst = hs + b * (2 * FF_STAGE) + hsel * FF_STAGE + row * 128;
@@ -369,13 +394,16 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmemT<false>::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmemT<true>::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
     const int grid = num_m < sm_count() ? num_m : sm_count();
     const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags};
-    ffn_ln_tcgen05_kernel<<<grid, 320, FfnSmem::TOTAL, (cudaStream_t)stream>>>(tx, tw1, tw2, to, a);
-    DTLR_CHECK_LAUNCH();
+    if (g_debug_flags & 4096)        // hidden chunk through shared memory (first version); default: through TMEM
+        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false>, dim3(grid), dim3(320), FfnSmemT<false>::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    else
+        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<true>, dim3(grid), dim3(320), FfnSmemT<true>::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
     return DTLR_OK;
 }

@@ -266,9 +266,9 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
     return add_layernorm(x, None, gamma, beta, add2=add2)
 
 
-# measured in the full step (B200, B=64): 9.71 ms with the fused FFN kernel vs 9.54 ms with linear1 + linear2/LN (whose hidden
-# activation partly stays in the 126 MB L2) -- the single-CTA fused kernel is shared-memory-bandwidth bound; opt-in
-FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "0") != "0"
+# fused FFN block kernel (csrc/ffn.cu).  Measured in the full step (B200, B=64, same box): with the hidden chunk fed to linear2 from
+# TMEM 8.77 ms vs 8.84 ms for linear1 + linear2/LN (the first version, hidden chunk through shared memory, lost 9.71 vs 9.54)
+FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "1") != "0"
 # measured (one box, full step): no chunking 8.82 ms, 37888-row chunks 8.96, 18944: 9.32, 9472: 10.01 -> off by default
 FFN_CHUNK_ROWS = int(_os.environ.get("DTLR_FFN_CHUNK_ROWS", "0"))
 
