@@ -6,19 +6,25 @@
 // :876-880 (decoder layer); d_model 256, dim_feedforward 2048, ReLU, dropout 0, post-norm.
 //
 // Why fused: as two GEMMs the hidden activation (M x 2048 bf16 = 239 MB at B = 64) is written to HBM and read back; measured
-// (tools/gemm_probe.py) linear1 is bound by that write (64 us, HBM floor 42 us) and linear2 by re-reading it (~95 us), 159 us
-// per layer for 122 GFLOP.  Here the hidden activation never leaves the SM:
+// (tools/gemm_probe.py) linear1 is bound by that write (64 us, HBM floor 42 us) and linear2 by re-reading it (78-90 us).
+// Here the hidden activation never leaves the SM -- and never touches shared memory either:
 //
-//   per 128-row tile of X (resident in shared memory, 64 KB, also the residual and finally the output staging):
+//   per 128-row tile of X (shared memory, 64 KB, double-buffered: A operand of linear1, the residual, finally the output staging):
 //     for each chunk j of 128 hidden units (HID / 128 chunks, software-pipelined by one chunk):
-//       G1(j):  Hacc[j&1] (TMEM, 128 x 128 fp32)  = X . W1[j]^T                      16 x tcgen05.mma 128x128x16
-//       E1(j):  8 epilogue warps: TMEM -> +b1 -> ReLU -> bf16 -> shared memory Hs[j&1] in the K-major 128B-swizzled
-//               A-operand layout (conflict-free 16-byte stores, thread = row)
-//       G2(j):  Yacc (TMEM, 128 x 256 fp32)      += Hs[j&1] . W2[:, j]^T              16 x tcgen05.mma 128x128x16
-//     final:   Yacc + b2 + X -> LayerNorm (row statistics: thread = row, the two column halves meet in shared memory)
-//              -> bf16 written over the X tile in place -> TMA store.
+//       G1(j):  Hacc[j&1] (TMEM, 128 x 128 fp32)  = X . W1[j]^T                      16 x tcgen05.mma 128x128x16 (SS)
+//       E1(j):  8 epilogue warps: tcgen05.ld -> +b1 -> ReLU -> bf16 -> tcgen05.st back IN PLACE over the first 64 columns of
+//               the accumulator it came from (thread = row; the two warps of a lane quarter meet at a 64-thread barrier)
+//       G2(j):  Yacc (TMEM, 128 x 256 fp32)      += H[j&1] . W2[:, j]^T               16 x tcgen05.mma 128x128x16 with the A
+//               operand read from TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): no shared-memory round trip for H
+//     final:   Yacc + b2 + X -> bf16 (packed in registers, ONE TMEM read; the accumulator is released to the next tile at once)
+//              -> LayerNorm (row statistics: thread = row, the two column halves meet in shared memory) -> written over the X
+//              tile in place -> TMA store.  The next tile's X is already resident in the other buffer and its G1 runs meanwhile.
 //   W1 / W2 chunks (2 MB per tile in total, L2-resident) stream through a 5-stage TMA ring of 16 KB stages.
-//   TMEM: Yacc 256 columns + 2 x 128 columns of Hacc = 512.
+//   TMEM: Yacc 256 columns + 2 x 128 columns of Hacc / H = 512.
+//
+// Measured history (M = 58368, CUDA-graph timing): hidden chunk through shared memory 146 us (shared-memory-bandwidth bound:
+// 6.5 MB of operand / TMA / epilogue traffic per tile) -> through TMEM 135 us -> see DESIGN.md 3.2b for the current number;
+// un-fused linear1 + linear2/LN: 147 us.
 //
 // Warp roles as in gemm.cu: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue.
 #include "tc_common.cuh"
@@ -42,55 +48,44 @@ struct FfnArgs {
     int dbg;              // probes (dtlr_debug_flags): 256 no E1 work, 512 no G1 MMAs, 1024 no G2 MMAs, 2048 no final epilogue work
 };
 
-// HTM: the hidden chunk goes back into TMEM (bf16, in place over its own fp32 accumulator) and feeds G2 as a TMEM A operand:
-// no shared-memory round trip for H (-1.5 MB of shared-memory traffic per tile) and 64 KB more for the weight ring
-template <bool HTM>
-struct FfnSmemT {
-    static constexpr int XS = 4 * FF_STAGE;                 // X tile: 4 k-blocks of 128 x 64
-    static constexpr int HS = HTM ? 0 : 2 * 2 * FF_STAGE;   // hidden chunk, A-operand layout, double-buffered (2 k-blocks each)
-    static constexpr int NS = HTM ? 9 : FF_NS;              // ring depth
-    static constexpr int RING = NS * FF_STAGE;
+struct FfnSmem {
+    static constexpr int XS = 4 * FF_STAGE;                 // one X tile: 4 k-blocks of 128 x 64
+    static constexpr int RING = FF_NS * FF_STAGE;
     static constexpr int B1 = FF_MAX_HID * 4;
     static constexpr int VEC = 3 * FF_D * 4;                // b2, gamma, beta
     static constexpr int STAT = FF_BM * 2 * 2 * 4;          // per row, per column half: sum, sum of squares
     static constexpr int BAR = 512;
-    static constexpr int TOTAL = 1024 + XS + HS + RING + B1 + VEC + STAT + BAR;
-    static_assert(TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
+    static constexpr int TOTAL = 1024 + 2 * XS + RING + B1 + VEC + STAT + BAR;
 };
+static_assert(FfnSmem::TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
 
 __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ float ff_round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <bool HTM>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    using FfnSmem = FfnSmemT<HTM>;
-    constexpr int NS = FfnSmem::NS;
+    constexpr int NS = FF_NS;
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* xs = smem;
-    unsigned char* hs = xs + FfnSmem::XS;
-    unsigned char* ring = hs + FfnSmem::HS;
+    unsigned char* xs = smem;                                // [2][4 k-blocks][128 rows x 128 B]
+    unsigned char* ring = xs + 2 * FfnSmem::XS;
     float* b1_s = reinterpret_cast<float*>(ring + FfnSmem::RING);
     float* b2_s = b1_s + FF_MAX_HID;
     float* gamma_s = b2_s + FF_D;
     float* beta_s = gamma_s + FF_D;
     float* stat_s = beta_s + FF_D;                           // [128 rows][2 halves][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + FF_BM * 4);
-    uint64_t* x_full = bars;             // [1]
-    uint64_t* x_free = bars + 1;         // [1]  8 arrivals (epilogue warps): the X tile (output staging) may be overwritten
-    uint64_t* w_full = bars + 2;         // [NS]
+    uint64_t* x_full = bars;             // [2]
+    uint64_t* x_free = bars + 2;         // [2]  8 arrivals (epilogue warps): the X tile (output staging) may be overwritten
+    uint64_t* w_full = bars + 4;         // [NS]
     uint64_t* w_empty = w_full + NS;     // [NS]
-    uint64_t* hacc_full = w_empty + NS;  // [2] G1 complete
-    uint64_t* hacc_free = hacc_full + 2;     // [2] 8 arrivals: TMEM hidden accumulator drained
-    uint64_t* hs_full = hacc_free + 2;       // [2] 8 arrivals: hidden chunk written to shared memory
-    uint64_t* hs_free = hs_full + 2;         // [2] G2 complete
-    uint64_t* y_full = hs_free + 2;          // [1]
-    uint64_t* y_free = y_full + 1;           // [1] 8 arrivals
+    uint64_t* hacc_full = w_empty + NS;  // [2] G1 complete: fp32 hidden chunk in TMEM
+    uint64_t* h_full = hacc_full + 2;    // [2] 8 arrivals: bf16 hidden chunk written back to TMEM
+    uint64_t* y_full = h_full + 2;       // [1] all G2 of the tile complete
+    uint64_t* y_free = y_full + 1;       // [1] 8 arrivals: output accumulator read out
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(y_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,17 +97,15 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tma_prefetch_desc(&tmW1);
         tma_prefetch_desc(&tmW2);
         tma_prefetch_desc(&tmO);
-        mbar_init(x_full, 1);
-        mbar_init(x_free, 8);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&x_full[b], 1);
+            mbar_init(&x_free[b], 8);
+            mbar_init(&hacc_full[b], 1);
+            mbar_init(&h_full[b], 8);
+        }
         for (int s = 0; s < NS; ++s) {
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&hacc_full[b], 1);
-            mbar_init(&hacc_free[b], 8);
-            mbar_init(&hs_full[b], 8);
-            mbar_init(&hs_free[b], 1);
         }
         mbar_init(y_full, 1);
         mbar_init(y_free, 8);
@@ -135,14 +128,20 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t tm_h = tmem_base + 256;           // 2 x 128 columns
 
     if (warp == 0) {
-        // ===== TMA producer: X tile, then the weight chunks in exactly the order the MMA warp consumes them
+        // ===== TMA producer: weight chunks in exactly the order the MMA warp consumes them; the X tile of the NEXT row tile is
+        //       requested half way through the current one (its buffer was released by the tile before)
         if (elect_one()) {
             uint32_t it = 0, t = 0;
+            auto load_x = [&](int mt, uint32_t tt) {
+                const uint32_t xb = tt & 1;
+                mbar_wait(&x_free[xb], ((tt >> 1) & 1) ^ 1);
+                mbar_expect_tx(&x_full[xb], FfnSmem::XS);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
+            };
+            if ((int)blockIdx.x < num_m) load_x(blockIdx.x, 0);
             for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t) {
-                mbar_wait(x_free, (t & 1) ^ 1);
-                mbar_expect_tx(x_full, FfnSmem::XS);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + kb * FF_STAGE, &tmX, x_full, kb * 64, mt * FF_BM);
                 for (int j = 0; j <= NJ; ++j) {
+                    if (j == NJ / 2 && mt + (int)gridDim.x < num_m) load_x(mt + gridDim.x, t + 1);
                     if (j < NJ) {
                         for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
                             const int s = it % NS;
@@ -163,25 +162,23 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: G1(j) one chunk ahead of G2(j-1)
+        // ===== MMA issuer: G1(j) one chunk ahead of G2(j-1).  Hacc[b] is rewritten by G1(j+2) only after G2(j), its last reader, in
+        //       issue order; E1(j) finished with it before h_full(j), which G2(j) waited for
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
         uint32_t it = 0, g = 0, t = 0;
         for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
-            mbar_wait(x_full, t & 1);
+            const uint32_t xb = t & 1;
+            mbar_wait(&x_full[xb], (t >> 1) & 1);
             tcgen05_fence_after();
             for (int j = 0; j <= NJ; ++j) {
                 if (j < NJ) {
-                    const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
-                    if (!HTM) {                                              // (HTM: ordered behind G2 of chunk gj-2 by issue order)
-                        mbar_wait(&hacc_free[b], (u & 1) ^ 1);               // epilogue has drained this hidden accumulator
-                        tcgen05_fence_after();
-                    }
+                    const uint32_t b = (g + j) & 1;
                     for (int kb = 0; kb < 4; ++kb, ++it) {
                         const int s = it % NS;
                         mbar_wait(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + kb * FF_STAGE));
+                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + xb * FfnSmem::XS + kb * FF_STAGE));
                             const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -196,8 +193,8 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 }
                 if (j >= 1) {
                     const uint32_t gj = g + j - 1, b = gj & 1, u = gj >> 1;
-                    mbar_wait(&hs_full[b], u & 1);                           // hidden chunk j-1 is in shared memory
-                    if (j == 1) mbar_wait(y_free, (t & 1) ^ 1);              // previous tile's output accumulator drained
+                    mbar_wait(&h_full[b], u & 1);                            // bf16 hidden chunk j-1 is in TMEM
+                    if (j == 1) mbar_wait(y_free, (t & 1) ^ 1);              // previous tile's output accumulator read out
                     tcgen05_fence_after();
                     for (int q = 0; q < 4; ++q, ++it) {
                         const int s = it % NS;
@@ -205,23 +202,16 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         mbar_wait(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         if (elect_one()) {
-                            const uint64_t da = make_sw128_kmajor_desc(smem_u32(hs + b * (2 * FF_STAGE) + kb2 * FF_STAGE));
                             const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if (a.dbg & 1024) break;
-                                if (HTM)   // A = bf16 hidden chunk in TMEM: 64 hidden units of k-block kb2 = 32 columns, 8 per K = 16 step
-                                    umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
-                                                 (j > 1) || kb2 > 0 || k > 0);
-                                else
-                                    umma_bf16(tm_y + half * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
-                                              (j > 1) || kb2 > 0 || k > 0);
+                                // A = bf16 hidden chunk in TMEM: the 64 hidden units of k-block kb2 = 32 columns, 8 per K = 16 step
+                                umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
+                                             (j > 1) || kb2 > 0 || k > 0);
                             }
                             umma_commit(&w_empty[s]);
-                            if (q == 3) {
-                                umma_commit(&hs_free[b]);
-                                if (j == NJ) umma_commit(y_full);
-                            }
+                            if (q == 3 && j == NJ) umma_commit(y_full);
                         }
                         __syncwarp();
                     }
@@ -237,7 +227,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         uint32_t g = 0, t = 0;
         for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
-            // ---- E1: hidden chunk j: +b1, ReLU, bf16, into the A-operand tile of G2
+            // ---- E1: hidden chunk j: +b1, ReLU, bf16, back into TMEM in place
             for (int j = 0; j < NJ; ++j) {
                 const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
                 mbar_wait(&hacc_full[b], u & 1);
@@ -245,16 +235,11 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 if (a.dbg & 256) {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&hacc_free[b]);
-                    mbar_wait(&hs_free[b], (u & 1) ^ 1);
-                    if (lane == 0) mbar_arrive(&hs_full[b]);
+                    if (lane == 0) mbar_arrive(&h_full[b]);
                     continue;
                 }
                 uint32_t acc[64];
                 tmem_ld64(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 64), acc);
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hacc_free[b]);
                 const float* bp = b1_s + j * FF_HC + hsel * 64;
                 uint32_t pk[32];
 #pragma unroll
@@ -265,53 +250,57 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     pk[c / 2] = ff_pack_bf16x2(v0, v1);
                     pk[c / 2 + 1] = ff_pack_bf16x2(v2, v3);
                 }
-                if (HTM) {
-                    // in place: this warp's 64 hidden units -> 32 packed columns at hsel*32 of the accumulator it came from; the
-                    // partner warp of the lane quarter (other 64 columns) must have finished ITS load of those columns first
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-                    tmem_st32(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 32), pk);
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&hs_full[b]);
-                    continue;
-                }
-                mbar_wait(&hs_free[b], (u & 1) ^ 1);                         // G2 of chunk gj-2 has finished reading this buffer
-                unsigned char* dst = hs + b * (2 * FF_STAGE) + hsel * FF_STAGE + row * 128;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    *reinterpret_cast<uint4*>(dst + ((k ^ swz) * 16)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-                fence_proxy_async();
+                // this warp's 64 hidden units -> 32 packed columns at hsel*32 of the accumulator; the partner warp of the lane quarter
+                // (the other 64 fp32 columns, which the columns written here overlap) must have finished ITS load first
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+                tmem_st32(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 32), pk);
+                tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&hs_full[b]);
+                if (lane == 0) mbar_arrive(&h_full[b]);
             }
             // ---- final: Yacc + b2 + X -> LayerNorm -> bf16 over the X tile -> TMA store
-            mbar_wait(x_full, t & 1);
+            const uint32_t xb = t & 1;
+            unsigned char* xt = xs + xb * FfnSmem::XS;
+            mbar_wait(&x_full[xb], (t >> 1) & 1);
             mbar_wait(y_full, t & 1);
             tcgen05_fence_after();
             if (a.dbg & 2048) {
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(y_free); mbar_arrive(x_free); }
+                if (lane == 0) { mbar_arrive(y_free); mbar_arrive(&x_free[xb]); }
                 continue;
             }
             float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+            uint32_t xp[64];                                 // the row's 128 pre-norm values of this warp, packed bf16x2
+#pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
-                uint32_t acc[64];
-                tmem_ld64(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64), acc);
-                const unsigned char* xrow = xs + (hsel * 2 + cb) * FF_STAGE + row * 128;
-                const float* bp = b2_s + hsel * 128 + cb * 64;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint4 r4 = *reinterpret_cast<const uint4*>(xrow + ((k ^ swz) * 16));
-                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t acc[32];
+                    tmem_ld32(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64 + hf * 32), acc);
+                    if (cb == 1 && hf == 1) {                // the output accumulator is in registers: the next tile's G2 may start
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(y_free);
+                    }
+                    const unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                    const float* bp = b2_s + hsel * 128 + cb * 64 + hf * 32;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float x0 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i]) + bp[k * 8 + 2 * i] + __uint_as_float(rw[i] << 16));
-                        const float x1 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i + 1]) + bp[k * 8 + 2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u));
-                        sum += x0 + x1;
-                        sq = fmaf(x0, x0, sq);
-                        sq = fmaf(x1, x1, sq);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = hf * 4 + kk;
+                        const uint4 r4 = *reinterpret_cast<const uint4*>(xrow + ((k ^ swz) * 16));
+                        const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bp[kk * 8 + 2 * i] + __uint_as_float(rw[i] << 16);
+                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bp[kk * 8 + 2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
+                            const uint32_t pk = ff_pack_bf16x2(x0, x1);
+                            xp[cb * 32 + k * 4 + i] = pk;
+                            const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
+                            sum += y0 + y1;
+                            sq = fmaf(y0, y0, sq);
+                            sq = fmaf(y1, y1, sq);
+                        }
                     }
                 }
             }
@@ -321,46 +310,38 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const float mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
             const float var = fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
             const float rstd = rsqrtf(var + a.eps);
-#pragma unroll 1
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // statistics consumed before the next tile overwrites them
+#pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
-                uint32_t acc[64];
-                tmem_ld64(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64), acc);
-                if (cb == 1) {                                               // last TMEM read of the output accumulator
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(y_free);
-                }
-                unsigned char* xrow = xs + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
                 const int c0 = hsel * 128 + cb * 64;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    uint4* p = reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16));
-                    const uint4 r4 = *p;
-                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
                     uint32_t o[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
+                        const uint32_t pk = xp[cb * 32 + k * 4 + i];
                         const int c = c0 + k * 8 + 2 * i;
-                        const float x0 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i]) + b2_s[c] + __uint_as_float(rw[i] << 16));
-                        const float x1 = ff_round_bf16(__uint_as_float(acc[k * 8 + 2 * i + 1]) + b2_s[c + 1] + __uint_as_float(rw[i] & 0xffff0000u));
-                        o[i] = ff_pack_bf16x2((x0 - mean) * rstd * gamma_s[c] + beta_s[c], (x1 - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
+                        o[i] = ff_pack_bf16x2((__uint_as_float(pk << 16) - mean) * rstd * gamma_s[c] + beta_s[c],
+                                              (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
                     }
-                    *p = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 for (int cb = 0; cb < 2; ++cb)
-                    tma_store_2d(&tmO, xs + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, mt * FF_BM + qd * 32);
+                    tma_store_2d(&tmO, xt + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, mt * FF_BM + qd * 32);
                 tma_store_commit();
-                tma_store_wait_read<0>();                                    // the X tile may now be refilled
-                mbar_arrive(x_free);
+                tma_store_wait_read<0>();                                    // this X buffer may now be refilled
+                mbar_arrive(&x_free[xb]);
             }
             __syncwarp();
         }
         if (lane == 0) tma_store_wait<0>();
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
@@ -394,16 +375,12 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmemT<false>::TOTAL));
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmemT<true>::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
     const int grid = num_m < sm_count() ? num_m : sm_count();
     const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags};
-    if (g_debug_flags & 4096)        // hidden chunk through shared memory (first version); default: through TMEM
-        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false>, dim3(grid), dim3(320), FfnSmemT<false>::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
-    else
-        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<true>, dim3(grid), dim3(320), FfnSmemT<true>::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
     return DTLR_OK;
 }

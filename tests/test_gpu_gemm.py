@@ -133,8 +133,7 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
 
 
 @pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048)])
-@pytest.mark.parametrize("h_via_smem", [False, True])
-def test_fused_ffn_block(M, hid, h_via_smem):
+def test_fused_ffn_block(M, hid):
     """dtlr_ffn_ln: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM / shared memory) vs
     torch fp32 on the same bf16 operands with the hidden activation rounded to bf16 (as both our paths do), and vs the
     un-fused kernels (linear1 GEMM + linear2/LayerNorm GEMM)."""
@@ -148,14 +147,11 @@ def test_fused_ffn_block(M, hid, h_via_smem):
     b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
     gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
     beta = 0.1 * torch.randn(256, device="cuda", generator=g)
-    from dtlr_b200 import _lib
-    ops.FFN_FUSED = True
-    _lib.lib().dtlr_debug_flags(4096 if h_via_smem else 0)      # hidden chunk through shared memory / through TMEM (default)
+    saved, ops.FFN_FUSED = ops.FFN_FUSED, True
     try:
         y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
     finally:
-        ops.FFN_FUSED = False
-        _lib.lib().dtlr_debug_flags(0)
+        ops.FFN_FUSED = saved
     h = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
     pre = (h @ w2.float().T + b2 + x.float()).bfloat16().float()
     ref = F.layer_norm(pre, (256,), gamma, beta, 1e-5)
@@ -164,6 +160,7 @@ def test_fused_ffn_block(M, hid, h_via_smem):
     assert (y.float() - ref).abs().mean().item() < 4e-3
     un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
+    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining)
 
 
 @pytest.mark.parametrize("M,N,K,out_dtype", [(57600 * 2, 166, 256, torch.float32), (58368, 166, 256, torch.float32),
