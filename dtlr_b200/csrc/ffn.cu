@@ -64,6 +64,10 @@ __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// CL: launched as clusters of two CTAs that stream the SAME weight chunks: each ring stage is fetched from L2 once by one CTA
+// of the pair (alternating) and multicast into both, halving the L2 -> SM traffic (912 MB per call otherwise); a stage is refilled
+// once BOTH tensor cores have released it (multicast tcgen05.commit on both CTAs' w_empty barriers)
+template <bool CL>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
@@ -91,6 +95,11 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (a.M + FF_BM - 1) / FF_BM;
     const int NJ = a.HID / FF_HC;
+    // CL: both CTAs of a pair (even grid, rank = blockIdx.x & 1) must consume the same number of weight chunks: the pair works on
+    // tiles (2p, 2p+1), (2p, 2p+1) + grid, ... while the EVEN tile exists; an odd tile == num_m is a ghost (X rows zero-filled by
+    // TMA, stores clipped by TMA)
+    auto more = [&](int mt) { return CL ? ((mt & ~1) < num_m) : (mt < num_m); };
+    const uint32_t cta_rank = CL ? cluster_cta_rank() : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
@@ -105,7 +114,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         for (int s = 0; s < NS; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&w_empty[s], 1);
+            mbar_init(&w_empty[s], CL ? 2 : 1);
         }
         mbar_init(y_full, 1);
         mbar_init(y_free, 8);
@@ -120,6 +129,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();                      // the peer's barriers are initialised before anything is multicast at them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
@@ -138,16 +148,17 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_expect_tx(&x_full[xb], FfnSmem::XS);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
             };
-            if ((int)blockIdx.x < num_m) load_x(blockIdx.x, 0);
-            for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t) {
+            if (more(blockIdx.x)) load_x(blockIdx.x, 0);
+            for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t) {
                 for (int j = 0; j <= NJ; ++j) {
-                    if (j == NJ / 2 && mt + (int)gridDim.x < num_m) load_x(mt + gridDim.x, t + 1);
+                    if (j == NJ / 2 && more(mt + (int)gridDim.x)) load_x(mt + gridDim.x, t + 1);
                     if (j < NJ) {
                         for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
                             const int s = it % NS;
                             mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
-                            tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
+                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
+                            else if ((it & 1) == cta_rank) tma_load_2d_multicast(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC, 3);
                         }
                     }
                     if (j >= 1) {
@@ -155,7 +166,9 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             const int s = it % NS;
                             mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
-                            tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                            else if ((it & 1) == cta_rank)
+                                tma_load_2d_multicast(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128, 3);
                         }
                     }
                 }
@@ -166,7 +179,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         //       issue order; E1(j) finished with it before h_full(j), which G2(j) waited for
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
         uint32_t it = 0, g = 0, t = 0;
-        for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
+        for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t, g += NJ) {
             const uint32_t xb = t & 1;
             mbar_wait(&x_full[xb], (t >> 1) & 1);
             tcgen05_fence_after();
@@ -185,7 +198,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                                 if (a.dbg & 512) break;
                                 umma_bf16(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
                             }
-                            umma_commit(&w_empty[s]);
+                            if (CL) umma_commit_multicast(&w_empty[s], 3); else umma_commit(&w_empty[s]);
                             if (kb == 3) umma_commit(&hacc_full[b]);
                         }
                         __syncwarp();
@@ -210,7 +223,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                                 umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
                                              (j > 1) || kb2 > 0 || k > 0);
                             }
-                            umma_commit(&w_empty[s]);
+                            if (CL) umma_commit_multicast(&w_empty[s], 3); else umma_commit(&w_empty[s]);
                             if (q == 3 && j == NJ) umma_commit(y_full);
                         }
                         __syncwarp();
@@ -226,7 +239,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t swz = (uint32_t)(lane & 7);
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         uint32_t g = 0, t = 0;
-        for (int mt = blockIdx.x; mt < num_m; mt += gridDim.x, ++t, g += NJ) {
+        for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t, g += NJ) {
             // ---- E1: hidden chunk j: +b1, ReLU, bf16, back into TMEM in place
             for (int j = 0; j < NJ; ++j) {
                 const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
@@ -343,6 +356,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();                      // no CTA leaves while its peer may still multicast data / arrivals into it
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -375,12 +389,23 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
-    const int grid = num_m < sm_count() ? num_m : sm_count();
     const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags};
-    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    // CTA pairs with multicast weights: measured identical (129.0 vs 130.1 us): halving the L2 reads does not help because the
+    // limit of the weight stream is the ~51 B/clk at which one SM's shared memory is filled (loads alone: 63 us with or without
+    // multicast, with 5 or 9 ring stages).  Kept (dtlr_debug_flags(4096)) as the validated base of the cta_group::2 version, which
+    // halves the bytes each SM must take in.
+    if ((g_debug_flags & 4096) && num_m >= 2) {
+        int grid = num_m < sm_count() ? num_m : sm_count();
+        grid &= ~1;
+        DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_tcgen05_kernel<true>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
+        return DTLR_OK;
+    }
+    const int grid = num_m < sm_count() ? num_m : sm_count();
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
     return DTLR_OK;
 }

@@ -132,8 +132,9 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
             assert (o.float() - old.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()
 
 
-@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048)])
-def test_fused_ffn_block(M, hid):
+@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048), (37000, 2048)])
+@pytest.mark.parametrize("pairs", [True, False])
+def test_fused_ffn_block(M, hid, pairs):
     """dtlr_ffn_ln: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM / shared memory) vs
     torch fp32 on the same bf16 operands with the hidden activation rounded to bf16 (as both our paths do), and vs the
     un-fused kernels (linear1 GEMM + linear2/LayerNorm GEMM)."""
@@ -147,11 +148,14 @@ def test_fused_ffn_block(M, hid):
     b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
     gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
     beta = 0.1 * torch.randn(256, device="cuda", generator=g)
+    from dtlr_b200 import _lib
     saved, ops.FFN_FUSED = ops.FFN_FUSED, True
+    _lib.lib().dtlr_debug_flags(4096 if pairs else 0)      # CTA pairs with multicast weights (opt-in) / independent CTAs (default)
     try:
         y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
     finally:
         ops.FFN_FUSED = saved
+        _lib.lib().dtlr_debug_flags(0)
     h = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
     pre = (h @ w2.float().T + b2 + x.float()).bfloat16().float()
     ref = F.layer_norm(pre, (256,), gamma, beta, 1e-5)

@@ -45,7 +45,7 @@ def ffn_probe(M=58368, hid=2048, nbuf=4):
     ops.FFN_FUSED = True
     fused = timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10)
     probes = {}
-    for name, f in [("no_E1", 256), ("no_G1", 512), ("no_G2", 1024), ("no_final", 2048), ("no_mma", 1536), ("no_mma_no_E1", 1792), ("loads_only", 3840)]:
+    for name, f in [("cta_pairs_multicast", 4096), ("no_E1", 256), ("no_G1", 512), ("no_G2", 1024), ("no_final", 2048), ("no_mma", 1536), ("no_mma_no_E1", 1792), ("loads_only", 3840)]:
         _lib.lib().dtlr_debug_flags(f)
         probes[name] = round(timeit(lambda i: ops.ffn_ln(x[i % nbuf], w1, b1, w2, b2, gm, bt), iters=10), 1)
     _lib.lib().dtlr_debug_flags(0)
