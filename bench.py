@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 
 BATCH_PER_GPU = 64
 IMG_H, IMG_W = 40, 1024
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE ffn_ln_tcgen05_kernel launch at M = 58368 (ncu --set full, profiles/r1_ffn_ncu.txt);
+# None until that capture exists.  Algorithmic bytes of the launch: X in + Y out (2 x 29.9 MB) + 2 MB of weights = 61.9 MB
+FFN_DRAM_BYTES_PER_LAUNCH = None
 WORKLOAD = "IAM English config/Latin_CTC.py: ResNet-50 + 6+6 deformable enc/dec, 900 queries, 166 classes, 64x3x40x1024 per GPU, forward"
 
 
@@ -184,6 +187,8 @@ def main():
     gemm_events, cur = [], {}
 
     msda_events = []
+    ffn_events = []
+    buckets = {"gemm": gemm_events, "msda": msda_events, "ffn": ffn_events}
 
     def timer(name, qty, dev, begin):
         if begin:
@@ -193,7 +198,7 @@ def main():
         else:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            (gemm_events if name == "gemm" else msda_events).append((cur["e0"], e1, cur["fl"]))
+            buckets[name].append((cur["e0"], e1, cur["fl"]))
 
     barrier()
     _lib.LAUNCHES = 0
@@ -234,6 +239,8 @@ def main():
     gemm_flops = sum(f for _, _, f in gemm_events)
     n_gemm = len(gemm_events)
     msda_ms = sum(a.elapsed_time(b) for a, b, _ in msda_events)
+    ffn_ms = sum(a.elapsed_time(b) for a, b, _ in ffn_events)
+    ffn_flops = sum(f for _, _, f in ffn_events)
     msda_bytes = sum(q for _, _, q in msda_events)
 
     # ---------------- end to end through the public API with HOST buffers (`e2e`)
@@ -269,12 +276,27 @@ def main():
     pk, pk_kind = peaks()
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"kernel": "gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions)" if dtype == torch.bfloat16 else "sgemm_kernel (fp32 parity mode)",
-                "bound": "tensor", "achieved": round(ach_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(ach_tf / peak_tf, 4), "traffic": None, "peak_kind": pk_kind + " sustained cuBLAS bf16",
-                "launches_timed": n_gemm, "share_of_step": round(gemm_ms / n_prof / ms_step, 3),
-                "eager_profiled_ms_per_step": round(prof_ms / n_prof, 3),
-                "algorithmic_flops_per_step": gemm_flops / n_prof}
+    roofline_gemm = {"kernel": "gemm_ws_tcgen05_kernel + gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions outside the FFN blocks)" if dtype == torch.bfloat16 else "sgemm_kernel (fp32 parity mode)",
+                     "bound": "tensor", "achieved": round(ach_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": round(ach_tf / peak_tf, 4), "traffic": None, "peak_kind": pk_kind + " sustained cuBLAS bf16",
+                     "launches_timed": n_gemm, "share_of_step": round(gemm_ms / n_prof / ms_step, 3),
+                     "algorithmic_flops_per_step": gemm_flops / n_prof,
+                     "note": "K <= 256 for ~150 of these launches (arithmetic intensity <= 128 flop/B): HBM / epilogue bound, not tensor bound -- DESIGN.md 3.2"}
+    # the dominant kernel of the step (profiles/r1_launches_step_v5.txt: 18.9 %): the fused FFN block, one launch per encoder /
+    # decoder layer; algorithmic FLOPs 4*M*hid*256 per launch; `traffic` = DRAM bytes of one launch from
+    # the ncu --set full capture in profiles/r1_ffn_ncu.txt
+    if ffn_events:
+        ffn_tf = ffn_flops / (ffn_ms * 1e-3) / 1e12
+        roofline = {"kernel": "ffn_ln_tcgen05_kernel (dtlr_ffn_ln: linear1 + ReLU + linear2 + residual + LayerNorm, hidden activation in TMEM)",
+                    "bound": "tensor", "achieved": round(ffn_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": round(ffn_tf / peak_tf, 4), "traffic": FFN_DRAM_BYTES_PER_LAUNCH,
+                    "peak_kind": pk_kind + " sustained cuBLAS bf16 (the kernel runs inside a long step)",
+                    "launches_timed": len(ffn_events), "share_of_step": round(ffn_ms / n_prof / ms_step, 3),
+                    "algorithmic_flops_per_launch": ffn_flops / len(ffn_events),
+                    "us_per_launch": round(1e3 * ffn_ms / len(ffn_events), 1),
+                    "eager_profiled_ms_per_step": round(prof_ms / n_prof, 3)}
+    else:                                   # fp32 parity mode / DTLR_FFN_FUSED=0: the GEMM family is the dominant one
+        roofline = dict(roofline_gemm, eager_profiled_ms_per_step=round(prof_ms / n_prof, 3))
     # the north-star kernel (multi-scale deformable attention core, fused prologue): HBM roofline from its algorithmic bytes;
     # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1_msda_mma_ncu.txt)
     hbm = pk["hbm_gbs"]
@@ -300,7 +322,8 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": host_imgs.numel() * 4 ,
                     "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(e2e_ms / args.steps, 3),
                     "api": "dtlr_b200.pipeline.HostPipeline: pinned host images -> DINO.forward -> dino.decode_frames (fused CTC-view argmax) -> pinned host int32 frame ids; H2D / compute / D2H of consecutive steps overlap"},
-            "gpu_launches": launches, "roofline": roofline, "roofline_msda": roofline_msda, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_msda": roofline_msda,
+            "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     dist_util.shutdown()
 

@@ -283,8 +283,12 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     if (FFN_FUSED and x.dtype == torch.bfloat16 and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
             and x.stride(1) == 1 and x.stride(0) % 8 == 0):
         y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
+        if L.TIMER is not None:     # bench.py: algorithmic FLOPs of the block = the two contractions, 2*M*hid*256 each
+            L.TIMER("ffn", 4.0 * M * hid * 256, x.device, True)
         _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
               ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _st(x))
+        if L.TIMER is not None:
+            L.TIMER("ffn", 0.0, x.device, False)
         return (y, add(y, add2)) if add2 is not None else y
     # experiment (opt-in): un-fused in row chunks that keep the hidden activation inside the 126 MB L2 (one reused buffer that
     # linear2 reads back before it is evicted).  The saved HBM traffic does not pay for the extra launches, the smaller M per

@@ -20,6 +20,7 @@ class HostPipeline:
         self.down = torch.cuda.Stream(device=self.device)
         self._dev_in = [None] * slots
         self._host_out = [None] * slots
+        self._consumed = [None] * slots       # compute-stream event: the forward that read this input slot has been enqueued
 
     @torch.no_grad()
     def run(self, host_batches):
@@ -35,11 +36,17 @@ class HostPipeline:
                 yield self._host_out[s]
             if self._dev_in[slot] is None or self._dev_in[slot].shape != hb.shape:
                 self._dev_in[slot] = torch.empty(hb.shape, dtype=hb.dtype, device=self.device)
-            self.up.wait_stream(compute)                        # the previous consumer of this slot has been enqueued
+                self._consumed[slot] = None                     # recycled allocator block: order after all compute work
+            if self._consumed[slot] is not None:                # only the forward that last read THIS slot (batch i - slots):
+                self.up.wait_event(self._consumed[slot])        # the upload of batch i overlaps the forward of batch i-1
+            else:
+                self.up.wait_stream(compute)                    # first use: order after the allocation / caller's work
             with torch.cuda.stream(self.up):
                 self._dev_in[slot].copy_(hb, non_blocking=True)
             compute.wait_stream(self.up)
             out = self.model(self._dev_in[slot])
+            self._consumed[slot] = torch.cuda.Event()
+            self._consumed[slot].record(compute)
             frames = dino.decode_frames(out, self.eps)
             if self._host_out[slot] is None or self._host_out[slot].shape != frames.shape:
                 self._host_out[slot] = torch.empty(frames.shape, dtype=frames.dtype).pin_memory()
