@@ -88,7 +88,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "device-resident timed region + end-to-end timed region (nvidia-smi -lms 20)"}
+                "window": "device-resident timed region + end-to-end timed regions (nvidia-smi -lms 20)"}
 
 
 def build_ours(device, dtype):
@@ -265,9 +265,28 @@ def main():
         t1.record()
         barrier()
         sampler.end()
-    clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- the same end to end with the GPU input stage: the host hands over 8-bit grayscale lines, 1 byte per
+    # pixel crosses PCIe, dtlr_preprocess_u8 normalises / pads on the GPU; bucketed LineEvaluator loop, class-id lists back on the host
+    import numpy as np
+    from dtlr_b200.evaluation import LineEvaluator
+    rng = np.random.default_rng(200 + rank)
+    u8_lines = [rng.integers(0, 256, (IMG_H, IMG_W), dtype=np.uint8) for _ in range(B)]
+    evaluator = LineEvaluator(model, [chr(0x21 + i) for i in range(166)], batch_size=B, width_multiple=32, eps=0.003)
+    evaluator.predict(u8_lines * 2)
+    barrier()
+    sampler.begin()
+    u0 = torch.cuda.Event(enable_timing=True); u1 = torch.cuda.Event(enable_timing=True)
+    u0.record()
+    u8_preds = evaluator.predict(u8_lines * args.steps)
+    u1.record()
+    barrier()
+    sampler.end()
+    u8_ms = max_over_ranks(u0.elapsed_time(u1))
+    u8_value = world * B * args.steps / (u8_ms / 1e3)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         dist_util.shutdown()
@@ -322,6 +341,9 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": host_imgs.numel() * 4 ,
                     "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(e2e_ms / args.steps, 3),
                     "api": "dtlr_b200.pipeline.HostPipeline: pinned host images -> DINO.forward -> dino.decode_frames (fused CTC-view argmax) -> pinned host int32 frame ids; H2D / compute / D2H of consecutive steps overlap"},
+            "e2e_u8": {"value": round(u8_value, 1), "unit": "images/s", "h2d_bytes_per_step": evaluator.prep.h2d_bytes,
+                       "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(u8_ms / args.steps, 3),
+                       "api": "dtlr_b200.evaluation.LineEvaluator.predict: host u8 grayscale lines -> dtlr_preprocess_u8 (ToTensor + Normalize + pad on the GPU) -> DINO.forward -> fused decode -> host class-id lists"},
             "gpu_launches": launches, "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_msda": roofline_msda,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

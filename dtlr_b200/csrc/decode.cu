@@ -16,8 +16,8 @@ __device__ __forceinline__ float warp_sum_d(float v) {
 }
 
 // one warp per (b,q): label = 0 (blank) or 1 + argmax class
-__global__ void ctc_row_label_kernel(const float* __restrict__ logits, int ld, int C, float eps, int* __restrict__ label,
-                                     float* __restrict__ row_sum, long long rows) {
+__global__ void ctc_row_label_kernel(const float* __restrict__ logits, int ld, int C, float eps, float pscale,
+                                     int* __restrict__ label, float* __restrict__ row_sum, long long rows) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -25,7 +25,7 @@ __global__ void ctc_row_label_kernel(const float* __restrict__ logits, int ld, i
     float s = 0.f, best = -1.f;
     int arg = 0x7fffffff;
     for (int c = lane; c < C; c += 32) {
-        const float p = 1.f / (1.f + expf(-x[c]));
+        const float p = pscale * (1.f / (1.f + expf(-x[c])));
         s += p;
         if (p > best) { best = p; arg = c; }
     }
@@ -80,8 +80,9 @@ __global__ void ctc_sort_emit_kernel(const float* __restrict__ boxes, const int*
 }
 
 // optional: new_pred_logits[b, pos, :] from logits[b, perm[pos], :]   (one warp per output row)
-__global__ void ctc_new_pred_kernel(const float* __restrict__ logits, int ld, int C, float eps, const int* __restrict__ perm,
-                                    const float* __restrict__ row_sum, float* __restrict__ new_pred, int Q, long long rows) {
+__global__ void ctc_new_pred_kernel(const float* __restrict__ logits, int ld, int C, float eps, float pscale,
+                                    const int* __restrict__ perm, const float* __restrict__ row_sum,
+                                    float* __restrict__ new_pred, int Q, long long rows) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -94,7 +95,7 @@ __global__ void ctc_new_pred_kernel(const float* __restrict__ logits, int ld, in
     float* o = new_pred + (size_t)row * (C + 1);
     if (lane == 0) o[0] = low ? 1.f - s : eps;
     for (int c = lane; c < C; c += 32) {
-        const float p = 1.f / (1.f + expf(-x[c]));
+        const float p = pscale * (1.f / (1.f + expf(-x[c])));
         o[c + 1] = low ? p : (1.f - eps) * p / s;
     }
     (void)scale;
@@ -104,8 +105,9 @@ __global__ void ctc_new_pred_kernel(const float* __restrict__ logits, int ld, in
 
 using namespace dtlr;
 
-extern "C" int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
-                               int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, void* stream) {
+extern "C" int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
+                                      int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, float prob_scale,
+                                      void* stream) {
     DTLR_CHECK_ARG(B >= 0 && Q >= 0 && C > 0 && ld >= C, "ctc_decode: bad sizes");
     if (B == 0 || Q == 0) return DTLR_OK;
     DTLR_CHECK_ARG(logits && boxes && frames && scratch_label, "ctc_decode: null pointer");
@@ -115,7 +117,7 @@ extern "C" int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, 
     DTLR_CHECK_ARG((size_t)n * 8 <= (size_t)max_smem_optin(), "ctc_decode: %d queries per line exceed the shared-memory sort", Q);
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * Q;
-    ctc_row_label_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, scratch_label, scratch_sum, rows);
+    ctc_row_label_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, prob_scale, scratch_label, scratch_sum, rows);
     DTLR_CHECK_LAUNCH();
     const size_t smem = (size_t)n * 8;
     if (smem > 48 * 1024)
@@ -123,8 +125,13 @@ extern "C" int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, 
     ctc_sort_emit_kernel<<<B, n < 1024 ? n : 1024, smem, st>>>(boxes, scratch_label, frames, perm, Q, n);
     DTLR_CHECK_LAUNCH();
     if (new_pred) {
-        ctc_new_pred_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, perm, scratch_sum, new_pred, Q, rows);
+        ctc_new_pred_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, prob_scale, perm, scratch_sum, new_pred, Q, rows);
         DTLR_CHECK_LAUNCH();
     }
     return DTLR_OK;
+}
+
+extern "C" int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
+                               int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, void* stream) {
+    return dtlr_ctc_decode_scaled(logits, ld, boxes, frames, perm, new_pred, scratch_label, scratch_sum, B, Q, C, eps, 1.f, stream);
 }

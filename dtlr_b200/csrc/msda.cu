@@ -692,6 +692,118 @@ __global__ void msda_bwd_kernel(const T* __restrict__ value, const T* __restrict
     }
 }
 
+// backward fast path: D = 32, fp32, L*P = 16 (every shipped DTLR config).  One warp per (b,q,m), no shared memory:
+//  * lane pt (< 16) computes the tap parameters of sampling point pt ONCE (the generic kernel above recomputes them in all
+//    32 lanes for every point): biased pixel index of the (y0,x0) corner, fractional weights, the four corner-validity bits;
+//    4 shuffles per point hand them to the warp.
+//  * lane = (corner k = lane>>3, channel group j = lane&7): ONE 16-byte load fetches the four corners of a point (4 x 128 B,
+//    coalesced), d = <grad_out[4j..4j+3], v> is the only per-channel arithmetic, and ONE `red.global.add.v4.f32`
+//    (REDG.E.ADD.F32x4) scatters the point's grad_value contribution: 16 vector reductions per (q,m) instead of 64 scalar
+//    warp-wide atomics (the reference scatters scalar atomicAdd, ms_deform_im2col_cuda.cuh:125-152).
+//  * the 48 partial sums (16 points x {grad_attn, grad_x, grad_y}) stay in registers and are reduced over the 32 lanes by a
+//    transposed butterfly (24+12+6+3+3 = 48 shuffles instead of 48 x 5); it leaves point p's three sums in lanes 2p, 2p+1,
+//    which store grad_attn / grad_loc coalesced (the reference: shared memory + a serial thread-0 sum, :377-393).
+template <int NPT>
+__device__ __forceinline__ void transposed_reduce(float (&r)[3 * NPT], const int lane) {
+    static_assert(NPT == 16, "layout below assumes 48 partials over 32 lanes");
+    // after the step with offset o, the lanes with bit o clear own the first half of the live values, the others the second
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const bool hi = lane & 16;
+        const float send = hi ? r[i] : r[i + 24], keep = hi ? r[i + 24] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const bool hi = lane & 8;
+        const float send = hi ? r[i] : r[i + 12], keep = hi ? r[i + 12] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const bool hi = lane & 4;
+        const float send = hi ? r[i] : r[i + 6], keep = hi ? r[i + 6] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const bool hi = lane & 2;
+        const float send = hi ? r[i] : r[i + 3], keep = hi ? r[i + 3] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+}
+
+__device__ __forceinline__ void red_add_f32x4(float* p, const float a, const float b, const float c, const float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int PTS>      // sampling points per level (L * PTS == 16)
+__global__ void __launch_bounds__(256)
+msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
+                    const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
+                    float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
+                    const int M, const int Lq) {
+    const int lane = threadIdx.x & 31;
+    const int k = lane >> 3, j = lane & 7;
+    const bool ky = k >> 1, kx = k & 1;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // the tap parameters of lane pt's level are loop-invariant
+    const int pl = (lane & 15) / PTS;
+    const int pH = lv.H[pl], pW = lv.W[pl], pstart = lv.start[pl];
+    for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < total; wid += nwarps) {
+        const int m = (int)(wid % M);
+        const int b = (int)((wid / M) / Lq);
+        const size_t voff = ((size_t)b * S * M + m) * 32 + 4 * j;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gout + (size_t)wid * 32) + j);
+        // ---- lane pt: parameters of point pt (lanes 16-31 mirror 0-15; only their shuffled-from copies in 0-15 are used)
+        const size_t ip = (size_t)wid * 16 + (lane & 15);
+        const float2 lxy = __ldg(reinterpret_cast<const float2*>(loc) + ip);
+        const float paw = __ldg(attn + ip);
+        const float y = lxy.y * pH - 0.5f, x = lxy.x * pW - 0.5f;
+        const bool inside = y > -1.f && x > -1.f && y < pH && x < pW;
+        const float fy0 = floorf(y), fx0 = floorf(x);
+        const int y0 = (int)fy0, x0 = (int)fx0;
+        const float pfy = y - fy0, pfx = x - fx0;
+        unsigned ppix = 0;
+        if (inside) {
+            const unsigned okY0 = y0 >= 0, okY1 = y0 + 1 <= pH - 1, okX0 = x0 >= 0, okX1 = x0 + 1 <= pW - 1;
+            const unsigned bits = (okY0 & okX0) | ((okY0 & okX1) << 1) | ((okY1 & okX0) << 2) | ((okY1 & okX1) << 3);
+            // pixel index of corner (y0,x0), biased by one row + one pixel so that it is never negative; bits 24-27: validity
+            ppix = (unsigned)(pstart + (y0 + 1) * pW + (x0 + 1)) | (bits << 24);
+        }
+        float r[48];
+#pragma unroll
+        for (int pt = 0; pt < 16; ++pt) {
+            const unsigned pix = __shfl_sync(0xffffffffu, ppix, pt);
+            const float fy = __shfl_sync(0xffffffffu, pfy, pt);
+            const float fx = __shfl_sync(0xffffffffu, pfx, pt);
+            const float aw = __shfl_sync(0xffffffffu, paw, pt);
+            const int W = lv.W[pt / PTS], H = lv.H[pt / PTS];
+            const float wy = ky ? fy : 1.f - fy, wx = kx ? fx : 1.f - fx;
+            float d = 0.f;
+            if ((pix >> (24 + k)) & 1u) {
+                const int pixel = (int)(pix & 0xffffffu) - W - 1 + (ky ? W : 0) + (kx ? 1 : 0);
+                const size_t idx = voff + (size_t)pixel * M * 32;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(value + idx));
+                d = g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+                const float c = wy * wx * aw;
+                red_add_f32x4(gvalue + idx, c * g.x, c * g.y, c * g.z, c * g.w);
+            }
+            r[3 * pt] = wy * wx * d;                               // -> grad_attn
+            r[3 * pt + 1] = (kx ? wy : -wy) * d * aw * (float)W;   // -> grad_loc.x   (d bilinear / dx = +-wy)
+            r[3 * pt + 2] = (ky ? wx : -wx) * d * aw * (float)H;   // -> grad_loc.y
+        }
+        transposed_reduce<16>(r, lane);
+        if (!(lane & 1)) {
+            const size_t op = (size_t)wid * 16 + (lane >> 1);
+            gattn[op] = r[0];
+            *reinterpret_cast<float2*>(gloc + 2 * op) = make_float2(r[1], r[2]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int fill_levels(Levels& lv, const int64_t* shapes, const int64_t* lsi, int L, int S) {
     DTLR_CHECK_ARG(L >= 1 && L <= MAX_LEVELS, "msda: n_levels %d not in [1,%d]", L, MAX_LEVELS);
@@ -877,7 +989,27 @@ extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, cons
     const int threads = 256;
     const long long blocks = (warps * 32 + threads - 1) / threads;
     DTLR_CHECK_ARG(blocks < (1ll << 31), "msda_backward: problem too large");
-    if (dtype == DTLR_F32) {
+    int maxW = 0;
+    for (int l = 0; l < L; ++l) maxW = max(maxW, lv.W[l]);
+    const bool fast = dtype == DTLR_F32 && D == 32 && L * P == 16 && (P == 2 || P == 4 || P == 8 || P == 16) &&
+                      (long long)S + maxW + 2 < (1ll << 24) && !(g_debug_flags & 8192) &&   // flag 8192: generic kernel (A/B)
+                      ((((uintptr_t)value | (uintptr_t)grad_value | (uintptr_t)grad_out) & 15) == 0) &&
+                      ((((uintptr_t)loc | (uintptr_t)grad_loc) & 7) == 0);
+    if (fast) {
+        // grid-stride over the (b,q,m) items: enough 8-warp CTAs to fill the machine a few times over
+        const long long want = (warps + 7) / 8;
+        const unsigned grid = (unsigned)min(want, (long long)sm_count() * 32);
+        auto launch = [&](auto kern) {
+            kern<<<grid, 256, 0, st>>>((const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out,
+                                       (float*)grad_value, (float*)grad_loc, (float*)grad_attn, lv, warps, S, M, Lq);
+        };
+        switch (P) {
+            case 2: launch(msda_bwd_d32_kernel<2>); break;
+            case 4: launch(msda_bwd_d32_kernel<4>); break;
+            case 8: launch(msda_bwd_d32_kernel<8>); break;
+            default: launch(msda_bwd_d32_kernel<16>); break;
+        }
+    } else if (dtype == DTLR_F32) {
         msda_bwd_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
             (const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out, (float*)grad_value,
             (float*)grad_loc, (float*)grad_attn, lv, B, S, M, D, Lq, P);

@@ -214,9 +214,10 @@ def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
     return out
 
 
-def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
+def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False, prob_scale=1.0):
     """fused CTC-view decode: pred_logits fp32 (B,Q,C), pred_boxes fp32 (B,Q,4) -> frames int32 (B,Q) in reading order
-    (0 = blank, c+1 = class c) [, new_pred_logits fp32 (B,Q,C+1)]."""
+    (0 = blank, c+1 = class c) [, new_pred_logits fp32 (B,Q,C+1)].  prob_scale multiplies every class probability before the
+    blank synthesis (reference ngram/prediction_helpers.py:5-46 `multiply_pred_logits_by`)."""
     import ctypes
     L.require_cuda(pred_logits, pred_boxes)
     B, Q, C = pred_logits.shape
@@ -230,8 +231,8 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False):
     perm = torch.empty((B, Q), dtype=torch.int32, device=dev) if want_new_pred else None
     rsum = torch.empty((B, Q), dtype=torch.float32, device=dev) if want_new_pred else None
     newp = torch.empty((B, Q, C + 1), dtype=torch.float32, device=dev) if want_new_pred else None
-    _call("dtlr_ctc_decode", _p(logits), logits.stride(1), _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum), B, Q, C,
-          ctypes.c_float(eps), _st(logits))
+    _call("dtlr_ctc_decode_scaled", _p(logits), logits.stride(1), _p(boxes), _p(frames), _p(perm), _p(newp), _p(label), _p(rsum),
+          B, Q, C, ctypes.c_float(eps), ctypes.c_float(prob_scale), _st(logits))
     return (frames, newp) if want_new_pred else frames
 
 
@@ -304,3 +305,18 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
                     out2=y2[r0:r1] if add2 is not None else None)
         return (y, y2) if add2 is not None else y
     return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta, add2=add2)
+
+
+def preprocess_u8(packed_u8, offsets_i64, hw_i32, channels, B, Hmax, Wmax, mean, std):
+    """GPU input stage (csrc/input.cu): packed u8 images -> (B,3,Hmax,Wmax) fp32 normalised + zero padded, (B,Hmax,Wmax) bool mask."""
+    import ctypes
+    L.require_cuda(packed_u8, offsets_i64, hw_i32)
+    assert packed_u8.dtype == torch.uint8 and offsets_i64.dtype == torch.int64 and hw_i32.dtype == torch.int32
+    dev = packed_u8.device
+    out = torch.empty((B, 3, Hmax, Wmax), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, Hmax, Wmax), dtype=torch.bool, device=dev)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _call("dtlr_preprocess_u8", _p(packed_u8), _p(offsets_i64), _p(hw_i32), int(channels), _p(out), _p(mask), B, Hmax, Wmax, m3, s3,
+          _st(packed_u8))
+    return out, mask

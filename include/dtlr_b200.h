@@ -187,6 +187,21 @@ int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void* v, int ld
  * scratch_sum fp32 [B*Q] (may be NULL when new_pred is NULL). */
 int dtlr_ctc_decode(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
                     int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, void* stream);
+/* Same with every class probability multiplied by prob_scale before the blank synthesis: the layout the n-gram rescoring
+ * tool feeds to its CTC beam-search decoder (ngram/prediction_helpers.py:5-46, `multiply_pred_logits_by`). */
+int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* boxes, int* frames, int* perm, float* new_pred,
+                           int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, float prob_scale,
+                           void* stream);
+
+/* GPU input stage for already-resized 8-bit line images: ToTensor (datasets/transforms.py:247-249) + Normalize
+ * (datasets/transforms.py:552-558) + nested_tensor_from_tensor_list (util/misc.py:375-397) in one kernel.
+ * packed (dev u8): the B images back to back, image b at byte offsets[b] (dev int64 [B]), h x w x channels, row-major, channels
+ * interleaved (PIL layout; channels = 1: grayscale replicated to the 3 planes as datasets/IAM.py:86-88 does, 3: RGB).
+ * hw (dev int32 [B,2]) = (h, w) of every image, h <= Hmax, w <= Wmax.  out (dev f32 [B,3,Hmax,Wmax]) = ((u8/255) - mean) / std in
+ * IEEE fp32, bit-identical to the torch chain, zero on the padding; mask (dev u8 [B,Hmax,Wmax]) = 1 on the padding.
+ * mean3/std3 are HOST pointers to 3 floats. */
+int dtlr_preprocess_u8(const uint8_t* packed, const long long* offsets, const int* hw, int channels, float* out, uint8_t* mask,
+                       int B, int Hmax, int Wmax, const float* mean3_host, const float* std3_host, void* stream);
 
 /* Hungarian matcher of the detection loss (models/dino/matcher.py:57-96), two kernels for all P = layers x B problems of a
  * training step at once (the reference runs a cdist/GIoU chain over the full (B*Q) x sum(T) matrix, copies it to the CPU and

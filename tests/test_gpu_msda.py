@@ -157,6 +157,57 @@ def test_backward_fp32_vs_oracle_config_size():
     assert torch.allclose(ga.cpu().double(), ra, rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("shapes,P", [(A_SHAPES, 4), ([(5, 128), (3, 64)], 8), ([(7, 33)], 16),
+                                      ([(4, 9), (3, 7), (2, 5), (2, 3), (1, 4), (1, 3), (1, 2), (1, 1)], 2)])
+def test_backward_fast_path_vs_oracle_and_generic_kernel(shapes, P):
+    """D = 32 fp32 with L*P = 16 runs msda_bwd_d32_kernel (vector reductions, transposed shuffle reduction): against the fp64
+    C oracle, and against the generic one-warp-per-item kernel (debug flag 8192) on the same inputs, with points on the map
+    borders / outside and a ragged warp count."""
+    from dtlr_b200 import _lib, msda
+    B, Lq, M = 3, 37, 8
+    value, shp, lsi, loc, w = _rand_case(B, shapes, M, 32, Lq, P, 31 + P)
+    special = torch.tensor([0.0, 1.0, -1e-7, 1.0 + 1e-7, 0.5 / 128, 1 - 0.5 / 128, -5.0, 7.0, 0.3, 0.999999])
+    g = torch.Generator().manual_seed(5)
+    pick = torch.rand(loc.shape, generator=g) < 0.25
+    loc = torch.where(pick, special[torch.randint(0, len(special), loc.shape, generator=g)], loc)
+    go = torch.randn(B, Lq, M * 32, generator=g)
+    rv, rl, ra = omsda.msda_backward(value.double(), shp, lsi, loc.double(), w.double(), go.double())
+    args = (value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), go.cuda(), 64)
+    gv, gl, ga = msda.ms_deform_attn_backward(*args)
+    _lib.lib().dtlr_debug_flags(8192)
+    try:
+        gv0, gl0, ga0 = msda.ms_deform_attn_backward(*args)
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
+    for new, old, ref, atol in ((gv, gv0, rv, 1e-4), (gl, gl0, rl, 1e-3), (ga, ga0, ra, 1e-4)):
+        assert torch.isfinite(new).all()
+        assert torch.allclose(new.cpu().double(), ref, rtol=1e-3, atol=atol)
+        assert torch.allclose(new, old, rtol=1e-3, atol=atol)
+
+
+def test_backward_full_size_matches_generic_kernel_and_is_linear_in_grad_out():
+    """BASELINE config-5 shape per GPU (B = 32, 900 queries): fast vs generic kernel, and linearity in grad_out
+    (size-independent property: bwd(a*g1 + g2) == a*bwd(g1) + bwd(g2))."""
+    from dtlr_b200 import _lib, msda
+    B, Lq = 32, 900
+    value, shp, lsi, loc, w = _rand_case(B, A_SHAPES, 8, 32, Lq, 4, 77)
+    g = torch.Generator().manual_seed(6)
+    g1, g2 = torch.randn(B, Lq, 256, generator=g).cuda(), torch.randn(B, Lq, 256, generator=g).cuda()
+    a = (value.cuda(), shp.cuda(), lsi.cuda(), loc.cuda(), w.cuda())
+    r1 = msda.ms_deform_attn_backward(*a, g1, 64)
+    r2 = msda.ms_deform_attn_backward(*a, g2, 64)
+    r12 = msda.ms_deform_attn_backward(*a, 0.5 * g1 + g2, 64)
+    for x1, x2, x12 in zip(r1, r2, r12):
+        assert torch.allclose(x12, 0.5 * x1 + x2, rtol=1e-3, atol=2e-3)
+    _lib.lib().dtlr_debug_flags(8192)
+    try:
+        r1g = msda.ms_deform_attn_backward(*a, g1, 64)
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
+    for x, y in zip(r1, r1g):
+        assert torch.allclose(x, y, rtol=1e-3, atol=2e-3)
+
+
 def test_full_size_linearity_config2():
     """BASELINE config 2 size (B=64, S=912, Lq=912): size-independent property -- the op is linear in value and in the
     attention weights: f(a*v1 + v2, w) == a*f(v1,w) + f(v2,w)."""

@@ -1,0 +1,101 @@
+"""CPU: (1) the I/O oracle (oracle/io_ref.py) against the golden vectors the unmodified reference produced
+(tests/golden/make_golden_io.py); (2) the product's host-side logic for SURVEY §8f rows 2-4 -- the resize size rule, u8 packing,
+width bucketing, CER / WER -- against the same fixtures and the oracle.  No CUDA here."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import io_ref
+
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+@pytest.fixture(scope="module")
+def io(golden_dir):
+    return np.load(os.path.join(golden_dir, "io.npz"))
+
+
+@pytest.fixture(scope="module")
+def metrics(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "io_metrics.json")))
+
+
+def test_oracle_totensor_normalize_pad_bit_exact(io):
+    ts = [io_ref.to_tensor_normalize(io["img%d_u8" % i], MEAN, STD) for i in range(4)]
+    batch, mask = io_ref.nested_batch(ts)
+    assert torch.equal(batch, torch.from_numpy(io["batch"])) and torch.equal(mask, torch.from_numpy(io["mask"]))
+    ts = [io_ref.to_tensor_normalize(io["rgb%d_u8" % i], MEAN, STD) for i in range(2)]
+    batch, mask = io_ref.nested_batch(ts)
+    assert torch.equal(batch, torch.from_numpy(io["rgb_batch"])) and torch.equal(mask, torch.from_numpy(io["rgb_mask"]))
+
+
+def test_size_rule_oracle_and_product(io):
+    from dtlr_b200.input import get_size_with_aspect_ratio
+    for w, h, size, mx, oh, ow in io["size_table"].tolist():
+        assert io_ref.resized_size((w, h), size, mx) == (oh, ow)
+        assert get_size_with_aspect_ratio((w, h), size, mx) == (oh, ow)
+
+
+def test_oracle_ngram_new_pred_logits(io):
+    lg, bx = torch.from_numpy(io["np_logits"]), torch.from_numpy(io["np_boxes"])
+    for mult in (1, 2):
+        ref = torch.from_numpy(io["new_pred_x%d" % mult])
+        assert ((ref[..., 0] - 0.003).abs() < 1e-9).any() and ((ref[..., 0] - 0.003).abs() > 1e-4).any()   # both blank branches
+        assert torch.allclose(io_ref.new_pred_logits(lg, bx, mult), ref, rtol=1e-6, atol=1e-7)
+
+
+def test_metrics_oracle_and_product(metrics):
+    from dtlr_b200 import evaluation as ev
+    cs = metrics["charset"]
+    for r in metrics["rows"]:
+        pl, gl = [cs.index(c) for c in r["pred"]], [cs.index(c) for c in r["gt"]]
+        for mod_cer, mod_clean, mod_split, mod_wer in ((io_ref.cer, io_ref.clean_string, io_ref.split_words, io_ref.wer),
+                                                       (ev.character_error_rate, ev.process_pred_string, ev.split_labels_into_words,
+                                                        ev.word_error_rate)):
+            assert mod_cer(r["pred"], r["gt"]) == r["cer"]
+            assert mod_clean(r["pred"]) == r["clean_pred"] and mod_clean(r["gt"]) == r["clean_gt"]
+            assert mod_split(pl, cs) == r["pred_words"] and mod_split(gl, cs) == r["gt_words"]
+            assert mod_wer(mod_split(gl, cs), mod_split(pl, cs)) == r["wer_ref_call"]
+    assert ev.levenshtein_distance("kitten", "sitting") == 3 and ev.levenshtein_distance([], [1, 2]) == 2
+
+
+def test_bucket_batches_properties():
+    from dtlr_b200.evaluation import bucket_batches
+    rng = np.random.default_rng(1)
+    widths = rng.integers(60, 1400, 257).tolist()
+    for bs, mult in ((64, 32), (7, 1), (1, 32), (300, 64)):
+        batches = bucket_batches(widths, bs, mult)
+        flat = [i for b in batches for i in b]
+        assert sorted(flat) == list(range(len(widths)))                         # a partition
+        assert all(1 <= len(b) <= bs for b in batches)
+        for b in batches:                                                       # one bucket per batch, ascending widths
+            ws = [widths[i] for i in b]
+            assert ws == sorted(ws)
+            assert len({(w + mult - 1) // mult for w in ws}) == 1
+        firsts = [widths[b[0]] for b in batches]
+        assert firsts == sorted(firsts)
+    assert bucket_batches([], 4) == []
+    capped = bucket_batches([100, 101, 127, 128], 8, 128, max_pad_frac=0.1)
+    assert [len(b) for b in capped] == [2, 2] or sum(len(b) for b in capped) == 4
+    with pytest.raises(ValueError):
+        bucket_batches([1], 0)
+
+
+def test_pack_u8_layout_and_errors(io):
+    from dtlr_b200.input import pack_u8
+    imgs = [io["img%d_u8" % i] for i in range(4)]
+    packed, off, sizes, ch = pack_u8(imgs)
+    assert ch == 1 and packed.dtype == np.uint8 and packed.size == sum(im.size for im in imgs)
+    for im, o, (h, w) in zip(imgs, off, sizes):
+        assert (h, w) == im.shape and np.array_equal(packed[o:o + im.size].reshape(h, w), im)
+    packed, off, sizes, ch = pack_u8([io["rgb0_u8"], torch.from_numpy(io["rgb1_u8"])])
+    assert ch == 3 and off[1] == io["rgb0_u8"].size
+    with pytest.raises(ValueError):
+        pack_u8([io["img0_u8"], io["rgb0_u8"]])
+    with pytest.raises(TypeError):
+        pack_u8([io["img0_u8"].astype(np.float32)])
+    with pytest.raises(ValueError):
+        pack_u8([])
