@@ -111,7 +111,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // MT = 16-query m-tiles per warp: every K / V fragment fetched from shared memory feeds MT MMAs (MT = 2 halves the
 // ldmatrix traffic per FLOP, which is what bounds the MT = 1 version).
-template <int MT>
+// PIPE: the S = Q K^T MMAs of key block kb+1 are issued before the softmax of block kb (two ping-pong score arrays, the loop body
+// instantiated twice), so that the tensor pipe works under the MUFU / FMNMX / shuffle chain of the softmax instead of idling in
+// front of it -- the un-pipelined kernel is latency bound (ncu: 0.35 IPC per scheduler, MUFU 39 % busy, 4 warps per scheduler).
+template <int MT, bool PIPE>
 __global__ void __launch_bounds__(FA_WARPS * 32)
 mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off, const __nv_bfloat16* __restrict__ v, int ld_v,
                       __nv_bfloat16* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
@@ -176,9 +179,8 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                 for (int k = 0; k < 4; ++k) o[mt][n][k] = 0.f;
         }
 
-        for (int kb = 0; kb < KP; kb += 64) {
-            // ---- S = Q K^T for 64 keys: 8 n-blocks of 8 keys, each K fragment reused by the MT m-tiles
-            float sc[MT][8][4];
+        // ---- S = Q K^T for the 64 keys from kb: 8 n-blocks of 8 keys, each K fragment reused by the MT m-tiles
+        auto qk_block = [&](float (&sc)[MT][8][4], const int kb) {
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 uint32_t kf[4];
@@ -190,6 +192,9 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                     mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
                 }
             }
+        };
+        // ---- masking of the key padding, online softmax, O += P V for the 64 keys from kb (scores in sc)
+        auto softmax_pv = [&](float (&sc)[MT][8][4], const int kb) {
             if (kb + 64 > Q) {    // key padding -> -inf
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -201,7 +206,7 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                     }
                 }
             }
-            // ---- online softmax (rows g and g+8 of each m-tile); a quad of lanes shares a row
+            // online softmax (rows g and g+8 of each m-tile); a quad of lanes shares a row
             uint32_t pa[MT][4][4];    // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -231,7 +236,7 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                     pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
                 }
             }
-            // ---- O += P V, each V fragment reused by the MT m-tiles
+            // O += P V, each V fragment reused by the MT m-tiles
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
@@ -244,6 +249,26 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
                         mma_bf16_16816(o[mt][nn * 2 + 1], pa[mt][kk], vf[2], vf[3]);
                     }
                 }
+            }
+        };
+        if (PIPE) {
+            float sa[MT][8][4], sb[MT][8][4];
+            qk_block(sa, 0);
+            for (int kb = 0;;) {
+                if (kb + 64 < KP) qk_block(sb, kb + 64);
+                softmax_pv(sa, kb);
+                kb += 64;
+                if (kb >= KP) break;
+                if (kb + 64 < KP) qk_block(sa, kb + 64);
+                softmax_pv(sb, kb);
+                kb += 64;
+                if (kb >= KP) break;
+            }
+        } else {
+            for (int kb = 0; kb < KP; kb += 64) {
+                float sc[MT][8][4];
+                qk_block(sc, kb);
+                softmax_pv(sc, kb);
             }
         }
 #pragma unroll
@@ -289,9 +314,10 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         const int per_round = FA_WARPS * 16 * FA_MT;
         const int splits = (Q + per_round - 1) / per_round;
         int q_per_cta = ((Q + splits - 1) / splits + 16 * FA_MT - 1) / (16 * FA_MT) * (16 * FA_MT);
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(mha_flash_bf16_kernel<FA_MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
-        DTLR_CHECK_CUDA(launch_pdl(mha_flash_bf16_kernel<FA_MT>, fgrid, dim3(FA_WARPS * 32), smem, st, (const __nv_bfloat16*)qk, ld_qk, k_off,
+        auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, false> : mha_flash_bf16_kernel<FA_MT, true>;   // flag 16384: un-pipelined (A/B)
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(FA_WARPS * 32), smem, st, (const __nv_bfloat16*)qk, ld_qk, k_off,
                                    (const __nv_bfloat16*)v, ld_v, (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
     } else if (dtype == DTLR_BF16)
         mha_simt_kernel<__nv_bfloat16><<<grid, ATT_QT, 0, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v, attn_mask, (__nv_bfloat16*)out, ld_o, Q, scale);

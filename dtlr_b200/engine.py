@@ -217,7 +217,7 @@ class InferenceEngine:
             with torch.cuda.graph(graph):
                 out = self._forward_eager(NestedTensor(sx, sm, getattr(samples, "nopad", False)), None)
             ent = (graph, sx, sm, out)
-            if len(self._graphs) > 8:
+            if len(self._graphs) >= getattr(m, "max_cuda_graphs", 8):     # every graph owns its static buffers + activation pool
                 self._graphs.clear()
             self._graphs[key] = ent
         graph, sx, sm, out = ent

@@ -2,9 +2,11 @@
 
 The reference's evaluation loop (evaluation.py:486-535) runs one image at a time -- `model.cuda()(image[None].cuda())`, a
 dozen host syncs per image in `convert_output_to_pred` (evaluation.py:116-160), `editdistance` on the critical path.  Here:
-  * lines are sorted by resized width and cut into batches whose members share one padded width bucket
-    (`bucket_batches`): little padding, few distinct shapes (one captured CUDA graph per bucket);
-  * a batch crosses PCIe as packed u8 and is normalised / padded on the GPU (`input.GpuPreprocessor`);
+  * lines are cut into batches whose members share one padded (width, height) bucket (`bucket_batches`; the reference's
+    evaluation resize caps the long side at 1333, so real lines share the width and differ in height): little padding, few
+    distinct shapes (one captured CUDA graph per bucket);
+  * a batch crosses PCIe as packed u8 and is normalised / padded on the GPU (`input.GpuPreprocessor`) on a side stream, under
+    the forward of the previous batch;
   * the decode is the fused kernel pair of csrc/decode.cu with evaluation.py's eps = 0.03 / C (evaluation.py:141) and only
     the int32 frame labels come back; frames of batch i are downloaded while batch i+1 computes;
   * CER / WER accumulate on the host off the critical path, with the reference's own definitions: `character_error_rate`
@@ -80,25 +82,36 @@ def process_pred_string(s):
 
 
 # ------------------------------------------------------------------------------------------------ batching (host)
-def bucket_batches(widths, batch_size, width_multiple=32, max_pad_frac=None):
-    """indices sorted by width, cut into batches of <= batch_size whose widths round up to the same multiple of
-    `width_multiple` (so a batch pads by < width_multiple columns beyond its widest line and every batch shape is one of a few
-    buckets).  With `max_pad_frac` a batch is also cut when its narrowest line would be padded by more than that fraction.
-    Returns a list of index lists; every index appears exactly once."""
-    if batch_size < 1 or width_multiple < 1:
-        raise ValueError("batch_size and width_multiple must be >= 1")
-    order = sorted(range(len(widths)), key=lambda i: (widths[i], i))
+def bucket_batches(widths, batch_size, width_multiple=32, max_pad_frac=None, heights=None, height_multiple=8):
+    """indices cut into batches of <= batch_size whose members share one padded-size bucket: widths that round up to the same
+    multiple of `width_multiple` and -- when `heights` is given (the reference's evaluation resize caps the long side at 1333, so
+    real lines share the width and differ in height) -- heights that round up to the same multiple of `height_multiple`.  Within
+    a bucket lines are taken in ascending (height, width) order, so a batch pads by less than one multiple beyond its largest line
+    and every batch shape is one of a few buckets.  With `max_pad_frac` a batch is also cut when its narrowest line would be
+    padded by more than that fraction of the bucket width.  Returns a list of index lists; every index appears exactly once."""
+    if batch_size < 1 or width_multiple < 1 or height_multiple < 1:
+        raise ValueError("batch_size and the size multiples must be >= 1")
+    n = len(widths)
+    if heights is not None and len(heights) != n:
+        raise ValueError("heights and widths differ in length")
+
+    def bucket(i):
+        wb = (int(widths[i]) + width_multiple - 1) // width_multiple
+        hb = (int(heights[i]) + height_multiple - 1) // height_multiple if heights is not None else 0
+        return (wb, hb)
+
+    order = sorted(range(n), key=lambda i: (bucket(i), int(heights[i]) if heights is not None else 0, int(widths[i]), i))
     batches, cur, cur_bucket = [], [], None
     for i in order:
-        bucket = (int(widths[i]) + width_multiple - 1) // width_multiple
-        cut = cur and (len(cur) >= batch_size or bucket != cur_bucket)
+        bk = bucket(i)
+        cut = cur and (len(cur) >= batch_size or bk != cur_bucket)
         if cur and not cut and max_pad_frac is not None:
-            cut = (bucket * width_multiple - widths[cur[0]]) > max_pad_frac * bucket * width_multiple
+            cut = (bk[0] * width_multiple - min(widths[j] for j in cur)) > max_pad_frac * bk[0] * width_multiple
         if cut:
             batches.append(cur)
             cur = []
         if not cur:
-            cur_bucket = bucket
+            cur_bucket = bk
         cur.append(i)
     if cur:
         batches.append(cur)
@@ -114,27 +127,35 @@ def frames_to_labels(frames_row):
 class LineEvaluator:
     """model: dtlr_b200 DINO in eval mode on a CUDA device; charset: list of characters (class c -> charset[c])."""
 
-    def __init__(self, model, charset, batch_size=64, width_multiple=32, eps=None):
+    def __init__(self, model, charset, batch_size=64, width_multiple=32, height_multiple=8, eps=None):
         self.model = model
         self.charset = list(charset)
         self.batch_size = batch_size
         self.width_multiple = width_multiple
+        self.height_multiple = height_multiple
         self.eps = eps                      # None -> 0.03 / num_classes like evaluation.py:141
         self.device = next(model.parameters()).device
-        self.prep = GpuPreprocessor(self.device, pad_w_multiple=width_multiple)
+        # one captured CUDA graph per (batch size, width bucket): keep them all alive over a data set
+        model.max_cuda_graphs = max(getattr(model, "max_cuda_graphs", 8), 48)
+        self.prep = GpuPreprocessor(self.device, pad_w_multiple=width_multiple, pad_h_multiple=height_multiple)
+        self.up = torch.cuda.Stream(device=self.device)         # H2D + input kernel of batch i+1 overlap the forward of batch i
         self.down = torch.cuda.Stream(device=self.device)
         self._host = {}                     # pinned result buffers: (shape, parity) -> tensor (2-deep ring per shape)
+
+    def batches(self, images):
+        """the index lists `predict` runs, in order"""
+        return bucket_batches([int(im.shape[1]) for im in images], self.batch_size, self.width_multiple,
+                              heights=[int(im.shape[0]) for im in images], height_multiple=self.height_multiple)
 
     @torch.no_grad()
     def predict(self, images):
         """images: list of resized u8 (H,W[,1|3]) arrays.  Returns the predicted class-id list of every image, input order."""
-        widths = [int(im.shape[1]) for im in images]
-        batches = bucket_batches(widths, self.batch_size, self.width_multiple)
+        batches = self.batches(images)
         preds = [None] * len(images)
         compute = torch.cuda.current_stream(self.device)
         pending = None                      # (indices, pinned frames, event) of the previous batch
         for n, idx in enumerate(batches):
-            samples = self.prep([images[i] for i in idx])
+            samples = self.prep([images[i] for i in idx], stream=self.up)
             out = self.model(samples)
             C = out["pred_logits"].shape[-1]
             frames = ops.ctc_decode(out["pred_logits"], out["pred_boxes"], self.eps if self.eps is not None else 0.03 / C)

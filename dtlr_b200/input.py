@@ -66,13 +66,16 @@ def pack_u8(images):
 
 class GpuPreprocessor:
     """host u8 images -> NestedTensor on `device` (one pinned staging buffer, one H2D copy, one kernel).
-    `pad_w_multiple` rounds the batch width up (fewer distinct shapes -> fewer captured CUDA graphs); the extra columns are
-    ordinary padding (mask True), exactly what a wider image in the batch would cause in the reference."""
+    `pad_w_multiple` / `pad_h_multiple` round the batch size up (fewer distinct shapes -> fewer captured CUDA graphs); the extra
+    columns / rows are ordinary padding (mask True), exactly what a larger image in the batch would cause in the reference.
+    With `stream=` the copy and the kernel run on that side stream (overlapping whatever the caller's stream is computing) and the
+    caller's current stream is made to wait for them."""
 
-    def __init__(self, device, mean=IMAGENET_MEAN, std=IMAGENET_STD, pad_w_multiple=1):
+    def __init__(self, device, mean=IMAGENET_MEAN, std=IMAGENET_STD, pad_w_multiple=1, pad_h_multiple=1):
         self.device = torch.device(device)
         self.mean, self.std = tuple(mean), tuple(std)
         self.pad_w_multiple = int(pad_w_multiple)
+        self.pad_h_multiple = int(pad_h_multiple)
         self._stage = None
         self._meta = None
         self._copied = None             # event after the last H2D copies: the pinned staging buffers may be rewritten after it
@@ -85,25 +88,33 @@ class GpuPreprocessor:
             self._meta = torch.empty(max(3 * B, 384), dtype=torch.int64).pin_memory()
         return self._stage, self._meta
 
-    def __call__(self, images):
+    def __call__(self, images, stream=None):
         packed, offsets, sizes, ch = pack_u8(images)
         B = len(sizes)
-        Hmax = int(sizes[:, 0].max())
-        Wmax = int(sizes[:, 1].max())
-        m = self.pad_w_multiple
-        Wpad = (Wmax + m - 1) // m * m
+        mh, mw = self.pad_h_multiple, self.pad_w_multiple
+        Hpad = (int(sizes[:, 0].max()) + mh - 1) // mh * mh
+        Wpad = (int(sizes[:, 1].max()) + mw - 1) // mw * mw
         if self._copied is not None:
             self._copied.synchronize()
         stage, meta = self._staging(packed.size, B)
         stage[:packed.size].copy_(torch.from_numpy(packed))
         meta[:3 * B].copy_(torch.from_numpy(np.concatenate((offsets, sizes[:, 0].astype(np.int64), sizes[:, 1].astype(np.int64)))))
-        d_packed = stage[:packed.size].to(self.device, non_blocking=True)       # ONE u8 copy + one 24*B-byte copy
-        d_meta = meta[:3 * B].to(self.device, non_blocking=True)
-        self._copied = torch.cuda.Event()
-        self._copied.record(torch.cuda.current_stream(self.device))
-        d_off = d_meta[:B]
-        hw = torch.stack((d_meta[B:2 * B], d_meta[2 * B:]), 1).to(torch.int32).contiguous()
+        consumer = torch.cuda.current_stream(self.device)
+        work = stream if stream is not None else consumer
+        with torch.cuda.stream(work):
+            d_packed = stage[:packed.size].to(self.device, non_blocking=True)       # ONE u8 copy + one 24*B-byte copy
+            d_meta = meta[:3 * B].to(self.device, non_blocking=True)
+            self._copied = torch.cuda.Event()
+            self._copied.record(work)
+            hw = torch.stack((d_meta[B:2 * B], d_meta[2 * B:]), 1).to(torch.int32).contiguous()
+            out, mask = ops.preprocess_u8(d_packed, d_meta[:B].contiguous(), hw, ch, B, Hpad, Wpad, self.mean, self.std)
+            if stream is not None:
+                done = torch.cuda.Event()
+                done.record(work)
+        if stream is not None:
+            consumer.wait_event(done)
+            out.record_stream(consumer)
+            mask.record_stream(consumer)
         self.h2d_bytes = packed.size + 24 * B
-        out, mask = ops.preprocess_u8(d_packed, d_off.contiguous(), hw, ch, B, Hmax, Wpad, self.mean, self.std)
-        same = bool((sizes[:, 0] == Hmax).all() and (sizes[:, 1] == Wpad).all())
+        same = bool((sizes[:, 0] == Hpad).all() and (sizes[:, 1] == Wpad).all())
         return NestedTensor(out, mask, nopad=same)

@@ -29,12 +29,14 @@ def to_tensor_normalize(img_u8_hwc, mean, std):
     return x.sub(m).div(s)
 
 
-def nested_batch(tensors, pad_to_w=None):
-    """util/misc.py:375-397: zero-pad (C,h,w) tensors to the batch max, mask True on padding."""
+def nested_batch(tensors, pad_to_w=None, pad_to_h=None):
+    """util/misc.py:375-397: zero-pad (C,h,w) tensors to the batch max (or a larger given size), mask True on padding."""
     h = max(int(t.shape[1]) for t in tensors)
     w = max(int(t.shape[2]) for t in tensors)
     if pad_to_w is not None:
         w = max(w, pad_to_w)
+    if pad_to_h is not None:
+        h = max(h, pad_to_h)
     out = torch.zeros((len(tensors), tensors[0].shape[0], h, w), dtype=tensors[0].dtype)
     mask = torch.ones((len(tensors), h, w), dtype=torch.bool)
     for t, o, m in zip(tensors, out, mask):

@@ -40,6 +40,14 @@ def test_gpu_preprocess_width_rounding_full_size_and_all_u8_values():
     ref, mask = io_ref.nested_batch([io_ref.to_tensor_normalize(im, MEAN, STD) for im in imgs], pad_to_w=1024)
     assert nt.tensors.shape == (5, 3, 40, 1024)
     assert torch.equal(nt.tensors.cpu(), ref) and torch.equal(nt.mask.cpu(), mask)
+    # odd batch width (scalar store path), height rounding, and the side-stream variant (caller's stream waits for it)
+    side = torch.cuda.Stream()
+    odd = [imgs[2], imgs[3], imgs[4][:, :33]]
+    for stream in (None, side):
+        nt = GpuPreprocessor("cuda", pad_h_multiple=16)(odd, stream=stream)
+        ref, mask = io_ref.nested_batch([io_ref.to_tensor_normalize(im, MEAN, STD) for im in odd], pad_to_h=48)
+        assert nt.tensors.shape == (3, 3, 48, 37)
+        assert torch.equal(nt.tensors.cpu(), ref) and torch.equal(nt.mask.cpu(), mask)
     same = GpuPreprocessor("cuda")([imgs[1], imgs[1]])                                   # equal sizes -> dense-batch hint
     assert same.nopad and not bool(same.mask.any())
 
@@ -92,10 +100,13 @@ def test_bucketed_evaluator_equals_direct_batches_and_oracle_metrics():
         preds = res["preds"]
         assert len(preds) == len(images) and all(p is not None for p in preds)
         seen = 0
-        for idx in evaluation.bucket_batches(widths, 3, 32):
+        batches = ev.batches(images)
+        assert batches == evaluation.bucket_batches(widths, 3, 32, heights=[im.shape[0] for im in images], height_multiple=8)
+        for idx in batches:
             ts = [io_ref.to_tensor_normalize(images[i], MEAN, STD) for i in idx]
             wpad = (max(widths[i] for i in idx) + 31) // 32 * 32
-            x, m = io_ref.nested_batch(ts, pad_to_w=wpad)
+            hpad = (max(images[i].shape[0] for i in idx) + 7) // 8 * 8
+            x, m = io_ref.nested_batch(ts, pad_to_w=wpad, pad_to_h=hpad)
             with torch.no_grad():
                 out = model(NestedTensor(x.cuda(), m.cuda()))
                 frames = ops.ctc_decode(out["pred_logits"], out["pred_boxes"], 0.03 / C).cpu()

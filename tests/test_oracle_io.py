@@ -77,6 +77,14 @@ def test_bucket_batches_properties():
             assert len({(w + mult - 1) // mult for w in ws}) == 1
         firsts = [widths[b[0]] for b in batches]
         assert firsts == sorted(firsts)
+    heights = rng.integers(40, 200, len(widths)).tolist()                      # real evaluation geometry: (W, H) buckets
+    batches = bucket_batches(widths, 16, 64, heights=heights, height_multiple=8)
+    assert sorted(i for b in batches for i in b) == list(range(len(widths)))
+    for b in batches:
+        assert 1 <= len(b) <= 16
+        assert len({((widths[i] + 63) // 64, (heights[i] + 7) // 8) for i in b}) == 1
+    with pytest.raises(ValueError):
+        bucket_batches([1, 2], 4, heights=[1])
     assert bucket_batches([], 4) == []
     capped = bucket_batches([100, 101, 127, 128], 8, 128, max_pad_frac=0.1)
     assert [len(b) for b in capped] == [2, 2] or sum(len(b) for b in capped) == 4
