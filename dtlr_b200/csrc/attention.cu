@@ -111,9 +111,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // MT = 16-query m-tiles per warp: every K / V fragment fetched from shared memory feeds MT MMAs (MT = 2 halves the
 // ldmatrix traffic per FLOP, which is what bounds the MT = 1 version).
-// PIPE: the S = Q K^T MMAs of key block kb+1 are issued before the softmax of block kb (two ping-pong score arrays, the loop body
-// instantiated twice), so that the tensor pipe works under the MUFU / FMNMX / shuffle chain of the softmax instead of idling in
-// front of it -- the un-pipelined kernel is latency bound (ncu: 0.35 IPC per scheduler, MUFU 39 % busy, 4 warps per scheduler).
+// PIPE (experiment, opt-in with dtlr_debug_flags(16384)): the S = Q K^T MMAs of key block kb+1 are issued before the softmax of block
+// kb (two ping-pong score arrays, the loop body instantiated twice), so that the tensor pipe could work under the MUFU / FMNMX /
+// shuffle chain of the softmax.  Measured SLOWER on B200 (B=64, Q=900: 281.6 us vs 255.4 us un-pipelined, same box): the second
+// score array takes the kernel from 86 to 128 registers (the cap at 512 threads) with 60 bytes of spills, and ptxas already
+// interleaves the P.V MMAs with the exponentials of the same block -- the four warps per scheduler cover the rest.
 template <int MT, bool PIPE>
 __global__ void __launch_bounds__(FA_WARPS * 32)
 mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off, const __nv_bfloat16* __restrict__ v, int ld_v,
@@ -315,7 +317,7 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         const int splits = (Q + per_round - 1) / per_round;
         int q_per_cta = ((Q + splits - 1) / splits + 16 * FA_MT - 1) / (16 * FA_MT) * (16 * FA_MT);
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
-        auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, false> : mha_flash_bf16_kernel<FA_MT, true>;   // flag 16384: un-pipelined (A/B)
+        auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, true> : mha_flash_bf16_kernel<FA_MT, false>;   // flag 16384: QK-pipelined variant (A/B)
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(FA_WARPS * 32), smem, st, (const __nv_bfloat16*)qk, ld_qk, k_off,
                                    (const __nv_bfloat16*)v, ld_v, (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));

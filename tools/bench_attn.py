@@ -10,7 +10,7 @@ B, Q, heads, d = 64, 900, 8, 256
 qk = torch.randn(B * Q, 2 * d, device="cuda").bfloat16()
 v = torch.randn(B * Q, d, device="cuda").bfloat16()
 fl = 4.0 * B * heads * Q * Q * 32
-for name, impl, flags in (("mma.sync flash, software-pipelined QK (default)", "flash", 0), ("mma.sync flash, un-pipelined", "flash", 16384),
+for name, impl, flags in (("mma.sync flash (default)", "flash", 0), ("mma.sync flash, QK of the next key block software-pipelined", "flash", 16384),
                           ("tcgen05 single-pass", "tc", 0), ("tcgen05 two-pass", "tc", 256)):
     ops.ATTN_IMPL = impl
     _lib.lib().dtlr_debug_flags(flags)
