@@ -327,7 +327,7 @@ def main():
                      "algorithmic_bytes_per_launch": round(msda_bytes / max(1, len(msda_events))),
                      "binding_resource": "shared-memory gather bandwidth (4 KB of taps per (query, head) at 128 B/clk/SM), see DESIGN.md 3.1"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only; --impl reference gives the N > 1 arm
         ips, sec = cpu_baseline_run(8, 3, 1)
         cpu = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "3 forwards of 8 images (3x40x1024) after 1 warm-up, oracle/dino_ref.py + oracle/msda_ref.c, fp32"}
