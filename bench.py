@@ -160,6 +160,8 @@ def main():
         return
 
     from dtlr_b200 import dist_util
+    # keep stdout to the ONE JSON line: NCCL prints its version banner there when the environment asks for NCCL_DEBUG=VERSION/INFO
+    os.environ["NCCL_DEBUG"] = os.environ.get("DTLR_NCCL_DEBUG", "WARN")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist_util.init("nccl", device)
