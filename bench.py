@@ -304,7 +304,7 @@ def main():
                      "launches_timed": n_gemm, "share_of_step": round(gemm_ms / n_prof / ms_step, 3),
                      "algorithmic_flops_per_step": gemm_flops / n_prof,
                      "note": "K <= 256 for ~150 of these launches (arithmetic intensity <= 128 flop/B): HBM / epilogue bound, not tensor bound -- DESIGN.md 3.2"}
-    # the dominant kernel of the step (profiles/r1_launches_step_v5.txt: 18.9 %): the fused FFN block, one launch per encoder /
+    # the dominant kernel of the step (profiles/r1_launches_step_v6.txt: 18.9 %): the fused FFN block, one launch per encoder /
     # decoder layer; algorithmic FLOPs 4*M*hid*256 per launch; `traffic` = DRAM bytes of one launch from
     # the ncu --set full capture in profiles/r1_ffn_ncu.txt
     if ffn_events:

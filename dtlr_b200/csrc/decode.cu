@@ -15,20 +15,42 @@ __device__ __forceinline__ float warp_sum_d(float v) {
     return v;
 }
 
-// one warp per (b,q): label = 0 (blank) or 1 + argmax class
-__global__ void ctc_row_label_kernel(const float* __restrict__ logits, int ld, int C, float eps, float pscale,
-                                     int* __restrict__ label, float* __restrict__ row_sum, long long rows) {
+// one warp per (b,q): label = 0 (blank) or 1 + argmax class.  HBM bound (B*Q*C*4 bytes read once; 848 MB at C = 7356, B = 32):
+// VEC = 4 reads the row with 16-byte loads, two per lane in flight per iteration (the scalar version reached 26 % of the copy
+// peak at C = 7356: too few bytes in flight per warp); rows are 16-byte aligned when ld % 4 == 0.  Exact expf: the blank / class
+// decision is compared bit-for-bit with the reference's argmax.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ctc_row_label_kernel(const float* __restrict__ logits, int ld, int C, float eps, float pscale,
+                     int* __restrict__ label, float* __restrict__ row_sum, long long rows) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const float* x = logits + (size_t)row * ld;
     float s = 0.f, best = -1.f;
     int arg = 0x7fffffff;
-    for (int c = lane; c < C; c += 32) {
-        const float p = pscale * (1.f / (1.f + expf(-x[c])));
+    auto take = [&](const float xv, const int c) {
+        const float p = pscale * (1.f / (1.f + expf(-xv)));
         s += p;
-        if (p > best) { best = p; arg = c; }
+        if (p > best) { best = p; arg = c; }          // strict: the first maximum of this lane's ascending indices wins
+    };
+    int c0 = 0;
+    if (VEC == 4) {
+        const int n4 = C >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        int i = lane;
+        for (; i + 32 < n4; i += 64) {                // two independent 16-byte loads per lane per iteration
+            const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + 32);
+            take(a.x, 4 * i); take(a.y, 4 * i + 1); take(a.z, 4 * i + 2); take(a.w, 4 * i + 3);
+            take(b.x, 4 * i + 128); take(b.y, 4 * i + 129); take(b.z, 4 * i + 130); take(b.w, 4 * i + 131);
+        }
+        if (i < n4) {
+            const float4 a = __ldg(x4 + i);
+            take(a.x, 4 * i); take(a.y, 4 * i + 1); take(a.z, 4 * i + 2); take(a.w, 4 * i + 3);
+        }
+        c0 = n4 << 2;                                  // scalar tail: C % 4 classes
     }
+    for (int c = c0 + lane; c < C; c += 32) take(x[c], c);
     s = warp_sum_d(s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -117,7 +139,11 @@ extern "C" int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* 
     DTLR_CHECK_ARG((size_t)n * 8 <= (size_t)max_smem_optin(), "ctc_decode: %d queries per line exceed the shared-memory sort", Q);
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * Q;
-    ctc_row_label_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, prob_scale, scratch_label, scratch_sum, rows);
+    // 16-byte-load kernel: opt-in (dtlr_debug_flags(32768)) until its GPU parity run is recorded
+    if ((g_debug_flags & 32768) && (ld % 4) == 0 && (((uintptr_t)logits) & 15) == 0 && C >= 4)
+        ctc_row_label_kernel<4><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, prob_scale, scratch_label, scratch_sum, rows);
+    else
+        ctc_row_label_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, ld, C, eps, prob_scale, scratch_label, scratch_sum, rows);
     DTLR_CHECK_LAUNCH();
     const size_t smem = (size_t)n * 8;
     if (smem > 48 * 1024)

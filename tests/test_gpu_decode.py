@@ -34,3 +34,22 @@ def test_matches_torch_statement(B, Q, C, eps, shift):
     decided = ((top2[..., 0] - top2[..., 1]) > 1e-6) & clear
     assert (frames.long() == ref_new.argmax(-1))[decided].all()
     assert ((s < 1 - eps).any() and (s >= 1 - eps).any()) or C <= 5      # both branches of the blank synthesis exercised
+
+
+@pytest.mark.parametrize("C,pitch", [(166, 168), (7355, 7356), (4, 4), (1001, 1004)])
+def test_pitched_rows_take_the_vector_path_and_match_contiguous_rows(C, pitch):
+    """engine layout: class rows padded to a multiple of 4 floats (166 -> 168) run the 16-byte-load kernel with a scalar tail of
+    C % 4 classes; same frames / new_pred_logits as the contiguous (scalar-load) call and as the torch statement."""
+    g = torch.Generator(device="cuda").manual_seed(C)
+    buf = torch.randn(2, 333, pitch, device="cuda", generator=g) * 2.0 - (6.0 if C < 2000 else 10.5)
+    logits = buf[:, :, :C]
+    boxes = torch.rand(2, 333, 4, device="cuda", generator=g)
+    f_vec, n_vec = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)
+    f_sc, n_sc = ops.ctc_decode(logits.contiguous() if C % 4 else logits.contiguous()[:, :, :C], boxes, 0.003, want_new_pred=True)
+    ref_new = dino.ctc_view(logits, boxes, 0.003)
+    s = torch.gather(logits.sigmoid().sum(-1), 1, torch.sort(boxes[:, :, 0])[1])
+    clear = (s - (1 - 0.003)).abs() > 1e-4
+    top2 = ref_new.topk(2, dim=-1)[0]
+    decided = ((top2[..., 0] - top2[..., 1]) > 1e-6) & clear
+    assert torch.allclose(n_vec[clear], ref_new[clear], rtol=2e-5, atol=1e-7)
+    assert (f_vec.long() == ref_new.argmax(-1))[decided].all() and (f_vec == f_sc)[decided].all()
