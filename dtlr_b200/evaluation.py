@@ -118,6 +118,45 @@ def bucket_batches(widths, batch_size, width_multiple=32, max_pad_frac=None, hei
     return batches
 
 
+def shard_batches(batches, costs, rank, world):
+    """multi-GPU evaluation (lines are independent -- no data-path collective): deterministic assignment of whole
+    batches to ranks, largest cost first onto the least-loaded rank (costs: e.g. padded pixels per batch), so every rank computes
+    the same assignment locally and the per-rank loads differ by at most one batch.  Returns this rank's batches, in the original
+    relative order."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world")
+    if len(costs) != len(batches):
+        raise ValueError("one cost per batch")
+    load = [0] * world
+    owner = [0] * len(batches)
+    for b in sorted(range(len(batches)), key=lambda i: (-costs[i], i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[b] = r
+        load[r] += costs[b]
+    return [batches[i] for i in range(len(batches)) if owner[i] == rank]
+
+
+def gather_predictions(preds, group=None):
+    """every rank passes its list with None at the lines it did not evaluate; returns the complete list on every rank
+    (`all_gather_object` of the host-side label lists -- the only communication of a sharded evaluation)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return preds
+    mine = {i: p for i, p in enumerate(preds) if p is not None}
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, mine, group=group)
+    out = [None] * len(preds)
+    for part in parts:
+        for i, p in part.items():
+            if out[i] is not None:
+                raise RuntimeError("line %d was evaluated by two ranks" % i)
+            out[i] = p
+    missing = [i for i, p in enumerate(out) if p is None]
+    if missing:
+        raise RuntimeError("no rank evaluated lines %s..." % missing[:5])
+    return out
+
+
 def frames_to_labels(frames_row):
     """one row of int32 frame labels (0 = blank, c+1 = class c) -> class ids (engine.py:523-529 / evaluation.py:152-158)"""
     return [int(v) - 1 for v in frames_row if int(v) != 0]
@@ -148,9 +187,15 @@ class LineEvaluator:
                               heights=[int(im.shape[0]) for im in images], height_multiple=self.height_multiple)
 
     @torch.no_grad()
-    def predict(self, images):
-        """images: list of resized u8 (H,W[,1|3]) arrays.  Returns the predicted class-id list of every image, input order."""
+    def predict(self, images, rank=0, world=1):
+        """images: list of resized u8 (H,W[,1|3]) arrays.  Returns the predicted class-id list of every image, input order.
+        With world > 1 only this rank's share of the batches is evaluated (None elsewhere; `gather_predictions` completes it)."""
         batches = self.batches(images)
+        if world > 1:
+            wm, hm = self.width_multiple, self.height_multiple
+            costs = [len(b) * (-(-max(int(images[i].shape[0]) for i in b) // hm) * hm) * (-(-max(int(images[i].shape[1]) for i in b) // wm) * wm)
+                     for b in batches]
+            batches = shard_batches(batches, costs, rank, world)
         preds = [None] * len(images)
         compute = torch.cuda.current_stream(self.device)
         pending = None                      # (indices, pinned frames, event) of the previous batch
@@ -185,10 +230,16 @@ class LineEvaluator:
             row = arr[r]
             preds[i] = (row[row != 0] - 1).tolist()
 
-    def evaluate(self, images, gt_labels):
+    def evaluate(self, images, gt_labels, distributed=False):
         """gt_labels: list of class-id lists.  Returns dict(cer=sum(dist)/sum(len) over post-processed strings (the "DAN CER" of
-        evaluation.py:529), cer_txt=mean per-line raw CER (:519-520), wer=mean per-line WER (:531-535), preds, pred_strs)."""
-        preds = self.predict(images)
+        evaluation.py:529), cer_txt=mean per-line raw CER (:519-520), wer=mean per-line WER (:531-535), preds, pred_strs).
+        distributed=True (torch.distributed initialised, one process per GPU, every rank passes the SAME lists): the batches are
+        sharded over the ranks, the label lists gathered on the host, and every rank returns the full metrics."""
+        if distributed:
+            import torch.distributed as dist
+            preds = gather_predictions(self.predict(images, dist.get_rank(), dist.get_world_size()))
+        else:
+            preds = self.predict(images)
         cs = self.charset
         dist_sum = len_sum = 0
         cer_txt, wer = [], []

@@ -54,3 +54,50 @@ def test_reference_arm_runs_on_rank0_only():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
+
+
+def _eval_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from dtlr_b200 import dist_util, evaluation
+    dist_util.init("gloo")
+    rng = np.random.default_rng(0)                                     # every rank sees the SAME data set
+    heights, widths = rng.integers(48, 200, 101).tolist(), rng.integers(900, 1334, 101).tolist()
+    batches = evaluation.bucket_batches(widths, 8, 64, heights=heights, height_multiple=16)
+    costs = [len(b) * max(heights[i] for i in b) * max(widths[i] for i in b) for b in batches]
+    mine = evaluation.shard_batches(batches, costs, rank, world)
+    preds = [None] * 101
+    for b in mine:
+        for i in b:
+            preds[i] = [i % 7, heights[i] % 5]                         # stand-in for the GPU forward + decode of line i
+    full = evaluation.gather_predictions(preds)
+    q.put((rank, sum(len(b) for b in mine), sum(costs[batches.index(b)] for b in mine), full))
+    dist_util.barrier()
+    dist_util.shutdown()
+
+
+def test_sharded_evaluation_two_ranks_gloo():
+    """multi-GPU evaluation shards whole batches over the ranks (no data-path collective) and gathers the host-side label lists:
+    every line evaluated exactly once, both ranks end with the complete, identical list, loads balanced."""
+    from dtlr_b200 import evaluation
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, 29541, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] + res[1][1] == 101 and res[0][1] > 0 and res[1][1] > 0
+    assert res[0][3] == res[1][3] and all(p is not None for p in res[0][3])
+    assert abs(res[0][2] - res[1][2]) <= 0.15 * (res[0][2] + res[1][2])          # greedy balance by padded pixels
+    # single-process properties of the assignment
+    batches = [[0, 1], [2], [3, 4, 5], [6]]
+    parts = [evaluation.shard_batches(batches, [5, 1, 9, 2], r, 3) for r in range(3)]
+    assert sorted(b for p in parts for b in map(tuple, p)) == sorted(map(tuple, batches))
+    assert evaluation.shard_batches(batches, [1, 1, 1, 1], 0, 1) == batches
+    import pytest
+    with pytest.raises(ValueError):
+        evaluation.shard_batches(batches, [1], 0, 2)

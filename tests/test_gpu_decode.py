@@ -44,7 +44,12 @@ def test_pitched_rows_take_the_vector_path_and_match_contiguous_rows(C, pitch):
     buf = torch.randn(2, 333, pitch, device="cuda", generator=g) * 2.0 - (6.0 if C < 2000 else 10.5)
     logits = buf[:, :, :C]
     boxes = torch.rand(2, 333, 4, device="cuda", generator=g)
-    f_vec, n_vec = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)
+    from dtlr_b200 import _lib
+    _lib.lib().dtlr_debug_flags(32768)              # the 16-byte-load row kernel
+    try:
+        f_vec, n_vec = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)
+    finally:
+        _lib.lib().dtlr_debug_flags(0)
     f_sc, n_sc = ops.ctc_decode(logits.contiguous() if C % 4 else logits.contiguous()[:, :, :C], boxes, 0.003, want_new_pred=True)
     ref_new = dino.ctc_view(logits, boxes, 0.003)
     s = torch.gather(logits.sigmoid().sum(-1), 1, torch.sort(boxes[:, :, 0])[1])
