@@ -739,12 +739,21 @@ __device__ __forceinline__ void red_add_f32x4(float* p, const float a, const flo
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int PTS>      // sampling points per level (L * PTS == 16)
-__global__ void __launch_bounds__(256)
-msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
-                    const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
-                    float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
-                    const int M, const int Lq) {
+// same reduction without the "memory" clobber: grad_value never aliases the buffers this kernel loads from, so the compiler may
+// keep later loads in flight across it (used by the GROUPED variant only)
+__device__ __forceinline__ void red_add_f32x4_nc(float* p, const float a, const float b, const float c, const float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+
+// GROUPED (opt-in, dtlr_debug_flags(65536); NOT yet run on a GPU -- written from the ncu reading of the default variant,
+// profiles/r1_msda_bwd_ncu.txt: 16 warps per SM, one value load in flight per warp because the clobbered `red` asm pins the
+// next point's load behind it): the four value loads of a group of 4 points are issued before any of their arithmetic and the
+// reductions carry no memory clobber, so a warp keeps 4 L2 round trips in flight instead of 1.  Arithmetic per point is identical.
+template <int PTS, bool GROUPED>      // PTS: sampling points per level (L * PTS == 16)
+__device__ __forceinline__ void msda_bwd_d32_body(const float* __restrict__ value, const float* __restrict__ loc,
+                                                  const float* __restrict__ attn, const float* __restrict__ gout,
+                                                  float* __restrict__ gvalue, float* __restrict__ gloc, float* __restrict__ gattn,
+                                                  const Levels& lv, const long long total, const int S, const int M, const int Lq) {
     const int lane = threadIdx.x & 31;
     const int k = lane >> 3, j = lane & 7;
     const bool ky = k >> 1, kx = k & 1;
@@ -774,6 +783,42 @@ msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ l
             ppix = (unsigned)(pstart + (y0 + 1) * pW + (x0 + 1)) | (bits << 24);
         }
         float r[48];
+        if (GROUPED) {
+#pragma unroll
+            for (int g0 = 0; g0 < 16; g0 += 4) {
+                float4 v[4];
+                float wy[4], wx[4], aw[4];
+                int off[4];                              // element offset of this lane's 4 channels of its corner; -1: corner not on the map
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pt = g0 + i;
+                    const unsigned pix = __shfl_sync(0xffffffffu, ppix, pt);
+                    const float fy = __shfl_sync(0xffffffffu, pfy, pt);
+                    const float fx = __shfl_sync(0xffffffffu, pfx, pt);
+                    aw[i] = __shfl_sync(0xffffffffu, paw, pt);
+                    const int W = lv.W[pt / PTS];
+                    wy[i] = ky ? fy : 1.f - fy;
+                    wx[i] = kx ? fx : 1.f - fx;
+                    const bool ok = (pix >> (24 + k)) & 1u;
+                    const int pixel = (int)(pix & 0xffffffu) - W - 1 + (ky ? W : 0) + (kx ? 1 : 0);
+                    off[i] = ok ? pixel * M * 32 : -1;
+                    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(value + voff + (size_t)off[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pt = g0 + i;
+                    const int W = lv.W[pt / PTS], H = lv.H[pt / PTS];
+                    const float d = g.x * v[i].x + g.y * v[i].y + g.z * v[i].z + g.w * v[i].w;      // 0 for an off-map corner
+                    if (off[i] >= 0) {
+                        const float c = wy[i] * wx[i] * aw[i];
+                        red_add_f32x4_nc(gvalue + voff + (size_t)off[i], c * g.x, c * g.y, c * g.z, c * g.w);
+                    }
+                    r[3 * pt] = wy[i] * wx[i] * d;
+                    r[3 * pt + 1] = (kx ? wy[i] : -wy[i]) * d * aw[i] * (float)W;
+                    r[3 * pt + 2] = (ky ? wx[i] : -wx[i]) * d * aw[i] * (float)H;
+                }
+            }
+        } else
 #pragma unroll
         for (int pt = 0; pt < 16; ++pt) {
             const unsigned pix = __shfl_sync(0xffffffffu, ppix, pt);
@@ -802,6 +847,24 @@ msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ l
             *reinterpret_cast<float2*>(gloc + 2 * op) = make_float2(r[1], r[2]);
         }
     }
+}
+
+template <int PTS>
+__global__ void __launch_bounds__(256)
+msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
+                    const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
+                    float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
+                    const int M, const int Lq) {
+    msda_bwd_d32_body<PTS, false>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
+}
+
+template <int PTS>
+__global__ void __launch_bounds__(256, 2)
+msda_bwd_d32_grouped_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
+                            const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
+                            float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
+                            const int M, const int Lq) {
+    msda_bwd_d32_body<PTS, true>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1003,7 +1066,9 @@ extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, cons
             kern<<<grid, 256, 0, st>>>((const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out,
                                        (float*)grad_value, (float*)grad_loc, (float*)grad_attn, lv, warps, S, M, Lq);
         };
-        switch (P) {
+        if ((g_debug_flags & 65536) && P == 4) {            // grouped-load variant: opt-in until it has a GPU parity run
+            launch(msda_bwd_d32_grouped_kernel<4>);
+        } else switch (P) {
             case 2: launch(msda_bwd_d32_kernel<2>); break;
             case 4: launch(msda_bwd_d32_kernel<4>); break;
             case 8: launch(msda_bwd_d32_kernel<8>); break;

@@ -9,7 +9,7 @@ No reference source enters the repository: the sources are read where they lie u
 longer compiles against torch 2.x (`AT_DISPATCH_FLOATING_TYPES(value.type(), ...)` at cuda/ms_deform_attn_cuda.cu:64,134 --
 DeprecatedTypeProperties is no longer convertible to ScalarType) is patched in a scratch copy under /tmp (`.type()` ->
 `.scalar_type()` on those two dispatch lines only).  Output: oracle/_ref/MultiScaleDeformableAttention.so (git-ignored, travels
-to the GPU box with the snapshot).  Only tests/ and tools/bench_msda_vs_ref.py load it.
+to the GPU box with the snapshot).  Only tests/ and tests/perf_msda_vs_ref_cuda.py load it.
 
     python oracle/build_ref_cuda.py          (build container: needs /root/reference, nvcc, torch headers; ~2 min)
 """

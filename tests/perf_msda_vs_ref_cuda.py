@@ -7,7 +7,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 from dtlr_b200 import msda  # noqa: E402
 from oracle import build_ref_cuda  # noqa: E402   (dev tooling: the reference kernel is the measured baseline here)
 

@@ -45,9 +45,10 @@ def test_pitched_rows_take_the_vector_path_and_match_contiguous_rows(C, pitch):
     logits = buf[:, :, :C]
     boxes = torch.rand(2, 333, 4, device="cuda", generator=g)
     from dtlr_b200 import _lib
-    _lib.lib().dtlr_debug_flags(32768)              # the 16-byte-load row kernel
+    f_vec, n_vec = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)      # pitched rows: the 16-byte-load row kernel
+    _lib.lib().dtlr_debug_flags(32768)                                            # same pitched rows on the scalar-load kernel
     try:
-        f_vec, n_vec = ops.ctc_decode(logits, boxes, 0.003, want_new_pred=True)
+        f_sc2 = ops.ctc_decode(logits, boxes, 0.003)
     finally:
         _lib.lib().dtlr_debug_flags(0)
     f_sc, n_sc = ops.ctc_decode(logits.contiguous() if C % 4 else logits.contiguous()[:, :, :C], boxes, 0.003, want_new_pred=True)
@@ -57,4 +58,4 @@ def test_pitched_rows_take_the_vector_path_and_match_contiguous_rows(C, pitch):
     top2 = ref_new.topk(2, dim=-1)[0]
     decided = ((top2[..., 0] - top2[..., 1]) > 1e-6) & clear
     assert torch.allclose(n_vec[clear], ref_new[clear], rtol=2e-5, atol=1e-7)
-    assert (f_vec.long() == ref_new.argmax(-1))[decided].all() and (f_vec == f_sc)[decided].all()
+    assert (f_vec.long() == ref_new.argmax(-1))[decided].all() and (f_vec == f_sc)[decided].all() and (f_vec == f_sc2)[decided].all()
