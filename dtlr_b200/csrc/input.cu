@@ -91,3 +91,69 @@ extern "C" int dtlr_preprocess_u8(const uint8_t* packed, const long long* offset
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 8-bit bilinear resize with PIL's arithmetic: the reference resizes every line on the host with
+// torchvision F.resize -> PIL Image.resize(BILINEAR) (datasets/transforms.py:107-108, Pillow src/libImaging/Resample.c): a
+// triangle filter whose support grows with the down-scale factor, coefficients in 22-bit fixed point, a horizontal pass into an
+// 8-bit intermediate and a vertical pass.  The coefficient tables are built on the host in double precision exactly as
+// precompute_coeffs / normalize_coeffs_8bpc do (dtlr_b200/input.py: resample_tables); the two kernels below are the integer
+// multiply-accumulate passes, so the result is bit-identical to PIL.  One launch pair handles a whole ragged batch.
+namespace dtlr {
+
+constexpr int RS_META = 12;   // int64 per image: in_off, tmp_off, out_off, h, w, oh, ow, xtab_off, ytab_off, ksx, ksy, reserved
+constexpr int RS_PRECISION_BITS = 32 - 8 - 2;
+
+// table of one axis at tab + off: xmin[n_out], count[n_out], coef[n_out * ksize]
+template <int CH, bool VERTICAL>
+__global__ void __launch_bounds__(128)
+resize_pass_kernel(const uint8_t* __restrict__ src_base, uint8_t* __restrict__ dst_base, const long long* __restrict__ meta,
+                   const int* __restrict__ tab) {
+    const long long* m = meta + (size_t)blockIdx.z * RS_META;
+    const int h = (int)m[3], w = (int)m[4], oh = (int)m[5], ow = (int)m[6];
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    // horizontal: (h, w) -> (h, ow);  vertical: (h, ow) -> (oh, ow)
+    const int rows = VERTICAL ? oh : h;
+    if (ox >= ow || oy >= rows) return;
+    const uint8_t* src = src_base + (VERTICAL ? m[1] : m[0]);
+    uint8_t* dst = dst_base + (VERTICAL ? m[2] : m[1]);
+    const int n_out = VERTICAL ? oh : ow, ks = (int)(VERTICAL ? m[10] : m[9]);
+    const int* t = tab + (VERTICAL ? m[8] : m[7]);
+    const int o = VERTICAL ? oy : ox;
+    const int lo = t[o], cnt = t[n_out + o];
+    const int* k = t + 2 * n_out + (size_t)o * ks;
+    int acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 1 << (RS_PRECISION_BITS - 1);
+    for (int i = 0; i < cnt; ++i) {
+        const int kv = k[i];
+        const uint8_t* p = VERTICAL ? src + ((size_t)(lo + i) * ow + ox) * CH : src + ((size_t)oy * w + lo + i) * CH;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] += (int)p[c] * kv;
+    }
+    uint8_t* q = dst + ((size_t)oy * ow + ox) * CH;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = (uint8_t)min(255, max(0, acc[c] >> RS_PRECISION_BITS));
+}
+
+}  // namespace dtlr
+
+extern "C" int dtlr_resize_u8_bilinear(const uint8_t* in, const long long* meta, const int* tables, uint8_t* tmp, uint8_t* out,
+                                       int B, int channels, int max_h, int max_oh, int max_ow, void* stream) {
+    DTLR_CHECK_ARG(B >= 0 && max_h > 0 && max_oh > 0 && max_ow > 0, "resize_u8: bad sizes");
+    DTLR_CHECK_ARG(channels == 1 || channels == 3, "resize_u8: channels must be 1 or 3");
+    if (B == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(in && meta && tables && tmp && out, "resize_u8: null pointer");
+    DTLR_CHECK_ARG(B <= 65535 && max_h <= 65535 && max_oh <= 65535, "resize_u8: B or a height exceeds 65535");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 block(128), gh((max_ow + 127) / 128, max_h, B), gv((max_ow + 127) / 128, max_oh, B);
+    if (channels == 1) {
+        resize_pass_kernel<1, false><<<gh, block, 0, st>>>(in, tmp, meta, tables);
+        resize_pass_kernel<1, true><<<gv, block, 0, st>>>(tmp, out, meta, tables);
+    } else {
+        resize_pass_kernel<3, false><<<gh, block, 0, st>>>(in, tmp, meta, tables);
+        resize_pass_kernel<3, true><<<gv, block, 0, st>>>(tmp, out, meta, tables);
+    }
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}

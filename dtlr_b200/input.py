@@ -64,6 +64,105 @@ def pack_u8(images):
     return packed, offsets, sizes, ch
 
 
+PRECISION_BITS = 32 - 8 - 2          # Pillow Resample.c: 8-bit samples, 22-bit fixed-point coefficients
+
+
+def resample_tables(in_size, out_size):
+    """coefficient table of one axis of PIL's bilinear (triangle-filter, antialiased) resize, as Pillow's precompute_coeffs +
+    normalize_coeffs_8bpc build it (double precision, same operation order; the reference resizes with torchvision F.resize on PIL
+    images, datasets/transforms.py:107-108).  Returns (xmin[out] int32, count[out] int32, coef[out, ksize] int32)."""
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    center = (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    xmin = np.maximum(np.trunc(center - support + 0.5).astype(np.int64), 0)       # C (int) casts truncate toward zero
+    xmax = np.minimum(np.trunc(center + support + 0.5).astype(np.int64), in_size)
+    cnt = xmax - xmin
+    x = np.arange(ksize, dtype=np.int64)[None, :]
+    t = np.abs(((x + xmin[:, None]).astype(np.float64) - center[:, None] + 0.5) * ss)
+    w = np.where(t < 1.0, 1.0 - t, 0.0)
+    w = np.where(x < cnt[:, None], w, 0.0)
+    ww = np.zeros(out_size, dtype=np.float64)
+    for k in range(ksize):                                                          # sequential sum, as the C loop
+        ww = ww + w[:, k]
+    kk = np.where(ww[:, None] != 0.0, w / np.where(ww == 0.0, 1.0, ww)[:, None], w)
+    coef = np.trunc(0.5 + kk * float(1 << PRECISION_BITS)).astype(np.int32)         # bilinear weights are >= 0
+    coef = np.where(x < cnt[:, None], coef, 0).astype(np.int32)
+    return xmin.astype(np.int32), cnt.astype(np.int32), coef
+
+
+def apply_tables_u8(img, out_h, out_w):
+    """host check of the tables only (numpy; used by the CPU tests, never by the product path): the two integer passes the
+    CUDA kernels run, on an (H,W[,C]) u8 array."""
+    a = np.asarray(img)
+    squeeze = a.ndim == 2
+    if squeeze:
+        a = a[:, :, None]
+    for axis, n_out in ((1, out_w), (0, out_h)):
+        xmin, cnt, coef = resample_tables(a.shape[axis], n_out)
+        src = np.moveaxis(a, axis, 0).astype(np.int64)
+        idx = np.minimum(xmin[:, None] + np.arange(coef.shape[1])[None, :], src.shape[0] - 1)
+        acc = (1 << (PRECISION_BITS - 1)) + np.einsum("ok,ok...->o...", coef.astype(np.int64), src[idx])
+        a = np.moveaxis(np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8), 0, axis)
+    return a[:, :, 0] if squeeze else a
+
+
+class GpuResizer:
+    """ragged batch of u8 images -> PIL-exact bilinear resize on the GPU (dtlr_resize_u8_bilinear).  Returns the packed resized
+    images as device tensors in the layout dtlr_preprocess_u8 takes: (packed u8, int64 offsets, int32 (B,2) sizes, channels)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._tables = {}                      # (in_size, out_size) -> flat int32 table, cached across batches
+
+    def _table(self, n_in, n_out):
+        key = (int(n_in), int(n_out))
+        t = self._tables.get(key)
+        if t is None:
+            xmin, cnt, coef = resample_tables(*key)
+            t = (np.concatenate((xmin, cnt, coef.reshape(-1))).astype(np.int32), coef.shape[1])
+            if len(self._tables) > 4096:
+                self._tables.clear()
+            self._tables[key] = t
+        return t
+
+    def plan(self, images, out_sizes):
+        """host half: (packed u8 input, int64 meta [B,12], flat int32 tables, tmp bytes, out bytes, channels, input sizes) in the
+        layout include/dtlr_b200.h documents for dtlr_resize_u8_bilinear."""
+        packed, in_off, sizes, ch = pack_u8(images)
+        B = len(sizes)
+        meta = np.zeros((B, 12), dtype=np.int64)
+        tabs, tab_off, tmp_off, out_off = [], 0, 0, 0
+        for b in range(B):
+            h, w = int(sizes[b, 0]), int(sizes[b, 1])
+            oh, ow = int(out_sizes[b][0]), int(out_sizes[b][1])
+            tx, ksx = self._table(w, ow)
+            ty, ksy = self._table(h, oh)
+            meta[b] = (in_off[b], tmp_off, out_off, h, w, oh, ow, tab_off, tab_off + tx.size, ksx, ksy, 0)
+            tabs += [tx, ty]
+            tab_off += tx.size + ty.size
+            tmp_off += h * ow * ch
+            out_off += oh * ow * ch
+        return packed, meta, np.concatenate(tabs), tmp_off, out_off, ch, sizes
+
+    def __call__(self, images, out_sizes):
+        """images: list of (H,W[,1|3]) u8; out_sizes: list of (oh, ow)."""
+        packed, meta, tab, tmp_off, out_off, ch, sizes = self.plan(images, out_sizes)
+        B = len(sizes)
+        dev = self.device
+        d_in = torch.from_numpy(packed).to(dev, non_blocking=True)
+        d_meta = torch.from_numpy(meta).to(dev, non_blocking=True)
+        d_tab = torch.from_numpy(tab).to(dev, non_blocking=True)
+        d_tmp = torch.empty(max(tmp_off, 1), dtype=torch.uint8, device=dev)
+        d_out = torch.empty(max(out_off, 1), dtype=torch.uint8, device=dev)
+        ops.resize_u8_bilinear(d_in, d_meta, d_tab, d_tmp, d_out, B, ch, int(sizes[:, 0].max()),
+                               max(int(s[0]) for s in out_sizes), max(int(s[1]) for s in out_sizes))
+        hw = torch.tensor([[int(s[0]), int(s[1])] for s in out_sizes], dtype=torch.int32).to(dev, non_blocking=True)
+        return d_out, d_meta[:, 2].contiguous(), hw, ch
+
+
 class GpuPreprocessor:
     """host u8 images -> NestedTensor on `device` (one pinned staging buffer, one H2D copy, one kernel).
     `pad_w_multiple` / `pad_h_multiple` round the batch size up (fewer distinct shapes -> fewer captured CUDA graphs); the extra
@@ -87,6 +186,34 @@ class GpuPreprocessor:
         if self._meta is None or self._meta.numel() < 3 * B:
             self._meta = torch.empty(max(3 * B, 384), dtype=torch.int64).pin_memory()
         return self._stage, self._meta
+
+    def resized(self, images, size, max_size=None, stream=None):
+        """the reference's evaluation transform on the GPU: RandomResize([size], max_size) (datasets/transforms.py:78-108, PIL-exact
+        bilinear) + ToTensor + Normalize + padding.  `images` are the ORIGINAL u8 scans.  (The resize kernels have CPU-pinned tables but
+        no recorded GPU run yet -- see DESIGN.md 3.7.)"""
+        if not hasattr(self, "_resizer"):
+            self._resizer = GpuResizer(self.device)
+        arrs = [_as_u8_array(im) for im in images]
+        out_sizes = [get_size_with_aspect_ratio((a.shape[1], a.shape[0]), size, max_size) for a in arrs]
+        consumer = torch.cuda.current_stream(self.device)
+        work = stream if stream is not None else consumer
+        B = len(arrs)
+        mh, mw = self.pad_h_multiple, self.pad_w_multiple
+        Hpad = (max(s[0] for s in out_sizes) + mh - 1) // mh * mh
+        Wpad = (max(s[1] for s in out_sizes) + mw - 1) // mw * mw
+        with torch.cuda.stream(work):
+            d_packed, d_off, hw, ch = self._resizer(arrs, out_sizes)
+            out, mask = ops.preprocess_u8(d_packed, d_off, hw, ch, B, Hpad, Wpad, self.mean, self.std)
+            if stream is not None:
+                done = torch.cuda.Event()
+                done.record(work)
+        if stream is not None:
+            consumer.wait_event(done)
+            out.record_stream(consumer)
+            mask.record_stream(consumer)
+        self.h2d_bytes = sum(a.size for a in arrs)
+        same = all(s[0] == Hpad and s[1] == Wpad for s in out_sizes)
+        return NestedTensor(out, mask, nopad=same)
 
     def __call__(self, images, stream=None):
         packed, offsets, sizes, ch = pack_u8(images)

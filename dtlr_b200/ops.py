@@ -320,3 +320,12 @@ def preprocess_u8(packed_u8, offsets_i64, hw_i32, channels, B, Hmax, Wmax, mean,
     _call("dtlr_preprocess_u8", _p(packed_u8), _p(offsets_i64), _p(hw_i32), int(channels), _p(out), _p(mask), B, Hmax, Wmax, m3, s3,
           _st(packed_u8))
     return out, mask
+
+
+def resize_u8_bilinear(packed_in, meta_i64, tables_i32, tmp_u8, out_u8, B, channels, max_h, max_oh, max_ow):
+    """PIL-exact 8-bit bilinear resize of a ragged batch (csrc/input.cu); buffers are filled in place."""
+    L.require_cuda(packed_in, meta_i64, tables_i32, tmp_u8, out_u8)
+    assert packed_in.dtype == torch.uint8 and meta_i64.dtype == torch.int64 and tables_i32.dtype == torch.int32
+    _call("dtlr_resize_u8_bilinear", _p(packed_in), _p(meta_i64), _p(tables_i32), _p(tmp_u8), _p(out_u8), B, int(channels),
+          int(max_h), int(max_oh), int(max_ow), _st(packed_in))
+    return out_u8

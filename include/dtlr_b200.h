@@ -202,6 +202,14 @@ int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* boxes, int*
  * mean3/std3 are HOST pointers to 3 floats. */
 int dtlr_preprocess_u8(const uint8_t* packed, const long long* offsets, const int* hw, int channels, float* out, uint8_t* mask,
                        int B, int Hmax, int Wmax, const float* mean3_host, const float* std3_host, void* stream);
+/* 8-bit bilinear resize of a ragged batch with PIL's arithmetic (torchvision F.resize on PIL images, datasets/transforms.py:107-108;
+ * Pillow src/libImaging/Resample.c): horizontal pass in -> tmp, vertical pass tmp -> out, 22-bit fixed-point coefficients.
+ * meta (dev int64 [B,12]) per image: byte offsets of the image in `in`, `tmp`, `out`; h, w, oh, ow; int32-element offsets of its
+ * horizontal and vertical tables in `tables`; their kernel sizes ksx, ksy; one reserved word.  A table of an axis with n outputs is
+ * xmin[n], count[n], coef[n*ksize] (built on the host as precompute_coeffs / normalize_coeffs_8bpc do: dtlr_b200/input.py).
+ * Images are h x w x channels, interleaved.  tmp holds h x ow x channels per image, out oh x ow x channels. */
+int dtlr_resize_u8_bilinear(const uint8_t* in, const long long* meta, const int* tables, uint8_t* tmp, uint8_t* out, int B,
+                            int channels, int max_h, int max_oh, int max_ow, void* stream);
 
 /* Hungarian matcher of the detection loss (models/dino/matcher.py:57-96), two kernels for all P = layers x B problems of a
  * training step at once (the reference runs a cdist/GIoU chain over the full (B*Q) x sum(T) matrix, copies it to the CPU and

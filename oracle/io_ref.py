@@ -119,3 +119,80 @@ def clean_string(s):
     s = re.sub(r"(?<=\S)€(?=\S)", " € ", s)
     s = re.sub(r"(?<!\.)\.\.(?!\.)", ".", s)
     return s.replace(",,", ",")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PIL's 8-bit bilinear resize (what torchvision F.resize does to the PIL images of datasets/transforms.py:107-108 ->
+# Image.resize(size, BILINEAR)).  Third-party arithmetic: Pillow (12.2 installed here; `requirements.txt` pins nothing),
+# src/libImaging/Resample.c -- precompute_coeffs / normalize_coeffs_8bpc / ImagingResampleHorizontal_8bpc / ...Vertical_8bpc:
+# a triangle filter whose support grows with the down-scale factor (antialiasing), coefficients normalised in double precision and
+# rounded to 22-bit fixed point, a horizontal pass into an 8-bit intermediate, then a vertical pass.  Restated here in numpy and
+# pinned bit-for-bit against the installed PIL by tests/test_oracle_io.py.
+PRECISION_BITS = 32 - 8 - 2
+
+
+def resample_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs (bilinear: support 1.0) + normalize_coeffs_8bpc.
+    Returns (xmin[out], count[out], coef[out, ksize] int32)."""
+    import math
+    import numpy as np
+    scale = float(in_size) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    xmin_a = np.zeros(out_size, np.int32)
+    cnt_a = np.zeros(out_size, np.int32)
+    coef = np.zeros((out_size, ksize), np.int32)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)          # C (int) cast: truncation toward zero
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = []
+        for x in range(xmax):
+            t = (x + xmin - center + 0.5) * ss
+            t = -t if t < 0.0 else t
+            w.append(1.0 - t if t < 1.0 else 0.0)
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x in range(xmax):
+            k = w[x] / ww if ww != 0.0 else w[x]
+            coef[xx, x] = int(-0.5 + k * (1 << PRECISION_BITS)) if k < 0 else int(0.5 + k * (1 << PRECISION_BITS))
+        xmin_a[xx], cnt_a[xx] = xmin, xmax
+    return xmin_a, cnt_a, coef
+
+
+def _resample_axis(img, out_size, axis):
+    """one 8bpc pass along `axis` of an (H,W,C) u8 array"""
+    import numpy as np
+    in_size = img.shape[axis]
+    xmin, cnt, coef = resample_coeffs(in_size, out_size)
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((out_size,) + src.shape[1:], np.uint8)
+    for xx in range(out_size):
+        ss = np.full(src.shape[1:], 1 << (PRECISION_BITS - 1), np.int64)
+        for k in range(cnt[xx]):
+            ss += src[xmin[xx] + k] * int(coef[xx, k])
+        out[xx] = np.clip(ss >> PRECISION_BITS, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def pil_resize_bilinear_u8(img, out_h, out_w):
+    """Image.resize((out_w, out_h), BILINEAR) on an (H,W) or (H,W,C) u8 array: horizontal pass first (only if the width
+    changes), then the vertical pass (only if the height changes) -- Resample.c ImagingResampleInner."""
+    import numpy as np
+    a = np.asarray(img)
+    squeeze = a.ndim == 2
+    if squeeze:
+        a = a[:, :, None]
+    if out_w != a.shape[1]:
+        a = _resample_axis(a, out_w, 1)
+    if out_h != a.shape[0]:
+        a = _resample_axis(a, out_h, 0)
+    return a[:, :, 0] if squeeze else a

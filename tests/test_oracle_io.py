@@ -107,3 +107,65 @@ def test_pack_u8_layout_and_errors(io):
         pack_u8([io["img0_u8"].astype(np.float32)])
     with pytest.raises(ValueError):
         pack_u8([])
+
+
+RESIZE_CASES = [(57, 913, 40, 640), (61, 2011, 31, 1021), (33, 301, 40, 364), (120, 1750, 91, 1333), (40, 512, 40, 512), (30, 100, 60, 250),
+                (94, 1333, 94, 1000), (17, 23, 5, 7), (5, 7, 17, 23), (128, 2200, 78, 1340)]
+
+
+def test_oracle_resize_is_bit_identical_to_pil():
+    """third-party arithmetic (Pillow Resample.c) restated in oracle/io_ref.py, pinned against the PIL installed here -- the library
+    torchvision F.resize calls for the reference's PIL images (datasets/transforms.py:107-108)."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    for h, w, oh, ow in RESIZE_CASES:
+        for shape in ((h, w), (h, w, 3)):
+            a = rng.integers(0, 256, shape, dtype=np.uint8)
+            ref = np.asarray(Image.fromarray(a).resize((ow, oh), Image.BILINEAR))
+            assert np.array_equal(io_ref.pil_resize_bilinear_u8(a, oh, ow), ref), (shape, oh, ow)
+
+
+def test_product_resample_tables_match_oracle_and_pil():
+    """dtlr_b200.input.resample_tables (the host half of dtlr_resize_u8_bilinear) == the oracle's tables, coefficient for
+    coefficient, and the two integer passes over those tables (numpy stand-in for the kernels) reproduce PIL."""
+    from dtlr_b200 import input as din
+    for n_in, n_out in [(913, 640), (2011, 1021), (57, 40), (61, 31), (301, 364), (33, 40), (1750, 1333), (120, 91), (512, 512), (100, 250),
+                        (7, 23), (23, 7), (2200, 1340), (1, 5), (5, 1), (1333, 1333)]:
+        for a, b in zip(io_ref.resample_coeffs(n_in, n_out), din.resample_tables(n_in, n_out)):
+            assert a.dtype == b.dtype and np.array_equal(a, b), (n_in, n_out)
+    rng = np.random.default_rng(1)
+    for h, w, oh, ow in RESIZE_CASES[:6]:
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(din.apply_tables_u8(a, oh, ow), io_ref.pil_resize_bilinear_u8(a, oh, ow))
+
+
+def test_resize_plan_layout_drives_a_kernel_emulation_to_the_pil_result():
+    """the host/kernel contract of dtlr_resize_u8_bilinear: a literal numpy transcription of resize_pass_kernel (csrc/input.cu), fed
+    with GpuResizer.plan()'s packed input / meta / tables for a ragged batch, reproduces the oracle's (== PIL's) images."""
+    from dtlr_b200.input import GpuResizer
+    rng = np.random.default_rng(4)
+    for ch in (1, 3):
+        imgs = [rng.integers(0, 256, (h, w) if ch == 1 else (h, w, 3), dtype=np.uint8) for h, w in [(9, 31), (12, 50), (7, 7)]]
+        sizes = [(5, 20), (12, 33), (14, 3)]
+        packed, meta, tab, tmp_bytes, out_bytes, c, _ = GpuResizer("cpu").plan(imgs, sizes)
+        assert c == ch and meta.shape == (3, 12)
+        tmp, out = np.zeros(tmp_bytes, np.uint8), np.zeros(out_bytes, np.uint8)
+        for m in meta.tolist():
+            in_off, tmp_off, out_off, h, w, oh, ow, xoff, yoff, ksx, ksy, _r = m
+            for vertical in (False, True):
+                src, so = (tmp, tmp_off) if vertical else (packed, in_off)
+                dst, do = (out, out_off) if vertical else (tmp, tmp_off)
+                n_out, ks, t = (oh, ksy, tab[yoff:]) if vertical else (ow, ksx, tab[xoff:])
+                for oy in range(oh if vertical else h):
+                    for ox in range(ow):
+                        o = oy if vertical else ox
+                        lo, cnt = int(t[o]), int(t[n_out + o])
+                        for cc in range(ch):
+                            acc = 1 << 21
+                            for i in range(cnt):
+                                p = ((lo + i) * ow + ox) * ch if vertical else (oy * w + lo + i) * ch
+                                acc += int(src[so + p + cc]) * int(t[2 * n_out + o * ks + i])
+                            dst[do + (oy * ow + ox) * ch + cc] = min(255, max(0, acc >> 22))
+        for im, (oh, ow), m in zip(imgs, sizes, meta.tolist()):
+            got = out[m[2]:m[2] + oh * ow * ch].reshape((oh, ow) if ch == 1 else (oh, ow, 3))
+            assert np.array_equal(got, io_ref.pil_resize_bilinear_u8(im, oh, ow))
