@@ -1,6 +1,5 @@
 """GPU: the stages either side of the forward through the C ABI against the reference's golden vectors
 (tests/golden/io.npz, produced by the unmodified reference) and the CPU oracle (oracle/io_ref.py)."""
-import json
 import os
 
 import numpy as np
@@ -79,7 +78,7 @@ def test_bucketed_evaluator_equals_direct_batches_and_oracle_metrics():
     """LineEvaluator (width buckets, GPU input stage, overlapped frame download, eps = 0.03/C) returns for every line exactly what a
     direct call on that line's batch returns, in input order; CER / WER equal the oracle's on those predictions."""
     from gpu_common import build_model
-    from dtlr_b200 import dino, evaluation, ops
+    from dtlr_b200 import evaluation, ops
     from dtlr_b200.misc import NestedTensor
     model, _, _ = build_model(100)
     model.eval()

@@ -14,7 +14,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dtlr_b200 import config, dino, evaluation, ops, synth  # noqa: E402
-from dtlr_b200.input import GpuPreprocessor, IMAGENET_MEAN, IMAGENET_STD, pack_u8  # noqa: E402
+from dtlr_b200.input import IMAGENET_MEAN, IMAGENET_STD, pack_u8  # noqa: E402
 
 PEAK = 6467.7
 try:
