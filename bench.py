@@ -328,6 +328,14 @@ def main():
                      "launches_timed": len(msda_events), "share_of_step": round(msda_ms / n_prof / ms_step, 3),
                      "algorithmic_bytes_per_launch": round(msda_bytes / max(1, len(msda_events))),
                      "binding_resource": "shared-memory gather bandwidth (4 KB of taps per (query, head) at 128 B/clk/SM), see DESIGN.md 3.1"}
+    # the resource that actually binds it: shared-memory wavefronts (one 128-byte wavefront per clock per SM).  20.2 M wavefronts per
+    # launch (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum, profiles/r1_msda_mma_ncu.txt) / (SMs x SM clock) = the floor
+    if msda_events and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        floor_us = 20217621 / sms / clocks["sm_mhz"]
+        us = 1e3 * msda_ms / len(msda_events)
+        roofline_msda.update({"us_per_launch": round(us, 1), "binding_floor_us": round(floor_us, 1),
+                              "binding_frac": round(floor_us / us, 3), "shared_wavefronts_per_launch": 20217621})
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only; --impl reference gives the N > 1 arm
         ips, sec = cpu_baseline_run(8, 3, 1)
