@@ -189,8 +189,7 @@ class GpuPreprocessor:
 
     def resized(self, images, size, max_size=None, stream=None):
         """the reference's evaluation transform on the GPU: RandomResize([size], max_size) (datasets/transforms.py:78-108, PIL-exact
-        bilinear) + ToTensor + Normalize + padding.  `images` are the ORIGINAL u8 scans.  (The resize kernels have CPU-pinned tables but
-        no recorded GPU run yet -- see DESIGN.md 3.7.)"""
+        bilinear) + ToTensor + Normalize + padding.  `images` are the ORIGINAL u8 scans."""
         if not hasattr(self, "_resizer"):
             self._resizer = GpuResizer(self.device)
         arrs = [_as_u8_array(im) for im in images]

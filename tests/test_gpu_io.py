@@ -125,10 +125,9 @@ def test_bucketed_evaluator_equals_direct_batches_and_oracle_metrics():
         assert res["cer"] == d / max(l, 1) and abs(res["wer"] - sum(wers) / len(wers)) < 1e-12
 
 
-@pytest.mark.skipif(os.environ.get("DTLR_TEST_UNVALIDATED") != "1",
-                    reason="dtlr_resize_u8_bilinear was written after the round-1 GPU budget was spent: its first GPU run is opt-in "
-                           "(DTLR_TEST_UNVALIDATED=1); the tables and the pass arithmetic are pinned against PIL on the CPU")
 def test_gpu_resize_bit_identical_to_pil_restatement():
+    """dtlr_resize_u8_bilinear (ragged batch, 1 and 3 channels, up- and down-scaling) == the oracle's restatement of PIL's
+    Image.resize(BILINEAR) bit for bit, and GpuPreprocessor.resized == the reference's whole evaluation transform."""
     from dtlr_b200.input import GpuPreprocessor, GpuResizer, get_size_with_aspect_ratio
     rng = np.random.default_rng(3)
     for ch in (1, 3):
