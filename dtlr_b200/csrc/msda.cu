@@ -749,7 +749,7 @@ __device__ __forceinline__ void red_add_f32x4_nc(float* p, const float a, const 
 // profiles/r1_msda_bwd_ncu.txt: 16 warps per SM, one value load in flight per warp because the clobbered `red` asm pins the
 // next point's load behind it): the four value loads of a group of 4 points are issued before any of their arithmetic and the
 // reductions carry no memory clobber, so a warp keeps 4 L2 round trips in flight instead of 1.  Arithmetic per point is identical.
-template <int PTS, bool GROUPED>      // PTS: sampling points per level (L * PTS == 16)
+template <int PTS, int GROUP>      // PTS: sampling points per level (L * PTS == 16); GROUP: value loads in flight (0: one)
 __device__ __forceinline__ void msda_bwd_d32_body(const float* __restrict__ value, const float* __restrict__ loc,
                                                   const float* __restrict__ attn, const float* __restrict__ gout,
                                                   float* __restrict__ gvalue, float* __restrict__ gloc, float* __restrict__ gattn,
@@ -783,14 +783,15 @@ __device__ __forceinline__ void msda_bwd_d32_body(const float* __restrict__ valu
             ppix = (unsigned)(pstart + (y0 + 1) * pW + (x0 + 1)) | (bits << 24);
         }
         float r[48];
-        if (GROUPED) {
+        if (GROUP > 0) {
+            constexpr int G = GROUP > 0 ? GROUP : 1;
 #pragma unroll
-            for (int g0 = 0; g0 < 16; g0 += 4) {
-                float4 v[4];
-                float wy[4], wx[4], aw[4];
-                int off[4];                              // element offset of this lane's 4 channels of its corner; -1: corner not on the map
+            for (int g0 = 0; g0 < 16; g0 += G) {
+                float4 v[G];
+                float wy[G], wx[G], aw[G];
+                int off[G];                              // element offset of this lane's 4 channels of its corner; -1: corner not on the map
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < G; ++i) {
                     const int pt = g0 + i;
                     const unsigned pix = __shfl_sync(0xffffffffu, ppix, pt);
                     const float fy = __shfl_sync(0xffffffffu, pfy, pt);
@@ -805,7 +806,7 @@ __device__ __forceinline__ void msda_bwd_d32_body(const float* __restrict__ valu
                     v[i] = ok ? __ldg(reinterpret_cast<const float4*>(value + voff + (size_t)off[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < G; ++i) {
                     const int pt = g0 + i;
                     const int W = lv.W[pt / PTS], H = lv.H[pt / PTS];
                     const float d = g.x * v[i].x + g.y * v[i].y + g.z * v[i].z + g.w * v[i].w;      // 0 for an off-map corner
@@ -855,16 +856,16 @@ msda_bwd_d32_kernel(const float* __restrict__ value, const float* __restrict__ l
                     const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
                     float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
                     const int M, const int Lq) {
-    msda_bwd_d32_body<PTS, false>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
+    msda_bwd_d32_body<PTS, 0>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
 }
 
-template <int PTS>
-__global__ void __launch_bounds__(256, 2)
+template <int PTS, int GROUP>
+__global__ void __launch_bounds__(GROUP > 4 ? 128 : 256, GROUP > 4 ? 3 : 2)
 msda_bwd_d32_grouped_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                             const float* __restrict__ gout, float* __restrict__ gvalue, float* __restrict__ gloc,
                             float* __restrict__ gattn, const __grid_constant__ Levels lv, const long long total, const int S,
                             const int M, const int Lq) {
-    msda_bwd_d32_body<PTS, true>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
+    msda_bwd_d32_body<PTS, GROUP>(value, loc, attn, gout, gvalue, gloc, gattn, lv, total, S, M, Lq);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1059,16 +1060,18 @@ extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, cons
                       ((((uintptr_t)value | (uintptr_t)grad_value | (uintptr_t)grad_out) & 15) == 0) &&
                       ((((uintptr_t)loc | (uintptr_t)grad_loc) & 7) == 0);
     if (fast) {
-        // grid-stride over the (b,q,m) items: enough 8-warp CTAs to fill the machine a few times over
-        const long long want = (warps + 7) / 8;
-        const unsigned grid = (unsigned)min(want, (long long)sm_count() * 32);
-        auto launch = [&](auto kern) {
-            kern<<<grid, 256, 0, st>>>((const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out,
-                                       (float*)grad_value, (float*)grad_loc, (float*)grad_attn, lv, warps, S, M, Lq);
+        // grid-stride over the (b,q,m) items: enough CTAs to fill the machine a few times over (32 x 8 warps per SM at most)
+        auto launch = [&](auto kern, int threads_per_cta = 256) {
+            const long long ctas = (warps * 32 + threads_per_cta - 1) / threads_per_cta;
+            const unsigned g = (unsigned)min(ctas, (long long)sm_count() * 32 * (256 / threads_per_cta));
+            kern<<<g, threads_per_cta, 0, st>>>((const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out,
+                                                (float*)grad_value, (float*)grad_loc, (float*)grad_attn, lv, warps, S, M, Lq);
         };
         // grouped-load variant (433 vs 594 us): opt-in until the complete GPU suite has run with it; int offsets need S*M*32 < 2^31
         if ((g_debug_flags & 65536) && P == 4 && (long long)S * M * 32 < (1ll << 31)) {
-            launch(msda_bwd_d32_grouped_kernel<4>);
+            // flag 131072 (with 65536): 8 loads in flight, 128-thread CTAs (148 registers -> 3 CTAs per SM) -- not yet measured
+            if (g_debug_flags & 131072) launch(msda_bwd_d32_grouped_kernel<4, 8>, 128);
+            else launch(msda_bwd_d32_grouped_kernel<4, 4>);
         } else switch (P) {
             case 2: launch(msda_bwd_d32_kernel<2>); break;
             case 4: launch(msda_bwd_d32_kernel<4>); break;
