@@ -1,43 +1,41 @@
-"""Builder registry with the reference's interface (models/registry.py:12-58): finetuning.py:123-131 does
-`MODULE_BUILD_FUNCS.get(args.modelname)(args)`."""
-import inspect
-from functools import partial
+"""Name -> builder table with the public surface the reference's entry scripts use (models/registry.py:12-58):
+`MODULE_BUILD_FUNCS.get(args.modelname)(args)` (finetuning.py:123-131), the decorator `@MODULE_BUILD_FUNCS.registe_with_name(
+module_name="dino")` (models/dino/dino.py:1049) and plain `register(fn)`.  Written for this package: one dict, one decorator
+factory; same names, same error types."""
+import types
 
 
-class Registry(object):
+class Registry:
     def __init__(self, name):
-        self._name = name
-        self._module_dict = dict()
-
-    def __repr__(self):
-        return "%s(name=%s, items=%s)" % (self.__class__.__name__, self._name, list(self._module_dict.keys()))
+        self.name = name
+        self.module_dict = {}                  # builder name -> function(args) -> (model, criterion, postprocessors)
 
     def __len__(self):
-        return len(self._module_dict)
+        return len(self.module_dict)
 
-    @property
-    def name(self):
-        return self._name
+    def __contains__(self, key):
+        return key in self.module_dict
 
-    @property
-    def module_dict(self):
-        return self._module_dict
+    def __repr__(self):
+        return "Registry(name=%s, items=%s)" % (self.name, sorted(self.module_dict))
 
     def get(self, key):
-        return self._module_dict.get(key, None)
-
-    def registe_with_name(self, module_name=None, force=False):   # (sic) the reference spells it this way
-        return partial(self.register, module_name=module_name, force=force)
+        """the builder registered under `key`, or None (the reference's callers test for None)"""
+        return self.module_dict.get(key)
 
     def register(self, module_build_function, module_name=None, force=False):
-        if not inspect.isfunction(module_build_function):
+        if not isinstance(module_build_function, types.FunctionType):
             raise TypeError("module_build_function must be a function, but got %s" % type(module_build_function))
-        if module_name is None:
-            module_name = module_build_function.__name__
-        if not force and module_name in self._module_dict:
-            raise KeyError("%s is already registered in %s" % (module_name, self.name))
-        self._module_dict[module_name] = module_build_function
+        key = module_name or module_build_function.__name__
+        if key in self.module_dict and not force:
+            raise KeyError("%s is already registered in %s" % (key, self.name))
+        self.module_dict[key] = module_build_function
         return module_build_function
+
+    def registe_with_name(self, module_name=None, force=False):      # (sic) spelled as in the reference, whose decorators we mirror
+        def decorator(fn):
+            return self.register(fn, module_name=module_name, force=force)
+        return decorator
 
 
 MODULE_BUILD_FUNCS = Registry("model build functions")
