@@ -162,12 +162,32 @@ def frames_to_labels(frames_row):
     return [int(v) - 1 for v in frames_row if int(v) != 0]
 
 
+def nms_decode(outputs, postprocessor, TH, NM, num_select=900):
+    """the reference's alternative decode, evaluation.py:94-115 (`args.NMS_inference`): PostProcess with `num_select` (query, class)
+    pairs and class-agnostic NMS at IoU `NM` on unit-size images, keep scores > `TH`, read the labels in order of box centre x.
+    Batched (the reference handles image 0 only); returns one class-id list per image.  Mutates the post-processor's
+    `num_select` / `nms_iou_threshold` exactly as the reference does (evaluation.py:97-98)."""
+    logits = outputs["pred_logits"]
+    postprocessor.num_select = min(num_select, logits.shape[1] * logits.shape[2])
+    postprocessor.nms_iou_threshold = NM
+    res = postprocessor(outputs, torch.ones((logits.shape[0], 2), dtype=torch.float32, device=logits.device))
+    preds = []
+    for r in res:
+        x0, _, x1, _ = r["boxes"].unbind(-1)
+        sel = r["scores"] > TH
+        order = torch.sort(((x0 + x1) / 2)[sel])[1]
+        preds.append(r["labels"].long()[sel][order].tolist())
+    return preds
+
+
 # ------------------------------------------------------------------------------------------------ the loop
 class LineEvaluator:
     """model: dtlr_b200 DINO in eval mode on a CUDA device; charset: list of characters (class c -> charset[c])."""
 
-    def __init__(self, model, charset, batch_size=64, width_multiple=32, height_multiple=8, eps=None):
+    def __init__(self, model, charset, batch_size=64, width_multiple=32, height_multiple=8, eps=None, nms=None):
+        """nms=(postprocessor, TH, NM) switches the decode to the reference's `args.NMS_inference` branch (evaluation.py:94-115)."""
         self.model = model
+        self.nms = nms
         self.charset = list(charset)
         self.batch_size = batch_size
         self.width_multiple = width_multiple
@@ -202,6 +222,10 @@ class LineEvaluator:
         for n, idx in enumerate(batches):
             samples = self.prep([images[i] for i in idx], stream=self.up)
             out = self.model(samples)
+            if self.nms is not None:            # alternative decode: torch ops + host lists (synchronises per batch)
+                for i, p in zip(idx, nms_decode(out, *self.nms)):
+                    preds[i] = p
+                continue
             C = out["pred_logits"].shape[-1]
             frames = ops.ctc_decode(out["pred_logits"], out["pred_boxes"], self.eps if self.eps is not None else 0.03 / C)
             key = (tuple(frames.shape), n & 1)

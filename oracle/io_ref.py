@@ -196,3 +196,37 @@ def pil_resize_bilinear_u8(img, out_h, out_w):
     if out_h != a.shape[0]:
         a = _resample_axis(a, out_h, 0)
     return a[:, :, 0] if squeeze else a
+
+
+def nms_decode(pred_logits, pred_boxes, th, nm, num_select=900):
+    """evaluation.py:94-115 (args.NMS_inference) on top of models/dino/dino.py:1000-1034 (PostProcess with target size (1,1)):
+    top-`num_select` (query, class) pairs by sigmoid score, xyxy boxes, greedy class-agnostic NMS at IoU `nm` (torchvision.ops.nms:
+    suppress when IoU > threshold), keep scores > th, order by box centre x.  One image (B = 1 like the reference's loop).
+    Returns the class ids in reading order."""
+    prob = pred_logits[0].sigmoid().reshape(-1)
+    C = pred_logits.shape[2]
+    scores, idx = torch.topk(prob, min(num_select, prob.numel()))
+    q, labels = idx // C, idx % C
+    cx, cy, w, h = pred_boxes[0][q].unbind(-1)
+    boxes = torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), -1)
+    keep = []
+    order = torch.argsort(scores, descending=True, stable=True).tolist()
+    area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+    alive = [True] * len(order)
+    for a_i, a in enumerate(order):
+        if not alive[a_i]:
+            continue
+        keep.append(a)
+        for b_i in range(a_i + 1, len(order)):
+            if alive[b_i]:
+                b = order[b_i]
+                iw = (torch.min(boxes[a, 2], boxes[b, 2]) - torch.max(boxes[a, 0], boxes[b, 0])).clamp(min=0)
+                ih = (torch.min(boxes[a, 3], boxes[b, 3]) - torch.max(boxes[a, 1], boxes[b, 1])).clamp(min=0)
+                inter = iw * ih
+                if inter / (area[a] + area[b] - inter) > nm:
+                    alive[b_i] = False
+    keep = torch.tensor(keep, dtype=torch.long)
+    s, l, bx = scores[keep], labels[keep], boxes[keep]
+    sel = s > th
+    centre = (bx[sel][:, 0] + bx[sel][:, 2]) / 2
+    return l[sel][torch.sort(centre)[1]].tolist()

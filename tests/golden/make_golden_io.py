@@ -113,9 +113,38 @@ def metric_case():
     return {"charset": charset, "rows": rows}
 
 
+def nms_decode_case():
+    """evaluation.py:92-160 convert_output_to_pred with args.NMS_inference (top-900 (query, class) pairs, class-agnostic NMS, score
+    threshold, sort by cx): the function is extracted by AST and run unmodified with the globals it reads (args, postprocessors,
+    dataset_val, box_ops) bound to the reference's own PostProcess / box_ops."""
+    import types as _t
+    ref_shims.load_reference()
+    from models.dino.dino import PostProcess          # reference classes
+    from util import box_ops
+    src = open(os.path.join(REF, "evaluation.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "convert_output_to_pred"][0]
+    ns = {"torch": torch, "box_ops": box_ops, "args": _t.SimpleNamespace(NMS_inference=True),
+          "postprocessors": {"bbox": PostProcess()}, "dataset_val": _t.SimpleNamespace(charset=list(range(20)))}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "evaluation.py", "exec"), ns)
+    g = torch.Generator().manual_seed(9)
+    out = {}
+    for i, (TH, NM) in enumerate([(0.3, 0.5), (0.5, 0.2), (0.05, 0.9)]):
+        logits = torch.randn(1, 120, 20, generator=g) * 2.0 - 2.0
+        cx = torch.rand(1, 120, 1, generator=g)
+        boxes = torch.cat((cx, 0.5 + 0.02 * torch.randn(1, 120, 1, generator=g), 0.02 + 0.03 * torch.rand(1, 120, 1, generator=g),
+                           0.6 + 0.2 * torch.rand(1, 120, 1, generator=g)), -1)
+        preds, labels = ns["convert_output_to_pred"]({"pred_logits": logits, "pred_boxes": boxes}, None, list(range(20)), TH=TH, NM=NM)
+        assert preds == labels and len(labels) > 3
+        out["nms%d_logits" % i], out["nms%d_boxes" % i] = logits.numpy(), boxes.numpy()
+        out["nms%d_labels" % i] = np.array(labels, dtype=np.int64)
+        out["nms%d_th_nm" % i] = np.array([TH, NM])
+    return out
+
+
 def main():
     out = transforms_case()
     out.update(ngram_case())
+    out.update(nms_decode_case())
     np.savez_compressed(os.path.join(HERE, "io.npz"), **out)
     json.dump(metric_case(), open(os.path.join(HERE, "io_metrics.json"), "w"), indent=1, ensure_ascii=False)
     print("wrote io.npz (%d arrays), io_metrics.json" % len(out))

@@ -169,3 +169,22 @@ def test_resize_plan_layout_drives_a_kernel_emulation_to_the_pil_result():
         for im, (oh, ow), m in zip(imgs, sizes, meta.tolist()):
             got = out[m[2]:m[2] + oh * ow * ch].reshape((oh, ow) if ch == 1 else (oh, ow, 3))
             assert np.array_equal(got, io_ref.pil_resize_bilinear_u8(im, oh, ow))
+
+
+def test_nms_decode_oracle_and_product_match_reference(io):
+    """evaluation.py:94-115 (NMS_inference branch) as run by the unmodified reference (golden), the oracle restatement, and the
+    product's batched `evaluation.nms_decode` over dtlr_b200's PostProcess (torch ops -- here on CPU tensors, on the GPU in use)."""
+    from dtlr_b200 import dino, evaluation
+    for i in range(3):
+        lg, bx = torch.from_numpy(io["nms%d_logits" % i]), torch.from_numpy(io["nms%d_boxes" % i])
+        th, nm = io["nms%d_th_nm" % i].tolist()
+        want = io["nms%d_labels" % i].tolist()
+        assert io_ref.nms_decode(lg, bx, th, nm) == want
+        got = evaluation.nms_decode({"pred_logits": lg, "pred_boxes": bx}, dino.PostProcess(), th, nm)
+        assert got == [want]
+    # batched: two different images in one call
+    lg = torch.cat([torch.from_numpy(io["nms%d_logits" % i]) for i in (0, 1)])
+    bx = torch.cat([torch.from_numpy(io["nms%d_boxes" % i]) for i in (0, 1)])
+    th, nm = io["nms0_th_nm"].tolist()
+    got = evaluation.nms_decode({"pred_logits": lg, "pred_boxes": bx}, dino.PostProcess(), th, nm)
+    assert got[0] == io["nms0_labels"].tolist() and got[1] == io_ref.nms_decode(lg[1:], bx[1:], th, nm)
