@@ -35,6 +35,8 @@ def lib():
 LAUNCHES = 0
 # optional profiler hook: callable(name) -> context manager, set by bench.py to time one kernel family with CUDA events
 TIMER = None
+# algorithmic bytes (A + W + output [+ residual]) of the dtlr_gemm launches issued while TIMER is set (bench.py: HBM view of the family)
+GEMM_BYTES = 0
 
 
 def check(rc, what):

@@ -26,6 +26,8 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
         ldr = residual.stride(0)
     if L.TIMER is not None:
         L.TIMER("gemm", 2.0 * M * N * K, a.device, True)
+        L.GEMM_BYTES += (M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
+                         + (M * N * residual.element_size() if residual is not None else 0))
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
