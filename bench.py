@@ -92,6 +92,24 @@ class ClockSampler:
                 "window": "device-resident timed region + end-to-end timed regions (nvidia-smi -lms 20)"}
 
 
+def gemm_hbm_view(gemm_bytes, gemm_ms, n_prof, hbm_peak_gbs):
+    """HBM reading of the dtlr_gemm family: sum of algorithmic bytes / sum of event-timed durations against the copy peak."""
+    gbs = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0
+    return {"achieved": round(gbs, 1), "peak": hbm_peak_gbs, "unit": "GB/s", "frac": round(gbs / hbm_peak_gbs, 4),
+            "algorithmic_bytes_per_step": gemm_bytes / max(1, n_prof),
+            "what": "sum over the same launches of A + W + output (+ residual) bytes / sum of durations, against the measured copy peak"}
+
+
+MSDA_SHARED_WAVEFRONTS_PER_LAUNCH = 20217621      # ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum, profiles/r1_msda_mma_ncu.txt
+
+
+def msda_binding_view(us_per_launch, sms, sm_mhz):
+    """the resource that binds the deformable-attention core: shared-memory wavefronts, one 128-byte wavefront per clock per SM"""
+    floor_us = MSDA_SHARED_WAVEFRONTS_PER_LAUNCH / sms / sm_mhz
+    return {"us_per_launch": round(us_per_launch, 1), "binding_floor_us": round(floor_us, 1),
+            "binding_frac": round(floor_us / us_per_launch, 3), "shared_wavefronts_per_launch": MSDA_SHARED_WAVEFRONTS_PER_LAUNCH}
+
+
 def build_ours(device, dtype):
     from dtlr_b200 import config, dino, synth
     model, criterion, post = dino.build_dino(config.latin_ctc_args())
@@ -301,9 +319,7 @@ def main():
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     try:        # secondary view, added after the last GPU run of the round: must never cost the headline line
-        hbm_view = {"achieved": round(gemm_bytes / (gemm_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(gemm_bytes / (gemm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "algorithmic_bytes_per_step": gemm_bytes / n_prof,
-                    "what": "sum over the same launches of A + W + output (+ residual) bytes / sum of durations, against the measured copy peak"}
+        hbm_view = gemm_hbm_view(gemm_bytes, gemm_ms, n_prof, pk["hbm_gbs"])
     except Exception as e:
         hbm_view = {"error": repr(e)}
     roofline_gemm = {"kernel": "gemm_ws_tcgen05_kernel + gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions outside the FFN blocks)" if dtype == torch.bfloat16 else "sgemm_kernel (fp32 parity mode)",
@@ -341,11 +357,8 @@ def main():
     # launch (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum, profiles/r1_msda_mma_ncu.txt) / (SMs x SM clock) = the floor
     try:
         if msda_events and clocks and clocks.get("sm_mhz"):
-            sms = torch.cuda.get_device_properties(device).multi_processor_count
-            floor_us = 20217621 / sms / clocks["sm_mhz"]
-            us = 1e3 * msda_ms / len(msda_events)
-            roofline_msda.update({"us_per_launch": round(us, 1), "binding_floor_us": round(floor_us, 1),
-                                  "binding_frac": round(floor_us / us, 3), "shared_wavefronts_per_launch": 20217621})
+            roofline_msda.update(msda_binding_view(1e3 * msda_ms / len(msda_events),
+                                                   torch.cuda.get_device_properties(device).multi_processor_count, clocks["sm_mhz"]))
     except Exception as e:      # secondary view, added after the last GPU run of the round
         roofline_msda["binding_error"] = repr(e)
     cpu = None

@@ -101,3 +101,14 @@ def test_sharded_evaluation_two_ranks_gloo():
     import pytest
     with pytest.raises(ValueError):
         evaluation.shard_batches(batches, [1], 0, 2)
+
+
+def test_bench_secondary_views_arithmetic():
+    """the helper arithmetic behind roofline_gemm.hbm_view and roofline_msda.binding_* (bench.py), on known numbers"""
+    sys.path.insert(0, ROOT)
+    import bench
+    v = bench.gemm_hbm_view(3.0e9, 1.5, 3, 6000.0)                 # 3 GB over 1.5 ms = 2000 GB/s
+    assert v["achieved"] == 2000.0 and v["frac"] == round(2000.0 / 6000.0, 4) and v["algorithmic_bytes_per_step"] == 1.0e9
+    assert bench.gemm_hbm_view(0.0, 0.0, 0, 6000.0)["achieved"] == 0.0
+    b = bench.msda_binding_view(107.0, 148, 1965.0)
+    assert abs(b["binding_floor_us"] - 69.5) < 0.1 and abs(b["binding_frac"] - 0.65) < 0.01
