@@ -49,6 +49,12 @@ def nested_tensor_from_tensor_list(tensor_list: List[Tensor]):
     return NestedTensor(tensor, mask, nopad=same)
 
 
+def collate_fn(batch):
+    """reference util/misc.py:285-289: DataLoader collate -- (images, targets) pairs -> (NestedTensor, tuple of targets)."""
+    images, *rest = zip(*batch)
+    return (nested_tensor_from_tensor_list(list(images)), *rest)
+
+
 def inverse_sigmoid(x, eps=1e-3):
     """reference util/misc.py:575-579"""
     x = x.clamp(min=0, max=1)

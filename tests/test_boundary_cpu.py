@@ -74,3 +74,14 @@ def test_synth_weights_are_key_determined():
     b = synth.synth_tensor("transformer.decoder.class_embed.0.weight", (166, 256))
     assert torch.equal(a, b)
     assert not torch.equal(a, synth.synth_tensor("transformer.enc_out_class_embed.weight", (166, 256)))
+
+
+def test_collate_fn_like_reference():
+    """util/misc.py:285-289: a list of (image, target) pairs -> (NestedTensor padded to the batch max, tuple of targets)"""
+    import torch
+    from dtlr_b200.misc import NestedTensor, collate_fn
+    batch = [(torch.ones(3, 4, 7), {"labels": torch.tensor([1, 2])}), (torch.ones(3, 5, 6), {"labels": torch.tensor([3])})]
+    samples, targets = collate_fn(batch)
+    assert isinstance(samples, NestedTensor) and samples.tensors.shape == (2, 3, 5, 7) and isinstance(targets, tuple) and len(targets) == 2
+    assert samples.mask[0, :4, :7].sum() == 0 and samples.mask[0, 4].all() and samples.mask[1, :, 6].all() and not samples.nopad
+    assert targets[1]["labels"].tolist() == [3]
