@@ -24,10 +24,52 @@ sys.path.insert(0, ROOT)
 
 BATCH_PER_GPU = 64
 IMG_H, IMG_W = 40, 1024
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE ffn_ln_tcgen05_kernel launch at M = 58368 (ncu --set full, profiles/r1_ffn_ncu.txt);
-# 32.05 MB read + 0.68 MB written.  Algorithmic bytes of the launch: X in + Y out (2 x 29.9 MB) + 2 MB of weights = 61.9 MB -- the
-# output stays in the 126 MB L2 (write-back) when the kernel is profiled alone, so DRAM traffic is below the algorithmic bytes
-FFN_DRAM_BYTES_PER_LAUNCH = 32.73e6
+import glob
+import re
+
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3}
+
+
+def profile_metrics(kernel_regex, metrics, hint="", prefer=("r2_", "r1_")):
+    """Read per-launch ncu metrics of one kernel from the committed summaries under profiles/ (written by tools/ncu_summary.py from
+    an `ncu --set full` capture; newest round first).  Returns ({metric: value in base units}, file) or ({}, None)."""
+    pat = re.compile(kernel_regex)
+    files = []
+    for pre in prefer:
+        fs = sorted(glob.glob(os.path.join(ROOT, "profiles", pre + "*ncu*.txt")), reverse=True)
+        files += [f for f in fs if hint and hint in os.path.basename(f)] + [f for f in fs if not (hint and hint in os.path.basename(f))]
+    for f in files:
+        block = None
+        found = {}
+        try:
+            lines = open(f).read().splitlines()
+        except OSError:
+            continue
+        for ln in lines:
+            if ln.startswith("===="):
+                if found:
+                    break
+                block = pat.search(ln) is not None
+                continue
+            if block:
+                parts = ln.split()
+                if len(parts) >= 2 and parts[0] in metrics:
+                    try:
+                        val = float(parts[1].replace(",", ""))
+                    except ValueError:
+                        continue
+                    found[parts[0]] = val * _UNIT.get(parts[2] if len(parts) > 2 else "", 1.0)
+        if found:
+            return found, os.path.relpath(f, ROOT)
+    return {}, None
+
+
+def profile_traffic(kernel_regex, hint=""):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from the newest committed ncu summary"""
+    m, f = profile_metrics(kernel_regex, ("dram__bytes_read.sum", "dram__bytes_write.sum"), hint)
+    if len(m) == 2:
+        return m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"], f
+    return None, None
 WORKLOAD = "IAM English config/Latin_CTC.py: ResNet-50 + 6+6 deformable enc/dec, 900 queries, 166 classes, 64x3x40x1024 per GPU, forward"
 
 
@@ -100,14 +142,12 @@ def gemm_hbm_view(gemm_bytes, gemm_ms, n_prof, hbm_peak_gbs):
             "what": "sum over the same launches of A + W + output (+ residual) bytes / sum of durations, against the measured copy peak"}
 
 
-MSDA_SHARED_WAVEFRONTS_PER_LAUNCH = 20217621      # ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum, profiles/r1_msda_mma_ncu.txt
-
-
-def msda_binding_view(us_per_launch, sms, sm_mhz):
-    """the resource that binds the deformable-attention core: shared-memory wavefronts, one 128-byte wavefront per clock per SM"""
-    floor_us = MSDA_SHARED_WAVEFRONTS_PER_LAUNCH / sms / sm_mhz
+def msda_binding_view(us_per_launch, sms, sm_mhz, wavefronts, source):
+    """the resource that binds the deformable-attention core: shared-memory wavefronts, one 128-byte wavefront per clock per SM
+    (wavefronts = ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of one launch, read from the committed summary `source`)"""
+    floor_us = wavefronts / sms / sm_mhz
     return {"us_per_launch": round(us_per_launch, 1), "binding_floor_us": round(floor_us, 1),
-            "binding_frac": round(floor_us / us_per_launch, 3), "shared_wavefronts_per_launch": MSDA_SHARED_WAVEFRONTS_PER_LAUNCH}
+            "binding_frac": round(floor_us / us_per_launch, 3), "shared_wavefronts_per_launch": wavefronts, "wavefronts_from": source}
 
 
 def build_ours(device, dtype):
@@ -131,7 +171,8 @@ def cpu_baseline_run(batch, iters, warmup=1):
     cfg = dino_ref.default_cfg(num_queries=900)
     x = synth.synth_images(batch, IMG_H, IMG_W, seed=0)
     # all the host threads the restatement can use: its small per-layer ops stop scaling past ~16-32 threads (measured on the
-    # 128-core B200 host: 8 threads 5.7 img/s, 16: 6.3, 32: 6.2, 64: 3.7, 128: 0.38), so the baseline runs at its best setting
+    # 128-core B200 host: 8 threads 5.7 img/s, 16: 6.3, 32: 6.2, 64: 3.7, 128: 0.38), so the baseline runs at its best setting;
+    # both numbers are reported: `cores` = threads used, `host_cores` = os.cpu_count()
     torch.set_num_threads(min(os.cpu_count() or 1, 16))
     for _ in range(warmup):
         dino_ref.dino_forward(sd, cfg, x)
@@ -152,11 +193,95 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": "bounded sample: %d images per step on the host CPU" % batch},
-            "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+                             "why_port": "the reference is a Python source tree with no setup.py / pyproject (not pip-installable) and cannot travel to the GPU box; its CPU restatement, pinned to reference-generated fixtures, is timed",
                              "sample": "%d steps of %d images (3x40x1024), oracle/dino_ref.py + oracle/msda_ref.c, fp32" % (args.steps, batch)},
             "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+TRAIN_BATCH_PER_GPU = 32
+
+
+def train_step_leg(device, rank, world, local, steps=5, warmup=2):
+    """BASELINE config 5: IAM fine-tune step = forward(samples, targets) + loss_CTC + backward + clip_grad_norm(0.01) + AdamW, 32 lines
+    per GPU, DistributedDataParallel over NCCL when N > 1 (reference engine.py:172-274, finetuning.py:211-215).  Timed on the device,
+    max over ranks.  Kernels: dtlr deformable attention forward/backward + fused CTC loss (C ABI); the remaining layers are torch autograd
+    over cuBLAS / cuDNN with TF32 (stated in the result)."""
+    from dtlr_b200 import config, dino, dist_util, synth
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    model, crit, _ = dino.build_dino(config.latin_ctc_args())
+    synth.load_synth_weights(model, seed=0)
+    model = model.to(device).train()
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local], find_unused_parameters=True)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+    B = TRAIN_BATCH_PER_GPU
+    x = synth.synth_images(B, IMG_H, IMG_W, seed=300 + rank).to(device)
+    tg = [{k: v.to(device) for k, v in t.items()} for t in synth.synth_targets(B, 166, seed=300 + rank)]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = net(x, tg)
+        loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.01)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    dist_util.barrier(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    dist_util.barrier(device)
+    ms = dist_util.max_over_ranks(e0.elapsed_time(e1), device) / steps
+    n_grad = sum(p.numel() for p in params)
+    res = {"value": round(world * B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 2), "batch_per_gpu": B,
+           "global_batch": B * world, "loss": round(float(loss), 4), "steps": steps, "warmup": warmup,
+           "collective": ("DDP bucketed NCCL all-reduce of %d fp32 gradients (%.0f MB) per step, overlapped with backward"
+                          % (n_grad, n_grad * 4 / 1e6)) if world > 1 else "none (N = 1)",
+           "what": "forward(samples, targets) + loss_CTC + backward + clip + AdamW; dtlr kernels: deformable attention fwd/bwd, fused CTC "
+                   "loss fwd/bwd; other layers torch autograd over cuBLAS/cuDNN (TF32)"}
+    del net, model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def gpu_reference_leg(device, batch, iters=3):
+    """The reference-shaped torch path on the SAME GPU: oracle/dino_ref.py run on CUDA tensors (torch fp32 ops over cuBLAS / cuDNN, TF32
+    off) with the reference's OWN deformable-attention CUDA kernel recompiled for sm_100a (oracle/_ref).  A like-for-like baseline for the
+    fused engine, reported beside the CPU arm; test infrastructure, never on the product path."""
+    import json as _json
+    from dtlr_b200 import synth
+    from oracle import dino_ref
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    shapes = _json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    sd = {k: v.to(device) for k, v in synth.synth_state_dict(shapes, seed=0).items()}
+    cfg = dino_ref.default_cfg(num_queries=900)
+    x = synth.synth_images(batch, IMG_H, IMG_W, seed=100).to(device)
+    mask = torch.zeros((batch, IMG_H, IMG_W), dtype=torch.bool, device=device)
+    with torch.device(device):
+        out = dino_ref.dino_forward(sd, cfg, x, mask=mask)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = dino_ref.dino_forward(sd, cfg, x, mask=mask)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": round(batch / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 2), "batch": batch, "dtype": "f32",
+            "what": "oracle/dino_ref.py on CUDA (eager torch fp32, TF32 off) + the reference's own MSDA CUDA kernel (oracle/_ref, sm_100a)"}
 
 
 def main():
@@ -167,6 +292,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -178,8 +305,11 @@ def main():
         return
 
     from dtlr_b200 import dist_util
-    # keep stdout to the ONE JSON line: NCCL prints its version banner there when the environment asks for NCCL_DEBUG=VERSION/INFO
-    os.environ["NCCL_DEBUG"] = os.environ.get("DTLR_NCCL_DEBUG", "WARN")
+    # The environment's NCCL_DEBUG is left alone (the driver reads NCCL's own rank report).  NCCL logs to file descriptor 1; to keep
+    # stdout to the ONE JSON line, fd 1 is pointed at stderr for the run and the line is written to the saved original stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist_util.init("nccl", device)
@@ -311,6 +441,18 @@ def main():
     u8_value = world * B * args.steps / (u8_ms / 1e3)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- BASELINE config 5: the fine-tune step at this N (outside the clock-sampled inference regions)
+    train = None
+    if not args.no_train_step:
+        try:
+            train = train_step_leg(device, rank, world, local)
+        except Exception as e:      # a secondary leg must never cost the headline line
+            train = {"error": repr(e)[:300]}
+            try:
+                barrier()
+            except Exception:
+                pass
+
     if rank != 0:
         dist_util.shutdown()
         return
@@ -332,11 +474,13 @@ def main():
     # the dominant kernel of the step (profiles/r1_launches_step_v6.txt: 18.9 %): the fused FFN block, one launch per encoder /
     # decoder layer; algorithmic FLOPs 4*M*hid*256 per launch; `traffic` = DRAM bytes of one launch from
     # the ncu --set full capture in profiles/r1_ffn_ncu.txt
+    ffn_traffic, ffn_traffic_src = profile_traffic(r"ffn_ln_tcgen05_kernel", "ffn")
+    msda_traffic, msda_traffic_src = profile_traffic(r"msda_fwd", "msda")
     if ffn_events:
         ffn_tf = ffn_flops / (ffn_ms * 1e-3) / 1e12
         roofline = {"kernel": "ffn_ln_tcgen05_kernel (dtlr_ffn_ln: linear1 + ReLU + linear2 + residual + LayerNorm, hidden activation in TMEM)",
                     "bound": "tensor", "achieved": round(ffn_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": round(ffn_tf / peak_tf, 4), "traffic": FFN_DRAM_BYTES_PER_LAUNCH,
+                    "frac": round(ffn_tf / peak_tf, 4), "traffic": ffn_traffic, "traffic_from": ffn_traffic_src,
                     "peak_kind": pk_kind + " sustained cuBLAS bf16 (the kernel runs inside a long step)",
                     "launches_timed": len(ffn_events), "share_of_step": round(ffn_ms / n_prof / ms_step, 3),
                     "algorithmic_flops_per_launch": ffn_flops / len(ffn_events),
@@ -349,23 +493,31 @@ def main():
     hbm = pk["hbm_gbs"]
     msda_gbs = msda_bytes / (msda_ms * 1e-3) / 1e9 if msda_ms > 0 else 0.0
     roofline_msda = {"kernel": "msda_fwd_mma_kernel (dtlr_msda_forward_fused)", "bound": "hbm", "achieved": round(msda_gbs, 1), "peak": hbm,
-                     "unit": "GB/s", "frac": round(msda_gbs / hbm, 4), "traffic": 86.7e6, "peak_kind": pk_kind + " copy bandwidth",
+                     "unit": "GB/s", "frac": round(msda_gbs / hbm, 4), "traffic": msda_traffic, "traffic_from": msda_traffic_src, "peak_kind": pk_kind + " copy bandwidth",
                      "launches_timed": len(msda_events), "share_of_step": round(msda_ms / n_prof / ms_step, 3),
                      "algorithmic_bytes_per_launch": round(msda_bytes / max(1, len(msda_events))),
                      "binding_resource": "shared-memory gather bandwidth (4 KB of taps per (query, head) at 128 B/clk/SM), see DESIGN.md 3.1"}
     # the resource that actually binds it: shared-memory wavefronts (one 128-byte wavefront per clock per SM).  20.2 M wavefronts per
     # launch (ncu l1tex__data_pipe_lsu_wavefronts_mem_shared.sum, profiles/r1_msda_mma_ncu.txt) / (SMs x SM clock) = the floor
     try:
-        if msda_events and clocks and clocks.get("sm_mhz"):
+        wf, wf_src = profile_metrics(r"msda_fwd", ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",), "msda")
+        if msda_events and clocks and clocks.get("sm_mhz") and wf:
             roofline_msda.update(msda_binding_view(1e3 * msda_ms / len(msda_events),
-                                                   torch.cuda.get_device_properties(device).multi_processor_count, clocks["sm_mhz"]))
+                                                   torch.cuda.get_device_properties(device).multi_processor_count, clocks["sm_mhz"],
+                                                   wf["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"], wf_src))
     except Exception as e:      # secondary view, added after the last GPU run of the round
         roofline_msda["binding_error"] = repr(e)
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N = 1 only; --impl reference gives the N > 1 arm
         ips, sec = cpu_baseline_run(8, 3, 1)
-        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+        cpu = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
                "sample": "3 forwards of 8 images (3x40x1024) after 1 warm-up, oracle/dino_ref.py + oracle/msda_ref.c, fp32"}
+    gpu_ref = None
+    if not args.no_gpu_reference and world == 1:
+        try:
+            gpu_ref = gpu_reference_leg(device, B)
+        except Exception as e:
+            gpu_ref = {"error": repr(e)[:300]}
     line = {"metric": "text-line images/sec (DINO forward)", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -381,8 +533,9 @@ def main():
                        "d2h_bytes_per_step": int(ids.numel() * 4), "ms_per_step": round(u8_ms / args.steps, 3),
                        "api": "dtlr_b200.evaluation.LineEvaluator.predict: host u8 grayscale lines -> dtlr_preprocess_u8 (ToTensor + Normalize + pad on the GPU) -> DINO.forward -> fused decode -> host class-id lists"},
             "gpu_launches": launches, "roofline": roofline, "roofline_gemm": roofline_gemm, "roofline_msda": roofline_msda,
-            "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+            "cpu_baseline": cpu, "gpu_reference": gpu_ref, "train_step": train}
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     dist_util.shutdown()
 
 

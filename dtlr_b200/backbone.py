@@ -163,12 +163,58 @@ def build_position_encoding(args):
     return PositionEmbeddingSineHW(args.hidden_dim // 2, args.pe_temperatureH, args.pe_temperatureW)
 
 
+TORCHVISION_RESNET50_FILES = ("resnet50-0676ba61.pth", "resnet50-19c8e357.pth", "resnet50-11ad3fa6.pth")
+
+
+def find_pretrained_resnet50(args=None):
+    """Where ImageNet ResNet-50 weights can come from without a network: `args.backbone_pretrained` (a torchvision-format state-dict
+    file), $DTLR_RESNET50_WEIGHTS, or a file torchvision already downloaded into the torch hub cache."""
+    import os
+    cand = [getattr(args, "backbone_pretrained", None), os.environ.get("DTLR_RESNET50_WEIGHTS")]
+    hub = os.path.join(torch.hub.get_dir(), "checkpoints")
+    cand += [os.path.join(hub, f) for f in TORCHVISION_RESNET50_FILES]
+    return next((c for c in cand if c and os.path.isfile(c)), None)
+
+
+def load_pretrained_resnet50(body, path):
+    """reference backbone.py:118-121 builds torchvision resnet50(pretrained=is_main_process()): rank 0 holds ImageNet weights (incl. the
+    FrozenBatchNorm statistics) and DDP's construction-time broadcast hands them to the other ranks.  Here: rank 0 reads `path`
+    (torchvision key layout; `fc.*` and `num_batches_tracked` are dropped as IntermediateLayerGetter / FrozenBatchNorm2d do), then the
+    tensors are broadcast when torch.distributed is initialised."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if rank == 0:
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd.get("model", sd)) if isinstance(sd, dict) else sd
+        sd = {k: v for k, v in sd.items() if not k.startswith("fc.") and not k.endswith("num_batches_tracked")}
+        missing, unexpected = body.load_state_dict(sd, strict=False)
+        if missing or unexpected:
+            raise RuntimeError("pretrained ResNet-50 file %s does not match the torchvision layout: missing %s unexpected %s"
+                               % (path, list(missing)[:5], list(unexpected)[:5]))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(body.parameters()) + list(body.buffers()):
+            dist.broadcast(t.data, src=0)
+
+
 def build_backbone(args):
-    """reference backbone.py:147-219"""
+    """reference backbone.py:147-219.  Divergence handled here: the reference DOWNLOADS ImageNet weights on rank 0
+    (backbone.py:118-121); there is no network on the target boxes, so the weights are taken from a local file
+    (find_pretrained_resnet50) and, when none exists, the body keeps its random init with a warning -- harmless for checkpoint-based
+    inference / fine-tuning (the checkpoint overwrites every backbone tensor), wrong for from-scratch training."""
+    import warnings
     train_backbone = args.lr_backbone > 0
     if not train_backbone:
         raise ValueError("Please set lr_backbone > 0")
     backbone = Backbone(args.backbone, train_backbone, args.dilation, args.return_interm_indices)
+    path = find_pretrained_resnet50(args)
+    if path is not None:
+        load_pretrained_resnet50(backbone.body, path)
+    elif getattr(args, "backbone_pretrained", None) or getattr(args, "require_pretrained_backbone", False):
+        raise FileNotFoundError("pretrained ResNet-50 weights requested but not found: %r" % getattr(args, "backbone_pretrained", None))
+    else:
+        warnings.warn("dtlr_b200: no ImageNet ResNet-50 weights found (args.backbone_pretrained / $DTLR_RESNET50_WEIGHTS / torch hub "
+                      "cache): the frozen stem + layer1 and the FrozenBatchNorm statistics stay at their random / identity init. "
+                      "Load a checkpoint before use, or pass the torchvision resnet50 state dict for from-scratch training.")
     model = Joiner(backbone, build_position_encoding(args))
     model.num_channels = backbone.num_channels
     return model

@@ -36,8 +36,8 @@ def latin_ctc_args(**overrides):
 
 
 def latin_args(**overrides):
-    """config/Latin.py (synthetic pre-training; differs from Latin_CTC on the hot path only by use_dn=True)."""
-    d = dict(_LATIN_CTC, use_dn=True)
+    """config/Latin.py (synthetic pre-training; differs from Latin_CTC on the hot path only by use_dn=True; lr_backbone 1e-5, Latin.py:7)."""
+    d = dict(_LATIN_CTC, use_dn=True, lr_backbone=1e-5)
     d.update(overrides)
     return SimpleNamespace(**d)
 

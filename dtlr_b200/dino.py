@@ -50,6 +50,10 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
     known_bid = batch_idx.repeat(2 * dn_number, 1).view(-1)
     known_bboxs = boxes.repeat(2 * dn_number, 1)
     known_bbox_expand = known_bboxs.clone()
+    if label_noise_ratio > 0:
+        # reference dn_components.py:64-70 draws the label-noise mask and never applies it (chosen_indice is unused); the draw is kept
+        # so that the generator stream -- and with it the box noise below -- matches the reference seed for seed
+        torch.rand_like(known_labels.float())
     single_pad = max(known_num)
     pad_size = int(single_pad * 2 * dn_number)
     nb = boxes.shape[0]
@@ -199,6 +203,18 @@ class DINO(nn.Module):
             from .engine import InferenceEngine
             self._engine = InferenceEngine(self)
         return self._engine
+
+    def invalidate_engine(self):
+        """Call after editing weights through `.data` (e.g. the class-head surgery of reference finetuning.py:329-353 /
+        evaluation.py:60-86 when done AFTER an eval forward): the fused engine keeps packed (folded, bf16) copies of the weights and
+        CUDA graphs that in-place `.data` writes cannot be seen through.  load_state_dict() calls it itself."""
+        if self._engine is not None:
+            self._engine.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        self.invalidate_engine()
+        return r
 
     def forward(self, samples: NestedTensor, targets: List = None):
         samples = self._make_inputs(samples)

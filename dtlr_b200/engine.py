@@ -38,15 +38,27 @@ class InferenceEngine:
         self.model = model
         self._packed = None
         self._key = None
+        self._epoch = 0
 
     # ------------------------------------------------------------------------------------------------ packing
     def _pack_key(self, dtype, device):
-        ver = 0
-        for p in self.model.parameters():
-            ver += p._version
-        for b in self.model.buffers():
-            ver += b._version
-        return (dtype, str(device), ver)
+        """Cache key of the packed weights and of the captured graphs: identity, storage and in-place version of every parameter and
+        buffer (a replaced module, a re-assigned `.data` tensor or an optimizer step all change it).  Writes THROUGH `.data`
+        (`p.data[i] = v`, `p.data.mul_()` -- reference finetuning.py:329-353 does this) change none of the three: callers that do
+        such surgery after an eval forward call `model.invalidate_engine()` (DINO.load_state_dict does it by itself)."""
+        sig = [self._epoch]
+        for t in self.model.parameters():
+            sig.append((id(t), t.data_ptr(), t._version))
+        for t in self.model.buffers():
+            sig.append((id(t), t.data_ptr(), t._version))
+        return (dtype, str(device), hash(tuple(sig)))
+
+    def invalidate(self):
+        """drop the packed weights and every captured CUDA graph (they hold copies of the weights)"""
+        self._epoch += 1
+        self._packed = self._key = None
+        if hasattr(self, "_graphs"):
+            self._graphs.clear()
 
     def packed(self, dtype, device):
         key = self._pack_key(dtype, device)
@@ -200,10 +212,16 @@ class InferenceEngine:
         x, mask = samples.tensors, samples.mask
         key = (tuple(x.shape), str(x.device), m.compute_dtype, m.engine_outputs, bool(getattr(samples, "nopad", False)),
                self._pack_key(m.compute_dtype, x.device))
-        ent = self._graphs.get(key) if hasattr(self, "_graphs") else None
-        if ent is None:
-            if not hasattr(self, "_graphs"):
-                self._graphs = {}
+        if not hasattr(self, "_graphs"):
+            import collections
+            self._graphs = collections.OrderedDict()
+            # ONE private memory pool for every captured shape: graphs replay one at a time on one stream, so their intermediate
+            # activations (> 1 GB at B = 64) can share addresses; only the static inputs / outputs of each entry stay distinct
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        ent = self._graphs.get(key)
+        if ent is not None:
+            self._graphs.move_to_end(key)
+        else:
             sx = x.float().contiguous().clone()
             sm = mask.contiguous().clone()
             side = torch.cuda.Stream(device=x.device)
@@ -214,11 +232,11 @@ class InferenceEngine:
             torch.cuda.current_stream(x.device).wait_stream(side)
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, pool=self._graph_pool):
                 out = self._forward_eager(NestedTensor(sx, sm, getattr(samples, "nopad", False)), None)
             ent = (graph, sx, sm, out)
-            if len(self._graphs) >= getattr(m, "max_cuda_graphs", 8):     # every graph owns its static buffers + activation pool
-                self._graphs.clear()
+            while len(self._graphs) >= max(1, getattr(m, "max_cuda_graphs", 8)):     # least recently used shape goes first
+                self._graphs.popitem(last=False)
             self._graphs[key] = ent
         graph, sx, sm, out = ent
         sx.copy_(x, non_blocking=True)

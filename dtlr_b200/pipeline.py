@@ -11,8 +11,11 @@ from . import dino
 
 
 class HostPipeline:
-    def __init__(self, model, device=None, eps=0.003, slots=2):
+    def __init__(self, model, device=None, eps=0.003, slots=2, copy=True):
+        """copy=True (default): every yielded tensor is the caller's own.  copy=False yields the internal pinned result buffer of
+        the slot, which is OVERWRITTEN `slots` batches later -- only for callers that consume each result before pulling the next."""
         self.model = model
+        self.copy = copy
         self.device = device or next(model.parameters()).device
         self.eps = eps
         self.slots = slots
@@ -33,7 +36,7 @@ class HostPipeline:
             if len(pending) >= self.slots:                      # the slot's previous result must have left the device
                 s, ev = pending.pop(0)
                 ev.synchronize()
-                yield self._host_out[s]
+                yield self._host_out[s].clone() if self.copy else self._host_out[s]
             if self._dev_in[slot] is None or self._dev_in[slot].shape != hb.shape:
                 self._dev_in[slot] = torch.empty(hb.shape, dtype=hb.dtype, device=self.device)
                 self._consumed[slot] = None                     # recycled allocator block: order after all compute work
@@ -59,4 +62,4 @@ class HostPipeline:
             pending.append((slot, ev))
         for s, ev in pending:
             ev.synchronize()
-            yield self._host_out[s]
+            yield self._host_out[s].clone() if self.copy else self._host_out[s]

@@ -40,8 +40,27 @@ def _prep(value, shapes, lsi, loc, w):
     return dt, v, sh, ls, lo, ww, (B, S, M, D, L, Lq, P)
 
 
+_REF_CUDA = None
+
+
+def _ref_cuda():
+    """the reference's OWN CUDA op recompiled for sm_100a (oracle/_ref/, oracle/build_ref_cuda.py): the GPU-side baseline"""
+    global _REF_CUDA
+    if _REF_CUDA is None:
+        from . import build_ref_cuda
+        _REF_CUDA = build_ref_cuda.load()
+        if _REF_CUDA is None:
+            raise RuntimeError("oracle/_ref/MultiScaleDeformableAttention.so not built (python oracle/build_ref_cuda.py)")
+    return _REF_CUDA
+
+
 def msda_forward(value, shapes, lsi, loc, w):
-    """value (B,S,M,D), shapes (L,2), lsi (L,), loc (B,Lq,M,L,P,2), w (B,Lq,M,L,P) -> (B,Lq,M*D) torch CPU."""
+    """value (B,S,M,D), shapes (L,2), lsi (L,), loc (B,Lq,M,L,P,2), w (B,Lq,M,L,P) -> (B,Lq,M*D) torch CPU.
+    CUDA tensors go to the reference's own CUDA kernel (bench.py `gpu_reference` leg: reference-shaped torch path on the same GPU)."""
+    if value.is_cuda:
+        B = value.shape[0]
+        return _ref_cuda().ms_deform_attn_forward(value.contiguous(), shapes.to(value.device), lsi.to(value.device),
+                                                  loc.contiguous(), w.contiguous(), 64 if B % 64 == 0 else B)
     dt, v, sh, ls, lo, ww, (B, S, M, D, L, Lq, P) = _prep(value, shapes, lsi, loc, w)
     out = np.empty((B, Lq, M * D), dtype=dt)
     fn = _lib().msda_ref_fwd_f64 if dt == np.float64 else _lib().msda_ref_fwd_f32

@@ -11,6 +11,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # tests fill the model with dtlr_b200.synth weights right after building it
+    config.addinivalue_line("filterwarnings", "ignore:dtlr_b200. no ImageNet ResNet-50 weights found")
 
 
 @pytest.fixture(scope="session")

@@ -85,3 +85,44 @@ def test_collate_fn_like_reference():
     assert isinstance(samples, NestedTensor) and samples.tensors.shape == (2, 3, 5, 7) and isinstance(targets, tuple) and len(targets) == 2
     assert samples.mask[0, :4, :7].sum() == 0 and samples.mask[0, 4].all() and samples.mask[1, :, 6].all() and not samples.nopad
     assert targets[1]["labels"].tolist() == [3]
+
+
+def test_pretrained_backbone_file_is_loaded_and_missing_file_is_loud(tmp_path):
+    """reference backbone.py:118-121 starts from ImageNet weights (downloaded); here they come from a torchvision-format file"""
+    import warnings
+    from dtlr_b200 import backbone
+    donor = backbone.ResNet50Body((1, 2, 3))
+    sd = {k: torch.randn_like(v) for k, v in donor.state_dict().items()}
+    tv = dict(sd)
+    tv["fc.weight"], tv["fc.bias"] = torch.zeros(1000, 2048), torch.zeros(1000)        # dropped like IntermediateLayerGetter does
+    tv["bn1.num_batches_tracked"] = torch.tensor(0)
+    path = str(tmp_path / "resnet50.pth")
+    torch.save(tv, path)
+    bb = backbone.build_backbone(config.latin_ctc_args(backbone_pretrained=path))
+    got = bb[0].body.state_dict()
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.raises(FileNotFoundError):
+        backbone.build_backbone(config.latin_ctc_args(backbone_pretrained=str(tmp_path / "nope.pth")))
+    if backbone.find_pretrained_resnet50(config.latin_ctc_args()) is None:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            backbone.build_backbone(config.latin_ctc_args())
+        assert any("no ImageNet ResNet-50 weights" in str(x.message) for x in w)
+
+
+def test_engine_cache_key_sees_replaced_modules_and_invalidate():
+    """the packed-weight / graph cache key must change when a head is replaced (evaluation.py:60-86 style surgery)"""
+    model = MODULE_BUILD_FUNCS.get("dino")(config.latin_ctc_args(num_queries=10))[0]
+    eng = model.engine()
+    k0 = eng._pack_key(torch.float32, "cpu")
+    assert eng._pack_key(torch.float32, "cpu") == k0
+    model.transformer.enc_out_class_embed = torch.nn.Linear(256, 166)          # fresh module: every _version is again 0/1
+    k1 = eng._pack_key(torch.float32, "cpu")
+    assert k1 != k0
+    model.class_embed[0].weight.data[3] = 1.0                                  # invisible to autograd versions ...
+    assert eng._pack_key(torch.float32, "cpu") == k1
+    model.invalidate_engine()                                                  # ... so the caller says so
+    assert eng._pack_key(torch.float32, "cpu") != k1
+    k2 = eng._pack_key(torch.float32, "cpu")
+    model.load_state_dict(model.state_dict())
+    assert eng._pack_key(torch.float32, "cpu") != k2

@@ -110,5 +110,11 @@ def test_bench_secondary_views_arithmetic():
     v = bench.gemm_hbm_view(3.0e9, 1.5, 3, 6000.0)                 # 3 GB over 1.5 ms = 2000 GB/s
     assert v["achieved"] == 2000.0 and v["frac"] == round(2000.0 / 6000.0, 4) and v["algorithmic_bytes_per_step"] == 1.0e9
     assert bench.gemm_hbm_view(0.0, 0.0, 0, 6000.0)["achieved"] == 0.0
-    b = bench.msda_binding_view(107.0, 148, 1965.0)
+    b = bench.msda_binding_view(107.0, 148, 1965.0, 20217621, "profiles/x.txt")
     assert abs(b["binding_floor_us"] - 69.5) < 0.1 and abs(b["binding_frac"] - 0.65) < 0.01
+    # the ncu-derived constants are parsed from the committed summaries, not pasted into bench.py
+    t, src = bench.profile_traffic(r"ffn_ln_tcgen05_kernel", "ffn")
+    assert src is not None and 1e6 < t < 1e9
+    m, src = bench.profile_metrics(r"msda_fwd", ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",), "msda")
+    assert src is not None and m["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"] > 1e6
+    assert bench.profile_metrics(r"no_such_kernel", ("dram__bytes_read.sum",)) == ({}, None)

@@ -137,30 +137,119 @@ def test_bf16_throughput_mode_agreement():
     assert e_log < 5e-2 and e_box < 5e-2 and agree >= 0.90
 
 
-def test_hwdb_wide_head_engine_matches_module_path():
-    """BASELINE config 3 (config/HWDB_full.py, 7356 classes): no reference fixture exists for it (52 M parameters, no
-    checkpoint), so the fused engine is checked against the module path, which is itself pinned to the reference vectors
-    at C=166; the only new ingredient is the C-wide class head (N = 7356 GEMMs, 7357-row label table)."""
+def _oracle_run(model, x, cfg_kw):
+    """the CPU oracle (oracle/dino_ref.py, pinned to the reference-generated fixtures by tests/test_oracle_dino.py) on the model's
+    own weights -- runs on the host cores of the GPU box (about 15 images/s)"""
+    from oracle import dino_ref
+    sd = {k: v.detach().cpu().float() for k, v in model.state_dict().items()}
+    st = {}
+    ref = dino_ref.dino_forward(sd, dino_ref.default_cfg(**cfg_kw), x, stages=st)
+    return ref, st
+
+
+def _decidable_frames(ref, out, margin):
+    """frames of the CTC view (reference dino.py:472-502 + engine.py:523-529) that the reference decides by more than `margin`
+    (neighbouring cx gap and top-2 probability gap); returns (#frames, #decidable, #decidable mismatching)"""
+    from oracle import dino_ref
+    ref_new, idx = dino_ref.ctc_view(ref["pred_logits"], ref["pred_boxes"])
+    cx = torch.gather(ref["pred_boxes"][:, :, 0], 1, idx)
+    gap = torch.minimum(torch.diff(cx, dim=1, prepend=cx[:, :1] - 1), torch.diff(cx, dim=1, append=cx[:, -1:] + 1))
+    top2 = ref_new.topk(2, dim=-1)[0]
+    decidable = (gap >= margin) & ((top2[..., 0] - top2[..., 1]) >= margin)
+    mine = dino.decode_frames(out).long().cpu()
+    mism = mine != ref_new.argmax(-1)
+    return mism.numel(), int(decidable.sum()), int((mism & decidable).sum())
+
+
+@pytest.fixture(scope="module")
+def bench_shape():
+    """BASELINE config 2 at the shape bench.py times: 64 x 3x40x1024, Q = 900, C = 166, the bench's own synthetic batch"""
+    model, _, _ = build_model(900)
+    x = synth.synth_images(64, 40, 1024, seed=100)
+    ref, st = _oracle_run(model, x, dict(num_queries=900))
+    return model, x, ref, st
+
+
+def test_bench_shape_fp32_vs_oracle(bench_shape):
+    """parity AT the bench shape (B = 64 selects other tile shapes / persistent-grid schedules / weight-stationary
+    slicing than the B <= 3 fixtures): fp32 mode within 1e-3 of the oracle on every stage and output, rankings identical wherever the
+    reference's score gap is decidable, identical character frames, and CUDA-graph replay == eager launches."""
+    model, x, ref, rst = bench_shape
+    xg = x.cuda()
+    out, st = run_engine(model, xg, force=rst["topk_idx"])
+    for a, b, name in ((st["memory"], rst["memory"], "memory"), (st["topk_scores"], rst["topk_scores"], "scores"),
+                       (st["hs"][5], rst["hs"][5], "hs5"), (out["pred_logits"], ref["pred_logits"], "logits"),
+                       (out["pred_boxes"], ref["pred_boxes"], "boxes"),
+                       (out["aux_outputs"][0]["pred_logits"], ref["aux_outputs"][0]["pred_logits"], "aux0 logits"),
+                       (out["interm_outputs"]["pred_boxes"], ref["interm_outputs"]["pred_boxes"], "interm boxes")):
+        e = rel(a.float(), b)
+        print("B=64 fp32 %-12s rel-to-max %.2e" % (name, e))
+        assert e < TOL, name
+    n, dec, bad = _decidable_frames(ref, out, 1e-4)
+    print("B=64 fp32 frames %d decidable (margin 1e-4) %d mismatching-decidable %d" % (n, dec, bad))
+    assert bad == 0 and dec > 0.9 * n
+    # un-forced ranking: every mismatch sits on a reference near-tie
+    out_u, st_u = run_engine(model, xg)
+    sc = torch.gather(rst["topk_scores"], 1, rst["topk_idx"]).numpy()
+    tie = np.minimum(np.abs(np.diff(sc, axis=1, prepend=np.inf)), np.abs(np.diff(sc, axis=1, append=-np.inf))) < 1e-4
+    mism = st_u["topk_idx"].cpu().numpy() != rst["topk_idx"].numpy()
+    print("B=64 fp32 un-forced ranking: %d of %d positions differ, all on near-ties: %s" % (mism.sum(), mism.size, bool(tie[mism].all())))
+    assert tie[mism].all() and mism.mean() < 0.05
+    # CUDA-graph replay (what bench.py times) returns what the eager launches return
+    model.use_cuda_graph = True
+    try:
+        with torch.no_grad():
+            model(xg)
+            og = model(xg)
+        assert torch.equal(og["pred_logits"], out_u["pred_logits"]) and torch.equal(og["pred_boxes"], out_u["pred_boxes"])
+    finally:
+        model.use_cuda_graph = False
+
+
+def test_bench_shape_throughput_mode_vs_oracle(bench_shape):
+    """the mode bench.py times (16-bit tensor-core operands, fp32 accumulation), at the bench shape, against the oracle with the
+    reference ranking forced.  The bound asserted here is the mode's documented error budget (regenerated by
+    tests/precision_sim.py): no single-pass 16-bit operand format reaches 1e-3 through ~100 dependent layers."""
+    model, x, ref, rst = bench_shape
+    dt = torch.bfloat16
+    out, st = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=dt)
+    errs = {}
+    for a, b, name in ((st["feats"][2][0], rst["feats"][2], "feat_c5"), (st["memory"], rst["memory"], "memory"),
+                       (st["topk_scores"], rst["topk_scores"], "scores"), (st["hs"][5], rst["hs"][5], "hs5"),
+                       (out["pred_logits"], ref["pred_logits"], "logits"), (out["pred_boxes"], ref["pred_boxes"], "boxes")):
+        errs[name] = rel(a.float(), b)
+    n, dec, bad = _decidable_frames(ref, out, 0.05)
+    print("B=64 %s per-stage rel-to-max: %s ; frames %d, decided by >0.05 in the reference %d, of those mismatching %d" % (
+        dt, " ".join("%s %.2e" % kv for kv in errs.items()), n, dec, bad))
+    assert errs["logits"] < 5e-2 and errs["boxes"] < 5e-2
+    assert bad <= 0.02 * dec
+
+
+def test_hwdb_wide_head_engine_vs_oracle():
+    """BASELINE config 3 (config/HWDB_full.py, 7356 classes) against the ORACLE: the C-wide class heads
+    (N = 7356 GEMMs on 912 tokens + 6 x 900 queries, 7357-column CTC view) in fp32 at 1e-3 with identical frames, and the
+    throughput mode within its documented bound."""
     from dtlr_b200 import config
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     model, _, _ = dino.build_dino(config.hwdb_args(num_queries=300))
     synth.load_synth_weights(model, 0)
     model = model.cuda().eval()
-    x = synth.synth_images(2, 40, 1024, seed=7).cuda()
-    model.use_engine = False
-    st = {}
-    model.transformer.debug_stages = st
-    with torch.no_grad():
-        ref = model(x)
-    model.transformer.debug_stages = None
-    out, _ = run_engine(model, x, force=st["topk_idx"])
+    x = synth.synth_images(2, 40, 1024, seed=7)
+    ref, rst = _oracle_run(model, x, dict(num_queries=300, num_classes=7356))
+    out, st = run_engine(model, x.cuda(), force=rst["topk_idx"])
     assert out["pred_logits"].shape == (2, 300, 7356)
-    assert rel(out["pred_logits"], ref["pred_logits"]) < TOL and rel(out["pred_boxes"], ref["pred_boxes"]) < TOL
-    frames = dino.decode_frames(out)
-    assert (frames.long().cpu() == dino.ctc_view(ref["pred_logits"], ref["pred_boxes"]).argmax(-1).cpu()).float().mean() > 0.99
-    out16, _ = run_engine(model, x, force=st["topk_idx"], dtype=torch.bfloat16)
-    assert rel(out16["pred_logits"], ref["pred_logits"]) < 5e-2
+    for a, b, name in ((st["topk_scores"], rst["topk_scores"], "scores"), (out["pred_logits"], ref["pred_logits"], "logits"),
+                       (out["pred_boxes"], ref["pred_boxes"], "boxes"),
+                       (out["interm_outputs"]["pred_logits"], ref["interm_outputs"]["pred_logits"], "interm logits")):
+        e = rel(a.float(), b)
+        print("HWDB fp32 %-13s rel-to-max %.2e" % (name, e))
+        assert e < TOL, name
+    n, dec, bad = _decidable_frames(ref, out, 1e-5)
+    print("HWDB fp32 frames %d decidable (margin 1e-5) %d mismatching-decidable %d" % (n, dec, bad))
+    assert bad == 0
+    out16, _ = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=torch.bfloat16)
+    assert rel(out16["pred_logits"].float(), ref["pred_logits"]) < 5e-2
 
 
 def test_host_pipeline_matches_direct_calls():
@@ -176,7 +265,7 @@ def test_host_pipeline_matches_direct_calls():
         direct = [dino.decode_frames(model(b.cuda())).cpu() for b in batches]
         for graph in (False, True):
             model.use_cuda_graph = graph
-            got = [f.clone() for f in HostPipeline(model).run(iter(batches))]
+            got = list(HostPipeline(model).run(iter(batches)))       # default copy=True: results are not aliased ring buffers
             assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, direct))
 
 

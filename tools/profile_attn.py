@@ -3,7 +3,7 @@ ncu --set full --clock-control none --import-source on -k regex:mha_tc2 -s 2 -c 
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dtlr_b200 import ops
-ops.ATTN_IMPL = "tc"
+ops.ATTN_IMPL = sys.argv[1] if len(sys.argv) > 1 else "tc"
 B, Q, heads, d = 64, 900, 8, 256
 qk = torch.randn(B * Q, 2 * d, device="cuda").bfloat16()
 v = torch.randn(B * Q, d, device="cuda").bfloat16()
