@@ -745,7 +745,7 @@ __device__ __forceinline__ void red_add_f32x4_nc(float* p, const float a, const 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
-// GROUPED (opt-in, dtlr_debug_flags(65536); measured 433 us vs 594 us at B=32, Lq=900 -- written from the ncu reading of the default variant,
+// GROUPED (default for P = 4 since round 2; dtlr_debug_flags(65536) = the variant above; measured 433 us vs 594 us at B=32, Lq=900 -- written from the ncu reading of the default variant,
 // profiles/r1_msda_bwd_ncu.txt: 16 warps per SM, one value load in flight per warp because the clobbered `red` asm pins the
 // next point's load behind it): the four value loads of a group of 4 points are issued before any of their arithmetic and the
 // reductions carry no memory clobber, so a warp keeps 4 L2 round trips in flight instead of 1.  Arithmetic per point is identical.
@@ -1067,9 +1067,11 @@ extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, cons
             kern<<<g, threads_per_cta, 0, st>>>((const float*)value, (const float*)loc, (const float*)attn, (const float*)grad_out,
                                                 (float*)grad_value, (float*)grad_loc, (float*)grad_attn, lv, warps, S, M, Lq);
         };
-        // grouped-load variant (433 vs 594 us): opt-in until the complete GPU suite has run with it; int offsets need S*M*32 < 2^31
-        if ((g_debug_flags & 65536) && P == 4 && (long long)S * M * 32 < (1ll << 31)) {
-            // flag 131072 (with 65536): 8 loads in flight, 128-thread CTAs (148 registers -> 3 CTAs per SM) -- not yet measured
+        // grouped-load variant: the default since round 2 (the complete GPU suite passes with it; B = 64, Lq = 912: 855 us vs 1197 us,
+        // B = 32, Lq = 900: 433 vs 594 us).  dtlr_debug_flags(65536) selects the one-load-in-flight variant (A/B); int offsets need
+        // S*M*32 < 2^31
+        if (!(g_debug_flags & 65536) && P == 4 && (long long)S * M * 32 < (1ll << 31)) {
+            // flag 131072: 8 loads in flight, 128-thread CTAs (148 registers -> 3 CTAs per SM) -- not yet measured
             if (g_debug_flags & 131072) launch(msda_bwd_d32_grouped_kernel<4, 8>, 128);
             else launch(msda_bwd_d32_grouped_kernel<4, 4>);
         } else switch (P) {

@@ -304,10 +304,34 @@ class SetCriterion(nn.Module):
             self.losses_all = list(losses)
             self.losses_CTC = ["loss_CTC"]
 
+    fused_ctc = True        # CUDA: dtlr_ctc_loss (csrc/decode.cu); False: the reference's literal torch chain (kept as the A/B check)
+
     def loss_CTC(self, outputs, targets, indices, num_boxes, log=True, return_preds=False):
-        """reference dino.py:457-551"""
-        pred_logits = outputs["pred_logits"].float()
+        """reference dino.py:457-551.  On CUDA the whole chain (cx sort, sigmoid, blank synthesis, hard-blank interleave, log,
+        nn.CTCLoss forward AND backward) is the fused kernel set behind dtlr_ctc_loss: the (B,2Q,C+1) tensor is never built."""
+        pred_logits = outputs["pred_logits"]
         device = pred_logits.device
+        lens = [len(t["labels"]) for t in targets]
+        if self.fused_ctc and pred_logits.is_cuda:
+            from . import ops
+            B = pred_logits.shape[0]
+            Lmax = max(lens) if lens else 0
+            with torch.no_grad():
+                tt = torch.zeros((B, max(Lmax, 1)), dtype=torch.int32, device=device)
+                for i, t in enumerate(targets):
+                    if lens[i]:
+                        tt[i, : lens[i]] = t["labels"].to(device=device, dtype=torch.int32)
+                ll = torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
+            if Lmax == 0:
+                tt = tt[:, :0]
+            loss = ops.ctc_loss(pred_logits, outputs["pred_boxes"], tt, ll, eps=0.003, zero_infinity=True)
+            losses = {"loss_CTC": loss}
+            if return_preds:
+                with torch.no_grad():
+                    _, new_pred_logits = ops.ctc_decode(pred_logits.detach(), outputs["pred_boxes"].detach(), 0.003, want_new_pred=True)
+                return losses, new_pred_logits, None
+            return losses
+        pred_logits = pred_logits.float()
         new_pred_logits = ctc_view(pred_logits, outputs["pred_boxes"].float(), eps=0.003)
         B, Q, C1 = new_pred_logits.shape
         padded = torch.empty(B, 2 * Q, C1, dtype=new_pred_logits.dtype, device=device)
@@ -316,7 +340,6 @@ class SetCriterion(nn.Module):
         padded[:, 1::2, 0] = 1
         length_pred = torch.full((B,), 2 * Q, dtype=torch.int64)
         with torch.no_grad():
-            lens = [len(t["labels"]) for t in targets]
             length_input = torch.tensor(lens, dtype=torch.int64)
             targets_tensor = torch.zeros(B, max(lens) if lens else 0)
             for i, t in enumerate(targets):

@@ -238,6 +238,55 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False, prob_sca
     return (frames, newp) if want_new_pred else frames
 
 
+class _FusedCTCLoss(torch.autograd.Function):
+    """loss_CTC of reference models/dino/dino.py:457-551 as ONE autograd node over the fused kernels of csrc/decode.cu
+    (dtlr_ctc_loss): forward computes the loss AND d loss / d pred_logits (alpha-beta over the implicit interleaved-blank
+    sequence); backward scales it.  pred_boxes only steer the cx sort -- no gradient, exactly as in the reference."""
+
+    @staticmethod
+    def forward(ctx, pred_logits, pred_boxes, targets_i32, lens_i32, eps, zero_infinity):
+        import ctypes
+        L.require_cuda(pred_logits, pred_boxes, targets_i32, lens_i32)
+        B, Q, C = pred_logits.shape
+        logits = pred_logits.float()
+        if not (logits.stride(2) == 1 and logits.stride(0) == Q * logits.stride(1)):
+            logits = logits.contiguous()
+        boxes = pred_boxes.detach().float().contiguous()
+        dev = logits.device
+        Lmax = int(targets_i32.shape[1])
+        S = 2 * Lmax + 1
+        nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        grad = torch.empty((B, Q, C), dtype=torch.float32, device=dev)
+        perm = torch.empty((B, Q), dtype=torch.int32, device=dev)
+        rsum = torch.empty((B, Q), dtype=torch.float32, device=dev)
+        label = torch.empty((B, Q), dtype=torch.int32, device=dev)
+        frames = torch.empty((B, Q), dtype=torch.int32, device=dev)
+        lp = torch.empty((B, Q, Lmax + 1), dtype=torch.float32, device=dev)
+        alpha = torch.empty((B, Q, S), dtype=torch.float32, device=dev)
+        gext = torch.empty((B, Q, S), dtype=torch.float32, device=dev)
+        _call("dtlr_ctc_loss", _p(logits), logits.stride(1), _p(boxes), _p(targets_i32), _p(lens_i32), Lmax, ctypes.c_float(eps),
+              1 if zero_infinity else 0, _p(nll), _p(grad), _p(perm), _p(rsum), _p(label), _p(frames), _p(lp), _p(alpha), _p(gext),
+              B, Q, C, _st(logits))
+        L.LAUNCHES += 4                    # row sums, sort, lp table, lattice, gradient: 5 kernels behind one C call
+        per = nll / lens_i32.clamp(min=1).float()
+        if zero_infinity:
+            per = torch.where(torch.isinf(nll), torch.zeros_like(per), per)
+        ctx.save_for_backward(grad)
+        ctx.in_dtype = pred_logits.dtype
+        return per.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).to(ctx.in_dtype), None, None, None, None, None
+
+
+def ctc_loss(pred_logits, pred_boxes, targets_i32, lens_i32, eps=0.003, zero_infinity=True):
+    """pred_logits (B,Q,C), pred_boxes (B,Q,4); targets_i32 (B,Lmax) class ids 0..C-1 (padding ignored), lens_i32 (B) -> scalar loss
+    = nn.CTCLoss(blank=0, reduction='mean', zero_infinity)(log of the interleaved CTC view) of reference dino.py:505-544."""
+    return _FusedCTCLoss.apply(pred_logits, pred_boxes, targets_i32.contiguous(), lens_i32.contiguous(), float(eps), bool(zero_infinity))
+
+
 def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5, out=None, out2=None):
     """bf16 only, N = 256: y = LN(a @ w.T + bias (+ residual)); optional y2 = y + add2.  One tcgen05 kernel."""
     import ctypes

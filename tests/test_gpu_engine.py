@@ -10,6 +10,7 @@ from gpu_common import build_model, fixture, near_tie_mask, rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+MODE_TOL = 5e-2     # documented bound of the 16-bit-operand throughput mode with the ranking forced; measured ~2e-2
 
 
 def run_engine(model, x, force=None, dtype=torch.float32):
@@ -147,18 +148,29 @@ def _oracle_run(model, x, cfg_kw):
     return ref, st
 
 
-def _decidable_frames(ref, out, margin):
-    """frames of the CTC view (reference dino.py:472-502 + engine.py:523-529) that the reference decides by more than `margin`
-    (neighbouring cx gap and top-2 probability gap); returns (#frames, #decidable, #decidable mismatching)"""
+def _decidable_frames(ref, out, cx_margin, p_margin):
+    """frames of the CTC view (reference dino.py:472-502 + engine.py:523-529) that the reference decides by a margin: neighbouring
+    cx gap >= cx_margin (the reading order) and top-2 probability gap >= p_margin (the label).
+    Returns (#frames, #decidable, #decidable mismatching)"""
     from oracle import dino_ref
     ref_new, idx = dino_ref.ctc_view(ref["pred_logits"], ref["pred_boxes"])
     cx = torch.gather(ref["pred_boxes"][:, :, 0], 1, idx)
     gap = torch.minimum(torch.diff(cx, dim=1, prepend=cx[:, :1] - 1), torch.diff(cx, dim=1, append=cx[:, -1:] + 1))
     top2 = ref_new.topk(2, dim=-1)[0]
-    decidable = (gap >= margin) & ((top2[..., 0] - top2[..., 1]) >= margin)
+    decidable = (gap >= cx_margin) & ((top2[..., 0] - top2[..., 1]) >= p_margin)
     mine = dino.decode_frames(out).long().cpu()
     mism = mine != ref_new.argmax(-1)
     return mism.numel(), int(decidable.sum()), int((mism & decidable).sum())
+
+
+def _query_decisions(logits, eps=0.003):
+    """blank-or-class decision of every query BEFORE the cx sort, with the top-2 margin of the CTC-view probabilities"""
+    p = logits.sigmoid()
+    s = p.sum(-1, keepdim=True)
+    low = s < 1 - eps
+    new = torch.cat([torch.where(low, 1 - s, torch.full_like(s, eps)), torch.where(low, p, (1 - eps) * p / s)], -1)
+    top2, arg = new.topk(2, dim=-1)
+    return arg[..., 0], top2[..., 0] - top2[..., 1]
 
 
 @pytest.fixture(scope="module")
@@ -185,8 +197,8 @@ def test_bench_shape_fp32_vs_oracle(bench_shape):
         e = rel(a.float(), b)
         print("B=64 fp32 %-12s rel-to-max %.2e" % (name, e))
         assert e < TOL, name
-    n, dec, bad = _decidable_frames(ref, out, 1e-4)
-    print("B=64 fp32 frames %d decidable (margin 1e-4) %d mismatching-decidable %d" % (n, dec, bad))
+    n, dec, bad = _decidable_frames(ref, out, 1e-5, 1e-4)
+    print("B=64 fp32 frames %d decidable (cx gap >= 1e-5, top-2 gap >= 1e-4) %d mismatching-decidable %d" % (n, dec, bad))
     assert bad == 0 and dec > 0.9 * n
     # un-forced ranking: every mismatch sits on a reference near-tie
     out_u, st_u = run_engine(model, xg)
@@ -218,11 +230,15 @@ def test_bench_shape_throughput_mode_vs_oracle(bench_shape):
                        (st["topk_scores"], rst["topk_scores"], "scores"), (st["hs"][5], rst["hs"][5], "hs5"),
                        (out["pred_logits"], ref["pred_logits"], "logits"), (out["pred_boxes"], ref["pred_boxes"], "boxes")):
         errs[name] = rel(a.float(), b)
-    n, dec, bad = _decidable_frames(ref, out, 0.05)
-    print("B=64 %s per-stage rel-to-max: %s ; frames %d, decided by >0.05 in the reference %d, of those mismatching %d" % (
-        dt, " ".join("%s %.2e" % kv for kv in errs.items()), n, dec, bad))
-    assert errs["logits"] < 5e-2 and errs["boxes"] < 5e-2
-    assert bad <= 0.02 * dec
+    mine, _ = _query_decisions(out["pred_logits"].float().cpu())
+    want, margin = _query_decisions(ref["pred_logits"])
+    dec = margin >= 0.1
+    agree_all = (mine == want).float().mean().item()
+    bad = int(((mine != want) & dec).sum())
+    print("B=64 %s per-stage rel-to-max: %s ; per-query blank/label decisions equal %.4f; of the %d decided by >= 0.1 in the reference, %d differ" % (
+        dt, " ".join("%s %.2e" % kv for kv in errs.items()), agree_all, int(dec.sum()), bad))
+    assert errs["logits"] < MODE_TOL and errs["boxes"] < MODE_TOL
+    assert bad <= 0.005 * int(dec.sum()) and agree_all >= 0.9
 
 
 def test_hwdb_wide_head_engine_vs_oracle():
@@ -245,8 +261,8 @@ def test_hwdb_wide_head_engine_vs_oracle():
         e = rel(a.float(), b)
         print("HWDB fp32 %-13s rel-to-max %.2e" % (name, e))
         assert e < TOL, name
-    n, dec, bad = _decidable_frames(ref, out, 1e-5)
-    print("HWDB fp32 frames %d decidable (margin 1e-5) %d mismatching-decidable %d" % (n, dec, bad))
+    n, dec, bad = _decidable_frames(ref, out, 2e-6, 1e-5)
+    print("HWDB fp32 frames %d decidable (cx gap >= 2e-6, top-2 gap >= 1e-5) %d mismatching-decidable %d" % (n, dec, bad))
     assert bad == 0
     out16, _ = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=torch.bfloat16)
     assert rel(out16["pred_logits"].float(), ref["pred_logits"]) < 5e-2
