@@ -578,11 +578,25 @@ class PostProcess(nn.Module):
         self.num_select = num_select
         self.nms_iou_threshold = nms_iou_threshold
 
+    fused = True        # CUDA: the selection / NMS kernels of csrc/select.cu; False: the literal torch statement (A/B check)
+
     @torch.no_grad()
     def forward(self, outputs, target_sizes, not_to_xyxy=False, test=False):
-        out_logits, out_bbox = outputs["pred_logits"].float(), outputs["pred_boxes"].float()
+        out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
         assert len(out_logits) == len(target_sizes)
         assert target_sizes.shape[1] == 2
+        if self.fused and out_logits.is_cuda and (self.nms_iou_threshold <= 0 or self.num_select <= 1024):
+            from . import ops
+            if test:
+                assert not not_to_xyxy
+            mode = 2 if test else (1 if not_to_xyxy else 0)
+            if self.nms_iou_threshold > 0:
+                scores, labels, boxes, keep, _, _ = ops.postprocess(out_logits, out_bbox, target_sizes.to(out_logits.device), self.num_select,
+                                                                    mode, nms_iou=float(self.nms_iou_threshold))
+                return [{"scores": s[k], "labels": l[k], "boxes": b[k]} for s, l, b, k in zip(scores, labels, boxes, keep)]
+            scores, labels, boxes = ops.postprocess(out_logits, out_bbox, target_sizes.to(out_logits.device), self.num_select, mode)
+            return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, boxes)]
+        out_logits, out_bbox = out_logits.float(), out_bbox.float()
         prob = out_logits.sigmoid()
         scores, topk_indexes = torch.topk(prob.view(out_logits.shape[0], -1), self.num_select, dim=1)
         topk_boxes = topk_indexes // out_logits.shape[2]
@@ -598,6 +612,16 @@ class PostProcess(nn.Module):
             keep = [_nms(b, s, self.nms_iou_threshold) for b, s in zip(boxes, scores)]
             return [{"scores": s[i], "labels": l[i], "boxes": b[i]} for s, l, b, i in zip(scores, labels, boxes, keep)]
         return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, boxes)]
+
+    @torch.no_grad()
+    def read(self, outputs, target_sizes, score_threshold):
+        """PostProcess + NMS + the reading of reference evaluation.py:101-115 in two kernels: labels of the kept detections with score
+        above `score_threshold` in order of box centre x.  Returns (read_labels int32 (B,K) padded with -1, read_count int32 (B))."""
+        from . import ops
+        out_logits = outputs["pred_logits"]
+        r = ops.postprocess(out_logits, outputs["pred_boxes"], target_sizes.to(out_logits.device), self.num_select, 0,
+                            nms_iou=float(self.nms_iou_threshold), score_thr=float(score_threshold))
+        return r[4], r[5]
 
 
 @MODULE_BUILD_FUNCS.registe_with_name(module_name="dino")

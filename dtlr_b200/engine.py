@@ -344,18 +344,18 @@ class InferenceEngine:
             omn = ops.linear_ln(om, *P["enc_output"], None, *P["enc_output_norm"])
             cls_unsel = self._head_gemm(omn, *P["enc_cls"])
             scores = ops.rowmax(cls_unsel, cls_unsel.shape[1]).view(B, S)
-            coord_unsel = (self._mlp3(omn, P["enc_bbox"]) + prop).view(B, S, 4)
-            topk = torch.topk(scores, Q, dim=1)[1]
+            delta_unsel = self._mlp3(omn, P["enc_bbox"]).view(B, S, 4)
+            # fused select (csrc/select.cu): per-line shared-memory sort of the S scores, then ONE gather kernel for the anchors, the
+            # sigmoid of the proposals and the selected memory rows (the reference: torch.topk + 3 torch.gather + sigmoid)
+            topk = ops.topk_select(scores, Q)
             if tr.debug_force_topk is not None:
-                topk = tr.debug_force_topk.to(dev)
+                topk = tr.debug_force_topk.to(dev).contiguous()
             if st is not None:
                 st["topk_scores"], st["topk_idx"] = scores, topk
-            refpoint = torch.gather(coord_unsel, 1, topk.unsqueeze(-1).expand(-1, -1, 4)).contiguous()
-            init_box_proposal = torch.gather(prop.view(B, S, 4), 1, topk.unsqueeze(-1).expand(-1, -1, 4)).sigmoid()
-            tgt_undetach = torch.gather(omn.view(B, S, d), 1, topk.unsqueeze(-1).expand(-1, -1, d)).contiguous()
+            ref0, init_box_proposal, tgt_undetach = ops.select_gather(topk, delta_unsel, prop.view(B, S, 4), omn.view(B, S, d))
 
             # ---- decoder (deformable_transformer.py:652-766)
-            ref = ops.sigmoid(refpoint.view(B * Q, 4))
+            ref = ref0.view(B * Q, 4)           # sigmoid(refpoint_embed): the decoder's first reference points = the interm boxes
             refs = [ref]
             # cross-attention values of all decoder layers in one GEMM: memory is read once, N = n_layers * 256
             val_all = ops.gemm(memory, *P["dec_val_all"])
@@ -411,7 +411,7 @@ class InferenceEngine:
             if m.aux_loss:
                 out["aux_outputs"] = [{"pred_logits": classes[i], "pred_boxes": coords[i]} for i in want if i != n_dec - 1]
             interm_class = self._head_gemm(tgt_undetach.view(B * Q, d), *P["enc_cls"]).unflatten(0, (B, Q))
-            out["interm_outputs"] = {"pred_logits": interm_class, "pred_boxes": refpoint.sigmoid()}
+            out["interm_outputs"] = {"pred_logits": interm_class, "pred_boxes": ref0}
             out["interm_outputs_for_matching_pre"] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
             out["dn_meta"] = None
             self._launches_per_forward = L.LAUNCHES - launches0

@@ -170,7 +170,14 @@ def nms_decode(outputs, postprocessor, TH, NM, num_select=900):
     logits = outputs["pred_logits"]
     postprocessor.num_select = min(num_select, logits.shape[1] * logits.shape[2])
     postprocessor.nms_iou_threshold = NM
-    res = postprocessor(outputs, torch.ones((logits.shape[0], 2), dtype=torch.float32, device=logits.device))
+    sizes = torch.ones((logits.shape[0], 2), dtype=torch.float32, device=logits.device)
+    if getattr(postprocessor, "fused", False) and logits.is_cuda and postprocessor.num_select <= 1024:
+        # two kernels per batch (csrc/select.cu: radix-select top-k + box conversion; NMS bit matrix + greedy scan + threshold + cx order)
+        # and ONE device->host copy, instead of topk / gather / per-image NMS / boolean indexing / sort with a host sync each
+        labels, counts = postprocessor.read(outputs, sizes, TH)
+        labels, counts = labels.cpu(), counts.cpu().tolist()
+        return [labels[i, :n].tolist() for i, n in enumerate(counts)]
+    res = postprocessor(outputs, sizes)
     preds = []
     for r in res:
         x0, _, x1, _ = r["boxes"].unbind(-1)

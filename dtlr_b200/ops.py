@@ -238,6 +238,60 @@ def ctc_decode(pred_logits, pred_boxes, eps=0.003, want_new_pred=False, prob_sca
     return (frames, newp) if want_new_pred else frames
 
 
+def topk_select(scores, K):
+    """scores fp32 (B,S) -> int64 (B,K) = torch.topk(scores, K, dim=1)[1] (csrc/select.cu; ties -> lowest index)"""
+    L.require_cuda(scores)
+    B, S = scores.shape
+    scores = scores.contiguous()
+    idx = torch.empty((B, K), dtype=torch.int64, device=scores.device)
+    _call("dtlr_topk_select", _p(scores), B, S, K, _p(idx), _st(scores))
+    return idx
+
+
+def select_gather(idx, coord, prop, mem):
+    """idx int64 (B,K); coord (bbox-head output) / prop (anchors, logit space) fp32 (B,S,4); mem (B,S,d) ->
+    sigmoid(coord + prop)[idx] (B,K,4), sigmoid(prop)[idx] (B,K,4), mem[idx] (B,K,d)"""
+    L.require_cuda(idx, coord, prop, mem)
+    B, K = idx.shape
+    S, d = mem.shape[1], mem.shape[2]
+    assert coord.is_contiguous() and prop.is_contiguous() and mem.is_contiguous() and idx.is_contiguous()
+    ref = torch.empty((B, K, 4), dtype=torch.float32, device=mem.device)
+    box = torch.empty((B, K, 4), dtype=torch.float32, device=mem.device)
+    tgt = torch.empty((B, K, d), dtype=mem.dtype, device=mem.device)
+    _call("dtlr_select_gather", _p(idx), _p(coord), _p(prop), _p(mem), _p(ref), _p(box), _p(tgt), B, S, K, d, L.dtype_code(mem), _st(mem))
+    return ref, box, tgt
+
+
+def postprocess(pred_logits, pred_boxes, target_sizes, num_select, box_mode=0, nms_iou=None, score_thr=0.0):
+    """PostProcess of reference dino.py:1008-1046 as kernels (csrc/select.cu): returns scores (B,K) fp32, labels (B,K) int64, boxes
+    (B,K,4) fp32 [, keep (B,K) bool, read_labels (B,K) int32, read_count (B) int32 when nms_iou is not None]."""
+    import ctypes
+    L.require_cuda(pred_logits, pred_boxes, target_sizes)
+    B, Q, C = pred_logits.shape
+    logits = pred_logits.float()
+    if not (logits.stride(2) == 1 and logits.stride(0) == Q * logits.stride(1)):
+        logits = logits.contiguous()
+    boxes = pred_boxes.float().contiguous()
+    sizes = target_sizes.float().contiguous()
+    dev = logits.device
+    K = int(num_select)
+    scores = torch.empty((B, K), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, K), dtype=torch.int32, device=dev)
+    out_boxes = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+    keep = rl = rc = None
+    if nms_iou is not None:
+        keep = torch.empty((B, K), dtype=torch.uint8, device=dev)
+        rl = torch.empty((B, K), dtype=torch.int32, device=dev)
+        rc = torch.empty((B,), dtype=torch.int32, device=dev)
+    _call("dtlr_postprocess", _p(logits), logits.stride(1), _p(boxes), _p(sizes), B, Q, C, K, int(box_mode),
+          ctypes.c_float(nms_iou if nms_iou is not None else -1.0), ctypes.c_float(score_thr), _p(scores), _p(labels), _p(out_boxes),
+          _p(keep), _p(rl), _p(rc), _st(logits))
+    if nms_iou is None:
+        return scores, labels.long(), out_boxes
+    L.LAUNCHES += 1
+    return scores, labels.long(), out_boxes, keep.bool(), rl, rc
+
+
 class _FusedCTCLoss(torch.autograd.Function):
     """loss_CTC of reference models/dino/dino.py:457-551 as ONE autograd node over the fused kernels of csrc/decode.cu
     (dtlr_ctc_loss): forward computes the loss AND d loss / d pred_logits (alpha-beta over the implicit interleaved-blank

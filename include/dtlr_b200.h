@@ -193,6 +193,39 @@ int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* boxes, int*
                            int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, float prob_scale,
                            void* stream);
 
+/* Two-stage query selection (models/dino/deformable_transformer.py:345-353): idx int64 [B,K] = torch.topk(scores [B,S], K, dim=1)[1]
+ * (descending, ties resolved to the lowest token index); fails like torch.topk when K > S (reference quirk: 40x704 lines have 627 < 900
+ * tokens).  dtlr_select_gather then performs what follows it in one pass (:348-353, :676): refpoint [B,K,4] = sigmoid((coord +
+ * prop)[idx]) -- coord = enc_out_bbox_embed output, prop = the logit-space anchors (+inf where invalid -> 1.0) --, initbox [B,K,4] =
+ * sigmoid(prop[idx]), tgt [B,K,d] = mem[idx] (mem / tgt of `dtype`, the others fp32). */
+int dtlr_topk_select(const float* scores, int B, int S, int K, long long* idx, void* stream);
+int dtlr_select_gather(const long long* idx, const float* coord, const float* prop, const void* mem, float* refpoint,
+                       float* initbox, void* tgt, int B, int S, int K, int d, int dtype, void* stream);
+/* PostProcess.forward (models/dino/dino.py:1008-1046) and, with `keep`, its NMS branch plus the reading of evaluation.py:94-115:
+ * scores [B,K] / labels int32 [B,K] / boxes_out [B,K,4] = the K largest of the Q*C sigmoid scores of each line (descending; ties ->
+ * lowest flat index q*C + c), label = index % C, box of query index / C converted (box_mode 0: cxcywh -> xyxy, 1: as stored,
+ * 2: x0,y0,w,h -- the reference's `test` flag) and scaled by sizes [B,2] = (img_h, img_w).  logits fp32 [B*Q, ld], boxes fp32 [B*Q,4].
+ * keep (uint8 [B,K], may be NULL): class-agnostic greedy NMS with torchvision.ops.nms semantics at IoU > nms_iou (<= 0: keep all);
+ * read_labels int32 [B,K] / read_count int32 [B]: labels of the kept detections with score > score_thr in order of box centre
+ * (x0+x1)/2 (-1 padded).  K <= 1024 when keep is given. */
+int dtlr_postprocess(const float* logits, int ld, const float* boxes, const float* sizes, int B, int Q, int C, int K,
+                     int box_mode, float nms_iou, float score_thr, float* scores, int* labels, float* boxes_out,
+                     unsigned char* keep, int* read_labels, int* read_count, void* stream);
+
+/* The CTC loss of the fine-tuning step, fused forward + backward (SetCriterion.loss_CTC, models/dino/dino.py:457-551: cx sort, sigmoid,
+ * blank synthesis with eps, one hard-blank frame (1, 1e-5, ...) interleaved after every query (:505-517), log, nn.CTCLoss(blank=0,
+ * zero_infinity, reduction 'mean') (:538-544)) WITHOUT the (B,2Q,C+1) tensors: only the blank and target-label probabilities of each
+ * frame enter a per-line alpha/beta lattice kernel.
+ * logits fp32 [B*Q, ld], boxes fp32 [B*Q,4]; targets dev int32 [B, Lmax] class ids 0..C-1 (padding ignored), target_len dev int32 [B]
+ * (Lmax <= 511).  nll fp32 [B] receives -log p(target | line) (+inf when no alignment exists); grad_logits fp32 [B,Q,C] (may be NULL)
+ * receives d(mean_b nll_b / max(len_b,1)) / d logits in the ORIGINAL query order (zero rows for infeasible lines when zero_infinity).
+ * Scratch (device): perm int32 [B*Q] (the cx permutation, also an output), row_sum fp32 [B*Q], scratch_label / scratch_frames int32
+ * [B*Q], lp fp32 [B*Q*(Lmax+1)], alpha and gext fp32 [B*Q*(2*Lmax+1)] each. */
+int dtlr_ctc_loss(const float* logits, int ld, const float* boxes, const int* targets, const int* target_len, int Lmax,
+                  float eps, int zero_infinity, float* nll, float* grad_logits, int* perm, float* row_sum,
+                  int* scratch_label, int* scratch_frames, float* lp, float* alpha, float* gext, int B, int Q, int C,
+                  void* stream);
+
 /* GPU input stage for already-resized 8-bit line images: ToTensor (datasets/transforms.py:247-249) + Normalize
  * (datasets/transforms.py:552-558) + nested_tensor_from_tensor_list (util/misc.py:375-397) in one kernel.
  * packed (dev u8): the B images back to back, image b at byte offsets[b] (dev int64 [B]), h x w x channels, row-major, channels
