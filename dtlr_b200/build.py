@@ -11,8 +11,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libdtlr_b200.so")
+LIB = os.path.join(HERE, "libdtlr_b200.so")            # 16-bit type = bf16
+LIB_F16 = os.path.join(HERE, "libdtlr_b200_f16.so")    # the same sources with fp16 as the 16-bit type (-DDTLR_BUILD_F16)
 OBJ = os.path.join(CSRC, "build")
+FLAVORS = {"bf16": (LIB, OBJ, []), "f16": (LIB_F16, os.path.join(CSRC, "build", "f16"), ["-DDTLR_BUILD_F16"])}
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -38,28 +40,34 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build_library(force=False, verbose=False, flavors=("bf16", "f16")):
+    """compile every .cu for sm_100a once per 16-bit flavour (all nvcc processes run concurrently) and link the two libraries"""
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    objs = []
-    procs = []
-    for src in sources():
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        objs.append(obj)
-        if force or _stale(obj, [src] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    procs, plan = [], []
+    for fl in flavors:
+        lib, objdir, defs = FLAVORS[fl]
+        os.makedirs(objdir, exist_ok=True)
+        objs, dirty = [], False
+        for src in sources():
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            if force or _stale(obj, [src] + headers):
+                dirty = True
+                cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+                procs.append((fl + ":" + os.path.basename(src), subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        plan.append((lib, objs, dirty))
     failed = False
-    for src, p in procs:
+    for name, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write("---- %s\n%s\n" % (os.path.basename(src), out))
+            sys.stderr.write("---- %s\n%s\n" % (name, out))
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-        subprocess.check_call(cmd)
+    for lib, objs, dirty in plan:
+        if force or dirty or _stale(lib, objs):
+            # -Bsymbolic: calls between the library's own extern "C" entry points bind inside the library (two flavours coexist)
+            subprocess.check_call([_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-Bsymbolic"])
     return LIB
 
 

@@ -11,10 +11,10 @@ namespace dtlr {
 
 template <typename T> __device__ __forceinline__ float ldf_(const T* p);
 template <> __device__ __forceinline__ float ldf_<float>(const float* p) { return *p; }
-template <> __device__ __forceinline__ float ldf_<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldf_<op16_t>(const op16_t* p) { return op16_to_f32(*p); }
 template <typename T> __device__ __forceinline__ void stf_(T* p, float v);
 template <> __device__ __forceinline__ void stf_<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void stf_<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stf_<op16_t>(op16_t* p, float v) { *p = f32_to_op16(v); }
 
 constexpr int ATT_DH = 32;
 constexpr int ATT_QT = 128;   // queries per CTA (one per thread)
@@ -90,7 +90,7 @@ constexpr int FA_MT = 1;        // 16-query m-tiles per warp (MT = 2 with 8 warp
 constexpr int FA_PITCH = 40;   // bf16 elements per smem row (32 + 8 padding)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." DTLR_OP16_PTX "." DTLR_OP16_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -105,7 +105,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    op16x2_t t = op16_pack2(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -118,12 +118,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // interleaves the P.V MMAs with the exponentials of the same block -- the four warps per scheduler cover the rest.
 template <int MT, bool PIPE>
 __global__ void __launch_bounds__(FA_WARPS * 32)
-mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off, const __nv_bfloat16* __restrict__ v, int ld_v,
-                      __nv_bfloat16* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
+mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const op16_t* __restrict__ v, int ld_v,
+                      op16_t* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
     extern __shared__ __align__(16) unsigned char fa_smem[];
     const int KP = (Q + 63) / 64 * 64;                        // keys padded to the 64-key sweep
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(fa_smem);
-    __nv_bfloat16* Vs = Ks + (size_t)KP * FA_PITCH;
+    op16_t* Ks = reinterpret_cast<op16_t*>(fa_smem);
+    op16_t* Vs = Ks + (size_t)KP * FA_PITCH;
     const int b = blockIdx.z, h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t row0 = (size_t)b * Q;
@@ -159,8 +159,8 @@ mha_flash_bf16_kernel(const __nv_bfloat16* __restrict__ qk, int ld_qk, int k_off
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const int r_lo = min(q0 + mt * 16 + g, Q - 1), r_hi = min(q0 + mt * 16 + g + 8, Q - 1);
-            const __nv_bfloat16* qlo = qk + (row0 + r_lo) * ld_qk + h * 32;
-            const __nv_bfloat16* qhi = qk + (row0 + r_hi) * ld_qk + h * 32;
+            const op16_t* qlo = qk + (row0 + r_lo) * ld_qk + h * 32;
+            const op16_t* qhi = qk + (row0 + r_hi) * ld_qk + h * 32;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 qa[mt][ks][0] = *reinterpret_cast<const uint32_t*>(qlo + ks * 16 + 2 * t);
@@ -308,7 +308,7 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DTLR_F32)
         mha_simt_kernel<float><<<grid, ATT_QT, 0, st>>>((const float*)qk, ld_qk, k_off, (const float*)v, ld_v, attn_mask, (float*)out, ld_o, Q, scale);
-    else if (dtype == DTLR_BF16 && !attn_mask && (ld_qk % 8) == 0 && (ld_v % 8) == 0 && (k_off % 8) == 0 && (ld_o % 2) == 0 &&
+    else if (dtype == DTLR_OP16 && !attn_mask && (ld_qk % 8) == 0 && (ld_v % 8) == 0 && (k_off % 8) == 0 && (ld_o % 2) == 0 &&
              (size_t)((Q + 63) / 64 * 64) * FA_PITCH * 2 * 2 <= (size_t)max_smem_optin()) {
         const int KP = (Q + 63) / 64 * 64;
         const size_t smem = (size_t)KP * FA_PITCH * 2 * 2;
@@ -319,10 +319,10 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
         auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, true> : mha_flash_bf16_kernel<FA_MT, false>;   // flag 16384: QK-pipelined variant (A/B)
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(FA_WARPS * 32), smem, st, (const __nv_bfloat16*)qk, ld_qk, k_off,
-                                   (const __nv_bfloat16*)v, ld_v, (__nv_bfloat16*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
-    } else if (dtype == DTLR_BF16)
-        mha_simt_kernel<__nv_bfloat16><<<grid, ATT_QT, 0, st>>>((const __nv_bfloat16*)qk, ld_qk, k_off, (const __nv_bfloat16*)v, ld_v, attn_mask, (__nv_bfloat16*)out, ld_o, Q, scale);
+        DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(FA_WARPS * 32), smem, st, (const op16_t*)qk, ld_qk, k_off,
+                                   (const op16_t*)v, ld_v, (op16_t*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
+    } else if (dtype == DTLR_OP16)
+        mha_simt_kernel<op16_t><<<grid, ATT_QT, 0, st>>>((const op16_t*)qk, ld_qk, k_off, (const op16_t*)v, ld_v, attn_mask, (op16_t*)out, ld_o, Q, scale);
     else { set_error("mha: unsupported dtype"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

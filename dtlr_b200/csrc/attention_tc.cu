@@ -28,13 +28,13 @@ constexpr int AT_XCH_FLOATS = 2 * 2 * 128 * 4;     // {max, sum} x tile parity x
 constexpr int AT_SMEM_TOTAL = AT_SMEM_K + AT_SMEM_V + AT_SMEM_Q + 2 * AT_SMEM_P + AT_XCH_FLOATS * 4 + 1024 + 512;
 
 // V^T pre-pass: vt[(b*H + h)*32 + d][key] = v[b*Q + key][h*32 + d], zero for key >= Q
-__global__ void vt_transpose_kernel(const __nv_bfloat16* __restrict__ v, int ld_v, __nv_bfloat16* __restrict__ vt, int Q, int H) {
-    __shared__ __nv_bfloat16 tile[32][34];
+__global__ void vt_transpose_kernel(const op16_t* __restrict__ v, int ld_v, op16_t* __restrict__ vt, int Q, int H) {
+    __shared__ op16_t tile[32][34];
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8 threads
     for (int r = ty; r < 32; r += 8) {
         const int key = k0 + r;
-        tile[r][tx] = key < Q ? v[((size_t)b * Q + key) * ld_v + h * 32 + tx] : __float2bfloat16(0.f);
+        tile[r][tx] = key < Q ? v[((size_t)b * Q + key) * ld_v + h * 32 + tx] : f32_to_op16(0.f);
     }
     __syncthreads();
     for (int d = ty; d < 32; d += 8)
@@ -43,7 +43,7 @@ __global__ void vt_transpose_kernel(const __nv_bfloat16* __restrict__ v, int ld_
 
 __global__ void __launch_bounds__(576, 1)
 mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ld_o, int Q, int H, int k_off,
+                   const __grid_constant__ CUtensorMap tmV, op16_t* __restrict__ out, int ld_o, int Q, int H, int k_off,
                    float scale_log2) {
     extern __shared__ unsigned char at_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)at_raw + 1023) & ~(uintptr_t)1023);
@@ -105,8 +105,8 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_S = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(AT_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_O = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(kv_full, 0);
         uint32_t si = 0;     // S-buffer use counter (buffer si & 1, phase (si >> 1) & 1)
         uint32_t pi = 0;     // P-buffer use counter
@@ -226,8 +226,8 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 o;
-                        __nv_bfloat162 a0 = __floats2bfloat162_rn(p[j], p[j + 1]), a1 = __floats2bfloat162_rn(p[j + 2], p[j + 3]);
-                        __nv_bfloat162 a2 = __floats2bfloat162_rn(p[j + 4], p[j + 5]), a3 = __floats2bfloat162_rn(p[j + 6], p[j + 7]);
+                        op16x2_t a0 = op16_pack2(p[j], p[j + 1]), a1 = op16_pack2(p[j + 2], p[j + 3]);
+                        op16x2_t a2 = op16_pack2(p[j + 4], p[j + 5]), a3 = op16_pack2(p[j + 6], p[j + 7]);
                         o.x = *reinterpret_cast<uint32_t*>(&a0); o.y = *reinterpret_cast<uint32_t*>(&a1);
                         o.z = *reinterpret_cast<uint32_t*>(&a2); o.w = *reinterpret_cast<uint32_t*>(&a3);
                         const int chunk = (part & 1) * 4 + j / 8;                // 16-byte chunk inside the 128-byte row
@@ -252,11 +252,11 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
             if (q < Q) {
-                __nv_bfloat16* op = out + (size_t)(row_base + q) * ld_o + h * 32 + part * 8;
+                op16_t* op = out + (size_t)(row_base + q) * ld_o + h * 32 + part * 8;
                 uint32_t w[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(oacc[2 * j]) * inv, __uint_as_float(oacc[2 * j + 1]) * inv);
+                    op16x2_t t0 = op16_pack2(__uint_as_float(oacc[2 * j]) * inv, __uint_as_float(oacc[2 * j + 1]) * inv);
                     w[j] = *reinterpret_cast<uint32_t*>(&t0);
                 }
                 *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -297,7 +297,7 @@ static_assert(A2_SMEM_TOTAL <= 232448, "attention kernel shared memory exceeds 2
 
 __global__ void __launch_bounds__(576, 1)
 mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-               __nv_bfloat16* __restrict__ out, int ld_o, int Q, int H, int k_off, float scale_log2) {
+               op16_t* __restrict__ out, int ld_o, int Q, int H, int k_off, float scale_log2) {
     extern __shared__ unsigned char at_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)at_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sK = smem;
@@ -356,8 +356,8 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t IDESC_O = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_S = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t IDESC_O = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(kv_full, 0);
         for (int sl = 0; sl < my_tiles; ++sl) mbar_wait(&q_full[sl], 0);
         tcgen05_fence_after();
@@ -472,7 +472,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[j * 8 + 2 * i]) * inv, __uint_as_float(o[j * 8 + 2 * i + 1]) * inv);
+                        op16x2_t t0 = op16_pack2(__uint_as_float(o[j * 8 + 2 * i]) * inv, __uint_as_float(o[j * 8 + 2 * i + 1]) * inv);
                         w[i] = *reinterpret_cast<uint32_t*>(&t0);
                     }
                     op[j] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -503,7 +503,7 @@ extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void
     if (B == 0) return DTLR_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 tg(AT_KPAD / 32, heads, B);
-    vt_transpose_kernel<<<tg, 256, 0, st>>>((const __nv_bfloat16*)v, ld_v, (__nv_bfloat16*)vt_scratch, Q, heads);
+    vt_transpose_kernel<<<tg, 256, 0, st>>>((const op16_t*)v, ld_v, (op16_t*)vt_scratch, Q, heads);
     DTLR_CHECK_LAUNCH();
     CUtensorMap tmQ, tmK, tmV;
     int rc;
@@ -526,10 +526,10 @@ extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void
             configured2 = true;
         }
         grid.x = (n_qtiles + A2_SLOTS - 1) / A2_SLOTS;
-        DTLR_CHECK_CUDA(launch_pdl(mha_tc2_kernel, grid, dim3(576), A2_SMEM_TOTAL, st, tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2));
+        DTLR_CHECK_CUDA(launch_pdl(mha_tc2_kernel, grid, dim3(576), A2_SMEM_TOTAL, st, tmQ, tmK, tmV, (op16_t*)out, ld_o, Q, heads, k_off, scale_log2));
         return DTLR_OK;
     }
-    mha_tcgen05_kernel<<<grid, 576, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_o, Q, heads, k_off, scale_log2);
+    mha_tcgen05_kernel<<<grid, 576, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (op16_t*)out, ld_o, Q, heads, k_off, scale_log2);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

@@ -8,6 +8,43 @@
 
 #include "../../include/dtlr_b200.h"
 
+// ---- the 16-bit operand / activation type of the throughput mode.  The library is built twice from the same sources:
+//   libdtlr_b200.so      op16 = bf16 (8 significand bits)   -- torch.bfloat16 models
+//   libdtlr_b200_f16.so  op16 = fp16 (11 significand bits)  -- torch.float16 models: same tcgen05 / HMMA rate and the same bytes, 8x
+//                        finer operand rounding (the error budget of the benchmarked mode)
+// Everything that depends on the flavour is below: the types, the conversions (incl. the bit tricks bf16 allows), the PTX type
+// token of mma.sync, the tcgen05 instruction-descriptor format bits, the TMA element type and the C-ABI dtype code.
+#ifdef DTLR_BUILD_F16
+#include <cuda_fp16.h>
+namespace dtlr {
+typedef __half op16_t;
+typedef __half2 op16x2_t;
+#define DTLR_OP16_PTX "f16"
+#define DTLR_TMAP_OP16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+constexpr uint32_t OP16_IDESC_AB = 0u;                                  // A format [7,10) = F16, B format [10,13) = F16
+constexpr int DTLR_OP16 = DTLR_F16;
+__device__ __forceinline__ float op16_lo_f32(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float op16_hi_f32(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+__device__ __forceinline__ op16x2_t op16_pack2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+__device__ __forceinline__ float op16_to_f32(op16_t v) { return __half2float(v); }
+__device__ __forceinline__ op16_t f32_to_op16(float v) { return __float2half_rn(v); }
+}  // namespace dtlr
+#else
+namespace dtlr {
+typedef __nv_bfloat16 op16_t;
+typedef __nv_bfloat162 op16x2_t;
+#define DTLR_OP16_PTX "bf16"
+#define DTLR_TMAP_OP16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+constexpr uint32_t OP16_IDESC_AB = (1u << 7) | (1u << 10);              // A format [7,10) = BF16, B format [10,13) = BF16
+constexpr int DTLR_OP16 = DTLR_BF16;
+__device__ __forceinline__ float op16_lo_f32(uint32_t u) { return __uint_as_float(u << 16); }           // bf16 = the top half of fp32
+__device__ __forceinline__ float op16_hi_f32(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ op16x2_t op16_pack2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ float op16_to_f32(op16_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ op16_t f32_to_op16(float v) { return __float2bfloat16_rn(v); }
+}  // namespace dtlr
+#endif
+
 namespace dtlr {
 
 void set_error(const char* fmt, ...);

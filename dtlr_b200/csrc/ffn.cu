@@ -60,7 +60,7 @@ struct FfnSmem {
 static_assert(FfnSmem::TOTAL <= 232448, "FFN kernel shared memory exceeds 227 KB");
 
 __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    op16x2_t t = op16_pack2(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -177,7 +177,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else if (warp == 1) {
         // ===== MMA issuer: G1(j) one chunk ahead of G2(j-1).  Hacc[b] is rewritten by G1(j+2) only after G2(j), its last reader, in
         //       issue order; E1(j) finished with it before h_full(j), which G2(j) waited for
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
+        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
         uint32_t it = 0, g = 0, t = 0;
         for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t, g += NJ) {
             const uint32_t xb = t & 1;
@@ -305,11 +305,11 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bp[kk * 8 + 2 * i] + __uint_as_float(rw[i] << 16);
-                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bp[kk * 8 + 2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
+                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bp[kk * 8 + 2 * i] + op16_lo_f32(rw[i]);
+                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bp[kk * 8 + 2 * i + 1] + op16_hi_f32(rw[i]);
                             const uint32_t pk = ff_pack_bf16x2(x0, x1);
                             xp[cb * 32 + k * 4 + i] = pk;
-                            const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
+                            const float y0 = op16_lo_f32(pk), y1 = op16_hi_f32(pk);
                             sum += y0 + y1;
                             sq = fmaf(y0, y0, sq);
                             sq = fmaf(y1, y1, sq);
@@ -335,8 +335,8 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t pk = xp[cb * 32 + k * 4 + i];
                         const int c = c0 + k * 8 + 2 * i;
-                        o[i] = ff_pack_bf16x2((__uint_as_float(pk << 16) - mean) * rstd * gamma_s[c] + beta_s[c],
-                                              (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
+                        o[i] = ff_pack_bf16x2((op16_lo_f32(pk) - mean) * rstd * gamma_s[c] + beta_s[c],
+                                              (op16_hi_f32(pk) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
                     }
                     *reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }

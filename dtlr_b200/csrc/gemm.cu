@@ -18,23 +18,23 @@
 namespace dtlr {
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    op16x2_t t = op16_pack2(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 template <typename OutT> __device__ __forceinline__ void unpack_chunk(const uint4& d, float* f);
 template <> __device__ __forceinline__ void unpack_chunk<float>(const uint4& d, float* f) {
     f[0] = __uint_as_float(d.x); f[1] = __uint_as_float(d.y); f[2] = __uint_as_float(d.z); f[3] = __uint_as_float(d.w);
 }
-template <> __device__ __forceinline__ void unpack_chunk<__nv_bfloat16>(const uint4& d, float* f) {
+template <> __device__ __forceinline__ void unpack_chunk<op16_t>(const uint4& d, float* f) {
     const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    for (int i = 0; i < 4; ++i) { f[2 * i] = op16_lo_f32(w[i]); f[2 * i + 1] = op16_hi_f32(w[i]); }
 }
 template <typename OutT> __device__ __forceinline__ uint4 pack_chunk(const float* f);
 template <> __device__ __forceinline__ uint4 pack_chunk<float>(const float* f) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
 }
-template <> __device__ __forceinline__ uint4 pack_chunk<__nv_bfloat16>(const float* f) {
+template <> __device__ __forceinline__ uint4 pack_chunk<op16_t>(const float* f) {
     return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
@@ -87,7 +87,7 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + LN_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void ln_load_blk(uint4 (&dst)[8], const __nv_bfloat16* src, const int ld, const int cb, const int m0,
+__device__ __forceinline__ void ln_load_blk(uint4 (&dst)[8], const op16_t* src, const int ld, const int cb, const int m0,
                                             const int qd, const int lane, const int M) {
 #pragma unroll
     for (int itx = 0; itx < 8; ++itx) {
@@ -109,8 +109,8 @@ __device__ __forceinline__ void ln_stage_blk(const uint4 (&src)[8], unsigned cha
     __syncwarp();
 }
 __device__ __forceinline__ uint32_t ln_norm_pair(const uint32_t pk, const float mean, const float rstd, const float* g, const float* b) {
-    const float y0 = (__uint_as_float(pk << 16) - mean) * rstd * g[0] + b[0];
-    const float y1 = (__uint_as_float(pk & 0xffff0000u) - mean) * rstd * g[1] + b[1];
+    const float y0 = (op16_lo_f32(pk) - mean) * rstd * g[0] + b[0];
+    const float y1 = (op16_hi_f32(pk) - mean) * rstd * g[1] + b[1];
     return pack_bf16x2(y0, y1);
 }
 
@@ -124,8 +124,8 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpi& e, const CUtenso
                                                  const uint32_t tmem_acc, uint64_t* full_bar, const uint32_t full_phase, uint64_t* empty_bar,
                                                  unsigned char* buf0, const float* bias_s, const float* gamma_s, const float* beta_s,
                                                  float* stat_s, const int qd, const int hsel, const int lane) {
-    const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(e.residual);
-    const __nv_bfloat16* add2 = reinterpret_cast<const __nv_bfloat16*>(e.ln.add2);
+    const op16_t* resp = reinterpret_cast<const op16_t*>(e.residual);
+    const op16_t* add2 = reinterpret_cast<const op16_t*>(e.ln.add2);
     const int row = qd * 32 + lane;
     const uint32_t swz = (uint32_t)(lane & 7);
     unsigned char* srow = buf0 + lane * 128;
@@ -162,11 +162,11 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpi& e, const CUtenso
                 const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bv[2 * i] + __uint_as_float(rw[i] << 16);
-                    const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bv[2 * i + 1] + __uint_as_float(rw[i] & 0xffff0000u);
+                    const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bv[2 * i] + op16_lo_f32(rw[i]);
+                    const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bv[2 * i + 1] + op16_hi_f32(rw[i]);
                     const uint32_t pk = pack_bf16x2(x0, x1);
                     xp[blk * 32 + k * 4 + i] = pk;
-                    const float y0 = __uint_as_float(pk << 16), y1 = __uint_as_float(pk & 0xffff0000u);
+                    const float y0 = op16_lo_f32(pk), y1 = op16_hi_f32(pk);
                     sum += y0 + y1;
                     sq = fmaf(y0, y0, sq);
                     sq = fmaf(y1, y1, sq);
@@ -213,8 +213,8 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpi& e, const CUtenso
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const uint32_t y = ln_norm_pair(xp[blk * 32 + k * 4 + i], mean, rstd, gamma_s + cb * 64 + k * 8 + 2 * i, beta_s + cb * 64 + k * 8 + 2 * i);
-                    z[i] = pack_bf16x2(__uint_as_float(y << 16) + __uint_as_float(tw[i] << 16),
-                                       __uint_as_float(y & 0xffff0000u) + __uint_as_float(tw[i] & 0xffff0000u));
+                    z[i] = pack_bf16x2(op16_lo_f32(y) + op16_lo_f32(tw[i]),
+                                       op16_hi_f32(y) + op16_hi_f32(tw[i]));
                 }
                 *p = make_uint4(z[0], z[1], z[2], z[3]);
             }
@@ -313,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ===== MMA issuer =====
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
         // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -534,7 +534,7 @@ struct WsSmem {
 };
 
 template <typename OutT, int CB> struct TmemBlock;
-template <> struct TmemBlock<__nv_bfloat16, 64> {
+template <> struct TmemBlock<op16_t, 64> {
     static __device__ __forceinline__ void load(uint32_t taddr, uint32_t (&r)[64]) { tmem_ld64(taddr, r); }
 };
 template <> struct TmemBlock<float, 32> {
@@ -617,7 +617,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
         uint32_t it = 0, tcount = 0;
         for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -833,7 +833,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, DTLR_TMAP_OP16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -854,7 +854,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int 
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)GEMM_BK, (cuuint32_t)seg_w, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, DTLR_TMAP_OP16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -876,7 +876,7 @@ static int make_tmap_out(CUtensorMap* map, const void* base, int rows, int cols,
     cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(OutT)};
     cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(OutT)), 32};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, sizeof(OutT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(map, sizeof(OutT) == 2 ? DTLR_TMAP_OP16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -987,28 +987,28 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
         DTLR_CHECK_LAUNCH();
         return DTLR_OK;
     }
-    DTLR_CHECK_ARG(in_dtype == DTLR_BF16, "gemm: operands must be f32 or bf16");
-    DTLR_CHECK_ARG(out_dtype == DTLR_BF16 || out_dtype == DTLR_F32, "gemm: output must be bf16 or f32");
+    DTLR_CHECK_ARG(in_dtype == DTLR_OP16, "gemm: operands must be f32 or bf16");
+    DTLR_CHECK_ARG(out_dtype == DTLR_OP16 || out_dtype == DTLR_F32, "gemm: output must be bf16 or f32");
     DTLR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0,
                    "gemm: bf16 operands need 16-byte aligned rows (lda=%d ldw=%d)", lda, ldw);
     CUtensorMap ta, tb;
     int rc = DTLR_OK;
-    if (out_dtype == DTLR_BF16 ? ws_try<__nv_bfloat16>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
-    if (out_dtype == DTLR_BF16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8)) {
+    if (out_dtype == DTLR_OP16 ? ws_try<op16_t>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
+    if (out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
         // N = 256 layers become one tile per row block
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
         if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 256))) return rc;
-        return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, st);
+        return launch_tc<256, 3, op16_t>(ta, tb, e, st);
     }
     if (N > 64) {
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
         if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 128))) return rc;
-        return out_dtype == DTLR_BF16 ? launch_tc<128, 4, __nv_bfloat16>(ta, tb, e, st) : launch_tc<128, 4, float>(ta, tb, e, st);
+        return out_dtype == DTLR_OP16 ? launch_tc<128, 4, op16_t>(ta, tb, e, st) : launch_tc<128, 4, float>(ta, tb, e, st);
     }
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 64))) return rc;
-    return out_dtype == DTLR_BF16 ? launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st) : launch_tc<64, 6, float>(ta, tb, e, st);
+    return out_dtype == DTLR_OP16 ? launch_tc<64, 6, op16_t>(ta, tb, e, st) : launch_tc<64, 6, float>(ta, tb, e, st);
 }
 
 // y = LayerNorm_256(A.W^T + bias (+ residual)) * gamma + beta, optional y2 = y + add2 -- the Linear -> (+residual) -> LayerNorm
@@ -1028,15 +1028,15 @@ extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, cons
     GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
     // K <= 256: weight-stationary kernel; otherwise the tile kernel -- both end in ln_epilogue_tile (TMA stores)
     if (K <= 256 && (long long)((M + GEMM_BM - 1) / GEMM_BM) >= 2ll * sm_count() && !(g_debug_flags & 32))
-        return launch_ws<256, __nv_bfloat16, false, true>(A, lda, W, ldw, e, (cudaStream_t)stream);
+        return launch_ws<256, op16_t, false, true>(A, lda, W, ldw, e, (cudaStream_t)stream);
     CUtensorMap ta, tb, tc, tc2;
     int rc;
     if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 256))) return rc;
-    if ((rc = make_tmap_out<__nv_bfloat16>(&tc, Y, M, N, ldy))) return rc;
+    if ((rc = make_tmap_out<op16_t>(&tc, Y, M, N, ldy))) return rc;
     tc2 = tc;
-    if (Y2 && (rc = make_tmap_out<__nv_bfloat16>(&tc2, Y2, M, N, ld2))) return rc;
-    return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, (cudaStream_t)stream, &tc, &tc2);
+    if (Y2 && (rc = make_tmap_out<op16_t>(&tc2, Y2, M, N, ld2))) return rc;
+    return launch_tc<256, 3, op16_t>(ta, tb, e, (cudaStream_t)stream, &tc, &tc2);
 }
 
 // Convolution (stride 1, "same" padding) on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel above: no im2col
@@ -1050,7 +1050,7 @@ extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias,
     DTLR_CHECK_ARG(seg_w >= 8 && (128 % seg_w) == 0 && (W % seg_w) == 0,
                    "conv2d_nhwc: output width %d cannot be tiled into 128-pixel row segments (use im2col + gemm)", W);
     DTLR_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv2d_nhwc: operands must be 16-byte aligned");
-    DTLR_CHECK_ARG(out_dtype == DTLR_BF16, "conv2d_nhwc: bf16 output only");
+    DTLR_CHECK_ARG(out_dtype == DTLR_OP16, "conv2d_nhwc: bf16 output only");
     const int M = B * H * W, K = KH * KW * C;
     if (M == 0) return DTLR_OK;
     GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w}, g_debug_flags};
@@ -1060,12 +1060,12 @@ extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias,
     cudaStream_t st = (cudaStream_t)stream;
     if ((Cout % 256) == 0) {
         if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 256))) return rc;
-        return launch_tc<256, 3, __nv_bfloat16>(ta, tb, e, st);
+        return launch_tc<256, 3, op16_t>(ta, tb, e, st);
     }
     if (Cout > 64) {
         if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 128))) return rc;
-        return launch_tc<128, 4, __nv_bfloat16>(ta, tb, e, st);
+        return launch_tc<128, 4, op16_t>(ta, tb, e, st);
     }
     if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 64))) return rc;
-    return launch_tc<64, 6, __nv_bfloat16>(ta, tb, e, st);
+    return launch_tc<64, 6, op16_t>(ta, tb, e, st);
 }

@@ -57,19 +57,19 @@ struct Vec16<float> {
     }
 };
 template <>
-struct Vec16<__nv_bfloat16> {
+struct Vec16<op16_t> {
     static constexpr int NP = 4;
     __device__ static __forceinline__ void load(const void* p, unsigned long long (&v)[4]) {
         const uint4 t = *reinterpret_cast<const uint4*>(p);
-        v[0] = pack2u(t.x << 16, t.x & 0xffff0000u);
-        v[1] = pack2u(t.y << 16, t.y & 0xffff0000u);
-        v[2] = pack2u(t.z << 16, t.z & 0xffff0000u);
-        v[3] = pack2u(t.w << 16, t.w & 0xffff0000u);
+        v[0] = pack2u(__float_as_uint(op16_lo_f32(t.x)), __float_as_uint(op16_hi_f32(t.x)));
+        v[1] = pack2u(__float_as_uint(op16_lo_f32(t.y)), __float_as_uint(op16_hi_f32(t.y)));
+        v[2] = pack2u(__float_as_uint(op16_lo_f32(t.z)), __float_as_uint(op16_hi_f32(t.z)));
+        v[3] = pack2u(__float_as_uint(op16_lo_f32(t.w)), __float_as_uint(op16_hi_f32(t.w)));
     }
 };
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_out(op16_t* p, float v) { *p = f32_to_op16(v); }
 
 // FUSED: the kernel also does the MSDeformAttn prologue (reference ops/modules/ms_deform_attn.py:98-108): `loc` points at
 // the fp32 projection rows [B*Lq, fz.ld] (M*L*P*2 offsets, then M*L*P attention logits); the softmax over the L*P
@@ -141,10 +141,10 @@ msda_fwd_d32_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
         if (FUSED) {
             const size_t row = (size_t)b * Lq + q;
             if (fz.proj_bf16) {
-                const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(loc) + row * fz.ld;
+                const op16_t* pr = reinterpret_cast<const op16_t*>(loc) + row * fz.ld;
                 const uint32_t o2 = *reinterpret_cast<const uint32_t*>(pr + ((size_t)m * LP + pt) * 2);
-                pf_a = make_float2(__uint_as_float(o2 << 16), __uint_as_float(o2 & 0xffff0000u));
-                pf_b = __bfloat162float(pr[(size_t)M * LP * 2 + (size_t)m * LP + pt]);
+                pf_a = make_float2(op16_lo_f32(o2), op16_hi_f32(o2));
+                pf_b = op16_to_f32(pr[(size_t)M * LP * 2 + (size_t)m * LP + pt]);
             } else {
                 const float* pr = loc + row * fz.ld;
                 pf_a = *reinterpret_cast<const float2*>(pr + ((size_t)m * LP + pt) * 2);
@@ -343,7 +343,7 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const uint32_t s
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 __device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." DTLR_OP16_PTX "." DTLR_OP16_PTX ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -353,7 +353,7 @@ __device__ __forceinline__ uint32_t prmt(const uint32_t a, const uint32_t b, con
     return d;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2_rn(const float lo, const float hi) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    op16x2_t t = op16_pack2(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -361,8 +361,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(const float lo, const float h
 // MODE 1: fused prologue, fp32 projection rows;  MODE 2: fused prologue, bf16 projection rows
 template <int MODE>
 __global__ void __launch_bounds__(MMA_NW * 32, 2)
-msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restrict__ loc_or_proj, const float* __restrict__ attn,
-                    __nv_bfloat16* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
+msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ loc_or_proj, const float* __restrict__ attn,
+                    op16_t* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
                     const int q_per_cta, const FusedArgs fz, const int vld) {
     constexpr int P = 4, LP = 16;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -381,13 +381,13 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
     // fetched by cp.async with consecutive lanes on consecutive 16-byte chunks (6-11 lines per instruction instead of 32) into the
     // warp's table region (112-byte pitch: conflict-free 16-byte reads by lane = query); the first batch flies behind the slab copy
     auto stage_raw = [&](int qb) {
-        const __nv_bfloat16* pbase = reinterpret_cast<const __nv_bfloat16*>(loc_or_proj);
+        const op16_t* pbase = reinterpret_cast<const op16_t*>(loc_or_proj);
 #pragma unroll
         for (int u = 0; u < 6; ++u) {
             const int c = lane + 32 * u;
             const int qi = c / 6, part = c - qi * 6;
             const int q = min(qb + qi, wq1 - 1);
-            const __nv_bfloat16* src = pbase + ((size_t)b * Lq + q) * fz.ld + (part < 4 ? m * (LP * 2) + part * 8 : M * (LP * 2) + m * LP + (part - 4) * 8);
+            const op16_t* src = pbase + ((size_t)b * Lq + q) * fz.ld + (part < 4 ? m * (LP * 2) + part * 8 : M * (LP * 2) + m * LP + (part - 4) * 8);
             cp_async16(tab + qi * MMA_RAW_PITCH + part * 16, src);
         }
         cp_async_commit();
@@ -461,14 +461,14 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
                     const uint4 t = raw[k];
                     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { ox[4 * k + i] = __uint_as_float(w4[i] << 16); oy[4 * k + i] = __uint_as_float(w4[i] & 0xffff0000u); }
+                    for (int i = 0; i < 4; ++i) { ox[4 * k + i] = op16_lo_f32(w4[i]); oy[4 * k + i] = op16_hi_f32(w4[i]); }
                 }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const uint4 t = raw[4 + k];
                     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { aw[8 * k + 2 * i] = __uint_as_float(w4[i] << 16); aw[8 * k + 2 * i + 1] = __uint_as_float(w4[i] & 0xffff0000u); }
+                    for (int i = 0; i < 4; ++i) { aw[8 * k + 2 * i] = op16_lo_f32(w4[i]); aw[8 * k + 2 * i + 1] = op16_hi_f32(w4[i]); }
                 }
             }
             float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -580,9 +580,9 @@ msda_fwd_mma_kernel(const __nv_bfloat16* __restrict__ value, const void* __restr
             r0 += __shfl_down_sync(0xffffffffu, r2, 2);
             r1 += __shfl_down_sync(0xffffffffu, r3, 2);
             if (j < 2) {
-                __nv_bfloat16* o = out + ((size_t)((size_t)b * Lq + qb + jq) * M + m) * 32 + g;
-                o[(2 * j) * 8] = __float2bfloat16_rn(r0);
-                o[(2 * j + 1) * 8] = __float2bfloat16_rn(r1);
+                op16_t* o = out + ((size_t)((size_t)b * Lq + qb + jq) * M + m) * 32 + g;
+                o[(2 * j) * 8] = f32_to_op16(r0);
+                o[(2 * j + 1) * 8] = f32_to_op16(r1);
             }
         }
         __syncwarp();                // the table is rewritten by the next batch
@@ -949,7 +949,7 @@ static int launch_fwd_mma(const void* value, const void* loc, const void* attn, 
     auto k = mode == 0 ? msda_fwd_mma_kernel<0> : (mode == 1 ? msda_fwd_mma_kernel<1> : msda_fwd_mma_kernel<2>);
     DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(qsplit, M, B), block(MMA_NW * 32);
-    DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const __nv_bfloat16*)value, loc, (const float*)attn, (__nv_bfloat16*)out, lv, S, M, Lq, q_per_cta, fz, vld));
+    DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const op16_t*)value, loc, (const float*)attn, (op16_t*)out, lv, S, M, Lq, q_per_cta, fz, vld));
     return DTLR_OK;
 }
 
@@ -987,9 +987,9 @@ extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const
     DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward: B or M exceeds 65535");
     cudaStream_t st = (cudaStream_t)stream;
     const bool aligned = (((uintptr_t)value | (uintptr_t)loc) & 15) == 0;
-    if (D == 32 && aligned && (dtype == DTLR_F32 || dtype == DTLR_BF16)) {
+    if (D == 32 && aligned && (dtype == DTLR_F32 || dtype == DTLR_OP16)) {
         return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, loc, attn, out, lv, B, S, M, Lq, P, st)
-                                 : launch_fwd_d32<__nv_bfloat16>(value, loc, attn, out, lv, B, S, M, Lq, P, st);
+                                 : launch_fwd_d32<op16_t>(value, loc, attn, out, lv, B, S, M, Lq, P, st);
     }
     const long long warps = (long long)B * Lq * M;
     const int threads = 256;
@@ -1012,9 +1012,9 @@ extern "C" int dtlr_msda_forward(const void* value, const int64_t* shapes, const
 extern "C" int dtlr_msda_forward_fused(const void* value, int value_ld, const int64_t* shapes, const int64_t* lsi, const void* proj,
                                        int ld_proj, int proj_dtype, const float* ref, int ref_dim, const float* valid_ratios,
                                        void* out, int B, int S, int M, int D, int L, int Lq, int P, int dtype, void* stream) {
-    DTLR_CHECK_ARG(proj_dtype == DTLR_F32 || proj_dtype == DTLR_BF16, "msda_forward_fused: projection must be f32 or bf16");
+    DTLR_CHECK_ARG(proj_dtype == DTLR_F32 || proj_dtype == DTLR_OP16, "msda_forward_fused: projection must be f32 or bf16");
     DTLR_CHECK_ARG(B >= 0 && Lq >= 0 && S > 0 && M > 0 && P > 0, "msda_forward_fused: bad sizes");
-    DTLR_CHECK_ARG(D == 32 && (dtype == DTLR_F32 || dtype == DTLR_BF16), "msda_forward_fused: needs D=32, f32 or bf16 values");
+    DTLR_CHECK_ARG(D == 32 && (dtype == DTLR_F32 || dtype == DTLR_OP16), "msda_forward_fused: needs D=32, f32 or bf16 values");
     DTLR_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "msda_forward_fused: reference points must have 2 or 4 coordinates");
     DTLR_CHECK_ARG(shapes && lsi, "msda_forward_fused: null shapes");
     DTLR_CHECK_ARG(ld_proj >= M * L * P * 3 && (ld_proj % 2) == 0, "msda_forward_fused: projection row pitch %d too small/odd", ld_proj);
@@ -1026,10 +1026,10 @@ extern "C" int dtlr_msda_forward_fused(const void* value, int value_ld, const in
     DTLR_CHECK_ARG((((uintptr_t)value | (uintptr_t)proj) & 15) == 0, "msda_forward_fused: value/proj must be 16-byte aligned");
     DTLR_CHECK_ARG((long long)B <= 65535 && (long long)M <= 65535, "msda_forward_fused: B or M exceeds 65535");
     DTLR_CHECK_ARG(value_ld >= M * 32 && (value_ld % 8) == 0, "msda_forward_fused: value row pitch %d too small / unaligned", value_ld);
-    const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim, proj_dtype == DTLR_BF16 ? 1 : 0};
+    const FusedArgs fz{ref, valid_ratios, ld_proj, ref_dim, proj_dtype == DTLR_OP16 ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == DTLR_F32 ? launch_fwd_d32<float>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz, value_ld)
-                             : launch_fwd_d32<__nv_bfloat16>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz, value_ld);
+                             : launch_fwd_d32<op16_t>(value, (const float*)proj, nullptr, out, lv, B, S, M, Lq, P, st, &fz, value_ld);
 }
 
 extern "C" int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,

@@ -21,10 +21,10 @@ namespace dtlr {
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
-template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ldf<op16_t>(const op16_t* p) { return op16_to_f32(*p); }
 template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void stf<op16_t>(op16_t* p, float v) { *p = f32_to_op16(v); }
 
 // 8 consecutive channels <-> 8 floats
 template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
@@ -32,21 +32,21 @@ template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+template <> __device__ __forceinline__ void ld8<op16_t>(const op16_t* p, float (&v)[8]) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    for (int i = 0; i < 4; ++i) { v[2 * i] = op16_lo_f32(w[i]); v[2 * i + 1] = op16_hi_f32(w[i]); }
 }
 template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+template <> __device__ __forceinline__ void st8<op16_t>(op16_t* p, const float (&v)[8]) {
     uint4 o;
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    op16x2_t a = op16_pack2(v[0], v[1]), b = op16_pack2(v[2], v[3]);
+    op16x2_t c = op16_pack2(v[4], v[5]), d = op16_pack2(v[6], v[7]);
     o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
     o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
     *reinterpret_cast<uint4*>(p) = o;
@@ -454,7 +454,7 @@ __global__ void sine_embed_kernel(const float* __restrict__ ref, const float* __
 // sin/cos are accurate to ~1e-6 absolute -- far below the bf16 output rounding; 1/dim_t from one ex2 per thread, 32 rows per
 // block, (sin, cos) pairs stored as one packed 4-byte word (256-byte coalesced rows per component).
 __global__ void __launch_bounds__(256)
-sine_embed_bf16_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, __nv_bfloat16* __restrict__ out,
+sine_embed_bf16_kernel(const float* __restrict__ ref, const float* __restrict__ valid_ratios, op16_t* __restrict__ out,
                        const long long rows, const int Q, const int L) {
     pdl_launch_dependents();
     pdl_wait();
@@ -475,7 +475,7 @@ sine_embed_bf16_kernel(const float* __restrict__ ref, const float* __restrict__ 
         for (int part = 0; part < 4; ++part) {
             float sn, cs;
             __sincosf(comp[part] * w, &sn, &cs);
-            __nv_bfloat162 t = __floats2bfloat162_rn(sn, cs);
+            op16x2_t t = op16_pack2(sn, cs);
             o[part * 64] = *reinterpret_cast<uint32_t*>(&t);
         }
     }
@@ -597,7 +597,7 @@ using namespace dtlr;
 
 #define DISPATCH_T(dtype, ...)                                          \
     if ((dtype) == DTLR_F32) { using T = float; __VA_ARGS__ }           \
-    else if ((dtype) == DTLR_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+    else if ((dtype) == DTLR_OP16) { using T = op16_t; __VA_ARGS__ } \
     else { set_error("unsupported dtype %d", (int)(dtype)); return DTLR_ERR_INVALID; }
 
 // Stem patches for the tensor-core path: fp32 NCHW network input (C = 3) -> bf16 rows [B*Ho*Wo, ldo] in (kh, kw, c) order for a
@@ -609,12 +609,12 @@ constexpr int SIC_SEG = 128;                     // output pixels per CTA
 constexpr int SIC_COLS = 2 * SIC_SEG + 5;        // input columns touched
 constexpr int SIC_ROW = SIC_COLS * 3 + 1;        // bf16 elements per staged input row (column-major pixels, channel fastest)
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, const int H, const int W, const int Ho,
+stem_im2col_kernel(const float* __restrict__ x, op16_t* __restrict__ out, const int H, const int W, const int Ho,
                    const int Wo, const int ldo) {
     pdl_launch_dependents();
     pdl_wait();
     // tile[kh][col * 3 + c]: for a fixed kh the 21 values (kw, c) of output pixel p are the 21 CONSECUTIVE elements from 6 * p
-    __shared__ __nv_bfloat16 tile[7 * SIC_ROW];
+    __shared__ op16_t tile[7 * SIC_ROW];
     const int ox0 = blockIdx.x * SIC_SEG, oy = blockIdx.y, b = blockIdx.z;
     const int ix0 = 2 * ox0 - 3;
     constexpr int NLD = (21 * SIC_COLS + 255) / 256;                   // all loads of a thread in flight together
@@ -633,7 +633,7 @@ stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
         const int i = threadIdx.x + u * 256;
         const int rowi = i / SIC_COLS, col = i - rowi * SIC_COLS;
         const int kh = rowi / 3, c = rowi - kh * 3;
-        if (i < 21 * SIC_COLS) tile[kh * SIC_ROW + col * 3 + c] = __float2bfloat16_rn(v[u]);
+        if (i < 21 * SIC_COLS) tile[kh * SIC_ROW + col * 3 + c] = f32_to_op16(v[u]);
     }
     __syncthreads();
     const int nchunk = ldo / 8;                                        // 16-byte chunks per output row
@@ -670,10 +670,10 @@ extern "C" int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C,
     if (!nchw_input && in_dtype == out_dtype && C % 8 == 0 && ldo == KH * KW * C) {
         const long long t8 = total / 8;
         DISPATCH_T(in_dtype, DTLR_LAUNCH((im2col_vec8_kernel<T>), grid_for(t8, 256), 256, 0, st, (const T*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo);)
-    } else if (nchw_input && in_dtype == DTLR_F32 && out_dtype == DTLR_BF16 && C == 3 && KH == 7 && KW == 7 && stride == 2 && pad == 3 &&
+    } else if (nchw_input && in_dtype == DTLR_F32 && out_dtype == DTLR_OP16 && C == 3 && KH == 7 && KW == 7 && stride == 2 && pad == 3 &&
                (ldo % 8) == 0 && (((uintptr_t)out) & 15) == 0 && B <= 65535 && Ho <= 65535) {
         dim3 grid((Wo + SIC_SEG - 1) / SIC_SEG, Ho, B);
-        DTLR_LAUNCH((stem_im2col_kernel), grid, 256, 0, st, (const float*)x, (__nv_bfloat16*)out, H, W, Ho, Wo, ldo);
+        DTLR_LAUNCH((stem_im2col_kernel), grid, 256, 0, st, (const float*)x, (op16_t*)out, H, W, Ho, Wo, ldo);
     } else if (nchw_input && in_dtype == DTLR_F32) {
         DISPATCH_T(out_dtype, DTLR_LAUNCH((im2col_kernel<float, T, true>), grid_for(total, 256), 256, 0, st, (const float*)x, (T*)out, B, H, W, C, KH, KW, stride, pad, Ho, Wo, ldo);)
     } else if (!nchw_input && in_dtype == out_dtype) {
@@ -697,9 +697,9 @@ extern "C" int dtlr_stem_conv(const float* x, const float* w, const float* bias,
     if (out_dtype == DTLR_F32) {
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DTLR_LAUNCH((stem_conv7x7_kernel<float>), grid, 256, smem, st, x, w, bias, (float*)out, H, W, Ho, Wo);
-    } else if (out_dtype == DTLR_BF16) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DTLR_LAUNCH((stem_conv7x7_kernel<__nv_bfloat16>), grid, 256, smem, st, x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo);
+    } else if (out_dtype == DTLR_OP16) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7x7_kernel<op16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DTLR_LAUNCH((stem_conv7x7_kernel<op16_t>), grid, 256, smem, st, x, w, bias, (op16_t*)out, H, W, Ho, Wo);
     } else { set_error("stem_conv: unsupported dtype"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -813,8 +813,8 @@ extern "C" int dtlr_rowmax(const float* x, int ld, int N, float* out, long long 
 extern "C" int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int B, int Q, int L, int out_dtype, void* stream) {
     const long long rows = (long long)B * Q;
     if (rows == 0) return DTLR_OK;
-    if (out_dtype == DTLR_BF16 && !(g_debug_flags & 128)) {
-        DTLR_LAUNCH((sine_embed_bf16_kernel), (unsigned)((rows + 31) / 32), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (__nv_bfloat16*)out, rows, Q, L);
+    if (out_dtype == DTLR_OP16 && !(g_debug_flags & 128)) {
+        DTLR_LAUNCH((sine_embed_bf16_kernel), (unsigned)((rows + 31) / 32), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (op16_t*)out, rows, Q, L);
         return DTLR_OK;
     }
     DISPATCH_T(out_dtype, DTLR_LAUNCH((sine_embed_kernel<T>), (unsigned)((rows + 3) / 4), 256, 0, (cudaStream_t)stream, ref, valid_ratios, (T*)out, B, Q, L);)
@@ -840,14 +840,14 @@ extern "C" int dtlr_sigmoid(const float* x, float* out, long long n, void* strea
 extern "C" int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype, void* stream) {
     if (n == 0) return DTLR_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_dtype == DTLR_F32 && out_dtype == DTLR_BF16)
-        DTLR_LAUNCH((cast_kernel<float, __nv_bfloat16>), grid_for(n, 256), 256, 0, st, (const float*)x, (__nv_bfloat16*)out, n);
-    else if (in_dtype == DTLR_BF16 && out_dtype == DTLR_F32)
-        DTLR_LAUNCH((cast_kernel<__nv_bfloat16, float>), grid_for(n, 256), 256, 0, st, (const __nv_bfloat16*)x, (float*)out, n);
+    if (in_dtype == DTLR_F32 && out_dtype == DTLR_OP16)
+        DTLR_LAUNCH((cast_kernel<float, op16_t>), grid_for(n, 256), 256, 0, st, (const float*)x, (op16_t*)out, n);
+    else if (in_dtype == DTLR_OP16 && out_dtype == DTLR_F32)
+        DTLR_LAUNCH((cast_kernel<op16_t, float>), grid_for(n, 256), 256, 0, st, (const op16_t*)x, (float*)out, n);
     else if (in_dtype == out_dtype && in_dtype == DTLR_F32)
         DTLR_LAUNCH((cast_kernel<float, float>), grid_for(n, 256), 256, 0, st, (const float*)x, (float*)out, n);
-    else if (in_dtype == out_dtype && in_dtype == DTLR_BF16)
-        DTLR_LAUNCH((cast_kernel<__nv_bfloat16, __nv_bfloat16>), grid_for(n, 256), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, n);
+    else if (in_dtype == out_dtype && in_dtype == DTLR_OP16)
+        DTLR_LAUNCH((cast_kernel<op16_t, op16_t>), grid_for(n, 256), 256, 0, st, (const op16_t*)x, (op16_t*)out, n);
     else { set_error("cast: unsupported dtypes"); return DTLR_ERR_INVALID; }
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

@@ -287,9 +287,9 @@ extern "C" int dtlr_select_gather(const long long* idx, const float* coord, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DTLR_F32)
         select_gather_kernel<float><<<grid, 256, 0, st>>>(idx, coord, prop, (const float*)mem, refpoint, initbox, (float*)tgt, S, K, d, rows);
-    else if (dtype == DTLR_BF16)
-        select_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(idx, coord, prop, (const __nv_bfloat16*)mem, refpoint, initbox,
-                                                                  (__nv_bfloat16*)tgt, S, K, d, rows);
+    else if (dtype == DTLR_OP16)
+        select_gather_kernel<op16_t><<<grid, 256, 0, st>>>(idx, coord, prop, (const op16_t*)mem, refpoint, initbox,
+                                                                  (op16_t*)tgt, S, K, d, rows);
     else
         DTLR_CHECK_ARG(false, "select_gather: unsupported dtype %d", dtype);
     DTLR_CHECK_LAUNCH();

@@ -217,7 +217,7 @@ static inline int make_tmap_2d_bf16(CUtensorMap* map, const void* base, long lon
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = enc(map, DTLR_TMAP_OP16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for %lldx%d ld=%lld box %dx%d", (int)r, rows, cols, ld, box_rows, box_cols);

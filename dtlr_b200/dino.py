@@ -183,7 +183,7 @@ class DINO(nn.Module):
             nn.init.constant_(proj[0].bias, 0)
 
         # ---- dtlr_b200 execution controls (not part of the reference surface)
-        self.compute_dtype = torch.float32      # torch.float32 = parity mode, torch.bfloat16 = throughput mode
+        self.compute_dtype = torch.float32      # torch.float32 = parity mode; torch.float16 / torch.bfloat16 = throughput mode (16-bit tensor-core operands)
         self.use_engine = True                  # eval + no_grad -> fused inference engine
         self.engine_outputs = "all"             # "all": every reference dict key; "final": last-layer logits/boxes only
         self.use_cuda_graph = False             # replay one captured CUDA graph per input shape (static output buffers)

@@ -72,7 +72,7 @@ class InferenceEngine:
         P["stem_direct"] = ((body.conv1.weight.detach().float() * sc.float().view(-1, 1, 1, 1)).permute(2, 3, 1, 0).contiguous(),
                             sb.detach().float().contiguous())          # [kh][kw][cin][cout] fp32, bias
         # bf16 throughput mode: the stem runs on the tensor cores as patches (shared-memory staged im2col) x [64, 152] GEMM
-        P["stem_gemm"] = _fold_conv_bn(body.conv1, body.bn1, dtype) if dtype == torch.bfloat16 else None
+        P["stem_gemm"] = _fold_conv_bn(body.conv1, body.bn1, dtype) if dtype in ops.HALF else None
         blocks = []
         for li in range(1, 5):
             for blk in getattr(body, "layer%d" % li):
@@ -256,6 +256,7 @@ class InferenceEngine:
         dev = x.device
         x = x.float().contiguous()
         B, _, H, W = x.shape
+        L.set_flavor(T)               # bf16 / fp16 model: the library built for that 16-bit type (fp32 parity mode: either)
         P = self.packed(T, dev)
         d = tr.d_model
         st = stages

@@ -66,7 +66,7 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     B, S, M, D = value.shape
     # value may be a column block of a wider matrix (several layers' value projections from one GEMM): pixel pitch = stride(1)
     assert value.stride(3) == 1 and value.stride(2) == D and value.stride(0) == S * value.stride(1), "unsupported value layout"
-    assert proj.dtype in (torch.float32, torch.bfloat16) and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
+    assert proj.dtype in (torch.float32, torch.bfloat16, torch.float16) and ref.dtype == torch.float32 and valid_ratios.dtype == torch.float32
     assert ref.is_contiguous() and valid_ratios.is_contiguous() and proj.stride(1) == 1
     if out is None:
         out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)

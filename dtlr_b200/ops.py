@@ -4,6 +4,8 @@ import torch
 
 from . import _lib as L
 
+HALF = (torch.bfloat16, torch.float16)      # the two 16-bit flavours of the throughput mode (one library each, _lib.set_flavor)
+
 
 def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
@@ -28,10 +30,11 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
         L.TIMER("gemm", 2.0 * M * N * K, a.device, True)
         L.GEMM_BYTES += (M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
                          + (M * N * residual.element_size() if residual is not None else 0))
+    in_code, out_code = L.dtype_code(a), L.dtype_code(out)     # (16-bit tensors select the library flavour before L.lib())
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
-                               M, N, K, L.dtype_code(a), L.dtype_code(out), int(relu), L.stream_ptr(a.device))
+                               M, N, K, in_code, out_code, int(relu), L.stream_ptr(a.device))
     L.check(rc, "dtlr_gemm")
     if L.TIMER is not None:
         L.TIMER("gemm", 0.0, a.device, False)
@@ -70,13 +73,13 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
 
 def conv2d_nhwc_supported(x, H, W, C, k, stride):
     seg = 128 if W >= 128 else W
-    return (x.dtype == torch.bfloat16 and stride == 1 and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and W % seg == 0)
+    return (x.dtype in HALF and stride == 1 and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and W % seg == 0)
 
 
 def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None):
     """stride-1 'same' conv as implicit GEMM: x bf16 [B*H*W, C] NHWC, w bf16 [Cout, k*k*C] -> bf16 [B*H*W, Cout]"""
     Cout = w.shape[0]
-    out = torch.empty((B * H * W, Cout), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B * H * W, Cout), dtype=x.dtype, device=x.device)
     _call("dtlr_conv2d_nhwc", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(relu),
           L.dtype_code(out), _st(x))
     return out
@@ -202,8 +205,8 @@ ATTN_IMPL = _os.environ.get("DTLR_ATTN", "hmma")
 
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
     out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
-    if ATTN_IMPL == "tc" and v.dtype == torch.bfloat16 and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:
-        vt = torch.empty((B * heads * 32, 1024), dtype=torch.bfloat16, device=v.device)
+    if ATTN_IMPL == "tc" and v.dtype in HALF and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:
+        vt = torch.empty((B * heads * 32, 1024), dtype=v.dtype, device=v.device)
         rc = L.lib().dtlr_mha_tcgen05(_p(qk), qk.stride(0), k_off, _p(v), v.stride(0), _p(vt), _p(out), out.stride(0), B, Q, heads,
                                       head_dim, _st(v))
         if rc == 0:
@@ -345,11 +348,12 @@ def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5, out=None, ou
     """bf16 only, N = 256: y = LN(a @ w.T + bias (+ residual)); optional y2 = y + add2.  One tcgen05 kernel."""
     import ctypes
     M, K = a.shape
-    assert w.shape[0] == 256 and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
-    y = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if out is None else out
+    assert w.shape[0] == 256 and a.dtype in HALF and w.dtype == a.dtype
+    L.set_flavor(a.dtype)
+    y = torch.empty((M, 256), dtype=a.dtype, device=a.device) if out is None else out
     y2 = None
     if add2 is not None:
-        y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=a.device) if out2 is None else out2
+        y2 = torch.empty((M, 256), dtype=a.dtype, device=a.device) if out2 is None else out2
     _call("dtlr_gemm_ln", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
           _p(gamma), _p(beta), ctypes.c_float(eps), _p(y), y.stride(0), _p(add2), _p(y2), add2.stride(0) if add2 is not None else 0,
           M, K, _st(a))
@@ -360,12 +364,12 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
     """Linear (+residual) + LayerNorm [+ second output]: fused tcgen05 kernel in bf16 mode, GEMM + LN kernels otherwise."""
     # fused only when the main loop is long enough to hide the two-pass LN epilogue (measured on B200: K = 256 layers are
     # epilogue-bound and run faster as GEMM + add_layernorm256; K = 2048 (FFN linear2) gains)
-    if a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] >= LN_FUSE_MIN_K:
+    if a.dtype in HALF and w.shape[0] == 256 and a.shape[1] >= LN_FUSE_MIN_K:
         return gemm_ln(a, w, bias, residual, gamma, beta, add2)
     # K <= 256 on many rows: the weight-stationary kernel normalises in its TMA-store epilogue.  Measured (B200, M = 58368,
     # CUDA-graph timing): 23 us without a residual vs 16 + 17 us un-fused; WITH a residual the 128 KB resident weight slice
     # leaves no room to prefetch residual tiles by TMA and the LSU transposition makes it 34 us vs 33 us -> un-fused then.
-    if (LN_FUSE_WS and a.dtype == torch.bfloat16 and w.shape[0] == 256 and a.shape[1] <= 256 and residual is None and add2 is None
+    if (LN_FUSE_WS and a.dtype in HALF and w.shape[0] == 256 and a.shape[1] <= 256 and residual is None and add2 is None
             and a.shape[0] >= 2 * 148 * 128):
         return gemm_ln(a, w, bias, None, gamma, beta, None)
     x = gemm(a, w, bias, residual=residual)
@@ -386,9 +390,10 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     import ctypes
     M = x.shape[0]
     hid = w1.shape[0]
-    if (FFN_FUSED and x.dtype == torch.bfloat16 and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
+    if (FFN_FUSED and x.dtype in HALF and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
             and x.stride(1) == 1 and x.stride(0) % 8 == 0):
-        y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((M, 256), dtype=x.dtype, device=x.device)
+        L.set_flavor(x.dtype)
         if L.TIMER is not None:     # bench.py: algorithmic FLOPs of the block = the two contractions, 2*M*hid*256 each
             L.TIMER("ffn", 4.0 * M * hid * 256, x.device, True)
         _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
@@ -399,10 +404,10 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     # experiment (opt-in): un-fused in row chunks that keep the hidden activation inside the 126 MB L2 (one reused buffer that
     # linear2 reads back before it is evicted).  The saved HBM traffic does not pay for the extra launches, the smaller M per
     # launch and the repeated weight-slice loads
-    if (FFN_CHUNK_ROWS > 0 and x.dtype == torch.bfloat16 and w2.shape[0] == 256 and hid >= LN_FUSE_MIN_K and M > FFN_CHUNK_ROWS):
-        y = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device)
-        y2 = torch.empty((M, 256), dtype=torch.bfloat16, device=x.device) if add2 is not None else None
-        hbuf = torch.empty((FFN_CHUNK_ROWS, hid), dtype=torch.bfloat16, device=x.device)
+    if (FFN_CHUNK_ROWS > 0 and x.dtype in HALF and w2.shape[0] == 256 and hid >= LN_FUSE_MIN_K and M > FFN_CHUNK_ROWS):
+        y = torch.empty((M, 256), dtype=x.dtype, device=x.device)
+        y2 = torch.empty((M, 256), dtype=x.dtype, device=x.device) if add2 is not None else None
+        hbuf = torch.empty((FFN_CHUNK_ROWS, hid), dtype=x.dtype, device=x.device)
         for r0 in range(0, M, FFN_CHUNK_ROWS):
             r1 = min(M, r0 + FFN_CHUNK_ROWS)
             h = gemm(x[r0:r1], w1, b1, relu=1, out=hbuf[:r1 - r0])

@@ -24,7 +24,9 @@ typedef enum {
     DTLR_ERR_UNSUPPORTED = 3  /* valid request that this build has no kernel for                 */
 } dtlr_status;
 
-typedef enum { DTLR_F32 = 0, DTLR_BF16 = 1, DTLR_F64 = 2 } dtlr_dtype;
+/* DTLR_BF16 is served by libdtlr_b200.so, DTLR_F16 by libdtlr_b200_f16.so (the same sources built with fp16 as the 16-bit type);
+ * each library rejects the other 16-bit code. */
+typedef enum { DTLR_F32 = 0, DTLR_BF16 = 1, DTLR_F64 = 2, DTLR_F16 = 3 } dtlr_dtype;
 
 /* library identification: (major<<16 | minor<<8 | patch), and the SM architecture the kernels were built for */
 int dtlr_version(void);

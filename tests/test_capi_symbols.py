@@ -14,15 +14,16 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol():
     from dtlr_b200 import build
-    path = build.build_library()
-    lib = ctypes.CDLL(path)
+    build.build_library()
     syms = declared_symbols()
-    assert "dtlr_msda_forward" in syms and "dtlr_msda_backward" in syms
-    for s in syms:
-        assert hasattr(lib, s), "missing export %s" % s
-    lib.dtlr_version.restype = ctypes.c_int
-    assert lib.dtlr_version() >= 0x000100
-    assert lib.dtlr_built_for_sm() == 100
+    assert "dtlr_msda_forward" in syms and "dtlr_msda_backward" in syms and "dtlr_ctc_loss" in syms and "dtlr_postprocess" in syms
+    for path in (build.LIB, build.LIB_F16):          # the two 16-bit flavours of the same sources (bf16 | fp16 operands)
+        lib = ctypes.CDLL(path)
+        for s in syms:
+            assert hasattr(lib, s), "%s: missing export %s" % (os.path.basename(path), s)
+        lib.dtlr_version.restype = ctypes.c_int
+        assert lib.dtlr_version() >= 0x000100
+        assert lib.dtlr_built_for_sm() == 100
 
 
 def test_ops_fail_loudly_without_cuda():

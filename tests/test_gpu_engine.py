@@ -106,16 +106,17 @@ def _edit_distance(a, b):
     return prev[-1]
 
 
-def test_bf16_throughput_mode_agreement():
-    """bf16 operands / activations, fp32 accumulation.  Not a 1e-3 mode (bf16 eps is 4e-3): with the reference ranking
-    forced the documented bounds are 5e-2 relative-to-max on logits / boxes and >= 90 % of queries with the same
-    blank/character decision (measured on B200: 2.2e-2 / 1.7e-2 / 94.8 %); the character error rate of the decoded
-    lines against the fp32 reference decode is printed (random weights put many decisions and cx orderings at
+@pytest.mark.parametrize("dt,bound,min_agree", [(torch.float16, 1e-2, 0.97), (torch.bfloat16, 5e-2, 0.90)])
+def test_throughput_mode_agreement_with_reference_fixture(dt, bound, min_agree):
+    """16-bit operands / activations, fp32 accumulation, against the reference-generated fixture.  Not 1e-3 modes: with
+    the reference ranking forced the documented bounds are, relative-to-max on logits / boxes, 1e-2 for fp16 (measured ~3e-3) and
+    5e-2 for bf16 (measured on B200: 2.2e-2 / 1.7e-2, 94.8 % of queries with the same blank/character decision); the character error
+    rate of the decoded lines against the fp32 reference decode is printed (random weights put many decisions and cx orderings at
     near-ties, so this is a pessimistic stand-in for trained weights)."""
     fx = fixture("dino_A_b2")
     model, crit, _ = build_model(900)
     x = synth.synth_images(2, 40, 1024, seed=0).cuda()
-    out, st = run_engine(model, x, force=torch.from_numpy(fx["topk_idx"]).long(), dtype=torch.bfloat16)
+    out, st = run_engine(model, x, force=torch.from_numpy(fx["topk_idx"]).long(), dtype=dt)
     e_log, e_box = rel(out["pred_logits"], fx["pred_logits"]), rel(out["pred_boxes"], fx["pred_boxes"])
     ref_logits, ref_boxes = torch.from_numpy(fx["pred_logits"]), torch.from_numpy(fx["pred_boxes"])
 
@@ -133,9 +134,9 @@ def test_bf16_throughput_mode_agreement():
     seq = dino.convert_output_to_pred(dino.ctc_view(out["pred_logits"].float(), out["pred_boxes"].float()))
     seq_ref = dino.convert_output_to_pred(dino.ctc_view(ref_logits, ref_boxes))
     cer = sum(_edit_distance(a, b) for a, b in zip(seq, seq_ref)) / max(1, sum(len(b) for b in seq_ref))
-    print("bf16: logits %.3e boxes %.3e memory %.3e per-query decision agreement %.4f CER-vs-fp32-decode %.4f" % (
-        e_log, e_box, rel(st["memory"][:, ::8, ::4].float(), fx["memory_s"]), agree, cer))
-    assert e_log < 5e-2 and e_box < 5e-2 and agree >= 0.90
+    print("%s: logits %.3e boxes %.3e memory %.3e per-query decision agreement %.4f CER-vs-fp32-decode %.4f" % (
+        dt, e_log, e_box, rel(st["memory"][:, ::8, ::4].float(), fx["memory_s"]), agree, cer))
+    assert e_log < bound and e_box < bound and agree >= min_agree
 
 
 def _oracle_run(model, x, cfg_kw):
@@ -218,12 +219,13 @@ def test_bench_shape_fp32_vs_oracle(bench_shape):
         model.use_cuda_graph = False
 
 
-def test_bench_shape_throughput_mode_vs_oracle(bench_shape):
-    """the mode bench.py times (16-bit tensor-core operands, fp32 accumulation), at the bench shape, against the oracle with the
-    reference ranking forced.  The bound asserted here is the mode's documented error budget (regenerated by
-    tests/precision_sim.py): no single-pass 16-bit operand format reaches 1e-3 through ~100 dependent layers."""
+@pytest.mark.parametrize("dt,MODE_TOL,min_agree", [(torch.float16, 1e-2, 0.97), (torch.bfloat16, 5e-2, 0.9)])
+def test_bench_shape_throughput_mode_vs_oracle(bench_shape, dt, MODE_TOL, min_agree):
+    """the modes bench.py times (16-bit tensor-core operands and activations, fp32 accumulation), at the bench shape, against the
+    oracle with the reference ranking forced.  The bounds asserted here are the modes' documented error budgets (DESIGN.md 2.1,
+    regenerated by tests/precision_sim.py): no single-pass 16-bit operand format reaches 1e-3 through ~100 dependent layers; fp16
+    (11 significand bits, the default throughput mode) is ~6x closer than bf16 (8 bits) at the same speed."""
     model, x, ref, rst = bench_shape
-    dt = torch.bfloat16
     out, st = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=dt)
     errs = {}
     for a, b, name in ((st["feats"][2][0], rst["feats"][2], "feat_c5"), (st["memory"], rst["memory"], "memory"),
@@ -238,7 +240,7 @@ def test_bench_shape_throughput_mode_vs_oracle(bench_shape):
     print("B=64 %s per-stage rel-to-max: %s ; per-query blank/label decisions equal %.4f; of the %d decided by >= 0.1 in the reference, %d differ" % (
         dt, " ".join("%s %.2e" % kv for kv in errs.items()), agree_all, int(dec.sum()), bad))
     assert errs["logits"] < MODE_TOL and errs["boxes"] < MODE_TOL
-    assert bad <= 0.005 * int(dec.sum()) and agree_all >= 0.9
+    assert bad <= 0.005 * int(dec.sum()) and agree_all >= min_agree
 
 
 def test_hwdb_wide_head_engine_vs_oracle():
@@ -264,8 +266,11 @@ def test_hwdb_wide_head_engine_vs_oracle():
     n, dec, bad = _decidable_frames(ref, out, 2e-6, 1e-5)
     print("HWDB fp32 frames %d decidable (cx gap >= 2e-6, top-2 gap >= 1e-5) %d mismatching-decidable %d" % (n, dec, bad))
     assert bad == 0
-    out16, _ = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=torch.bfloat16)
-    assert rel(out16["pred_logits"].float(), ref["pred_logits"]) < 5e-2
+    for dt, tol in ((torch.bfloat16, 5e-2), (torch.float16, 1e-2)):
+        out16, _ = run_engine(model, x.cuda(), force=rst["topk_idx"], dtype=dt)
+        e = rel(out16["pred_logits"].float(), ref["pred_logits"])
+        print("HWDB %s logits rel-to-max %.2e" % (dt, e))
+        assert e < tol
 
 
 def test_host_pipeline_matches_direct_calls():
