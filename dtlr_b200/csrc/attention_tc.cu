@@ -435,9 +435,14 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const float p0 = ex2_approx(fmaf(__uint_as_float(a[j]), scale_log2, -mxs)), p1 = ex2_approx(fmaf(__uint_as_float(a[j + 1]), scale_log2, -mxs));
                     const float p2 = ex2_approx(fmaf(__uint_as_float(a[j + 2]), scale_log2, -mxs)), p3 = ex2_approx(fmaf(__uint_as_float(a[j + 3]), scale_log2, -mxs));
                     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+#ifdef DTLR_BUILD_F16
+                    { const op16x2_t t0 = op16_pack2(p0, p1), t1 = op16_pack2(p2, p3);
+                      a[j / 2] = *reinterpret_cast<const uint32_t*>(&t0); a[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&t1); }
+#else
                     // round to nearest bf16 on the integer pipe (p >= 0, finite): + 0x8000, keep the high halves
                     a[j / 2] = __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632);
                     a[j / 2 + 1] = __byte_perm(__float_as_uint(p2) + 0x8000u, __float_as_uint(p3) + 0x8000u, 0x7632);
+#endif
                 }
                 l = l * alpha + ((s0 + s1) + (s2 + s3));
                 m = m_new;

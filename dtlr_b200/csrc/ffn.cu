@@ -46,6 +46,11 @@ struct FfnArgs {
     float eps;
     int M, HID;
     int dbg;              // probes (dtlr_debug_flags): 256 no E1 work, 512 no G1 MMAs, 1024 no G2 MMAs, 2048 no final epilogue work
+    // HEAD variant (3-layer MLP head with a 4-wide last layer, reference models/dino/utils.py:110-122 as used for bbox_embed):
+    const float* w3;      // [4][256] fp32 (nn.Linear weight of the last layer)
+    const float* b3;      // [4]
+    const float* ref;     // [M][4] reference boxes in (0,1) or null: out = sigmoid(delta + inverse_sigmoid(ref)) (box refinement)
+    float* out4;          // [M][4]
 };
 
 struct FfnSmem {
@@ -67,7 +72,11 @@ __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
 // CL: launched as clusters of two CTAs that stream the SAME weight chunks: each ring stage is fetched from L2 once by one CTA
 // of the pair (alternating) and multicast into both, halving the L2 -> SM traffic (912 MB per call otherwise); a stage is refilled
 // once BOTH tensor cores have released it (multicast tcgen05.commit on both CTAs' w_empty barriers)
-template <bool CL>
+// HEAD: the same two chained contractions with HID = 256 as the first two layers of a 3-layer MLP head -- Y = relu(W2 relu(W1 X + b1)
+// + b2) stays in registers, the 4-wide last layer is 4 dot products per row on the FMA pipe, followed (optionally) by the box
+// refinement sigmoid(delta + inverse_sigmoid(ref)) of reference deformable_transformer.py:734-738 / dino.py:343-345: one kernel reads
+// X once and writes 16 bytes per row, instead of three GEMMs (two 256-wide intermediates through HBM) + an elementwise kernel.
+template <bool CL, bool HEAD>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
@@ -122,10 +131,16 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
     for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + i);
+    float* w3_s = b1_s + FF_D;                       // HEAD: [256 columns][4 outputs] behind the 256 b1 entries (HID == 256)
     for (int i = threadIdx.x; i < FF_D; i += 320) {
         b2_s[i] = __ldg(a.b2 + i);
-        gamma_s[i] = __ldg(a.gamma + i);
-        beta_s[i] = __ldg(a.beta + i);
+        if (!HEAD) {
+            gamma_s[i] = __ldg(a.gamma + i);
+            beta_s[i] = __ldg(a.beta + i);
+        } else {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) w3_s[i * 4 + n] = __ldg(a.w3 + n * FF_D + i);
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -274,6 +289,56 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // ---- final: Yacc + b2 + X -> LayerNorm -> bf16 over the X tile -> TMA store
             const uint32_t xb = t & 1;
             unsigned char* xt = xs + xb * FfnSmem::XS;
+            if (HEAD) {
+                // ---- final (HEAD): relu(Yacc + b2) . W3^T + b3 [-> box refinement] -> 16 bytes per row
+                mbar_wait(y_full, t & 1);                    // every MMA of the tile is complete: X is no longer read either
+                tcgen05_fence_after();
+                if (lane == 0) mbar_arrive(&x_free[xb]);
+                float o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t acc[32];
+                        tmem_ld32(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64 + hf * 32), acc);
+                        if (cb == 1 && hf == 1) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(y_free);
+                        }
+                        const int c0 = hsel * 128 + cb * 64 + hf * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float v = fmaxf(__uint_as_float(acc[i]) + b2_s[c0 + i], 0.f);
+                            const float4 w = *reinterpret_cast<const float4*>(w3_s + (c0 + i) * 4);
+                            o4[0] = fmaf(v, w.x, o4[0]); o4[1] = fmaf(v, w.y, o4[1]);
+                            o4[2] = fmaf(v, w.z, o4[2]); o4[3] = fmaf(v, w.w, o4[3]);
+                        }
+                    }
+                }
+                if (hsel == 1) *reinterpret_cast<float4*>(stat_s + row * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // the two column halves of a row meet
+                if (hsel == 0) {
+                    const float4 p = *reinterpret_cast<const float4*>(stat_s + row * 4);
+                    const long long rg = (long long)mt * FF_BM + row;
+                    if (rg < a.M) {
+                        float z[4] = {o4[0] + p.x + __ldg(a.b3), o4[1] + p.y + __ldg(a.b3 + 1), o4[2] + p.z + __ldg(a.b3 + 2), o4[3] + p.w + __ldg(a.b3 + 3)};
+                        if (a.ref) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.ref) + rg);
+                            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                            for (int n = 0; n < 4; ++n) {
+                                const float x = fminf(fmaxf(rr[n], 0.f), 1.f);
+                                const float x1 = fmaxf(x, 1e-3f), x2 = fmaxf(1.f - x, 1e-3f);
+                                z[n] = 1.f / (1.f + expf(-(z[n] + logf(x1 / x2))));
+                            }
+                        }
+                        reinterpret_cast<float4*>(a.out4)[rg] = make_float4(z[0], z[1], z[2], z[3]);
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // partials consumed before the next tile overwrites them
+                continue;
+            }
             mbar_wait(&x_full[xb], (t >> 1) & 1);
             mbar_wait(y_full, t & 1);
             tcgen05_fence_after();
@@ -389,12 +454,12 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
-    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags};
+    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags, nullptr, nullptr, nullptr, nullptr};
     // CTA pairs with multicast weights: measured identical (129.0 vs 130.1 us): halving the L2 reads does not help because the
     // limit of the weight stream is the ~51 B/clk at which one SM's shared memory is filled (loads alone: 63 us with or without
     // multicast, with 5 or 9 ring stages).  Kept (dtlr_debug_flags(4096)) as the validated base of the cta_group::2 version, which
@@ -402,10 +467,39 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((g_debug_flags & 4096) && num_m >= 2) {
         int grid = num_m < sm_count() ? num_m : sm_count();
         grid &= ~1;
-        DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_tcgen05_kernel<true>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
+        DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_tcgen05_kernel<true, false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
         return DTLR_OK;
     }
     const int grid = num_m < sm_count() ? num_m : sm_count();
-    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    return DTLR_OK;
+}
+
+// 3-layer MLP head with a 4-wide last layer (reference models/dino/utils.py:110-122: bbox_embed / enc_out_bbox_embed, 256 -> 256 ->
+// 256 -> 4) fused with the box refinement that follows it (deformable_transformer.py:734-738, dino.py:343-345) -- the HEAD variant of
+// the FFN kernel above.  X [M,256] 16-bit, W1 / W2 [256,256] 16-bit, b1 / b2 fp32, W3 [4,256] fp32, b3 [4] fp32, ref [M,4] fp32 or
+// NULL (NULL: out4 = the raw deltas), out4 [M,4] fp32.
+extern "C" int dtlr_mlp_head(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                             const float* b2, const float* W3, const float* b3, const float* ref, float* out4, int M, void* stream) {
+    DTLR_CHECK_ARG(M >= 0, "mlp_head: bad sizes");
+    if (M == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(X && W1 && b1 && W2 && b2 && W3 && b3 && out4, "mlp_head: null pointer");
+    DTLR_CHECK_ARG(ldx >= FF_D && ldw1 >= FF_D && ldw2 >= FF_D, "mlp_head: leading dimension too small");
+    DTLR_CHECK_ARG((ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 && ((((uintptr_t)X | (uintptr_t)W1 | (uintptr_t)W2)) & 15) == 0 &&
+                   ((((uintptr_t)out4 | (uintptr_t)ref)) & 15) == 0, "mlp_head: operands need 16-byte aligned rows");
+    CUtensorMap tx, tw1, tw2;
+    int rc;
+    if ((rc = ffn_tmap(&tx, X, M, FF_D, ldx, FF_BM))) return rc;
+    if ((rc = ffn_tmap(&tw1, W1, FF_D, FF_D, ldw1, 128))) return rc;
+    if ((rc = ffn_tmap(&tw2, W2, FF_D, FF_D, ldw2, 128))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        configured = true;
+    }
+    const int num_m = (M + FF_BM - 1) / FF_BM;
+    const FfnArgs a{b1, b2, nullptr, nullptr, 0.f, M, FF_D, g_debug_flags, W3, b3, ref, out4};
+    const int grid = num_m < sm_count() ? num_m : sm_count();
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, true>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, tx, a));
     return DTLR_OK;
 }

@@ -124,6 +124,9 @@ class InferenceEngine:
         P["dec_norm"] = ln(tr.decoder.norm)
         P["rph"] = [_lin(l, dtype) for l in tr.decoder.ref_point_head.layers]
         P["bbox"] = [[_lin(l, dtype) for l in be.layers] for be in m.bbox_embed]
+        # fp32 copies of the 4-wide last layers for the fused MLP-head kernel (dtlr_mlp_head)
+        P["bbox_w3"] = [be.layers[-1].weight.detach().float().contiguous() for be in m.bbox_embed]
+        P["enc_bbox_w3"] = tr.enc_out_bbox_embed.layers[-1].weight.detach().float().contiguous()
         P["cls"] = [_lin(ce, dtype) for ce in m.class_embed]
         P["tgt_embed"] = tr.tgt_embed.weight.detach().to(dtype).contiguous()
         self._packed, self._key = P, key
@@ -143,6 +146,16 @@ class InferenceEngine:
         h = ops.gemm(x, *layers[0], relu=1)
         h = ops.gemm(h, *layers[1], relu=1)
         return ops.gemm(h, *layers[2], out_dtype=torch.float32 if out_f32_last else None)
+
+    @staticmethod
+    def _box_head(x, layers, w3_f32, ref):
+        """bbox MLP (reference models/dino/utils.py:110-122) + box refinement against `ref` (None: raw deltas).  16-bit modes: one
+        fused tcgen05 kernel; fp32 parity mode / unusual widths: three GEMMs + the refinement kernel."""
+        if (ops.MLP_HEAD_FUSED and x.dtype in ops.HALF and len(layers) == 3 and x.shape[1] == 256 and layers[0][0].shape == (256, 256)
+                and layers[1][0].shape == (256, 256) and layers[2][0].shape == (4, 256) and x.stride(0) % 8 == 0):
+            return ops.mlp_head(x, layers[0], layers[1], w3_f32, layers[2][1], ref)
+        delta = InferenceEngine._mlp3(x, layers)
+        return delta if ref is None else ops.box_refine(delta, ref)
 
     def _backbone(self, P, x, B, H, W, T):
         if P["stem_gemm"] is not None and ops.STEM_TENSOR_CORE:
@@ -345,7 +358,7 @@ class InferenceEngine:
             omn = ops.linear_ln(om, *P["enc_output"], None, *P["enc_output_norm"])
             cls_unsel = self._head_gemm(omn, *P["enc_cls"])
             scores = ops.rowmax(cls_unsel, cls_unsel.shape[1]).view(B, S)
-            delta_unsel = self._mlp3(omn, P["enc_bbox"]).view(B, S, 4)
+            delta_unsel = self._box_head(omn, P["enc_bbox"], P["enc_bbox_w3"], None).view(B, S, 4)
             # fused select (csrc/select.cu): per-line shared-memory sort of the S scores, then ONE gather kernel for the anchors, the
             # sigmoid of the proposals and the selected memory rows (the reference: torch.topk + 3 torch.gather + sigmoid)
             topk = ops.topk_select(scores, Q)
@@ -384,7 +397,7 @@ class InferenceEngine:
                     st["dec0_core"] = core.view(B, Q, d)
                 tgt = ops.linear_ln(core, *lyr["ca"]["out"], tgt, *lyr["ln1"])
                 tgt = ops.ffn_ln(tgt, *lyr["l1"], *lyr["l2"], *lyr["ln3"])
-                ref = ops.box_refine(self._mlp3(tgt, P["bbox"][i]), ref)
+                ref = self._box_head(tgt, P["bbox"][i], P["bbox_w3"][i], ref)
                 refs.append(ref)
                 if hs_all is not None:       # decoder.norm output of layer i lands in row block i of one (n_dec*B*Q, d) matrix
                     hs.append(ops.add_layernorm(tgt, None, *P["dec_norm"], out=hs_all[i * B * Q:(i + 1) * B * Q]))
@@ -400,13 +413,13 @@ class InferenceEngine:
             coords, classes = {}, {}
             if hs_all is not None:
                 ref_all = torch.cat(refs[:n_dec], 0)
-                box_all = ops.box_refine(self._mlp3(hs_all, P["bbox"][0]), ref_all).view(n_dec, B, Q, 4)
+                box_all = self._box_head(hs_all, P["bbox"][0], P["bbox_w3"][0], ref_all).view(n_dec, B, Q, 4)
                 cls_all = self._head_gemm(hs_all, *P["cls"][0]).unflatten(0, (n_dec, B, Q))
                 for i in want:
                     coords[i], classes[i] = box_all[i], cls_all[i]
             else:
                 for i in want:
-                    coords[i] = ops.box_refine(self._mlp3(hs[i], P["bbox"][i]), refs[i]).view(B, Q, 4)
+                    coords[i] = self._box_head(hs[i], P["bbox"][i], P["bbox_w3"][i], refs[i]).view(B, Q, 4)
                     classes[i] = self._head_gemm(hs[i], *P["cls"][i]).unflatten(0, (B, Q))
             out = {"pred_logits": classes[n_dec - 1], "pred_boxes": coords[n_dec - 1]}
             if m.aux_loss:

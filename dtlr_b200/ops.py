@@ -417,6 +417,24 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     return linear_ln(gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta, add2=add2)
 
 
+MLP_HEAD_FUSED = _os.environ.get("DTLR_MLP_HEAD_FUSED", "1") != "0"
+
+
+def mlp_head(x, l1, l2, w3_f32, b3, ref=None):
+    """3-layer box MLP (256 -> 256 -> 256 -> 4) [+ box refinement against `ref`] as ONE tcgen05 kernel (csrc/ffn.cu, HEAD variant).
+    x (M,256) 16-bit; l1 / l2 = (weight (256,256) 16-bit, bias fp32); w3_f32 (4,256) fp32, b3 (4) fp32; ref (M,4) fp32 or None.
+    Returns fp32 (M,4): sigmoid(mlp(x) + inverse_sigmoid(ref)), or the raw mlp(x) when ref is None."""
+    L.require_cuda(x, w3_f32, b3, ref)
+    M = x.shape[0]
+    assert x.dtype in HALF and x.shape[1] == 256 and x.stride(1) == 1 and l1[0].shape == (256, 256) and l2[0].shape == (256, 256)
+    assert w3_f32.dtype == torch.float32 and w3_f32.shape == (4, 256) and w3_f32.is_contiguous() and (ref is None or ref.is_contiguous())
+    L.set_flavor(x.dtype)
+    out = torch.empty((M, 4), dtype=torch.float32, device=x.device)
+    _call("dtlr_mlp_head", _p(x), x.stride(0), _p(l1[0]), l1[0].stride(0), _p(l1[1]), _p(l2[0]), l2[0].stride(0), _p(l2[1]), _p(w3_f32), _p(b3),
+          _p(ref), _p(out), M, _st(x))
+    return out
+
+
 def preprocess_u8(packed_u8, offsets_i64, hw_i32, channels, B, Hmax, Wmax, mean, std):
     """GPU input stage (csrc/input.cu): packed u8 images -> (B,3,Hmax,Wmax) fp32 normalised + zero padded, (B,Hmax,Wmax) bool mask."""
     import ctypes

@@ -195,6 +195,15 @@ int dtlr_ctc_decode_scaled(const float* logits, int ld, const float* boxes, int*
                            int* scratch_label, float* scratch_sum, int B, int Q, int C, float eps, float prob_scale,
                            void* stream);
 
+/* The 3-layer box MLP (models/dino/utils.py:110-122 as instantiated for bbox_embed / enc_out_bbox_embed: 256 -> 256 -> 256 -> 4, ReLU
+ * between) fused with the iterative box refinement that consumes it (models/dino/deformable_transformer.py:734-738 and the repeated
+ * evaluation in models/dino/dino.py:343-345): out4[r] = sigmoid(MLP(X[r]) + inverse_sigmoid(ref[r])) with inverse_sigmoid of
+ * util/misc.py:575-579 (eps 1e-3), or the raw MLP output when ref is NULL.  One tcgen05 kernel (the FFN kernel's HEAD variant): the two
+ * 256-wide intermediates never reach HBM.  X [M, ldx] / W1 / W2 [256, ld] 16-bit (the library's flavour), b1 / b2 fp32 [256],
+ * W3 fp32 [4,256], b3 fp32 [4], ref fp32 [M,4] or NULL, out4 fp32 [M,4]. */
+int dtlr_mlp_head(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                  const float* b2, const float* W3, const float* b3, const float* ref, float* out4, int M, void* stream);
+
 /* Two-stage query selection (models/dino/deformable_transformer.py:345-353): idx int64 [B,K] = torch.topk(scores [B,S], K, dim=1)[1]
  * (descending, ties resolved to the lowest token index); fails like torch.topk when K > S (reference quirk: 40x704 lines have 627 < 900
  * tokens).  dtlr_select_gather then performs what follows it in one pass (:348-353, :676): refpoint [B,K,4] = sigmoid((coord +

@@ -188,3 +188,32 @@ def test_weight_stationary_ragged_slice_pitched_output(M, N, K, out_dtype):
     finally:
         _lib.lib().dtlr_debug_flags(0)
     assert torch.equal(out, old)
+
+
+@pytest.mark.parametrize("M,with_ref", [(57600, True), (128 * 148 + 77, True), (300, False), (58368, False)])
+def test_fused_mlp_head_box_refine(M, with_ref):
+    """dtlr_mlp_head (the FFN kernel's HEAD variant): 256 -> 256 -> 256 -> 4 MLP (reference models/dino/utils.py:110-122) + box refinement
+    (deformable_transformer.py:734-738, util/misc.py:575-579) against torch fp32 on the same 16-bit operands (first hidden layer
+    rounded to 16 bits as the kernel keeps it in TMEM, second one in fp32)."""
+    from dtlr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(256, 256, device="cuda", generator=g) / 16).bfloat16()
+    w2 = (torch.randn(256, 256, device="cuda", generator=g) / 16).bfloat16()
+    b1 = torch.randn(256, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(256, device="cuda", generator=g) * 0.1
+    w3 = torch.randn(4, 256, device="cuda", generator=g) * 0.05
+    b3 = torch.randn(4, device="cuda", generator=g) * 0.1
+    ref = torch.rand(M, 4, device="cuda", generator=g) if with_ref else None
+    if with_ref:
+        ref[::7] = 0.0            # clamped by eps = 1e-3 on both sides
+        ref[3::11] = 1.0
+    got = ops.mlp_head(x, (w1, b1), (w2, b2), w3, b3, ref)
+    h1 = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
+    h2 = torch.relu(h1 @ w2.float().T + b2)
+    want = h2 @ w3.T + b3
+    if with_ref:
+        r = ref.clamp(0, 1)
+        want = (want + torch.log(r.clamp(min=1e-3) / (1 - r).clamp(min=1e-3))).sigmoid()
+    assert got.shape == (M, 4) and got.dtype == torch.float32
+    assert torch.allclose(got, want, rtol=2e-3, atol=2e-3), (got - want).abs().max()
