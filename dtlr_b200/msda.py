@@ -43,6 +43,7 @@ def _host_levels(spatial_shapes, level_start_index):
 def msda_forward_raw(value, shapes_host, lsi_host, n_levels, loc, attn, out=None):
     """value (B,S,M,D) cuda contiguous; shapes_host/lsi_host ctypes int64 arrays; loc (B,Lq,M,L,P,2); attn (B,Lq,M,L,P)."""
     L.require_cuda(value, loc, attn)
+    L.set_flavor(value.dtype)
     if not (value.is_contiguous() and loc.is_contiguous() and attn.is_contiguous()):
         raise L.DtlrError("ms_deform_attn_forward: value, sampling_loc and attn_weight must be contiguous")
     B, S, M, D = value.shape
@@ -63,6 +64,7 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     """MSDA core with the prologue fused (include/dtlr_b200.h: dtlr_msda_forward_fused).  value (B,S,M,32);
     proj fp32 (B*Lq, ld) = offsets | logits; ref fp32 (B*Lq, 2|4); valid_ratios fp32 (B,L,2)."""
     L.require_cuda(value, proj, ref, valid_ratios)
+    L.set_flavor(value.dtype)
     B, S, M, D = value.shape
     # value may be a column block of a wider matrix (several layers' value projections from one GEMM): pixel pitch = stride(1)
     assert value.stride(3) == 1 and value.stride(2) == D and value.stride(0) == S * value.stride(1), "unsupported value layout"

@@ -204,6 +204,7 @@ ATTN_IMPL = _os.environ.get("DTLR_ATTN", "hmma")
 
 
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
+    L.set_flavor(v.dtype)
     out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
     if ATTN_IMPL == "tc" and v.dtype in HALF and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:
         vt = torch.empty((B * heads * 32, 1024), dtype=v.dtype, device=v.device)

@@ -16,7 +16,7 @@ for line in out.splitlines():
         cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()[:110]
         hist[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(.*?);", line)
     if m and cur:
         ins = m.group(1).split()
         op = ins[1] if ins[0].startswith("@") else ins[0]
