@@ -218,7 +218,10 @@ def train_step_leg(device, rank, world, local, steps=5, warmup=2):
     net = model
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(model, device_ids=[local], find_unused_parameters=True)
+        # the CTC-only loss leaves the box heads without gradient (reference points are detached, pred_boxes only steer the sort): the
+        # reference passes find_unused_parameters (finetuning.py:211-215); a static graph lets DDP learn the unused set once instead
+        # of walking the autograd graph every step, and bucket views avoid one copy of the 187 MB of gradients
+        net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True, bucket_cap_mb=64)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
     B = TRAIN_BATCH_PER_GPU
