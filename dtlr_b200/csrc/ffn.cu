@@ -51,6 +51,11 @@ struct FfnArgs {
     const float* b3;      // [4]
     const float* ref;     // [M][4] reference boxes in (0,1) or null: out = sigmoid(delta + inverse_sigmoid(ref)) (box refinement)
     float* out4;          // [M][4]
+    // PART variant (wave-quantisation tail, see dtlr_ffn_ln): CTA u works on row tile tile_base + u / nsplit and on the hidden slice
+    // (u % nsplit) of width HID (the LOCAL width; b1 / W1 / W2 are offset by the slice) and stores its raw fp32 partial of
+    // W2 . relu(W1 X + b1) to partial[slice][tile - tile_base][128][256]
+    int tile_base, nsplit;
+    float* partial;
 };
 
 struct FfnSmem {
@@ -76,12 +81,13 @@ __device__ __forceinline__ uint32_t ff_pack_bf16x2(float lo, float hi) {
 // + b2) stays in registers, the 4-wide last layer is 4 dot products per row on the FMA pipe, followed (optionally) by the box
 // refinement sigmoid(delta + inverse_sigmoid(ref)) of reference deformable_transformer.py:734-738 / dino.py:343-345: one kernel reads
 // X once and writes 16 bytes per row, instead of three GEMMs (two 256-wide intermediates through HBM) + an elementwise kernel.
-template <bool CL, bool HEAD>
+template <bool CL, int VAR>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
     extern __shared__ unsigned char smem_raw[];
     constexpr int NS = FF_NS;
+    constexpr bool HEAD = VAR == 1, PART = VAR == 2;
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* xs = smem;                                // [2][4 k-blocks][128 rows x 128 B]
     unsigned char* ring = xs + 2 * FfnSmem::XS;
@@ -104,6 +110,10 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (a.M + FF_BM - 1) / FF_BM;
     const int NJ = a.HID / FF_HC;
+    // row tiles of this CTA: persistent stride over all tiles, or (PART) exactly one tile and one hidden slice of NJ chunks from jo
+    const int mt_first = PART ? a.tile_base + (int)blockIdx.x / a.nsplit : (int)blockIdx.x;
+    const int mt_step = PART ? (1 << 28) : (int)gridDim.x;
+    const int jo = PART ? ((int)blockIdx.x % a.nsplit) * NJ : 0;
     // CL: both CTAs of a pair (even grid, rank = blockIdx.x & 1) must consume the same number of weight chunks: the pair works on
     // tiles (2p, 2p+1), (2p, 2p+1) + grid, ... while the EVEN tile exists; an odd tile == num_m is a ghost (X rows zero-filled by
     // TMA, stores clipped by TMA)
@@ -130,7 +140,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
-    for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + i);
+    for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + jo * FF_HC + i);
     float* w3_s = b1_s + FF_D;                       // HEAD: [256 columns][4 outputs] behind the 256 b1 entries (HID == 256)
     for (int i = threadIdx.x; i < FF_D; i += 320) {
         b2_s[i] = __ldg(a.b2 + i);
@@ -163,17 +173,17 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mbar_expect_tx(&x_full[xb], FfnSmem::XS);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
             };
-            if (more(blockIdx.x)) load_x(blockIdx.x, 0);
-            for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t) {
+            if (more(mt_first)) load_x(mt_first, 0);
+            for (int mt = mt_first; more(mt); mt += mt_step, ++t) {
                 for (int j = 0; j <= NJ; ++j) {
-                    if (j == NJ / 2 && more(mt + (int)gridDim.x)) load_x(mt + gridDim.x, t + 1);
+                    if (j == NJ / 2 && more(mt + mt_step)) load_x(mt + mt_step, t + 1);
                     if (j < NJ) {
                         for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
                             const int s = it % NS;
                             mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
-                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
-                            else if ((it & 1) == cta_rank) tma_load_2d_multicast(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC, 3);
+                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, (jo + j) * FF_HC);
+                            else if ((it & 1) == cta_rank) tma_load_2d_multicast(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, (jo + j) * FF_HC, 3);
                         }
                     }
                     if (j >= 1) {
@@ -181,9 +191,9 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                             const int s = it % NS;
                             mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
                             mbar_expect_tx(&w_full[s], FF_STAGE);
-                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                            if (!CL) tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], (jo + j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128);
                             else if ((it & 1) == cta_rank)
-                                tma_load_2d_multicast(ring + s * FF_STAGE, &tmW2, &w_full[s], (j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128, 3);
+                                tma_load_2d_multicast(ring + s * FF_STAGE, &tmW2, &w_full[s], (jo + j - 1) * FF_HC + (q >> 1) * 64, (q & 1) * 128, 3);
                         }
                     }
                 }
@@ -194,7 +204,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         //       issue order; E1(j) finished with it before h_full(j), which G2(j) waited for
         constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
         uint32_t it = 0, g = 0, t = 0;
-        for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t, g += NJ) {
+        for (int mt = mt_first; more(mt); mt += mt_step, ++t, g += NJ) {
             const uint32_t xb = t & 1;
             mbar_wait(&x_full[xb], (t >> 1) & 1);
             tcgen05_fence_after();
@@ -254,7 +264,7 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t swz = (uint32_t)(lane & 7);
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         uint32_t g = 0, t = 0;
-        for (int mt = blockIdx.x; more(mt); mt += gridDim.x, ++t, g += NJ) {
+        for (int mt = mt_first; more(mt); mt += mt_step, ++t, g += NJ) {
             // ---- E1: hidden chunk j: +b1, ReLU, bf16, back into TMEM in place
             for (int j = 0; j < NJ; ++j) {
                 const uint32_t gj = g + j, b = gj & 1, u = gj >> 1;
@@ -289,6 +299,31 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // ---- final: Yacc + b2 + X -> LayerNorm -> bf16 over the X tile -> TMA store
             const uint32_t xb = t & 1;
             unsigned char* xt = xs + xb * FfnSmem::XS;
+            if (PART) {
+                // ---- final (PART): the raw fp32 partial of this hidden slice -> scratch (summed + normalised by ffn_tail_ln_kernel)
+                mbar_wait(y_full, t & 1);
+                tcgen05_fence_after();
+                if (lane == 0) mbar_arrive(&x_free[xb]);
+                float* dst = a.partial + (((size_t)((int)blockIdx.x % a.nsplit) * (size_t)(gridDim.x / a.nsplit) + (size_t)(mt - a.tile_base)) * FF_BM + row) * FF_D;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t acc[32];
+                        tmem_ld32(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64 + hf * 32), acc);
+                        if (cb == 1 && hf == 1) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(y_free);
+                        }
+                        float4* d4 = reinterpret_cast<float4*>(dst + hsel * 128 + cb * 64 + hf * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            d4[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+                    }
+                }
+                continue;
+            }
             if (HEAD) {
                 // ---- final (HEAD): relu(Yacc + b2) . W3^T + b3 [-> box refinement] -> 16 bytes per row
                 mbar_wait(y_full, t & 1);                    // every MMA of the tile is complete: X is no longer read either
@@ -428,6 +463,54 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
 }
 
+// The rows of the wave-quantisation tail: sum of the hidden-slice partials (fixed order: deterministic) + b2 + X -> rounded to the
+// 16-bit type like the main kernel's packed pre-norm row -> LayerNorm -> Y.  One warp per row, 8 columns per lane.
+__global__ void __launch_bounds__(256)
+ffn_tail_ln_kernel(const float* __restrict__ partial, const int nsplit, const size_t slice_stride, const op16_t* __restrict__ x, const int ldx,
+                   const float* __restrict__ b2, const float* __restrict__ gamma, const float* __restrict__ beta, const float eps,
+                   op16_t* __restrict__ y, const int ldy, const int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int c = (threadIdx.x & 31) * 8;
+    float v[8];
+    {
+        const uint4 xr = *reinterpret_cast<const uint4*>(x + (size_t)row * ldx + c);
+        const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+        const float4 ba = *reinterpret_cast<const float4*>(b2 + c), bb = *reinterpret_cast<const float4*>(b2 + c + 4);
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = bv[2 * i] + op16_lo_f32(xw[i]); v[2 * i + 1] = bv[2 * i + 1] + op16_hi_f32(xw[i]); }
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sidx = 0; sidx < nsplit; ++sidx) {
+        const float4* p = reinterpret_cast<const float4*>(partial + (size_t)sidx * slice_stride + (size_t)row * FF_D + c);
+        const float4 a = p[0], b = p[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    float sum = 0.f, sq = 0.f;
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pk[i] = ff_pack_bf16x2(acc[2 * i] + v[2 * i], acc[2 * i + 1] + v[2 * i + 1]);
+        const float y0 = op16_lo_f32(pk[i]), y1 = op16_hi_f32(pk[i]);
+        sum += y0 + y1;
+        sq = fmaf(y0, y0, sq);
+        sq = fmaf(y1, y1, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    const float mean = sum * (1.f / 256.f);
+    const float rstd = rsqrtf(fmaxf(sq * (1.f / 256.f) - mean * mean, 0.f) + eps);
+    uint32_t o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        o4[i] = ff_pack_bf16x2((op16_lo_f32(pk[i]) - mean) * rstd * gamma[c + 2 * i] + beta[c + 2 * i],
+                               (op16_hi_f32(pk[i]) - mean) * rstd * gamma[c + 2 * i + 1] + beta[c + 2 * i + 1]);
+    *reinterpret_cast<uint4*>(y + (size_t)row * ldy + c) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+}
+
 static int ffn_tmap(CUtensorMap* map, const void* base, long long rows, int cols, long long ld, int box_rows) {
     return make_tmap_2d_bf16(map, base, rows, cols, ld, box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -435,6 +518,61 @@ static int ffn_tmap(CUtensorMap* map, const void* base, long long rows, int cols
 }  // namespace dtlr
 
 using namespace dtlr;
+
+// Wave quantisation: the block runs one 128-row tile per SM at a time; num_m tiles on `sm` SMs take ceil(num_m / sm)
+// rounds (456 tiles at B = 64: 3.08 waves -> 4 rounds).  When the last round is mostly empty the split entry point runs the full
+// rounds with the main kernel and the `rem` tail tiles with the PART variant -- each tail tile's hidden dimension cut into `nsplit`
+// slices on otherwise idle SMs, partial sums to a workspace -- followed by ffn_tail_ln_kernel.
+static void ffn_split_plan(int M, int hidden, int* main_rows, int* rem_tiles, int* nsplit) {
+    const int num_m = (M + FF_BM - 1) / FF_BM, sm = sm_count();
+    const int full = num_m / sm, rem = num_m % sm;
+    *main_rows = M; *rem_tiles = 0; *nsplit = 1;
+    if ((g_debug_flags & 262144) || full < 1 || rem == 0 || rem * 2 > sm) return;      // flag 262144: never split (A/B)
+    int ns = 1;
+    const int nj = hidden / FF_HC;
+    while (ns * 2 <= nj && (nj % (ns * 2)) == 0 && rem * ns * 2 <= sm) ns *= 2;
+    if (ns < 2) return;
+    *main_rows = full * sm * FF_BM; *rem_tiles = rem; *nsplit = ns;
+}
+
+extern "C" long long dtlr_ffn_workspace_bytes(int M, int hidden) {
+    int main_rows, rem, ns;
+    if (M <= 0 || hidden <= 0 || (hidden % FF_HC) != 0 || hidden > FF_MAX_HID) return 0;
+    ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
+    return rem ? (long long)ns * rem * FF_BM * FF_D * 4 : 0;
+}
+
+extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                           const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
+                           void* stream);
+
+extern "C" int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                              const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
+                              void* workspace, long long workspace_bytes, void* stream) {
+    int main_rows = M, rem = 0, ns = 1;
+    if (M > 0 && hidden > 0 && (hidden % FF_HC) == 0 && hidden <= FF_MAX_HID) ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
+    if (!rem || !workspace || workspace_bytes < (long long)ns * rem * FF_BM * FF_D * 4)
+        return dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, M, hidden, stream);
+    int rc = dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, main_rows, hidden, stream);
+    if (rc) return rc;
+    const op16_t* xt = reinterpret_cast<const op16_t*>(X) + (size_t)main_rows * ldx;
+    op16_t* yt = reinterpret_cast<op16_t*>(Y) + (size_t)main_rows * ldy;
+    const int mt = M - main_rows;
+    CUtensorMap tx, tw1, tw2;
+    if ((rc = ffn_tmap(&tx, xt, mt, FF_D, ldx, FF_BM))) return rc;
+    if ((rc = ffn_tmap(&tw1, W1, hidden, FF_D, ldw1, 128))) return rc;
+    if ((rc = ffn_tmap(&tw2, W2, FF_D, hidden, ldw2, 128))) return rc;
+    static bool configured = false;
+    if (!configured) {
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        configured = true;
+    }
+    const FfnArgs a{b1, b2, gamma, beta, eps, mt, hidden / ns, g_debug_flags, nullptr, nullptr, nullptr, nullptr, 0, ns, (float*)workspace};
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, 2>, dim3(rem * ns), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, tx, a));
+    DTLR_CHECK_CUDA(launch_pdl(ffn_tail_ln_kernel, dim3((mt + 7) / 8), dim3(256), 0, (cudaStream_t)stream, (const float*)workspace, ns,
+                               (size_t)rem * FF_BM * FF_D, xt, ldx, b2, gamma, beta, eps, yt, ldy, mt));
+    return DTLR_OK;
+}
 
 extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
                            const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
@@ -454,12 +592,12 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
-    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags, nullptr, nullptr, nullptr, nullptr};
+    const FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags, nullptr, nullptr, nullptr, nullptr, 0, 1, nullptr};
     // CTA pairs with multicast weights: measured identical (129.0 vs 130.1 us): halving the L2 reads does not help because the
     // limit of the weight stream is the ~51 B/clk at which one SM's shared memory is filled (loads alone: 63 us with or without
     // multicast, with 5 or 9 ring stages).  Kept (dtlr_debug_flags(4096)) as the validated base of the cta_group::2 version, which
@@ -467,11 +605,11 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
     if ((g_debug_flags & 4096) && num_m >= 2) {
         int grid = num_m < sm_count() ? num_m : sm_count();
         grid &= ~1;
-        DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_tcgen05_kernel<true, false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
+        DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_tcgen05_kernel<true, 0>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
         return DTLR_OK;
     }
     const int grid = num_m < sm_count() ? num_m : sm_count();
-    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, false>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, 0>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
     return DTLR_OK;
 }
 
@@ -494,12 +632,12 @@ extern "C" int dtlr_mlp_head(const void* X, int ldx, const void* W1, int ldw1, c
     if ((rc = ffn_tmap(&tw2, W2, FF_D, FF_D, ldw2, 128))) return rc;
     static bool configured = false;
     if (!configured) {
-        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+        DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_tcgen05_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
         configured = true;
     }
     const int num_m = (M + FF_BM - 1) / FF_BM;
-    const FfnArgs a{b1, b2, nullptr, nullptr, 0.f, M, FF_D, g_debug_flags, W3, b3, ref, out4};
+    const FfnArgs a{b1, b2, nullptr, nullptr, 0.f, M, FF_D, g_debug_flags, W3, b3, ref, out4, 0, 1, nullptr};
     const int grid = num_m < sm_count() ? num_m : sm_count();
-    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, true>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, tx, a));
+    DTLR_CHECK_CUDA(launch_pdl(ffn_ln_tcgen05_kernel<false, 1>, dim3(grid), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, tx, a));
     return DTLR_OK;
 }

@@ -382,6 +382,7 @@ def linear_ln(a, w, bias, residual, gamma, beta, add2=None):
 FFN_FUSED = _os.environ.get("DTLR_FFN_FUSED", "1") != "0"
 # measured (one box, full step): no chunking 8.82 ms, 37888-row chunks 8.96, 18944: 9.32, 9472: 10.01 -> off by default
 FFN_CHUNK_ROWS = int(_os.environ.get("DTLR_FFN_CHUNK_ROWS", "0"))
+FFN_SPLIT_TAIL = _os.environ.get("DTLR_FFN_SPLIT_TAIL", "1") != "0"
 
 
 def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
@@ -397,8 +398,16 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
         L.set_flavor(x.dtype)
         if L.TIMER is not None:     # bench.py: algorithmic FLOPs of the block = the two contractions, 2*M*hid*256 each
             L.TIMER("ffn", 4.0 * M * hid * 256, x.device, True)
-        _call("dtlr_ffn_ln", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
-              ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _st(x))
+        # wave-quantisation tail: when the last round of 128-row tiles is mostly empty the library splits the tail
+        # tiles' hidden dimension over the idle SMs; it needs an fp32 workspace for the partial sums (0 bytes: no split)
+        lib = L.lib()
+        lib.dtlr_ffn_workspace_bytes.restype = ctypes.c_longlong
+        nws = int(lib.dtlr_ffn_workspace_bytes(M, hid)) if FFN_SPLIT_TAIL else 0
+        ws = torch.empty((nws,), dtype=torch.uint8, device=x.device) if nws > 0 else None
+        _call("dtlr_ffn_ln_ws", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
+              ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _p(ws), ctypes.c_longlong(nws), _st(x))
+        if nws > 0:
+            L.LAUNCHES += 2
         if L.TIMER is not None:
             L.TIMER("ffn", 0.0, x.device, False)
         return (y, add(y, add2)) if add2 is not None else y

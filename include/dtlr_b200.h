@@ -106,6 +106,14 @@ int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, const float* bi
  * X [M,ldx], W1 [hidden,ldw1] (256 used), W2 [256,ldw2] (hidden used), Y [M,ldy]; b1 [hidden], b2/gamma/beta [256] fp32. */
 int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2, const float* b2,
                 const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden, void* stream);
+/* The same block with the wave-quantisation tail split over idle SMs: the full rounds of 128-row tiles run on the
+ * kernel above, the remaining tiles with their hidden dimension cut into slices (partial sums in `workspace`, fp32) followed by a
+ * sum + residual + LayerNorm kernel.  dtlr_ffn_workspace_bytes(M, hidden) = the workspace the plan for this shape needs (0: no
+ * split pays; then, or with a NULL / too small workspace, the call is dtlr_ffn_ln).  Deterministic: fixed summation order. */
+long long dtlr_ffn_workspace_bytes(int M, int hidden);
+int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                   const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
+                   void* workspace, long long workspace_bytes, void* stream);
 /* tuning aid only: sets kernel debug flags (0 = normal operation), returns the previous value */
 int dtlr_debug_flags(int flags);
 /* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */

@@ -164,7 +164,25 @@ def test_fused_ffn_block(M, hid, pairs):
     assert (y.float() - ref).abs().mean().item() < 4e-3
     un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
-    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining)
+    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining);
+    # the same two cases take the wave-quantisation split (3 full rounds on the main kernel + the tail tiles' hidden dimension cut
+    # into 8 / 16 slices on idle SMs + the sum / LayerNorm kernel) on a 148-SM part; without it the result must agree as well
+    import ctypes
+    lib = _lib.lib()
+    lib.dtlr_ffn_workspace_bytes.restype = ctypes.c_longlong
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    tiles = (M + 127) // 128
+    if tiles // sms >= 1 and 0 < tiles % sms <= sms // 2 and hid >= 256:
+        assert lib.dtlr_ffn_workspace_bytes(M, hid) > 0
+        saved_split, ops.FFN_SPLIT_TAIL = ops.FFN_SPLIT_TAIL, False
+        try:
+            y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+        finally:
+            ops.FFN_SPLIT_TAIL = saved_split
+        main_rows = (tiles // sms) * sms * 128
+        assert torch.equal(y[:main_rows], y0[:main_rows])
+        assert (y[main_rows:].float() - y0[main_rows:].float()).abs().max().item() < 5e-2
+        assert (y[main_rows:].float() - y0[main_rows:].float()).abs().mean().item() < 2e-3
 
 
 @pytest.mark.parametrize("M,N,K,out_dtype", [(57600 * 2, 166, 256, torch.float32), (58368, 166, 256, torch.float32),
