@@ -85,7 +85,8 @@ mha_simt_kernel(const T* __restrict__ qk, int ld_qk, int k_off, const T* __restr
 // the head (Q x 32 bf16 each) are staged once in shared memory (80-byte row pitch: conflict-free ldmatrix), each warp
 // owns 16 queries at a time and sweeps the keys 64 at a time: S = Q K^T and O += P V on mma.sync m16n8k16 (bf16 in,
 // fp32 accumulate), online softmax in registers with exp2f.  Scores never leave the register file.
-constexpr int FA_WARPS = 16;
+constexpr int FA_WARPS = 16;       // default warps per CTA (dtlr_attn_config overrides: 8..20)
+constexpr int FA_WARPS_MAX = 20;   // 640 threads x 86 registers fit the register file (limit 102 per thread)
 constexpr int FA_MT = 1;        // 16-query m-tiles per warp (MT = 2 with 8 warps measured slower: 305 vs 287 us/layer)
 constexpr int FA_PITCH = 40;   // bf16 elements per smem row (32 + 8 padding)
 
@@ -117,7 +118,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // score array takes the kernel from 86 to 128 registers (the cap at 512 threads) with 60 bytes of spills, and ptxas already
 // interleaves the P.V MMAs with the exponentials of the same block -- the four warps per scheduler cover the rest.
 template <int MT, bool PIPE>
-__global__ void __launch_bounds__(FA_WARPS * 32)
+__global__ void __launch_bounds__(FA_WARPS_MAX * 32)
 mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const op16_t* __restrict__ v, int ld_v,
                       op16_t* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
     extern __shared__ __align__(16) unsigned char fa_smem[];
@@ -126,12 +127,13 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
     op16_t* Vs = Ks + (size_t)KP * FA_PITCH;
     const int b = blockIdx.z, h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x, nwarps = blockDim.x >> 5;
     const size_t row0 = (size_t)b * Q;
     pdl_launch_dependents();
     pdl_wait();
 
     // ---- stage K and V of this (image, head): 4 x 16-byte chunks per row, zero rows for the key padding
-    for (int i = tid; i < KP * 4; i += FA_WARPS * 32) {
+    for (int i = tid; i < KP * 4; i += nthr) {
         const int r = i >> 2, c = i & 3;
         if (r < Q) {
             cp_async16(Ks + (size_t)r * FA_PITCH + c * 8, qk + (row0 + r) * ld_qk + k_off + h * 32 + c * 8);
@@ -153,7 +155,7 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
     const int k_row = lane & 7, k_chunk = lane >> 3;
     const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_chunk = lane >> 4;
 
-    for (int q0 = q_begin + warp * (16 * MT); q0 < q_end; q0 += FA_WARPS * 16 * MT) {
+    for (int q0 = q_begin + warp * (16 * MT); q0 < q_end; q0 += nwarps * 16 * MT) {
         // ---- Q fragments (A operand, 2 k-steps over dh = 32), straight from global memory
         uint32_t qa[MT][2][4];
 #pragma unroll
@@ -297,6 +299,10 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
 
 using namespace dtlr;
 
+static int g_attn_warps = 0, g_attn_splits = 0;
+// tuning hook: warps per CTA (1..20) and query splits per (image, head) of the flash kernel; 0, 0 = automatic
+extern "C" int dtlr_attn_config(int warps, int splits) { g_attn_warps = warps; g_attn_splits = splits; return DTLR_OK; }
+
 extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, const void* v, int ld_v,
                                        const unsigned char* attn_mask, void* out, int ld_o, int B, int Q, int heads,
                                        int head_dim, int dtype, void* stream) {
@@ -312,14 +318,28 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
              (size_t)((Q + 63) / 64 * 64) * FA_PITCH * 2 * 2 <= (size_t)max_smem_optin()) {
         const int KP = (Q + 63) / 64 * 64;
         const size_t smem = (size_t)KP * FA_PITCH * 2 * 2;
-        // one round of (16*MT)-query tiles per CTA: ceil(Q / 256) CTAs per (image, head), each staging K and V once
-        const int per_round = FA_WARPS * 16 * FA_MT;
-        const int splits = (Q + per_round - 1) / per_round;
-        int q_per_cta = ((Q + splits - 1) / splits + 16 * FA_MT - 1) / (16 * FA_MT) * (16 * FA_MT);
+        // Work partition.  A (image, head) has T = ceil(Q / 16) query tiles of one warp each; it is cut into `splits` CTAs of W warps
+        // (each CTA stages K and V once).  Two quantisations cost time: tiles per CTA vs W (Q = 900: 57 tiles; 4 x 16 warps = 64
+        // slots = 89 %, 3 x 19 = 57 = 100 %) and CTAs vs SMs (one CTA per SM: 144 KB of K / V).  Auto: the (W, splits) with the fewest
+        // warp-rounds = ceil(CTAs / SMs) * ceil(tiles per CTA / W) * W, ties to fewer splits; dtlr_attn_config() overrides (A/B).
+        const int T = (Q + 16 * FA_MT - 1) / (16 * FA_MT);
+        int W = g_attn_warps, splits = g_attn_splits;
+        if (W <= 0 || splits <= 0) {
+            long long best = -1;
+            for (int s_ = 1; s_ <= 8; ++s_)
+                for (int w_ = 12; w_ <= FA_WARPS_MAX; ++w_) {
+                    const int tpc = (T + s_ - 1) / s_;
+                    const long long ctas = (long long)s_ * heads * B;
+                    const long long cost = ((ctas + sm_count() - 1) / sm_count()) * (((tpc + w_ - 1) / w_) * (long long)w_ + 2);   // + 2: K / V staging
+                    if (best < 0 || cost < best) { best = cost; W = w_; splits = s_; }
+                }
+        }
+        W = W < 1 ? 1 : (W > FA_WARPS_MAX ? FA_WARPS_MAX : W);
+        int q_per_cta = ((T + splits - 1) / splits) * 16 * FA_MT;
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
         auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, true> : mha_flash_bf16_kernel<FA_MT, false>;   // flag 16384: QK-pipelined variant (A/B)
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(FA_WARPS * 32), smem, st, (const op16_t*)qk, ld_qk, k_off,
+        DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(W * 32), smem, st, (const op16_t*)qk, ld_qk, k_off,
                                    (const op16_t*)v, ld_v, (op16_t*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
     } else if (dtype == DTLR_OP16)
         mha_simt_kernel<op16_t><<<grid, ATT_QT, 0, st>>>((const op16_t*)qk, ld_qk, k_off, (const op16_t*)v, ld_v, attn_mask, (op16_t*)out, ld_o, Q, scale);

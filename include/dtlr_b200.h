@@ -185,6 +185,9 @@ int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype
  * attn_mask uint8 [Q,Q], 1 = blocked, or NULL; out [B*Q, ld_o]. */
 int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const unsigned char* attn_mask,
                             void* out, int ld_o, int B, int Q, int heads, int head_dim, int dtype, void* stream);
+/* tuning hook of the 16-bit flash kernel above: warps per CTA (1..20) and query splits per (image, head); (0, 0) = automatic (the
+ * partition with the fewest warp-rounds, see csrc/attention.cu) */
+int dtlr_attn_config(int warps, int splits);
 /* The same attention on the tcgen05 tensor cores (bf16, no mask, head_dim 32, Q <= 1024): K / V^T resident in shared memory via
  * TMA, S = QK^T and O += PV as tcgen05.mma with TMEM accumulators, two-pass softmax between them.  vt_scratch: device buffer of
  * B*heads*32*1024 bf16 (V^T, written by a pre-pass).  Returns DTLR_ERR_UNSUPPORTED for shapes it does not cover. */

@@ -17,3 +17,11 @@ for name, impl, flags in (("mma.sync flash (default)", "flash", 0), ("mma.sync f
     us = timeit(lambda i: ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32), iters=10)
     _lib.lib().dtlr_debug_flags(0)
     print(json.dumps({"kernel": name, "us": round(us, 1), "TFLOPs": round(fl / us / 1e6, 1)}), flush=True)
+
+# work partition of the flash kernel: warps per CTA x query splits per (image, head)  (0, 0 = automatic)
+ops.ATTN_IMPL = "flash"
+for W, S in ((16, 4), (0, 0), (19, 3), (20, 3), (15, 4), (19, 1), (20, 1), (16, 2), (18, 2), (12, 5), (19, 2), (15, 2)):
+    _lib.lib().dtlr_attn_config(W, S)
+    us = timeit(lambda i: ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32), iters=10)
+    print(json.dumps({"kernel": "flash warps=%d splits=%d" % (W, S), "us": round(us, 1), "TFLOPs": round(fl / us / 1e6, 1)}), flush=True)
+_lib.lib().dtlr_attn_config(0, 0)
