@@ -320,17 +320,20 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         const size_t smem = (size_t)KP * FA_PITCH * 2 * 2;
         // Work partition.  A (image, head) has T = ceil(Q / 16) query tiles of one warp each; it is cut into `splits` CTAs of W warps
         // (each CTA stages K and V once).  Two quantisations cost time: tiles per CTA vs W (Q = 900: 57 tiles; 4 x 16 warps = 64
-        // slots = 89 %, 3 x 19 = 57 = 100 %) and CTAs vs SMs (one CTA per SM: 144 KB of K / V).  Auto: the (W, splits) with the fewest
-        // warp-rounds = ceil(CTAs / SMs) * ceil(tiles per CTA / W) * W, ties to fewer splits; dtlr_attn_config() overrides (A/B).
+        // slots = 89 %) and CTAs vs SMs (one CTA per SM: 144 KB of K / V).  Measured on B200 (B = 64, Q = 900, tools/bench_attn.py, us):
+        // (W, splits) = (16,4) 255.7 [round 1], (16,2) 233.3, (15,2) 240.3, (19,1) 240.4, (20,1) 240.2, (19,3) 248.8, (12,5) 279.2: the
+        // kernel is issue-bound, not latency-bound (a round costs in proportion to the warps per scheduler, so W is kept a multiple of
+        // 4), and every extra split re-stages K and V (~3 warp-rounds).  Auto: minimise ceil(CTAs / SMs) * (ceil(tiles per CTA / W) * W
+        // + 3) over W in {12, 16, 20}; dtlr_attn_config() overrides (A/B).
         const int T = (Q + 16 * FA_MT - 1) / (16 * FA_MT);
         int W = g_attn_warps, splits = g_attn_splits;
         if (W <= 0 || splits <= 0) {
             long long best = -1;
             for (int s_ = 1; s_ <= 8; ++s_)
-                for (int w_ = 12; w_ <= FA_WARPS_MAX; ++w_) {
+                for (int w_ = 12; w_ <= FA_WARPS_MAX; w_ += 4) {
                     const int tpc = (T + s_ - 1) / s_;
                     const long long ctas = (long long)s_ * heads * B;
-                    const long long cost = ((ctas + sm_count() - 1) / sm_count()) * (((tpc + w_ - 1) / w_) * (long long)w_ + 2);   // + 2: K / V staging
+                    const long long cost = ((ctas + sm_count() - 1) / sm_count()) * (((tpc + w_ - 1) / w_) * (long long)w_ + 3);   // + 3: K / V staging
                     if (best < 0 || cost < best) { best = cost; W = w_; splits = s_; }
                 }
         }

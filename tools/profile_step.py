@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from dtlr_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-model = bench.build_ours(torch.device("cuda", 0), torch.bfloat16)
+model = bench.build_ours(torch.device("cuda", 0), torch.float16 if os.environ.get("DTLR_PROFILE_DTYPE", "f16") == "f16" else torch.bfloat16)
 model.use_cuda_graph = False
 x = synth.synth_images(bench.BATCH_PER_GPU, bench.IMG_H, bench.IMG_W, seed=100).cuda()
 with torch.no_grad():
