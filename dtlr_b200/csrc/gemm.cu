@@ -994,14 +994,19 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     CUtensorMap ta, tb;
     int rc = DTLR_OK;
     if (out_dtype == DTLR_OP16 ? ws_try<op16_t>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
-    if (out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8)) {
+    const long long row_tiles_ = (M + GEMM_BM - 1) / GEMM_BM;
+    if (out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8) &&
+        (K < 1024 || ((row_tiles_ * (N / 128) + sm_count() - 1) / sm_count()) * 128 * 3 > ((row_tiles_ * (N / 256) + sm_count() - 1) / sm_count()) * 256 * 2)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
         // N = 256 layers become one tile per row block
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
         if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 256))) return rc;
         return launch_tc<256, 3, op16_t>(ta, tb, e, st);
     }
-    if (N > 64) {
+    // few tiles and a long K loop (e.g. the 3x3 stride-2 input_proj of the last level: M = 1024, N = 256, K = 18432 -> 16 tiles of
+    // 128 x 128 on 148 SMs): 64-wide tiles double the CTAs that share the K loop
+    const long long tiles128 = (long long)((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
+    if (N > 64 && !(tiles128 * 2 <= sm_count() && K >= 1024 && (N % 64) == 0)) {
         if ((rc = make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM))) return rc;
         if ((rc = make_tmap_bf16(&tb, W, N, K, ldw, 128))) return rc;
         return out_dtype == DTLR_OP16 ? launch_tc<128, 4, op16_t>(ta, tb, e, st) : launch_tc<128, 4, float>(ta, tb, e, st);
@@ -1058,11 +1063,22 @@ extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias,
     int rc;
     if ((rc = make_tmap_nhwc(&ta, x, B, H, W, C, seg_w))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((Cout % 256) == 0) {
+    // tile width by SM fill: 128 x 256 tiles halve the A traffic per FLOP, but the deep stages have few rows (layer4: M = 4096 = 32
+    // row tiles x 2 column tiles of 256 = 64 CTAs on 148 SMs).  cost(BN) = rounds of CTAs x BN; a narrower tile is taken only when it
+    // cuts that cost by >= 1.5x (layer4: 256 -> 128 halves it; layer3, 96 CTAs, stays at 256)
+    const long long row_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    auto tile_cost = [&](int bn) { const long long ctas = row_tiles * ((Cout + bn - 1) / bn); return ((ctas + sm_count() - 1) / sm_count()) * bn; };
+    const bool ok256 = (Cout % 256) == 0, ok128 = Cout > 64;
+    int bn_pick = ok256 ? 256 : (ok128 ? 128 : 64);
+    if (!(g_debug_flags & 1048576)) {       // flag 1048576: round-1 rule (widest tile that divides Cout), A/B
+        if (bn_pick == 256 && (Cout % 128) == 0 && tile_cost(128) * 3 <= tile_cost(256) * 2) bn_pick = 128;
+        if (bn_pick == 128 && (Cout % 64) == 0 && tile_cost(64) * 3 <= tile_cost(128) * 2) bn_pick = 64;
+    }
+    if (bn_pick == 256) {
         if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 256))) return rc;
         return launch_tc<256, 3, op16_t>(ta, tb, e, st);
     }
-    if (Cout > 64) {
+    if (bn_pick == 128) {
         if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 128))) return rc;
         return launch_tc<128, 4, op16_t>(ta, tb, e, st);
     }

@@ -192,6 +192,94 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// Coalesced variant for 8 channels per group (GroupNorm(32, 256)): one CTA per (image, 32-channel quad = 4 groups), every warp reads
+// full 128-byte row segments with 16-byte loads (lane & 7 = float4 within the segment, so a thread always sees ONE group), rows
+// strided over the 32 row slots of the CTA.  With HW <= 32 * RPT the CTA's slice stays in registers: one read of x instead of three.
+// Two-pass statistics (mean, then centred sum of squares) like the kernel above -- same arithmetic, same eps placement.
+template <typename TO, int RPT>
+__global__ void __launch_bounds__(256)
+groupnorm8_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  TO* __restrict__ out, int HW, int C, long long out_stride_b, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cq = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f4 = lane & 7;                              // float4 index inside the 32-channel segment
+    const int grp = f4 >> 1;                              // group (of this CTA's 4) the thread works for
+    const int slot = warp * 4 + (lane >> 3);              // row slot 0..31
+    const float* xb = x + (size_t)b * HW * C + cq * 32 + f4 * 4;
+    __shared__ float red[8][4];
+    __shared__ float stat[2][4];
+    const bool cached = HW <= 32 * RPT;
+    float4 v[RPT];
+    float s = 0.f;
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = slot + 32 * i;
+            v[i] = r < HW ? *reinterpret_cast<const float4*>(xb + (size_t)r * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    } else {
+        for (int r = slot; r < HW; r += 32) {
+            const float4 t = *reinterpret_cast<const float4*>(xb + (size_t)r * C);
+            s += (t.x + t.y) + (t.z + t.w);
+        }
+    }
+    const float inv_n = 1.f / (float)(HW * 8);
+    auto group_reduce = [&](float val, float* dst) {       // sum over the threads of one group: lanes ^1, ^8, ^16, then the 8 warps
+        val += __shfl_xor_sync(0xffffffffu, val, 1);
+        val += __shfl_xor_sync(0xffffffffu, val, 8);
+        val += __shfl_xor_sync(0xffffffffu, val, 16);
+        if ((lane & 25) == 0) red[warp][grp] = val;         // lanes 0, 2, 4, 6: one per group
+        __syncthreads();
+        if (tid < 4) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][tid];
+            dst[tid] = t;
+        }
+        __syncthreads();
+    };
+    group_reduce(s, stat[0]);
+    const float mean = stat[0][grp] * inv_n;
+    float ss = 0.f;
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (slot + 32 * i < HW) {
+                const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                ss += (a * a + bq * bq) + (c * c + d * d);
+            }
+        }
+    } else {
+        for (int r = slot; r < HW; r += 32) {
+            const float4 t = *reinterpret_cast<const float4*>(xb + (size_t)r * C);
+            const float a = t.x - mean, bq = t.y - mean, c = t.z - mean, d = t.w - mean;
+            ss += (a * a + bq * bq) + (c * c + d * d);
+        }
+    }
+    group_reduce(ss, stat[1]);
+    const float rstd = rsqrtf(stat[1][grp] * inv_n + eps);
+    const int c0 = cq * 32 + f4 * 4;
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c0), bt = *reinterpret_cast<const float4*>(beta + c0);
+    TO* ob = out + (size_t)b * out_stride_b * C + c0;
+    auto emit = [&](const int r, const float4 t) {
+        TO* o = ob + (size_t)r * C;
+        stf<TO>(o, (t.x - mean) * rstd * gm.x + bt.x);
+        stf<TO>(o + 1, (t.y - mean) * rstd * gm.y + bt.y);
+        stf<TO>(o + 2, (t.z - mean) * rstd * gm.z + bt.z);
+        stf<TO>(o + 3, (t.w - mean) * rstd * gm.w + bt.w);
+    };
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+            if (slot + 32 * i < HW) emit(slot + 32 * i, v[i]);
+    } else {
+        for (int r = slot; r < HW; r += 32) emit(r, *reinterpret_cast<const float4*>(xb + (size_t)r * C));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- sine position embedding
 // reference models/dino/position_encoding.py:79-108 (+ level_embed, deformable_transformer.py:281-282).
 // mask [B,H,W] uint8 (1 = padding); out rows b*out_stride_b + (y*W+x), C = 2*npf channels: [pos_y | pos_x].
@@ -379,14 +467,17 @@ __global__ void enc_ref_kernel(const float* __restrict__ valid_ratios, float* __
 // ---------------------------------------------------------------------------------------------- two-stage proposals
 // reference models/dino/utils.py:15-64: anchor (cx,cy,w,h) per token, validity, logit; zeroes invalid/padded memory rows.
 // valid_hw [B, L, 2] = (valid_H, valid_W) counts from the level masks.
+// One warp per token (8 tokens per CTA), 16-byte loads / stores when the row allows: HBM bound (one read + one write of the memory).
 template <typename T>
-__global__ void proposals_kernel(const T* __restrict__ memory, const unsigned char* __restrict__ pad, const int* __restrict__ valid_hw,
-                                 T* __restrict__ out_memory, float* __restrict__ proposals, const __grid_constant__ PrepLevels lv,
-                                 int B, int S, int C, float default_hw) {
+__global__ void __launch_bounds__(256)
+proposals_kernel(const T* __restrict__ memory, const unsigned char* __restrict__ pad, const int* __restrict__ valid_hw,
+                 T* __restrict__ out_memory, float* __restrict__ proposals, const __grid_constant__ PrepLevels lv,
+                 int B, int S, int C, float default_hw) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long tok = blockIdx.x;
+    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tok >= (long long)B * S) return;
+    const int lane = threadIdx.x & 31;
     const int b = (int)(tok / S);
     int t = (int)(tok % S), l = 0;
     while (l < lv.n - 1 && t >= lv.H[l] * lv.W[l]) { t -= lv.H[l] * lv.W[l]; ++l; }
@@ -400,9 +491,17 @@ __global__ void proposals_kernel(const T* __restrict__ memory, const unsigned ch
 #pragma unroll
     for (int k = 0; k < 4; ++k) valid = valid && (p[k] > 0.01f) && (p[k] < 0.99f);
     const bool keep = valid && !pad[tok];
-    if (threadIdx.x < 4) proposals[tok * 4 + threadIdx.x] = keep ? logf(p[threadIdx.x] / (1.f - p[threadIdx.x])) : INFINITY;
-    for (int c = threadIdx.x; c < C; c += blockDim.x)
-        out_memory[tok * C + c] = keep ? memory[tok * C + c] : (T)0.f;
+    if (lane < 4) proposals[tok * 4 + lane] = keep ? logf(p[lane] / (1.f - p[lane])) : INFINITY;
+    const T* src = memory + (size_t)tok * C;
+    T* dst = out_memory + (size_t)tok * C;
+    if (((size_t)C * sizeof(T)) % 16 == 0 && ((((uintptr_t)memory) | ((uintptr_t)out_memory)) & 15) == 0) {
+        const int n16 = (int)((size_t)C * sizeof(T) / 16);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int i = lane; i < n16; i += 32) d4[i] = keep ? s4[i] : make_uint4(0, 0, 0, 0);
+    } else {
+        for (int c = lane; c < C; c += 32) dst[c] = keep ? src[c] : (T)0.f;
+    }
 }
 
 // row-wise max over the first N columns (two-stage class score, deformable_transformer.py:345)
@@ -718,6 +817,12 @@ extern "C" int dtlr_groupnorm(const float* x, const float* gamma, const float* b
                               long long out_stride_b, float eps, int out_dtype, void* stream) {
     DTLR_CHECK_ARG(C % G == 0, "groupnorm: C %% G != 0");
     if (B == 0 || HW == 0) return DTLR_OK;
+    if (C / G == 8 && (C % 32) == 0 && ((((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta)) & 15) == 0 && !(g_debug_flags & 524288)) {
+        dim3 grid8(C / 32, B);          // flag 524288: the one-CTA-per-group kernel (A/B)
+        DISPATCH_T(out_dtype, DTLR_LAUNCH((groupnorm8_kernel<T, 20>), grid8, 256, 0, (cudaStream_t)stream, x, gamma, beta, (T*)out, HW, C, out_stride_b, eps);)
+        DTLR_CHECK_LAUNCH();
+        return DTLR_OK;
+    }
     dim3 grid(G, B);
     DISPATCH_T(out_dtype, DTLR_LAUNCH((groupnorm_kernel<T>), grid, 256, 0, (cudaStream_t)stream, x, gamma, beta, (T*)out, HW, C, G, out_stride_b, eps);)
     DTLR_CHECK_LAUNCH();
@@ -798,7 +903,7 @@ extern "C" int dtlr_encoder_proposals(const void* memory, const unsigned char* p
     if (rc) return rc;
     const long long total = (long long)B * S;
     if (total == 0) return DTLR_OK;
-    DISPATCH_T(dtype, DTLR_LAUNCH((proposals_kernel<T>), (unsigned)total, 128, 0, (cudaStream_t)stream, (const T*)memory, pad, valid_hw, (T*)out_memory, proposals, lv, B, S, C, default_hw);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((proposals_kernel<T>), (unsigned)((total + 7) / 8), 256, 0, (cudaStream_t)stream, (const T*)memory, pad, valid_hw, (T*)out_memory, proposals, lv, B, S, C, default_hw);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
