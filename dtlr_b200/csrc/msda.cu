@@ -16,7 +16,7 @@
 //    construction; fp32 accumulation; butterfly "transpose" reduction leaves one output channel per lane.
 //  * slabs that do not fit in shared memory (large S) use the same code with the taps read through L1/L2.
 //  * generic path (any D, fp32/fp64): one warp per (b,q,m), lanes over channels.  Used by the fp64 KATs.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dtlr {
 
@@ -363,9 +363,13 @@ template <int MODE>
 __global__ void __launch_bounds__(MMA_NW * 32, 2)
 msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ loc_or_proj, const float* __restrict__ attn,
                     op16_t* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
-                    const int q_per_cta, const FusedArgs fz, const int vld) {
+                    const int q_per_cta, const FusedArgs fz, const int vld, const __grid_constant__ CUtensorMap tmV, const int tma_rows) {
     constexpr int P = 4, LP = 16;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem_base[];
+    // the slab starts 64 bytes into the allocation: pixel p lives at smem + (p + 1) * 64, so the first DATA row sits on a 128-byte
+    // boundary, which is what a TMA box destination needs (tma_rows > 0: the slab is staged by cp.async.bulk.tensor)
+    unsigned char* const smem = smem_base + 64;
+    __shared__ __align__(8) uint64_t slab_bar;
     const int b = blockIdx.z, m = blockIdx.y;
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(Lq, q0 + q_per_cta);
@@ -395,7 +399,21 @@ msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ l
     if (MODE == 2 && wq0 < wq1) stage_raw(wq0);
 
     // ---- stage the head's value slab: slab pixel p+1 = pixel p, pixels 0 and S+1 are zero padding
-    {
+    if (tma_rows > 0) {
+        // TMA: S / tma_rows boxes of (32 channels = 64 bytes) x tma_rows pixels from the (B*S, vld) value matrix, issued by one thread,
+        // completion on an mbarrier -- no per-thread address arithmetic, no register staging (the cp.async path issues S*4 copies)
+        if (tid == 0) {
+            mbar_init(&slab_bar, 1);
+            fence_barrier_init();
+            mbar_expect_tx(&slab_bar, (uint32_t)S * 64u);
+            for (int r0 = 0; r0 < S; r0 += tma_rows) tma_load_2d(smem + (size_t)(r0 + 1) * 64, &tmV, &slab_bar, m * 32, b * S + r0);
+        }
+        cp_async_commit();          // keeps the group numbering of the MODE 2 raw-row prefetch (an empty group completes at once)
+        if (tid < 8) {
+            const int row = (tid < 4) ? 0 : (S + 1);
+            *reinterpret_cast<uint4*>(smem + (size_t)row * 64 + (tid & 3) * 16) = make_uint4(0, 0, 0, 0);
+        }
+    } else {
         const unsigned char* gbase = reinterpret_cast<const unsigned char*>(value) + ((size_t)b * S * vld + (size_t)m * 32) * 2;
         const size_t gstride = (size_t)vld * 2;
         for (int i = tid; i < S * 4; i += MMA_NW * 32) {
@@ -548,7 +566,8 @@ msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ l
         }
         if (first) {
             cp_async_wait_all();
-            __syncthreads();
+            __syncthreads();                                     // (also: every thread now sees the initialised slab barrier)
+            if (tma_rows > 0) mbar_wait(&slab_bar, 0);           // the TMA boxes of the slab have landed
             first = false;
         } else {
             __syncwarp();
@@ -925,7 +944,7 @@ static int launch_fwd_d32_nw(const void* value, const void* loc, const void* att
 static bool mma_path_ok(const Levels& lv, int S, int P, const void* loc, const void* attn, const FusedArgs* fzp, int vld) {
     if (g_debug_flags & 16) return false;
     if (lv.n != 4 || P != 4 || S > 1023 || (vld % 8) != 0) return false;
-    if ((size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES > (size_t)max_smem_optin()) return false;
+    if (64 + (size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES > (size_t)max_smem_optin()) return false;
     if (fzp) {
         if ((fzp->ld % (fzp->proj_bf16 ? 8 : 4)) != 0) return false;
         if (((uintptr_t)fzp->ref & (fzp->RD == 4 ? 15 : 7)) != 0) return false;
@@ -937,7 +956,18 @@ static bool mma_path_ok(const Levels& lv, int S, int P, const void* loc, const v
 
 static int launch_fwd_mma(const void* value, const void* loc, const void* attn, void* out, const Levels& lv, int B, int S,
                           int M, int Lq, const FusedArgs* fzp, cudaStream_t st, int vld) {
-    const size_t smem = (size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES;
+    const size_t smem = 64 + (size_t)(S + 2) * 64 + (size_t)MMA_NW * MMA_TAB_BYTES;
+    // slab staging by TMA (north star: "TMA / shared-memory staging of per-level value tiles"): boxes of S / k pixels (k minimal with
+    // S % k == 0, S / k <= 256 and even, so that every box lands on a 128-byte boundary); otherwise, or with dtlr_debug_flags(2097152),
+    // the cp.async path
+    CUtensorMap tmv;
+    memset(&tmv, 0, sizeof(tmv));
+    int tma_rows = 0;
+    if (!(g_debug_flags & 2097152) && (((uintptr_t)value) & 15) == 0) {
+        for (int k = 1; k <= 16; ++k)
+            if (S % k == 0 && S / k <= 256 && ((S / k) % 2) == 0) { tma_rows = S / k; break; }
+        if (tma_rows && make_tmap_2d_bf16(&tmv, value, (long long)B * S, M * 32, vld, tma_rows, 32, CU_TENSOR_MAP_SWIZZLE_NONE) != DTLR_OK) tma_rows = 0;
+    }
     // one 32-query batch per warp where possible: ceil(Lq / 256) CTAs per (image, head); small problems are split further
     // (down to 64 queries per CTA) until the grid covers the machine twice
     int qsplit = (Lq + MMA_NW * 32 - 1) / (MMA_NW * 32);
@@ -949,7 +979,7 @@ static int launch_fwd_mma(const void* value, const void* loc, const void* attn, 
     auto k = mode == 0 ? msda_fwd_mma_kernel<0> : (mode == 1 ? msda_fwd_mma_kernel<1> : msda_fwd_mma_kernel<2>);
     DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(qsplit, M, B), block(MMA_NW * 32);
-    DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const op16_t*)value, loc, (const float*)attn, (op16_t*)out, lv, S, M, Lq, q_per_cta, fz, vld));
+    DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const op16_t*)value, loc, (const float*)attn, (op16_t*)out, lv, S, M, Lq, q_per_cta, fz, vld, tmv, tma_rows));
     return DTLR_OK;
 }
 
