@@ -184,21 +184,30 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
         }
 
         // ---- S = Q K^T for the 64 keys from kb: 8 n-blocks of 8 keys, each K fragment reused by the MT m-tiles
+        // (the last block of a line is mostly key padding -- Q = 900: 4 real keys + 60 zeros -- so its all-padding groups of 8 keys
+        //  are skipped here and in the softmax / P.V below: nb8 = groups of 8 keys with at least one real key, uniform per block)
         auto qk_block = [&](float (&sc)[MT][8][4], const int kb) {
+            const int nb8 = min(8, (Q - kb + 7) >> 3);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                uint32_t kf[4];
-                ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + k_row) * FA_PITCH + k_chunk * 8);
+                if (n < nb8) {
+                    uint32_t kf[4];
+                    ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + k_row) * FA_PITCH + k_chunk * 8);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
-                    mma_bf16_16816(sc[mt][n], qa[mt][0], kf[0], kf[1]);
-                    mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
+                        mma_bf16_16816(sc[mt][n], qa[mt][0], kf[0], kf[1]);
+                        mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = -INFINITY;
                 }
             }
         };
         // ---- masking of the key padding, online softmax, O += P V for the 64 keys from kb (scores in sc)
         auto softmax_pv = [&](float (&sc)[MT][8][4], const int kb) {
+            const int nb8 = min(8, (Q - kb + 7) >> 3);
             if (kb + 64 > Q) {    // key padding -> -inf
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -232,17 +241,23 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
                 const float ml = mx_lo * scale_log2, mh = mx_hi * scale_log2;
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                    const float p0 = ex2_approx(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = ex2_approx(fmaf(sc[mt][n][1], scale_log2, -ml));
-                    const float p2 = ex2_approx(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = ex2_approx(fmaf(sc[mt][n][3], scale_log2, -mh));
-                    l_lo[mt] += p0 + p1;
-                    l_hi[mt] += p2 + p3;
-                    pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
-                    pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
+                    if (n < nb8) {
+                        const float p0 = ex2_approx(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = ex2_approx(fmaf(sc[mt][n][1], scale_log2, -ml));
+                        const float p2 = ex2_approx(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = ex2_approx(fmaf(sc[mt][n][3], scale_log2, -mh));
+                        l_lo[mt] += p0 + p1;
+                        l_hi[mt] += p2 + p3;
+                        pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
+                        pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
+                    } else {                    // an all-padding group of 8 keys: P = 0
+                        pa[mt][n >> 1][(n & 1) * 2] = 0u;
+                        pa[mt][n >> 1][(n & 1) * 2 + 1] = 0u;
+                    }
                 }
             }
             // O += P V, each V fragment reused by the MT m-tiles
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
+                if (kk * 2 >= nb8) continue;        // 16 keys of pure padding: P is zero there
 #pragma unroll
                 for (int nn = 0; nn < 2; ++nn) {
                     uint32_t vf[4];

@@ -46,6 +46,8 @@ struct ConvGeo {
     int enabled;
     int Ho, Wo, KW, pad, cblocks;     // cblocks = C / 64
     int seg_w, nseg;                  // seg_w * nseg == 128, Wo % seg_w == 0
+    int stride;                       // 1, or 2: the A tensor map traverses W and H with this element stride (TMA loads every
+                                      // stride-th pixel of a box that spans seg_w * stride input pixels)
 };
 
 // optional LayerNorm fused into the epilogue of a full-row (N == 256 == BN) bf16 GEMM:
@@ -299,7 +301,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             const int hw = cg.Ho * cg.Wo;
                             const int bimg = p / hw, rem = p - bimg * hw;
                             const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
-                            tma_load_4d(sa + (size_t)j * cg.seg_w * (GEMM_BK * 2), &tmA, &full_bar[s], c0, wo + kw - cg.pad, ho + kh - cg.pad, bimg);
+                            tma_load_4d(sa + (size_t)j * cg.seg_w * (GEMM_BK * 2), &tmA, &full_bar[s], c0, wo * cg.stride + kw - cg.pad,
+                                        ho * cg.stride + kh - cg.pad, bimg);
                         }
                     } else {
                         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
@@ -844,7 +847,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, int rows, int cols
 }
 
 // 4-D bf16 tensor map over NHWC activations: dims (C, W, H, B), box (64 channels, seg_w pixels, 1, 1), 128B swizzle
-static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int W, int C, int seg_w) {
+static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int W, int C, int seg_w, int stride = 1) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -852,8 +855,9 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)GEMM_BK, (cuuint32_t)seg_w, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // traversal stride s in W and H: a box spanning seg_w * s input pixels delivers ceil(seg_w * s / s) = seg_w of them
+    cuuint32_t box[4] = {(cuuint32_t)GEMM_BK, (cuuint32_t)(seg_w * stride), 1, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = enc(map, DTLR_TMAP_OP16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -979,7 +983,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
     DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
-    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
+    GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0, 1}, g_debug_flags};
     if (in_dtype == DTLR_F32) {
         DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
         dim3 grid((M + 63) / 64, (N + 63) / 64);
@@ -1030,7 +1034,7 @@ extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, cons
     DTLR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && (ldy % 8) == 0 && (!residual || (ldr % 8) == 0) && (!Y2 || (ld2 % 8) == 0) &&
                    ((((uintptr_t)A | (uintptr_t)W | (uintptr_t)Y | (uintptr_t)residual | (uintptr_t)add2 | (uintptr_t)Y2)) & 15) == 0,
                    "gemm_ln: operands need 16-byte aligned rows");
-    GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0}, g_debug_flags};
+    GemmEpi e{bias, residual, Y, ldr, ldy, M, N, K, 0, LnArgs{gamma, beta, add2, Y2, ld2, eps}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0, 1}, g_debug_flags};
     // K <= 256: weight-stationary kernel; otherwise the tile kernel -- both end in ln_epilogue_tile (TMA stores)
     if (K <= 256 && (long long)((M + GEMM_BM - 1) / GEMM_BM) >= 2ll * sm_count() && !(g_debug_flags & 32))
         return launch_ws<256, op16_t, false, true>(A, lda, W, ldw, e, (cudaStream_t)stream);
@@ -1046,11 +1050,24 @@ extern "C" int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, cons
 
 // Convolution (stride 1, "same" padding) on NHWC bf16 activations as an implicit GEMM on the tcgen05 kernel above: no im2col
 // matrix ever exists; the k x k taps are TMA loads with shifted coordinates and hardware zero fill.
+extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int Hin,
+                                        int Win, int C, int Cout, int KH, int KW, int pad, int stride, int relu, int out_dtype, void* stream);
 extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int H,
                                 int W, int C, int Cout, int KH, int KW, int pad, int relu, int out_dtype, void* stream) {
+    return dtlr_conv2d_nhwc_strided(x, w, bias, residual, out, B, H, W, C, Cout, KH, KW, pad, 1, relu, out_dtype, stream);
+}
+
+// The same implicit GEMM for stride 1 or 2 (ResNet's stride-2 3x3 convs and strided 1x1 downsample convs, torchvision Bottleneck
+// v1.5 as built by reference models/dino/backbone.py:118-120): the A tensor map traverses W and H with element stride 2, so the
+// producer's per-tap TMA boxes deliver exactly the input pixels of 128 consecutive output pixels -- no im2col matrix (round 1 wrote
+// and re-read a 9x larger A for these six convs).  H, W are the INPUT sizes; output (H + 2 pad - KH) / stride + 1.
+extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int Hin,
+                                        int Win, int C, int Cout, int KH, int KW, int pad, int stride, int relu, int out_dtype, void* stream) {
     DTLR_CHECK_ARG(x && w && out, "conv2d_nhwc: null pointer");
-    DTLR_CHECK_ARG(KH == 2 * pad + 1 && KW == 2 * pad + 1, "conv2d_nhwc: only stride-1 'same' convolutions (k = 2*pad+1)");
+    DTLR_CHECK_ARG(stride == 1 || stride == 2, "conv2d_nhwc: stride must be 1 or 2");
+    DTLR_CHECK_ARG(KH == 2 * pad + 1 && KW == 2 * pad + 1, "conv2d_nhwc: only 'same'-padded kernels (k = 2*pad+1)");
     DTLR_CHECK_ARG(C % 64 == 0, "conv2d_nhwc: C must be a multiple of 64 (got %d)", C);
+    const int H = (Hin + 2 * pad - KH) / stride + 1, W = (Win + 2 * pad - KW) / stride + 1;       // output size
     int seg_w = W >= 128 ? 128 : W;
     DTLR_CHECK_ARG(seg_w >= 8 && (128 % seg_w) == 0 && (W % seg_w) == 0,
                    "conv2d_nhwc: output width %d cannot be tiled into 128-pixel row segments (use im2col + gemm)", W);
@@ -1058,10 +1075,10 @@ extern "C" int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias,
     DTLR_CHECK_ARG(out_dtype == DTLR_OP16, "conv2d_nhwc: bf16 output only");
     const int M = B * H * W, K = KH * KW * C;
     if (M == 0) return DTLR_OK;
-    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w}, g_debug_flags};
+    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w, stride}, g_debug_flags};
     CUtensorMap ta, tb;
     int rc;
-    if ((rc = make_tmap_nhwc(&ta, x, B, H, W, C, seg_w))) return rc;
+    if ((rc = make_tmap_nhwc(&ta, x, B, Hin, Win, C, seg_w, stride))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // tile width by SM fill: 128 x 256 tiles halve the A traffic per FLOP, but the deep stages have few rows (layer4: M = 4096 = 32
     // row tiles x 2 column tiles of 256 = 64 CTAs on 148 SMs).  cost(BN) = rounds of CTAs x BN; a narrower tile is taken only when it

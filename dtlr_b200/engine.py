@@ -174,13 +174,17 @@ class InferenceEngine:
             a = ops.gemm(y, *blk["c1"], relu=1)
             planes = blk["c1"][0].shape[0]
             if ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
-                bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1), Hc, Wc
+                bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1, stride=s)
             else:
                 col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
                 bmid = ops.gemm(col, *blk["c2"], relu=1)
             if blk["ds"] is not None:
-                sub = y if s == 1 else ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0]
-                idt = ops.gemm(sub, *blk["ds"])
+                if s == 1:
+                    idt = ops.gemm(y, *blk["ds"])
+                elif ops.conv2d_nhwc_supported(y, Hc, Wc, cin, 1, s):      # strided 1x1 downsample: TMA traversal stride, no gather pass
+                    idt = ops.conv2d_nhwc(y, *blk["ds"], B, Hc, Wc, cin, 1, 0, stride=s)[0]
+                else:
+                    idt = ops.gemm(ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0], *blk["ds"])
             else:
                 idt = y
             y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2)

@@ -71,18 +71,28 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
     return out, Ho, Wo
 
 
+CONV_STRIDED_IMPLICIT = _os.environ.get("DTLR_CONV_STRIDED_IMPLICIT", "1") != "0"
+
+
 def conv2d_nhwc_supported(x, H, W, C, k, stride):
-    seg = 128 if W >= 128 else W
-    return (x.dtype in HALF and stride == 1 and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and W % seg == 0)
+    """implicit-GEMM conv (csrc/gemm.cu): 16-bit NHWC, 'same' padding k = 2*pad+1, stride 1 or 2, C % 64 == 0 and an OUTPUT width that
+    tiles into 128-pixel row segments"""
+    if stride not in (1, 2) or (stride == 2 and not CONV_STRIDED_IMPLICIT):
+        return False
+    Wo = (W + 2 * (k // 2) - k) // stride + 1
+    seg = 128 if Wo >= 128 else Wo
+    return (x.dtype in HALF and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and Wo % seg == 0)
 
 
-def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None):
-    """stride-1 'same' conv as implicit GEMM: x bf16 [B*H*W, C] NHWC, w bf16 [Cout, k*k*C] -> bf16 [B*H*W, Cout]"""
+def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None, stride=1):
+    """'same'-padded k x k conv with stride 1 or 2 as implicit GEMM: x 16-bit [B*H*W, C] NHWC, w 16-bit [Cout, k*k*C] ->
+    16-bit [B*Ho*Wo, Cout]; returns (out, Ho, Wo)"""
     Cout = w.shape[0]
-    out = torch.empty((B * H * W, Cout), dtype=x.dtype, device=x.device)
-    _call("dtlr_conv2d_nhwc", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(relu),
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty((B * Ho * Wo, Cout), dtype=x.dtype, device=x.device)
+    _call("dtlr_conv2d_nhwc_strided", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(stride), int(relu),
           L.dtype_code(out), _st(x))
-    return out
+    return out, Ho, Wo
 
 
 def stem_conv(x, w_khkwcico, bias, B, H, W, out_dtype):

@@ -134,6 +134,11 @@ int dtlr_im2col(const void* x, void* out, int B, int H, int W, int C, int KH, in
  * (the 3x3 conv2 of every torchvision Bottleneck, models/dino/backbone.py:109-128) */
 int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int H, int W,
                      int C, int Cout, int KH, int KW, int pad, int relu, int out_dtype, void* stream);
+/* The same for stride 1 or 2 (the stride-2 3x3 conv2 and the strided 1x1 downsample of the first Bottleneck of layer2-4): the A tensor
+ * map traverses W and H with element stride 2, so no im2col matrix is built.  Hin, Win: INPUT size; output (Hin + 2 pad - KH) / stride
+ * + 1 by (Win + 2 pad - KW) / stride + 1, its width subject to the tiling rule above; residual / out [B*Hout*Wout, Cout]. */
+int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int Hin,
+                             int Win, int C, int Cout, int KH, int KW, int pad, int stride, int relu, int out_dtype, void* stream);
 /* ResNet stem: conv1 7x7/s2/p3 (3->64) + folded FrozenBatchNorm + ReLU, direct (no im2col): x fp32 NCHW [B,3,H,W],
  * w fp32 [7][7][3][64] (BN scale folded), bias fp32 [64] -> out NHWC [B*Ho*Wo, 64] of out_dtype.
  * (torchvision resnet50.conv1/bn1/relu as wrapped by models/dino/backbone.py:109-128, FrozenBatchNorm2d :62-72) */

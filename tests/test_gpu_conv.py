@@ -25,15 +25,41 @@ def test_implicit_gemm_conv3x3(B, H, W, C, Cout):
     xb = x.permute(0, 2, 3, 1).reshape(B * H * W, C).bfloat16().contiguous()
     wb = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).bfloat16().contiguous()
     assert ops.conv2d_nhwc_supported(xb, H, W, C, 3, 1)
-    out = ops.conv2d_nhwc(xb, wb, bias, B, H, W, C, 3, 1, relu=1)
+    out, Ho, Wo = ops.conv2d_nhwc(xb, wb, bias, B, H, W, C, 3, 1, relu=1)
+    assert (Ho, Wo) == (H, W)
     ref = F.relu(F.conv2d(xb.float().view(B, H, W, C).permute(0, 3, 1, 2), wb.float().view(Cout, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1))
     ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
     assert (out.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
     res = torch.randn(B * H * W, Cout, device="cuda", generator=g).bfloat16()
-    out2 = ops.conv2d_nhwc(xb, wb, bias, B, H, W, C, 3, 1, relu=2, residual=res)
+    out2 = ops.conv2d_nhwc(xb, wb, bias, B, H, W, C, 3, 1, relu=2, residual=res)[0]
     ref2 = F.relu(F.conv2d(xb.float().view(B, H, W, C).permute(0, 3, 1, 2), wb.float().view(Cout, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1)
                   .permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res.float())
     assert (out2.float() - ref2).abs().max().item() / ref2.abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,k", [(2, 10, 256, 128, 128, 3), (3, 5, 128, 256, 256, 3), (5, 3, 64, 512, 512, 3), (64, 10, 256, 128, 128, 3),
+                                            (2, 10, 256, 256, 512, 1), (3, 5, 128, 512, 1024, 1), (4, 3, 64, 1024, 2048, 1), (2, 4, 64, 64, 64, 3)])
+def test_strided_implicit_gemm_conv(B, H, W, C, Cout, k):
+    """stride-2 'same'-padded convs of the first Bottleneck of layer2-4 (3x3 conv2 and the 1x1 downsample) as implicit GEMMs: the A
+    tensor map traverses W and H with element stride 2 (dtlr_conv2d_nhwc_strided) -- against torch conv2d and, exactly, against the
+    im2col + GEMM path it replaces (odd heights: 5 -> 3, 3 -> 2 with the bottom padding row)"""
+    from dtlr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * H + W + k)
+    pad = k // 2
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, C, k, k, device="cuda", generator=g) / (k * k * C) ** 0.5
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    xb = x.permute(0, 2, 3, 1).reshape(B * H * W, C).bfloat16().contiguous()
+    wb = w.permute(0, 2, 3, 1).reshape(Cout, k * k * C).bfloat16().contiguous()
+    assert ops.conv2d_nhwc_supported(xb, H, W, C, k, 2)
+    out, Ho, Wo = ops.conv2d_nhwc(xb, wb, bias, B, H, W, C, k, pad, relu=1, stride=2)
+    ref = F.relu(F.conv2d(xb.float().view(B, H, W, C).permute(0, 3, 1, 2), wb.float().view(Cout, k, k, C).permute(0, 3, 1, 2), bias, stride=2, padding=pad))
+    assert (Ho, Wo) == tuple(ref.shape[-2:])
+    ref = ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Cout)
+    assert (out.float() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
+    col, Ho2, Wo2 = ops.im2col(xb, B, H, W, C, k, k, 2, pad, torch.bfloat16)
+    old = ops.gemm(col, wb, bias, relu=1)
+    assert (Ho2, Wo2) == (Ho, Wo) and (out.float() - old.float()).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
