@@ -117,8 +117,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // shuffle chain of the softmax.  Measured SLOWER on B200 (B=64, Q=900: 281.6 us vs 255.4 us un-pipelined, same box): the second
 // score array takes the kernel from 86 to 128 registers (the cap at 512 threads) with 60 bytes of spills, and ptxas already
 // interleaves the P.V MMAs with the exponentials of the same block -- the four warps per scheduler cover the rest.
-template <int MT, bool PIPE>
-__global__ void __launch_bounds__(FA_WARPS_MAX * 32)
+// MAXW: the launch bound in warps -- 16 (86 registers, no spills) for CTAs of up to 16 warps, 20 (96 registers + 40 bytes of spills under
+// the 102-register cap of 640 threads) only when the partition really asks for more than 16 warps
+template <int MT, bool PIPE, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32)
 mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const op16_t* __restrict__ v, int ld_v,
                       op16_t* __restrict__ out, int ld_o, int Q, int q_per_cta, float scale_log2) {
     extern __shared__ __align__(16) unsigned char fa_smem[];
@@ -184,30 +186,23 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
         }
 
         // ---- S = Q K^T for the 64 keys from kb: 8 n-blocks of 8 keys, each K fragment reused by the MT m-tiles
-        // (the last block of a line is mostly key padding -- Q = 900: 4 real keys + 60 zeros -- so its all-padding groups of 8 keys
-        //  are skipped here and in the softmax / P.V below: nb8 = groups of 8 keys with at least one real key, uniform per block)
+        // (tried in round 2: skipping the all-padding groups of 8 keys of the last block -- Q = 900: 4 real keys + 60 zeros -- with
+        //  uniform predicates here and in the softmax / P.V: 86 -> 95 registers and 240 -> 301 us per layer on B200; reverted)
         auto qk_block = [&](float (&sc)[MT][8][4], const int kb) {
-            const int nb8 = min(8, (Q - kb + 7) >> 3);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                if (n < nb8) {
-                    uint32_t kf[4];
-                    ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + k_row) * FA_PITCH + k_chunk * 8);
+                uint32_t kf[4];
+                ldmatrix_x4(kf, Ks + (size_t)(kb + n * 8 + k_row) * FA_PITCH + k_chunk * 8);
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
-                        mma_bf16_16816(sc[mt][n], qa[mt][0], kf[0], kf[1]);
-                        mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = -INFINITY;
+                for (int mt = 0; mt < MT; ++mt) {
+                    sc[mt][n][0] = sc[mt][n][1] = sc[mt][n][2] = sc[mt][n][3] = 0.f;
+                    mma_bf16_16816(sc[mt][n], qa[mt][0], kf[0], kf[1]);
+                    mma_bf16_16816(sc[mt][n], qa[mt][1], kf[2], kf[3]);
                 }
             }
         };
         // ---- masking of the key padding, online softmax, O += P V for the 64 keys from kb (scores in sc)
         auto softmax_pv = [&](float (&sc)[MT][8][4], const int kb) {
-            const int nb8 = min(8, (Q - kb + 7) >> 3);
             if (kb + 64 > Q) {    // key padding -> -inf
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -241,23 +236,17 @@ mha_flash_bf16_kernel(const op16_t* __restrict__ qk, int ld_qk, int k_off, const
                 const float ml = mx_lo * scale_log2, mh = mx_hi * scale_log2;
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                    if (n < nb8) {
-                        const float p0 = ex2_approx(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = ex2_approx(fmaf(sc[mt][n][1], scale_log2, -ml));
-                        const float p2 = ex2_approx(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = ex2_approx(fmaf(sc[mt][n][3], scale_log2, -mh));
-                        l_lo[mt] += p0 + p1;
-                        l_hi[mt] += p2 + p3;
-                        pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
-                        pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
-                    } else {                    // an all-padding group of 8 keys: P = 0
-                        pa[mt][n >> 1][(n & 1) * 2] = 0u;
-                        pa[mt][n >> 1][(n & 1) * 2 + 1] = 0u;
-                    }
+                    const float p0 = ex2_approx(fmaf(sc[mt][n][0], scale_log2, -ml)), p1 = ex2_approx(fmaf(sc[mt][n][1], scale_log2, -ml));
+                    const float p2 = ex2_approx(fmaf(sc[mt][n][2], scale_log2, -mh)), p3 = ex2_approx(fmaf(sc[mt][n][3], scale_log2, -mh));
+                    l_lo[mt] += p0 + p1;
+                    l_hi[mt] += p2 + p3;
+                    pa[mt][n >> 1][(n & 1) * 2] = pack_bf16(p0, p1);
+                    pa[mt][n >> 1][(n & 1) * 2 + 1] = pack_bf16(p2, p3);
                 }
             }
             // O += P V, each V fragment reused by the MT m-tiles
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                if (kk * 2 >= nb8) continue;        // 16 keys of pure padding: P is zero there
 #pragma unroll
                 for (int nn = 0; nn < 2; ++nn) {
                     uint32_t vf[4];
@@ -355,7 +344,8 @@ extern "C" int dtlr_mha_self_attention(const void* qk, int ld_qk, int k_off, con
         W = W < 1 ? 1 : (W > FA_WARPS_MAX ? FA_WARPS_MAX : W);
         int q_per_cta = ((T + splits - 1) / splits) * 16 * FA_MT;
         dim3 fgrid((Q + q_per_cta - 1) / q_per_cta, heads, B);
-        auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, true> : mha_flash_bf16_kernel<FA_MT, false>;   // flag 16384: QK-pipelined variant (A/B)
+        auto kern = (g_debug_flags & 16384) ? mha_flash_bf16_kernel<FA_MT, true, FA_WARPS_MAX>              // flag 16384: QK-pipelined variant (A/B)
+                                            : (W <= 16 ? mha_flash_bf16_kernel<FA_MT, false, 16> : mha_flash_bf16_kernel<FA_MT, false, FA_WARPS_MAX>);
         DTLR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DTLR_CHECK_CUDA(launch_pdl(kern, fgrid, dim3(W * 32), smem, st, (const op16_t*)qk, ld_qk, k_off,
                                    (const op16_t*)v, ld_v, (op16_t*)out, ld_o, Q, q_per_cta, scale * 1.4426950408889634f));
