@@ -284,19 +284,48 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
+                // implicit-GEMM conv: the (image, row, column) of every pixel run of the tile is fixed for the whole K loop and the tap
+                // (kh, kw, channel block) advances by counters -- round 1 recomputed both with ~8 integer divisions per k-step on this
+                // single producer thread, which made the producer the bottleneck of the deep convs (layer4: 0.85 us per k-step against
+                // 0.11 us of MMA; ncu: L2 / tensor pipe / l1tex all below 17 %)
+                const ConvGeo& cg = e.conv;
+                int seg_x[4], seg_y[4], seg_b[4], nvalid = 0, ck = 0, ckw = 0, ckh = 0;        // (registers: every loop over them is unrolled)
+                const bool hoisted = cg.enabled && cg.nseg <= 4;
+                if (hoisted) {
+                    const int hw = cg.Ho * cg.Wo;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = m0 + j * cg.seg_w;
+                        seg_b[j] = seg_y[j] = seg_x[j] = 0;
+                        if (j < cg.nseg && p < e.M) {
+                            const int bimg = p / hw, rem = p - bimg * hw;
+                            const int ho = rem / cg.Wo;
+                            seg_b[j] = bimg; seg_y[j] = ho * cg.stride - cg.pad; seg_x[j] = (rem - ho * cg.Wo) * cg.stride - cg.pad;
+                            nvalid = j + 1;
+                        }
+                    }
+                }
+                const uint32_t conv_tx = (uint32_t)(nvalid * cg.seg_w * GEMM_BK * 2 + S::B_BYTES);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);                   // slot free (first lap passes immediately)
                     unsigned char* sa = smem + s * S::STAGE_BYTES;
-                    if (e.conv.enabled) {
-                        const ConvGeo& cg = e.conv;
+                    if (hoisted) {
+                        mbar_expect_tx(&full_bar[s], conv_tx);
+                        const int c0 = ck * GEMM_BK;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < nvalid)
+                                tma_load_4d(sa + (size_t)j * cg.seg_w * (GEMM_BK * 2), &tmA, &full_bar[s], c0, seg_x[j] + ckw, seg_y[j] + ckh, seg_b[j]);
+                        if (++ck == cg.cblocks) { ck = 0; if (++ckw == cg.KW) { ckw = 0; ++ckh; } }
+                    } else if (cg.enabled) {                            // narrow maps (more than 4 pixel runs per tile): per-step arithmetic
                         const int kpos = kb / cg.cblocks, c0 = (kb - kpos * cg.cblocks) * GEMM_BK;
                         const int kh = kpos / cg.KW, kw = kpos - kh * cg.KW;
-                        int nvalid = 0;
-                        for (int j = 0; j < cg.nseg; ++j) nvalid += (m0 + j * cg.seg_w < e.M) ? 1 : 0;
-                        mbar_expect_tx(&full_bar[s], (uint32_t)(nvalid * cg.seg_w * GEMM_BK * 2 + S::B_BYTES));
-                        for (int j = 0; j < nvalid; ++j) {
+                        int nv = 0;
+                        for (int j = 0; j < cg.nseg; ++j) nv += (m0 + j * cg.seg_w < e.M) ? 1 : 0;
+                        mbar_expect_tx(&full_bar[s], (uint32_t)(nv * cg.seg_w * GEMM_BK * 2 + S::B_BYTES));
+                        for (int j = 0; j < nv; ++j) {
                             const int p = m0 + j * cg.seg_w;
                             const int hw = cg.Ho * cg.Wo;
                             const int bimg = p / hw, rem = p - bimg * hw;
