@@ -359,7 +359,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(const float lo, const float h
 
 // MODE 0: sampling locations / attention weights given (fp32 tensors of the operator boundary)
 // MODE 1: fused prologue, fp32 projection rows;  MODE 2: fused prologue, bf16 projection rows
-template <int MODE>
+// QU: queries per phase-2 iteration (loop unroll): QU independent ldmatrix -> mma chains in flight per warp; all variants stay
+// within the 128-register budget of 2 CTAs per SM
+template <int MODE, int QU>
 __global__ void __launch_bounds__(MMA_NW * 32, 2)
 msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ loc_or_proj, const float* __restrict__ attn,
                     op16_t* __restrict__ out, const __grid_constant__ Levels lv, const int S, const int M, const int Lq,
@@ -576,6 +578,7 @@ msda_fwd_mma_kernel(const op16_t* __restrict__ value, const void* __restrict__ l
 
         // =============================== phase 2: one query at a time, 8 x (ldmatrix.x4.trans + mma)
         const int nq = min(32, wq1 - qb);
+#pragma unroll (QU)
         for (int jq = 0; jq < nq; ++jq) {
             const unsigned char* t = tab + jq * MMA_TSTRIDE;
             const uint4 o4 = *reinterpret_cast<const uint4*>(t + tab_o);
@@ -976,7 +979,12 @@ static int launch_fwd_mma(const void* value, const void* loc, const void* attn, 
     qsplit = (Lq + q_per_cta - 1) / q_per_cta;
     const FusedArgs fz = fzp ? *fzp : FusedArgs{nullptr, nullptr, 0, 0, 0};
     const int mode = !fzp ? 0 : (fzp->proj_bf16 ? 2 : 1);
-    auto k = mode == 0 ? msda_fwd_mma_kernel<0> : (mode == 1 ? msda_fwd_mma_kernel<1> : msda_fwd_mma_kernel<2>);
+    // dtlr_debug_flags 4194304 / 8388608: one / four queries per phase-2 iteration instead of two (A/B)
+    const int qu = (g_debug_flags & 4194304) ? 1 : ((g_debug_flags & 8388608) ? 4 : 2);
+    auto pick = [&](auto k1, auto k2, auto k4) { return qu == 1 ? k1 : (qu == 4 ? k4 : k2); };
+    auto k = mode == 0 ? pick(msda_fwd_mma_kernel<0, 1>, msda_fwd_mma_kernel<0, 2>, msda_fwd_mma_kernel<0, 4>)
+                       : (mode == 1 ? pick(msda_fwd_mma_kernel<1, 1>, msda_fwd_mma_kernel<1, 2>, msda_fwd_mma_kernel<1, 4>)
+                                    : pick(msda_fwd_mma_kernel<2, 1>, msda_fwd_mma_kernel<2, 2>, msda_fwd_mma_kernel<2, 4>));
     DTLR_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(qsplit, M, B), block(MMA_NW * 32);
     DTLR_CHECK_CUDA(launch_pdl(k, grid, block, smem, st, (const op16_t*)value, loc, (const float*)attn, (op16_t*)out, lv, S, M, Lq, q_per_cta, fz, vld, tmv, tma_rows));
