@@ -67,7 +67,7 @@ def run_fused(B=64, Lq=912, ref_dim=2, iters=20, kernel="default"):
         ref[:, 2:] *= 0.3
     vr = torch.ones(B, L, 2, device="cuda")
     out = torch.empty(B, Lq, M * D, device="cuda", dtype=torch.bfloat16)
-    _lib.lib().dtlr_debug_flags({"simt": 16, "qu1": 4194304, "qu4": 8388608, "cpasync": 2097152, "cpasync_qu1": 2097152 + 4194304}.get(kernel, 0))
+    _lib.lib().dtlr_debug_flags({"simt": 16, "qu1": 4194304, "qu2": 8388608, "cpasync": 2097152, "cpasync_qu1": 2097152 + 4194304}.get(kernel, 0))
     us = _time(lambda: msda.msda_forward_fused(value, sh, ls, n, proj, ref, vr, Lq, P, out), iters)
     _lib.lib().dtlr_debug_flags(0)
     # algorithmic bytes (SURVEY 8d with bf16 value/out, and the projection rows + reference points instead of loc / weights)
@@ -78,7 +78,7 @@ def run_fused(B=64, Lq=912, ref_dim=2, iters=20, kernel="default"):
 
 
 if __name__ == "__main__":
-    for kern in ("default", "qu1", "qu4", "cpasync", "cpasync_qu1"):      # phase-2 unroll 2 (default) / 1 / 4; slab by TMA (default) / cp.async
+    for kern in ("default", "qu1", "qu2", "cpasync", "cpasync_qu1"):      # phase-2 unroll 4 (default) / 1 / 2; slab by TMA (default) / cp.async
         run_fused(Lq=912, ref_dim=2, kernel=kern)
         run_fused(Lq=900, ref_dim=4, kernel=kern)
     for kern in ("default", "simt"):
