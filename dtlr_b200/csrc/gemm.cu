@@ -961,8 +961,8 @@ static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi
         if ((e.N % 128) == 0) bn = 128;
         else if ((e.N % 64) == 0) bn = 64;
     } else {
-        if ((e.N % 256) == 0) bn = 256;
-        else if ((e.N % 192) == 0) bn = 192;
+        if ((e.N % 256) == 0 && !(g_debug_flags & 16777216)) bn = 256;       // flag 16777216: 128-wide slices (8 A stages instead of 4), A/B
+        else if ((e.N % 192) == 0 && !(g_debug_flags & 33554432)) bn = 192;  // flag 33554432: N = 384 as 3 x 128 instead of 2 x 192
         else if ((e.N % 128) == 0) bn = 128;
         else if ((e.N % 64) == 0) bn = 64;
         else if (e.N <= 256 && e.N > 16) bn = (e.N + 63) / 64 * 64;          // one ragged slice (e.g. the 166-class heads)
