@@ -328,44 +328,55 @@ __global__ void pos_sine_kernel(const unsigned char* __restrict__ mask, const fl
 // reference nn.LayerNorm(256) eps 1e-5 after every attention / FFN block (deformable_transformer.py:813-814,806-807,
 // 906-907,956-957,878-879), enc_output_norm (:326) and decoder.norm (:758).  One warp per row, 8 channels per lane.
 // y = LN(x (+ res)); optional second output y2 = y + add2 (the "+pos" query of the next block).
-template <typename T>
-__global__ void add_layernorm256_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, T* __restrict__ y, const T* __restrict__ add2,
-                                        T* __restrict__ y2, int rows, float eps) {
+// R consecutive rows per warp: all of their loads (x, res, add2) are issued before the first reduction, so a warp keeps R (x 2-3)
+// 512-byte rows in flight -- with one row per warp the kernel ran at ~55 % of the copy bandwidth (latency bound).
+template <typename T, int R>
+__global__ void __launch_bounds__(256)
+add_layernorm256_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, T* __restrict__ y, const T* __restrict__ add2,
+                        T* __restrict__ y2, int rows, float eps) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= rows) return;
     const int lane = threadIdx.x & 31;
-    const size_t off = (size_t)row * 256 + lane * 8;
-    float v[8];
-    ld8<T>(x + off, v);
-    if (res) {
-        float r[8];
-        ld8<T>(res + off, r);
+    float v[R][8], a[R][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] += r[k];
+    for (int i = 0; i < R; ++i) {
+        const size_t off = (size_t)min(row0 + i, rows - 1) * 256 + lane * 8;
+        ld8<T>(x + off, v[i]);
+        if (res) {
+            float r[8];
+            ld8<T>(res + off, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i][k] += r[k];
+        }
+        if (y2) ld8<T>(add2 + off, a[i]);
     }
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += v[k];
-    const float mean = warp_sum_f(s) * (1.f / 256.f);
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; ss += d * d; }
-    const float rstd = rsqrtf(warp_sum_f(ss) * (1.f / 256.f) + eps);
-    float g[8], bt[8], o[8];
+    float g[8], bt[8];
     ld8<float>(gamma + lane * 8, g);
     ld8<float>(beta + lane * 8, bt);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = (v[k] - mean) * rstd * g[k] + bt[k];
-    st8<T>(y + off, o);
-    if (y2) {
-        float a[8];
-        ld8<T>(add2 + off, a);
+    for (int i = 0; i < R; ++i) {
+        if (row0 + i >= rows) break;
+        const size_t off = (size_t)(row0 + i) * 256 + lane * 8;
+        float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] += o[k];
-        st8<T>(y2 + off, a);
+        for (int k = 0; k < 8; ++k) s += v[i][k];
+        const float mean = warp_sum_f(s) * (1.f / 256.f);
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; ss += d * d; }
+        const float rstd = rsqrtf(warp_sum_f(ss) * (1.f / 256.f) + eps);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[k] + bt[k];
+        st8<T>(y + off, o);
+        if (y2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[i][k] += o[k];
+            st8<T>(y2 + off, a[i]);
+        }
     }
 }
 
@@ -843,8 +854,14 @@ extern "C" int dtlr_add_layernorm(const void* x, const void* res, const float* g
     DTLR_CHECK_ARG(C == 256, "add_layernorm: only C=256 (d_model of every DTLR config) is implemented, got %d", C);
     if (rows == 0) return DTLR_OK;
     const int wpb = 8;
+    if (rows >= 4096 && !(g_debug_flags & 67108864)) {       // two rows per warp (flag 67108864: one, A/B)
+        const unsigned grid2 = (unsigned)((rows + 2 * wpb - 1) / (2 * wpb));
+        DISPATCH_T(dtype, DTLR_LAUNCH((add_layernorm256_kernel<T, 2>), grid2, wpb * 32, 0, (cudaStream_t)stream, (const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
+        DTLR_CHECK_LAUNCH();
+        return DTLR_OK;
+    }
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    DISPATCH_T(dtype, DTLR_LAUNCH((add_layernorm256_kernel<T>), grid, wpb * 32, 0, (cudaStream_t)stream, (const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((add_layernorm256_kernel<T, 1>), grid, wpb * 32, 0, (cudaStream_t)stream, (const T*)x, (const T*)res, gamma, beta, (T*)y, (const T*)add2, (T*)y2, (int)rows, eps);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
