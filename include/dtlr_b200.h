@@ -287,6 +287,43 @@ int dtlr_match_cost(const float* logits, const float* boxes, const int64_t* tgt_
                     float alpha, float* cost, void* stream);
 int dtlr_lsap(const float* cost, int P, int B, int Q, const int* t_cnt, int Tmax, int* q_of_t, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward half of the fine-tune step (engine.py:172-274 train_one_epoch_CTC: loss.backward(), clip_grad_norm_(0.01), AdamW.step;
+ * finetuning.py:211-231).  The reference gets these from torch autograd over cuBLAS / ATen; here (csrc/train.cu):
+ *
+ * dtlr_wgrad: dW[n,k] += sum_r dY[r,n] * X[r,k] -- the weight gradient of every nn.Linear (and 1x1 conv on NHWC rows).  dY [rows, ldy]
+ *   (N used), X [rows, ldx] (K used) of `dtype` (the library's 16-bit type: tcgen05 with both operands MN-major, read in place; F32:
+ *   exact SIMT), dW fp32 [N, ldw], ACCUMULATED with atomic reductions (the caller zeroes the gradient arena once per step; shared
+ *   heads accumulate over their uses).  The dgrad dX = dY . W is dtlr_gemm(dY, W^T) against the transposed operand copy below.
+ * dtlr_colsum: out[c] += sum of column c over nseg segments of seg_rows rows, segment s starting at row s*seg_stride (bias gradients:
+ *   one segment; per-level sums for level_embed: nseg = B, seg_stride = S).  x [.., ld] of `dtype`, out fp32 [N].
+ * dtlr_layernorm_bwd: nn.LayerNorm(256) backward from the saved pre-norm rows z (`dtype`), dy (+ dy2, may be NULL) fp32; dz32 (fp32)
+ *   and / or dz16 (`dtype`) receive dz, dgamma / dbeta fp32 [256] are accumulated (any of the four may be NULL).
+ * dtlr_relu_bwd: dh = h > 0 ? dh : 0 in place.   dtlr_add_cast: out = a (+ b) (+ c), fp32 in, fp32 or 16-bit out.
+ * dtlr_msda_bwd_glue: grad of the fused projection row [offsets | logits] (ms_deform_attn.py:98-108: softmax + sampling locations)
+ *   from dtlr_msda_backward's grad_loc / grad_attn; ref / valid_ratios as dtlr_msda_prep (no gradient: detached in the reference).
+ * dtlr_pack_weights: one launch over a device table of fp32 matrices -> 16-bit (or fp32) copy [rows, ld_dst] and / or transposed
+ *   copy [cols, ld_dstT]; entry = 8 int64 {src, rows, cols, ld_src, dst|0, ld_dst, dstT|0, ld_dstT}; tile_start int32 [n+1] = prefix
+ *   of 32x32 tiles per entry.
+ * dtlr_optim_begin / dtlr_grad_sumsq / dtlr_adamw: state fp32[4] on the device ([0] sum of squared gradients, [1] step count);
+ *   begin zeroes [0] and advances [1]; sumsq adds one arena; adamw applies the clip coefficient min(1, max_norm / (norm + 1e-6))
+ *   (max_norm <= 0: none) and the torch.optim.AdamW update to one arena slice (one learning-rate group). */
+int dtlr_wgrad(const void* dY, int ldy, const void* X, int ldx, float* dW, int ldw, int rows, int N, int K, int dtype, void* stream);
+int dtlr_colsum(const void* x, long long ld, int N, long long nseg, long long seg_rows, long long seg_stride, float* out, int dtype,
+                void* stream);
+int dtlr_layernorm_bwd(const void* z, const float* dy, const float* dy2, const float* gamma, float* dz32, void* dz16, float* dgamma,
+                       float* dbeta, long long rows, int C, float eps, int dtype, void* stream);
+int dtlr_relu_bwd(void* dh, const void* h, long long n, int dtype, void* stream);
+int dtlr_add_cast(const float* a, const float* b, const float* c, void* out, long long n, int out_dtype, void* stream);
+int dtlr_msda_bwd_glue(const float* grad_loc, const float* grad_attn, const float* attn, const float* ref, int ref_dim,
+                       const float* valid_ratios, const int64_t* shapes, int L, void* dproj, int ld, int B, int Lq, int M, int P,
+                       int out_dtype, void* stream);
+int dtlr_pack_weights(const long long* table, const int* tile_start, int n_entries, int total_tiles, int dtype, void* stream);
+int dtlr_optim_begin(float* state, void* stream);
+int dtlr_grad_sumsq(const float* g, long long n, float* state, void* stream);
+int dtlr_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, float max_norm, const float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""CPU check of the native fine-tune step's orchestration (dtlr_b200/train_engine.py): with the torch stand-in of the kernel namespace
+(tests/train_ops_double.py) the explicit backward must reproduce torch autograd of the reference-shaped module path -- loss, every
+parameter gradient, and the parameters after clip_grad_norm_ + AdamW (reference engine.py:192-241)."""
+import copy
+import warnings
+
+import pytest
+import torch
+
+from dtlr_b200 import config, dino, ms_deform_attn, synth, train_engine
+from dtlr_b200.misc import nested_tensor_from_tensor_list
+
+import train_ops_double as KD
+
+
+class _TorchMSDA(torch.autograd.Function):
+    """differentiable torch core in place of the C-ABI op, so that the module path runs on the CPU"""
+
+    @staticmethod
+    def apply(value, shapes, lsi, loc, attn, im2col_step=64):
+        hw = [tuple(int(v) for v in r) for r in shapes.tolist()]
+        return KD.msda_core(value, loc, attn, hw)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, crit, _ = dino.build_dino(config.latin_ctc_args(num_queries=60, device="cpu"))
+    synth.load_synth_weights(model, 0)
+    model.train()
+    model.use_engine = False
+    B = 2
+    x = synth.synth_images(B, 40, 256, seed=5)
+    tg = synth.synth_targets(B, 166, seed=5, mean_len=6.0, std_len=2.0, min_len=3, max_len=9)
+    return model, crit, x, tg
+
+
+def _reference_step(model, crit, x, tg, lr, lr_backbone, wd, max_norm):
+    ref = copy.deepcopy(model)
+    old = ms_deform_attn.MSDeformAttnFunction
+    ms_deform_attn.MSDeformAttnFunction = _TorchMSDA
+    try:
+        out = ref.forward_modules(nested_tensor_from_tensor_list(x), tg)
+        crit.fused_ctc = False
+        loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
+        loss.backward()
+    finally:
+        ms_deform_attn.MSDeformAttnFunction = old
+    named = [(n, p) for n, p in ref.named_parameters() if p.requires_grad]
+    grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in named}
+    opt = torch.optim.AdamW([{"params": [p for n, p in named if "backbone" not in n], "lr": lr},
+                             {"params": [p for n, p in named if "backbone" in n], "lr": lr_backbone}], lr=lr, weight_decay=wd)
+    torch.nn.utils.clip_grad_norm_([p for _, p in named], max_norm)
+    opt.step()
+    return float(loss), grads, {n: p.detach().clone() for n, p in ref.named_parameters()}
+
+
+def test_native_step_matches_autograd_on_cpu(setup):
+    model, crit, x, tg = setup
+    lr, lrb, wd, mn = 1e-3, 1e-4, 1e-2, 0.1
+    loss_ref, g_ref, p_ref = _reference_step(model, crit, x, tg, lr, lrb, wd, mn)
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, lr=lr, lr_backbone=lrb, weight_decay=wd, max_norm=mn, dtype=torch.float32, K=KD)
+    eng.zero_grad()
+    loss = eng.forward_backward(x, tg)
+    assert abs(float(loss) - loss_ref) < 1e-4 * abs(loss_ref)
+    live = {n for n, *_ in eng.layout}
+    worst = 0.0
+    for n, p in m2.named_parameters():
+        if not p.requires_grad:
+            continue
+        gr = g_ref[n]
+        if n not in live:
+            assert gr is None or float(gr.abs().max()) == 0.0, "parameter %s left out of the arena has a reference gradient" % n
+            continue
+        assert gr is not None, n
+        g = eng.grad(p)
+        scale = float(gr.abs().max())
+        err = float((g - gr).abs().max())
+        # fp32 round-off of two summation orders, plus the odd ReLU unit whose pre-activation sits at zero and flips (one column of a
+        # weight gradient moves by O(1e-3) of the maximum): bound the maximum loosely, the direction tightly
+        assert err <= 5e-3 * scale + 1e-7, (n, err, scale)
+        cos = float(torch.nn.functional.cosine_similarity(g.flatten().double(), gr.flatten().double(), dim=0))
+        assert cos > 1 - 1e-5 or scale < 1e-6, (n, cos)
+        worst = max(worst, err / (scale + 1e-12))
+    # optimizer: clip_grad_norm_ + AdamW with the backbone learning-rate group.  Adam's first step is lr * g / (|g| + eps): elements
+    # whose gradient is round-off noise around zero move by +-lr either way, so the update is compared on IDENTICAL gradients
+    for n, p in m2.named_parameters():
+        if n in live:
+            eng.grad(p).copy_(g_ref[n])
+    eng.optimizer_step()
+    for n, p in m2.named_parameters():
+        assert float((p.detach() - p_ref[n]).abs().max()) <= 2e-6 * (1 + float(p_ref[n].abs().max())), n
+
+
+def test_arena_layout_and_dead_parameters(setup):
+    model, _, _, _ = setup
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, dtype=torch.float32, K=KD)
+    names = [n for n, *_ in eng.layout]
+    assert not any(n.startswith(train_engine.DEAD_PREFIXES) for n in names)
+    assert any(n.startswith("transformer.decoder.class_embed.") for n in names)
+    segs = [s for _, _, _, s, _, _ in eng.layout]
+    gis = [g for _, _, g, _, _, _ in eng.layout]
+    assert gis == sorted(gis) and all(segs[i] <= segs[i + 1] or gis[i] < gis[i + 1] for i in range(len(segs) - 1))
+    for n, p, gi, seg, o, k in eng.layout:          # parameters and gradients are views of the arenas
+        assert p.data_ptr() == eng.flat_p.data_ptr() + 4 * o and p.grad.data_ptr() == eng.flat_g.data_ptr() + 4 * o
+    # frozen stem / layer1 are not in the arena
+    assert not any("layer1" in n or n.endswith("body.conv1.weight") for n in names)
+
+
+def test_head_only_finetuning_step(setup):
+    """step-1 fine-tuning (reference finetuning.py:531-539): only the class heads require grad"""
+    model, crit, x, tg = setup
+    m2 = copy.deepcopy(model)
+    for n, p in m2.named_parameters():
+        p.requires_grad_("class_embed" in n and "enc_out" not in n)
+    eng = train_engine.TrainEngine(m2, dtype=torch.float32, K=KD)
+    assert all(n.startswith(train_engine.HEAD_PREFIXES) for n, *_ in eng.layout)
+    before = m2.class_embed[0].weight.detach().clone()
+    loss = eng.step(x, tg)
+    assert torch.isfinite(loss) and float((m2.class_embed[0].weight.detach() - before).abs().max()) > 0
