@@ -204,38 +204,56 @@ def run_reference(args, rank):
 TRAIN_BATCH_PER_GPU = 32
 
 
-def train_step_leg(device, rank, world, local, steps=5, warmup=2):
+def train_step_leg(device, rank, world, local, steps=5, warmup=3, impl="native"):
     """BASELINE config 5: IAM fine-tune step = forward(samples, targets) + loss_CTC + backward + clip_grad_norm(0.01) + AdamW, 32 lines
-    per GPU, DistributedDataParallel over NCCL when N > 1 (reference engine.py:172-274, finetuning.py:211-215).  Timed on the device,
-    max over ranks.  Kernels: dtlr deformable attention forward/backward + fused CTC loss (C ABI); the remaining layers are torch autograd
-    over cuBLAS / cuDNN with TF32 (stated in the result)."""
+    per GPU (reference engine.py:172-274, finetuning.py:211-231).  Timed on the device, max over ranks.
+    impl "native": dtlr_b200.train_engine.TrainEngine -- transformer forward AND backward, loss and optimizer on libdtlr_b200 kernels
+    (bf16 tcgen05 operands, fp32 accumulation / gradient arena), ResNet front under torch autograd; N > 1: the flat gradient arena is
+    all-reduced over NCCL in three segments overlapped with the backward.
+    impl "torch": the module path under torch autograd (cuBLAS / cuDNN, TF32) with DistributedDataParallel -- the round-1 step, kept as
+    the A/B."""
     from dtlr_b200 import config, dino, dist_util, synth
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     model, crit, _ = dino.build_dino(config.latin_ctc_args())
     synth.load_synth_weights(model, seed=0)
     model = model.to(device).train()
-    net = model
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        # the CTC-only loss leaves the box heads without gradient (reference points are detached, pred_boxes only steer the sort): the
-        # reference passes find_unused_parameters (finetuning.py:211-215); a static graph lets DDP learn the unused set once instead
-        # of walking the autograd graph every step, and bucket views avoid one copy of the 187 MB of gradients
-        net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True, bucket_cap_mb=64)
-    params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
     B = TRAIN_BATCH_PER_GPU
     x = synth.synth_images(B, IMG_H, IMG_W, seed=300 + rank).to(device)
     tg = [{k: v.to(device) for k, v in t.items()} for t in synth.synth_targets(B, 166, seed=300 + rank)]
+    if impl == "native":
+        from dtlr_b200 import train_engine
+        eng = train_engine.TrainEngine(model, lr=1e-5, lr_backbone=1e-10, weight_decay=1e-4, max_norm=0.01, dtype=torch.bfloat16,
+                                       world_size=world)
+        n_grad = eng.n_live
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        out = net(x, tg)
-        loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 0.01)
-        opt.step()
-        return loss
+        def step():
+            return eng.step(x, tg)
+        what = ("forward(samples, targets) + loss_CTC + backward + clip + AdamW on dtlr kernels: encoder / decoder / heads forward and "
+                "backward (tcgen05 GEMM, dgrad, MN-major wgrad; LayerNorm / MSDA / CTC backward kernels), fused clip + AdamW over flat fp32 "
+                "arenas; ResNet front + input_proj: torch autograd over cuDNN (TF32); decoder self-attention: torch SDPA")
+        coll = ("%d async NCCL all-reduces of the flat fp32 gradient arena (%d gradients, %.0f MB) issued as each segment's backward "
+                "completes (decoder | encoder | front)" % (len(eng.chunks), n_grad, n_grad * 4 / 1e6))
+    else:
+        net = model
+        if world > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True, bucket_cap_mb=64)
+        params = [p for p in net.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
+        n_grad = sum(p.numel() for p in params)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = net(x, tg)
+            loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 0.01)
+            opt.step()
+            return loss
+        what = ("forward(samples, targets) + loss_CTC + backward + clip + AdamW; dtlr kernels: deformable attention fwd/bwd, fused CTC "
+                "loss fwd/bwd; other layers torch autograd over cuBLAS/cuDNN (TF32)")
+        coll = "DDP bucketed NCCL all-reduce of %d fp32 gradients (%.0f MB) per step, overlapped with backward" % (n_grad, n_grad * 4 / 1e6)
 
     for _ in range(warmup):
         step()
@@ -247,14 +265,10 @@ def train_step_leg(device, rank, world, local, steps=5, warmup=2):
     e1.record()
     dist_util.barrier(device)
     ms = dist_util.max_over_ranks(e0.elapsed_time(e1), device) / steps
-    n_grad = sum(p.numel() for p in params)
     res = {"value": round(world * B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 2), "batch_per_gpu": B,
-           "global_batch": B * world, "loss": round(float(loss), 4), "steps": steps, "warmup": warmup,
-           "collective": ("DDP bucketed NCCL all-reduce of %d fp32 gradients (%.0f MB) per step, overlapped with backward"
-                          % (n_grad, n_grad * 4 / 1e6)) if world > 1 else "none (N = 1)",
-           "what": "forward(samples, targets) + loss_CTC + backward + clip + AdamW; dtlr kernels: deformable attention fwd/bwd, fused CTC "
-                   "loss fwd/bwd; other layers torch autograd over cuBLAS/cuDNN (TF32)"}
-    del net, model, opt
+           "global_batch": B * world, "loss": round(float(loss), 4), "steps": steps, "warmup": warmup, "impl": impl,
+           "collective": coll if world > 1 else "none (N = 1)", "what": what}
+    del model
     torch.cuda.empty_cache()
     return res
 
@@ -298,6 +312,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--train-impl", default="native", choices=["native", "torch"],
+                    help="fine-tune step leg: native TrainEngine (default) or the torch-autograd module path")
+    ap.add_argument("--train-ab", action="store_true", help="also time the torch-autograd fine-tune step beside the native one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -449,7 +466,10 @@ def main():
     train = None
     if not args.no_train_step:
         try:
-            train = train_step_leg(device, rank, world, local)
+            train = train_step_leg(device, rank, world, local, impl=args.train_impl)
+            if args.train_impl == "native" and args.train_ab:
+                train["torch_autograd_ab"] = {k: v for k, v in train_step_leg(device, rank, world, local, impl="torch").items()
+                                              if k in ("value", "ms_per_step", "impl")}
         except Exception as e:      # a secondary leg must never cost the headline line
             train = {"error": repr(e)[:300]}
             try:

@@ -1,0 +1,125 @@
+"""-m gpu: the native fine-tune step (dtlr_b200/train_engine.py on libdtlr_b200 kernels) against torch autograd of the reference-shaped
+module path on the same GPU and against the reference-generated fixture dino_T_b2 (training-mode forward + loss_CTC of the UNMODIFIED
+reference, tests/golden/make_golden.py).  fp32 = parity mode (exact SIMT contractions), bf16 = the tcgen05 mode the bench line times."""
+import copy
+
+import pytest
+import torch
+
+from gpu_common import build_model, fixture, rel
+from dtlr_b200 import synth, train_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    fx = fixture("dino_T_b2")
+    model, crit, _ = build_model(300)
+    model.train()
+    model.use_engine = False
+    tg = [{k: v.cuda() for k, v in t.items()} for t in synth.synth_targets(2, 166, seed=3)]
+    x = synth.synth_images(2, 40, 1024, seed=3).cuda()
+    model.transformer.debug_force_topk = torch.from_numpy(fx["topk_idx"]).long().cuda()
+    return fx, model, crit, x, tg
+
+
+def _autograd_reference(model, crit, x, tg):
+    ref = copy.deepcopy(model)
+    out = ref(x, tg)
+    loss = crit.loss_CTC(out, tg, None, None)["loss_CTC"]
+    loss.backward()
+    return float(loss), out, {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in ref.named_parameters()}
+
+
+def _compare(eng, model, grads_ref, max_tol, cos_tol, loose=(), loose_cos=0.0):
+    live = {n for n, *_ in eng.layout}
+    coss = []
+    worst = (0.0, None)
+    worst_cos = (1.0, None)
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        gr = grads_ref[n]
+        if n not in live:
+            assert gr is None or float(gr.abs().max()) == 0.0, n
+            continue
+        assert gr is not None, n
+        g = eng.grad(p)
+        assert torch.isfinite(g).all(), n
+        scale = float(gr.abs().max())
+        if scale < 1e-9:
+            continue
+        err = float((g - gr).abs().max()) / scale
+        cos = float(torch.nn.functional.cosine_similarity(g.flatten().double(), gr.flatten().double(), dim=0))
+        coss.append(cos)
+        if any(k in n for k in loose):
+            assert cos > loose_cos, (n, cos)
+            continue
+        if err > worst[0]:
+            worst = (err, n)
+        if cos < worst_cos[0]:
+            worst_cos = (cos, n)
+    coss.sort()
+    print("worst max-rel error %.3e (%s); worst cosine %.6f (%s); median cosine %.6f" % (worst + worst_cos + (coss[len(coss) // 2],)))
+    assert worst[0] < max_tol, worst
+    assert worst_cos[0] > cos_tol, worst_cos
+    return coss
+
+
+def test_fp32_step_matches_autograd_and_reference_fixture():
+    fx, model, crit, x, tg = _setup()
+    loss_ref, out_ref, grads_ref = _autograd_reference(model, crit, x, tg)
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, dtype=torch.float32)
+    eng.zero_grad()
+    loss = eng.forward_backward(x, tg)
+    assert abs(float(loss) - float(fx["ctc_loss"])) < 1e-3 * float(fx["ctc_loss"])
+    assert abs(float(loss) - loss_ref) < 1e-4 * abs(loss_ref)
+    assert eng.last["pred_logits"].shape[1] == int(fx["pad_size"]) + 300
+    assert rel(eng.last["pred_logits"], fx["pred_logits"]) < 1e-3 and rel(eng.last["pred_boxes"], fx["pred_boxes"]) < 1e-3
+    _compare(eng, m2, grads_ref, 2e-2, 1 - 1e-4)
+
+
+def test_bf16_step_against_fp32_autograd():
+    fx, model, crit, x, tg = _setup()
+    loss_ref, out_ref, grads_ref = _autograd_reference(model, crit, x, tg)
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, dtype=torch.bfloat16)
+    eng.zero_grad()
+    loss = eng.forward_backward(x, tg)
+    print("bf16 loss %.5f vs fp32 %.5f" % (float(loss), loss_ref))
+    assert abs(float(loss) - loss_ref) < 2e-3 * abs(loss_ref)
+    # bf16 operands (8 significand bits) against fp32 autograd.  The gradients of sampling_offsets are differences of neighbouring
+    # value pixels weighted by the output gradient -- the operand rounding of the value projection input is amplified there (measured
+    # cosine 0.77 on the worst layer, 0.9x elsewhere); every other parameter's gradient keeps its direction
+    coss = _compare(eng, m2, grads_ref, 0.35, 0.97, loose=("sampling_offsets",), loose_cos=0.6)
+    assert coss[len(coss) // 2] > 0.995
+
+
+def test_full_step_updates_parameters_like_torch_adamw():
+    """zero_grad + forward/backward + clip_grad_norm_(0.1) + AdamW through TrainEngine.step (fp32 mode) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the autograd gradients (reference engine.py:236-241)."""
+    fx, model, crit, x, tg = _setup()
+    ref = copy.deepcopy(model)
+    out = ref(x, tg)
+    crit.loss_CTC(out, tg, None, None)["loss_CTC"].backward()
+    named = [(n, p) for n, p in ref.named_parameters() if p.requires_grad]
+    opt = torch.optim.AdamW([{"params": [p for n, p in named if "backbone" not in n], "lr": 1e-4},
+                             {"params": [p for n, p in named if "backbone" in n], "lr": 1e-5}], lr=1e-4, weight_decay=1e-4)
+    total = torch.nn.utils.clip_grad_norm_([p for _, p in named], 0.1)
+    opt.step()
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, lr=1e-4, lr_backbone=1e-5, weight_decay=1e-4, max_norm=0.1, dtype=torch.float32)
+    eng.step(x, tg)
+    assert abs(eng.grad_norm() - float(total)) < 1e-3 * float(total)
+    pr = dict(ref.named_parameters())
+    moved = 0
+    for n, p in m2.named_parameters():
+        # Adam's first step moves every element by ~lr * sign(g): elements whose gradient is round-off noise may differ by 2 lr
+        lr = 1e-5 if "backbone" in n else 1e-4
+        assert float((p.detach() - pr[n].detach()).abs().max()) <= 2.001 * lr + 1e-7, n
+        moved += int(float((p.detach() - model.state_dict()[n]).abs().max()) > 0)
+    assert moved > 200
+    # the operand copies follow the masters
+    l = eng.enc[0]["l1"]
+    assert torch.equal(l.w16, m2.transformer.encoder.layers[0].linear1.weight.detach()) and torch.equal(l.wT16[:, :l.N], l.w16.t())

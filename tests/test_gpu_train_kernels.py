@@ -1,0 +1,169 @@
+"""-m gpu: the backward kernels of csrc/train.cu, each against its plain formula (tests/train_ops_double.py evaluated on the CPU in
+fp32 / fp64).  16-bit cases bound the error by the operand rounding; fp32 cases are the parity mode."""
+import math
+
+import pytest
+import torch
+
+import train_ops_double as KD
+from dtlr_b200 import _lib as L
+from dtlr_b200 import train_ops as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _relmax(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,N,Kd,ldy", [(29184, 256, 256, 256), (1000, 384, 256, 384), (777, 166, 256, 168), (4096, 2048, 256, 2048),
+                                          (4099, 256, 2048, 256), (130, 512, 512, 512), (64, 128, 128, 128), (5, 256, 256, 256)])
+def test_wgrad(dtype, rows, N, Kd, ldy):
+    g = torch.Generator(device="cpu").manual_seed(rows + N)
+    dy = torch.zeros(rows, ldy)
+    dy[:, :N] = torch.randn(rows, N, generator=g)
+    x = torch.randn(rows, Kd, generator=g)
+    dy_d, x_d = dy.to(DEV, dtype), x.to(DEV, dtype)
+    gw = torch.full((N, Kd), 0.5, device=DEV)              # accumulates into what is there
+    K.wgrad(dy_d[:, :N], x_d, gw)
+    ref = 0.5 + dy_d[:, :N].double().cpu().t() @ x_d.double().cpu()
+    tol = 2e-5 if dtype == torch.float32 else 2e-5        # products of the ROUNDED operands are exact in fp32; only the order differs
+    assert _relmax(gw, ref) < tol * max(1.0, math.sqrt(rows) / 8)
+
+
+def test_wgrad_column_slices_of_a_fused_projection():
+    """the engine passes column slices of dY (offsets | logits) with the row pitch of the fused matrix"""
+    rows = 3000
+    dy = torch.randn(rows, 384, device=DEV).bfloat16()
+    x = torch.randn(rows, 256, device=DEV).bfloat16()
+    g0 = torch.zeros(256, 256, device=DEV)
+    g1 = torch.zeros(128, 256, device=DEV)
+    K.wgrad(dy[:, :256], x, g0)
+    K.wgrad(dy[:, 256:], x, g1)
+    ref = dy.double().t() @ x.double()
+    assert _relmax(g0, ref[:256]) < 1e-4 and _relmax(g1, ref[256:]) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,N,ld", [(29184, 256, 256), (1000, 384, 384), (777, 166, 168), (513, 2048, 2048), (300, 7356, 7360)])
+def test_colsum(dtype, rows, N, ld):
+    x = torch.zeros(rows, ld, device=DEV, dtype=dtype)
+    x[:, :N] = torch.randn(rows, N, device=DEV).to(dtype)
+    out = torch.ones(N, device=DEV)
+    K.colsum(x[:, :N], out)
+    assert _relmax(out, 1 + x[:, :N].double().sum(0)) < 1e-5 * max(1.0, math.sqrt(rows))
+
+
+def test_colsum_segments_are_the_levels_of_the_token_tensor():
+    B, S, C = 3, 912, 256
+    x = torch.randn(B * S, C, device=DEV)
+    starts, sizes = [0, 640, 832, 896], [640, 192, 64, 16]
+    for s0, n in zip(starts, sizes):
+        out = torch.zeros(C, device=DEV)
+        K.colsum(x, out, nseg=B, seg_rows=n, seg_stride=S, row0=s0)
+        ref = x.view(B, S, C)[:, s0:s0 + n].double().sum((0, 1))
+        assert _relmax(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows", [29184, 1001, 7])
+def test_layernorm_bwd(dtype, rows):
+    z = (torch.randn(rows, 256, device=DEV) * 2 + 0.3).to(dtype)
+    dy = torch.randn(rows, 256, device=DEV)
+    dy2 = torch.randn(rows, 256, device=DEV)
+    gamma = torch.rand(256, device=DEV) + 0.5
+    dg, db = torch.zeros(256, device=DEV), torch.zeros(256, device=DEV)
+    dz32, dz16 = K.layernorm_bwd(z, dy, dy2, gamma, dg, db)
+    dg_r, db_r = torch.zeros(256, dtype=torch.float64), torch.zeros(256, dtype=torch.float64)
+    r32, _ = KD.layernorm_bwd(z.double().cpu(), dy.double().cpu(), dy2.double().cpu(), gamma.double().cpu(), dg_r, db_r)
+    assert _relmax(dz32, r32) < 1e-5
+    assert _relmax(dz16, r32) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert _relmax(dg, dg_r) < 1e-4 and _relmax(db, db_r) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_relu_bwd_and_add_cast(dtype):
+    h = torch.randn(1000, 2048, device=DEV).to(dtype)
+    dh = torch.randn(1000, 2048, device=DEV).to(dtype)
+    ref = torch.where(h > 0, dh, torch.zeros_like(dh))
+    K.relu_bwd_(dh, h)
+    assert torch.equal(dh, ref)
+    a, b = torch.randn(999, 256, device=DEV), torch.randn(999, 256, device=DEV)
+    assert torch.equal(K.add_cast(a, b, None, dtype), (a + b).to(dtype))
+    assert torch.equal(K.add_cast(a, None, None, dtype), a.to(dtype))
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_msda_bwd_glue(ref_dim):
+    B, Lq, M, P = 2, 300, 8, 4
+    level_hw = [(5, 128), (3, 64), (2, 32), (1, 16)]
+    geo = {"B": B, "S": 912, "nlev": 4, "level_hw": level_hw, "shapes_host": L.i64_host([v for hw in level_hw for v in hw])}
+    gl = torch.randn(B, Lq, M, 4, P, 2)
+    ga = torch.randn(B, Lq, M, 4, P)
+    attn = torch.softmax(torch.randn(B, Lq, M, 16), -1).view(B, Lq, M, 4, P)
+    ref = torch.rand(B * Lq, ref_dim) * 0.8 + 0.1
+    vr = torch.rand(B, 4, 2) * 0.5 + 0.5
+    want = KD.msda_bwd_glue(gl, ga, attn, ref, vr, geo, Lq, M, P, torch.float32)
+    got = K.msda_bwd_glue(gl.to(DEV), ga.to(DEV), attn.to(DEV).contiguous(), ref.to(DEV), vr.to(DEV), geo, Lq, M, P, torch.float32)
+    assert _relmax(got, want) < 1e-5
+    got16 = K.msda_bwd_glue(gl.to(DEV), ga.to(DEV), attn.to(DEV).contiguous(), ref.to(DEV), vr.to(DEV), geo, Lq, M, P, torch.bfloat16)
+    assert _relmax(got16, want) < 1e-2
+
+
+def test_msda_prologue_chain_rule_against_autograd():
+    """dtlr_msda_prep forward + dtlr_msda_bwd_glue backward = autograd of the module's softmax / sampling-location code
+    (ms_deform_attn.py:98-108) for both reference-point layouts"""
+    B, Lq, M, P = 2, 50, 8, 4
+    level_hw = [(5, 128), (3, 64), (2, 32), (1, 16)]
+    geo = {"B": B, "S": 912, "nlev": 4, "level_hw": level_hw, "shapes_host": L.i64_host([v for hw in level_hw for v in hw])}
+    for rd in (2, 4):
+        oa = torch.randn(B * Lq, 384, requires_grad=True)
+        ref = torch.rand(B * Lq, rd) * 0.8 + 0.1
+        vr = torch.rand(B, 4, 2) * 0.5 + 0.5
+        loc, attn = KD.msda_prep(oa, ref, vr, geo, Lq, M, P)
+        gl, ga = torch.randn_like(loc), torch.randn_like(attn)
+        (want,) = torch.autograd.grad([loc, attn], oa, [gl, ga])
+        loc_d, attn_d = K.msda_prep(oa.detach().to(DEV), ref.to(DEV), vr.to(DEV), geo, Lq, M, P)
+        assert _relmax(loc_d, loc) < 1e-5 and _relmax(attn_d, attn) < 1e-5
+        got = K.msda_bwd_glue(gl.to(DEV), ga.to(DEV), attn_d, ref.to(DEV), vr.to(DEV), geo, Lq, M, P, torch.float32)
+        assert _relmax(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_pack_weights(dtype):
+    ws = [torch.randn(256, 256, device=DEV), torch.randn(166, 256, device=DEV), torch.randn(768, 256, device=DEV), torch.randn(256, 2048, device=DEV)]
+    rows, tiles, outs = [], [0], []
+    for w in ws + [ws[2]]:
+        r0, n = (512, 256) if len(rows) == 4 else (0, w.shape[0])       # last entry: a row slice (the v rows of in_proj_weight)
+        src = w[r0:r0 + n]
+        ldn = (n + 7) // 8 * 8
+        d = torch.zeros(n, w.shape[1], device=DEV, dtype=dtype)
+        dT = torch.zeros(w.shape[1], ldn, device=DEV, dtype=dtype)
+        rows.append([src.data_ptr(), n, w.shape[1], w.shape[1], d.data_ptr(), w.shape[1], dT.data_ptr(), ldn])
+        tiles.append(tiles[-1] + ((n + 31) // 32) * ((w.shape[1] + 31) // 32))
+        outs.append((src, d, dT, n))
+    K.pack_weights(torch.tensor(rows, dtype=torch.int64).to(DEV), torch.tensor(tiles, dtype=torch.int32).to(DEV), len(rows), tiles[-1], dtype)
+    for src, d, dT, n in outs:
+        assert torch.equal(d, src.to(dtype)) and torch.equal(dT[:, :n], src.t().to(dtype))
+
+
+def test_fused_clip_adamw_matches_torch():
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device=DEV)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=1e-2)
+    p, m, v, state = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(4, device=DEV)
+    for step in range(3):
+        g = torch.randn(n, device=DEV) * (10.0 if step == 1 else 1e-4)       # one step that clips, two that do not
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 0.1)
+        opt.step()
+        K.optim_begin(state)
+        K.grad_sumsq(g, state)
+        K.adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 0.1, state)
+        assert abs(float(state[0].sqrt()) - float(g.norm())) < 1e-4 * float(g.norm())
+        assert float((p - ref.detach()).abs().max()) < 2e-6
