@@ -458,6 +458,60 @@ __global__ void msda_prep_kernel(const float* __restrict__ proj, int ld, const f
     }
 }
 
+// 4 levels x 4 points (every shipped config), fp32 projection rows with 16-byte aligned pitch: the 16 points of a (query, head) in
+// registers, 16-byte loads / stores; arithmetic identical to the generic kernel above (used by the fine-tune step, which needs
+// sampling_locations / attention_weights in HBM for the backward; the inference path fuses all of this into the gather kernel)
+__global__ void __launch_bounds__(128)
+msda_prep16_kernel(const float* __restrict__ proj, int ld, const float* __restrict__ ref, int RD, const float* __restrict__ valid_ratios,
+                   float* __restrict__ loc, float* __restrict__ attn, const __grid_constant__ PrepLevels lv, int B, int Lq, int M) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * Lq * M) return;
+    const int m = (int)(i % M);
+    const long long row = i / M;
+    const int b = (int)(row / Lq);
+    const float* pr = proj + (size_t)row * ld;
+    float off[32], lg[16];
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(off + k) = *reinterpret_cast<const float4*>(pr + (size_t)m * 32 + k);
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(lg + k) = *reinterpret_cast<const float4*>(pr + (size_t)M * 32 + (size_t)m * 16 + k);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) mx = fmaxf(mx, lg[k]);
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) den += expf(lg[k] - mx);
+    const float inv = 1.f / den;
+    const float* rf = ref + (size_t)row * RD;
+    const float r0 = rf[0], r1 = rf[1];
+    float rw = 0.f, rh = 0.f;
+    if (RD == 4) { rw = rf[2]; rh = rf[3]; }
+    float lo[32], at[16];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const float vx = valid_ratios[((size_t)b * 4 + l) * 2], vy = valid_ratios[((size_t)b * 4 + l) * 2 + 1];
+        const float rx = r0 * vx, ry = r1 * vy;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int k = l * 4 + p;
+            if (RD == 2) {
+                lo[2 * k] = rx + off[2 * k] / (float)lv.W[l];
+                lo[2 * k + 1] = ry + off[2 * k + 1] / (float)lv.H[l];
+            } else {
+                lo[2 * k] = rx + off[2 * k] / 4.f * (rw * vx) * 0.5f;
+                lo[2 * k + 1] = ry + off[2 * k + 1] / 4.f * (rh * vy) * 0.5f;
+            }
+            at[k] = expf(lg[k] - mx) * inv;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(loc + (size_t)i * 32 + k) = *reinterpret_cast<const float4*>(lo + k);
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4*>(attn + (size_t)i * 16 + k) = *reinterpret_cast<const float4*>(at + k);
+}
+
 // encoder reference points before the per-level valid-ratio product (deformable_transformer.py:479-490):
 // ref[b, tok] = ((x+0.5)/(vr_w*W_l), (y+0.5)/(vr_h*H_l)) for the token's own level l.
 __global__ void enc_ref_kernel(const float* __restrict__ valid_ratios, float* __restrict__ ref, const __grid_constant__ PrepLevels lv,
@@ -897,6 +951,11 @@ extern "C" int dtlr_msda_prep(const float* proj, int ld, const float* ref, int r
     if (rc) return rc;
     const long long total = (long long)B * Lq * M;
     if (total == 0) return DTLR_OK;
+    if (L == 4 && P == 4 && (ld % 4) == 0 && ((((uintptr_t)proj | (uintptr_t)loc | (uintptr_t)attn)) & 15) == 0 && !(g_debug_flags & 268435456)) {
+        DTLR_LAUNCH((msda_prep16_kernel), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, proj, ld, ref, ref_dim, valid_ratios, loc, attn, lv, B, Lq, M);
+        DTLR_CHECK_LAUNCH();
+        return DTLR_OK;
+    }
     DTLR_LAUNCH((msda_prep_kernel), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, proj, ld, ref, ref_dim, valid_ratios, loc, attn, lv, B, Lq, M, P);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

@@ -235,7 +235,7 @@ wgrad_f32_kernel(const float* __restrict__ dY, int ldy, const float* __restrict_
 // (bias gradients: one segment; per-level sums over the (B, S, C) token tensor for level_embed: nseg = B, seg_stride = S).
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, long long ld, int N, long long nseg, long long seg_rows, long long seg_stride, float* __restrict__ out,
+colsum_kernel(const T* __restrict__ x, long long ld, int N, int nseg, int seg_rows, long long seg_stride, float* __restrict__ out,
               int rows_per_block) {
     __shared__ float sm[256 * 8];
     pdl_launch_dependents();
@@ -245,21 +245,37 @@ colsum_kernel(const T* __restrict__ x, long long ld, int N, long long nseg, long
     const int cg = min(256, cg_all - cg0);                            // column groups (8 columns each) of this block
     const int rp = 256 / cg;                                          // rows in flight per block
     const int c = threadIdx.x % cg, ry = threadIdx.x / cg;
-    const long long total = nseg * seg_rows;
-    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(total, r0 + rows_per_block);
+    const int total = nseg * seg_rows;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(total, r0 + rows_per_block);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int col = (cg0 + c) * 8;
     if (ry < rp) {
-        for (long long g = r0 + ry; g < r1; g += rp) {
-            const long long seg = g / seg_rows;
-            const long long row = seg * seg_stride + (g - seg * seg_rows);
-            const T* p = x + row * ld + col;
-            if (col + 7 < N) {
+        if (col + 7 < N) {
+            // four rows per iteration: their loads are independent and issued together (the first version took one row at a time
+            // behind a 64-bit division and was latency bound)
+            int g = r0 + ry;
+            for (; g + 3 * rp < r1; g += 4 * rp) {
+                float f[4][8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int gg = g + u * rp;
+                    const int seg = nseg == 1 ? 0 : gg / seg_rows;
+                    ld8<T>(x + ((long long)seg * seg_stride + (gg - seg * seg_rows)) * ld + col, f[u]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += (f[0][k] + f[1][k]) + (f[2][k] + f[3][k]);
+            }
+            for (; g < r1; g += rp) {
                 float f[8];
-                ld8<T>(p, f);
+                const int seg = nseg == 1 ? 0 : g / seg_rows;
+                ld8<T>(x + ((long long)seg * seg_stride + (g - seg * seg_rows)) * ld + col, f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[k] += f[k];
-            } else {
+            }
+        } else {
+            for (int g = r0 + ry; g < r1; g += rp) {
+                const int seg = nseg == 1 ? 0 : g / seg_rows;
+                const T* p = x + ((long long)seg * seg_stride + (g - seg * seg_rows)) * ld + col;
                 for (int k = 0; k < 8; ++k)
                     if (col + k < N) acc[k] += ld1<T>(p + k);
             }
@@ -269,10 +285,20 @@ colsum_kernel(const T* __restrict__ x, long long ld, int N, long long nseg, long
     for (int k = 0; k < 8; ++k) sm[threadIdx.x * 8 + k] = acc[k];
     __syncthreads();
     if (ry == 0) {
+        float s[8];
+#pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float s = 0.f;
-            for (int j = 0; j < rp; ++j) s += sm[(j * cg + c) * 8 + k];
-            if (col + k < N) atomicAdd(out + col + k, s);
+            s[k] = 0.f;
+            for (int j = 0; j < rp; ++j) s[k] += sm[(j * cg + c) * 8 + k];
+        }
+        // few CTAs and vector reductions: every CTA adds into the same N addresses, and same-line atomics serialise in L2 (the first
+        // version: 456 CTAs x 256 scalar atomics on 8 lines = 39 us for a 15 MB input; ncu-free diagnosis from the launch list)
+        if (col + 7 < N && ((((uintptr_t)(out + col)) & 15) == 0)) {
+            red_add_v4(out + col, s[0], s[1], s[2], s[3]);
+            red_add_v4(out + col + 4, s[4], s[5], s[6], s[7]);
+        } else {
+            for (int k = 0; k < 8; ++k)
+                if (col + k < N) atomicAdd(out + col + k, s[k]);
         }
     }
 }
@@ -332,24 +358,27 @@ layernorm256_bwd_kernel(const T* __restrict__ z, const float* __restrict__ dy, c
         if (dz32) st8<float>(dz32 + off, o);
         if (dzT) st8<T>(dzT + off, o);
     }
-    if (dgamma) {
+    // per-CTA sums, then one 16-byte reduction per 4 channels (same-line atomics serialise in L2: few CTAs, vector operations)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = ag[k];
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (!dst) continue;
         __syncthreads();
-        float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        atomicAdd(dgamma + threadIdx.x, s);
+        for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = pass == 0 ? ag[k] : ab[k];
         __syncthreads();
-    }
-    if (dbeta) {
+        if (threadIdx.x < 64) {
+            float s4[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = ab[k];
-        __syncthreads();
-        float s = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                s4[j] = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        atomicAdd(dbeta + threadIdx.x, s);
+                for (int w = 0; w < 8; ++w) s4[j] += red[w][threadIdx.x * 4 + j];
+            }
+            if ((((uintptr_t)dst) & 15) == 0) red_add_v4(dst + threadIdx.x * 4, s4[0], s4[1], s4[2], s4[3]);
+            else
+                for (int j = 0; j < 4; ++j) atomicAdd(dst + threadIdx.x * 4 + j, s4[j]);
+        }
     }
 }
 
@@ -435,6 +464,60 @@ __global__ void msda_bwd_glue_kernel(const float* __restrict__ gloc, const float
             st1<T>(pl + k, at[k] * (ga[k] - dot));
         }
     }
+}
+
+// L * P == 16 (every shipped config: 4 levels x 4 points): the same arithmetic with the 16 points of a (query, head) in registers,
+// 16-byte loads and stores (the generic kernel above walks them with scalar accesses 128 bytes apart across the warp: 113 us per call
+// at 32 lines against ~30 us of memory time)
+template <typename T, int NL, int NP>
+__global__ void __launch_bounds__(128)
+msda_bwd_glue16_kernel(const float* __restrict__ gloc, const float* __restrict__ gattn, const float* __restrict__ attn,
+                       const float* __restrict__ ref, int RD, const float* __restrict__ valid_ratios, const __grid_constant__ GlueLevels lv,
+                       T* __restrict__ dproj, int ld, int B, int Lq, int M) {
+    static_assert(NL * NP == 16, "16 sampling points per head");
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * Lq * M) return;
+    const int m = (int)(i % M);
+    const long long row = i / M;
+    const int b = (int)(row / Lq);
+    float at[16], ga[16], gl[32];
+#pragma unroll
+    for (int k = 0; k < 16; k += 8) { ld8<float>(attn + (size_t)i * 16 + k, at + k); ld8<float>(gattn + (size_t)i * 16 + k, ga + k); }
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) ld8<float>(gloc + (size_t)i * 32 + k, gl + k);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dot = fmaf(at[k], ga[k], dot);
+    const float* rf = ref + (size_t)row * RD;
+    float rw = 0.f, rh = 0.f;
+    if (RD == 4) { rw = rf[2]; rh = rf[3]; }
+    float o[32], lg[16];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        float sx, sy;
+        if (RD == 2) {
+            sx = 1.f / (float)lv.W[l];
+            sy = 1.f / (float)lv.H[l];
+        } else {
+            sx = (rw * valid_ratios[((size_t)b * NL + l) * 2]) * 0.5f / (float)NP;
+            sy = (rh * valid_ratios[((size_t)b * NL + l) * 2 + 1]) * 0.5f / (float)NP;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int k = l * NP + p;
+            o[2 * k] = gl[2 * k] * sx;
+            o[2 * k + 1] = gl[2 * k + 1] * sy;
+            lg[k] = at[k] * (ga[k] - dot);
+        }
+    }
+    T* po = dproj + (size_t)row * ld + (size_t)m * 32;
+    T* pl = dproj + (size_t)row * ld + (size_t)M * 32 + (size_t)m * 16;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) st8<T>(po + k, o + k);
+#pragma unroll
+    for (int k = 0; k < 16; k += 8) st8<T>(pl + k, lg + k);
 }
 
 // ---------------------------------------------------------------------------------------------- operand copies of the weights
@@ -605,17 +688,18 @@ extern "C" int dtlr_colsum(const void* x, long long ld, int N, long long nseg, l
     DTLR_CHECK_ARG(N > 0 && nseg >= 0 && seg_rows >= 0 && ld >= N, "colsum: bad sizes");
     const long long total = nseg * seg_rows;
     if (total == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(total < (1ll << 31) && nseg < (1ll << 31), "colsum: more than 2^31 rows");
     DTLR_CHECK_ARG((dtype == DTLR_F32 ? (ld % 4) == 0 : (ld % 8) == 0) && (((uintptr_t)x) & 15) == 0, "colsum: rows must be 16-byte aligned");
     const int cg_all = (N + 7) / 8;
     const int ny = (cg_all + 255) / 256;
     const int rp = 256 / (cg_all < 256 ? cg_all : 256);
-    long long blocks = (long long)sm_count() * 4 / ny;
+    long long blocks = (long long)sm_count() * 2 / ny;                 // one wave; every CTA ends with N / 4 vector reductions
     if (blocks < 1) blocks = 1;
     long long rpb = (total + blocks - 1) / blocks;
-    if (rpb < 8LL * rp) rpb = 8LL * rp;
+    if (rpb < 16LL * rp) rpb = 16LL * rp;
     blocks = (total + rpb - 1) / rpb;
     dim3 grid((unsigned)blocks, ny);
-    DISPATCH_T(dtype, DTLR_LAUNCH((colsum_kernel<T>), grid, 256, 0, (cudaStream_t)stream, (const T*)x, ld, N, nseg, seg_rows, seg_stride, out, (int)rpb);)
+    DISPATCH_T(dtype, DTLR_LAUNCH((colsum_kernel<T>), grid, 256, 0, (cudaStream_t)stream, (const T*)x, ld, N, (int)nseg, (int)seg_rows, seg_stride, out, (int)rpb);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }
@@ -624,7 +708,7 @@ extern "C" int dtlr_layernorm_bwd(const void* z, const float* dy, const float* d
                                   float* dgamma, float* dbeta, long long rows, int C, float eps, int dtype, void* stream) {
     DTLR_CHECK_ARG(C == 256, "layernorm_bwd: only C=256 (d_model of every DTLR config) is implemented, got %d", C);
     if (rows == 0) return DTLR_OK;
-    const unsigned grid = grid_cap(rows, 8, 8);
+    const unsigned grid = grid_cap(rows, 8, 4);
     DISPATCH_T(dtype, DTLR_LAUNCH((layernorm256_bwd_kernel<T>), grid, 256, 0, (cudaStream_t)stream, (const T*)z, dy, dy2, gamma, dz32, (T*)dz16, dgamma, dbeta, rows, eps);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
@@ -656,6 +740,13 @@ extern "C" int dtlr_msda_bwd_glue(const float* grad_loc, const float* grad_attn,
     for (int l = 0; l < L; ++l) { lv.H[l] = (int)shapes[2 * l]; lv.W[l] = (int)shapes[2 * l + 1]; }
     const long long total = (long long)B * Lq * M;
     if (total == 0) return DTLR_OK;
+    const bool rows16 = out_dtype == DTLR_F32 ? ((ld % 4) == 0) : ((ld % 8) == 0);
+    if (L == 4 && P == 4 && rows16 && ((((uintptr_t)dproj | (uintptr_t)grad_loc | (uintptr_t)grad_attn | (uintptr_t)attn)) & 15) == 0 &&
+        !(g_debug_flags & 268435456)) {                  // flag 268435456: the generic kernel (A/B)
+        DISPATCH_T(out_dtype, DTLR_LAUNCH((msda_bwd_glue16_kernel<T, 4, 4>), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, grad_loc, grad_attn, attn, ref, ref_dim, valid_ratios, lv, (T*)dproj, ld, B, Lq, M);)
+        DTLR_CHECK_LAUNCH();
+        return DTLR_OK;
+    }
     DISPATCH_T(out_dtype, DTLR_LAUNCH((msda_bwd_glue_kernel<T>), (unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream, grad_loc, grad_attn, attn, ref, ref_dim, valid_ratios, lv, (T*)dproj, ld, B, Lq, M, P);)
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;

@@ -91,10 +91,13 @@ class TrainEngine:
         self._build_linears()
         self.repack()
         self.last = {}
+        self._masks = {}
 
     # ------------------------------------------------------------------------------------------------ arenas
     def _segment_of(self, name):
-        if name.startswith("backbone.") or name.startswith("input_proj."):
+        # segment 2 = everything whose gradient is produced by the closing torch.autograd.backward call: the front, and the two
+        # embedding tables behind the decoder's input (tgt_embed, label_enc) -- NOT final when the decoder backward has been issued
+        if name.startswith(("backbone.", "input_proj.", "transformer.tgt_embed.", "label_enc.")):
             return 2
         if name.startswith("transformer.encoder.") or name == "transformer.level_embed":
             return 1
@@ -452,7 +455,15 @@ class TrainEngine:
         Qt = ref_all.shape[1]
         ref = ref_all.reshape(B * Qt, 4).contiguous()
         tgt = K.cast(tgt_full.detach().reshape(B * Qt, d).contiguous(), T)
-        mask_bool = attn_mask
+        mkey = (Qt, None if dn_meta is None else (dn_meta["pad_size"], dn_meta["num_dn_group"]))
+        if attn_mask is None:
+            mask_bool = None
+        else:                               # the mask depends only on (pad_size, groups, Q): its bit-matrix form is built once per shape
+            if mkey not in self._masks:
+                if len(self._masks) > 64:
+                    self._masks.clear()
+                self._masks[mkey] = K.make_mask(attn_mask)
+            mask_bool = self._masks[mkey]
 
         # ---- decoder
         dec_saved = []

@@ -160,27 +160,62 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, weight_decay, max_norm, state):
 
 
 # ------------------------------------------------------------------------------------------------------------ decoder self-attention
-SA_IMPL = "sdpa"        # stage 1: torch scaled_dot_product_attention (library kernel) forward + backward; see DESIGN.md (training step)
+def make_mask(mask_bool):
+    """(Q,Q) bool, True = blocked (dn_components.py:121-141) -> the bit matrices of csrc/attention_train.cu in both orientations
+    (uint32 words stored as int32: word w of row i holds keys 32w .. 32w+31)"""
+    if mask_bool is None:
+        return None
+    Q = mask_bool.shape[0]
+    KP = (Q + 63) // 64 * 64
+    sh = torch.arange(32, device=mask_bool.device, dtype=torch.int64)
+
+    def bits(m):
+        full = torch.zeros((Q, KP), dtype=torch.int64, device=m.device)
+        full[:, :Q] = m
+        w = (full.view(Q, KP // 32, 32) << sh).sum(-1)
+        return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
+    return {"bool": mask_bool, "bits": bits(mask_bool), "bitsT": bits(mask_bool.t())}
 
 
-def sa_forward(qk, v, mask_bool, B, Q, heads):
-    """nn.MultiheadAttention core (deformable_transformer.py:847, 903-905) with saved context for the backward.
-    qk (B*Q, 2*d) = [q | k] projections, v (B*Q, d); mask_bool (Q,Q) True = blocked or None.  Returns (att (B*Q, d), ctx)."""
+def sa_forward(qk, v, mask, B, Q, heads):
+    """nn.MultiheadAttention core (deformable_transformer.py:847, 903-905) with what the backward needs.  qk (B*Q, 2d) = [q | k]
+    projections, v (B*Q, d); mask = make_mask(...) or None.  16-bit: the flash kernels of csrc/attention_train.cu (forward keeps only
+    the per-row log-sum-exp); fp32 parity mode: torch scaled_dot_product_attention under autograd.  Returns (att (B*Q, d), ctx)."""
     d = v.shape[1]
     hd = d // heads
+    if qk.dtype in HALF and hd == 32:
+        out = torch.empty((B * Q, d), dtype=v.dtype, device=v.device)
+        lse2 = torch.empty((B, heads, Q), dtype=torch.float32, device=v.device)
+        bits = mask["bits"] if mask is not None else None
+        _call("dtlr_mha_train_forward", _p(qk), qk.stride(0), d, _p(v), v.stride(0), _p(bits), _p(out), out.stride(0), _p(lse2), B, Q, heads,
+              hd, L.dtype_code(v), _st(v))
+        return out, ("native", qk, v, out, lse2, mask, B, Q, heads, hd)
     q4 = qk[:, :d].reshape(B, Q, heads, hd).transpose(1, 2).detach().requires_grad_(True)
     k4 = qk[:, d:].reshape(B, Q, heads, hd).transpose(1, 2).detach().requires_grad_(True)
     v4 = v.reshape(B, Q, heads, hd).transpose(1, 2).detach().requires_grad_(True)
-    allow = None if mask_bool is None else ~mask_bool
+    allow = None if mask is None else ~(mask["bool"] if isinstance(mask, dict) else mask)
     with torch.enable_grad():
         o = F.scaled_dot_product_attention(q4, k4, v4, attn_mask=allow)
     att = o.detach().transpose(1, 2).reshape(B * Q, d)
-    return att, (o, q4, k4, v4, B, Q, heads, hd)
+    return att, ("sdpa", o, q4, k4, v4, B, Q, heads, hd)
 
 
 def sa_backward(ctx, datt):
     """datt (B*Q, d) -> (dqk (B*Q, 2d), dv (B*Q, d)) of datt.dtype"""
-    o, q4, k4, v4, B, Q, heads, hd = ctx
+    if ctx[0] == "native":
+        _, qk, v, out, lse2, mask, B, Q, heads, hd = ctx
+        d = heads * hd
+        datt = datt.contiguous()
+        dqk = torch.empty((B * Q, 2 * d), dtype=qk.dtype, device=qk.device)
+        dv = torch.empty((B * Q, d), dtype=qk.dtype, device=qk.device)
+        Dv = torch.empty((B, heads, Q), dtype=torch.float32, device=qk.device)
+        bits = mask["bits"] if mask is not None else None
+        bitsT = mask["bitsT"] if mask is not None else None
+        _call("dtlr_mha_train_backward", _p(qk), qk.stride(0), d, _p(v), v.stride(0), _p(out), out.stride(0), _p(datt), datt.stride(0),
+              _p(bits), _p(bitsT), _p(lse2), _p(Dv), _p(dqk), dqk.stride(0), _p(dv), dv.stride(0), B, Q, heads, hd, L.dtype_code(v), _st(v))
+        L.LAUNCHES += 2
+        return dqk, dv
+    _, o, q4, k4, v4, B, Q, heads, hd = ctx
     g = datt.reshape(B, Q, heads, hd).transpose(1, 2).to(o.dtype)
     dq, dk, dv = torch.autograd.grad(o, (q4, k4, v4), g)
     d = heads * hd

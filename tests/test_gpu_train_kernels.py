@@ -167,3 +167,42 @@ def test_fused_clip_adamw_matches_torch():
         K.adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 0.1, state)
         assert abs(float(state[0].sqrt()) - float(g.norm())) < 1e-4 * float(g.norm())
         assert float((p - ref.detach()).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("Q,pad", [(1014, 114), (133, 0), (900, 0), (333, 60)])
+def test_self_attention_forward_backward_flash_kernels(Q, pad):
+    """csrc/attention_train.cu against an explicit fp64 softmax attention (nn.MultiheadAttention core with the boolean denoising mask:
+    regular queries may not see the DN queries, dn_components.py:121-141)"""
+    B, H, d = 2, 8, 256
+    torch.manual_seed(Q)
+    qk = (torch.randn(B * Q, 2 * d, device=DEV) * 0.7).bfloat16()
+    v = torch.randn(B * Q, d, device=DEV).bfloat16()
+    dout = torch.randn(B * Q, d, device=DEV).bfloat16()
+    mask = None
+    if pad:
+        mask = torch.zeros(Q, Q, dtype=torch.bool, device=DEV)
+        mask[pad:, :pad] = True
+        mask[:pad // 2, pad // 2:pad] = True           # two DN groups
+        mask[pad // 2:pad, :pad // 2] = True
+    mobj = K.make_mask(mask)
+    att, ctx = K.sa_forward(qk, v, mobj, B, Q, H)
+    assert ctx[0] == "native"
+    dqk, dv = K.sa_backward(ctx, dout)
+    q4 = qk[:, :d].double().view(B, Q, H, 32).transpose(1, 2).requires_grad_(True)
+    k4 = qk[:, d:].double().view(B, Q, H, 32).transpose(1, 2).requires_grad_(True)
+    v4 = v.double().view(B, Q, H, 32).transpose(1, 2).requires_grad_(True)
+    s = q4 @ k4.transpose(-1, -2) / math.sqrt(32)
+    if mask is not None:
+        s = s.masked_fill(mask, float("-inf"))
+    o = torch.softmax(s, -1) @ v4
+    ref = o.transpose(1, 2).reshape(B * Q, d)
+    gq, gk, gv = torch.autograd.grad(o, (q4, k4, v4), dout.double().view(B, Q, H, 32).transpose(1, 2))
+    assert _relmax(att, ref) < 2e-2
+    lse = torch.logsumexp(s, -1) / math.log(2.0)
+    assert float((ctx[4].double() - lse).abs().max()) < 2e-2
+    # gradients: bf16 P / dS operands (8 bits) -> compare the direction and the scale
+    for got, want in ((dqk[:, :d], gq), (dqk[:, d:], gk), (dv, gv)):
+        want = want.transpose(1, 2).reshape(B * Q, d)
+        cos = float(torch.nn.functional.cosine_similarity(got.double().flatten(), want.flatten(), dim=0))
+        assert cos > 0.999, cos
+        assert _relmax(got, want) < 5e-2

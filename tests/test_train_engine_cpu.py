@@ -122,3 +122,61 @@ def test_head_only_finetuning_step(setup):
     before = m2.class_embed[0].weight.detach().clone()
     loss = eng.step(x, tg)
     assert torch.isfinite(loss) and float((m2.class_embed[0].weight.detach() - before).abs().max()) > 0
+
+
+def _ddp_worker(rank, world, port, q):
+    import os
+    import sys
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    import warnings
+    import torch.distributed as dist
+    import train_ops_double as KD_
+    from dtlr_b200 import config as cfg_, dino as dino_, synth as synth_, train_engine as te_
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model, _, _ = dino_.build_dino(cfg_.latin_ctc_args(num_queries=60, device="cpu"))
+    synth_.load_synth_weights(model, 0)
+    model.train()
+    res = {}
+    for w_, tag in ((1, "local"), (world, "reduced")):
+        m2 = copy.deepcopy(model)
+        eng = te_.TrainEngine(m2, dtype=torch.float32, K=KD_, world_size=w_)
+        x = synth_.synth_images(1, 40, 256, seed=50 + rank)
+        tg = synth_.synth_targets(1, 166, seed=50 + rank, mean_len=5.0, std_len=1.0, min_len=3, max_len=7)
+        eng.zero_grad()
+        eng.forward_backward(x, tg)
+        if w_ > 1:
+            for wk in eng._works:
+                wk.wait()
+            assert len(eng._reduced) == len(eng.chunks) == 4          # decoder | encoder | input_proj (lr group 0), backbone (group 1)
+        res[tag] = eng.flat_g.clone()
+    gathered = [torch.zeros_like(res["local"]) for _ in range(world)]
+    dist.all_gather(gathered, res["local"])
+    mean = sum(gathered) / world
+    err = float((res["reduced"] - mean).abs().max() / mean.abs().max())
+    q.put((rank, err, float(gathered[0].abs().sum()), float(gathered[1].abs().sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce_gloo():
+    """N > 1 path of the native step (world size 2, gloo, CPU stand-in kernels): each rank's arena after the segmented asynchronous
+    all-reduces = the mean over ranks of the single-rank gradients (DistributedDataParallel semantics, finetuning.py:211-215)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=900) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, err, s0, s1 in res:
+        assert err < 1e-5, (rank, err)
+        assert s0 != s1                                               # the two ranks really had different lines

@@ -18,6 +18,10 @@ def check_device(*tensors):
     pass
 
 
+def make_mask(mask_bool):
+    return mask_bool
+
+
 # ------------------------------------------------------------------------------------------------------------ forward pieces
 def gemm(a, w, bias=None, residual=None, relu=0, out_dtype=None, out=None):
     c = a.float() @ w.float().t()
