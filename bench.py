@@ -229,16 +229,18 @@ def train_step_leg(device, rank, world, local, steps=5, warmup=3, impl="native")
 
         def step():
             return eng.step(x, tg)
-        what = ("forward(samples, targets) + loss_CTC + backward + clip + AdamW on dtlr kernels: encoder / decoder / heads forward and "
-                "backward (tcgen05 GEMM, dgrad, MN-major wgrad; LayerNorm / MSDA / CTC backward kernels), fused clip + AdamW over flat fp32 "
-                "arenas; ResNet front + input_proj: torch autograd over cuDNN (TF32); decoder self-attention: torch SDPA")
+        what = ("forward(samples, targets) + loss_CTC + backward + clip + AdamW on dtlr kernels in both directions: ResNet-50 layer2-4 + "
+                "input_proj / GroupNorm, encoder, decoder (flash self-attention forward + backward with the DN mask), heads -- tcgen05 GEMM / "
+                "implicit-GEMM conv forward, dgrad on the same kernels, MN-major tcgen05 wgrad, LayerNorm / GroupNorm / ReLU / MSDA / CTC "
+                "backward kernels, fused clip + AdamW over flat fp32 arenas; bf16 operands, fp32 accumulation and gradient stream; torch "
+                "only for index bookkeeping (masks, DN query table, embedding-table gradients)")
         coll = ("%d async NCCL all-reduces of the flat fp32 gradient arena (%d gradients, %.0f MB) issued as each segment's backward "
                 "completes (decoder | encoder | front)" % (len(eng.chunks), n_grad, n_grad * 4 / 1e6))
     else:
         net = model
         if world > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
-            net = DDP(model, device_ids=[local], static_graph=True, gradient_as_bucket_view=True, bucket_cap_mb=64)
+            net = DDP(model, device_ids=[local], find_unused_parameters=True, gradient_as_bucket_view=True, bucket_cap_mb=64)   # (finetuning.py:211-215)
         params = [p for p in net.parameters() if p.requires_grad]
         opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4)
         n_grad = sum(p.numel() for p in params)
@@ -468,8 +470,11 @@ def main():
         try:
             train = train_step_leg(device, rank, world, local, impl=args.train_impl)
             if args.train_impl == "native" and args.train_ab:
-                train["torch_autograd_ab"] = {k: v for k, v in train_step_leg(device, rank, world, local, impl="torch").items()
-                                              if k in ("value", "ms_per_step", "impl")}
+                try:
+                    train["torch_autograd_ab"] = {k: v for k, v in train_step_leg(device, rank, world, local, impl="torch").items()
+                                                  if k in ("value", "ms_per_step", "impl")}
+                except Exception as e:
+                    train["torch_autograd_ab"] = {"error": repr(e)[:200]}
         except Exception as e:      # a secondary leg must never cost the headline line
             train = {"error": repr(e)[:300]}
             try:

@@ -569,6 +569,217 @@ pack_weights_kernel(const long long* __restrict__ table, const int* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------- ResNet / input_proj backward pieces
+// (reference: torch autograd over cuDNN for models/dino/backbone.py:109-128 layer2-4 and models/dino/dino.py:118-135 input_proj)
+// v = y > 0 ? dy : 0 -- the ReLU that closes a Bottleneck (y = relu(conv3 + identity)): the masked gradient is needed twice, as fp32 (it
+// continues along the identity path) and as the 16-bit operand of conv3's dgrad / wgrad.  dy32 is updated in place.
+template <typename T>
+__global__ void relu_bwd_dual_kernel(float* __restrict__ dy32, const T* __restrict__ y, T* __restrict__ out16, long long n8) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float d[8], yy[8];
+        ld8<float>(dy32 + i * 8, d);
+        ld8<T>(y + i * 8, yy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = yy[k] > 0.f ? d[k] : 0.f;
+        st8<float>(dy32 + i * 8, d);
+        if (out16) st8<T>(out16 + i * 8, d);
+    }
+}
+
+// nn.GroupNorm(32, 256) backward (models/dino/dino.py:121-124) for one feature level.  x fp32 [B, HW, 256] = the saved conv output;
+// dy fp32: row (b, hw) at dy + (b * dy_stride_b + hw) * 256 (a level slice of the (B, S, 256) token-gradient tensor).
+// CTA = (32-channel block = 4 groups, image); thread = (row lane 0..63, group 0..3) walks the HW rows three times (statistics, the two
+// projections, the output) -- the slice (<= 655 KB per image) stays in L2.  dgamma / dbeta: one atomic per channel per image.
+template <typename T>
+__global__ void __launch_bounds__(256)
+groupnorm8_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long dy_stride_b, const float* __restrict__ gamma,
+                      T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, float eps) {
+    __shared__ float red[64][4][2];
+    __shared__ float stat[4][2];
+    __shared__ float chan[64][32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.y, c0 = blockIdx.x * 32;
+    const int gq = threadIdx.x & 3, rl = threadIdx.x >> 2;
+    const int ch = c0 + gq * 8;
+    const float* xb = x + (size_t)b * HW * C + ch;
+    const float* db = dy + (size_t)b * dy_stride_b * C + ch;
+    float g[8];
+    ld8<float>(gamma + ch, g);
+    auto group_reduce = [&](float a, float c, float& ra, float& rc) {
+        red[rl][gq][0] = a;
+        red[rl][gq][1] = c;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+            for (int r = 0; r < 64; ++r) t += red[r][threadIdx.x >> 1][threadIdx.x & 1];
+            stat[threadIdx.x >> 1][threadIdx.x & 1] = t;
+        }
+        __syncthreads();
+        ra = stat[gq][0];
+        rc = stat[gq][1];
+        __syncthreads();
+    };
+    float s = 0.f, ss = 0.f;
+    for (int r = rl; r < HW; r += 64) {
+        float v[8];
+        ld8<float>(xb + (size_t)r * C, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s += v[k]; ss = fmaf(v[k], v[k], ss); }
+    }
+    float S1, S2;
+    group_reduce(s, ss, S1, S2);
+    const float inv_n = 1.f / (float)(HW * 8);
+    const float mean = S1 * inv_n;
+    const float rstd = rsqrtf(fmaxf(S2 * inv_n - mean * mean, 0.f) + eps);
+    float a1 = 0.f, a2 = 0.f, dg[8], dbt[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dg[k] = dbt[k] = 0.f;
+    for (int r = rl; r < HW; r += 64) {
+        float v[8], d[8];
+        ld8<float>(xb + (size_t)r * C, v);
+        ld8<float>(db + (size_t)r * C, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = (v[k] - mean) * rstd, gy = d[k] * g[k];
+            a1 += gy;
+            a2 = fmaf(gy, xh, a2);
+            dg[k] = fmaf(d[k], xh, dg[k]);
+            dbt[k] += d[k];
+        }
+    }
+    float A1, A2;
+    group_reduce(a1, a2, A1, A2);
+    A1 *= inv_n;
+    A2 *= inv_n;
+    for (int r = rl; r < HW; r += 64) {
+        float v[8], d[8], o[8];
+        ld8<float>(xb + (size_t)r * C, v);
+        ld8<float>(db + (size_t)r * C, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float xh = (v[k] - mean) * rstd;
+            o[k] = rstd * (d[k] * g[k] - A1 - xh * A2);
+        }
+        st8<T>(dx + ((size_t)b * HW + r) * C + ch, o);
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (!dst) continue;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) chan[rl][gq * 8 + k] = pass == 0 ? dg[k] : dbt[k];
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = 0.f;
+            for (int r = 0; r < 64; ++r) t += chan[r][threadIdx.x];
+            atomicAdd(dst + c0 + threadIdx.x, t);
+        }
+    }
+}
+
+// Transposed convolution as a gather: dx[b, yi, xi, c] (+)= sum over the taps (kh, kw) whose output pixel yo = (yi + pad - kh) / stride,
+// xo = (xi + pad - kw) / stride exists, of dcol[(b, yo, xo), (kh * KW + kw) * C + c].  dcol fp32 [B*Ho*Wo, ldc] = dY . W (dtlr_gemm against
+// the transposed weight copy); used for the stride-2 3x3 convolutions, the strided 1x1 downsamples (KH = KW = 1: a row scatter) and
+// input_proj[3] (reference: cuDNN's strided dgrad kernels).
+__global__ void __launch_bounds__(256)
+col2im_kernel(const float* __restrict__ dcol, int ldc, float* __restrict__ dx, int B, int H, int W, int C, int KH, int KW, int stride, int pad,
+              int Ho, int Wo, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = (long long)B * H * W * (C / 4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % (C / 4));
+        long long p = i / (C / 4);
+        const int xi = (int)(p % W);
+        p /= W;
+        const int yi = (int)(p % H), b = (int)(p / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kh = 0; kh < KH; ++kh) {
+            const int ty = yi + pad - kh;
+            if (ty < 0 || (ty % stride) != 0) continue;
+            const int yo = ty / stride;
+            if (yo >= Ho) continue;
+            for (int kw = 0; kw < KW; ++kw) {
+                const int tx = xi + pad - kw;
+                if (tx < 0 || (tx % stride) != 0) continue;
+                const int xo = tx / stride;
+                if (xo >= Wo) continue;
+                const float4 v = *reinterpret_cast<const float4*>(dcol + ((size_t)(b * Ho + yo) * Wo + xo) * ldc + (size_t)(kh * KW + kw) * C + c4 * 4);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(dx + (((size_t)b * H + yi) * W + xi) * C + c4 * 4);
+        if (accumulate) { const float4 q = *o; acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w; }
+        *o = acc;
+    }
+}
+
+// Operand copies of the convolution weights with FrozenBatchNorm folded in (backbone.py:62-72: w' = w * scale[cout]), one launch over a
+// device table.  Entry (10 x int64): src fp32 [Cout, Cin, taps] (torch layout), Cout, Cin, taps, scale fp32 [Cout] | 0,
+// fwd dst [Cout, taps*Cin] (K order tap, cin -- the im2col / implicit-GEMM order), bwd dst | 0, bwd kind, bwd pitch, first element.
+//   bwd kind 1: plain transpose [taps*Cin, pitch >= Cout]  (dgrad of 1x1 convs; dcol = dY . W' for the strided convs)
+//   bwd kind 2: flipped taps    [Cin, taps*Cout]: dst[ci][(taps-1-t)*Cout + co]  (stride-1 3x3 dgrad as a convolution over dY)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_conv_kernel(const long long* __restrict__ table, int n_entries, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_entries - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[(size_t)mid * 10 + 9] <= e) lo = mid; else hi = mid - 1;
+        }
+        const long long* t = table + (size_t)lo * 10;
+        const float* src = reinterpret_cast<const float*>(t[0]);
+        const int Cin = (int)t[2], taps = (int)t[3];
+        const int Cout = (int)t[1];
+        const float* scale = reinterpret_cast<const float*>(t[4]);
+        T* fwd = reinterpret_cast<T*>(t[5]);
+        T* bwd = reinterpret_cast<T*>(t[6]);
+        const long long el = e - t[9];
+        const int tap = (int)(el % taps);
+        const int ci = (int)((el / taps) % Cin);
+        const int co = (int)(el / ((long long)taps * Cin));
+        const float v = src[el] * (scale ? scale[co] : 1.f);
+        st1<T>(fwd + (size_t)co * taps * Cin + (size_t)tap * Cin + ci, v);
+        if (bwd) {
+            if (t[7] == 1) st1<T>(bwd + ((size_t)tap * Cin + ci) * t[8] + co, v);
+            else st1<T>(bwd + (size_t)ci * t[8] + (size_t)(taps - 1 - tap) * Cout + co, v);
+        }
+    }
+}
+
+// The inverse for the weight GRADIENTS: dtlr_wgrad produced dW' in the forward operand layout [Cout, taps*Cin] (a zeroed scratch arena);
+// the parameter gradient is d w[co][ci][t] += scale[co] * dW'[co][t*Cin + ci].  Entry (6 x int64): scratch ptr, grad ptr, Cout, Cin, taps,
+// scale | 0; elem_start prefix in entry[...] is passed separately.
+__global__ void __launch_bounds__(256)
+unpack_conv_grads_kernel(const long long* __restrict__ table, const long long* __restrict__ elem_start, int n_entries, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_entries - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (elem_start[mid] <= e) lo = mid; else hi = mid - 1;
+        }
+        const long long* t = table + (size_t)lo * 6;
+        const float* tmp = reinterpret_cast<const float*>(t[0]);
+        float* grad = reinterpret_cast<float*>(t[1]);
+        const int Cin = (int)t[3], taps = (int)t[4];
+        const float* scale = reinterpret_cast<const float*>(t[5]);
+        const long long el = e - elem_start[lo];
+        const int tap = (int)(el % taps);
+        const int ci = (int)((el / taps) % Cin);
+        const int co = (int)(el / ((long long)taps * Cin));
+        grad[el] += tmp[(size_t)co * taps * Cin + (size_t)tap * Cin + ci] * (scale ? scale[co] : 1.f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- clip_grad_norm_ + AdamW
 // state (device, fp32[4]): [0] = sum of squares of all gradients of the step, [1] = step count.
 __global__ void optim_begin_kernel(float* state) {
@@ -775,6 +986,48 @@ extern "C" int dtlr_adamw(float* p, const float* g, float* m, float* v, long lon
                           float weight_decay, float max_norm, const float* state, void* stream) {
     if (n == 0) return DTLR_OK;
     DTLR_LAUNCH(adamw_kernel, grid_cap(n, 256, 16), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, max_norm, state);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_relu_bwd_dual(float* dy32, const void* y, void* out16, long long n, int dtype, void* stream) {
+    DTLR_CHECK_ARG((n % 8) == 0, "relu_bwd_dual: element count must be a multiple of 8");
+    if (n == 0) return DTLR_OK;
+    DISPATCH_T(dtype, DTLR_LAUNCH((relu_bwd_dual_kernel<T>), grid_cap(n / 8, 256, 16), 256, 0, (cudaStream_t)stream, dy32, (const T*)y, (T*)out16, n / 8);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_groupnorm_bwd(const float* x, const float* dy, long long dy_stride_b, const float* gamma, void* dx, float* dgamma,
+                                  float* dbeta, int B, int HW, int C, int G, float eps, int out_dtype, void* stream) {
+    DTLR_CHECK_ARG(C % G == 0 && C / G == 8 && (C % 32) == 0, "groupnorm_bwd: 8 channels per group (GroupNorm(32, 256)) only, got C=%d G=%d", C, G);
+    if (B == 0 || HW == 0) return DTLR_OK;
+    dim3 grid(C / 32, B);
+    DISPATCH_T(out_dtype, DTLR_LAUNCH((groupnorm8_bwd_kernel<T>), grid, 256, 0, (cudaStream_t)stream, x, dy, dy_stride_b, gamma, (T*)dx, dgamma, dbeta, HW, C, eps);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_col2im(const float* dcol, int ldc, float* dx, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho,
+                           int Wo, int accumulate, void* stream) {
+    DTLR_CHECK_ARG((C % 4) == 0 && (ldc % 4) == 0 && ldc >= KH * KW * C && stride >= 1, "col2im: bad sizes");
+    const long long total = (long long)B * H * W * (C / 4);
+    if (total == 0) return DTLR_OK;
+    DTLR_LAUNCH(col2im_kernel, grid_cap(total, 256, 16), 256, 0, (cudaStream_t)stream, dcol, ldc, dx, B, H, W, C, KH, KW, stride, pad, Ho, Wo, accumulate);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_pack_conv(const long long* table, int n_entries, long long total_elems, int dtype, void* stream) {
+    if (n_entries <= 0 || total_elems <= 0) return DTLR_OK;
+    DISPATCH_T(dtype, DTLR_LAUNCH((pack_conv_kernel<T>), grid_cap(total_elems, 256, 16), 256, 0, (cudaStream_t)stream, table, n_entries, total_elems);)
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_unpack_conv_grads(const long long* table, const long long* elem_start, int n_entries, long long total_elems, void* stream) {
+    if (n_entries <= 0 || total_elems <= 0) return DTLR_OK;
+    DTLR_LAUNCH(unpack_conv_grads_kernel, grid_cap(total_elems, 256, 16), 256, 0, (cudaStream_t)stream, table, elem_start, n_entries, total_elems);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

@@ -70,7 +70,9 @@ class Lin:
 
 class TrainEngine:
     def __init__(self, model, param_groups=None, lr=1e-4, lr_backbone=1e-5, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=0.1, dtype=torch.bfloat16, K=None, process_group=None, world_size=1):
+                 max_norm=0.1, dtype=torch.bfloat16, K=None, process_group=None, world_size=1, native_front=None):
+        if native_front is None:
+            native_front = K is None            # the torch stand-in of tests/ keeps the front under autograd
         if K is None:
             from . import train_ops as K_
             K = K_
@@ -89,7 +91,11 @@ class TrainEngine:
                             {"params": [p for n, p in named if "backbone" in n], "lr": lr_backbone, "weight_decay": weight_decay}]
         self._build_arena(param_groups, lr, weight_decay)
         self._build_linears()
-        self.repack()
+        self.front = None
+        if native_front:
+            from .train_front import NativeFront
+            self.front = NativeFront(self)          # (packs its own operand copies)
+        self.repack(front=False)
         self.last = {}
         self._masks = {}
 
@@ -213,8 +219,11 @@ class TrainEngine:
         self.pack_tiles = torch.tensor(tiles, dtype=torch.int32).to(self.device)
         self.pack_n, self.pack_total = len(rows), tiles[-1]
 
-    def repack(self):
-        """16-bit (or fp32) operand copies of every Linear from the fp32 masters: after construction and after every optimizer step"""
+    def repack(self, front=True):
+        """16-bit (or fp32) operand copies of every Linear / convolution from the fp32 masters: after construction and after every
+        optimizer step"""
+        if front and self.front is not None:
+            self.front.repack()
         if hasattr(self.K, "repack_lins"):          # (the torch stand-in of tests/ has no raw-pointer table walker)
             self.K.repack_lins(self.all_lins, self.T)
         else:
@@ -420,14 +429,20 @@ class TrainEngine:
         d = tr.d_model
         nopad = bool(getattr(samples, "nopad", False))
         live_seg = {e[3] for e in self.layout}
-        train_front, train_enc = 2 in live_seg, 1 in live_seg
-        train_dec = 0 in live_seg
-        src_flatten, pos32, mask_flatten, level_hw, masks = self._front(samples)
+        train_front = any(n.startswith(("backbone.", "input_proj.")) for n, *_ in self.layout)
+        train_enc = 1 in live_seg
+        train_dec = 0 in live_seg or 2 in live_seg
+        src_flatten = None
+        if self.front is not None:
+            src, pos32, mask_flatten, level_hw, masks = self.front.forward(samples)
+        else:
+            src_flatten, pos32, mask_flatten, level_hw, masks = self._front(samples)
         geo = self._geometry(B, level_hw, masks, mask_flatten, nopad)
         S = geo["S"]
         geo["ref_enc"] = K.enc_ref_points(geo["vr"], geo)
         pos = K.cast(pos32.reshape(B * S, d), T)
-        src = K.cast(src_flatten.detach().reshape(B * S, d), T)
+        if src_flatten is not None:
+            src = K.cast(src_flatten.detach().reshape(B * S, d), T)
 
         # ---- encoder
         q = K.add(src, pos)
@@ -527,8 +542,11 @@ class TrainEngine:
             roots, grads = [tgt_full], [d_tgt0.view(B, Qt, d)]
             if train_front:
                 dsrc0 = K.add_cast(d_y, dq, None, F32)                 # q0 = src0 + pos: both paths reach src_flatten
-                roots.append(src_flatten)
-                grads.append(dsrc0.view(B, S, d))
+                if self.front is not None:
+                    self.front.backward(dsrc0)
+                else:
+                    roots.append(src_flatten)
+                    grads.append(dsrc0.view(B, S, d))
         else:
             roots, grads = [tgt_full], [d_tgt0.view(B, Qt, d)]
         roots_g = [(r, g) for r, g in zip(roots, grads) if r.requires_grad]

@@ -338,6 +338,26 @@ int dtlr_mha_train_backward(const void* qk, int ld_qk, int k_off, const void* v,
                             float* D_scratch, void* dqk, int ld_dqk, void* dv, int ld_dv, int B, int Q, int heads, int head_dim,
                             int dtype, void* stream);
 
+/* Backward pieces of the ResNet-50 layer2-4 / input_proj front of the fine-tune step (reference: torch autograd over cuDNN for
+ * models/dino/backbone.py:109-128 and models/dino/dino.py:118-135), csrc/train.cu.  1x1 convolutions on NHWC rows are Linears
+ * (dtlr_wgrad / dtlr_gemm); 3x3 wgrad = dtlr_im2col + dtlr_wgrad; stride-1 3x3 dgrad = dtlr_conv2d_nhwc over dY with the flipped
+ * weight copy; strided dgrad = dtlr_gemm (dcol = dY . W') + dtlr_col2im.
+ * dtlr_relu_bwd_dual: v = y > 0 ? dy32 : 0 written back to dy32 (fp32) and to out16 (`dtype`, may be NULL).
+ * dtlr_groupnorm_bwd: nn.GroupNorm(32, 256) backward of one level: x fp32 [B, HW, C] (saved input), dy fp32 rows at
+ *   (b * dy_stride_b + hw) * C, dx [B*HW, C] of out_dtype, dgamma / dbeta fp32 [C] accumulated (may be NULL).
+ * dtlr_col2im: dx fp32 [B,H,W,C] (+)= gather of dcol fp32 [B*Ho*Wo, ldc] (K order kh, kw, c) -- the transposed convolution.
+ * dtlr_pack_conv: FrozenBatchNorm-folded 16-bit (or fp32) operand copies of convolution weights, entry = 10 int64 {src fp32
+ *   [Cout,Cin,taps], Cout, Cin, taps, scale|0, fwd dst [Cout, taps*Cin], bwd dst|0, bwd kind (1 transpose, 2 flipped taps), bwd pitch,
+ *   first element index}.  dtlr_unpack_conv_grads: grad[co][ci][t] += scale[co] * scratch[co][t*Cin+ci], entry = 6 int64 {scratch, grad,
+ *   Cout, Cin, taps, scale|0}, elem_start int64 [n]. */
+int dtlr_relu_bwd_dual(float* dy32, const void* y, void* out16, long long n, int dtype, void* stream);
+int dtlr_groupnorm_bwd(const float* x, const float* dy, long long dy_stride_b, const float* gamma, void* dx, float* dgamma,
+                       float* dbeta, int B, int HW, int C, int G, float eps, int out_dtype, void* stream);
+int dtlr_col2im(const float* dcol, int ldc, float* dx, int B, int H, int W, int C, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                int accumulate, void* stream);
+int dtlr_pack_conv(const long long* table, int n_entries, long long total_elems, int dtype, void* stream);
+int dtlr_unpack_conv_grads(const long long* table, const long long* elem_start, int n_entries, long long total_elems, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

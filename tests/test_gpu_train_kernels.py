@@ -206,3 +206,96 @@ def test_self_attention_forward_backward_flash_kernels(Q, pad):
         cos = float(torch.nn.functional.cosine_similarity(got.double().flatten(), want.flatten(), dim=0))
         assert cos > 0.999, cos
         assert _relmax(got, want) < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------- front (ResNet / input_proj) pieces
+def test_groupnorm_bwd_against_autograd():
+    from dtlr_b200 import ops
+    import ctypes
+    B, HW, C, S, start = 3, 192, 256, 912, 640
+    x = (torch.randn(B, HW, C, device=DEV) * 1.7 + 0.2).requires_grad_(True)
+    gamma = (torch.rand(C, device=DEV) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, device=DEV).requires_grad_(True)
+    dtok = torch.randn(B, S, C, device=DEV)
+    y = torch.nn.functional.group_norm(x.transpose(1, 2), 32, gamma, beta, 1e-5).transpose(1, 2)
+    gx, gg, gb = torch.autograd.grad(y, (x, gamma, beta), dtok[:, start:start + HW])
+    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 1e-2)):
+        dx = torch.empty(B * HW, C, device=DEV, dtype=dtype)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        ops._call("dtlr_groupnorm_bwd", ops._p(x.detach()), ops._p(dtok.view(B * S, C)[start:]), ctypes.c_longlong(S), ops._p(gamma.detach()),
+                  ops._p(dx), ops._p(dg), ops._p(db), B, HW, C, 32, ctypes.c_float(1e-5), L.dtype_code(dx), ops._st(dx))
+        assert _relmax(dx, gx.reshape(B * HW, C)) < tol
+        assert _relmax(dg, gg) < 1e-4 and _relmax(db, gb) < 1e-4
+
+
+@pytest.mark.parametrize("k,stride,pad,H,W", [(3, 2, 1, 5, 128), (3, 2, 1, 3, 64), (1, 2, 0, 5, 128), (3, 1, 1, 3, 64), (3, 2, 1, 2, 32)])
+def test_col2im_is_the_transposed_convolution(k, stride, pad, H, W):
+    from dtlr_b200 import ops
+    B, C, Cout = 2, 64, 32
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    w = torch.randn(Cout, C, k, k, device=DEV)
+    dy = torch.randn(B, Cout, Ho, Wo, device=DEV)
+    x = torch.zeros(B, C, H, W, device=DEV, requires_grad=True)
+    (want,) = torch.autograd.grad(torch.nn.functional.conv2d(x, w, stride=stride, padding=pad), x, dy)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k * C)                       # forward operand order (tap, cin)
+    dcol = (dy.permute(0, 2, 3, 1).reshape(-1, Cout) @ wp).contiguous()        # dY . W'
+    dx = torch.full((B * H * W, C), 7.0, device=DEV)
+    ops._call("dtlr_col2im", ops._p(dcol), dcol.stride(0), ops._p(dx), B, H, W, C, k, k, stride, pad, Ho, Wo, 0, ops._st(dx))
+    assert _relmax(dx, want.permute(0, 2, 3, 1).reshape(-1, C)) < 1e-5
+    ops._call("dtlr_col2im", ops._p(dcol), dcol.stride(0), ops._p(dx), B, H, W, C, k, k, stride, pad, Ho, Wo, 1, ops._st(dx))
+    assert _relmax(dx, 2 * want.permute(0, 2, 3, 1).reshape(-1, C)) < 1e-5
+
+
+def test_relu_bwd_dual():
+    from dtlr_b200 import ops
+    import ctypes
+    y = torch.randn(4096, 512, device=DEV).bfloat16()
+    dy = torch.randn(4096, 512, device=DEV)
+    want = torch.where(y > 0, dy, torch.zeros_like(dy))
+    out = torch.empty_like(y)
+    ops._call("dtlr_relu_bwd_dual", ops._p(dy), ops._p(y), ops._p(out), ctypes.c_longlong(dy.numel()), L.dtype_code(y), ops._st(y))
+    assert torch.equal(dy, want) and torch.equal(out, want.bfloat16())
+
+
+def test_native_front_matches_autograd_of_the_module_front():
+    """dtlr_b200/train_front.py (fp32 mode) against torch autograd of backbone + input_proj: src_flatten, and -- for a random
+    d loss / d src_flatten -- the gradient of every layer2-4 / input_proj parameter"""
+    import copy
+    from gpu_common import build_model
+    from dtlr_b200 import synth, train_engine
+    from dtlr_b200.misc import nested_tensor_from_tensor_list
+    model, _, _ = build_model(300)
+    model.train()
+    x = synth.synth_images(2, 40, 1024, seed=9).cuda()
+    m2 = copy.deepcopy(model)
+    eng = train_engine.TrainEngine(m2, dtype=torch.float32)
+    assert eng.front is not None
+    eng.zero_grad()
+    src, pos, mask_flatten, level_hw, masks = eng.front.forward(nested_tensor_from_tensor_list(x))
+    eng_torch = train_engine.TrainEngine(copy.deepcopy(model), dtype=torch.float32, native_front=False)
+    ref_src, ref_pos, _, ref_hw, _ = eng_torch._front(nested_tensor_from_tensor_list(x))
+    assert list(level_hw) == [tuple(v) for v in ref_hw]
+    assert _relmax(src, ref_src.reshape(src.shape)) < 1e-4 and _relmax(pos, ref_pos) < 1e-5
+    g = torch.randn_like(src)
+    eng_torch.zero_grad()
+    ref_src.backward(g.view(ref_src.shape))
+    eng.front.backward(g.clone())
+    ref_named = dict(eng_torch.model.named_parameters())
+    worst, worst_cos, errs = (0.0, None), (1.0, None), []
+    for n, p in m2.named_parameters():
+        if not (n.startswith("backbone.") or n.startswith("input_proj.")) or not p.requires_grad:
+            continue
+        gr, gn = eng_torch.grad(ref_named[n]), eng.grad(p)
+        err = _relmax(gn, gr)
+        cos = float(torch.nn.functional.cosine_similarity(gn.double().flatten(), gr.double().flatten(), dim=0))
+        errs.append(err)
+        if err > worst[0]:
+            worst = (err, n)
+        if cos < worst_cos[0]:
+            worst_cos = (cos, n)
+    errs.sort()
+    print("native front: worst parameter-gradient error %.3e (%s), median %.3e, worst cosine %.7f (%s)" % (worst + (errs[len(errs) // 2],) + worst_cos))
+    # a ReLU unit whose pre-activation is within round-off of zero flips between the two evaluation orders; on the 2 x 32 map of layer4
+    # (128 positions) one flipped unit moves a row of a weight gradient by ~1/sqrt(128): bound the maximum loosely, the typical
+    # error and the direction tightly
+    assert worst[0] < 0.15 and errs[len(errs) // 2] < 2e-4 and worst_cos[0] > 0.9995, (worst, worst_cos)
