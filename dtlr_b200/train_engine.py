@@ -143,13 +143,18 @@ class TrainEngine:
                 p.grad = self.flat_g[o:o + k].view(p.shape)
                 self.grad_of[id(p)] = p.grad
         # optimizer ranges (one per group) and all-reduce chunks (one per (group, segment) run)
-        self.group_ranges, self.chunks = [], []
+        # `param_groups` mirrors torch.optim.Optimizer.param_groups (lr / weight_decay are read at every step, so a scheduler -- or
+        # the reference's per-epoch lr drop, finetuning.py:616-622 -- only has to write g["lr"])
+        self.group_ranges, self.chunks, self.param_groups = [], [], []
         for gi, g in enumerate(param_groups):
             idx = [e for e in layout if e[2] == gi]
             if not idx:
                 continue
             a, b = idx[0][4], idx[-1][4] + (idx[-1][5] + 3) // 4 * 4
-            self.group_ranges.append((a, b, float(g.get("lr", lr)), float(g.get("weight_decay", weight_decay))))
+            pg = {"lr": float(g.get("lr", lr)), "weight_decay": float(g.get("weight_decay", weight_decay)), "params": [e[1] for e in idx]}
+            pg["initial_lr"] = pg["lr"]
+            self.param_groups.append(pg)
+            self.group_ranges.append((a, b, pg))
         run = None
         for n, p, gi, seg, o, k in layout:
             end = o + (k + 3) // 4 * 4
@@ -580,9 +585,9 @@ class TrainEngine:
                 w.wait()
         K.optim_begin(self.state)
         K.grad_sumsq(self.flat_g, self.state)
-        for a, b, lr, wd in self.group_ranges:
-            K.adamw(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], lr, self.betas[0], self.betas[1], self.eps,
-                    wd, self.max_norm, self.state)
+        for a, b, pg in self.group_ranges:
+            K.adamw(self.flat_p[a:b], self.flat_g[a:b], self.flat_m[a:b], self.flat_v[a:b], pg["lr"], self.betas[0], self.betas[1], self.eps,
+                    pg["weight_decay"], self.max_norm, self.state)
         self.repack()
         if getattr(self.model, "_engine", None) is not None:
             self.model.invalidate_engine()
@@ -596,3 +601,23 @@ class TrainEngine:
 
     def grad_norm(self):
         return float(torch.sqrt(self.state[0]))
+
+    # ------------------------------------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """optimizer state for the reference's checkpoint dict (finetuning.py:664-674 saves 'optimizer'): both moments, the step count and
+        the arena layout they refer to (parameter name -> offset, size), plus the current learning rates"""
+        return {"step": float(self.state[1]), "exp_avg": self.flat_m.detach().cpu(), "exp_avg_sq": self.flat_v.detach().cpu(),
+                "layout": [(n, o, k) for n, p, gi, seg, o, k in self.layout],
+                "param_groups": [{"lr": g["lr"], "weight_decay": g["weight_decay"], "initial_lr": g["initial_lr"]} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        mine = {n: (o, k) for n, p, gi, seg, o, k in self.layout}
+        m = sd["exp_avg"].to(self.device)
+        v = sd["exp_avg_sq"].to(self.device)
+        for n, o, k in sd["layout"]:           # by NAME: the arena order may differ (other param groups / frozen sets)
+            if n in mine and mine[n][1] == k:
+                self.flat_m[mine[n][0]:mine[n][0] + k].copy_(m[o:o + k])
+                self.flat_v[mine[n][0]:mine[n][0] + k].copy_(v[o:o + k])
+        self.state[1] = float(sd["step"])
+        for g, s_ in zip(self.param_groups, sd.get("param_groups", [])):
+            g.update(s_)

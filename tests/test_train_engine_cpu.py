@@ -180,3 +180,36 @@ def test_two_rank_gradient_all_reduce_gloo():
     for rank, err, s0, s1 in res:
         assert err < 1e-5, (rank, err)
         assert s0 != s1                                               # the two ranks really had different lines
+
+
+def test_finetune_loop_scheduler_and_checkpoint_resume(setup):
+    """dtlr_b200/finetune.train_one_epoch_CTC (mirror of reference engine.py:172-274) + TrainEngine.state_dict round trip: two steps in
+    one run == one step, checkpoint, resume in a fresh engine, one more step"""
+    from types import SimpleNamespace
+    from dtlr_b200 import finetune
+    model, crit, x, tg = setup
+    batches = [(x, tg), (x.flip(0), list(reversed(tg)))]
+
+    def fresh():
+        m = copy.deepcopy(model)
+        return m, train_engine.TrainEngine(m, lr=1e-3, lr_backbone=1e-4, weight_decay=1e-2, max_norm=0.1, dtype=torch.float32, K=KD)
+
+    m_a, e_a = fresh()
+    st = finetune.train_one_epoch_CTC(e_a, batches, "cpu", 0, args=SimpleNamespace(max_iterations=100, onecyclelr=False))
+    assert st["steps"] == 2 and st["loss"] > 0
+    m_b, e_b = fresh()
+    finetune.train_one_epoch_CTC(e_b, batches[:1], "cpu", 0)
+    ck_model, ck_opt = copy.deepcopy(m_b.state_dict()), e_b.state_dict()
+    m_c = copy.deepcopy(model)
+    m_c.load_state_dict(ck_model)
+    e_c = train_engine.TrainEngine(m_c, lr=1e-3, lr_backbone=1e-4, weight_decay=1e-2, max_norm=0.1, dtype=torch.float32, K=KD)
+    e_c.load_state_dict(ck_opt)
+    finetune.train_one_epoch_CTC(e_c, batches[1:], "cpu", 1)
+    pa = dict(m_a.named_parameters())
+    for n, p in m_c.named_parameters():
+        assert float((p.detach() - pa[n].detach()).abs().max()) <= 1e-6 * (1 + float(pa[n].abs().max())), n
+    # the iteration budget counts lines (reference engine.py:259-261) and a scheduler only has to write param_groups[i]["lr"]
+    m_d, e_d = fresh()
+    st = finetune.train_one_epoch_CTC(e_d, batches, "cpu", 0, args=SimpleNamespace(max_iterations=2, onecyclelr=True),
+                                      lr_scheduler=lambda: e_d.param_groups[0].__setitem__("lr", e_d.param_groups[0]["lr"] * 0.5))
+    assert st["steps"] == 1 and abs(e_d.param_groups[0]["lr"] - 5e-4) < 1e-12
