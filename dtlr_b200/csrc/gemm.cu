@@ -496,7 +496,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             float g[EPC];
                             unpack_chunk<OutT>(rres[it], g);
 #pragma unroll
-                            for (int k = 0; k < EPC; ++k) f[k] += g[k];
+                            for (int k = 0; k < EPC; ++k) f[k] = e.relu == 3 ? (g[k] > 0.f ? f[k] : 0.f) : f[k] + g[k];
                         }
                         if (e.relu == 2) {
 #pragma unroll
@@ -515,7 +515,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const int ch = col / EPC;
                     const OutT x = *reinterpret_cast<const OutT*>(my_rows + (size_t)r * S::ROW_BYTES + ((ch ^ (r & 7)) * 16) + (col % EPC) * sizeof(OutT));
                     float f = (float)x;
-                    if (e.residual) f += (float)reinterpret_cast<const OutT*>(e.residual)[(size_t)grow * e.ldr + n0 + col];
+                    if (e.residual) {
+                        const float r = (float)reinterpret_cast<const OutT*>(e.residual)[(size_t)grow * e.ldr + n0 + col];
+                        f = e.relu == 3 ? (r > 0.f ? f : 0.f) : f + r;
+                    }
                     if (e.relu == 2) f = fmaxf(f, 0.f);
                     reinterpret_cast<OutT*>(e.C)[(size_t)grow * e.ldc + n0 + col] = (OutT)f;
                 }
@@ -755,7 +758,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             float g[EPC];
                             unpack_chunk<OutT>(*reinterpret_cast<const uint4*>(srow + ((k ^ swz) * 16)), g);
 #pragma unroll
-                            for (int i = 0; i < EPC; ++i) v[k * EPC + i] += g[i];
+                            for (int i = 0; i < EPC; ++i) v[k * EPC + i] = e.relu == 3 ? (g[i] > 0.f ? v[k * EPC + i] : 0.f) : v[k * EPC + i] + g[i];
                         }
                     } else {
                         if (lane == 0) tma_store_wait_read<0>();         // the previous store has finished reading this buffer
@@ -846,7 +849,10 @@ sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, 
             float v = acc[i][j];
             if (e.bias) v += e.bias[gn];
             if (e.relu == 1) v = fmaxf(v, 0.f);
-            if (R) v += R[(size_t)gm * e.ldr + gn];
+            if (R) {
+                const float r = R[(size_t)gm * e.ldr + gn];
+                v = e.relu == 3 ? (r > 0.f ? v : 0.f) : v + r;
+            }
             if (e.relu == 2) v = fmaxf(v, 0.f);
             C[(size_t)gm * e.ldc + gn] = v;
         }

@@ -244,8 +244,9 @@ class TrainEngine:
     def _fwd(self, x, lin, relu=0, residual=None, out_dtype=None):
         return self.K.gemm(x, lin.w16, lin.bias, residual=residual, relu=relu, out_dtype=out_dtype)
 
-    def _bwd(self, lin, dy, x, need_dx=True, residual=None, out_dtype=None):
-        """weight / bias gradients of `lin` into the arena; returns dX = dY . W (+ residual) when need_dx"""
+    def _bwd(self, lin, dy, x, need_dx=True, residual=None, out_dtype=None, relu_mask=None):
+        """weight / bias gradients of `lin` into the arena; returns dX = dY . W (+ residual) when need_dx.  relu_mask = the saved
+        output h of a ReLU that produced x: the dgrad epilogue masks its result (h > 0 ? dX : 0) -- no separate ReLU-backward pass"""
         K = self.K
         c0 = 0
         for w, r0, n, b in lin.parts:
@@ -256,6 +257,9 @@ class TrainEngine:
             c0 += n
         if not need_dx:
             return None
+        if relu_mask is not None:
+            assert residual is None
+            return K.gemm(dy, lin.wT16[:, :lin.N], None, residual=relu_mask, relu=3, out_dtype=relu_mask.dtype)
         return K.gemm(dy, lin.wT16[:, :lin.N], None, residual=residual, out_dtype=out_dtype)
 
     def _ln_bwd(self, norm, z, dy, dy2=None, want32=True, want16=True):
@@ -339,8 +343,7 @@ class TrainEngine:
         a = lw["attn"]
         B, S = geo["B"], geo["S"]
         dz2_32, dz2 = self._ln_bwd(lw["ln2"], sv["z2"], d_y, d_qn)
-        dh = self._bwd(lw["l2"], dz2, sv["h"], out_dtype=T)
-        K.relu_bwd_(dh, sv["h"])
+        dh = self._bwd(lw["l2"], dz2, sv["h"], relu_mask=sv["h"])
         ds1 = self._bwd(lw["l1"], dh, sv["s1"], residual=dz2_32, out_dtype=F32)
         del dh
         dz1_32, dz1 = self._ln_bwd(lw["ln1"], sv["z1"], ds1)
@@ -393,8 +396,7 @@ class TrainEngine:
         B, S = geo["B"], geo["S"]
         a = lw["ca"]
         dz3_32, dz3 = self._ln_bwd(lw["ln3"], sv["z3"], d_t3)
-        dh = self._bwd(lw["l2"], dz3, sv["h"], out_dtype=T)
-        K.relu_bwd_(dh, sv["h"])
+        dh = self._bwd(lw["l2"], dz3, sv["h"], relu_mask=sv["h"])
         d_t1 = self._bwd(lw["l1"], dh, sv["t1"], residual=dz3_32, out_dtype=F32)
         del dh
         dz1_32, dz1 = self._ln_bwd(lw["ln1"], sv["z1"], d_t1)
@@ -416,8 +418,7 @@ class TrainEngine:
         d_tgt = K.add_cast(d_tgt, dqk_in, None, F32)
         if self.rph[0].train or self.rph[1].train:
             dqp = K.add_cast(dqca, dqk_in, None, T)                   # query_pos = ref_point_head(sine(ref)); ref is detached
-            dr1 = self._bwd(self.rph[1], dqp, sv["r1"], out_dtype=T)
-            K.relu_bwd_(dr1, sv["r1"])
+            dr1 = self._bwd(self.rph[1], dqp, sv["r1"], relu_mask=sv["r1"])
             self._bwd(self.rph[0], dr1, sv["sine"], need_dx=False)
         return d_tgt, dmem
 

@@ -296,20 +296,19 @@ class NativeFront:
         ops._call("dtlr_relu_bwd_dual", ops._p(dy32), ops._p(sv["y"]), ops._p(dsum), _ll(dy32.numel()), _code(dsum), ops._st(dsum))
         # conv3 (1x1)
         self._wgrad(c3, dsum, sv["bm"])
-        db = K.gemm(dsum, c3.bwdT[:, :c3.Cout], None, out_dtype=T)
-        K.relu_bwd_(db, sv["bm"])
+        db = K.gemm(dsum, c3.bwdT[:, :c3.Cout], None, residual=sv["bm"], relu=3, out_dtype=T)      # ReLU mask of bm in the epilogue
         # conv2 (3x3, stride s)
         col = sv["col"] if sv["col"] is not None else ops.im2col(sv["a"], B, Hi, Wi, p, 3, 3, s, 1, T)[0]
         self._wgrad(c2, db, col)
         del col
         if c2.bwdF is not None and ops.conv2d_nhwc_supported(db, Ho, Wo, p, 3, 1):
-            da = ops.conv2d_nhwc(db, c2.bwdF, None, B, Ho, Wo, p, 3, 1, relu=0)[0]
+            da = ops.conv2d_nhwc(db, c2.bwdF, None, B, Ho, Wo, p, 3, 1, relu=3, residual=sv["a"])[0]      # masked by a > 0
         else:
             dcol = K.gemm(db, c2.bwdT[:, :c2.Cout], None, out_dtype=F32)
             da32 = torch.empty((B * Hi * Wi, p), dtype=F32, device=dy32.device)
             _col2im(dcol, da32, B, Hi, Wi, p, 3, s, 1, Ho, Wo, 0)
             da = K.cast(da32, T)
-        K.relu_bwd_(da, sv["a"])
+            K.relu_bwd_(da, sv["a"])
         # conv1 (1x1) and the identity path
         self._wgrad(c1, da, sv["x"])
         if ds is None:

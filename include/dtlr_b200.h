@@ -116,7 +116,8 @@ int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, const float
                    void* workspace, long long workspace_bytes, void* stream);
 /* tuning aid only: sets kernel debug flags (0 = normal operation), returns the previous value */
 int dtlr_debug_flags(int flags);
-/* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output) */
+/* relu: 0 none, 1 ReLU before the residual add (FFN linear1), 2 ReLU after it (ResNet bottleneck output), 3 ReLU BACKWARD: the
+ * `residual` operand is the saved forward activation h and the result is masked, C = h > 0 ? A.W^T : 0 (dgrad of a Linear + ReLU pair) */
 
 /* ---------------------------------------------------------------------------------------------------------
  * Convolution front end (NHWC activations).  A k x k / strided convolution of the ResNet-50 trunk (torchvision

@@ -30,7 +30,7 @@ def gemm(a, w, bias=None, residual=None, relu=0, out_dtype=None, out=None):
     if relu == 1:
         c = F.relu(c)
     if residual is not None:
-        c = c + residual.float()
+        c = torch.where(residual.float() > 0, c, torch.zeros_like(c)) if relu == 3 else c + residual.float()
     if relu == 2:
         c = F.relu(c)
     c = c.to(out_dtype or a.dtype)
