@@ -56,6 +56,8 @@ struct FfnArgs {
     // W2 . relu(W1 X + b1) to partial[slice][tile - tile_base][128][256]
     int tile_base, nsplit;
     float* partial;
+    // stream-K kernel (ffn_ln_sk_kernel): one ready flag per CTA for the partial it leaves to its left neighbour
+    int* flags;
 };
 
 struct FfnSmem {
@@ -463,6 +465,371 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Stream-K variant of the block above (the default for more than one round of tiles).  Wave quantisation: num_m
+// 128-row tiles on G = 148 CTAs take ceil(num_m / G) rounds -- 456 tiles at B = 64 are 3.08 waves, i.e. a fourth round for 12 tiles.
+// Here the work is cut in UNITS = (row tile, hidden chunk of 128) instead: CTA c owns the contiguous unit range
+// [c U / G, (c + 1) U / G) of the U = num_m * NJ units, so every CTA does the same amount of tensor-core work (49 or 50 units at
+// B = 64) and a row tile whose chunks straddle a range boundary is shared by exactly two neighbours:
+//   * CTA c + 1 starts its range in the middle of tile T: it runs the LAST chunks of T first ("tail part"), stores the raw fp32
+//     partial of W2 . relu(W1 X + b1) over those chunks to workspace slot c + 1 and raises flag c + 1 (release);
+//   * CTA c ends its range with the FIRST chunks of T ("head part", the last thing it does -- by then the neighbour's partial has
+//     been in L2 for ~100 us): acquire flag, add the partial to its accumulator, + b2 + X -> LayerNorm -> store; flag reset to 0.
+// No CTA waits on a CTA that waits (the tail part is the first thing a CTA does and depends on nothing), all G <= SM count CTAs are
+// co-resident (1 CTA / SM by shared memory), so the spin cannot deadlock; the summation order is fixed (deterministic).
+// The unit stream is software-pipelined ACROSS tile boundaries: G1 of unit v + 1 is issued before G2 of unit v whatever tiles they
+// belong to, so the tensor pipe no longer idles between the last G2 of a tile and the first G1 of the next one.
+__global__ void __launch_bounds__(320, 1)
+ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int NS = FF_NS;
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* xs = smem;                                // [2][4 k-blocks][128 rows x 128 B]
+    unsigned char* ring = xs + 2 * FfnSmem::XS;
+    float* b1_s = reinterpret_cast<float*>(ring + FfnSmem::RING);
+    float* b2_s = b1_s + FF_MAX_HID;
+    float* gamma_s = b2_s + FF_D;
+    float* beta_s = gamma_s + FF_D;
+    float* stat_s = beta_s + FF_D;                           // [128 rows][2 halves][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + FF_BM * 4);
+    uint64_t* x_full = bars;             // [2]
+    uint64_t* x_free = bars + 2;         // [2]  8 arrivals (epilogue warps)
+    uint64_t* w_full = bars + 4;         // [NS]
+    uint64_t* w_empty = w_full + NS;     // [NS]
+    uint64_t* hacc_full = w_empty + NS;  // [2]
+    uint64_t* h_full = hacc_full + 2;    // [2] 8 arrivals
+    uint64_t* y_full = h_full + 2;       // [1]
+    uint64_t* y_free = y_full + 1;       // [1] 8 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(y_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (a.M + FF_BM - 1) / FF_BM;
+    const int NJ = a.HID / FF_HC;
+    const long long U = (long long)num_m * NJ;
+    const int cta = (int)blockIdx.x, G = (int)gridDim.x;
+    const int u0 = (int)(U * cta / G), u1 = (int)(U * (cta + 1) / G);
+    const int nu = u1 - u0;                                  // >= NJ (host: num_m >= G)
+    const int mt0 = u0 / NJ, j0 = u0 - mt0 * NJ;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW1);
+        tma_prefetch_desc(&tmW2);
+        tma_prefetch_desc(&tmO);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&x_full[b], 1);
+            mbar_init(&x_free[b], 8);
+            mbar_init(&hacc_full[b], 1);
+            mbar_init(&h_full[b], 8);
+        }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&w_empty[s], 1);
+        }
+        mbar_init(y_full, 1);
+        mbar_init(y_free, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + i);
+    for (int i = threadIdx.x; i < FF_D; i += 320) {
+        b2_s[i] = __ldg(a.b2 + i);
+        gamma_s[i] = __ldg(a.gamma + i);
+        beta_s[i] = __ldg(a.beta + i);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t tm_y = tmem_base;                 // columns [0, 256)
+    const uint32_t tm_h = tmem_base + 256;           // 2 x 128 columns
+
+    if (warp == 0) {
+        // ===== TMA producer: W1 chunk of unit v, then W2 chunk of unit v - 1 -- exactly the order the MMA warp consumes them
+        if (elect_one()) {
+            uint32_t it = 0;
+            int t = 0;                                           // item (= row tile visited) index of unit v
+            auto load_x = [&](int mt, uint32_t tt) {
+                const uint32_t xb = tt & 1;
+                mbar_wait(&x_free[xb], ((tt >> 1) & 1) ^ 1);
+                mbar_expect_tx(&x_full[xb], FfnSmem::XS);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
+            };
+            load_x(mt0, 0);
+            int mt = mt0, j = j0, pj = 0, item_v0 = 0, item_n = (NJ - j0 < nu) ? NJ - j0 : nu;
+            for (int v = 0; v <= nu; ++v) {
+                if (v < nu) {
+                    if (v > 0 && j == 0) {
+                        ++t;
+                        item_v0 = v;
+                        item_n = (NJ < nu - v) ? NJ : nu - v;
+                    }
+                    for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
+                        const int s = it % NS;
+                        mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
+                        mbar_expect_tx(&w_full[s], FF_STAGE);
+                        tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
+                    }
+                }
+                if (v >= 1) {
+                    for (int q = 0; q < 4; ++q, ++it) {                 // W2 output rows (q&1)*128.., hidden columns of chunk pj
+                        const int s = it % NS;
+                        mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
+                        mbar_expect_tx(&w_full[s], FF_STAGE);
+                        tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], pj * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                    }
+                }
+                if (v < nu) {
+                    // the X tile of the NEXT item, half way through this one (its buffer was released by the item before; everything
+                    // that item's last G2 needs has been requested above, so this wait cannot starve it)
+                    // (the first item: at once -- both buffers start free)
+                    const int at = (t == 0) ? 0 : ((item_n - 1 < NJ / 2) ? item_n - 1 : NJ / 2);
+                    if (v - item_v0 == at && item_v0 + item_n < nu) load_x(mt + 1, (uint32_t)(t + 1));
+                    pj = j;
+                    if (++j == NJ) { j = 0; ++mt; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: G1(v) one unit ahead of G2(v - 1), across tile boundaries
+        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
+        uint32_t it = 0;
+        int t = -1, j = j0;
+        uint32_t xb = 0;
+        bool first_w = false, last_w = false;
+        int tw = 0;
+        for (int v = 0; v <= nu; ++v) {
+            bool first_v = false, last_v = false;
+            if (v < nu) {
+                first_v = (v == 0) || (j == 0);
+                last_v = (v == nu - 1) || (j == NJ - 1);
+                if (first_v) {
+                    ++t;
+                    xb = (uint32_t)t & 1;
+                    mbar_wait(&x_full[xb], ((uint32_t)t >> 1) & 1);
+                    tcgen05_fence_after();
+                }
+                const uint32_t b = (uint32_t)v & 1;
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % NS;
+                    mbar_wait(&w_full[s], (it / NS) & 1);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + xb * FfnSmem::XS + kb * FF_STAGE));
+                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        umma_commit(&w_empty[s]);
+                        if (kb == 3) umma_commit(&hacc_full[b]);
+                    }
+                    __syncwarp();
+                }
+                if (++j == NJ) j = 0;
+            }
+            if (v >= 1) {
+                const uint32_t w = (uint32_t)(v - 1), b = w & 1;
+                mbar_wait(&h_full[b], (w >> 1) & 1);                     // bf16 hidden chunk of unit w is in TMEM
+                if (first_w) mbar_wait(y_free, ((uint32_t)tw & 1) ^ 1);  // previous item's output accumulator read out
+                tcgen05_fence_after();
+                for (int q = 0; q < 4; ++q, ++it) {
+                    const int s = it % NS;
+                    const int kb2 = q >> 1, half = q & 1;
+                    mbar_wait(&w_full[s], (it / NS) & 1);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
+                                         (!first_w) || kb2 > 0 || k > 0);
+                        umma_commit(&w_empty[s]);
+                        if (q == 3 && last_w) umma_commit(y_full);
+                    }
+                    __syncwarp();
+                }
+            }
+            first_w = first_v; last_w = last_v; tw = t;
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter qd (32 rows), column half hsel
+        const int qd = warp & 3;
+        const int hsel = (warp - 2) >> 2;
+        const int row = qd * 32 + lane;
+        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        // workspace slot s: [64 column groups of 4][128 rows] float4 -- a warp's 32 rows are consecutive 16-byte words
+        int mt = mt0, js = j0;
+        uint32_t t = 0;
+        for (int v = 0; v < nu; ++t, ++mt, js = 0) {
+            const int n = (NJ - js < nu - v) ? NJ - js : nu - v;
+            const bool tail = js > 0, head = (js == 0) && (n < NJ);
+            // ---- E1: +b1, ReLU, 16-bit, back into TMEM in place
+            for (int i = 0; i < n; ++i, ++v) {
+                const uint32_t b = (uint32_t)v & 1, u = (uint32_t)v >> 1;
+                mbar_wait(&hacc_full[b], u & 1);
+                tcgen05_fence_after();
+                uint32_t acc[64];
+                tmem_ld64(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 64), acc);
+                const float* bp = b1_s + (js + i) * FF_HC + hsel * 64;
+                uint32_t pk[32];
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bp + c);
+                    const float v0 = fmaxf(__uint_as_float(acc[c]) + b4.x, 0.f), v1 = fmaxf(__uint_as_float(acc[c + 1]) + b4.y, 0.f);
+                    const float v2 = fmaxf(__uint_as_float(acc[c + 2]) + b4.z, 0.f), v3 = fmaxf(__uint_as_float(acc[c + 3]) + b4.w, 0.f);
+                    pk[c / 2] = ff_pack_bf16x2(v0, v1);
+                    pk[c / 2 + 1] = ff_pack_bf16x2(v2, v3);
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+                tmem_st32(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 32), pk);
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_full[b]);
+            }
+            const uint32_t xb = t & 1;
+            unsigned char* xt = xs + xb * FfnSmem::XS;
+            if (tail) {
+                // ---- final (tail part): raw fp32 partial -> workspace slot `cta`, then the ready flag for the left neighbour
+                mbar_wait(y_full, t & 1);
+                tcgen05_fence_after();
+                if (lane == 0) mbar_arrive(&x_free[xb]);
+                float4* dst = reinterpret_cast<float4*>(a.partial) + (size_t)cta * (FF_BM * FF_D / 4) + row;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t acc[32];
+                        tmem_ld32(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64 + hf * 32), acc);
+                        if (cb == 1 && hf == 1) {
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(y_free);
+                        }
+                        const int cg0 = (hsel * 128 + cb * 64 + hf * 32) / 4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            __stcg(dst + (size_t)(cg0 + i) * FF_BM,
+                                   make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])));
+                    }
+                }
+                __threadfence();
+                asm volatile("bar.sync 5, 256;" ::: "memory");
+                if (threadIdx.x == 64) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + cta), "r"(1u) : "memory");
+                continue;
+            }
+            mbar_wait(&x_full[xb], (t >> 1) & 1);
+            mbar_wait(y_full, t & 1);
+            tcgen05_fence_after();
+            const float4* psrc = reinterpret_cast<const float4*>(a.partial) + (size_t)(cta + 1) * (FF_BM * FF_D / 4) + row;
+            if (head) {
+                // ---- head part: the right neighbour's partial over the remaining chunks of this tile (written long ago)
+                if (lane == 0) {
+                    uint32_t f;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.flags + cta + 1) : "memory");
+                    } while (f == 0u);
+                }
+                __syncwarp();
+            }
+            float sum = 0.f, sq = 0.f;
+            uint32_t xp[64];                                 // the row's 128 pre-norm values of this warp, packed 16-bit pairs
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t acc[32];
+                    tmem_ld32(tm_y + lane_addr + (uint32_t)(hsel * 128 + cb * 64 + hf * 32), acc);
+                    if (cb == 1 && hf == 1) {                // the output accumulator is in registers: the next item's G2 may start
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(y_free);
+                    }
+                    if (head) {
+                        const int cg0 = (hsel * 128 + cb * 64 + hf * 32) / 4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 p = __ldcg(psrc + (size_t)(cg0 + i) * FF_BM);
+                            acc[4 * i] = __float_as_uint(__uint_as_float(acc[4 * i]) + p.x);
+                            acc[4 * i + 1] = __float_as_uint(__uint_as_float(acc[4 * i + 1]) + p.y);
+                            acc[4 * i + 2] = __float_as_uint(__uint_as_float(acc[4 * i + 2]) + p.z);
+                            acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + p.w);
+                        }
+                    }
+                    const unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                    const float* bp = b2_s + hsel * 128 + cb * 64 + hf * 32;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = hf * 4 + kk;
+                        const uint4 r4 = *reinterpret_cast<const uint4*>(xrow + ((k ^ swz) * 16));
+                        const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bp[kk * 8 + 2 * i] + op16_lo_f32(rw[i]);
+                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bp[kk * 8 + 2 * i + 1] + op16_hi_f32(rw[i]);
+                            const uint32_t pk = ff_pack_bf16x2(x0, x1);
+                            xp[cb * 32 + k * 4 + i] = pk;
+                            const float y0 = op16_lo_f32(pk), y1 = op16_hi_f32(pk);
+                            sum += y0 + y1;
+                            sq = fmaf(y0, y0, sq);
+                            sq = fmaf(y1, y1, sq);
+                        }
+                    }
+                }
+            }
+            if (head) {
+                // every warp has consumed the partial: hand the flag back (0) for the next launch on this workspace
+                asm volatile("bar.sync 5, 256;" ::: "memory");
+                if (threadIdx.x == 64) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.flags + cta + 1), "r"(0u) : "memory");
+            }
+            stat_s[(row * 2 + hsel) * 2] = sum;
+            stat_s[(row * 2 + hsel) * 2 + 1] = sq;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // the two warps of this lane quarter
+            const float mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
+            const float var = fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + a.eps);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // statistics consumed before the next item overwrites them
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+                unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                const int c0 = hsel * 128 + cb * 64;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t pk = xp[cb * 32 + k * 4 + i];
+                        const int c = c0 + k * 8 + 2 * i;
+                        o[i] = ff_pack_bf16x2((op16_lo_f32(pk) - mean) * rstd * gamma_s[c] + beta_s[c],
+                                              (op16_hi_f32(pk) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                for (int cb = 0; cb < 2; ++cb)
+                    tma_store_2d(&tmO, xt + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, mt * FF_BM + qd * 32);
+                tma_store_commit();
+                tma_store_wait_read<0>();                                    // this X buffer may now be refilled
+                mbar_arrive(&x_free[xb]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // The rows of the wave-quantisation tail: sum of the hidden-slice partials (fixed order: deterministic) + b2 + X -> rounded to the
 // 16-bit type like the main kernel's packed pre-norm row -> LayerNorm -> Y.  One warp per row, 8 columns per lane.
 __global__ void __launch_bounds__(256)
@@ -535,11 +902,34 @@ static void ffn_split_plan(int M, int hidden, int* main_rows, int* rem_tiles, in
     *main_rows = full * sm * FF_BM; *rem_tiles = rem; *nsplit = ns;
 }
 
-extern "C" long long dtlr_ffn_workspace_bytes(int M, int hidden) {
-    int main_rows, rem, ns;
+// Which plan dtlr_ffn_ln_ws runs for a shape: 0 = the plain persistent kernel (one round, or an exact number of rounds), 1 = full
+// rounds + PART tail + ffn_tail_ln_kernel (round-2 first version, kept behind dtlr_debug_flags(536870912) for A/B), 2 = stream-K
+// (ffn_ln_sk_kernel, one launch).
+constexpr long long FF_SK_FLAG_BYTES = 1024;
+static int ffn_plan(int M, int hidden) {
     if (M <= 0 || hidden <= 0 || (hidden % FF_HC) != 0 || hidden > FF_MAX_HID) return 0;
-    ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
-    return rem ? (long long)ns * rem * FF_BM * FF_D * 4 : 0;
+    if (g_debug_flags & (262144 | 4096)) return 0;                  // flag 262144: never split (A/B); 4096: the CTA-pair variant
+    const int num_m = (M + FF_BM - 1) / FF_BM, sm = sm_count();
+    if (g_debug_flags & 536870912) {
+        int main_rows, rem, ns;
+        ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
+        return rem ? 1 : 0;
+    }
+    if (num_m <= sm || (num_m % sm) == 0 || sm * 4 > FF_SK_FLAG_BYTES) return 0;
+    return 2;
+}
+
+extern "C" int dtlr_ffn_plan(int M, int hidden) { return ffn_plan(M, hidden); }
+
+extern "C" long long dtlr_ffn_workspace_bytes(int M, int hidden) {
+    const int plan = ffn_plan(M, hidden);
+    if (plan == 2) return FF_SK_FLAG_BYTES + (long long)sm_count() * FF_BM * FF_D * 4;
+    if (plan == 1) {
+        int main_rows, rem, ns;
+        ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
+        return (long long)ns * rem * FF_BM * FF_D * 4;
+    }
+    return 0;
 }
 
 extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
@@ -549,11 +939,34 @@ extern "C" int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, con
 extern "C" int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
                               const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
                               void* workspace, long long workspace_bytes, void* stream) {
-    int main_rows = M, rem = 0, ns = 1;
-    if (M > 0 && hidden > 0 && (hidden % FF_HC) == 0 && hidden <= FF_MAX_HID) ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
-    if (!rem || !workspace || workspace_bytes < (long long)ns * rem * FF_BM * FF_D * 4)
+    const int plan = ffn_plan(M, hidden);
+    if (!plan || !workspace || workspace_bytes < dtlr_ffn_workspace_bytes(M, hidden))
         return dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, M, hidden, stream);
-    int rc = dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, main_rows, hidden, stream);
+    int rc;
+    if (plan == 2) {
+        DTLR_CHECK_ARG(X && W1 && b1 && W2 && b2 && gamma && beta && Y, "ffn_ln: null pointer");
+        DTLR_CHECK_ARG(ldx >= FF_D && ldw1 >= FF_D && ldw2 >= hidden && ldy >= FF_D, "ffn_ln: leading dimension too small");
+        DTLR_CHECK_ARG((ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 && (ldy % 8) == 0 &&
+                       ((((uintptr_t)X | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)Y | (uintptr_t)workspace)) & 15) == 0,
+                       "ffn_ln: operands need 16-byte aligned rows");
+        CUtensorMap tx, tw1, tw2, to;
+        if ((rc = ffn_tmap(&tx, X, M, FF_D, ldx, FF_BM))) return rc;
+        if ((rc = ffn_tmap(&tw1, W1, hidden, FF_D, ldw1, 128))) return rc;
+        if ((rc = ffn_tmap(&tw2, W2, FF_D, hidden, ldw2, 128))) return rc;
+        if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
+        static bool configured_sk = false;
+        if (!configured_sk) {
+            DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+            configured_sk = true;
+        }
+        FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags, nullptr, nullptr, nullptr, nullptr, 0, 1,
+                  reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + FF_SK_FLAG_BYTES), reinterpret_cast<int*>(workspace)};
+        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_sk_kernel, dim3(sm_count()), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+        return DTLR_OK;
+    }
+    int main_rows = M, rem = 0, ns = 1;
+    ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
+    rc = dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, main_rows, hidden, stream);
     if (rc) return rc;
     const op16_t* xt = reinterpret_cast<const op16_t*>(X) + (size_t)main_rows * ldx;
     op16_t* yt = reinterpret_cast<op16_t*>(Y) + (size_t)main_rows * ldy;

@@ -395,6 +395,18 @@ FFN_CHUNK_ROWS = int(_os.environ.get("DTLR_FFN_CHUNK_ROWS", "0"))
 FFN_SPLIT_TAIL = _os.environ.get("DTLR_FFN_SPLIT_TAIL", "1") != "0"
 
 
+_FFN_WS = {}
+
+
+def _ffn_workspace(device, nbytes):
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _FFN_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _FFN_WS[key] = ws
+    return ws
+
+
 def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     """y = LN(x + W2 relu(W1 x + b1) + b2) [, y2 = y + add2]: one tcgen05 kernel in bf16 mode when d_model = 256 and the hidden
     width is a multiple of 128 (<= 2048) -- the hidden activation never reaches HBM (opt-in, see FFN_FUSED); otherwise linear1 +
@@ -408,15 +420,17 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
         L.set_flavor(x.dtype)
         if L.TIMER is not None:     # bench.py: algorithmic FLOPs of the block = the two contractions, 2*M*hid*256 each
             L.TIMER("ffn", 4.0 * M * hid * 256, x.device, True)
-        # wave-quantisation tail: when the last round of 128-row tiles is mostly empty the library splits the tail
-        # tiles' hidden dimension over the idle SMs; it needs an fp32 workspace for the partial sums (0 bytes: no split)
+        # wave quantisation: with more than one round of 128-row tiles the library runs the stream-K kernel (equal
+        # (tile, hidden chunk) unit ranges per SM; neighbours exchange one fp32 partial tile through the workspace).  The workspace
+        # starts with the ready flags, which must be ZERO on first use and are handed back zero by every call -> one zero-initialised
+        # buffer per (device, stream), reused by every FFN block of the step (they run one after the other on that stream)
         lib = L.lib()
         lib.dtlr_ffn_workspace_bytes.restype = ctypes.c_longlong
         nws = int(lib.dtlr_ffn_workspace_bytes(M, hid)) if FFN_SPLIT_TAIL else 0
-        ws = torch.empty((nws,), dtype=torch.uint8, device=x.device) if nws > 0 else None
+        ws = _ffn_workspace(x.device, nws) if nws > 0 else None
         _call("dtlr_ffn_ln_ws", _p(x), x.stride(0), _p(w1), w1.stride(0), _p(b1), _p(w2), w2.stride(0), _p(b2), _p(gamma), _p(beta),
               ctypes.c_float(eps), _p(y), y.stride(0), M, hid, _p(ws), ctypes.c_longlong(nws), _st(x))
-        if nws > 0:
+        if nws > 0 and int(lib.dtlr_ffn_plan(M, hid)) == 1:      # the PART-tail plan (A/B flag): two more launches
             L.LAUNCHES += 2
         if L.TIMER is not None:
             L.TIMER("ffn", 0.0, x.device, False)

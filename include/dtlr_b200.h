@@ -106,11 +106,15 @@ int dtlr_gemm_ln(const void* A, int lda, const void* W, int ldw, const float* bi
  * X [M,ldx], W1 [hidden,ldw1] (256 used), W2 [256,ldw2] (hidden used), Y [M,ldy]; b1 [hidden], b2/gamma/beta [256] fp32. */
 int dtlr_ffn_ln(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2, const float* b2,
                 const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden, void* stream);
-/* The same block with the wave-quantisation tail split over idle SMs: the full rounds of 128-row tiles run on the
- * kernel above, the remaining tiles with their hidden dimension cut into slices (partial sums in `workspace`, fp32) followed by a
- * sum + residual + LayerNorm kernel.  dtlr_ffn_workspace_bytes(M, hidden) = the workspace the plan for this shape needs (0: no
- * split pays; then, or with a NULL / too small workspace, the call is dtlr_ffn_ln).  Deterministic: fixed summation order. */
+/* The same block without the wave-quantisation loss: with more than one round of 128-row tiles per SM the call runs
+ * the stream-K kernel -- every CTA owns an equal range of (row tile, 128-wide hidden chunk) units; a tile that straddles a range
+ * boundary is summed from two neighbouring CTAs' fp32 partials, exchanged through `workspace` behind a ready flag.
+ * dtlr_ffn_workspace_bytes(M, hidden) = the workspace the plan for this shape needs (0: none; then, or with a NULL / too small
+ * workspace, the call is dtlr_ffn_ln).  The first 1024 bytes of the workspace are the flags: they must be ZERO before the first
+ * call and are handed back zero by every completed call; calls that share a workspace must be ordered on one stream.
+ * Deterministic (fixed summation order).  dtlr_ffn_plan: 0 plain, 1 full rounds + split tail (A/B), 2 stream-K. */
 long long dtlr_ffn_workspace_bytes(int M, int hidden);
+int dtlr_ffn_plan(int M, int hidden);
 int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
                    const float* b2, const float* gamma, const float* beta, float eps, void* Y, int ldy, int M, int hidden,
                    void* workspace, long long workspace_bytes, void* stream);

@@ -132,7 +132,8 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
             assert (o.float() - old.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()
 
 
-@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048), (37000, 2048)])
+@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048), (37000, 2048), (50688, 2048), (40000, 1024),
+                                   (148 * 256, 2048), (19000, 256)])
 @pytest.mark.parametrize("pairs", [True, False])
 def test_fused_ffn_block(M, hid, pairs):
     """dtlr_ffn_ln: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM / shared memory) vs
@@ -164,25 +165,51 @@ def test_fused_ffn_block(M, hid, pairs):
     assert (y.float() - ref).abs().mean().item() < 4e-3
     un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
-    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining);
-    # the same two cases take the wave-quantisation split (3 full rounds on the main kernel + the tail tiles' hidden dimension cut
-    # into 8 / 16 slices on idle SMs + the sum / LayerNorm kernel) on a 148-SM part; without it the result must agree as well
+    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining).
+    # With more than one round of tiles (and no exact number of rounds) the default plan is the STREAM-K kernel: equal (tile,
+    # hidden chunk) unit ranges per CTA, a tile that straddles a range boundary is summed from two neighbours' partials.  Rows of
+    # tiles that are not shared must be bit-equal to the plain persistent kernel (same chunk order), shared tiles agree to fp32
+    # re-association; repeated calls on the same workspace are bit-equal (ready flags handed back, fixed summation order); the
+    # round-2 PART-tail plan (flag 536870912) must agree as well.
     import ctypes
     lib = _lib.lib()
     lib.dtlr_ffn_workspace_bytes.restype = ctypes.c_longlong
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     tiles = (M + 127) // 128
-    if tiles // sms >= 1 and 0 < tiles % sms <= sms // 2 and hid >= 256:
-        assert lib.dtlr_ffn_workspace_bytes(M, hid) > 0
+    if pairs:
+        return
+    if tiles > sms and tiles % sms != 0:
+        assert lib.dtlr_ffn_plan(M, hid) == 2 and lib.dtlr_ffn_workspace_bytes(M, hid) > 0
         saved_split, ops.FFN_SPLIT_TAIL = ops.FFN_SPLIT_TAIL, False
         try:
             y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
         finally:
             ops.FFN_SPLIT_TAIL = saved_split
-        main_rows = (tiles // sms) * sms * 128
-        assert torch.equal(y[:main_rows], y0[:main_rows])
-        assert (y[main_rows:].float() - y0[main_rows:].float()).abs().max().item() < 5e-2
-        assert (y[main_rows:].float() - y0[main_rows:].float()).abs().mean().item() < 2e-3
+        nj = hid // 128
+        units = tiles * nj
+        shared = sorted({(units * c // sms) // nj for c in range(1, sms) if (units * c // sms) % nj})
+        assert len(shared) > 0
+        keep = torch.ones(tiles * 128, dtype=torch.bool, device="cuda")
+        for t in shared:
+            keep[t * 128:(t + 1) * 128] = False
+        keep = keep[:M]
+        assert torch.equal(y[keep], y0[keep])
+        assert (y[~keep].float() - y0[~keep].float()).abs().max().item() < 5e-2
+        assert (y[~keep].float() - y0[~keep].float()).abs().mean().item() < 2e-3
+        for _ in range(3):
+            assert torch.equal(ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta), y)
+        if 0 < tiles % sms <= sms // 2 and hid >= 256:
+            lib.dtlr_debug_flags(536870912)
+            try:
+                assert lib.dtlr_ffn_plan(M, hid) == 1
+                y1 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+            finally:
+                lib.dtlr_debug_flags(0)
+            main_rows = (tiles // sms) * sms * 128
+            assert torch.equal(y1[:main_rows], y0[:main_rows])
+            assert (y1[main_rows:].float() - y0[main_rows:].float()).abs().max().item() < 5e-2
+    else:
+        assert lib.dtlr_ffn_plan(M, hid) == 0
 
 
 @pytest.mark.parametrize("M,N,K,out_dtype", [(57600 * 2, 166, 256, torch.float32), (58368, 166, 256, torch.float32),
