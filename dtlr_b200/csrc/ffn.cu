@@ -58,6 +58,8 @@ struct FfnArgs {
     float* partial;
     // stream-K kernel (ffn_ln_sk_kernel): one ready flag per CTA for the partial it leaves to its left neighbour
     int* flags;
+    // timeline probe (dtlr_ffn_debug_buffer): CTA 0 records clock() at fixed points of its three roles, [role][unit 64][slot 16]
+    unsigned int* dbgbuf;
 };
 
 struct FfnSmem {
@@ -479,11 +481,23 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // co-resident (1 CTA / SM by shared memory), so the spin cannot deadlock; the summation order is fixed (deterministic).
 // The unit stream is software-pipelined ACROSS tile boundaries: G1 of unit v + 1 is issued before G2 of unit v whatever tiles they
 // belong to, so the tensor pipe no longer idles between the last G2 of a tile and the first G1 of the next one.
+// barrier wait of the stream-K kernel: cluster-scope acquire when arrivals / transaction bytes come from the peer CTA (PAIR)
+template <bool PAIR>
+__device__ __forceinline__ void sk_wait(uint64_t* bar, uint32_t parity, bool spin = false) {
+    if (spin) mbar_spin_cluster(bar, parity);
+    else if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmO, const FfnArgs a) {
     extern __shared__ unsigned char smem_raw[];
+    // PAIR: a 16 KB stage is this CTA's HALF of the B operand of EIGHT K = 16 steps (G1: 64 of the chunk's 128 hidden rows x 128 k;
+    // G2: 128 of the 256 output rows x 64 hidden columns, N = 256 MMAs), so one barrier round trip / tcgen05.commit covers 512 clk of
+    // tensor work instead of 256 (measured: the per-stage handshake, not the tensor pipe, paced the single-CTA kernel)
     constexpr int NS = FF_NS;
+    constexpr int WST = FF_STAGE;
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* xs = smem;                                // [2][4 k-blocks][128 rows x 128 B]
     unsigned char* ring = xs + 2 * FfnSmem::XS;
@@ -506,11 +520,19 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (a.M + FF_BM - 1) / FF_BM;
     const int NJ = a.HID / FF_HC;
-    const long long U = (long long)num_m * NJ;
-    const int cta = (int)blockIdx.x, G = (int)gridDim.x;
-    const int u0 = (int)(U * cta / G), u1 = (int)(U * (cta + 1) / G);
-    const int nu = u1 - u0;                                  // >= NJ (host: num_m >= G)
-    const int mt0 = u0 / NJ, j0 = u0 - mt0 * NJ;
+    // PAIR: the work item is a PAIR tile (256 rows: row tile 2 pt + rank for the CTA of cluster rank `rank`), split over the pairs
+    constexpr int NC = PAIR ? 2 : 1;
+    const uint32_t rank = PAIR ? cluster_cta_rank() : 0;
+    const int num_pt = (num_m + NC - 1) / NC;
+    const long long U = (long long)num_pt * NJ;
+    const int cta = (int)blockIdx.x, G = (int)gridDim.x / NC, grp = cta / NC;
+    const int u0 = (int)(U * grp / G), u1 = (int)(U * (grp + 1) / G);
+    const int nu = u1 - u0;                                  // >= NJ (host: num_pt >= G)
+    const int mt0 = u0 / NJ, j0 = u0 - mt0 * NJ;             // mt counts pair tiles when PAIR
+    const bool leader = rank == 0;
+    const bool spin = (a.dbg & 32768) != 0;          // probe: busy-polling barrier waits
+    unsigned int* const dbgbuf = (cta == 0) ? a.dbgbuf : nullptr;
+#define FF_DBG(role, unit, slot) do { if (dbgbuf && (unit) < 64) dbgbuf[(((role) * 64 + (unit)) * 16 + (slot))] = (unsigned int)clock(); } while (0)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
@@ -521,17 +543,17 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_init(&x_full[b], 1);
             mbar_init(&x_free[b], 8);
             mbar_init(&hacc_full[b], 1);
-            mbar_init(&h_full[b], 8);
+            mbar_init(&h_full[b], 8 * NC);                   // PAIR: the peer's epilogue warps arrive on the leader's barrier
         }
         for (int s = 0; s < NS; ++s) {
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
         }
         mbar_init(y_full, 1);
-        mbar_init(y_free, 8);
+        mbar_init(y_free, 8 * NC);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<512>(tmem_ptr);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair<512>(tmem_ptr); else tmem_alloc<512>(tmem_ptr); }
     for (int i = threadIdx.x; i < a.HID; i += 320) b1_s[i] = __ldg(a.b1 + i);
     for (int i = threadIdx.x; i < FF_D; i += 320) {
         b2_s[i] = __ldg(a.b2 + i);
@@ -540,8 +562,12 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                    // both CTAs' barriers are initialised before anything arrives at them remotely
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // shared::cluster addresses of the LEADER's barriers (PAIR: TMA completions and epilogue arrivals of both CTAs go there)
+    const uint32_t ld_x_full = mapa_rank(smem_u32(x_full), 0), ld_w_full = mapa_rank(smem_u32(w_full), 0);
+    const uint32_t ld_h_full = mapa_rank(smem_u32(h_full), 0), ld_y_free = mapa_rank(smem_u32(y_free), 0);
     pdl_launch_dependents();
     pdl_wait();
     const uint32_t tm_y = tmem_base;                 // columns [0, 256)
@@ -554,32 +580,44 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             int t = 0;                                           // item (= row tile visited) index of unit v
             auto load_x = [&](int mt, uint32_t tt) {
                 const uint32_t xb = tt & 1;
-                mbar_wait(&x_free[xb], ((tt >> 1) & 1) ^ 1);
-                mbar_expect_tx(&x_full[xb], FfnSmem::XS);
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
+                sk_wait<PAIR>(&x_free[xb], ((tt >> 1) & 1) ^ 1, spin);
+                if (leader) mbar_expect_tx(&x_full[xb], NC * FfnSmem::XS);
+                for (int kb = 0; kb < 4; ++kb) {
+                    if (PAIR) tma_load_2d_pair(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, ld_x_full + xb * 8, kb * 64, (mt * NC + (int)rank) * FF_BM);
+                    else tma_load_2d(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, &x_full[xb], kb * 64, mt * FF_BM);
+                }
             };
             load_x(mt0, 0);
             int mt = mt0, j = j0, pj = 0, item_v0 = 0, item_n = (NJ - j0 < nu) ? NJ - j0 : nu;
             for (int v = 0; v <= nu; ++v) {
+                FF_DBG(0, v, 0);
                 if (v < nu) {
                     if (v > 0 && j == 0) {
                         ++t;
                         item_v0 = v;
                         item_n = (NJ < nu - v) ? NJ : nu - v;
                     }
-                    for (int kb = 0; kb < 4; ++kb, ++it) {              // W1 rows j*128.., k columns kb*64..
+                    for (int kb = 0; kb < (PAIR ? 2 : 4); ++kb, ++it) {  // W1 rows j*128.., k columns kb*64.. (PAIR: 64 rows x 2 k-blocks)
                         const int s = it % NS;
-                        mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
-                        mbar_expect_tx(&w_full[s], FF_STAGE);
-                        tma_load_2d(ring + s * FF_STAGE, &tmW1, &w_full[s], kb * 64, j * FF_HC);
+                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1, spin);
+                        FF_DBG(0, v, 1 + kb);
+                        if (a.dbg & 128) { if (leader) mbar_arrive(&w_full[s]); continue; }      // probe: no weight stream
+                        if (leader) mbar_expect_tx(&w_full[s], NC * WST);
+                        if (PAIR) {
+                            tma_load_2d_pair(ring + s * WST, &tmW1, ld_w_full + s * 8, (2 * kb) * 64, j * FF_HC + (int)rank * 64);
+                            tma_load_2d_pair(ring + s * WST + WST / 2, &tmW1, ld_w_full + s * 8, (2 * kb + 1) * 64, j * FF_HC + (int)rank * 64);
+                        } else tma_load_2d(ring + s * WST, &tmW1, &w_full[s], kb * 64, j * FF_HC);
                     }
                 }
                 if (v >= 1) {
-                    for (int q = 0; q < 4; ++q, ++it) {                 // W2 output rows (q&1)*128.., hidden columns of chunk pj
-                        const int s = it % NS;
-                        mbar_wait(&w_empty[s], ((it / NS) & 1) ^ 1);
-                        mbar_expect_tx(&w_full[s], FF_STAGE);
-                        tma_load_2d(ring + s * FF_STAGE, &tmW2, &w_full[s], pj * FF_HC + (q >> 1) * 64, (q & 1) * 128);
+                    for (int q = 0; q < (PAIR ? 2 : 4); ++q, ++it) {    // W2 output rows (q&1)*128.., hidden columns of chunk pj
+                        const int s = it % NS;                          // (PAIR: output rows rank*128.., hidden columns q*64..)
+                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1, spin);
+                        FF_DBG(0, v, 5 + q);
+                        if (a.dbg & 128) { if (leader) mbar_arrive(&w_full[s]); continue; }
+                        if (leader) mbar_expect_tx(&w_full[s], NC * WST);
+                        if (PAIR) tma_load_2d_pair(ring + s * WST, &tmW2, ld_w_full + s * 8, pj * FF_HC + q * 64, (int)rank * 128);
+                        else tma_load_2d(ring + s * WST, &tmW2, &w_full[s], pj * FF_HC + (q >> 1) * 64, (q & 1) * 128);
                     }
                 }
                 if (v < nu) {
@@ -587,15 +625,18 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     // that item's last G2 needs has been requested above, so this wait cannot starve it)
                     // (the first item: at once -- both buffers start free)
                     const int at = (t == 0) ? 0 : ((item_n - 1 < NJ / 2) ? item_n - 1 : NJ / 2);
+                    FF_DBG(0, v, 9);
                     if (v - item_v0 == at && item_v0 + item_n < nu) load_x(mt + 1, (uint32_t)(t + 1));
+                    FF_DBG(0, v, 10);
                     pj = j;
                     if (++j == NJ) { j = 0; ++mt; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: G1(v) one unit ahead of G2(v - 1), across tile boundaries
-        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(FF_BM >> 4) << 24);
+        // ===== MMA issuer: G1(v) one unit ahead of G2(v - 1), across tile boundaries (PAIR: the leader CTA issues for both, M = 256)
+        constexpr uint32_t IDESC = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)((NC * FF_BM) >> 4) << 24);
+        if (leader) {
         uint32_t it = 0;
         int t = -1, j = j0;
         uint32_t xb = 0;
@@ -603,26 +644,55 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         int tw = 0;
         for (int v = 0; v <= nu; ++v) {
             bool first_v = false, last_v = false;
+            FF_DBG(1, v, 0);
             if (v < nu) {
                 first_v = (v == 0) || (j == 0);
                 last_v = (v == nu - 1) || (j == NJ - 1);
                 if (first_v) {
                     ++t;
                     xb = (uint32_t)t & 1;
-                    mbar_wait(&x_full[xb], ((uint32_t)t >> 1) & 1);
+                    sk_wait<PAIR>(&x_full[xb], ((uint32_t)t >> 1) & 1, spin);
                     tcgen05_fence_after();
                 }
+                FF_DBG(1, v, 1);
                 const uint32_t b = (uint32_t)v & 1;
+                if (PAIR) {
+                    constexpr uint32_t IDESC2 = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                    for (int st = 0; st < 2; ++st, ++it) {
+                        const int s = it % NS;
+                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                        tcgen05_fence_after();
+                        FF_DBG(1, v, 2 + 2 * st);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb) {
+                                const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + xb * FfnSmem::XS + (2 * st + kb) * FF_STAGE));
+                                const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * WST + kb * (WST / 2)));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (a.dbg & 512) break;                                      // probe: no G1 MMAs
+                                    umma_bf16_pair(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC2, (st | kb | k) != 0);
+                                }
+                            }
+                            umma_commit_pair(&w_empty[s], 3);
+                            if (st == 1) umma_commit_pair(&hacc_full[b], 3);
+                        }
+                        __syncwarp();
+                        FF_DBG(1, v, 3 + 2 * st);
+                    }
+                } else
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % NS;
-                    mbar_wait(&w_full[s], (it / NS) & 1);
+                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + xb * FfnSmem::XS + kb * FF_STAGE));
-                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * WST));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < 4; ++k) {
+                            if (a.dbg & 512) break;                                              // probe: no G1 MMAs
                             umma_bf16(tm_h + b * FF_HC, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        }
                         umma_commit(&w_empty[s]);
                         if (kb == 3) umma_commit(&hacc_full[b]);
                     }
@@ -632,20 +702,46 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             if (v >= 1) {
                 const uint32_t w = (uint32_t)(v - 1), b = w & 1;
-                mbar_wait(&h_full[b], (w >> 1) & 1);                     // bf16 hidden chunk of unit w is in TMEM
-                if (first_w) mbar_wait(y_free, ((uint32_t)tw & 1) ^ 1);  // previous item's output accumulator read out
+                sk_wait<PAIR>(&h_full[b], (w >> 1) & 1, spin);             // 16-bit hidden chunk of unit w is in TMEM (of both CTAs)
+                FF_DBG(1, v, 6);
+                if (first_w) sk_wait<PAIR>(y_free, ((uint32_t)tw & 1) ^ 1, spin);  // previous item's output accumulator read out
                 tcgen05_fence_after();
+                FF_DBG(1, v, 7);
+                if (PAIR) {
+                    constexpr uint32_t IDESC3 = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+                    for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
+                        const int s = it % NS;
+                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                        tcgen05_fence_after();
+                        FF_DBG(1, v, 8 + 2 * kb2);
+                        if (elect_one()) {
+                            const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * WST));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (a.dbg & 1024) break;                                         // probe: no G2 MMAs
+                                umma_bf16_ts_pair(tm_y, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC3,
+                                                  (!first_w) || kb2 > 0 || k > 0);
+                            }
+                            umma_commit_pair(&w_empty[s], 3);
+                            if (kb2 == 1 && last_w) umma_commit_pair(y_full, 3);
+                        }
+                        __syncwarp();
+                        FF_DBG(1, v, 9 + 2 * kb2);
+                    }
+                } else
                 for (int q = 0; q < 4; ++q, ++it) {
                     const int s = it % NS;
                     const int kb2 = q >> 1, half = q & 1;
-                    mbar_wait(&w_full[s], (it / NS) & 1);
+                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
                     tcgen05_fence_after();
                     if (elect_one()) {
-                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * FF_STAGE));
+                        const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * WST));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < 4; ++k) {
+                            if (a.dbg & 1024) break;                                             // probe: no G2 MMAs
                             umma_bf16_ts(tm_y + half * 128, tm_h + b * FF_HC + kb2 * 32 + k * 8, db + (uint64_t)(2 * k), IDESC,
                                          (!first_w) || kb2 > 0 || k > 0);
+                        }
                         umma_commit(&w_empty[s]);
                         if (q == 3 && last_w) umma_commit(y_full);
                     }
@@ -653,6 +749,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 }
             }
             first_w = first_v; last_w = last_v; tw = t;
+        }
         }
     } else {
         // ===== epilogue warps: TMEM lane quarter qd (32 rows), column half hsel
@@ -666,14 +763,23 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t t = 0;
         for (int v = 0; v < nu; ++t, ++mt, js = 0) {
             const int n = (NJ - js < nu - v) ? NJ - js : nu - v;
-            const bool tail = js > 0, head = (js == 0) && (n < NJ);
+            const bool tail = (js > 0) && !(a.dbg & 16384), head = (js == 0) && (n < NJ) && !(a.dbg & 16384);   // probe 16384: no partial exchange
             // ---- E1: +b1, ReLU, 16-bit, back into TMEM in place
             for (int i = 0; i < n; ++i, ++v) {
                 const uint32_t b = (uint32_t)v & 1, u = (uint32_t)v >> 1;
-                mbar_wait(&hacc_full[b], u & 1);
+                if (threadIdx.x == 64) FF_DBG(2, v, 0);
+                sk_wait<PAIR>(&hacc_full[b], u & 1, spin);
                 tcgen05_fence_after();
+                if (threadIdx.x == 64) FF_DBG(2, v, 1);
+                if (a.dbg & 256) {                                                               // probe: no E1 work
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_h_full + b * 8); else mbar_arrive(&h_full[b]); }
+                    continue;
+                }
                 uint32_t acc[64];
                 tmem_ld64(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 64), acc);
+                if (threadIdx.x == 64) FF_DBG(2, v, 2);
                 const float* bp = b1_s + (js + i) * FF_HC + hsel * 64;
                 uint32_t pk[32];
 #pragma unroll
@@ -685,16 +791,19 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     pk[c / 2 + 1] = ff_pack_bf16x2(v2, v3);
                 }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+                if (threadIdx.x == 64) FF_DBG(2, v, 3);
                 tmem_st32(tm_h + b * FF_HC + lane_addr + (uint32_t)(hsel * 32), pk);
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&h_full[b]);
+                if (threadIdx.x == 64) FF_DBG(2, v, 4);
+                if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_h_full + b * 8); else mbar_arrive(&h_full[b]); }
+                if (threadIdx.x == 64) FF_DBG(2, v, 5);
             }
             const uint32_t xb = t & 1;
             unsigned char* xt = xs + xb * FfnSmem::XS;
             if (tail) {
                 // ---- final (tail part): raw fp32 partial -> workspace slot `cta`, then the ready flag for the left neighbour
-                mbar_wait(y_full, t & 1);
+                sk_wait<PAIR>(y_full, t & 1, spin);
                 tcgen05_fence_after();
                 if (lane == 0) mbar_arrive(&x_free[xb]);
                 float4* dst = reinterpret_cast<float4*>(a.partial) + (size_t)cta * (FF_BM * FF_D / 4) + row;
@@ -707,7 +816,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         if (cb == 1 && hf == 1) {
                             tcgen05_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(y_free);
+                            if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_y_free); else mbar_arrive(y_free); }
                         }
                         const int cg0 = (hsel * 128 + cb * 64 + hf * 32) / 4;
 #pragma unroll
@@ -721,19 +830,28 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (threadIdx.x == 64) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + cta), "r"(1u) : "memory");
                 continue;
             }
-            mbar_wait(&x_full[xb], (t >> 1) & 1);
-            mbar_wait(y_full, t & 1);
+            // (PAIR: this CTA's X tile completed on the leader's barrier; y_full -- every MMA of the pair done -- implies it landed)
+            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 0);
+            if (!PAIR) sk_wait<PAIR>(&x_full[xb], (t >> 1) & 1, spin);
+            sk_wait<PAIR>(y_full, t & 1, spin);
             tcgen05_fence_after();
-            const float4* psrc = reinterpret_cast<const float4*>(a.partial) + (size_t)(cta + 1) * (FF_BM * FF_D / 4) + row;
+            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 1);
+            const float4* psrc = reinterpret_cast<const float4*>(a.partial) + (size_t)(cta + NC) * (FF_BM * FF_D / 4) + row;
             if (head) {
                 // ---- head part: the right neighbour's partial over the remaining chunks of this tile (written long ago)
                 if (lane == 0) {
                     uint32_t f;
                     do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.flags + cta + 1) : "memory");
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(a.flags + cta + NC) : "memory");
                     } while (f == 0u);
                 }
                 __syncwarp();
+            }
+            if (a.dbg & 2048) {                              // probe: no final epilogue work
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_y_free); else mbar_arrive(y_free); mbar_arrive(&x_free[xb]); }
+                continue;
             }
             float sum = 0.f, sq = 0.f;
             uint32_t xp[64];                                 // the row's 128 pre-norm values of this warp, packed 16-bit pairs
@@ -746,7 +864,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     if (cb == 1 && hf == 1) {                // the output accumulator is in registers: the next item's G2 may start
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(y_free);
+                        if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_y_free); else mbar_arrive(y_free); }
                     }
                     if (head) {
                         const int cg0 = (hsel * 128 + cb * 64 + hf * 32) / 4;
@@ -783,8 +901,9 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (head) {
                 // every warp has consumed the partial: hand the flag back (0) for the next launch on this workspace
                 asm volatile("bar.sync 5, 256;" ::: "memory");
-                if (threadIdx.x == 64) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.flags + cta + 1), "r"(0u) : "memory");
+                if (threadIdx.x == 64) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.flags + cta + NC), "r"(0u) : "memory");
             }
+            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 2);
             stat_s[(row * 2 + hsel) * 2] = sum;
             stat_s[(row * 2 + hsel) * 2 + 1] = sq;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // the two warps of this lane quarter
@@ -811,22 +930,25 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             fence_proxy_async();
             __syncwarp();
+            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 3);
             if (lane == 0) {
                 for (int cb = 0; cb < 2; ++cb)
-                    tma_store_2d(&tmO, xt + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, mt * FF_BM + qd * 32);
+                    tma_store_2d(&tmO, xt + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, (mt * NC + (int)rank) * FF_BM + qd * 32);
                 tma_store_commit();
                 tma_store_wait_read<0>();                                    // this X buffer may now be refilled
                 mbar_arrive(&x_free[xb]);
             }
             __syncwarp();
+            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 4);
         }
         if (lane == 0) tma_store_wait<0>();
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                    // no CTA leaves (or frees tensor memory) while its peer may still use it
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -915,15 +1037,22 @@ static int ffn_plan(int M, int hidden) {
         ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
         return rem ? 1 : 0;
     }
-    if (num_m <= sm || (num_m % sm) == 0 || sm * 4 > FF_SK_FLAG_BYTES) return 0;
+    if (sm * 4 > FF_SK_FLAG_BYTES) return 0;
+    // CTA pairs (cta_group::2, 256-row pair tiles): opt-in (flag 1073741824) until measured
+    if ((g_debug_flags & 1073741824) && (sm % 2) == 0 && (num_m + 1) / 2 >= sm / 2) return 3;
+    if (num_m <= sm || (num_m % sm) == 0) return 0;
     return 2;
 }
 
 extern "C" int dtlr_ffn_plan(int M, int hidden) { return ffn_plan(M, hidden); }
 
+// timeline probe of the stream-K kernels (tools/ffn_timeline.py): a device buffer of 3 * 64 * 16 u32, or NULL (off)
+static unsigned int* g_ffn_dbgbuf = nullptr;
+extern "C" int dtlr_ffn_debug_buffer(void* buf) { g_ffn_dbgbuf = reinterpret_cast<unsigned int*>(buf); return DTLR_OK; }
+
 extern "C" long long dtlr_ffn_workspace_bytes(int M, int hidden) {
     const int plan = ffn_plan(M, hidden);
-    if (plan == 2) return FF_SK_FLAG_BYTES + (long long)sm_count() * FF_BM * FF_D * 4;
+    if (plan >= 2) return FF_SK_FLAG_BYTES + (long long)sm_count() * FF_BM * FF_D * 4;
     if (plan == 1) {
         int main_rows, rem, ns;
         ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
@@ -943,7 +1072,8 @@ extern "C" int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, 
     if (!plan || !workspace || workspace_bytes < dtlr_ffn_workspace_bytes(M, hidden))
         return dtlr_ffn_ln(X, ldx, W1, ldw1, b1, W2, ldw2, b2, gamma, beta, eps, Y, ldy, M, hidden, stream);
     int rc;
-    if (plan == 2) {
+    if (plan >= 2) {
+        const bool pair = plan == 3;
         DTLR_CHECK_ARG(X && W1 && b1 && W2 && b2 && gamma && beta && Y, "ffn_ln: null pointer");
         DTLR_CHECK_ARG(ldx >= FF_D && ldw1 >= FF_D && ldw2 >= hidden && ldy >= FF_D, "ffn_ln: leading dimension too small");
         DTLR_CHECK_ARG((ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 && (ldy % 8) == 0 &&
@@ -951,17 +1081,21 @@ extern "C" int dtlr_ffn_ln_ws(const void* X, int ldx, const void* W1, int ldw1, 
                        "ffn_ln: operands need 16-byte aligned rows");
         CUtensorMap tx, tw1, tw2, to;
         if ((rc = ffn_tmap(&tx, X, M, FF_D, ldx, FF_BM))) return rc;
-        if ((rc = ffn_tmap(&tw1, W1, hidden, FF_D, ldw1, 128))) return rc;
+        if ((rc = ffn_tmap(&tw1, W1, hidden, FF_D, ldw1, pair ? 64 : 128))) return rc;
         if ((rc = ffn_tmap(&tw2, W2, FF_D, hidden, ldw2, 128))) return rc;
         if ((rc = ffn_tmap(&to, Y, M, FF_D, ldy, 32))) return rc;
         static bool configured_sk = false;
         if (!configured_sk) {
-            DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+            DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_sk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
+            DTLR_CHECK_CUDA(cudaFuncSetAttribute(ffn_ln_sk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL));
             configured_sk = true;
         }
         FfnArgs a{b1, b2, gamma, beta, eps, M, hidden, g_debug_flags, nullptr, nullptr, nullptr, nullptr, 0, 1,
-                  reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + FF_SK_FLAG_BYTES), reinterpret_cast<int*>(workspace)};
-        DTLR_CHECK_CUDA(launch_pdl(ffn_ln_sk_kernel, dim3(sm_count()), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
+                  reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + FF_SK_FLAG_BYTES), reinterpret_cast<int*>(workspace), g_ffn_dbgbuf};
+        if (pair)
+            DTLR_CHECK_CUDA(launch_pdl_cluster(ffn_ln_sk_kernel<true>, dim3(sm_count()), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, 2u, tx, tw1, tw2, to, a));
+        else
+            DTLR_CHECK_CUDA(launch_pdl(ffn_ln_sk_kernel<false>, dim3(sm_count()), dim3(320), FfnSmem::TOTAL, (cudaStream_t)stream, tx, tw1, tw2, to, a));
         return DTLR_OK;
     }
     int main_rows = M, rem = 0, ns = 1;

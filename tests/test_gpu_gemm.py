@@ -212,6 +212,49 @@ def test_fused_ffn_block(M, hid, pairs):
         assert lib.dtlr_ffn_plan(M, hid) == 0
 
 
+@pytest.mark.parametrize("M,hid", [(58368, 2048), (57600 + 13, 2048), (37000, 2048), (148 * 128, 2048), (40000, 1024), (19000, 256)])
+def test_fused_ffn_block_cta_pairs(M, hid):
+    """the stream-K FFN kernel on CTA pairs (tcgen05 cta_group::2: 256-row pair tiles, each CTA holds half of every weight
+    stage; dtlr_debug_flags(1073741824)) vs the plain single-CTA kernel: rows of pair tiles that are not shared between two
+    pairs are bit-equal (same chunk order), shared ones agree to fp32 re-association; repeated calls are bit-equal."""
+    from dtlr_b200 import ops, _lib
+    g = torch.Generator(device="cuda").manual_seed(M + hid)
+    x = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(hid, 256, device="cuda", generator=g) / 16).bfloat16()
+    b1 = 0.5 * torch.randn(hid, device="cuda", generator=g)
+    w2 = (torch.randn(256, hid, device="cuda", generator=g) / hid ** 0.5).bfloat16()
+    b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(256, device="cuda", generator=g)
+    lib = _lib.lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    saved, ops.FFN_FUSED = ops.FFN_FUSED, True
+    try:
+        lib.dtlr_debug_flags(262144)
+        y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+        lib.dtlr_debug_flags(1073741824)
+        assert lib.dtlr_ffn_plan(M, hid) == 3
+        y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+        for _ in range(3):
+            assert torch.equal(ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta), y)
+    finally:
+        ops.FFN_FUSED = saved
+        lib.dtlr_debug_flags(0)
+    assert torch.isfinite(y).all()
+    tiles = (M + 127) // 128
+    ptiles, pairs, nj = (tiles + 1) // 2, sms // 2, hid // 128
+    units = ptiles * nj
+    shared = sorted({(units * c // pairs) // nj for c in range(1, pairs) if (units * c // pairs) % nj})
+    keep = torch.ones(ptiles * 256, dtype=torch.bool, device="cuda")
+    for t in shared:
+        keep[t * 256:(t + 1) * 256] = False
+    keep = keep[:M]
+    assert torch.equal(y[keep], y0[keep])
+    if len(shared):
+        assert (y[~keep].float() - y0[~keep].float()).abs().max().item() < 5e-2
+        assert (y[~keep].float() - y0[~keep].float()).abs().mean().item() < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K,out_dtype", [(57600 * 2, 166, 256, torch.float32), (58368, 166, 256, torch.float32),
                                               (60000, 100, 128, torch.bfloat16), (50000, 200, 256, torch.float32)])
 def test_weight_stationary_ragged_slice_pitched_output(M, N, K, out_dtype):

@@ -23,7 +23,12 @@ for M in Ms:
     gm = torch.ones(256, device="cuda")
     bt = torch.zeros(256, device="cuda")
     _lib.set_flavor(dt)
-    for name, flags in (("stream-K", 0), ("split tail", 536870912), ("plain", 262144)):
+    variants = [("stream-K", 0), ("SK pairs", 1073741824), ("split tail", 536870912), ("plain", 262144)]
+    if os.environ.get("FFN_PROBES"):      # parts of the stream-K kernels switched off (results are garbage; timing only)
+        for base, bn in ((0, "SK"), (1073741824, "SKp")):
+            for pf, pn in ((32768, "spin waits"), (32768 + 1920, "spin skeleton"), (32768 + 1920 + 2048, "spin skeleton - final"), (32768 + 384, "spin MMA only")):
+                variants.append(("%s %s" % (bn, pn), base | pf))
+    for name, flags in variants:
         _lib.lib().dtlr_debug_flags(flags)
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
@@ -46,6 +51,6 @@ for M in Ms:
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / N)
         tf = 4.0 * M * hid * 256 / (best * 1e-3) / 1e12
-        print("M %d %-10s plan %d: %.1f us per block, %.0f TFLOP/s = %.3f of the sustained peak (%.1f)" % (
+        print("M %d %-44s plan %d: %.1f us per block, %.0f TFLOP/s = %.3f of the sustained peak (%.1f)" % (
             M, name, _lib.lib().dtlr_ffn_plan(M, hid), best * 1e3, tf, tf / peak, peak), flush=True)
         _lib.lib().dtlr_debug_flags(0)
