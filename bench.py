@@ -503,11 +503,11 @@ def main():
     # the dominant kernel of the step (profiles/r1_launches_step_v6.txt: 18.9 %): the fused FFN block, one launch per encoder /
     # decoder layer; algorithmic FLOPs 4*M*hid*256 per launch; `traffic` = DRAM bytes of one launch from
     # the ncu --set full capture in profiles/r1_ffn_ncu.txt
-    ffn_traffic, ffn_traffic_src = profile_traffic(r"ffn_ln_tcgen05_kernel", "ffn")
+    ffn_traffic, ffn_traffic_src = profile_traffic(r"ffn_ln_(sk|tcgen05)_kernel", "ffn")
     msda_traffic, msda_traffic_src = profile_traffic(r"msda_fwd", "msda")
     if ffn_events:
         ffn_tf = ffn_flops / (ffn_ms * 1e-3) / 1e12
-        roofline = {"kernel": "ffn_ln_tcgen05_kernel (dtlr_ffn_ln: linear1 + ReLU + linear2 + residual + LayerNorm, hidden activation in TMEM)",
+        roofline = {"kernel": "ffn_ln_sk_kernel<PAIR> (dtlr_ffn_ln_ws: linear1 + ReLU + linear2 + residual + LayerNorm as one stream-K tcgen05 kernel on CTA pairs, cta_group::2; hidden activation in TMEM)",
                     "bound": "tensor", "achieved": round(ffn_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": round(ffn_tf / peak_tf, 4), "traffic": ffn_traffic, "traffic_from": ffn_traffic_src,
                     "peak_kind": pk_kind + " sustained cuBLAS bf16 (the kernel runs inside a long step)",

@@ -482,10 +482,10 @@ ffn_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // The unit stream is software-pipelined ACROSS tile boundaries: G1 of unit v + 1 is issued before G2 of unit v whatever tiles they
 // belong to, so the tensor pipe no longer idles between the last G2 of a tile and the first G1 of the next one.
 // barrier wait of the stream-K kernel: cluster-scope acquire when arrivals / transaction bytes come from the peer CTA (PAIR)
+constexpr bool g_dbg_cluster_scope = false;       // true: cluster-scope acquire on every wait (CCTL.IVALL each; first version)
 template <bool PAIR>
-__device__ __forceinline__ void sk_wait(uint64_t* bar, uint32_t parity, bool spin = false) {
-    if (spin) mbar_spin_cluster(bar, parity);
-    else if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+__device__ __forceinline__ void sk_wait(uint64_t* bar, uint32_t parity) {
+    if (PAIR && (g_dbg_cluster_scope)) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
 }
 
 template <bool PAIR>
@@ -530,7 +530,6 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int nu = u1 - u0;                                  // >= NJ (host: num_pt >= G)
     const int mt0 = u0 / NJ, j0 = u0 - mt0 * NJ;             // mt counts pair tiles when PAIR
     const bool leader = rank == 0;
-    const bool spin = (a.dbg & 32768) != 0;          // probe: busy-polling barrier waits
     unsigned int* const dbgbuf = (cta == 0) ? a.dbgbuf : nullptr;
 #define FF_DBG(role, unit, slot) do { if (dbgbuf && (unit) < 64) dbgbuf[(((role) * 64 + (unit)) * 16 + (slot))] = (unsigned int)clock(); } while (0)
 
@@ -580,7 +579,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             int t = 0;                                           // item (= row tile visited) index of unit v
             auto load_x = [&](int mt, uint32_t tt) {
                 const uint32_t xb = tt & 1;
-                sk_wait<PAIR>(&x_free[xb], ((tt >> 1) & 1) ^ 1, spin);
+                sk_wait<PAIR>(&x_free[xb], ((tt >> 1) & 1) ^ 1);
                 if (leader) mbar_expect_tx(&x_full[xb], NC * FfnSmem::XS);
                 for (int kb = 0; kb < 4; ++kb) {
                     if (PAIR) tma_load_2d_pair(xs + xb * FfnSmem::XS + kb * FF_STAGE, &tmX, ld_x_full + xb * 8, kb * 64, (mt * NC + (int)rank) * FF_BM);
@@ -599,7 +598,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     }
                     for (int kb = 0; kb < (PAIR ? 2 : 4); ++kb, ++it) {  // W1 rows j*128.., k columns kb*64.. (PAIR: 64 rows x 2 k-blocks)
                         const int s = it % NS;
-                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1, spin);
+                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1);
                         FF_DBG(0, v, 1 + kb);
                         if (a.dbg & 128) { if (leader) mbar_arrive(&w_full[s]); continue; }      // probe: no weight stream
                         if (leader) mbar_expect_tx(&w_full[s], NC * WST);
@@ -612,7 +611,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (v >= 1) {
                     for (int q = 0; q < (PAIR ? 2 : 4); ++q, ++it) {    // W2 output rows (q&1)*128.., hidden columns of chunk pj
                         const int s = it % NS;                          // (PAIR: output rows rank*128.., hidden columns q*64..)
-                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1, spin);
+                        sk_wait<PAIR>(&w_empty[s], ((it / NS) & 1) ^ 1);
                         FF_DBG(0, v, 5 + q);
                         if (a.dbg & 128) { if (leader) mbar_arrive(&w_full[s]); continue; }
                         if (leader) mbar_expect_tx(&w_full[s], NC * WST);
@@ -651,7 +650,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (first_v) {
                     ++t;
                     xb = (uint32_t)t & 1;
-                    sk_wait<PAIR>(&x_full[xb], ((uint32_t)t >> 1) & 1, spin);
+                    sk_wait<PAIR>(&x_full[xb], ((uint32_t)t >> 1) & 1);
                     tcgen05_fence_after();
                 }
                 FF_DBG(1, v, 1);
@@ -660,7 +659,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     constexpr uint32_t IDESC2 = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                     for (int st = 0; st < 2; ++st, ++it) {
                         const int s = it % NS;
-                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         FF_DBG(1, v, 2 + 2 * st);
                         if (elect_one()) {
@@ -683,7 +682,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 } else
                 for (int kb = 0; kb < 4; ++kb, ++it) {
                     const int s = it % NS;
-                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t da = make_sw128_kmajor_desc(smem_u32(xs + xb * FfnSmem::XS + kb * FF_STAGE));
@@ -702,16 +701,16 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             if (v >= 1) {
                 const uint32_t w = (uint32_t)(v - 1), b = w & 1;
-                sk_wait<PAIR>(&h_full[b], (w >> 1) & 1, spin);             // 16-bit hidden chunk of unit w is in TMEM (of both CTAs)
+                sk_wait<PAIR>(&h_full[b], (w >> 1) & 1);             // 16-bit hidden chunk of unit w is in TMEM (of both CTAs)
                 FF_DBG(1, v, 6);
-                if (first_w) sk_wait<PAIR>(y_free, ((uint32_t)tw & 1) ^ 1, spin);  // previous item's output accumulator read out
+                if (first_w) sk_wait<PAIR>(y_free, ((uint32_t)tw & 1) ^ 1);  // previous item's output accumulator read out
                 tcgen05_fence_after();
                 FF_DBG(1, v, 7);
                 if (PAIR) {
                     constexpr uint32_t IDESC3 = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
                     for (int kb2 = 0; kb2 < 2; ++kb2, ++it) {
                         const int s = it % NS;
-                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                        sk_wait<PAIR>(&w_full[s], (it / NS) & 1);
                         tcgen05_fence_after();
                         FF_DBG(1, v, 8 + 2 * kb2);
                         if (elect_one()) {
@@ -732,7 +731,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 for (int q = 0; q < 4; ++q, ++it) {
                     const int s = it % NS;
                     const int kb2 = q >> 1, half = q & 1;
-                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1, spin);
+                    sk_wait<PAIR>(&w_full[s], (it / NS) & 1);
                     tcgen05_fence_after();
                     if (elect_one()) {
                         const uint64_t db = make_sw128_kmajor_desc(smem_u32(ring + s * WST));
@@ -761,6 +760,58 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // workspace slot s: [64 column groups of 4][128 rows] float4 -- a warp's 32 rows are consecutive 16-byte words
         int mt = mt0, js = j0;
         uint32_t t = 0;
+        // The LayerNorm of a finished item is split: pass 1 (TMEM + b2 + X -> 16-bit pre-norm rows written IN PLACE over the X tile,
+        // row statistics) runs at once and releases the output accumulator; pass 2 (normalise in place, TMA store, X buffer release)
+        // is cut into 4 column chunks that run in the idle time after the next item's first E1 steps -- measured (tools/
+        // ffn_timeline.py): E1 takes ~1,200 of the ~2,300 clk of a unit, while the un-split LayerNorm stalled the MMA warp for
+        // ~12,000 clk per row tile
+        int pend = 0;                                        // pass-2 chunks still to do (4 .. 1), 0: none
+        bool p_store = false;                                // stores issued, their shared-memory reads not yet awaited
+        unsigned char* p_xt = xs;
+        int p_row0 = 0;
+        uint32_t p_xb = 0;
+        float p_mean = 0.f, p_rstd = 0.f;
+        auto pass2 = [&]() {
+            if (pend > 0) {
+                const int c = 4 - pend, cb = c >> 1, k0 = (c & 1) * 4;
+                unsigned char* xrow = p_xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                const float* gp = gamma_s + hsel * 128 + cb * 64 + k0 * 8;
+                const float* bp = beta_s + hsel * 128 + cb * 64 + k0 * 8;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    uint4* px = reinterpret_cast<uint4*>(xrow + (((k0 + kk) ^ swz) * 16));
+                    const uint4 r4 = *px;
+                    const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                    const float4 g0 = *reinterpret_cast<const float4*>(gp + kk * 8), g1 = *reinterpret_cast<const float4*>(gp + kk * 8 + 4);
+                    const float4 e0 = *reinterpret_cast<const float4*>(bp + kk * 8), e1 = *reinterpret_cast<const float4*>(bp + kk * 8 + 4);
+                    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        o[i] = ff_pack_bf16x2((op16_lo_f32(rw[i]) - p_mean) * p_rstd * gg[2 * i] + ee[2 * i],
+                                              (op16_hi_f32(rw[i]) - p_mean) * p_rstd * gg[2 * i + 1] + ee[2 * i + 1]);
+                    *px = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (--pend == 0) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        for (int cb2 = 0; cb2 < 2; ++cb2)
+                            tma_store_2d(&tmO, p_xt + (hsel * 2 + cb2) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb2) * 64, p_row0 + qd * 32);
+                        tma_store_commit();
+                    }
+                    p_store = true;
+                }
+            } else if (p_store) {
+                if (lane == 0) {
+                    tma_store_wait_read<0>();                                // the X buffer may now be refilled
+                    mbar_arrive(&x_free[p_xb]);
+                }
+                __syncwarp();
+                p_store = false;
+            }
+        };
         for (int v = 0; v < nu; ++t, ++mt, js = 0) {
             const int n = (NJ - js < nu - v) ? NJ - js : nu - v;
             const bool tail = (js > 0) && !(a.dbg & 16384), head = (js == 0) && (n < NJ) && !(a.dbg & 16384);   // probe 16384: no partial exchange
@@ -768,7 +819,7 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int i = 0; i < n; ++i, ++v) {
                 const uint32_t b = (uint32_t)v & 1, u = (uint32_t)v >> 1;
                 if (threadIdx.x == 64) FF_DBG(2, v, 0);
-                sk_wait<PAIR>(&hacc_full[b], u & 1, spin);
+                sk_wait<PAIR>(&hacc_full[b], u & 1);
                 tcgen05_fence_after();
                 if (threadIdx.x == 64) FF_DBG(2, v, 1);
                 if (a.dbg & 256) {                                                               // probe: no E1 work
@@ -798,12 +849,14 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (threadIdx.x == 64) FF_DBG(2, v, 4);
                 if (lane == 0) { if (PAIR) mbar_arrive_cluster(ld_h_full + b * 8); else mbar_arrive(&h_full[b]); }
                 if (threadIdx.x == 64) FF_DBG(2, v, 5);
+                pass2();
             }
+            while (pend > 0 || p_store) pass2();             // (short item: whatever is left of the previous item's LayerNorm)
             const uint32_t xb = t & 1;
             unsigned char* xt = xs + xb * FfnSmem::XS;
             if (tail) {
                 // ---- final (tail part): raw fp32 partial -> workspace slot `cta`, then the ready flag for the left neighbour
-                sk_wait<PAIR>(y_full, t & 1, spin);
+                sk_wait<PAIR>(y_full, t & 1);
                 tcgen05_fence_after();
                 if (lane == 0) mbar_arrive(&x_free[xb]);
                 float4* dst = reinterpret_cast<float4*>(a.partial) + (size_t)cta * (FF_BM * FF_D / 4) + row;
@@ -832,8 +885,8 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             // (PAIR: this CTA's X tile completed on the leader's barrier; y_full -- every MMA of the pair done -- implies it landed)
             if (threadIdx.x == 64) FF_DBG(2, 56 + t, 0);
-            if (!PAIR) sk_wait<PAIR>(&x_full[xb], (t >> 1) & 1, spin);
-            sk_wait<PAIR>(y_full, t & 1, spin);
+            if (!PAIR) sk_wait<PAIR>(&x_full[xb], (t >> 1) & 1);
+            sk_wait<PAIR>(y_full, t & 1);
             tcgen05_fence_after();
             if (threadIdx.x == 64) FF_DBG(2, 56 + t, 1);
             const float4* psrc = reinterpret_cast<const float4*>(a.partial) + (size_t)(cta + NC) * (FF_BM * FF_D / 4) + row;
@@ -854,7 +907,6 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 continue;
             }
             float sum = 0.f, sq = 0.f;
-            uint32_t xp[64];                                 // the row's 128 pre-norm values of this warp, packed 16-bit pairs
 #pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
@@ -877,24 +929,29 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                             acc[4 * i + 3] = __float_as_uint(__uint_as_float(acc[4 * i + 3]) + p.w);
                         }
                     }
-                    const unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
+                    unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
                     const float* bp = b2_s + hsel * 128 + cb * 64 + hf * 32;
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const int k = hf * 4 + kk;
-                        const uint4 r4 = *reinterpret_cast<const uint4*>(xrow + ((k ^ swz) * 16));
+                        uint4* px = reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16));
+                        const uint4 r4 = *px;
                         const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                        const float4 q0 = *reinterpret_cast<const float4*>(bp + kk * 8), q1 = *reinterpret_cast<const float4*>(bp + kk * 8 + 4);
+                        const float bb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        uint32_t o[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bp[kk * 8 + 2 * i] + op16_lo_f32(rw[i]);
-                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bp[kk * 8 + 2 * i + 1] + op16_hi_f32(rw[i]);
+                            const float x0 = __uint_as_float(acc[kk * 8 + 2 * i]) + bb[2 * i] + op16_lo_f32(rw[i]);
+                            const float x1 = __uint_as_float(acc[kk * 8 + 2 * i + 1]) + bb[2 * i + 1] + op16_hi_f32(rw[i]);
                             const uint32_t pk = ff_pack_bf16x2(x0, x1);
-                            xp[cb * 32 + k * 4 + i] = pk;
+                            o[i] = pk;
                             const float y0 = op16_lo_f32(pk), y1 = op16_hi_f32(pk);
                             sum += y0 + y1;
                             sq = fmaf(y0, y0, sq);
                             sq = fmaf(y1, y1, sq);
                         }
+                        *px = make_uint4(o[0], o[1], o[2], o[3]);      // the pre-norm row replaces the residual it was made from
                     }
                 }
             }
@@ -907,40 +964,16 @@ ffn_ln_sk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             stat_s[(row * 2 + hsel) * 2] = sum;
             stat_s[(row * 2 + hsel) * 2 + 1] = sq;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // the two warps of this lane quarter
-            const float mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
-            const float var = fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + a.eps);
+            p_mean = (stat_s[row * 4] + stat_s[row * 4 + 2]) * (1.f / 256.f);
+            p_rstd = rsqrtf(fmaxf((stat_s[row * 4 + 1] + stat_s[row * 4 + 3]) * (1.f / 256.f) - p_mean * p_mean, 0.f) + a.eps);
             asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");       // statistics consumed before the next item overwrites them
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                unsigned char* xrow = xt + (hsel * 2 + cb) * FF_STAGE + row * 128;
-                const int c0 = hsel * 128 + cb * 64;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t pk = xp[cb * 32 + k * 4 + i];
-                        const int c = c0 + k * 8 + 2 * i;
-                        o[i] = ff_pack_bf16x2((op16_lo_f32(pk) - mean) * rstd * gamma_s[c] + beta_s[c],
-                                              (op16_hi_f32(pk) - mean) * rstd * gamma_s[c + 1] + beta_s[c + 1]);
-                    }
-                    *reinterpret_cast<uint4*>(xrow + ((k ^ swz) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
+            pend = 4;
+            p_xt = xt;
+            p_xb = xb;
+            p_row0 = (mt * NC + (int)rank) * FF_BM;
             if (threadIdx.x == 64) FF_DBG(2, 56 + t, 3);
-            if (lane == 0) {
-                for (int cb = 0; cb < 2; ++cb)
-                    tma_store_2d(&tmO, xt + (hsel * 2 + cb) * FF_STAGE + (qd * 32) * 128, (hsel * 2 + cb) * 64, (mt * NC + (int)rank) * FF_BM + qd * 32);
-                tma_store_commit();
-                tma_store_wait_read<0>();                                    // this X buffer may now be refilled
-                mbar_arrive(&x_free[xb]);
-            }
-            __syncwarp();
-            if (threadIdx.x == 64) FF_DBG(2, 56 + t, 4);
         }
+        while (pend > 0 || p_store) pass2();                 // the last item's LayerNorm has nothing left to hide under
         if (lane == 0) tma_store_wait<0>();
     }
     tcgen05_fence_before();
@@ -1024,9 +1057,9 @@ static void ffn_split_plan(int M, int hidden, int* main_rows, int* rem_tiles, in
     *main_rows = full * sm * FF_BM; *rem_tiles = rem; *nsplit = ns;
 }
 
-// Which plan dtlr_ffn_ln_ws runs for a shape: 0 = the plain persistent kernel (one round, or an exact number of rounds), 1 = full
+// Which plan dtlr_ffn_ln_ws runs for a shape: 0 = the plain persistent kernel (fewer tiles than one pair tile per CTA pair), 1 = full
 // rounds + PART tail + ffn_tail_ln_kernel (round-2 first version, kept behind dtlr_debug_flags(536870912) for A/B), 2 = stream-K
-// (ffn_ln_sk_kernel, one launch).
+// on single CTAs (ffn_ln_sk_kernel<false>; A/B flag 1073741824), 3 = stream-K on CTA pairs (ffn_ln_sk_kernel<true>, the default).
 constexpr long long FF_SK_FLAG_BYTES = 1024;
 static int ffn_plan(int M, int hidden) {
     if (M <= 0 || hidden <= 0 || (hidden % FF_HC) != 0 || hidden > FF_MAX_HID) return 0;
@@ -1038,8 +1071,9 @@ static int ffn_plan(int M, int hidden) {
         return rem ? 1 : 0;
     }
     if (sm * 4 > FF_SK_FLAG_BYTES) return 0;
-    // CTA pairs (cta_group::2, 256-row pair tiles): opt-in (flag 1073741824) until measured
-    if ((g_debug_flags & 1073741824) && (sm % 2) == 0 && (num_m + 1) / 2 >= sm / 2) return 3;
+    // stream-K on CTA pairs (cta_group::2, 256-row pair tiles): the default from one pair tile per pair upwards (measured at
+    // M = 58368: 92 us against 108-118 us for the single-CTA stream-K kernel); flag 1073741824: single-CTA kernels only (A/B)
+    if (!(g_debug_flags & 1073741824) && (sm % 2) == 0 && (num_m + 1) / 2 >= sm / 2) return 3;
     if (num_m <= sm || (num_m % sm) == 0) return 0;
     return 2;
 }

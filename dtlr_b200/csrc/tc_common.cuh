@@ -141,8 +141,11 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// (default semantics, .release.cta, as CUTLASS's ClusterBarrier::arrive(cta_id): what is handed over lives in tensor memory and is
+// ordered by the tcgen05 fences.  A .release.cluster arrive compiles to MEMBAR.ALL.GPU (~1,300 clk measured in the FFN kernel's E1
+// step), an .acquire.cluster wait to a CCTL.IVALL after every barrier -- both were on the critical path of the first version)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // wait on a barrier that receives arrivals from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -154,16 +157,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "@P1 bra DONE_C;\n\t"
         "bra WAIT_LOOP_C;\n\t"
         "DONE_C:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// busy-polling wait (mbarrier.test_wait never suspends the thread): for the warps whose wake-up latency is on the critical path
-__device__ __forceinline__ void mbar_spin_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "SPIN_LOOP_C:\n\t"
-        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@!P1 bra SPIN_LOOP_C;\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 template <int NCOLS>

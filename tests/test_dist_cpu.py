@@ -113,7 +113,7 @@ def test_bench_secondary_views_arithmetic():
     b = bench.msda_binding_view(107.0, 148, 1965.0, 20217621, "profiles/x.txt")
     assert abs(b["binding_floor_us"] - 69.5) < 0.1 and abs(b["binding_frac"] - 0.65) < 0.01
     # the ncu-derived constants are parsed from the committed summaries, not pasted into bench.py
-    t, src = bench.profile_traffic(r"ffn_ln_tcgen05_kernel", "ffn")
+    t, src = bench.profile_traffic(r"ffn_ln_(sk|tcgen05)_kernel", "ffn")
     assert src is not None and 1e6 < t < 1e9
     m, src = bench.profile_metrics(r"msda_fwd", ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",), "msda")
     assert src is not None and m["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"] > 1e6

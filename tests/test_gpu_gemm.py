@@ -132,15 +132,7 @@ def test_weight_stationary_kernel(M, N, K, out_dtype):
             assert (o.float() - old.float()).abs().max().item() <= 2 ** -7 * r.abs().max().item()
 
 
-@pytest.mark.parametrize("M,hid", [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048), (37000, 2048), (50688, 2048), (40000, 1024),
-                                   (148 * 256, 2048), (19000, 256)])
-@pytest.mark.parametrize("pairs", [True, False])
-def test_fused_ffn_block(M, hid, pairs):
-    """dtlr_ffn_ln: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM / shared memory) vs
-    torch fp32 on the same bf16 operands with the hidden activation rounded to bf16 (as both our paths do), and vs the
-    un-fused kernels (linear1 GEMM + linear2/LayerNorm GEMM)."""
-    import torch.nn.functional as F
-    from dtlr_b200 import ops
+def _ffn_operands(M, hid):
     g = torch.Generator(device="cuda").manual_seed(M + hid)
     x = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
     w1 = (torch.randn(hid, 256, device="cuda", generator=g) / 16).bfloat16()
@@ -149,14 +141,49 @@ def test_fused_ffn_block(M, hid, pairs):
     b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
     gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
     beta = 0.1 * torch.randn(256, device="cuda", generator=g)
-    from dtlr_b200 import _lib
+    return x, w1, b1, w2, b2, gamma, beta
+
+
+FFN_SHAPES = [(128, 2048), (300, 256), (5000, 1024), (58368, 2048), (57600 + 13, 2048), (37000, 2048), (50688, 2048), (40000, 1024),
+              (148 * 256, 2048), (148 * 128, 2048), (19000, 256), (29184, 2048)]
+# dtlr_debug_flags: 0 default plan (stream-K on CTA pairs from 74 pair tiles upwards), 1073741824 single-CTA kernels (stream-K with
+# more than one round of tiles), 536870912 full rounds + split tail + tail kernel, 4096 CTA pairs that only multicast the weights
+FFN_MODES = {"default": 0, "single": 1073741824, "split-tail": 1073741824 | 536870912, "multicast": 4096}
+
+
+@pytest.mark.parametrize("M,hid", FFN_SHAPES)
+@pytest.mark.parametrize("mode", list(FFN_MODES))
+def test_fused_ffn_block(M, hid, mode):
+    """dtlr_ffn_ln_ws: LN(x + W2 relu(W1 x + b1) + b2) in one tcgen05 kernel (hidden activation only in TMEM) vs torch fp32 on the
+    same 16-bit operands with the hidden activation rounded to 16 bits (as every path does), vs the un-fused kernels (linear1 GEMM +
+    linear2/LayerNorm GEMM), and -- every plan of the library -- vs the plain persistent kernel: rows of (pair) tiles that are not
+    shared between two neighbouring CTAs (pairs) must be BIT-EQUAL (same chunk order), shared ones agree to fp32 re-association;
+    repeated calls on the same workspace are bit-equal (ready flags handed back, fixed summation order)."""
+    import torch.nn.functional as F
+    from dtlr_b200 import ops, _lib
+    x, w1, b1, w2, b2, gamma, beta = _ffn_operands(M, hid)
+    lib = _lib.lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    tiles, nj = (M + 127) // 128, hid // 128
     saved, ops.FFN_FUSED = ops.FFN_FUSED, True
-    _lib.lib().dtlr_debug_flags(4096 if pairs else 0)      # CTA pairs with multicast weights (opt-in) / independent CTAs (default)
     try:
+        lib.dtlr_debug_flags(262144)
+        assert lib.dtlr_ffn_plan(M, hid) == 0
+        y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+        lib.dtlr_debug_flags(FFN_MODES[mode])
+        plan = lib.dtlr_ffn_plan(M, hid)
         y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
+        for _ in range(3):
+            assert torch.equal(ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta), y)
     finally:
         ops.FFN_FUSED = saved
-        _lib.lib().dtlr_debug_flags(0)
+        lib.dtlr_debug_flags(0)
+    if mode == "default":
+        assert plan == (3 if (tiles + 1) // 2 >= sms // 2 else 0)
+    elif mode == "single":
+        assert plan == (2 if tiles > sms and tiles % sms else 0)
+    elif mode == "multicast":
+        assert plan == 0
     h = torch.relu(x.float() @ w1.float().T + b1).bfloat16().float()
     pre = (h @ w2.float().T + b2 + x.float()).bfloat16().float()
     ref = F.layer_norm(pre, (256,), gamma, beta, 1e-5)
@@ -165,92 +192,25 @@ def test_fused_ffn_block(M, hid, pairs):
     assert (y.float() - ref).abs().mean().item() < 4e-3
     un = ops.linear_ln(ops.gemm(x, w1, b1, relu=1), w2, b2, x, gamma, beta)
     assert (y.float() - un.float()).abs().max().item() < 5e-2
-    # many row tiles per CTA and a ragged last tile are covered by the M = 58368 / 57613 cases (X double buffer, tile pipelining).
-    # With more than one round of tiles (and no exact number of rounds) the default plan is the STREAM-K kernel: equal (tile,
-    # hidden chunk) unit ranges per CTA, a tile that straddles a range boundary is summed from two neighbours' partials.  Rows of
-    # tiles that are not shared must be bit-equal to the plain persistent kernel (same chunk order), shared tiles agree to fp32
-    # re-association; repeated calls on the same workspace are bit-equal (ready flags handed back, fixed summation order); the
-    # round-2 PART-tail plan (flag 536870912) must agree as well.
-    import ctypes
-    lib = _lib.lib()
-    lib.dtlr_ffn_workspace_bytes.restype = ctypes.c_longlong
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    tiles = (M + 127) // 128
-    if pairs:
-        return
-    if tiles > sms and tiles % sms != 0:
-        assert lib.dtlr_ffn_plan(M, hid) == 2 and lib.dtlr_ffn_workspace_bytes(M, hid) > 0
-        saved_split, ops.FFN_SPLIT_TAIL = ops.FFN_SPLIT_TAIL, False
-        try:
-            y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
-        finally:
-            ops.FFN_SPLIT_TAIL = saved_split
-        nj = hid // 128
-        units = tiles * nj
-        shared = sorted({(units * c // sms) // nj for c in range(1, sms) if (units * c // sms) % nj})
-        assert len(shared) > 0
-        keep = torch.ones(tiles * 128, dtype=torch.bool, device="cuda")
-        for t in shared:
-            keep[t * 128:(t + 1) * 128] = False
-        keep = keep[:M]
-        assert torch.equal(y[keep], y0[keep])
-        assert (y[~keep].float() - y0[~keep].float()).abs().max().item() < 5e-2
-        assert (y[~keep].float() - y0[~keep].float()).abs().mean().item() < 2e-3
-        for _ in range(3):
-            assert torch.equal(ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta), y)
-        if 0 < tiles % sms <= sms // 2 and hid >= 256:
-            lib.dtlr_debug_flags(536870912)
-            try:
-                assert lib.dtlr_ffn_plan(M, hid) == 1
-                y1 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
-            finally:
-                lib.dtlr_debug_flags(0)
-            main_rows = (tiles // sms) * sms * 128
-            assert torch.equal(y1[:main_rows], y0[:main_rows])
-            assert (y1[main_rows:].float() - y0[main_rows:].float()).abs().max().item() < 5e-2
+    # which rows may differ from the plain kernel
+    keep = torch.ones(((tiles + 1) // 2) * 256, dtype=torch.bool, device="cuda")
+    if plan == 3:
+        groups, rows, n_t = sms // 2, 256, (tiles + 1) // 2
+    elif plan == 2:
+        groups, rows, n_t = sms, 128, tiles
     else:
-        assert lib.dtlr_ffn_plan(M, hid) == 0
-
-
-@pytest.mark.parametrize("M,hid", [(58368, 2048), (57600 + 13, 2048), (37000, 2048), (148 * 128, 2048), (40000, 1024), (19000, 256)])
-def test_fused_ffn_block_cta_pairs(M, hid):
-    """the stream-K FFN kernel on CTA pairs (tcgen05 cta_group::2: 256-row pair tiles, each CTA holds half of every weight
-    stage; dtlr_debug_flags(1073741824)) vs the plain single-CTA kernel: rows of pair tiles that are not shared between two
-    pairs are bit-equal (same chunk order), shared ones agree to fp32 re-association; repeated calls are bit-equal."""
-    from dtlr_b200 import ops, _lib
-    g = torch.Generator(device="cuda").manual_seed(M + hid)
-    x = torch.randn(M, 256, device="cuda", generator=g).bfloat16()
-    w1 = (torch.randn(hid, 256, device="cuda", generator=g) / 16).bfloat16()
-    b1 = 0.5 * torch.randn(hid, device="cuda", generator=g)
-    w2 = (torch.randn(256, hid, device="cuda", generator=g) / hid ** 0.5).bfloat16()
-    b2 = 0.5 * torch.randn(256, device="cuda", generator=g)
-    gamma = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
-    beta = 0.1 * torch.randn(256, device="cuda", generator=g)
-    lib = _lib.lib()
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    saved, ops.FFN_FUSED = ops.FFN_FUSED, True
-    try:
-        lib.dtlr_debug_flags(262144)
-        y0 = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
-        lib.dtlr_debug_flags(1073741824)
-        assert lib.dtlr_ffn_plan(M, hid) == 3
-        y = ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta)
-        for _ in range(3):
-            assert torch.equal(ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta), y)
-    finally:
-        ops.FFN_FUSED = saved
-        lib.dtlr_debug_flags(0)
-    assert torch.isfinite(y).all()
-    tiles = (M + 127) // 128
-    ptiles, pairs, nj = (tiles + 1) // 2, sms // 2, hid // 128
-    units = ptiles * nj
-    shared = sorted({(units * c // pairs) // nj for c in range(1, pairs) if (units * c // pairs) % nj})
-    keep = torch.ones(ptiles * 256, dtype=torch.bool, device="cuda")
-    for t in shared:
-        keep[t * 256:(t + 1) * 256] = False
+        groups, rows, n_t = 0, 128, tiles
+    if plan == 1:
+        keep[(tiles // sms) * sms * 128:] = False
+    elif groups:
+        units = n_t * nj
+        for c in range(1, groups):
+            if (units * c // groups) % nj:
+                t = (units * c // groups) // nj
+                keep[t * rows:(t + 1) * rows] = False
     keep = keep[:M]
     assert torch.equal(y[keep], y0[keep])
-    if len(shared):
+    if (~keep).any():
         assert (y[~keep].float() - y0[~keep].float()).abs().max().item() < 5e-2
         assert (y[~keep].float() - y0[~keep].float()).abs().mean().item() < 2e-3
 

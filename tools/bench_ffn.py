@@ -1,5 +1,6 @@
 """Fused FFN block (dtlr_ffn_ln_ws) at the bench shapes, timed as a CUDA graph of N back-to-back calls on rotating inputs
-(> L2 working set), per plan: stream-K (default) / full rounds + split tail (dtlr_debug_flags 536870912) / plain (262144).
+(> L2 working set), per plan: stream-K on CTA pairs (default) / on single CTAs (dtlr_debug_flags 1073741824) / full rounds + split
+tail (536870912) / plain (262144).
 python tools/bench_ffn.py [M ...]"""
 import os
 import sys
@@ -23,11 +24,7 @@ for M in Ms:
     gm = torch.ones(256, device="cuda")
     bt = torch.zeros(256, device="cuda")
     _lib.set_flavor(dt)
-    variants = [("stream-K", 0), ("SK pairs", 1073741824), ("split tail", 536870912), ("plain", 262144)]
-    if os.environ.get("FFN_PROBES"):      # parts of the stream-K kernels switched off (results are garbage; timing only)
-        for base, bn in ((0, "SK"), (1073741824, "SKp")):
-            for pf, pn in ((32768, "spin waits"), (32768 + 1920, "spin skeleton"), (32768 + 1920 + 2048, "spin skeleton - final"), (32768 + 384, "spin MMA only")):
-                variants.append(("%s %s" % (bn, pn), base | pf))
+    variants = [("stream-K, CTA pairs (default)", 0), ("stream-K, single CTAs", 1073741824), ("full rounds + split tail", 536870912), ("plain", 262144)]
     for name, flags in variants:
         _lib.lib().dtlr_debug_flags(flags)
         side = torch.cuda.Stream()
