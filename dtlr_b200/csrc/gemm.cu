@@ -71,7 +71,11 @@ struct GemmEpi {
     LnArgs ln;
     ConvGeo conv;            // conv.enabled: implicit-GEMM convolution (A fetched through the 4-D map)
     int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
+    unsigned int* dbgbuf;    // timeline probe (dtlr_gemm_debug_buffer): CTA 0 of the weight-stationary kernel records clock() stamps
 };
+
+static unsigned int* g_gemm_dbgbuf = nullptr;
+extern "C" int dtlr_gemm_debug_buffer(void* buf) { g_gemm_dbgbuf = reinterpret_cast<unsigned int*>(buf); return DTLR_OK; }
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 bf16 = 128 B = one swizzle atom row
@@ -604,6 +608,9 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int n0 = slice * BN;
     const int num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+    unsigned int* const dbgbuf = (blockIdx.x == 0) ? e.dbgbuf : nullptr;
+#define WS_DBG(role, unit, slot) do { if (dbgbuf && (unit) < 64) dbgbuf[(((role) * 64 + (unit)) * 16 + (slot))] = (unsigned int)clock(); } while (0)
+    WS_DBG(3, 0, warp < 15 ? warp : 15);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -630,6 +637,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t tmem_base = *tmem_ptr;
     pdl_launch_dependents();
     if (warp != 0) pdl_wait();                         // (the producer first fetches the constant weight slice)
+    if (warp == 1) WS_DBG(3, 1, 0);
 
     if (warp == 0) {
         // ===== TMA producer: the weight slice once, then A tiles
@@ -640,11 +648,14 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             pdl_wait();                                // activations of the previous kernel from here on
             uint32_t it = 0;
-            for (int mt = r0; mt < num_m; mt += cps) {
+            int tcd = 0;
+            for (int mt = r0; mt < num_m; mt += cps, ++tcd) {
+                WS_DBG(0, tcd, 0);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    WS_DBG(0, tcd, 1 + kb);
                     mbar_expect_tx(&full_bar[s], S::A_BYTES);
                     tma_load_2d(aring + s * S::A_BYTES, &tmA, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM);
                 }
@@ -656,8 +667,10 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t it = 0, tcount = 0;
         for (int mt = r0; mt < num_m; mt += cps, ++tcount) {
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+            WS_DBG(1, tcount, 0);
             mbar_wait(&tmem_empty_bar[as], aph ^ 1);
             tcgen05_fence_after();
+            WS_DBG(1, tcount, 1);
             const uint32_t tmem_d = tmem_base + as * BN;
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
@@ -665,6 +678,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (tcount == 0) mbar_wait(&w_bar[kb], 0);              // weight k-block resident (first tile only)
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
+                WS_DBG(1, tcount, 2 + 2 * kb);
                 if (elect_one()) {
                     const uint64_t da = make_sw128_kmajor_desc(smem_u32(aring + s * S::A_BYTES));
                     const uint64_t db = make_sw128_kmajor_desc(smem_u32(wreg + kb * S::W_KB_BYTES));
@@ -677,6 +691,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
                 }
                 __syncwarp();
+                WS_DBG(1, tcount, 3 + 2 * kb);
             }
         }
     } else {
@@ -711,6 +726,8 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int m0 = mt * GEMM_BM;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             bool waited = false;
+            int blkd = 0;
+            if (threadIdx.x == 64) WS_DBG(2, tcount, 0);
             if (!(e.dbg & 4)) {
 #pragma unroll 1
                 for (int cb = hsel; cb < NCB; cb += 2, ++bcount) {
@@ -732,6 +749,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         tcgen05_fence_after();
                         waited = true;
                     }
+                    if (threadIdx.x == 64) WS_DBG(2, tcount, 1 + 5 * blkd);
                     uint32_t acc[CB];
                     TmemBlock<OutT, CB>::load(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * CB), acc);
                     if (cb + 2 >= NCB) {                                 // last TMEM read of this accumulator by this warp
@@ -739,6 +757,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                     }
+                    if (threadIdx.x == 64) WS_DBG(2, tcount, 2 + 5 * blkd);
                     float v[CB];
 #pragma unroll
                     for (int j = 0; j < CB; j += 4) {
@@ -761,9 +780,11 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             for (int i = 0; i < EPC; ++i) v[k * EPC + i] = e.relu == 3 ? (g[i] > 0.f ? v[k * EPC + i] : 0.f) : v[k * EPC + i] + g[i];
                         }
                     } else {
+                        if (threadIdx.x == 64) WS_DBG(2, tcount, 3 + 5 * blkd);
                         if (lane == 0) tma_store_wait_read<0>();         // the previous store has finished reading this buffer
                         __syncwarp();
                     }
+                    if (threadIdx.x == 64) WS_DBG(2, tcount, 4 + 5 * blkd);
                     if (e.relu == 2) {
 #pragma unroll
                         for (int j = 0; j < CB; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -777,6 +798,8 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         tma_store_2d(&tmC, buf, n0 + cb * CB, m0 + qd * 32);
                         tma_store_commit();
                     }
+                    if (threadIdx.x == 64) WS_DBG(2, tcount, 5 + 5 * blkd);
+                    ++blkd;
                 }
             }
             if (!waited) {                                               // no block of this tile belongs to this warp
@@ -787,6 +810,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
         if (lane == 0) tma_store_wait<0>();                              // the buffers must outlive the last store
+        if (threadIdx.x == 64) WS_DBG(3, 2, 0);
         }   // !LN
     }
     __syncthreads();
@@ -945,7 +969,9 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
     const int ns = (e.N + BN - 1) / BN, num_m = (e.M + GEMM_BM - 1) / GEMM_BM;
     int cps = sm_count() / ns;
     if (cps > num_m) cps = num_m;
-    DTLR_CHECK_CUDA(launch_pdl(k, dim3(ns * cps), dim3(320), S::TOTAL, st, ta, tb, tc, tr, e, ns, cps));
+    GemmEpi e2 = e;
+    e2.dbgbuf = g_gemm_dbgbuf;
+    DTLR_CHECK_CUDA(launch_pdl(k, dim3(ns * cps), dim3(320), S::TOTAL, st, ta, tb, tc, tr, e2, ns, cps));
     return DTLR_OK;
 }
 
