@@ -12,6 +12,7 @@ from dtlr_b200 import _lib, ops  # noqa: E402
 
 M, N, K = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (58368, 256, 256)
 res = len(sys.argv) > 4 and sys.argv[4] == "1"
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 dt = torch.float16
 g = torch.Generator(device="cuda").manual_seed(0)
 a = [torch.randn(M, K, device="cuda", generator=g).to(dt) for _ in range(3)]
@@ -20,6 +21,7 @@ b = torch.randn(N, device="cuda", generator=g) * 0.1
 r = torch.randn(M, N, device="cuda", generator=g).to(dt) if res else None
 _lib.set_flavor(dt)
 lib = _lib.lib()
+lib.dtlr_debug_flags(flags)
 buf = torch.zeros(4 * 64 * 16, dtype=torch.int32, device="cuda")
 for i in range(4):
     ops.gemm(a[i % 3], w, b, residual=r)
@@ -33,7 +35,9 @@ gr.replay()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
-print("M %d N %d K %d residual %s: %.1f us per call in a graph of 12" % (M, N, K, res, e0.elapsed_time(e1) / 12 * 1e3))
+print("M %d N %d K %d residual %s flags %d: %.1f us per call in a graph of 12" % (M, N, K, res, flags, e0.elapsed_time(e1) / 12 * 1e3))
+if os.environ.get("WS_TIME_ONLY"):
+    sys.exit(0)
 lib.dtlr_gemm_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
 ops.gemm(a[1], w, b, residual=r)
 ops.gemm(a[2], w, b, residual=r)      # the second launch overwrites: it is the one that overlapped a predecessor
