@@ -396,12 +396,16 @@ FFN_SPLIT_TAIL = _os.environ.get("DTLR_FFN_SPLIT_TAIL", "1") != "0"
 
 
 _FFN_WS = {}
+_FFN_WS_RETIRED = []      # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def _ffn_workspace(device, nbytes):
+    """zero-initialised workspace of the stream-K FFN kernel (ready flags + partial tiles), one per (device, stream)"""
     key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     ws = _FFN_WS.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _FFN_WS_RETIRED.append(ws)
         ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
         _FFN_WS[key] = ws
     return ws
