@@ -729,8 +729,15 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             int blkd = 0;
             if (threadIdx.x == 64) WS_DBG(2, tcount, 0);
             if (!(e.dbg & 4)) {
-#pragma unroll 1
-                for (int cb = hsel; cb < NCB; cb += 2, ++bcount) {
+                // TMEM reads in 32-column pieces, one piece ahead: while piece i is converted / staged, piece i + 1 is on its way
+                constexpr int PPB = CB / 32;                             // pieces per block (16-bit output: 2, fp32: 1)
+                constexpr int NBLK = (NCB + 1) / 2;                      // blocks of a tile this warp may own
+                const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(qd * 32) << 16);
+                uint32_t ra[32], rb[32];
+#pragma unroll
+                for (int bi = 0; bi < NBLK; ++bi) {
+                    const int cb = hsel + 2 * bi;
+                    if (cb >= NCB) break;
                     unsigned char* buf = buf0 + (RES ? (bcount & 1) * S::BLK_BYTES : 0);
                     if (RES && lane == 0) {
                         // the other buffer was last read by the store of block bcount-1 (the newest bulk group): once that read is
@@ -748,23 +755,33 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         mbar_wait(&tmem_full_bar[as], aph);
                         tcgen05_fence_after();
                         waited = true;
+                        tmem_ld32_issue(tacc + (uint32_t)(cb * CB), ra);             // (bi == 0: the first piece of the tile)
                     }
                     if (threadIdx.x == 64) WS_DBG(2, tcount, 1 + 5 * blkd);
-                    uint32_t acc[CB];
-                    TmemBlock<OutT, CB>::load(tmem_base + as * BN + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cb * CB), acc);
-                    if (cb + 2 >= NCB) {                                 // last TMEM read of this accumulator by this warp
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                    }
-                    if (threadIdx.x == 64) WS_DBG(2, tcount, 2 + 5 * blkd);
                     float v[CB];
 #pragma unroll
-                    for (int j = 0; j < CB; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cb * CB + j);
-                        v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
-                        v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+                    for (int pp = 0; pp < PPB; ++pp) {
+                        tmem_wait_ld();                                              // piece (cb, pp) has arrived
+                        const bool more = (pp + 1 < PPB) || (cb + 2 < NCB);
+                        const uint32_t nxt = tacc + (uint32_t)((pp + 1 < PPB) ? cb * CB + (pp + 1) * 32 : (cb + 2) * CB);
+                        auto step = [&](uint32_t (&cur)[32], uint32_t (&other)[32]) {
+                            if (more) {
+                                tmem_ld32_issue(nxt, other);
+                            } else {                                                 // last TMEM read of this accumulator by this warp
+                                tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cb * CB + pp * 32 + j);
+                                v[pp * 32 + j] = __uint_as_float(cur[j]) + b4.x; v[pp * 32 + j + 1] = __uint_as_float(cur[j + 1]) + b4.y;
+                                v[pp * 32 + j + 2] = __uint_as_float(cur[j + 2]) + b4.z; v[pp * 32 + j + 3] = __uint_as_float(cur[j + 3]) + b4.w;
+                            }
+                        };
+                        if (((bi * PPB + pp) & 1) == 0) step(ra, rb); else step(rb, ra);
                     }
+                    if (threadIdx.x == 64) WS_DBG(2, tcount, 2 + 5 * blkd);
                     if (e.relu == 1) {
 #pragma unroll
                         for (int j = 0; j < CB; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -800,6 +817,7 @@ gemm_ws_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                     if (threadIdx.x == 64) WS_DBG(2, tcount, 5 + 5 * blkd);
                     ++blkd;
+                    ++bcount;
                 }
             }
             if (!waited) {                                               // no block of this tile belongs to this warp

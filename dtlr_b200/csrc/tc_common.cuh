@@ -190,6 +190,22 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+// tcgen05.ld split in issue / wait: the load of the NEXT 32-column piece is in flight while the current one is processed (the
+// helper above waits at once; with 8 epilogue warps loading in lock-step the TMEM read port -- 64 B/clk per SM -- and the ALUs
+// otherwise take turns).  tcgen05.wait::ld covers every load this thread has issued.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SW128=2 [61,64))
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
