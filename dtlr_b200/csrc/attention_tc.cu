@@ -12,6 +12,8 @@
 //   epilogue O / rowsum -> bf16 -> global.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-17 softmax (four warps per TMEM lane quarter,
 // each owning 32 of the 128 key columns of a chunk).  All hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace dtlr {
@@ -291,20 +293,21 @@ mha_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int A2_KC = 64;                            // keys per chunk
 constexpr int A2_SLOTS = 4;                          // query tiles in flight
 constexpr int A2_SMEM_P = 16384;                     // P chunk of one tile: 128 rows x 128 B
-constexpr int A2_TM = 96;                            // TMEM columns per slot
-constexpr int A2_SMEM_TOTAL = AT_SMEM_K + AT_SMEM_V + A2_SLOTS * AT_SMEM_Q + A2_SLOTS * A2_SMEM_P + 1024 + 512;
+constexpr int A2_TM = 128;                           // TMEM columns per slot: S chunk (64 fp32) | P chunk (32 packed 16-bit pairs) | O (32 fp32)
+constexpr int A2_SMEM_TOTAL = AT_SMEM_K + AT_SMEM_V + A2_SLOTS * AT_SMEM_Q + 1024 + 512;     // (P lives in tensor memory)
 static_assert(A2_SMEM_TOTAL <= 232448, "attention kernel shared memory exceeds 227 KB");
 
 __global__ void __launch_bounds__(576, 1)
 mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-               op16_t* __restrict__ out, int ld_o, int Q, int H, int k_off, float scale_log2) {
+               op16_t* __restrict__ out, int ld_o, int Q, int H, int k_off, float scale_log2, unsigned int* dbgbuf_, const int dbg) {
     extern __shared__ unsigned char at_raw[];
+    unsigned int* const dbgbuf = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? dbgbuf_ : nullptr;
+#define A2_DBG(role, unit, slot) do { if (dbgbuf && (unit) < 16) dbgbuf[(((role) * 16 + (unit)) * 16 + (slot))] = (unsigned int)clock(); } while (0)
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)at_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sK = smem;
     unsigned char* sV = sK + AT_SMEM_K;
     unsigned char* sQ = sV + AT_SMEM_V;                      // [slots][128 rows x 64 B]
-    unsigned char* sP = sQ + A2_SLOTS * AT_SMEM_Q;           // [slots][128 rows][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + A2_SLOTS * A2_SMEM_P);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + A2_SLOTS * AT_SMEM_Q);
     uint64_t* kv_full = bars;                   // 1
     uint64_t* q_full = bars + 1;                // [slots]
     uint64_t* s_full = q_full + A2_SLOTS;       // commit: S chunk in TMEM
@@ -341,8 +344,13 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     pdl_launch_dependents();
     pdl_wait();
 
+    // The P chunk goes back into TENSOR memory (tcgen05.st over its own 32 columns, packed 16-bit pairs) and is the A operand of
+    // O += P V (tcgen05.mma [d], [a_tmem], b_desc) -- no shared-memory round trip, no proxy fence -- and the two MMA streams have
+    // their own issuers: warp 1 issues S = Q K^T, warp 0 (idle after its TMA loads) issues O += P V.  The timeline of the first
+    // version (tools/attn_timeline.py) showed ONE issuer warp pacing the kernel: 8 wait / issue / commit steps per 64-key round took
+    // ~3,600 clk against 2,048 clk of exponentials.
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer, then the P.V issuer =====
         if (elect_one()) {
             for (int sl = 0; sl < my_tiles; ++sl) {
                 mbar_expect_tx(&q_full[sl], AT_SMEM_Q);
@@ -354,75 +362,104 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < 16; ++j)
                 tma_load_2d(sV + j * 4096, &tmV, kv_full, j * 64, (b * H + h) * 32);
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        constexpr uint32_t IDESC_S = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        __syncwarp();
         constexpr uint32_t IDESC_O = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(kv_full, 0);
+        tcgen05_fence_after();
+        const uint32_t aV = smem_u32(sV);
+        // the four query tiles are independent pipelines: the issuer polls their barriers and serves whichever is ready, so a tile
+        // that is late does not hold the others back (in fixed order the tiles stayed in step and took turns at the MUFU unit:
+        // 2,800 clk per 64-key round against 2,048 clk of exponentials)
+        int nc[A2_SLOTS] = {0, 0, 0, 0};
+        for (int left = my_tiles * n_chunks; left > 0;) {
+            const int before = left;
+#pragma unroll
+            for (int sl = 0; sl < A2_SLOTS; ++sl) {          // O_sl += P_sl(c) V_c
+                const int c = nc[sl];
+                if (sl >= my_tiles || c >= n_chunks || !mbar_test(&p_full[sl], c & 1)) continue;
+                ++nc[sl];
+                --left;
+                tcgen05_fence_after();
+                A2_DBG(1, c + 1, sl * 2);
+                if (elect_one()) {
+                    const uint64_t dv = make_sw128_kmajor_desc(aV + c * 4096);
+                    const uint32_t tP = tmem_base + sl * A2_TM + A2_KC, tO = tP + 32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ts(tO, tP + k * 8, dv + (uint64_t)(2 * k), IDESC_O, (c == 0 && k == 0) ? 0u : 1u);
+                    umma_commit(&p_empty[sl]);
+                    if (c == n_chunks - 1) umma_commit(&o_full[sl]);
+                }
+                __syncwarp();
+                A2_DBG(1, c + 1, sl * 2 + 1);
+            }
+            if (left == before) __nanosleep(40);             // nothing was ready: leave the issue slots to the softmax warps
+        }
+    } else if (warp == 1) {
+        // ===== S = Q K^T issuer =====
+        constexpr uint32_t IDESC_S = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(kv_full, 0);
         for (int sl = 0; sl < my_tiles; ++sl) mbar_wait(&q_full[sl], 0);
         tcgen05_fence_after();
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-        for (int c = 0; c <= n_chunks; ++c) {
-            if (c < n_chunks) {
-                for (int sl = 0; sl < my_tiles; ++sl) {      // S_sl(c) = Q_sl K_c^T
-                    mbar_wait(&s_empty[sl], (c & 1) ^ 1);
-                    tcgen05_fence_after();
-                    if (elect_one()) {
-                        const uint64_t dq = make_sw64_kmajor_desc(aQ + sl * AT_SMEM_Q);
-                        const uint64_t dk = make_sw64_kmajor_desc(aK + c * A2_KC * 64);
-                        umma_bf16(tmem_base + sl * A2_TM, dq, dk, IDESC_S, 0);
-                        umma_bf16(tmem_base + sl * A2_TM, dq + 2, dk + 2, IDESC_S, 1);
-                        umma_commit(&s_full[sl]);
-                    }
-                    __syncwarp();
-                }
-            }
-            if (c >= 1) {
-                for (int sl = 0; sl < my_tiles; ++sl) {      // O_sl += P_sl(c-1) V_{c-1}
-                    mbar_wait(&p_full[sl], (c - 1) & 1);
-                    tcgen05_fence_after();
-                    if (elect_one()) {
-                        const uint64_t dp = make_sw128_kmajor_desc(aP + sl * A2_SMEM_P);
-                        const uint64_t dv = make_sw128_kmajor_desc(aV + (c - 1) * 4096);
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+        int nc[A2_SLOTS] = {0, 0, 0, 0};
+        for (int left = my_tiles * n_chunks; left > 0;) {
+            const int before = left;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_base + sl * A2_TM + A2_KC, dp + (uint64_t)(2 * k), dv + (uint64_t)(2 * k), IDESC_O,
-                                      (c == 1 && k == 0) ? 0u : 1u);
-                        umma_commit(&p_empty[sl]);
-                        if (c == n_chunks) umma_commit(&o_full[sl]);
-                    }
-                    __syncwarp();
+            for (int sl = 0; sl < A2_SLOTS; ++sl) {          // S_sl(c) = Q_sl K_c^T
+                const int c = nc[sl];
+                if (sl >= my_tiles || c >= n_chunks || !mbar_test(&s_empty[sl], (c & 1) ^ 1)) continue;
+                ++nc[sl];
+                --left;
+                tcgen05_fence_after();
+                A2_DBG(0, c, sl * 2);
+                if (elect_one()) {
+                    const uint64_t dq = make_sw64_kmajor_desc(aQ + sl * AT_SMEM_Q);
+                    const uint64_t dk = make_sw64_kmajor_desc(aK + c * A2_KC * 64);
+                    umma_bf16(tmem_base + sl * A2_TM, dq, dk, IDESC_S, 0);
+                    umma_bf16(tmem_base + sl * A2_TM, dq + 2, dk + 2, IDESC_S, 1);
+                    umma_commit(&s_full[sl]);
                 }
+                __syncwarp();
+                A2_DBG(0, c, sl * 2 + 1);
             }
+            if (left == before) __nanosleep(40);
         }
     } else {
         // ===== softmax warps: slot sl, TMEM lane quarter qd, thread = query row =====
         const int sl = (warp - 2) >> 2;
         const int qd = warp & 3;
         const int row = qd * 32 + lane;
-        const uint32_t tS = tmem_base + sl * A2_TM + ((uint32_t)(qd * 32) << 16), tO = tS + A2_KC;
-        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t tS = tmem_base + sl * A2_TM + ((uint32_t)(qd * 32) << 16), tP = tS + A2_KC, tO = tP + 32;
         if (sl < my_tiles) {
             const int q = (tile0 + sl) * AT_QT + row;
             float m = -INFINITY, l = 0.f;
-            unsigned char* prow = sP + sl * A2_SMEM_P + row * 128;
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&s_full[sl], c & 1);
-                tcgen05_fence_after();
+            const int drole = (warp == 2) ? 2 : ((warp == 14) ? 3 : -1);
+#define A2_DBGW(unit, slot) do { if (drole >= 0 && lane == 0) A2_DBG(drole, unit, slot); } while (0)
+            // Q = 900 is 7 tiles of 128 queries + 4: three of the last tile's four warps own no query at all.  They keep the barrier
+            // protocol going and skip every TMEM access and every exponential (the kernel is bound by the MUFU unit: 3 of a pair of
+            // CTAs' 32 softmax warps = 9 % of the work); their P / O rows hold garbage that only their own (never stored) rows see
+            const bool live = (tile0 + sl) * AT_QT + qd * 32 < Q;
+            if (sl > 0 && !(dbg & 1024)) __nanosleep(sl * 260);         // start the tiles a quarter round apart (A/B: flag 1024)
+            // one chunk of the online softmax over the first NK key columns of the chunk (NK = 64, or 16 for a short last chunk:
+            // Q = 900 leaves 4 keys in chunk 14); the remaining P columns are zero
+            auto chunk_body = [&](auto nk_tag, const int c) {
+                constexpr int NK = decltype(nk_tag)::value;
                 uint32_t a[64];
                 tmem_ld64(tS, a);
+                A2_DBGW(c, 2);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[sl]);                // the S buffer may be overwritten by the next chunk
                 const int key0 = c * A2_KC;
-                if (key0 + A2_KC > Q) {                                   // boundary chunk: keys beyond Q do not exist
+                if (key0 + NK > Q) {                                      // boundary chunk: keys beyond Q do not exist
 #pragma unroll
-                    for (int j = 0; j < 64; ++j)
+                    for (int j = 0; j < NK; ++j)
                         if (key0 + j >= Q) a[j] = 0xff800000u;
                 }
                 float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
+                for (int j = 0; j < NK; j += 4) {
                     c0 = fmaxf(c0, __uint_as_float(a[j])); c1 = fmaxf(c1, __uint_as_float(a[j + 1]));
                     c2 = fmaxf(c2, __uint_as_float(a[j + 2])); c3 = fmaxf(c3, __uint_as_float(a[j + 3]));
                 }
@@ -431,7 +468,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const float mxs = m_new * scale_log2;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {                             // P overwrites S in place: word j/2 = keys j, j+1
+                for (int j = 0; j < NK; j += 4) {                             // P overwrites S in place: word j/2 = keys j, j+1
                     const float p0 = ex2_approx(fmaf(__uint_as_float(a[j]), scale_log2, -mxs)), p1 = ex2_approx(fmaf(__uint_as_float(a[j + 1]), scale_log2, -mxs));
                     const float p2 = ex2_approx(fmaf(__uint_as_float(a[j + 2]), scale_log2, -mxs)), p3 = ex2_approx(fmaf(__uint_as_float(a[j + 3]), scale_log2, -mxs));
                     s0 += p0; s1 += p1; s2 += p2; s3 += p3;
@@ -444,11 +481,15 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     a[j / 2 + 1] = __byte_perm(__float_as_uint(p2) + 0x8000u, __float_as_uint(p3) + 0x8000u, 0x7632);
 #endif
                 }
+#pragma unroll
+                for (int j = NK / 2; j < 32; ++j) a[j] = 0u;
                 l = l * alpha + ((s0 + s1) + (s2 + s3));
                 m = m_new;
+                A2_DBGW(c, 3);
                 // the previous P.V has completed: P buffer free, O may be rescaled
                 mbar_wait(&p_empty[sl], (c & 1) ^ 1);
                 tcgen05_fence_after();
+                A2_DBGW(c, 4);
                 if (c > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
                     uint32_t o[32];
                     tmem_ld32(tO, o);
@@ -456,13 +497,29 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
                     tmem_st32(tO, o);
                 }
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                    *reinterpret_cast<uint4*>(prow + ((ch ^ swz) * 16)) = make_uint4(a[ch * 4], a[ch * 4 + 1], a[ch * 4 + 2], a[ch * 4 + 3]);
+                A2_DBGW(c, 5);
+                tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(a));      // P chunk: packed pairs, column j = keys 2j, 2j + 1
+            };
+            for (int c = 0; c < n_chunks; ++c) {
+                A2_DBGW(c, 0);
+                mbar_wait(&s_full[sl], c & 1);
+                tcgen05_fence_after();
+                A2_DBGW(c, 1);
+                if (live) {
+                    if (Q - c * A2_KC <= 16) chunk_body(std::integral_constant<int, 16>{}, c);
+                    else chunk_body(std::integral_constant<int, 64>{}, c);
+                } else {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[sl]);
+                    mbar_wait(&p_empty[sl], (c & 1) ^ 1);
+                    tcgen05_fence_after();
+                }
                 tcgen05_fence_before();
-                fence_proxy_async();
                 __syncwarp();
+                A2_DBGW(c, 6);
                 if (lane == 0) mbar_arrive(&p_full[sl]);
+                A2_DBGW(c, 7);
             }
             // ---- epilogue: O / l -> bf16 -> global (64 bytes per row)
             mbar_wait(&o_full[sl], 0);
@@ -496,6 +553,10 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }  // namespace dtlr
 
 using namespace dtlr;
+
+// timeline probe of mha_tc2_kernel (tools/attn_timeline.py): a device buffer of 4 * 16 * 16 u32, or NULL (off)
+static unsigned int* g_attn_dbgbuf = nullptr;
+extern "C" int dtlr_attn_debug_buffer(void* buf) { g_attn_dbgbuf = reinterpret_cast<unsigned int*>(buf); return DTLR_OK; }
 
 // returns DTLR_ERR_UNSUPPORTED when the shape does not fit this kernel (the caller then uses the mma.sync flash kernel)
 extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void* v, int ld_v, void* vt_scratch, void* out, int ld_o,
@@ -531,7 +592,7 @@ extern "C" int dtlr_mha_tcgen05(const void* qk, int ld_qk, int k_off, const void
             configured2 = true;
         }
         grid.x = (n_qtiles + A2_SLOTS - 1) / A2_SLOTS;
-        DTLR_CHECK_CUDA(launch_pdl(mha_tc2_kernel, grid, dim3(576), A2_SMEM_TOTAL, st, tmQ, tmK, tmV, (op16_t*)out, ld_o, Q, heads, k_off, scale_log2));
+        DTLR_CHECK_CUDA(launch_pdl(mha_tc2_kernel, grid, dim3(576), A2_SMEM_TOTAL, st, tmQ, tmK, tmV, (op16_t*)out, ld_o, Q, heads, k_off, scale_log2, g_attn_dbgbuf, g_debug_flags));
         return DTLR_OK;
     }
     mha_tcgen05_kernel<<<grid, 576, AT_SMEM_TOTAL, st>>>(tmQ, tmK, tmV, (op16_t*)out, ld_o, Q, heads, k_off, scale_log2);

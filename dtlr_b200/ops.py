@@ -208,9 +208,11 @@ def cast(x, dtype):
     return out
 
 
-# "hmma": mma.sync flash kernel (default: 287 us/layer at B=64); "tc": the tcgen05/TMEM kernel (correct, 519 us/layer in its
-# first version -- both are bound by the softmax ALU work, ~8.5 instructions per query-key pair, not by the tensor pipe)
-ATTN_IMPL = _os.environ.get("DTLR_ATTN", "hmma")
+# decoder self-attention without a mask (inference): "tc" (default) = the single-pass tcgen05 / TMEM kernel (226 us per layer at
+# B = 64, Q = 900: P in tensor memory, S and P.V issued by two warps that poll the four query-tile pipelines); "hmma" = the mma.sync
+# flash kernel (232 us; also the path for masks, other head sizes and Q > 1024).  Both are bound by the exponentials (MUFU) and the
+# softmax ALU work, not by the tensor pipe -- DESIGN.md 3.3
+ATTN_IMPL = _os.environ.get("DTLR_ATTN", "tc")
 
 
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
