@@ -552,7 +552,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (independent shards, no collective)" % world,
                        "weights": "random (dtlr_b200.synth, seed 0)",
-                       "precision": {"f16": "fp16 operands + activations (kind::f16 tcgen05 / HMMA at the bf16 rate), fp32 accumulation; measured vs the fp32 oracle at this shape: see tests/test_gpu_engine.py::test_bench_shape_throughput_mode_vs_oracle and DESIGN.md 2.1",
+                       "precision": {"f16": "fp16 operands + activations (kind::f16 tcgen05 at the bf16 rate: GEMMs, convs, FFN block, decoder self-attention; mma.sync in the MSDA gather), fp32 accumulation; measured vs the fp32 oracle at this shape: see tests/test_gpu_engine.py::test_bench_shape_throughput_mode_vs_oracle and DESIGN.md 2.1",
                                      "bf16": "bf16 operands + activations, fp32 accumulation", "f32": "fp32 SIMT parity mode"}[args.dtype], "outputs": "all reference dict keys (6 decoder layers + interm)",
                        "l2": "no explicit flush: one step streams >1 GB of activations (126 MB L2)",
                        "launch": "one CUDA-graph replay per step" if model.use_cuda_graph else "eager launches"},
