@@ -327,7 +327,9 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* p_full = s_empty + A2_SLOTS;      // 4 arrivals: P chunk in shared memory (and O rescaled)
     uint64_t* p_empty = p_full + A2_SLOTS;      // commit: P.V of the chunk complete
     uint64_t* o_full = p_empty + A2_SLOTS;      // commit: all P.V of the tile complete
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + A2_SLOTS);
+    uint64_t* k_full = o_full + A2_SLOTS;       // [4] one per 256-key box of K: S = Q K^T starts when the FIRST box has landed,
+    uint64_t* v_full = k_full + 4;              // [4] P.V when the first four V^T k-blocks have (not after all 128 KB of the head)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(v_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, h = blockIdx.y;
@@ -340,6 +342,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         mbar_init(kv_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
         for (int i = 0; i < A2_SLOTS; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
@@ -368,16 +371,17 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_expect_tx(&q_full[sl], AT_SMEM_Q);
                 tma_load_2d(sQ + sl * AT_SMEM_Q, &tmQ, &q_full[sl], h * 32, row_base + (tile0 + sl) * AT_QT);
             }
-            mbar_expect_tx(kv_full, AT_SMEM_K + AT_SMEM_V);
-            for (int j = 0; j < 4; ++j)
-                tma_load_2d(sK + j * 256 * 64, &tmK, kv_full, k_off + h * 32, row_base + j * 256);
-            for (int j = 0; j < 16; ++j)
-                tma_load_2d(sV + j * 4096, &tmV, kv_full, j * 64, (b * H + h) * 32);
+            for (int j = 0; j < 4; ++j) {                    // 256 keys at a time, in the order the chunks are consumed
+                mbar_expect_tx(&k_full[j], AT_SMEM_K / 4);
+                tma_load_2d(sK + j * 256 * 64, &tmK, &k_full[j], k_off + h * 32, row_base + j * 256);
+                mbar_expect_tx(&v_full[j], AT_SMEM_V / 4);
+                for (int i = 0; i < 4; ++i)
+                    tma_load_2d(sV + (4 * j + i) * 4096, &tmV, &v_full[j], (4 * j + i) * 64, (b * H + h) * 32);
+            }
         }
         __syncwarp();
         constexpr uint32_t IDESC_O = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        mbar_wait(kv_full, 0);
-        tcgen05_fence_after();
+        int v_ready = 0;
         const uint32_t aV = smem_u32(sV);
         // the four query tiles are independent pipelines: the issuer polls their barriers and serves whichever is ready, so a tile
         // that is late does not hold the others back (in fixed order the tiles stayed in step and took turns at the MUFU unit:
@@ -391,6 +395,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (sl >= my_tiles || c >= n_chunks || !mbar_test(&p_full[sl], c & 1)) continue;
                 ++nc[sl];
                 --left;
+                while (v_ready <= (c >> 2)) mbar_wait(&v_full[v_ready++], 0);
                 tcgen05_fence_after();
                 A2_DBG(1, c + 1, sl * 2);
                 if (elect_one()) {
@@ -410,11 +415,11 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else if (warp == 1) {
         // ===== S = Q K^T issuer =====
         constexpr uint32_t IDESC_S = (1u << 4) | OP16_IDESC_AB | ((uint32_t)(A2_KC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        mbar_wait(kv_full, 0);
         for (int sl = 0; sl < my_tiles; ++sl) mbar_wait(&q_full[sl], 0);
         tcgen05_fence_after();
         const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
         int nc[A2_SLOTS] = {0, 0, 0, 0};
+        int k_ready = 0;
         for (int left = my_tiles * n_chunks; left > 0;) {
             const int before = left;
 #pragma unroll
@@ -423,6 +428,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (sl >= my_tiles || c >= n_chunks || !mbar_test(&s_empty[sl], (c & 1) ^ 1)) continue;
                 ++nc[sl];
                 --left;
+                while (k_ready <= (c >> 2)) mbar_wait(&k_full[k_ready++], 0);
                 tcgen05_fence_after();
                 A2_DBG(0, c, sl * 2);
                 if (elect_one()) {
@@ -452,7 +458,6 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // protocol going and skip every TMEM access and every exponential (the kernel is bound by the MUFU unit: 3 of a pair of
             // CTAs' 32 softmax warps = 9 % of the work); their P / O rows hold garbage that only their own (never stored) rows see
             const bool live = (tile0 + sl) * AT_QT + qd * 32 < Q;
-            if (sl > 0 && !(dbg & 1024)) __nanosleep(sl * 260);         // start the tiles a quarter round apart (A/B: flag 1024)
             // one chunk of the online softmax over the first NK key columns of the chunk (NK = 64, or 16 for a short last chunk:
             // Q = 900 leaves 4 keys in chunk 14); the remaining P columns are zero
             auto chunk_body = [&](auto nk_tag, const int c) {

@@ -208,7 +208,7 @@ def cast(x, dtype):
     return out
 
 
-# decoder self-attention without a mask (inference): "tc" (default) = the single-pass tcgen05 / TMEM kernel (226 us per layer at
+# decoder self-attention without a mask (inference): "tc" (default) = the single-pass tcgen05 / TMEM kernel (206 us per layer at
 # B = 64, Q = 900: P in tensor memory, S and P.V issued by two warps that poll the four query-tile pipelines); "hmma" = the mma.sync
 # flash kernel (232 us; also the path for masks, other head sizes and Q > 1024).  Both are bound by the exponentials (MUFU) and the
 # softmax ALU work, not by the tensor pipe -- DESIGN.md 3.3

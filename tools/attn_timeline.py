@@ -19,7 +19,7 @@ qk = torch.randn(B * Q, 2 * d, device="cuda").to(dt)
 v = torch.randn(B * Q, d, device="cuda").to(dt)
 _lib.set_flavor(dt)
 lib = _lib.lib()
-for impl, flags, name in (("flash", 0, "mma.sync flash"), ("tc", 0, "tcgen05 single-pass"), ("tc", 1024, "tcgen05 single-pass, tiles started in step (flag 1024)")):
+for impl, flags, name in (("flash", 0, "mma.sync flash"), ("tc", 0, "tcgen05 single-pass")):
     ops.ATTN_IMPL = impl
     lib.dtlr_debug_flags(flags)
     us = timeit(lambda i: ops.mha_self_attention(qk, d, v, None, B, Q, heads, 32), iters=10)
