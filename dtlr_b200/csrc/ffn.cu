@@ -1070,7 +1070,7 @@ static int ffn_plan(int M, int hidden) {
         ffn_split_plan(M, hidden, &main_rows, &rem, &ns);
         return rem ? 1 : 0;
     }
-    if (sm * 4 > FF_SK_FLAG_BYTES) return 0;
+    if (sm * 4 > FF_SK_FLAG_BYTES || hidden < 2 * FF_HC) return 0;          // (one hidden chunk per tile: nothing to stream)
     // stream-K on CTA pairs (cta_group::2, 256-row pair tiles): the default from one pair tile per pair upwards (measured at
     // M = 58368: 92 us against 108-118 us for the single-CTA stream-K kernel); flag 1073741824: single-CTA kernels only (A/B)
     if (!(g_debug_flags & 1073741824) && (sm % 2) == 0 && (num_m + 1) / 2 >= sm / 2) return 3;

@@ -21,11 +21,12 @@ def ref_attention(qk, v, B, Q, heads, mask=None):
     return (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(B * Q, d)
 
 
-@pytest.mark.parametrize("Q", [900, 986, 100, 17, 1024])
+@pytest.mark.parametrize("Q", [900, 986, 100, 17, 1024, 912, 130, 65, 8, 513])
 @pytest.mark.parametrize("two_pass", [False, True])
 def test_self_attention_tcgen05_kernel(Q, two_pass, monkeypatch):
-    """the tcgen05 / TMEM / TMA attention kernels (opt-in, DTLR_ATTN=tc) against torch fp32 on the same bf16 operands: the
-    single-pass kernel (4 tiles in flight, online softmax with TMEM rescale) and the two-pass kernel (dtlr_debug_flags(256))"""
+    """the tcgen05 / TMEM / TMA attention kernels (the default without a mask; DTLR_ATTN) against torch fp32 on the same bf16
+    operands: the single-pass kernel (4 tiles in flight, P in tensor memory, online softmax with TMEM rescale; Q covers query tiles
+    with dead warps, 16-key / 1-key / full last chunks, one to eight tiles) and the two-pass kernel (dtlr_debug_flags(256))"""
     from dtlr_b200 import ops, _lib
     monkeypatch.setattr(ops, "ATTN_IMPL", "tc")
     _lib.lib().dtlr_debug_flags(256 if two_pass else 0)
