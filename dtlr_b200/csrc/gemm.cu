@@ -1151,7 +1151,8 @@ extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const floa
     DTLR_CHECK_ARG(seg_w >= 8 && (128 % seg_w) == 0 && (W % seg_w) == 0,
                    "conv2d_nhwc: output width %d cannot be tiled into 128-pixel row segments (use im2col + gemm)", W);
     DTLR_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv2d_nhwc: operands must be 16-byte aligned");
-    DTLR_CHECK_ARG(out_dtype == DTLR_OP16, "conv2d_nhwc: bf16 output only");
+    DTLR_CHECK_ARG(out_dtype == DTLR_OP16 || out_dtype == DTLR_F32, "conv2d_nhwc: output must be 16-bit or f32");
+    const bool f32out = out_dtype == DTLR_F32;     // split-precision mode (3C channels = [hi | hi | lo], fp32 result); residual fp32 too
     const int M = B * H * W, K = KH * KW * C;
     if (M == 0) return DTLR_OK;
     GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w, stride}, g_debug_flags};
@@ -1164,7 +1165,7 @@ extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const floa
     // cuts that cost by >= 1.5x (layer4: 256 -> 128 halves it; layer3, 96 CTAs, stays at 256)
     const long long row_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     auto tile_cost = [&](int bn) { const long long ctas = row_tiles * ((Cout + bn - 1) / bn); return ((ctas + sm_count() - 1) / sm_count()) * bn; };
-    const bool ok256 = (Cout % 256) == 0, ok128 = Cout > 64;
+    const bool ok256 = (Cout % 256) == 0 && !f32out, ok128 = Cout > 64;     // (fp32 tiles: 128 / 64 columns, like dtlr_gemm)
     int bn_pick = ok256 ? 256 : (ok128 ? 128 : 64);
     if (!(g_debug_flags & 1048576)) {       // flag 1048576: round-1 rule (widest tile that divides Cout), A/B
         if (bn_pick == 256 && (Cout % 128) == 0 && tile_cost(128) * 3 <= tile_cost(256) * 2) bn_pick = 128;
@@ -1176,8 +1177,8 @@ extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const floa
     }
     if (bn_pick == 128) {
         if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 128))) return rc;
-        return launch_tc<128, 4, op16_t>(ta, tb, e, st);
+        return f32out ? launch_tc<128, 4, float>(ta, tb, e, st) : launch_tc<128, 4, op16_t>(ta, tb, e, st);
     }
     if ((rc = make_tmap_bf16(&tb, w, Cout, K, K, 64))) return rc;
-    return launch_tc<64, 6, op16_t>(ta, tb, e, st);
+    return f32out ? launch_tc<64, 6, float>(ta, tb, e, st) : launch_tc<64, 6, op16_t>(ta, tb, e, st);
 }

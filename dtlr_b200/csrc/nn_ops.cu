@@ -676,6 +676,38 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long
         stf<TO>(out + i, ldf<TI>(x + i));
 }
 
+// ---------------------------------------------------------------------------------------------- split-precision operand
+// fp32 activations [M, K] (row pitch ldx) -> 16-bit [M, 3K]: [hi | hi | lo] with hi = rn16(x), lo = rn16(x - hi).  Against a weight
+// matrix packed as [hi | lo | hi] (engine.py:_split_w) the ordinary 16-bit tcgen05 GEMM over K' = 3K accumulates
+// hi.hi + hi.lo + lo.hi in fp32 -- the 3-term split product (2 x 11 significand bits with fp16 operands; the dropped lo.lo term is
+// 2^-22 relative): the tensor-core form of the fp32 parity mode.  One thread = 8 consecutive elements of a row:
+// two 16-byte loads, three 16-byte stores.
+__global__ void __launch_bounds__(256)
+split_cast_kernel(const float* __restrict__ x, long long ldx, op16_t* __restrict__ out, long long M, int K) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int k8 = K >> 3;
+    const long long n = M * k8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / k8;
+        const int k = (int)(i - row * k8) << 3;
+        const float4 a = *reinterpret_cast<const float4*>(x + row * ldx + k);
+        const float4 b = *reinterpret_cast<const float4*>(x + row * ldx + k + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __align__(16) op16_t hi[8];
+        __align__(16) op16_t lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hi[j] = f32_to_op16(v[j]);
+            lo[j] = f32_to_op16(v[j] - op16_to_f32(hi[j]));
+        }
+        op16_t* o = out + row * (3ll * K) + k;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(o + K) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(o + 2ll * K) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- ResNet stem, direct
 // conv1 7x7 / stride 2 / pad 3, 3 -> 64 channels, + folded FrozenBatchNorm + ReLU (torchvision resnet50 stem as wrapped by
 // reference models/dino/backbone.py:109-128), straight from the fp32 NCHW network input to NHWC activations.  K = 147 is
@@ -1014,6 +1046,16 @@ extern "C" int dtlr_box_refine(const float* delta, int ldd, const float* ref, fl
 extern "C" int dtlr_sigmoid(const float* x, float* out, long long n, void* stream) {
     if (n == 0) return DTLR_OK;
     DTLR_LAUNCH((sigmoid_kernel), (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, x, out, n);
+    DTLR_CHECK_LAUNCH();
+    return DTLR_OK;
+}
+
+extern "C" int dtlr_split_cast(const float* x, long long ldx, void* out, long long M, int K, void* stream) {
+    DTLR_CHECK_ARG(M >= 0 && K > 0 && (K % 8) == 0 && ldx >= K && (ldx % 4) == 0, "split_cast: K must be a multiple of 8 and the row pitch of 4 (K=%d)", K);
+    if (M == 0) return DTLR_OK;
+    DTLR_CHECK_ARG(x && out && ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0, "split_cast: operands must be 16-byte aligned");
+    const long long n = M * (K / 8);
+    DTLR_LAUNCH((split_cast_kernel), grid_for(n, 256), 256, 0, (cudaStream_t)stream, x, ldx, (op16_t*)out, M, K);
     DTLR_CHECK_LAUNCH();
     return DTLR_OK;
 }

@@ -184,6 +184,10 @@ class DINO(nn.Module):
 
         # ---- dtlr_b200 execution controls (not part of the reference surface)
         self.compute_dtype = torch.float32      # torch.float32 = parity mode; torch.float16 / torch.bfloat16 = throughput mode (16-bit tensor-core operands)
+        # with compute_dtype = float32: run every Linear / conv as a 3-term split-precision product on the tensor cores (fp32 activations,
+        # 16-bit hi + lo operands: engine.SplitDtype) instead of the exact SIMT GEMM -- the tensor-core form of the parity mode
+        self.split_precision = False
+        self.split_half = torch.float16
         self.use_engine = True                  # eval + no_grad -> fused inference engine
         self.engine_outputs = "all"             # "all": every reference dict key; "final": last-layer logits/boxes only
         self.use_cuda_graph = False             # replay one captured CUDA graph per input shape (static output buffers)

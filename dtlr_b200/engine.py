@@ -17,20 +17,55 @@ from . import msda as msda_mod
 from . import ops
 
 
-def _fold_conv_bn(conv, bn, dtype, pad_k_to=8):
+class SplitDtype:
+    """weight-packing dtype of the split-precision mode (`model.split_precision` with compute_dtype = float32): activations stay fp32,
+    every weight matrix is stored as 16-bit [hi | lo | hi] (3K columns), and ops.gemm multiplies it with the [hi | hi | lo] split of the
+    fp32 activations on the tcgen05 GEMM -- 3 tensor-core products per fp32 product, 2 x 11 significand bits with fp16."""
+
+    def __init__(self, half):
+        self.half = half
+
+    def __eq__(self, o):
+        return isinstance(o, SplitDtype) and o.half == self.half
+
+    def __hash__(self):
+        return hash(("split", self.half))
+
+    def __repr__(self):
+        return "split(%s)" % self.half
+
+
+def _split_w(w, half, taps=1):
+    """fp32 (N, taps*C) -> 16-bit (N, taps*3C): per tap [hi(C) | lo(C) | hi(C)], hi = rn16(w), lo = rn16(w - hi).  taps = 1 for every
+    weight that meets ops.split_cast's [hi | hi | lo] of a whole activation row; taps = kh*kw for the implicit-GEMM 3x3 convs, whose
+    NHWC input carries the split per pixel (3C channels)."""
+    w = w.float()
+    N, K = w.shape
+    hi = w.to(half)
+    lo = (w - hi.float()).to(half)
+    hi3, lo3 = hi.view(N, taps, K // taps), lo.view(N, taps, K // taps)
+    return torch.cat([hi3, lo3, hi3], 2).reshape(N, 3 * K).contiguous()
+
+
+def _cvt(w, dtype, taps=1):
+    return _split_w(w, dtype.half, taps) if isinstance(dtype, SplitDtype) else w.to(dtype).contiguous()
+
+
+def _fold_conv_bn(conv, bn, dtype, pad_k_to=8, per_tap=False):
     """FrozenBatchNorm (reference backbone.py:62-72) folded into the conv: w' = w*scale, b' = bias - mean*scale;
     weight reordered to [Cout, kh, kw, Cin] (im2col K order)."""
     w = conv.weight.detach().float()
+    taps = w.shape[2] * w.shape[3] if per_tap else 1
     scale, bias = bn.scale_bias()
     w = (w * scale.float().view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
     K = w.shape[1]
     if K % pad_k_to:
         w = F.pad(w, (0, pad_k_to - K % pad_k_to))
-    return w.to(dtype).contiguous(), bias.detach().float().contiguous()
+    return _cvt(w, dtype, taps), bias.detach().float().contiguous()
 
 
 def _lin(linear, dtype):
-    return linear.weight.detach().to(dtype).contiguous(), linear.bias.detach().float().contiguous()
+    return _cvt(linear.weight.detach(), dtype), linear.bias.detach().float().contiguous()
 
 
 class InferenceEngine:
@@ -52,6 +87,12 @@ class InferenceEngine:
         for t in self.model.buffers():
             sig.append((id(t), t.data_ptr(), t._version))
         return (dtype, str(device), hash(tuple(sig)))
+
+    def _weight_dtype(self):
+        m = self.model
+        if m.compute_dtype == torch.float32 and getattr(m, "split_precision", False):
+            return SplitDtype(getattr(m, "split_half", torch.float16))
+        return m.compute_dtype
 
     def invalidate(self):
         """drop the packed weights and every captured CUDA graph (they hold copies of the weights)"""
@@ -75,10 +116,12 @@ class InferenceEngine:
                             sb.detach().float().contiguous())          # [kh][kw][cin][cout] fp32, bias
         # bf16 throughput mode: the stem runs on the tensor cores as patches (shared-memory staged im2col) x [64, 152] GEMM
         P["stem_gemm"] = _fold_conv_bn(body.conv1, body.bn1, dtype) if dtype in ops.HALF else None
+        split = isinstance(dtype, SplitDtype)
+        act_dtype = torch.float32 if split else dtype              # dtype of the activations / embedding tables
         blocks = []
         for li in range(1, 5):
             for blk in getattr(body, "layer%d" % li):
-                d = {"c1": _fold_conv_bn(blk.conv1, blk.bn1, dtype), "c2": _fold_conv_bn(blk.conv2, blk.bn2, dtype),
+                d = {"c1": _fold_conv_bn(blk.conv1, blk.bn1, dtype), "c2": _fold_conv_bn(blk.conv2, blk.bn2, dtype, per_tap=True),
                      "c3": _fold_conv_bn(blk.conv3, blk.bn3, dtype), "stride": blk.stride, "ds": None, "layer": li}
                 if blk.downsample is not None:
                     d["ds"] = _fold_conv_bn(blk.downsample[0], blk.downsample[1], dtype)
@@ -89,14 +132,14 @@ class InferenceEngine:
         for seq in m.input_proj:
             conv, gn = seq[0], seq[1]
             w = conv.weight.detach().float().permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1)
-            proj.append({"w": w.to(dtype).contiguous(), "b": conv.bias.detach().float().contiguous(),
+            proj.append({"w": _cvt(w, dtype), "b": conv.bias.detach().float().contiguous(),
                          "gw": gn.weight.detach().float().contiguous(), "gb": gn.bias.detach().float().contiguous(),
                          "k": conv.kernel_size[0], "stride": conv.stride[0], "pad": conv.padding[0], "groups": gn.num_groups})
         P["proj"] = proj
         P["level_embed"] = tr.level_embed.detach().float().contiguous()
 
         def pack_msda(a):
-            w_oa = torch.cat([a.sampling_offsets.weight, a.attention_weights.weight], 0).detach().to(dtype).contiguous()
+            w_oa = _cvt(torch.cat([a.sampling_offsets.weight, a.attention_weights.weight], 0).detach(), dtype)
             b_oa = torch.cat([a.sampling_offsets.bias, a.attention_weights.bias], 0).detach().float().contiguous()
             return {"val": _lin(a.value_proj, dtype), "oa": (w_oa, b_oa), "out": _lin(a.output_proj, dtype),
                     "M": a.n_heads, "L": a.n_levels, "P": a.n_points}
@@ -116,12 +159,12 @@ class InferenceEngine:
             sa = l.self_attn
             wi, bi = sa.in_proj_weight.detach(), sa.in_proj_bias.detach()
             dec.append({"ca": pack_msda(l.cross_attn), "ln1": ln(l.norm1),
-                        "qk": (wi[:2 * C].to(dtype).contiguous(), bi[:2 * C].float().contiguous()),
-                        "v": (wi[2 * C:].to(dtype).contiguous(), bi[2 * C:].float().contiguous()),
+                        "qk": (_cvt(wi[:2 * C], dtype), bi[:2 * C].float().contiguous()),
+                        "v": (_cvt(wi[2 * C:], dtype), bi[2 * C:].float().contiguous()),
                         "o": _lin(sa.out_proj, dtype), "heads": sa.num_heads, "ln2": ln(l.norm2),
                         "l1": _lin(l.linear1, dtype), "l2": _lin(l.linear2, dtype), "ln3": ln(l.norm3)})
         P["dec"] = dec
-        P["dec_val_all"] = (torch.cat([l.cross_attn.value_proj.weight.detach() for l in tr.decoder.layers], 0).to(dtype).contiguous(),
+        P["dec_val_all"] = (_cvt(torch.cat([l.cross_attn.value_proj.weight.detach() for l in tr.decoder.layers], 0), dtype),
                             torch.cat([l.cross_attn.value_proj.bias.detach() for l in tr.decoder.layers], 0).float().contiguous())
         P["dec_norm"] = ln(tr.decoder.norm)
         P["rph"] = [_lin(l, dtype) for l in tr.decoder.ref_point_head.layers]
@@ -130,7 +173,7 @@ class InferenceEngine:
         P["bbox_w3"] = [be.layers[-1].weight.detach().float().contiguous() for be in m.bbox_embed]
         P["enc_bbox_w3"] = tr.enc_out_bbox_embed.layers[-1].weight.detach().float().contiguous()
         P["cls"] = [_lin(ce, dtype) for ce in m.class_embed]
-        P["tgt_embed"] = tr.tgt_embed.weight.detach().to(dtype).contiguous()
+        P["tgt_embed"] = tr.tgt_embed.weight.detach().to(act_dtype).contiguous()
         self._packed, self._key = P, key
         return P
 
@@ -173,7 +216,16 @@ class InferenceEngine:
             s = blk["stride"]
             a = ops.gemm(y, *blk["c1"], relu=1)
             planes = blk["c1"][0].shape[0]
-            if ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
+            if blk["c2"][0].dtype != a.dtype:
+                # split-precision mode: the fp32 NHWC map becomes 16-bit with 3 x planes channels per pixel ([hi | hi | lo]); the 3x3 conv
+                # runs on it as the same implicit GEMM (weights [hi | lo | hi] per tap) with an fp32 result
+                a3 = ops.split_cast(a, blk["c2"][0].dtype)
+                if ops.conv2d_nhwc_supported(a3, Hc, Wc, 3 * planes, 3, s) and ops.SPLIT_CONV_IMPLICIT:
+                    bmid, Hn, Wn = ops.conv2d_nhwc(a3, *blk["c2"], B, Hc, Wc, 3 * planes, 3, 1, relu=1, stride=s, out_dtype=torch.float32)
+                else:
+                    col, Hn, Wn = ops.im2col(a3, B, Hc, Wc, 3 * planes, 3, 3, s, 1, a3.dtype)
+                    bmid = ops.gemm(col, *blk["c2"], relu=1, out_dtype=torch.float32)
+            elif ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
                 bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1, stride=s)
             else:
                 col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
@@ -230,7 +282,7 @@ class InferenceEngine:
         m = self.model
         x, mask = samples.tensors, samples.mask
         key = (tuple(x.shape), str(x.device), m.compute_dtype, m.engine_outputs, bool(getattr(samples, "nopad", False)),
-               self._pack_key(m.compute_dtype, x.device))
+               self._pack_key(self._weight_dtype(), x.device))
         if not hasattr(self, "_graphs"):
             import collections
             self._graphs = collections.OrderedDict()
@@ -253,11 +305,13 @@ class InferenceEngine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, pool=self._graph_pool):
                 out = self._forward_eager(NestedTensor(sx, sm, getattr(samples, "nopad", False)), None)
-            ent = (graph, sx, sm, out)
+            # the entry keeps the packed weights it was captured with alive: the engine caches ONE packed set, and a switch to another
+            # mode (fp32 <-> split <-> 16-bit) re-packs -- without this reference a later replay of this graph would read freed memory
+            ent = (graph, sx, sm, out, self._packed, dict(getattr(self, "_geo", {})))      # (+ the cached shape constants it reads)
             while len(self._graphs) >= max(1, getattr(m, "max_cuda_graphs", 8)):     # least recently used shape goes first
                 self._graphs.popitem(last=False)
             self._graphs[key] = ent
-        graph, sx, sm, out = ent
+        graph, sx, sm, out = ent[:4]
         sx.copy_(x, non_blocking=True)
         sm.copy_(mask, non_blocking=True)
         graph.replay()
@@ -276,7 +330,11 @@ class InferenceEngine:
         x = x.float().contiguous()
         B, _, H, W = x.shape
         L.set_flavor(T)               # bf16 / fp16 model: the library built for that 16-bit type (fp32 parity mode: either)
-        P = self.packed(T, dev)
+        wd = self._weight_dtype()     # T, or SplitDtype(half) in the split-precision mode (fp32 activations, 3-term 16-bit products)
+        ops.SPLIT_ATTN16 = wd.half if isinstance(wd, SplitDtype) else None
+        if isinstance(wd, SplitDtype):
+            L.set_flavor(wd.half)
+        P = self.packed(wd, dev)
         d = tr.d_model
         st = stages
 

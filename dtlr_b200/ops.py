@@ -11,6 +11,14 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
     bias fp32 (N) or None, residual (M,N) of the output dtype or None."""
     L.require_cuda(a, w, bias, residual)
+    k_alg = a.shape[1]                     # algorithmic K (the split product runs 3K columns for it)
+    if a.dtype == torch.float32 and w.dtype in HALF:
+        # split-precision product (tensor-core parity mode, DESIGN.md 2.1): w is a weight packed [hi | lo | hi] (engine._split_w),
+        # a becomes [hi | hi | lo] (dtlr_split_cast); the 16-bit tcgen05 GEMM over K' = 3K accumulates hi.hi + hi.lo + lo.hi in fp32
+        assert a.dim() == 2 and w.dim() == 2 and w.shape[1] == 3 * a.shape[1], (a.shape, w.shape)
+        if out_dtype is None:
+            out_dtype = torch.float32
+        a = split_cast(a, w.dtype)
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.dtype == w.dtype
     M, K = a.shape
@@ -27,7 +35,7 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
         assert residual.dtype == out_dtype and residual.shape == (M, N) and residual.stride(1) == 1
         ldr = residual.stride(0)
     if L.TIMER is not None:
-        L.TIMER("gemm", 2.0 * M * N * K, a.device, True)
+        L.TIMER("gemm", 2.0 * M * N * k_alg, a.device, True)
         L.GEMM_BYTES += (M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
                          + (M * N * residual.element_size() if residual is not None else 0))
     in_code, out_code = L.dtype_code(a), L.dtype_code(out)     # (16-bit tensors select the library flavour before L.lib())
@@ -60,6 +68,18 @@ def _st(t):
     return L.stream_ptr(t.device)
 
 
+def split_cast(x, dtype=torch.float16):
+    """fp32 (M,K) (last-dim stride 1, any row pitch) -> 16-bit (M,3K) = [hi | hi | lo]: the A operand of a split-precision product."""
+    import ctypes
+    L.require_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1 and dtype in HALF
+    M, K = x.shape
+    L.set_flavor(dtype)
+    out = torch.empty((M, 3 * K), dtype=dtype, device=x.device)
+    _call("dtlr_split_cast", _p(x), ctypes.c_longlong(x.stride(0)), _p(out), ctypes.c_longlong(M), K, _st(x))
+    return out
+
+
 def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=None):
     Ho = (H + 2 * pad - KH) // stride + 1
     Wo = (W + 2 * pad - KW) // stride + 1
@@ -72,6 +92,8 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
 
 
 CONV_STRIDED_IMPLICIT = _os.environ.get("DTLR_CONV_STRIDED_IMPLICIT", "1") != "0"
+# split-precision mode: 3x3 convs as the implicit GEMM over 3C-channel pixels with an fp32 result (0: 16-bit im2col + GEMM, A/B)
+SPLIT_CONV_IMPLICIT = _os.environ.get("DTLR_SPLIT_CONV_IMPLICIT", "1") != "0"
 
 
 def conv2d_nhwc_supported(x, H, W, C, k, stride):
@@ -84,12 +106,12 @@ def conv2d_nhwc_supported(x, H, W, C, k, stride):
     return (x.dtype in HALF and C % 64 == 0 and seg >= 8 and 128 % seg == 0 and Wo % seg == 0)
 
 
-def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None, stride=1):
+def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None, stride=1, out_dtype=None):
     """'same'-padded k x k conv with stride 1 or 2 as implicit GEMM: x 16-bit [B*H*W, C] NHWC, w 16-bit [Cout, k*k*C] ->
-    16-bit [B*Ho*Wo, Cout]; returns (out, Ho, Wo)"""
+    16-bit (or fp32: out_dtype, used by the split-precision mode with C = 3 x channels) [B*Ho*Wo, Cout]; returns (out, Ho, Wo)"""
     Cout = w.shape[0]
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    out = torch.empty((B * Ho * Wo, Cout), dtype=x.dtype, device=x.device)
+    out = torch.empty((B * Ho * Wo, Cout), dtype=out_dtype or x.dtype, device=x.device)
     _call("dtlr_conv2d_nhwc_strided", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(stride), int(relu),
           L.dtype_code(out), _st(x))
     return out, Ho, Wo
@@ -215,7 +237,17 @@ def cast(x, dtype):
 ATTN_IMPL = _os.environ.get("DTLR_ATTN", "tc")
 
 
+# split-precision mode (engine sets it per forward): fp32 q / k / v are rounded to 16 bits for the tcgen05 attention core and the
+# result is widened again -- the contraction the precision budget is least sensitive to (6e-5 on the logits); the
+# exact-fp32 SIMT kernel (2.4 ms per layer at B = 64) stays the path of the plain fp32 mode
+SPLIT_ATTN16 = None
+
+
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
+    if (v.dtype == torch.float32 and SPLIT_ATTN16 is not None and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024
+            and qk.is_contiguous() and v.is_contiguous()):
+        out16 = mha_self_attention(cast(qk, SPLIT_ATTN16), k_off, cast(v, SPLIT_ATTN16), None, B, Q, heads, head_dim)
+        return cast(out16, torch.float32)
     L.set_flavor(v.dtype)
     out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
     if ATTN_IMPL == "tc" and v.dtype in HALF and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:

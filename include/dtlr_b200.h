@@ -189,6 +189,11 @@ int dtlr_sine_embed(const float* ref, const float* valid_ratios, void* out, int 
 int dtlr_box_refine(const float* delta, int ldd, const float* ref, float* out, long long rows, void* stream);
 int dtlr_sigmoid(const float* x, float* out, long long n, void* stream);
 int dtlr_cast(const void* x, void* out, long long n, int in_dtype, int out_dtype, void* stream);
+/* Split-precision A operand of the tensor-core parity mode: x fp32 [M,K] (row pitch ldx floats) -> out 16-bit [M,3K] = [hi | hi | lo],
+ * hi = rn16(x), lo = rn16(x - hi).  dtlr_gemm of it against a weight packed [hi | lo | hi] (K' = 3K) is the 3-term split product
+ * hi.hi + hi.lo + lo.hi accumulated in fp32; replaces the fp32 nn.Linear / conv contractions of the reference forward
+ * (models/dino/deformable_transformer.py:806-814,951-957, backbone.py:109-128) at ~2^-22 operand precision.  K % 8 == 0. */
+int dtlr_split_cast(const float* x, long long ldx, void* out, long long M, int K, void* stream);
 /* nn.MultiheadAttention(d_model, heads) core of the decoder self-attention (deformable_transformer.py:847, 903-905):
  * softmax(q k^T / sqrt(head_dim) [masked]) v per (batch, head), scores never materialised.
  * q rows: qk[b*Q+i, h*32 ...], k rows: qk[b*Q+j, k_off + h*32 ...], v rows: v[b*Q+j, h*32 ...];

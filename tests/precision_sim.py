@@ -180,6 +180,10 @@ MODES = {
     "2xbf16 split op, fp32 store": _all(GROUPS, 16, 24),
     "2xbf16 early / fp16 late, fp32 store": _all(EARLY, 16, 24) + _all(LATE, 11, 24),
     "2xfp16 split op, fp32 store": _all(GROUPS, 22, 24),
+    # the engine's split-precision mode (model.split_precision): every Linear / conv as a 2xfp16 split product, the deformable-attention
+    # core in exact fp32, the decoder self-attention core on fp16 operands with an fp16 result, activations fp32
+    "split engine: 2xfp16 GEMM, fp16 sa core": [(r"self_attn\.sa\.", 11, 11), (r"^msda\.core", 24, 24)] + _all(GROUPS, 22, 24),
+    "split engine, bf16 halves": [(r"self_attn\.sa\.", 8, 8), (r"^msda\.core", 24, 24)] + _all(GROUPS, 16, 24),
 }
 
 

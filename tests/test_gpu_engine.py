@@ -13,16 +13,20 @@ TOL = 1e-3
 MODE_TOL = 5e-2     # documented bound of the 16-bit-operand throughput mode with the ranking forced; measured ~2e-2
 
 
-def run_engine(model, x, force=None, dtype=torch.float32):
+def run_engine(model, x, force=None, dtype=torch.float32, split=False):
     model.eval()
     model.use_engine = True
     model.compute_dtype = dtype
+    model.split_precision = split
     st = {}
     model.transformer.debug_force_topk = force
     from dtlr_b200.misc import nested_tensor_from_tensor_list
-    with torch.no_grad():
-        out = model.engine().forward(nested_tensor_from_tensor_list(x), stages=st)
-    model.transformer.debug_force_topk = None
+    try:
+        with torch.no_grad():
+            out = model.engine().forward(nested_tensor_from_tensor_list(x), stages=st)
+    finally:
+        model.transformer.debug_force_topk = None
+        model.split_precision = False
     return out, st
 
 
@@ -217,6 +221,66 @@ def test_bench_shape_fp32_vs_oracle(bench_shape):
         assert torch.equal(og["pred_logits"], out_u["pred_logits"]) and torch.equal(og["pred_boxes"], out_u["pred_boxes"])
     finally:
         model.use_cuda_graph = False
+
+
+def test_split_precision_mode_config2_fixture_within_1e3():
+    """the tensor-core parity mode (model.split_precision: fp32 activations, every Linear / conv a 3-term fp16 split product on tcgen05,
+    fp16 attention core, exact fp32 deformable-attention core) against the reference-generated fixture: EVERY compared stage and output
+    within the north-star 1e-3 (predicted by tests/precision_sim.py: logits 1.7e-4, boxes 1.1e-4), frames identical wherever the
+    reference decides by a margin."""
+    fx = fixture("dino_A_b2")
+    model, _, _ = build_model(900)
+    x = synth.synth_images(2, 40, 1024, seed=0).cuda()
+    out, st = run_engine(model, x, force=torch.from_numpy(fx["topk_idx"]).long(), split=True)
+    check(fx, out, st, forced=True)
+    e_log, e_box = rel(out["pred_logits"], fx["pred_logits"]), rel(out["pred_boxes"], fx["pred_boxes"])
+    ref = {"pred_logits": torch.from_numpy(fx["pred_logits"]), "pred_boxes": torch.from_numpy(fx["pred_boxes"])}
+    n, dec, bad = _decidable_frames(ref, out, 1e-3, 1e-2)
+    # un-forced two-stage ranking: mismatches only where the reference's score gap is below the mode's score accuracy
+    out_u, st_u = run_engine(model, x, split=True)
+    mism = st_u["topk_idx"].cpu().numpy() != fx["topk_idx"]
+    ref_scores = np.take_along_axis(fx["topk_scores"], fx["topk_idx"].astype(np.int64), 1)
+    tie = np.minimum(np.abs(np.diff(ref_scores, axis=1, prepend=np.inf)), np.abs(np.diff(ref_scores, axis=1, append=-np.inf))) < 1e-3
+    print("split mode: logits %.2e boxes %.2e memory %.2e scores %.2e; frames %d decidable %d mismatching-decidable %d; un-forced rank positions "
+          "differing %d of %d (all on gaps < 1e-3: %s)" % (e_log, e_box, rel(st["memory"][:, ::8, ::4], fx["memory_s"]),
+                                                            rel(st["topk_scores"], fx["topk_scores"]), n, dec, bad, mism.sum(), mism.size,
+                                                            bool(tie[mism].all())))
+    assert bad == 0 and dec > 0.05 * n       # (random synthetic weights leave most frames at near-ties; trained weights do not)
+    assert tie[mism].all() and mism.mean() < 0.05
+
+
+def test_bench_shape_split_precision_vs_oracle(bench_shape):
+    """the same mode at the shape bench.py times (its `parity_mode` leg): B = 64, every stage within 1e-3 of the oracle, decidable frames
+    identical, CUDA-graph replay == eager launches"""
+    model, x, ref, rst = bench_shape
+    xg = x.cuda()
+    out, st = run_engine(model, xg, force=rst["topk_idx"], split=True)
+    for a, b, name in ((st["feats"][2][0], rst["feats"][2], "feat_c5"), (st["memory"], rst["memory"], "memory"),
+                       (st["topk_scores"], rst["topk_scores"], "scores"), (st["hs"][5], rst["hs"][5], "hs5"),
+                       (out["pred_logits"], ref["pred_logits"], "logits"), (out["pred_boxes"], ref["pred_boxes"], "boxes"),
+                       (out["aux_outputs"][0]["pred_logits"], ref["aux_outputs"][0]["pred_logits"], "aux0 logits"),
+                       (out["interm_outputs"]["pred_boxes"], ref["interm_outputs"]["pred_boxes"], "interm boxes")):
+        e = rel(a.float(), b)
+        print("B=64 split %-12s rel-to-max %.2e" % (name, e))
+        assert e < TOL, name
+    n, dec, bad = _decidable_frames(ref, out, 1e-3, 1e-2)
+    print("B=64 split frames %d decidable (cx gap >= 1e-3, top-2 gap >= 1e-2) %d mismatching-decidable %d" % (n, dec, bad))
+    assert bad == 0 and dec > 0.05 * n       # (random synthetic weights leave most frames at near-ties; trained weights do not)
+    model.split_precision = True
+    model.use_cuda_graph = True
+    try:
+        with torch.no_grad():
+            o1 = model(xg)
+            l1, b1 = o1["pred_logits"].clone(), o1["pred_boxes"].clone()
+            o2 = model(xg)
+        assert torch.equal(o2["pred_logits"], l1) and torch.equal(o2["pred_boxes"], b1)
+        model.use_cuda_graph = False
+        with torch.no_grad():
+            oe = model(xg)
+        assert torch.equal(oe["pred_logits"], l1) and torch.equal(oe["pred_boxes"], b1)
+    finally:
+        model.use_cuda_graph = False
+        model.split_precision = False
 
 
 @pytest.mark.parametrize("dt,MODE_TOL,min_agree", [(torch.float16, 1e-2, 0.97), (torch.bfloat16, 5e-2, 0.9)])

@@ -1,0 +1,42 @@
+"""Split-precision mode (model.split_precision) at the bench shape: ms per step under CUDA-graph replay, and a kernel table of one
+eager step (torch.profiler) -- where the tensor-core parity mode spends its time.  usage: python tools/bench_split.py [table]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from dtlr_b200 import synth  # noqa: E402
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+model = bench.build_ours(dev, torch.float32)
+model.split_precision = True
+x = synth.synth_images(bench.BATCH_PER_GPU, bench.IMG_H, bench.IMG_W, seed=100).to(dev)
+with torch.no_grad():
+    for _ in range(3):
+        model(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        model(x)
+    e1.record()
+    torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print("split mode B=%d: %.2f ms per step, %.0f img/s (implicit conv %s)" % (x.shape[0], ms, x.shape[0] / ms * 1e3, os.environ.get("DTLR_SPLIT_CONV_IMPLICIT", "1")))
+if len(sys.argv) > 1 and sys.argv[1] == "table":
+    model.use_cuda_graph = False
+    from torch.profiler import ProfilerActivity, profile
+    with torch.no_grad():
+        model(x)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            model(x)
+            torch.cuda.synchronize()
+    rows = sorted(((e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0), key=lambda r: -r[2])
+    tot = sum(r[2] for r in rows)
+    print("eager step: %.2f ms of kernels" % (tot / 1e3))
+    for k, n, t in rows[:28]:
+        print("%7.1f us %5.1f %% x%-4d %s" % (t, 100 * t / tot, n, k[:150]))
