@@ -12,6 +12,7 @@ _libs = {}
 FLAVOR = "bf16"
 
 F32, BF16, F64, F16 = 0, 1, 2, 3
+SPLIT16 = 4          # output-only code of dtlr_gemm / dtlr_conv2d_nhwc: the fp32 result as the 16-bit [hi | hi | lo] split operand
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float64: F64, torch.float16: F16}
 _FLAVOR_OF = {torch.bfloat16: "bf16", torch.float16: "f16"}
 

@@ -72,6 +72,8 @@ struct GemmEpi {
     ConvGeo conv;            // conv.enabled: implicit-GEMM convolution (A fetched through the 4-D map)
     int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
     unsigned int* dbgbuf;    // timeline probe (dtlr_gemm_debug_buffer): CTA 0 of the weight-stationary kernel records clock() stamps
+    int split_out = 0;       // fp32-output tile kernel only: write the result as the 16-bit split operand [hi | hi | lo] ([M, 3N], ldc in
+                             // 16-bit elements) that dtlr_split_cast would make of it -- the next split product reads it directly
 };
 
 static unsigned int* g_gemm_dbgbuf = nullptr;
@@ -507,6 +509,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             for (int k = 0; k < EPC; ++k) f[k] = fmaxf(f[k], 0.f);
                         }
                         d = pack_chunk<OutT>(f);
+                    }
+                    if constexpr (sizeof(OutT) == 4) {
+                        if (e.split_out) {       // 4 fp32 results -> hi at column n and n + N, lo = rn16(x - hi) at n + 2N (8-byte stores)
+                            float f[4];
+                            unpack_chunk<float>(d, f);
+                            float l[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) l[k] = f[k] - op16_to_f32(f32_to_op16(f[k]));
+                            const uint2 hi2 = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+                            const uint2 lo2 = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+                            op16_t* sp = reinterpret_cast<op16_t*>(e.C) + (size_t)grow * e.ldc + n0 + ch * 4;
+                            *reinterpret_cast<uint2*>(sp) = hi2;
+                            *reinterpret_cast<uint2*>(sp + e.N) = hi2;
+                            *reinterpret_cast<uint2*>(sp + 2 * (size_t)e.N) = lo2;
+                            continue;
+                        }
                     }
                     *reinterpret_cast<uint4*>(cp) = d;
                 }
@@ -997,7 +1015,7 @@ static int launch_ws(const void* A, int lda, const void* W, int ldw, const GemmE
 // tiles that every CTA amortises its weight slice over >= 2 of them
 template <typename OutT>
 static bool ws_try(const void* A, int lda, const void* W, int ldw, const GemmEpi& e, cudaStream_t st, int* rc) {
-    if (g_debug_flags & 32) return false;
+    if ((g_debug_flags & 32) || e.split_out) return false;
     constexpr int EPC = 16 / (int)sizeof(OutT);
     // only the row PITCH has to be 16-byte aligned (TMA store clips the columns beyond N, the weight rows beyond N are zero-filled)
     if (e.K > 256 || (e.ldc % EPC) != 0 || ((uintptr_t)e.C & 15) != 0) return false;
@@ -1060,9 +1078,17 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
     if (M == 0) return DTLR_OK;
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
-    DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= N && (!residual || ldr >= N), "gemm: leading dimension too small");
+    const bool split_out = out_dtype == DTLR_SPLIT16;      // fp32 result written as the 16-bit [hi | hi | lo] operand of the next split product
+    DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= (split_out ? 3 * N : N) && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpi e{bias, residual, C, ldr, ldc, M, N, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{0, 0, 0, 0, 0, 0, 0, 0, 1}, g_debug_flags};
+    if (split_out) {
+        DTLR_CHECK_ARG(in_dtype == DTLR_OP16 && (N % 4) == 0 && (ldc % 8) == 0 && (((uintptr_t)C) & 15) == 0 &&
+                       (!residual || ((ldr % 4) == 0 && (((uintptr_t)residual) & 15) == 0)),
+                       "gemm: split output needs 16-bit operands, N %% 4 == 0 and 16-byte aligned rows");
+        e.split_out = 1;            // e.ldc stays the pitch in 16-bit elements (the split stores use it; ldc % 8 also satisfies the fp32
+        out_dtype = DTLR_F32;       // epilogue's 16-byte rule, and N % 4 == 0 keeps every tile on its vector path)
+    }
     if (in_dtype == DTLR_F32) {
         DTLR_CHECK_ARG(out_dtype == DTLR_F32, "gemm: fp32 operands produce fp32 output");
         dim3 grid((M + 63) / 64, (N + 63) / 64);
@@ -1151,11 +1177,14 @@ extern "C" int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const floa
     DTLR_CHECK_ARG(seg_w >= 8 && (128 % seg_w) == 0 && (W % seg_w) == 0,
                    "conv2d_nhwc: output width %d cannot be tiled into 128-pixel row segments (use im2col + gemm)", W);
     DTLR_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv2d_nhwc: operands must be 16-byte aligned");
-    DTLR_CHECK_ARG(out_dtype == DTLR_OP16 || out_dtype == DTLR_F32, "conv2d_nhwc: output must be 16-bit or f32");
-    const bool f32out = out_dtype == DTLR_F32;     // split-precision mode (3C channels = [hi | hi | lo], fp32 result); residual fp32 too
+    DTLR_CHECK_ARG(out_dtype == DTLR_OP16 || out_dtype == DTLR_F32 || out_dtype == DTLR_SPLIT16, "conv2d_nhwc: output must be 16-bit, f32 or split");
+    const bool split_out = out_dtype == DTLR_SPLIT16;             // fp32 result written as [hi | hi | lo], 3 x Cout 16-bit columns per pixel
+    const bool f32out = out_dtype == DTLR_F32 || split_out;       // split-precision mode (3C input channels = [hi | hi | lo]); residual fp32 too
+    DTLR_CHECK_ARG(!split_out || ((Cout % 8) == 0 && (((uintptr_t)out) & 15) == 0), "conv2d_nhwc: split output needs Cout %% 8 == 0");
     const int M = B * H * W, K = KH * KW * C;
     if (M == 0) return DTLR_OK;
-    GemmEpi e{bias, residual, out, Cout, Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w, stride}, g_debug_flags};
+    GemmEpi e{bias, residual, out, Cout, split_out ? 3 * Cout : Cout, M, Cout, K, relu, LnArgs{nullptr, nullptr, nullptr, nullptr, 0, 0.f}, ConvGeo{1, H, W, KW, pad, C / 64, seg_w, 128 / seg_w, stride}, g_debug_flags};
+    e.split_out = split_out ? 1 : 0;
     CUtensorMap ta, tb;
     int rc;
     if ((rc = make_tmap_nhwc(&ta, x, B, Hin, Win, C, seg_w, stride))) return rc;

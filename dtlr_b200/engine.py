@@ -187,10 +187,19 @@ class InferenceEngine:
         return ops.gemm(x, w, b, out_dtype=torch.float32, out=buf[:, :N])
 
     @staticmethod
+    def _hidden_dtype(x, w):
+        """out_dtype of a layer whose result only feeds the next contraction: in the split-precision mode (fp32 / split activations against
+        16-bit [hi | lo | hi] weights) the epilogue writes the split operand itself (ops.SPLIT); otherwise the activation dtype"""
+        return ops.SPLIT if (InferenceEngine._split_now and ops.SPLIT_OUT_FUSED) else None
+
+    _split_now = False       # set per forward: the split-precision mode is running (16-bit tensors between layers are split operands)
+
+    @staticmethod
     def _mlp3(x, layers, out_f32_last=True):
-        h = ops.gemm(x, *layers[0], relu=1)
-        h = ops.gemm(h, *layers[1], relu=1)
-        return ops.gemm(h, *layers[2], out_dtype=torch.float32 if out_f32_last else None)
+        hd = InferenceEngine._hidden_dtype
+        h = ops.gemm(x, *layers[0], relu=1, out_dtype=hd(x, layers[0][0]))
+        h = ops.gemm(h, *layers[1], relu=1, out_dtype=hd(h, layers[1][0]))
+        return ops.gemm(h, *layers[2], out_dtype=torch.float32 if (out_f32_last or InferenceEngine._split_now) else None)
 
     @staticmethod
     def _box_head(x, layers, w3_f32, ref):
@@ -214,17 +223,26 @@ class InferenceEngine:
         nblk = len(P["blocks"])
         for i, blk in enumerate(P["blocks"]):
             s = blk["stride"]
-            a = ops.gemm(y, *blk["c1"], relu=1)
+            split = blk["c2"][0].dtype != y.dtype
             planes = blk["c1"][0].shape[0]
-            if blk["c2"][0].dtype != a.dtype:
-                # split-precision mode: the fp32 NHWC map becomes 16-bit with 3 x planes channels per pixel ([hi | hi | lo]); the 3x3 conv
-                # runs on it as the same implicit GEMM (weights [hi | lo | hi] per tap) with an fp32 result
-                a3 = ops.split_cast(a, blk["c2"][0].dtype)
+            if split:
+                # split-precision mode: conv1's result is written as 16-bit pixels of 3 x planes channels ([hi | hi | lo]: from the GEMM
+                # epilogue, or fp32 + dtlr_split_cast); the 3x3 conv runs on them as the same implicit GEMM (weights [hi | lo | hi] per tap)
+                # and hands conv3 its split operand the same way; the block output (residual stream) is fp32
+                fused = ops.SPLIT_OUT_FUSED
+                y3 = ops.split_cast(y, blk["c2"][0].dtype)          # shared by conv1 and the stride-1 downsample conv
+                a3 = ops.gemm(y3, *blk["c1"], relu=1, out_dtype=ops.SPLIT) if fused else \
+                    ops.split_cast(ops.gemm(y3, *blk["c1"], relu=1, out_dtype=torch.float32), blk["c2"][0].dtype)
+                mid_dt = ops.SPLIT if fused else torch.float32
                 if ops.conv2d_nhwc_supported(a3, Hc, Wc, 3 * planes, 3, s) and ops.SPLIT_CONV_IMPLICIT:
-                    bmid, Hn, Wn = ops.conv2d_nhwc(a3, *blk["c2"], B, Hc, Wc, 3 * planes, 3, 1, relu=1, stride=s, out_dtype=torch.float32)
+                    bmid, Hn, Wn = ops.conv2d_nhwc(a3, *blk["c2"], B, Hc, Wc, 3 * planes, 3, 1, relu=1, stride=s, out_dtype=mid_dt)
                 else:
                     col, Hn, Wn = ops.im2col(a3, B, Hc, Wc, 3 * planes, 3, 3, s, 1, a3.dtype)
-                    bmid = ops.gemm(col, *blk["c2"], relu=1, out_dtype=torch.float32)
+                    bmid = ops.gemm(col, *blk["c2"], relu=1, out_dtype=mid_dt)
+            else:
+                a = ops.gemm(y, *blk["c1"], relu=1)
+            if split:
+                pass
             elif ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
                 bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1, stride=s)
             else:
@@ -232,14 +250,14 @@ class InferenceEngine:
                 bmid = ops.gemm(col, *blk["c2"], relu=1)
             if blk["ds"] is not None:
                 if s == 1:
-                    idt = ops.gemm(y, *blk["ds"])
+                    idt = ops.gemm(y3, *blk["ds"], out_dtype=torch.float32) if split else ops.gemm(y, *blk["ds"])
                 elif ops.conv2d_nhwc_supported(y, Hc, Wc, cin, 1, s):      # strided 1x1 downsample: TMA traversal stride, no gather pass
                     idt = ops.conv2d_nhwc(y, *blk["ds"], B, Hc, Wc, cin, 1, 0, stride=s)[0]
                 else:
                     idt = ops.gemm(ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0], *blk["ds"])
             else:
                 idt = y
-            y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2)
+            y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2, out_dtype=idt.dtype)
             Hc, Wc, cin = Hn, Wn, planes * 4
             last_of_layer = (i == nblk - 1) or (P["blocks"][i + 1]["layer"] != blk["layer"])
             if last_of_layer and blk["layer"] in P["return_layers"]:
@@ -332,6 +350,7 @@ class InferenceEngine:
         L.set_flavor(T)               # bf16 / fp16 model: the library built for that 16-bit type (fp32 parity mode: either)
         wd = self._weight_dtype()     # T, or SplitDtype(half) in the split-precision mode (fp32 activations, 3-term 16-bit products)
         ops.SPLIT_ATTN16 = wd.half if isinstance(wd, SplitDtype) else None
+        InferenceEngine._split_now = isinstance(wd, SplitDtype)
         if isinstance(wd, SplitDtype):
             L.set_flavor(wd.half)
         P = self.packed(wd, dev)
@@ -469,11 +488,18 @@ class InferenceEngine:
             hs_all = torch.empty((n_layers * B * Q, d), dtype=T, device=dev) if shared_heads else None
             for i, lyr in enumerate(P["dec"]):
                 sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
-                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1), *P["rph"][1])
+                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype(sine, P["rph"][0][0])), *P["rph"][1], out_dtype=T)
                 qk_in = ops.add(tgt, qp)
-                qk = ops.gemm(qk_in, *lyr["qk"])
-                v = ops.gemm(tgt, *lyr["v"])
-                att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
+                if ops.SPLIT_ATTN16 is not None and d // lyr["heads"] == 32 and Q <= 1024:
+                    # split-precision mode: q / k / v leave their projections rounded to 16 bits for the tcgen05 attention core (the
+                    # contraction the error budget is least sensitive to), its result is widened for the fp32 residual stream
+                    qk = ops.gemm(qk_in, *lyr["qk"], out_dtype=ops.SPLIT_ATTN16)
+                    v = ops.gemm(tgt, *lyr["v"], out_dtype=ops.SPLIT_ATTN16)
+                    att = ops.cast(ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"]), torch.float32)
+                else:
+                    qk = ops.gemm(qk_in, *lyr["qk"])
+                    v = ops.gemm(tgt, *lyr["v"])
+                    att = ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"])
                 tgt, qca = ops.linear_ln(att, *lyr["o"], tgt, *lyr["ln2"], add2=qp)
                 core = self._msda(lyr["ca"], qca, ref, 4, val_all[:, i * d:(i + 1) * d], None, vr, shapes_host, lsi_host, nlev, B, Q, S, T,
                                   precomputed_value=True)

@@ -7,6 +7,17 @@ from . import _lib as L
 HALF = (torch.bfloat16, torch.float16)      # the two 16-bit flavours of the throughput mode (one library each, _lib.set_flavor)
 
 
+
+class _SplitOut:
+    """out_dtype marker of gemm / conv2d_nhwc: write the fp32 result as the split operand [hi | hi | lo] (include/dtlr_b200.h DTLR_SPLIT16)"""
+
+    def __repr__(self):
+        return "ops.SPLIT"
+
+
+SPLIT = _SplitOut()
+
+
 def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
     bias fp32 (N) or None, residual (M,N) of the output dtype or None."""
@@ -25,9 +36,14 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     N = w.shape[0]
     if out_dtype is None:
         out_dtype = a.dtype
-    if out is None:
+    split_out = out_dtype is SPLIT        # fp32 result stored as the 16-bit [hi | hi | lo] operand of the next split product: (M, 3N)
+    if split_out:
+        assert a.dtype in HALF and out is None and N % 4 == 0
+        out = torch.empty((M, 3 * N), dtype=a.dtype, device=a.device)
+        out_dtype = torch.float32         # (dtype of the residual)
+    elif out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
-    assert out.stride(1) == 1 and out.shape == (M, N) and out.dtype == out_dtype
+    assert split_out or (out.stride(1) == 1 and out.shape == (M, N) and out.dtype == out_dtype)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N
     ldr = 0
@@ -39,6 +55,8 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
         L.GEMM_BYTES += (M * K * a.element_size() + N * K * w.element_size() + M * N * out.element_size()
                          + (M * N * residual.element_size() if residual is not None else 0))
     in_code, out_code = L.dtype_code(a), L.dtype_code(out)     # (16-bit tensors select the library flavour before L.lib())
+    if split_out:
+        out_code = L.SPLIT16
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
@@ -94,6 +112,9 @@ def im2col(x, B, H, W, C, KH, KW, stride, pad, out_dtype, nchw_input=False, ldo=
 CONV_STRIDED_IMPLICIT = _os.environ.get("DTLR_CONV_STRIDED_IMPLICIT", "1") != "0"
 # split-precision mode: 3x3 convs as the implicit GEMM over 3C-channel pixels with an fp32 result (0: 16-bit im2col + GEMM, A/B)
 SPLIT_CONV_IMPLICIT = _os.environ.get("DTLR_SPLIT_CONV_IMPLICIT", "1") != "0"
+# split-precision mode: producers whose result only feeds another contraction (conv1 -> conv2 -> conv3 of a bottleneck, linear1 of an FFN,
+# MLP hidden layers) write the split operand from their epilogue (DTLR_SPLIT16) instead of fp32 + dtlr_split_cast (0: A/B)
+SPLIT_OUT_FUSED = _os.environ.get("DTLR_SPLIT_OUT_FUSED", "1") != "0"
 
 
 def conv2d_nhwc_supported(x, H, W, C, k, stride):
@@ -111,9 +132,14 @@ def conv2d_nhwc(x, w, bias, B, H, W, C, k, pad, relu=0, residual=None, stride=1,
     16-bit (or fp32: out_dtype, used by the split-precision mode with C = 3 x channels) [B*Ho*Wo, Cout]; returns (out, Ho, Wo)"""
     Cout = w.shape[0]
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    out = torch.empty((B * Ho * Wo, Cout), dtype=out_dtype or x.dtype, device=x.device)
+    if out_dtype is SPLIT:
+        out = torch.empty((B * Ho * Wo, 3 * Cout), dtype=x.dtype, device=x.device)
+        code = L.SPLIT16
+    else:
+        out = torch.empty((B * Ho * Wo, Cout), dtype=out_dtype or x.dtype, device=x.device)
+        code = L.dtype_code(out)
     _call("dtlr_conv2d_nhwc_strided", _p(x), _p(w), _p(bias), _p(residual), _p(out), B, H, W, C, Cout, k, k, pad, int(stride), int(relu),
-          L.dtype_code(out), _st(x))
+          code, _st(x))
     return out, Ho, Wo
 
 
@@ -452,6 +478,11 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     import ctypes
     M = x.shape[0]
     hid = w1.shape[0]
+    if x.dtype == torch.float32 and w1.dtype in HALF:
+        # split-precision mode: linear1 writes its ReLU output straight as the split operand of linear2 (no fp32 hidden activation in HBM)
+        h = gemm(x, w1, b1, relu=1, out_dtype=SPLIT if SPLIT_OUT_FUSED else None)
+        y = gemm(h, w2, b2, residual=x, out_dtype=torch.float32)
+        return add_layernorm(y, None, gamma, beta, add2=add2)
     if (FFN_FUSED and x.dtype in HALF and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
             and x.stride(1) == 1 and x.stride(0) % 8 == 0):
         y = torch.empty((M, 256), dtype=x.dtype, device=x.device)

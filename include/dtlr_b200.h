@@ -26,7 +26,10 @@ typedef enum {
 
 /* DTLR_BF16 is served by libdtlr_b200.so, DTLR_F16 by libdtlr_b200_f16.so (the same sources built with fp16 as the 16-bit type);
  * each library rejects the other 16-bit code. */
-typedef enum { DTLR_F32 = 0, DTLR_BF16 = 1, DTLR_F64 = 2, DTLR_F16 = 3 } dtlr_dtype;
+typedef enum { DTLR_F32 = 0, DTLR_BF16 = 1, DTLR_F64 = 2, DTLR_F16 = 3,
+               /* OUTPUT code of dtlr_gemm / dtlr_conv2d_nhwc[_strided] only: the fp32 result is written as the 16-bit split operand
+                * [hi | hi | lo] ([M, 3N], ldc in 16-bit elements, N % 4 == 0) that dtlr_split_cast would make of it */
+               DTLR_SPLIT16 = 4 } dtlr_dtype;
 
 /* library identification: (major<<16 | minor<<8 | patch), and the SM architecture the kernels were built for */
 int dtlr_version(void);
@@ -91,6 +94,8 @@ int dtlr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
  * rows 16-byte aligned (lda,ldw multiples of 8).  in_dtype DTLR_F32: exact-fp32 SIMT path (parity mode), out F32.
  * When N is no multiple of 16 bytes of output elements and ldc is exactly N rounded up to that multiple (a padded row pitch),
  * the pad columns of C are scratch: the TMA-store epilogue may write zeros there.
+ * out_dtype DTLR_SPLIT16 (16-bit operands only): C is 16-bit [M, 3N] = [hi | hi | lo] of the fp32 result (residual, if any, fp32) --
+ * the A operand of the next split-precision product (dtlr_split_cast) without the fp32 round trip.
  */
 int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, int ldr,
               void* C, int ldc, int M, int N, int K, int in_dtype, int out_dtype, int relu, void* stream);

@@ -81,3 +81,37 @@ def test_split_conv3x3_vs_fp64(half, tol, B, C, H, W, Co, stride):
         err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
         print("split conv %s %s C=%d %dx%d s%d: rel-to-max %.2e" % (name, half, C, H, W, stride, err))
         assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("half", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1824, 256, 256), (1800, 2048, 256), (1824, 256, 2048), (900, 384, 256), (130, 64, 64), (257, 200, 72),
+                                   (58368, 64, 64)])
+def test_split_output_epilogue_bit_exact(half, M, N, K):
+    """out_dtype = ops.SPLIT (DTLR_SPLIT16): the GEMM epilogue writes [hi | hi | lo] of its fp32 result -- bit-identical to dtlr_split_cast
+    of the fp32 output of the same product (bias, ReLU before / after an fp32 residual), from fp32 and from already-split A operands"""
+    from dtlr_b200 import engine, ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w3 = engine._split_w(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5, half)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    a3 = ops.split_cast(a, half)
+    for kw in (dict(relu=1), dict(relu=2, residual=res), dict()):
+        want = ops.split_cast(ops.gemm(a3, w3, bias, out_dtype=torch.float32, **kw), half)
+        got = ops.gemm(a3, w3, bias, out_dtype=ops.SPLIT, **kw)
+        assert got.shape == (M, 3 * N) and got.dtype == half
+        assert torch.equal(got, want), kw
+        assert torch.equal(ops.gemm(a, w3, bias, out_dtype=ops.SPLIT, **kw), want), kw
+
+
+@pytest.mark.parametrize("B,C,H,W,Co,stride", [(2, 64, 10, 256, 64, 1), (2, 128, 10, 256, 128, 2), (2, 512, 2, 32, 512, 1)])
+def test_split_output_conv_bit_exact(B, C, H, W, Co, stride):
+    from dtlr_b200 import engine, ops
+    half = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(C + W)
+    a3 = ops.split_cast(torch.randn(B * H * W, C, device="cuda", generator=g), half)
+    w3 = engine._split_w(torch.randn(Co, 9 * C, device="cuda", generator=g) / (9 * C) ** 0.5, half, taps=9)
+    bias = torch.randn(Co, device="cuda", generator=g)
+    f32, Ho, Wo = ops.conv2d_nhwc(a3, w3, bias, B, H, W, 3 * C, 3, 1, relu=1, stride=stride, out_dtype=torch.float32)
+    got = ops.conv2d_nhwc(a3, w3, bias, B, H, W, 3 * C, 3, 1, relu=1, stride=stride, out_dtype=ops.SPLIT)[0]
+    assert got.shape == (B * Ho * Wo, 3 * Co) and torch.equal(got, ops.split_cast(f32, half))
