@@ -72,6 +72,10 @@ struct GemmEpi {
     ConvGeo conv;            // conv.enabled: implicit-GEMM convolution (A fetched through the 4-D map)
     int dbg;                 // tuning only (dtlr_debug_flags): 1 skip global stores, 2 skip MMA issue, 4 skip step-1 staging
     unsigned int* dbgbuf;    // timeline probe (dtlr_gemm_debug_buffer): CTA 0 of the weight-stationary kernel records clock() stamps
+    int split3 = 0;          // tile kernel, even STAGES, plain (non-conv) A: the operands are split-precision matrices A = [hi | hi | lo],
+                             // W = [hi | lo | hi] over K = 3 Kl columns (Kl % 64 == 0).  Instead of walking 3 Kl columns (6 tile loads per
+                             // logical k-block) the producer loads A_hi, W_hi and A_lo, W_lo once (two pipeline stages) and the issuer
+                             // runs hi.hi, hi.lo, lo.hi from them: the same three products with 2/3 of the L2 -> shared-memory traffic
     int split_out = 0;       // fp32-output tile kernel only: write the result as the 16-bit split operand [hi | hi | lo] ([M, 3N], ldc in
                              // 16-bit elements) that dtlr_split_cast would make of it -- the next split product reads it directly
 };
@@ -261,7 +265,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m = (e.M + GEMM_BM - 1) / GEMM_BM, num_n = (e.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    const int num_kb = (e.K + GEMM_BK - 1) / GEMM_BK;
+    const int Kl = e.split3 ? e.K / 3 : 0;                                   // logical K of a split-precision product
+    const int num_kb = e.split3 ? 2 * (Kl / GEMM_BK) : (e.K + GEMM_BK - 1) / GEMM_BK;   // pipeline steps per tile
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -339,6 +344,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             tma_load_4d(sa + (size_t)j * cg.seg_w * (GEMM_BK * 2), &tmA, &full_bar[s], c0, wo * cg.stride + kw - cg.pad,
                                         ho * cg.stride + kh - cg.pad, bimg);
                         }
+                    } else if (e.split3) {                              // step 2j: (A_hi, W_hi) of logical block j; step 2j+1: (A_lo, W_lo)
+                        const int j = kb >> 1, part = kb & 1;
+                        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+                        tma_load_2d(sa, &tmA, &full_bar[s], (part ? 2 * Kl : 0) + j * GEMM_BK, m0);
+                        tma_load_2d(sa + S::A_BYTES, &tmB, &full_bar[s], (part ? Kl : 0) + j * GEMM_BK, n0);
+                        continue;
                     } else {
                         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
                         tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
@@ -358,6 +369,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             mbar_wait(&tmem_empty_bar[as], aph ^ 1);                    // epilogue has drained this accumulator
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
+            if (e.split3) {
+                // split-precision product: stages (s0, s1) = (A_hi | W_hi, A_lo | W_lo) of one logical k-block; hi.hi, hi.lo, lo.hi
+                for (int kb = 0; kb < num_kb; kb += 2, it += 2) {
+                    const int s0 = it % STAGES, s1 = (it + 1) % STAGES;
+                    mbar_wait(&full_bar[s0], (it / STAGES) & 1);
+                    mbar_wait(&full_bar[s1], ((it + 1) / STAGES) & 1);
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa0 = smem_u32(smem + s0 * S::STAGE_BYTES), sa1 = smem_u32(smem + s1 * S::STAGE_BYTES);
+                        const uint64_t da0 = make_sw128_kmajor_desc(sa0), db0 = make_sw128_kmajor_desc(sa0 + S::A_BYTES);
+                        const uint64_t da1 = make_sw128_kmajor_desc(sa1), db1 = make_sw128_kmajor_desc(sa1 + S::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tmem_d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tmem_d, da0 + (uint64_t)(2 * k), db1 + (uint64_t)(2 * k), IDESC, 1);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(tmem_d, da1 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), IDESC, 1);
+                        umma_commit(&empty_bar[s0]);
+                        umma_commit(&empty_bar[s1]);
+                        if (kb == num_kb - 2) umma_commit(&tmem_full_bar[as]);
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -1078,6 +1114,13 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     DTLR_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
     if (M == 0) return DTLR_OK;
     DTLR_CHECK_ARG(A && W && C, "gemm: null pointer");
+    // in_dtype DTLR_SPLIT16: A = [hi | hi | lo], W = [hi | lo | hi] (K = 3 Kl columns each) -- the same product as the plain walk over K,
+    // with the duplicate hi tiles loaded once where the tile kernel can (e.split3)
+    bool split_in = false;
+    if (in_dtype == DTLR_SPLIT16) {
+        split_in = (K % 3) == 0 && ((K / 3) % GEMM_BK) == 0 && !(g_debug_flags & 67108864);      // flag 67108864: plain 3K walk, A/B
+        in_dtype = DTLR_OP16;
+    }
     const bool split_out = out_dtype == DTLR_SPLIT16;      // fp32 result written as the 16-bit [hi | hi | lo] operand of the next split product
     DTLR_CHECK_ARG(lda >= K && ldw >= K && ldc >= (split_out ? 3 * N : N) && (!residual || ldr >= N), "gemm: leading dimension too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1104,7 +1147,8 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     int rc = DTLR_OK;
     if (out_dtype == DTLR_OP16 ? ws_try<op16_t>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
     const long long row_tiles_ = (M + GEMM_BM - 1) / GEMM_BM;
-    if (out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8) &&
+    e.split3 = split_in ? 1 : 0;           // the 128- and 64-wide tile kernels below (even stage counts); 256-wide 16-bit tiles walk 3 Kl
+    if (!split_in && out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8) &&
         (K < 1024 || ((row_tiles_ * (N / 128) + sm_count() - 1) / sm_count()) * 128 * 3 > ((row_tiles_ * (N / 256) + sm_count() - 1) / sm_count()) * 256 * 2)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
         // N = 256 layers become one tile per row block

@@ -197,9 +197,10 @@ class InferenceEngine:
     @staticmethod
     def _mlp3(x, layers, out_f32_last=True):
         hd = InferenceEngine._hidden_dtype
+        sp = InferenceEngine._split_now          # (every operand below is then a whole-row split matrix: [hi | hi | lo] x [hi | lo | hi])
         h = ops.gemm(x, *layers[0], relu=1, out_dtype=hd(x, layers[0][0]))
-        h = ops.gemm(h, *layers[1], relu=1, out_dtype=hd(h, layers[1][0]))
-        return ops.gemm(h, *layers[2], out_dtype=torch.float32 if (out_f32_last or InferenceEngine._split_now) else None)
+        h = ops.gemm(h, *layers[1], relu=1, out_dtype=hd(h, layers[1][0]), split3=sp)
+        return ops.gemm(h, *layers[2], out_dtype=torch.float32 if (out_f32_last or sp) else None, split3=sp)
 
     @staticmethod
     def _box_head(x, layers, w3_f32, ref):
@@ -231,8 +232,8 @@ class InferenceEngine:
                 # and hands conv3 its split operand the same way; the block output (residual stream) is fp32
                 fused = ops.SPLIT_OUT_FUSED
                 y3 = ops.split_cast(y, blk["c2"][0].dtype)          # shared by conv1 and the stride-1 downsample conv
-                a3 = ops.gemm(y3, *blk["c1"], relu=1, out_dtype=ops.SPLIT) if fused else \
-                    ops.split_cast(ops.gemm(y3, *blk["c1"], relu=1, out_dtype=torch.float32), blk["c2"][0].dtype)
+                a3 = ops.gemm(y3, *blk["c1"], relu=1, out_dtype=ops.SPLIT, split3=True) if fused else \
+                    ops.split_cast(ops.gemm(y3, *blk["c1"], relu=1, out_dtype=torch.float32, split3=True), blk["c2"][0].dtype)
                 mid_dt = ops.SPLIT if fused else torch.float32
                 if ops.conv2d_nhwc_supported(a3, Hc, Wc, 3 * planes, 3, s) and ops.SPLIT_CONV_IMPLICIT:
                     bmid, Hn, Wn = ops.conv2d_nhwc(a3, *blk["c2"], B, Hc, Wc, 3 * planes, 3, 1, relu=1, stride=s, out_dtype=mid_dt)
@@ -250,14 +251,14 @@ class InferenceEngine:
                 bmid = ops.gemm(col, *blk["c2"], relu=1)
             if blk["ds"] is not None:
                 if s == 1:
-                    idt = ops.gemm(y3, *blk["ds"], out_dtype=torch.float32) if split else ops.gemm(y, *blk["ds"])
+                    idt = ops.gemm(y3, *blk["ds"], out_dtype=torch.float32, split3=True) if split else ops.gemm(y, *blk["ds"])
                 elif ops.conv2d_nhwc_supported(y, Hc, Wc, cin, 1, s):      # strided 1x1 downsample: TMA traversal stride, no gather pass
                     idt = ops.conv2d_nhwc(y, *blk["ds"], B, Hc, Wc, cin, 1, 0, stride=s)[0]
                 else:
                     idt = ops.gemm(ops.im2col(y, B, Hc, Wc, cin, 1, 1, s, 0, T)[0], *blk["ds"])
             else:
                 idt = y
-            y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2, out_dtype=idt.dtype)
+            y = ops.gemm(bmid, *blk["c3"], residual=idt, relu=2, out_dtype=idt.dtype, split3=split and bmid.dtype in ops.HALF)
             Hc, Wc, cin = Hn, Wn, planes * 4
             last_of_layer = (i == nblk - 1) or (P["blocks"][i + 1]["layer"] != blk["layer"])
             if last_of_layer and blk["layer"] in P["return_layers"]:
@@ -488,7 +489,7 @@ class InferenceEngine:
             hs_all = torch.empty((n_layers * B * Q, d), dtype=T, device=dev) if shared_heads else None
             for i, lyr in enumerate(P["dec"]):
                 sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
-                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype(sine, P["rph"][0][0])), *P["rph"][1], out_dtype=T)
+                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype(sine, P["rph"][0][0])), *P["rph"][1], out_dtype=T, split3=self._split_now)
                 qk_in = ops.add(tgt, qp)
                 if ops.SPLIT_ATTN16 is not None and d // lyr["heads"] == 32 and Q <= 1024:
                     # split-precision mode: q / k / v leave their projections rounded to 16 bits for the tcgen05 attention core (the

@@ -18,7 +18,7 @@ class _SplitOut:
 SPLIT = _SplitOut()
 
 
-def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
+def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None, split3=False):
     """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
     bias fp32 (N) or None, residual (M,N) of the output dtype or None."""
     L.require_cuda(a, w, bias, residual)
@@ -30,6 +30,7 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
         if out_dtype is None:
             out_dtype = torch.float32
         a = split_cast(a, w.dtype)
+        split3 = True
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], (a.shape, w.shape)
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.dtype == w.dtype
     M, K = a.shape
@@ -57,6 +58,9 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None):
     in_code, out_code = L.dtype_code(a), L.dtype_code(out)     # (16-bit tensors select the library flavour before L.lib())
     if split_out:
         out_code = L.SPLIT16
+    if split3 and SPLIT3_LOADS:    # a = [hi | hi | lo], w = [hi | lo | hi] over whole rows: the tile kernel loads each hi / lo tile once (DTLR_SPLIT16 in)
+        assert a.dtype in HALF and K % 3 == 0
+        in_code = L.SPLIT16
     with torch.cuda.device(a.device):
         rc = L.lib().dtlr_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), L.ptr(bias) if bias is not None else None,
                                L.ptr(residual) if residual is not None else None, ldr, L.ptr(out), out.stride(0),
@@ -115,6 +119,9 @@ SPLIT_CONV_IMPLICIT = _os.environ.get("DTLR_SPLIT_CONV_IMPLICIT", "1") != "0"
 # split-precision mode: producers whose result only feeds another contraction (conv1 -> conv2 -> conv3 of a bottleneck, linear1 of an FFN,
 # MLP hidden layers) write the split operand from their epilogue (DTLR_SPLIT16) instead of fp32 + dtlr_split_cast (0: A/B)
 SPLIT_OUT_FUSED = _os.environ.get("DTLR_SPLIT_OUT_FUSED", "1") != "0"
+# split-precision products tell dtlr_gemm that their operands are [hi | hi | lo] x [hi | lo | hi] (in_dtype DTLR_SPLIT16): the tile kernel
+# then fetches A_hi, A_lo, W_hi, W_lo once per logical k-block instead of six tiles (0: plain walk over 3K, A/B)
+SPLIT3_LOADS = _os.environ.get("DTLR_SPLIT3_LOADS", "1") != "0"
 
 
 def conv2d_nhwc_supported(x, H, W, C, k, stride):
@@ -481,7 +488,7 @@ def ffn_ln(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
     if x.dtype == torch.float32 and w1.dtype in HALF:
         # split-precision mode: linear1 writes its ReLU output straight as the split operand of linear2 (no fp32 hidden activation in HBM)
         h = gemm(x, w1, b1, relu=1, out_dtype=SPLIT if SPLIT_OUT_FUSED else None)
-        y = gemm(h, w2, b2, residual=x, out_dtype=torch.float32)
+        y = gemm(h, w2, b2, residual=x, out_dtype=torch.float32, split3=True)
         return add_layernorm(y, None, gamma, beta, add2=add2)
     if (FFN_FUSED and x.dtype in HALF and x.shape[1] == 256 and w2.shape[0] == 256 and hid % 128 == 0 and hid <= 2048
             and x.stride(1) == 1 and x.stride(0) % 8 == 0):
