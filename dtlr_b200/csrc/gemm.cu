@@ -76,6 +76,7 @@ struct GemmEpi {
                              // W = [hi | lo | hi] over K = 3 Kl columns (Kl % 64 == 0).  Instead of walking 3 Kl columns (6 tile loads per
                              // logical k-block) the producer loads A_hi, W_hi and A_lo, W_lo once (two pipeline stages) and the issuer
                              // runs hi.hi, hi.lo, lo.hi from them: the same three products with 2/3 of the L2 -> shared-memory traffic
+    int nfast = 0;           // tile kernel: column tiles vary fastest over the persistent CTAs (A tiles shared through L2) instead of row tiles
     int split_out = 0;       // fp32-output tile kernel only: write the result as the 16-bit split operand [hi | hi | lo] ([M, 3N], ldc in
                              // 16-bit elements) that dtlr_split_cast would make of it -- the next split product reads it directly
 };
@@ -266,6 +267,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int num_m = (e.M + GEMM_BM - 1) / GEMM_BM, num_n = (e.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int Kl = e.split3 ? e.K / 3 : 0;                                   // logical K of a split-precision product
+    // tile order.  Default: row tiles fastest (the CTAs of a wave share one weight tile).  nfast: column tiles fastest -- the CTAs of a wave
+    // share their A tiles through L2.  The split-precision products stream a large A (up to 717 MB) beside an fp32 / split output of the same
+    // size; with row tiles fastest every column tile re-read A from DRAM (ncu, profiles/r2_split_gemm_ncu.txt: 1.0 GB read for 0.48 GB of A
+    // at N = 256, 0.69 GB for 0.06 GB at N = 2048 -- the output stream evicts it)
+    const bool nfast = e.nfast != 0;
     const int num_kb = e.split3 ? 2 * (Kl / GEMM_BK) : (e.K + GEMM_BK - 1) / GEMM_BK;   // pipeline steps per tile
 
     if (warp == 0 && lane == 0) {
@@ -294,7 +300,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (elect_one()) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
+                const int m0 = (nfast ? tile / num_n : tile % num_m) * GEMM_BM, n0 = (nfast ? tile % num_n : tile / num_m) * BN;
                 // implicit-GEMM conv: the (image, row, column) of every pixel run of the tile is fixed for the whole K loop and the tap
                 // (kh, kw, channel block) advances by counters -- round 1 recomputed both with ~8 integer divisions per k-step on this
                 // single producer thread, which made the producer the bottleneck of the deep convs (layer4: 0.85 us per k-step against
@@ -449,7 +455,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (!do_ln) {
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = (tile % num_m) * GEMM_BM, n0 = (tile / num_m) * BN;
+            const int m0 = (nfast ? tile / num_n : tile % num_m) * GEMM_BM, n0 = (nfast ? tile % num_n : tile / num_m) * BN;
             const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
             // bias row of this tile -> warp-private shared memory while the MMAs of the tile are still running
             float* my_bias = bias_s + (warp - 2) * HW_COLS - half * HW_COLS;   // indexed by tile column
@@ -1148,6 +1154,7 @@ extern "C" int dtlr_gemm(const void* A, int lda, const void* W, int ldw, const f
     if (out_dtype == DTLR_OP16 ? ws_try<op16_t>(A, lda, W, ldw, e, st, &rc) : ws_try<float>(A, lda, W, ldw, e, st, &rc)) return rc;
     const long long row_tiles_ = (M + GEMM_BM - 1) / GEMM_BM;
     e.split3 = split_in ? 1 : 0;           // the 128- and 64-wide tile kernels below (even stage counts); 256-wide 16-bit tiles walk 3 Kl
+    e.nfast = ((split_in || split_out) && !(g_debug_flags & 134217728)) ? 1 : 0;       // flag 134217728: row tiles fastest as before, A/B
     if (!split_in && out_dtype == DTLR_OP16 && (N % 256) == 0 && (K >= 512 || N >= 1024) && !(g_debug_flags & 8) &&
         (K < 1024 || ((row_tiles_ * (N / 128) + sm_count() - 1) / sm_count()) * 128 * 3 > ((row_tiles_ * (N / 256) + sm_count() - 1) / sm_count()) * 256 * 2)) {
         // 128 x 256 tiles: the A tile is shared by twice as many output columns (less L2 traffic per FLOP) and full-width
