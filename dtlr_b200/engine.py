@@ -187,19 +187,19 @@ class InferenceEngine:
         return ops.gemm(x, w, b, out_dtype=torch.float32, out=buf[:, :N])
 
     @staticmethod
-    def _hidden_dtype(x, w):
+    def _hidden_dtype():
         """out_dtype of a layer whose result only feeds the next contraction: in the split-precision mode (fp32 / split activations against
-        16-bit [hi | lo | hi] weights) the epilogue writes the split operand itself (ops.SPLIT); otherwise the activation dtype"""
+        16-bit [hi | lo | hi] weights) the epilogue writes the split operand itself (ops.SPLIT); otherwise None = the activation dtype"""
         return ops.SPLIT if (InferenceEngine._split_now and ops.SPLIT_OUT_FUSED) else None
 
     _split_now = False       # set per forward: the split-precision mode is running (16-bit tensors between layers are split operands)
 
     @staticmethod
     def _mlp3(x, layers, out_f32_last=True):
-        hd = InferenceEngine._hidden_dtype
+        hd = InferenceEngine._hidden_dtype()
         sp = InferenceEngine._split_now          # (every operand below is then a whole-row split matrix: [hi | hi | lo] x [hi | lo | hi])
-        h = ops.gemm(x, *layers[0], relu=1, out_dtype=hd(x, layers[0][0]))
-        h = ops.gemm(h, *layers[1], relu=1, out_dtype=hd(h, layers[1][0]), split3=sp)
+        h = ops.gemm(x, *layers[0], relu=1, out_dtype=hd)
+        h = ops.gemm(h, *layers[1], relu=1, out_dtype=hd, split3=sp)
         return ops.gemm(h, *layers[2], out_dtype=torch.float32 if (out_f32_last or sp) else None, split3=sp)
 
     @staticmethod
@@ -242,13 +242,11 @@ class InferenceEngine:
                     bmid = ops.gemm(col, *blk["c2"], relu=1, out_dtype=mid_dt)
             else:
                 a = ops.gemm(y, *blk["c1"], relu=1)
-            if split:
-                pass
-            elif ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
-                bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1, stride=s)
-            else:
-                col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
-                bmid = ops.gemm(col, *blk["c2"], relu=1)
+                if ops.conv2d_nhwc_supported(a, Hc, Wc, planes, 3, s):
+                    bmid, Hn, Wn = ops.conv2d_nhwc(a, *blk["c2"], B, Hc, Wc, planes, 3, 1, relu=1, stride=s)
+                else:
+                    col, Hn, Wn = ops.im2col(a, B, Hc, Wc, planes, 3, 3, s, 1, T)
+                    bmid = ops.gemm(col, *blk["c2"], relu=1)
             if blk["ds"] is not None:
                 if s == 1:
                     idt = ops.gemm(y3, *blk["ds"], out_dtype=torch.float32, split3=True) if split else ops.gemm(y, *blk["ds"])
@@ -489,7 +487,7 @@ class InferenceEngine:
             hs_all = torch.empty((n_layers * B * Q, d), dtype=T, device=dev) if shared_heads else None
             for i, lyr in enumerate(P["dec"]):
                 sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
-                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype(sine, P["rph"][0][0])), *P["rph"][1], out_dtype=T, split3=self._split_now)
+                qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype()), *P["rph"][1], out_dtype=T, split3=self._split_now)
                 qk_in = ops.add(tgt, qp)
                 if ops.SPLIT_ATTN16 is not None and d // lyr["heads"] == 32 and Q <= 1024:
                     # split-precision mode: q / k / v leave their projections rounded to 16 bits for the tcgen05 attention core (the
