@@ -214,7 +214,46 @@ def msda_forward_fused(value, shapes_host, lsi_host, n_levels, proj, ref, valid_
     return tdb.msda_core(value.float(), loc, attn, geo["level_hw"]).to(value.dtype).contiguous()
 
 
-def install(monkeypatch):
+# ---- the fused kernels of the 16-bit throughput modes (operands and stored activations rounded to 16 bits, fp32 accumulation)
+def gemm_ln(a, w, bias, residual, gamma, beta, add2=None, eps=1e-5, out=None, out2=None):
+    """dtlr_gemm_ln: y = LN_256(a W^T + bias (+ residual)) [, y2 = y + add2]"""
+    _count("gemm_ln")
+    assert a.dtype in HALF and w.dtype == a.dtype and w.shape[0] == 256
+    z = a.float() @ w.float().t() + bias
+    if residual is not None:
+        z = z + residual.float()
+    y = F.layer_norm(z, (256,), gamma, beta, eps).to(a.dtype)
+    return (y, (y.float() + add2.float()).to(a.dtype)) if add2 is not None else y
+
+
+def ffn_ln_half(x, w1, b1, w2, b2, gamma, beta, eps=1e-5, add2=None):
+    """dtlr_ffn_ln_ws: y = LN(x + W2 relu(W1 x + b1) + b2) [, y2 = y + add2]; the hidden activation is a 16-bit MMA operand in tensor memory"""
+    _count("ffn_fused")
+    assert x.dtype in HALF and x.shape[1] == 256 and w1.shape[0] % 128 == 0
+    h = F.relu(x.float() @ w1.float().t() + b1).to(x.dtype)
+    y = F.layer_norm(h.float() @ w2.float().t() + b2 + x.float(), (256,), gamma, beta, eps).to(x.dtype)
+    return (y, (y.float() + add2.float()).to(x.dtype)) if add2 is not None else y
+
+
+def mlp_head(x, l1, l2, w3_f32, b3, ref=None):
+    """dtlr_mlp_head: 256 -> 256 -> 256 -> 4 box MLP [+ sigmoid(delta + inverse_sigmoid(ref))], fp32 result"""
+    _count("mlp_head")
+    assert x.dtype in HALF and w3_f32.dtype == torch.float32 and w3_f32.shape == (4, 256)
+    h = F.relu(x.float() @ l1[0].float().t() + l1[1]).to(x.dtype)
+    h = F.relu(h.float() @ l2[0].float().t() + l2[1])
+    d = h @ w3_f32.t() + b3
+    return d if ref is None else (d + inverse_sigmoid(ref)).sigmoid()
+
+
+def install(monkeypatch, half=False):
+    if half:
+        monkeypatch.setattr(ops, "gemm_ln", gemm_ln)
+        monkeypatch.setattr(ops, "ffn_ln", ffn_ln_half)
+        monkeypatch.setattr(ops, "mlp_head", mlp_head)
+    _install_common(monkeypatch)
+
+
+def _install_common(monkeypatch):
     """route the engine's leaf launches to the stand-ins above (pytest monkeypatch: undone at the end of the test)"""
     CALLS.clear()
     for name in ("split_cast", "gemm", "im2col", "conv2d_nhwc", "stem_conv", "maxpool3x3s2", "groupnorm_into", "pos_sine_into", "add_layernorm",

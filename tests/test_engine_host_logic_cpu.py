@@ -13,9 +13,9 @@ import engine_ops_double as dbl
 from gpu_common import fixture, rel
 
 
-def _run(model, x, split, force=None):
+def _run(model, x, split, force=None, dtype=torch.float32):
     model.eval()
-    model.compute_dtype = torch.float32
+    model.compute_dtype = dtype
     model.split_precision = split
     model.use_cuda_graph = False
     model.transformer.debug_force_topk = force
@@ -111,3 +111,20 @@ def test_split_weight_pack_and_mode_switch(monkeypatch):
     assert ps["tgt_embed"].dtype == torch.float32 and ps["stem_gemm"] is None
     model.split_precision = False
     assert eng._weight_dtype() == torch.float32
+
+
+@pytest.mark.parametrize("dt,bound", [(torch.float16, 1e-2), (torch.bfloat16, 5e-2)])
+def test_engine_orchestration_throughput_modes(monkeypatch, dt, bound):
+    """the 16-bit modes bench.py's headline runs in: folded 16-bit conv weights, the tensor-core stem (staged im2col x [64, 152] GEMM), the fused
+    FFN / box-head / Linear+LayerNorm launches, 16-bit token buffers -- host logic only, against the fixture within the modes' documented
+    bounds (the stand-ins round operands and stored activations to 16 bits like the kernels)"""
+    dbl.install(monkeypatch, half=True)
+    fx = fixture("dino_A_b2")
+    model = _build(900)
+    out, st = _run(model, synth.synth_images(2, 40, 1024, seed=0), False, force=torch.from_numpy(fx["topk_idx"]).long(), dtype=dt)
+    assert st["memory"].dtype == dt and out["pred_logits"].dtype == torch.float32 and out["pred_boxes"].dtype == torch.float32
+    e_log, e_box = rel(out["pred_logits"], fx["pred_logits"]), rel(out["pred_boxes"], fx["pred_boxes"])
+    assert e_log < bound and e_box < bound, (e_log, e_box)
+    c = dbl.CALLS
+    # 12 fused FFN blocks; box heads: the two-stage proposals + 6 decoder refinements + the batched shared head; 16 implicit 3x3 convs + 3 strided 1x1
+    assert c["ffn_fused"] == 12 and c["mlp_head"] == 8 and c["conv2d_nhwc"] == 19 and "split_cast" not in c and "stem_conv" not in c
