@@ -350,8 +350,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
-                    help="f16 (default) / bf16: 16-bit tensor-core operands + activations, fp32 accumulation; f32: exact parity mode")
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32", "split"],
+                    help="f16 (default) / bf16: 16-bit tensor-core operands + activations, fp32 accumulation; f32: exact SIMT parity mode; "
+                         "split: fp32 activations, 3-term fp16 split products on the tensor cores (the parity mode at 1e-3, DESIGN.md 3.5b)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
@@ -380,8 +381,9 @@ def main():
     dist_util.init("nccl", device)
 
     from dtlr_b200 import _lib, dino, synth
-    dtype = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32}[args.dtype]
+    dtype = {"f16": torch.float16, "bf16": torch.bfloat16, "f32": torch.float32, "split": torch.float32}[args.dtype]
     model = build_ours(device, dtype)
+    model.split_precision = args.dtype == "split"
     B = BATCH_PER_GPU
     host_imgs = synth.synth_images(B, IMG_H, IMG_W, seed=100 + rank).pin_memory()
     dev_imgs = host_imgs.to(device, non_blocking=True)
@@ -535,7 +537,7 @@ def main():
         hbm_view = gemm_hbm_view(gemm_bytes, gemm_ms, n_prof, pk["hbm_gbs"])
     except Exception as e:
         hbm_view = {"error": repr(e)}
-    roofline_gemm = {"kernel": "gemm_ws_tcgen05_kernel + gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions outside the FFN blocks)" if dtype != torch.float32 else "sgemm_kernel (fp32 parity mode)",
+    roofline_gemm = {"kernel": "gemm_ws_tcgen05_kernel + gemm_bf16_tcgen05_kernel (dtlr_gemm: all Linear / 1x1-conv / im2col-conv contractions outside the FFN blocks)" if dtype != torch.float32 else ("gemm_bf16_tcgen05_kernel<.., float> on split operands + dtlr_split_cast (split-precision mode; FLOPs algorithmic, i.e. 1/3 of the tensor-core work)" if args.dtype == "split" else "sgemm_kernel (fp32 parity mode)"),
                      "bound": "tensor", "achieved": round(ach_tf, 2), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(ach_tf / peak_tf, 4), "traffic": None, "peak_kind": pk_kind + " sustained cuBLAS bf16",
                      "launches_timed": n_gemm, "share_of_step": round(gemm_ms / n_prof / ms_step, 3),
@@ -601,7 +603,8 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (independent shards, no collective)" % world,
                        "weights": "random (dtlr_b200.synth, seed 0)",
                        "precision": {"f16": "fp16 operands + activations (kind::f16 tcgen05 at the bf16 rate: GEMMs, convs, FFN block, decoder self-attention; mma.sync in the MSDA gather), fp32 accumulation; measured vs the fp32 oracle at this shape: see tests/test_gpu_engine.py::test_bench_shape_throughput_mode_vs_oracle and DESIGN.md 2.1",
-                                     "bf16": "bf16 operands + activations, fp32 accumulation", "f32": "fp32 SIMT parity mode"}[args.dtype], "outputs": "all reference dict keys (6 decoder layers + interm)",
+                                     "bf16": "bf16 operands + activations, fp32 accumulation", "f32": "fp32 SIMT parity mode",
+                                     "split": "fp32 activations, every Linear / conv a 3-term fp16 split product on tcgen05 (fp32 accumulation), fp16 self-attention core, exact fp32 MSDA core; within 1e-3 of the oracle at this shape (tests/test_gpu_engine.py::test_bench_shape_split_precision_vs_oracle)"}[args.dtype], "outputs": "all reference dict keys (6 decoder layers + interm)",
                        "l2": "no explicit flush: one step streams >1 GB of activations (126 MB L2)",
                        "launch": "one CUDA-graph replay per step" if model.use_cuda_graph else "eager launches"},
             "clocks": clocks,
