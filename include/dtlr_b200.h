@@ -146,7 +146,10 @@ int dtlr_conv2d_nhwc(const void* x, const void* w, const float* bias, const void
                      int C, int Cout, int KH, int KW, int pad, int relu, int out_dtype, void* stream);
 /* The same for stride 1 or 2 (the stride-2 3x3 conv2 and the strided 1x1 downsample of the first Bottleneck of layer2-4): the A tensor
  * map traverses W and H with element stride 2, so no im2col matrix is built.  Hin, Win: INPUT size; output (Hin + 2 pad - KH) / stride
- * + 1 by (Win + 2 pad - KW) / stride + 1, its width subject to the tiling rule above; residual / out [B*Hout*Wout, Cout]. */
+ * + 1 by (Win + 2 pad - KW) / stride + 1, its width subject to the tiling rule above; residual / out [B*Hout*Wout, Cout].
+ * out_dtype: the 16-bit type, or DTLR_F32 (fp32 result and residual), or DTLR_SPLIT16 (out [B*Hout*Wout, 3*Cout] = [hi | hi | lo] of the
+ * fp32 result, Cout % 8 == 0) -- the split-precision mode runs its 3x3 convs here on pixels of 3C channels with per-tap [hi | lo | hi]
+ * weights. */
 int dtlr_conv2d_nhwc_strided(const void* x, const void* w, const float* bias, const void* residual, void* out, int B, int Hin,
                              int Win, int C, int Cout, int KH, int KW, int pad, int stride, int relu, int out_dtype, void* stream);
 /* ResNet stem: conv1 7x7/s2/p3 (3->64) + folded FrozenBatchNorm + ReLU, direct (no im2col): x fp32 NCHW [B,3,H,W],
