@@ -348,8 +348,8 @@ class InferenceEngine:
         B, _, H, W = x.shape
         L.set_flavor(T)               # bf16 / fp16 model: the library built for that 16-bit type (fp32 parity mode: either)
         wd = self._weight_dtype()     # T, or SplitDtype(half) in the split-precision mode (fp32 activations, 3-term 16-bit products)
-        ops.SPLIT_ATTN16 = wd.half if isinstance(wd, SplitDtype) else None
-        InferenceEngine._split_now = isinstance(wd, SplitDtype)
+        split_half = wd.half if isinstance(wd, SplitDtype) else None
+        InferenceEngine._split_now = split_half is not None
         if isinstance(wd, SplitDtype):
             L.set_flavor(wd.half)
         P = self.packed(wd, dev)
@@ -489,11 +489,12 @@ class InferenceEngine:
                 sine = ops.sine_embed(ref, vr, B, Q, nlev, T)
                 qp = ops.gemm(ops.gemm(sine, *P["rph"][0], relu=1, out_dtype=self._hidden_dtype()), *P["rph"][1], out_dtype=T, split3=self._split_now)
                 qk_in = ops.add(tgt, qp)
-                if ops.SPLIT_ATTN16 is not None and d // lyr["heads"] == 32 and Q <= 1024:
+                if split_half is not None and d // lyr["heads"] == 32 and Q <= 1024:
                     # split-precision mode: q / k / v leave their projections rounded to 16 bits for the tcgen05 attention core (the
-                    # contraction the error budget is least sensitive to), its result is widened for the fp32 residual stream
-                    qk = ops.gemm(qk_in, *lyr["qk"], out_dtype=ops.SPLIT_ATTN16)
-                    v = ops.gemm(tgt, *lyr["v"], out_dtype=ops.SPLIT_ATTN16)
+                    # contraction the error budget is least sensitive to: 6e-5 on the logits), its result is widened for the
+                    # fp32 residual stream; other head sizes / longer query sets keep fp32 q / k / v and the exact SIMT kernel
+                    qk = ops.gemm(qk_in, *lyr["qk"], out_dtype=split_half)
+                    v = ops.gemm(tgt, *lyr["v"], out_dtype=split_half)
                     att = ops.cast(ops.mha_self_attention(qk, d, v, None, B, Q, lyr["heads"], d // lyr["heads"]), torch.float32)
                 else:
                     qk = ops.gemm(qk_in, *lyr["qk"])

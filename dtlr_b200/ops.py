@@ -270,17 +270,7 @@ def cast(x, dtype):
 ATTN_IMPL = _os.environ.get("DTLR_ATTN", "tc")
 
 
-# split-precision mode (engine sets it per forward): fp32 q / k / v are rounded to 16 bits for the tcgen05 attention core and the
-# result is widened again -- the contraction the precision budget is least sensitive to (6e-5 on the logits); the
-# exact-fp32 SIMT kernel (2.4 ms per layer at B = 64) stays the path of the plain fp32 mode
-SPLIT_ATTN16 = None
-
-
 def mha_self_attention(qk, k_off, v, attn_mask_u8, B, Q, heads, head_dim):
-    if (v.dtype == torch.float32 and SPLIT_ATTN16 is not None and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024
-            and qk.is_contiguous() and v.is_contiguous()):
-        out16 = mha_self_attention(cast(qk, SPLIT_ATTN16), k_off, cast(v, SPLIT_ATTN16), None, B, Q, heads, head_dim)
-        return cast(out16, torch.float32)
     L.set_flavor(v.dtype)
     out = torch.empty((B * Q, heads * head_dim), dtype=v.dtype, device=v.device)
     if ATTN_IMPL == "tc" and v.dtype in HALF and attn_mask_u8 is None and head_dim == 32 and 0 < Q <= 1024:
