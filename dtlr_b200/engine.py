@@ -1,7 +1,8 @@
 """Fused inference path of the DINO forward: every compute step is a libdtlr_b200 kernel (C ABI, include/dtlr_b200.h).
 
 Layout in HBM (DESIGN.md §data layout): activations are token-major / NHWC matrices [rows, channels] in the compute
-dtype T (bf16 throughput mode, fp32 parity mode); convolutions are (im2col +) GEMM with FrozenBatchNorm folded into
+dtype T (fp16 / bf16 throughput modes, fp32 parity modes: exact SIMT kernels, or -- model.split_precision -- 3-term 16-bit
+split products on the tensor cores, SplitDtype below); convolutions are (im2col +) GEMM with FrozenBatchNorm folded into
 weight and bias; the multi-level feature maps are written by the GroupNorm kernel directly into the flattened
 (B, S, 256) token tensor; sampling locations / attention weights / boxes / scores stay fp32.
 

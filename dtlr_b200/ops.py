@@ -20,7 +20,11 @@ SPLIT = _SplitOut()
 
 def gemm(a, w, bias=None, residual=None, relu=False, out_dtype=None, out=None, split3=False):
     """C = act(a @ w.T + bias) (+ residual); relu: 0/False none, 1/True before the residual add, 2 after it.  a (M,K) row-major (last-dim stride 1, any row pitch), w (N,K),
-    bias fp32 (N) or None, residual (M,N) of the output dtype or None."""
+    bias fp32 (N) or None, residual (M,N) of the output dtype or None.
+    Split-precision products: an fp32 `a` against a 16-bit `w` of 3K columns ([hi | lo | hi], engine._split_w) is split on the
+    fly ([hi | hi | lo], split_cast) and multiplied on the 16-bit tensor-core kernel with an fp32 result; out_dtype=SPLIT stores that result as
+    the split operand (M, 3N) of the next product; split3=True marks 16-bit operands that already ARE whole-row split matrices (the tile kernel
+    then fetches each hi / lo tile once)."""
     L.require_cuda(a, w, bias, residual)
     k_alg = a.shape[1]                     # algorithmic K (the split product runs 3K columns for it)
     if a.dtype == torch.float32 and w.dtype in HALF:
